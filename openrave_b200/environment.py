@@ -1,0 +1,164 @@
+"""Host-side mirror of the slice of OpenRAVE's Environment the collision path touches.
+
+Reference: src/libopenrave-core/environment-core.h — body list in insertion order (`GetBodies`, the
+order pqprave's env loop walks, collisionPQP.h:448), `SetCollisionChecker` -> `InitEnvironment`
+(:1460-1485), `Add` -> `InitKinBody` (:1019,1060), `CheckCollision` overloads routed to the current
+checker (:1491-1572).  This is the harness the tests and bench drive; inside a real OpenRAVE the
+same calls arrive through plugins/cudacollision/.
+"""
+import os
+
+from . import ravemath as rm
+from .kinbody import KinBody, Link, Robot
+
+
+class CollisionReport(object):
+    """CollisionReport subset (include/openrave/collisionchecker.h:138-179): link pairs in the order the
+    checker found them, `minDistance`, option bits."""
+
+    def __init__(self):
+        self.Reset()
+
+    def Reset(self, options=0):
+        self.options = options
+        self.vLinkColliding = []      # [(link1, link2)]; link1 belongs to the queried body
+        self.plink1 = None
+        self.plink2 = None
+        self.minDistance = 1e20
+        self.numCols = 0
+        self.nNumValidCollisions = 0
+
+    def AddLinkCollision(self, link1, link2):
+        """collisionchecker.cpp:577-596 — duplicates are not appended twice."""
+        for i, (a, b) in enumerate(self.vLinkColliding):
+            if a is link1 and b is link2:
+                return i
+        self.vLinkColliding.append((link1, link2))
+        self.nNumValidCollisions = len(self.vLinkColliding)
+        if self.plink1 is None:
+            self.plink1, self.plink2 = link1, link2
+        return len(self.vLinkColliding) - 1
+
+    @property
+    def collisionInfos(self):
+        return [CollisionPairInfo(a, b) for a, b in self.vLinkColliding]
+
+
+class CollisionPairInfo(object):
+    def __init__(self, link1, link2):
+        self.link1, self.link2 = link1, link2
+
+    def ExtractFirstBodyLinkGeomNames(self):
+        return (self.link1.body.name, self.link1.name, '')
+
+    def ExtractSecondBodyLinkGeomNames(self):
+        return (self.link2.body.name, self.link2.name, '')
+
+
+class Environment(object):
+    def __init__(self, data_dirs=None):
+        self.bodies = []
+        self.checker = None
+        self._next_id = 1
+        self.data_dirs = list(data_dirs) if data_dirs else default_data_dirs()
+
+    # ---- loading
+    def Load(self, filename):
+        if filename.endswith(".npz"):
+            from .serialize import load_environment_into
+            load_environment_into(self, filename)
+            return True
+        from .xmlscene import SceneLoader
+        SceneLoader(self.data_dirs).load_environment(self, filename)
+        return True
+
+    def ReadKinBodyURI(self, filename):
+        from .xmlscene import SceneLoader
+        return SceneLoader(self.data_dirs).load_body_file(self, filename, robot=False)
+
+    def ReadRobotURI(self, filename):
+        from .xmlscene import SceneLoader
+        return SceneLoader(self.data_dirs).load_body_file(self, filename, robot=True)
+
+    # ---- bodies
+    def Add(self, body, anonymous=False):
+        names = {b.name for b in self.bodies}
+        if body.name in names:
+            if not anonymous:
+                raise ValueError("body name %r already in the environment" % body.name)
+            k = 1
+            while "%s%d" % (body.name, k) in names:
+                k += 1
+            body.name = "%s%d" % (body.name, k)
+        body.env = self
+        body.env_id = self._next_id
+        self._next_id += 1
+        self.bodies.append(body)
+        body.compute_internal_information()
+        if self.checker is not None:
+            self.checker.InitKinBody(body)
+
+    def Remove(self, body):
+        if body in self.bodies:
+            self.bodies.remove(body)
+            if self.checker is not None:
+                self.checker.RemoveKinBody(body)
+
+    def GetBodies(self):
+        return list(self.bodies)
+
+    def GetRobots(self):
+        return [b for b in self.bodies if b.is_robot]
+
+    def GetKinBody(self, name):
+        for b in self.bodies:
+            if b.name == name:
+                return b
+        return None
+
+    GetRobot = GetKinBody
+
+    # ---- checker
+    def SetCollisionChecker(self, checker):
+        if self.checker is not None:
+            self.checker.DestroyEnvironment()
+        self.checker = checker
+        for b in self.bodies:
+            b._nonadjacent_cache = {}      # _ResetInternalCollisionCache on checker change
+        if checker is not None:
+            checker.env = self
+            checker.InitEnvironment()
+        return True
+
+    def GetCollisionChecker(self):
+        return self.checker
+
+    def CheckCollision(self, a, b=None, report=None):
+        cc = self.checker
+        if cc is None:
+            raise RuntimeError("no collision checker set")
+        if b is None:
+            return cc.CheckCollision(a, report=report)
+        return cc.CheckCollision(a, b, report=report)
+
+    def _body_changed(self, body):
+        if self.checker is not None:
+            self.checker._on_body_changed(body)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def default_data_dirs():
+    """$OPENRAVE_DATA-style search path (plugindatabase / RaveFindLocalFile).  In this image the
+    reference tree provides src/ (data/, robots/) and the extracted models.tgz (models/)."""
+    dirs = []
+    env = os.environ.get("OPENRAVE_DATA", "")
+    dirs += [d for d in env.split(os.pathsep) if d]
+    for d in ("/root/reference/src", os.environ.get("OPENRAVE_B200_MODELS", "/tmp/openrave_models")):
+        if d and os.path.isdir(d):
+            dirs.append(d)
+    return dirs
