@@ -131,6 +131,8 @@ int cc_body_set_attached(cc_scene* s, int body_a, int body_b, int attached);
 /* ---- kinematics of a body, read off a computed KinBody (used by the batched entry only) */
 int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints_in_fk_order,
                            const uint8_t* dof_affects_link /* [ndof][nlinks], KinBody::DoesAffect != 0 */);
+/* KinBody::GetDOFValues(): the values the DOFs that are NOT active in a query keep (robot.cpp:1193-1225) */
+int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof);
 /* KinBody::GetNonAdjacentLinks(0): packed pairs in CompareNonAdjacentFarthest order */
 int cc_body_set_nonadjacent_pairs(cc_scene* s, int body, const int32_t* packed_pairs, int npairs);
 
@@ -173,6 +175,13 @@ int cc_check_poses(cc_query* q, const double* link_transforms8, int n, int flags
                    uint32_t* verdict, int32_t* first_env, int32_t* first_self, uint32_t* pair_mask);
 /* Batched KinBody::SetDOFValues: out [n][nlinks][8] doubles (validation of the 1e-6 m / 1e-6 rad bound). */
 int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_transforms8);
+
+/* Wait for everything enqueued by cc_check_batch_device on this scene's device and report asynchronous
+ * failures (CC_ERR_NOMEM if a traversal overflowed its spill area). */
+int cc_scene_synchronize(cc_scene* s);
+/* Conservative margin of the FP32 triangle test in metres: two triangles closer than this on every
+ * separating-axis candidate count as touching.  0 (default) = the reference's strict test (pqp/PQP.cpp:366-367). */
+int cc_scene_set_tri_epsilon(cc_scene* s, double eps);
 
 /* ---- statistics (PQP_CollideResult::NumBVTests/NumTriTests analogue, pqp/PQP.cpp:489,500) */
 int cc_scene_set_counters(cc_scene* s, int enabled);

@@ -1,0 +1,469 @@
+"""`cudacollision` — the CollisionCheckerBase-shaped front of libcudacollision.so.
+
+This class is the harness twin of the OpenRAVE plugin in plugins/cudacollision/: same method names
+and argument meaning as `CollisionCheckerBase` (include/openrave/collisionchecker.h:186-367) with
+pqprave's semantics (plugins/pqprave/collisionPQP.h), plus the batched entry `CheckCollisionBatch`
+that `DynamicsCollisionConstraint::Check` (src/libopenrave/planningutils.cpp:3405-3526), the RRT
+family (plugins/rplanners/rplanners.h:365,370) and `CacheCollisionChecker` misses
+(plugins/configurationcache/cachechecker.cpp:252) call with N DOF vectors at once.
+
+Every collision verdict comes from the CUDA kernels through the C ABI (include/cudacollision.h).
+There is no CPU fallback: if the shared library or a CUDA device is missing, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import flatten
+from .flatten import cc_joint
+from .kinbody import KinBody, Link
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcudacollision.so")
+
+CO_Distance, CO_UseTolerance, CO_Contacts, CO_RayAnyHit = 1, 2, 4, 8
+CO_ActiveDOFs, CO_AllLinkCollisions, CO_AllGeometryCollisions, CO_AllGeometryContacts, CO_IgnoreCallbacks = \
+    0x10, 0x20, 0x40, 0x80, 0x100
+BATCH_ENV, BATCH_SELF, BATCH_ALL_PAIRS = 1, 2, 4
+
+
+class CudaCollisionError(RuntimeError):
+    pass
+
+
+class cc_query_info(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("ndof_active", "nlinks", "npairs_env", "npairs_self", "npairs_hoisted",
+                                              "mask_words", "total_nodes", "total_tris")]
+
+
+class cc_stats(ctypes.Structure):
+    _fields_ = [("configs", ctypes.c_uint64), ("bv_tests", ctypes.c_uint64), ("tri_tests", ctypes.c_uint64),
+                ("launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double)]
+
+
+EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy", "cc_scene_add_body",
+           "cc_scene_remove_body", "cc_body_set_link_mesh", "cc_body_set_link_enabled", "cc_body_set_link_transforms",
+           "cc_body_set_attached", "cc_body_set_kinematics", "cc_body_set_dof_values", "cc_body_set_nonadjacent_pairs",
+           "cc_scene_commit", "cc_query_create", "cc_query_create_pairs", "cc_query_destroy", "cc_query_get_info",
+           "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
+           "cc_scene_synchronize", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libcudacollision.so and declare the prototypes of include/cudacollision.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise CudaCollisionError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    lib.cc_last_error.restype = ctypes.c_char_p
+    lib.cc_scene_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.cc_scene_destroy.argtypes = [vp]
+    lib.cc_scene_add_body.argtypes = [vp, ctypes.c_char_p, ci, ci, ctypes.POINTER(ci)]
+    lib.cc_scene_remove_body.argtypes = [vp, ci]
+    lib.cc_body_set_link_mesh.argtypes = [vp, ci, ci, ctypes.c_char_p, vp, ci, vp, ci]
+    lib.cc_body_set_link_enabled.argtypes = [vp, ci, vp]
+    lib.cc_body_set_link_transforms.argtypes = [vp, ci, vp]
+    lib.cc_body_set_attached.argtypes = [vp, ci, ci, ci]
+    lib.cc_body_set_kinematics.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.cc_body_set_dof_values.argtypes = [vp, ci, vp, ci]
+    lib.cc_body_set_nonadjacent_pairs.argtypes = [vp, ci, vp, ci]
+    lib.cc_scene_commit.argtypes = [vp]
+    lib.cc_query_create.argtypes = [vp, ci, vp, ci, ci, ctypes.POINTER(vp)]
+    lib.cc_query_create_pairs.argtypes = [vp, ci, vp, ci, ctypes.POINTER(vp)]
+    lib.cc_query_destroy.argtypes = [vp]
+    lib.cc_query_get_info.argtypes = [vp, ctypes.POINTER(cc_query_info)]
+    lib.cc_query_get_pairs.argtypes = [vp, vp]
+    lib.cc_check_batch.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
+    lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+    lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
+    lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
+    lib.cc_scene_synchronize.argtypes = [vp]
+    lib.cc_scene_set_tri_epsilon.argtypes = [vp, cd]
+    lib.cc_scene_set_counters.argtypes = [vp, ci]
+    lib.cc_scene_get_stats.argtypes = [vp, ctypes.POINTER(cc_stats)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class BoundQuery(object):
+    """A cc_query plus its decoded pair table."""
+
+    def __init__(self, checker, handle, body):
+        self.checker = checker
+        self.lib = checker.lib
+        self.handle = handle
+        self.body = body
+        info = cc_query_info()
+        checker._ck(self.lib.cc_query_get_info(handle, ctypes.byref(info)))
+        self.info = info
+        self.npairs = info.npairs_env + info.npairs_self
+        self.pairs = np.zeros((max(self.npairs, 1), 4), dtype=np.int32)
+        checker._ck(self.lib.cc_query_get_pairs(handle, _ptr(self.pairs)))
+        self.pairs = self.pairs[:self.npairs]
+
+    def close(self):
+        if self.handle:
+            self.lib.cc_query_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode_env(self, idx):
+        """first_env indices -> [n,3] {query link, other body id, other link}, -1 rows where idx < 0."""
+        out = np.full((len(idx), 3), -1, dtype=np.int32)
+        ok = idx >= 0
+        out[ok] = self.pairs[idx[ok], 0:3]
+        return out
+
+    def decode_self(self, idx):
+        out = np.full((len(idx), 2), -1, dtype=np.int32)
+        ok = idx >= 0
+        out[ok, 0] = self.pairs[idx[ok], 0]
+        out[ok, 1] = self.pairs[idx[ok], 2]
+        return out
+
+    def check(self, q, flags=BATCH_ENV | BATCH_SELF, want_mask=False):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+        n = q.shape[0]
+        verdict = np.zeros(n, dtype=np.uint32)
+        fe = np.zeros(n, dtype=np.int32)
+        fs = np.zeros(n, dtype=np.int32)
+        mask = np.zeros((n, self.info.mask_words), dtype=np.uint32) if want_mask else None
+        self.checker._ck(self.lib.cc_check_batch(self.handle, _ptr(q), n, flags, _ptr(verdict), _ptr(fe), _ptr(fs), _ptr(mask)))
+        return verdict, fe, fs, mask
+
+    def check_poses(self, T8, flags=BATCH_ENV | BATCH_SELF, want_mask=False):
+        T8 = np.ascontiguousarray(T8, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
+        n = T8.shape[0]
+        verdict = np.zeros(n, dtype=np.uint32)
+        fe = np.zeros(n, dtype=np.int32)
+        fs = np.zeros(n, dtype=np.int32)
+        mask = np.zeros((n, self.info.mask_words), dtype=np.uint32) if want_mask else None
+        self.checker._ck(self.lib.cc_check_poses(self.handle, _ptr(T8), n, flags, _ptr(verdict), _ptr(fe), _ptr(fs), _ptr(mask)))
+        return verdict, fe, fs, mask
+
+    def fk(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+        n = q.shape[0]
+        out = np.zeros((n, self.info.nlinks, 8), dtype=np.float64)
+        self.checker._ck(self.lib.cc_fk_batch(self.handle, _ptr(q), n, _ptr(out)))
+        return out
+
+    def check_device(self, d_q_ptr, n, flags, d_verdict_ptr, d_fe_ptr, d_fs_ptr, d_mask_ptr=0, stream=0):
+        """Raw device-pointer entry (torch tensors' data_ptr()); asynchronous on `stream`."""
+        self.checker._ck(self.lib.cc_check_batch_device(self.handle, d_q_ptr, n, flags, d_verdict_ptr, d_fe_ptr, d_fs_ptr,
+                                                        d_mask_ptr or None, stream or None))
+
+
+class CudaCollisionChecker(object):
+    """RaveCreateCollisionChecker(env, 'cudacollision')."""
+
+    xmlid = "cudacollision"
+
+    def __init__(self, env=None, device=0):
+        self.lib = load_library()
+        self.env = env
+        self.device = device
+        self.scene = None
+        self._ids = {}
+        self._bodies = {}
+        self._dirty = set()
+        self._kin_dirty = set()
+        self._options = 0
+        self._queries = {}
+        self._epoch = 0
+        self._create_scene()
+
+    # ---- plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise CudaCollisionError("cudacollision error %d: %s" % (rc, self.lib.cc_last_error().decode()))
+
+    def _create_scene(self):
+        h = ctypes.c_void_p()
+        self._ck(self.lib.cc_scene_create(self.device, ctypes.byref(h)))
+        self.scene = h
+
+    def __del__(self):
+        try:
+            self.DestroyEnvironment()
+        except Exception:
+            pass
+
+    # ---- CollisionCheckerBase surface (collisionchecker.h:200-237)
+    def SetCollisionOptions(self, options):
+        if options & (CO_Distance | CO_UseTolerance | CO_Contacts):
+            return False   # distance / tolerance / contact points are not provided by this checker yet
+        if options != self._options:
+            self._options = int(options)
+            self._invalidate()
+        return True
+
+    def GetCollisionOptions(self):
+        return self._options
+
+    def SetTolerance(self, tol):
+        return False
+
+    def InitEnvironment(self):
+        self._drop_queries()
+        if self.scene is not None:
+            self.lib.cc_scene_destroy(self.scene)
+            self.scene = None
+        self._create_scene()
+        self._ids, self._bodies, self._dirty, self._kin_dirty = {}, {}, set(), set()
+        for b in self.env.GetBodies():
+            self.InitKinBody(b)
+        return True
+
+    def DestroyEnvironment(self):
+        self._drop_queries()
+        if self.scene is not None:
+            self.lib.cc_scene_destroy(self.scene)
+            self.scene = None
+        self._ids, self._bodies = {}, {}
+
+    def InitKinBody(self, body):
+        if id(body) in self._ids:
+            return True
+        bid = ctypes.c_int(-1)
+        self._ck(self.lib.cc_scene_add_body(self.scene, body.name.encode(), len(body.links), 1 if body.is_robot else 0,
+                                            ctypes.byref(bid)))
+        self._ids[id(body)] = bid.value
+        self._bodies[bid.value] = body
+        for l in body.links:
+            v, i = flatten.link_mesh_arrays(l)
+            self._ck(self.lib.cc_body_set_link_mesh(self.scene, bid.value, l.index, l.name.encode(), _ptr(v), v.shape[0],
+                                                    _ptr(i), i.shape[0]))
+        self._dirty.add(id(body))
+        self._kin_dirty.add(id(body))
+        self._invalidate()
+        return True
+
+    def RemoveKinBody(self, body):
+        bid = self._ids.pop(id(body), None)
+        if bid is not None:
+            self._bodies.pop(bid, None)
+            self._ck(self.lib.cc_scene_remove_body(self.scene, bid))
+            self._invalidate()
+
+    def _on_body_changed(self, body):
+        self._dirty.add(id(body))
+        self._invalidate()
+
+    def _invalidate(self):
+        self._epoch += 1
+        self._drop_queries()
+
+    def _drop_queries(self):
+        for q in self._queries.values():
+            q.close()
+        self._queries = {}
+
+    def _sync(self):
+        for b in self.env.GetBodies():
+            if id(b) not in self._ids:
+                self.InitKinBody(b)
+        for b in self.env.GetBodies():
+            if id(b) in self._dirty:
+                bid = self._ids[id(b)]
+                T = flatten.transforms8(b.GetLinkTransformations())
+                self._ck(self.lib.cc_body_set_link_transforms(self.scene, bid, _ptr(T)))
+                en = np.array([1 if l.enabled else 0 for l in b.links], dtype=np.uint8)
+                self._ck(self.lib.cc_body_set_link_enabled(self.scene, bid, _ptr(en)))
+                if b.GetDOF() > 0 and id(b) not in self._kin_dirty:
+                    cur = np.array(b.GetDOFValues(), dtype=np.float64)
+                    self._ck(self.lib.cc_body_set_dof_values(self.scene, bid, _ptr(cur), b.GetDOF()))
+        self._dirty.clear()
+        self._ck(self.lib.cc_scene_commit(self.scene))
+
+    def _sync_kinematics(self, body, need_pairs=True):
+        bid = self._ids[id(body)]
+        if id(body) in self._kin_dirty:
+            if body.sorted_joints_all:
+                arr, n = flatten.joint_table(body)
+                aff = flatten.affects_table(body)
+                self._ck(self.lib.cc_body_set_kinematics(self.scene, bid, body.GetDOF(), n, ctypes.addressof(arr), _ptr(aff)))
+                cur = np.array(body.GetDOFValues(), dtype=np.float64)
+                if body.GetDOF() > 0:
+                    self._ck(self.lib.cc_body_set_dof_values(self.scene, bid, _ptr(cur), body.GetDOF()))
+            self._kin_dirty.discard(id(body))
+        if need_pairs and len(body.links) > 1:
+            na = np.array(body.GetNonAdjacentLinks(0, checker=self), dtype=np.int32)
+            self._ck(self.lib.cc_body_set_nonadjacent_pairs(self.scene, bid, _ptr(na), int(na.size)))
+        return bid
+
+    # ---- bound queries
+    def bind(self, body, active=None, options=None):
+        """cc_query_create for (body, active DOFs, options); cached until the scene changes."""
+        self._sync()
+        bid = self._sync_kinematics(body)
+        opts = self._options if options is None else options
+        if active is None and body.is_robot and body.active_dofs is not None:
+            active = body.GetActiveDOFIndices()
+        key = (bid, tuple(active) if active is not None else None, opts)
+        q = self._queries.get(key)
+        if q is None:
+            h = ctypes.c_void_p()
+            if active is None:
+                self._ck(self.lib.cc_query_create(self.scene, bid, None, 0, opts, ctypes.byref(h)))
+            else:
+                act = np.array(active, dtype=np.int32)
+                self._ck(self.lib.cc_query_create(self.scene, bid, _ptr(act), len(active), opts, ctypes.byref(h)))
+            q = BoundQuery(self, h, body)
+            self._queries[key] = q
+        return q
+
+    def _bind_pairs(self, body, triples):
+        self._sync()
+        bid = self._sync_kinematics(body, need_pairs=False)
+        tr = np.ascontiguousarray(np.array(triples, dtype=np.int32).reshape(-1, 3))
+        h = ctypes.c_void_p()
+        self._ck(self.lib.cc_query_create_pairs(self.scene, bid, _ptr(tr), tr.shape[0], ctypes.byref(h)))
+        return BoundQuery(self, h, body)
+
+    def _check_link_pairs_at(self, body, transforms, pairs):
+        """CheckCollision(link,link) for many pairs of one body placed at `transforms`
+        (KinBody::GetNonAdjacentLinks' initial-pose probe, kinbody.cpp:5563-5577)."""
+        if not pairs:
+            return []
+        bid = self._ids[id(body)] if id(body) in self._ids else None
+        if bid is None:
+            self.InitKinBody(body)
+            bid = self._ids[id(body)]
+        q = self._bind_pairs(body, [(a, bid, b) for a, b in pairs])
+        try:
+            _, _, _, mask = q.check_poses(flatten.transforms8(transforms)[None], BATCH_SELF | BATCH_ALL_PAIRS, want_mask=True)
+        finally:
+            q.close()
+        return [bool((mask[0, p >> 5] >> (p & 31)) & 1) for p in range(len(pairs))]
+
+    # ---- the batched entry
+    def CheckCollisionBatch(self, robot, q, flags=BATCH_ENV | BATCH_SELF, active=None, all_pairs=False):
+        """N configurations at once.  `q` is [n, nactive] active-DOF values.  Returns a dict:
+        verdict[n] (bit0 env, bit1 self), first_env[n,3] {link, other body id, other link},
+        first_self[n,2] {link i, link j}, and with all_pairs the pair bitmask + the query (for decoding)."""
+        bq = self.bind(robot, active)
+        f = flags | (BATCH_ALL_PAIRS if all_pairs else 0)
+        verdict, fe, fs, mask = bq.check(q, f, want_mask=all_pairs)
+        return dict(verdict=verdict, first_env=bq.decode_env(fe), first_self=bq.decode_self(fs), mask=mask, query=bq,
+                    first_env_index=fe, first_self_index=fs)
+
+    def ForwardKinematicsBatch(self, robot, q, active=None):
+        return self.bind(robot, active).fk(q)
+
+    def body_id(self, body):
+        return self._ids[id(body)]
+
+    def body_from_id(self, bid):
+        return self._bodies[bid]
+
+    def GetStatistics(self):
+        st = cc_stats()
+        self._ck(self.lib.cc_scene_get_stats(self.scene, ctypes.byref(st)))
+        return dict(configs=st.configs, bv_tests=st.bv_tests, tri_tests=st.tri_tests, launches=st.launches,
+                    last_kernel_ms=st.last_kernel_ms)
+
+    def SetCounters(self, enabled):
+        self._ck(self.lib.cc_scene_set_counters(self.scene, 1 if enabled else 0))
+
+    def SetTriangleEpsilon(self, eps):
+        self._ck(self.lib.cc_scene_set_tri_epsilon(self.scene, float(eps)))
+
+    # ---- single-state overloads: the bodies' CURRENT link transforms, no FK (collisionPQP.h:172-329)
+    def CheckCollision(self, a, b=None, report=None):
+        if report is not None:
+            report.Reset(self._options)
+        if isinstance(a, KinBody) and b is None:
+            bq = self.bind(a)
+            T = flatten.transforms8(a.GetLinkTransformations())[None]
+            want_all = report is not None
+            verdict, fe, _, mask = bq.check_poses(T, BATCH_ENV | (BATCH_ALL_PAIRS if want_all else 0), want_mask=want_all)
+            hit = bool(verdict[0] & 1)
+            if hit and report is not None:
+                for p in range(bq.info.npairs_env):
+                    if (mask[0, p >> 5] >> (p & 31)) & 1:
+                        l1, ob, l2, _ = bq.pairs[p]
+                        report.AddLinkCollision(a.links[l1], self._bodies[ob].links[l2])
+                report.minDistance = 0
+            return hit
+        if isinstance(a, KinBody) and isinstance(b, KinBody):
+            triples = [(l1.index, self.body_id(b), l2.index) for l1 in a.links for l2 in b.links]
+            return self._single_pairs(a, triples, report)
+        if isinstance(a, Link) and isinstance(b, Link):
+            if a.body is b.body:
+                hit = self._check_link_pairs_at(a.body, a.body.GetLinkTransformations(),
+                                                [(a.index, b.index)])[0] if a.enabled and b.enabled else False
+                if hit and report is not None:
+                    report.AddLinkCollision(a, b)
+                    report.minDistance = 0
+                return hit
+            self._sync()
+            return self._single_pairs(a.body, [(a.index, self.body_id(b.body), b.index)], report)
+        if isinstance(a, Link) and isinstance(b, KinBody):
+            if b is a.body:
+                return False
+            self._sync()
+            return self._single_pairs(a.body, [(a.index, self.body_id(b), l.index) for l in b.links], report)
+        if isinstance(a, Link) and b is None:
+            self._sync()
+            triples = [(a.index, self.body_id(ob), l.index) for ob in self.env.GetBodies() if ob is not a.body for l in ob.links]
+            return self._single_pairs(a.body, triples, report)
+        raise CudaCollisionError("CheckCollision overload not supported (rays throw in pqprave as well)")
+
+    def _single_pairs(self, body, triples, report):
+        if not triples:
+            return False
+        q = self._bind_pairs(body, triples)
+        try:
+            T = flatten.transforms8(body.GetLinkTransformations())[None]
+            verdict, _, _, mask = q.check_poses(T, BATCH_ENV | BATCH_SELF | BATCH_ALL_PAIRS, want_mask=True)
+            hit = bool(verdict[0])
+            if hit and report is not None:
+                for p in range(q.npairs):
+                    if (mask[0, p >> 5] >> (p & 31)) & 1:
+                        l1, ob, l2, _ = q.pairs[p]
+                        report.AddLinkCollision(body.links[l1], self._bodies[ob].links[l2])
+                report.minDistance = 0
+        finally:
+            q.close()
+        return hit
+
+    def CheckStandaloneSelfCollision(self, body, report=None):
+        """collisionPQP.h:364-386: the body's non-adjacent list in order, first hit wins."""
+        if len(body.links) <= 1:
+            return False
+        if report is not None:
+            report.Reset(self._options)
+        bq = self.bind(body)
+        T = flatten.transforms8(body.GetLinkTransformations())[None]
+        verdict, _, fs, _ = bq.check_poses(T, BATCH_SELF)
+        hit = bool(verdict[0] & 2)
+        if hit and report is not None:
+            l0, l1 = bq.decode_self(fs)[0]
+            report.AddLinkCollision(body.links[l0], body.links[l1])
+            report.minDistance = 0
+        return hit
+
+
+def RaveCreateCollisionChecker(env, name):
+    """Name-based factory like RaveCreateCollisionChecker(env, name): 'cudacollision [device]'."""
+    parts = name.split()
+    if parts and parts[0].lower() == "cudacollision":
+        dev = int(parts[1]) if len(parts) > 1 else 0
+        return CudaCollisionChecker(env, dev)
+    return None

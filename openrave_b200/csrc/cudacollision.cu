@@ -1,0 +1,916 @@
+// cudacollision.cu — host side of libcudacollision.so: the C ABI of include/cudacollision.h.
+//
+// Host responsibilities (all one-off or per-batch, never per-configuration):
+//   * keep the flat scene the OpenRAVE-side plugin pushes in (bodies, link meshes, poses, kinematics);
+//   * build one link-frame AABB BVH per link (cc_scene_commit) and keep nodes/triangles resident in HBM;
+//   * bind a query: lay out the pair table in pqprave's iteration order (collisionPQP.h:432-498, 364-386),
+//     hoist the pairs whose relative pose cannot change with the active DOFs, compile the FK chain program;
+//   * launch ccdev::cc_check_kernel (cc_device.cuh) on the caller's stream.
+// There is NO CPU collision path here: without a CUDA device every query entry point fails with CC_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/cudacollision.h"
+#include "cc_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CC_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(CC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ host scene
+struct HNode { float c[3]; int32_t left; float e[3]; int32_t right; };   // matches the device's 2 x float4
+static_assert(sizeof(HNode) == 32, "node layout");
+
+struct HLink {
+    std::string name;
+    std::vector<double> verts;     // xyz
+    std::vector<int32_t> tris;
+    bool enabled = true;
+    double xf[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    bool dirty = false;            // mesh changed since the last commit
+    std::vector<HNode> nodes;      // local indices
+    std::vector<float> tridata;    // 12 floats per triangle
+    int node_base = -1, tri_base = -1;
+    int ntris() const { return (int)tris.size() / 3; }
+};
+
+struct HBody {
+    std::string name;
+    bool is_robot = false;
+    bool removed = false;
+    std::vector<HLink> links;
+    std::vector<int> attached;
+    int ndof = 0;
+    std::vector<cc_joint> joints;
+    std::vector<uint8_t> affects;      // [ndof][nlinks]
+    std::vector<double> dofvals;
+    std::vector<int32_t> nonadjacent;
+};
+
+const float kBoxInflate = 1e-5f;   // metres added to every half extent (conservative pruning, see cc_device.cuh)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t st = 0)
+    {
+        cudaError_t e = reserve(v.size() ? v.size() : 1);
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+};
+
+}  // namespace
+
+struct cc_scene {
+    int device = 0;
+    int num_sms = 0;
+    std::vector<HBody*> bodies;
+    bool committed = false;
+    DevBuf<float4> d_nodes, d_tris;
+    int total_nodes = 0, total_tris = 0;
+    DevBuf<uint32_t> d_spill;
+    int spill_warps = 0;
+    DevBuf<int32_t> d_counter_err;          // [0] work counter, [1] error flag
+    DevBuf<unsigned long long> d_stats;     // [0] bv, [1] tri
+    bool counters = false;
+    cc_stats stats = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    float tri_eps = 0.0f;
+    ~cc_scene()
+    {
+        for (HBody* b : bodies) delete b;
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ BVH build
+struct Builder {
+    const HLink& L;
+    std::vector<HNode>& nodes;
+    std::vector<int> order;                 // triangle permutation
+    std::vector<double> cen;                // centroids
+    Builder(const HLink& l, std::vector<HNode>& n) : L(l), nodes(n) {}
+
+    void bounds(int first, int count, double mn[3], double mx[3]) const
+    {
+        for (int k = 0; k < 3; ++k) { mn[k] = 1e300; mx[k] = -1e300; }
+        for (int i = first; i < first + count; ++i) {
+            int t = order[i];
+            for (int v = 0; v < 3; ++v) {
+                const double* p = &L.verts[3 * (size_t)L.tris[3 * t + v]];
+                for (int k = 0; k < 3; ++k) { if (p[k] < mn[k]) mn[k] = p[k]; if (p[k] > mx[k]) mx[k] = p[k]; }
+            }
+        }
+    }
+
+    void fill_box(HNode& n, const double mn[3], const double mx[3]) const
+    {
+        for (int k = 0; k < 3; ++k) {
+            double c = 0.5 * (mn[k] + mx[k]);
+            float cf = (float)c;
+            double e = 0.5 * (mx[k] - mn[k]) + fabs(c - (double)cf) + (double)kBoxInflate;
+            float ef = (float)e;
+            if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
+            n.c[k] = cf; n.e[k] = ef;
+        }
+    }
+
+    void build(int node, int first, int count)
+    {
+        double mn[3], mx[3];
+        bounds(first, count, mn, mx);
+        fill_box(nodes[node], mn, mx);
+        if (count == 1) {
+            nodes[node].left = ~order[first];
+            nodes[node].right = -1;
+            return;
+        }
+        // split the centroid bounds at the midpoint of the longest axis; fall back to the median
+        double cmn[3] = {1e300, 1e300, 1e300}, cmx[3] = {-1e300, -1e300, -1e300};
+        for (int i = first; i < first + count; ++i)
+            for (int k = 0; k < 3; ++k) { double c = cen[3 * (size_t)order[i] + k]; if (c < cmn[k]) cmn[k] = c; if (c > cmx[k]) cmx[k] = c; }
+        int ax = 0;
+        if (cmx[1] - cmn[1] > cmx[ax] - cmn[ax]) ax = 1;
+        if (cmx[2] - cmn[2] > cmx[ax] - cmn[ax]) ax = 2;
+        double mid = 0.5 * (cmn[ax] + cmx[ax]);
+        int* b = &order[first];
+        int nleft = (int)(std::partition(b, b + count, [&](int t) { return cen[3 * (size_t)t + ax] < mid; }) - b);
+        if (nleft == 0 || nleft == count) {
+            nleft = count / 2;
+            std::nth_element(b, b + nleft, b + count, [&](int x, int y) {
+                double cx = cen[3 * (size_t)x + ax], cy = cen[3 * (size_t)y + ax];
+                return cx < cy || (cx == cy && x < y);
+            });
+        }
+        int l = (int)nodes.size();
+        nodes.push_back(HNode()); nodes.push_back(HNode());
+        nodes[node].left = l; nodes[node].right = l + 1;
+        build(l, first, nleft);
+        build(l + 1, first + nleft, count - nleft);
+    }
+};
+
+void build_link_bvh(HLink& L)
+{
+    int nt = L.ntris();
+    L.nodes.clear(); L.tridata.clear();
+    if (nt == 0) return;
+    L.nodes.reserve(2 * (size_t)nt);
+    L.nodes.push_back(HNode());
+    Builder B(L, L.nodes);
+    B.order.resize(nt);
+    B.cen.resize(3 * (size_t)nt);
+    for (int t = 0; t < nt; ++t) {
+        B.order[t] = t;
+        for (int k = 0; k < 3; ++k)
+            B.cen[3 * (size_t)t + k] = (L.verts[3 * (size_t)L.tris[3 * t] + k] + L.verts[3 * (size_t)L.tris[3 * t + 1] + k] +
+                                        L.verts[3 * (size_t)L.tris[3 * t + 2] + k]) / 3.0;
+    }
+    B.build(0, 0, nt);
+    L.tridata.resize(12 * (size_t)nt);
+    for (int t = 0; t < nt; ++t)
+        for (int v = 0; v < 3; ++v) {
+            const double* p = &L.verts[3 * (size_t)L.tris[3 * t + v]];
+            float* o = &L.tridata[12 * (size_t)t + 4 * v];
+            o[0] = (float)p[0]; o[1] = (float)p[1]; o[2] = (float)p[2]; o[3] = 0.0f;
+        }
+}
+
+// quaternion pose -> FP32 R|t relative to `center` (matrixFromQuat, geometry.h:779-800)
+void pose_to_rt32(const double* x, const double center[3], float* o)
+{
+    double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+    double il = 2.0 / (q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    double qq1 = il * q1 * q1, qq2 = il * q2 * q2, qq3 = il * q3 * q3;
+    o[0] = (float)(1 - qq2 - qq3);            o[1] = (float)(il * (q1 * q2 - q0 * q3)); o[2] = (float)(il * (q1 * q3 + q0 * q2));
+    o[3] = (float)(il * (q1 * q2 + q0 * q3)); o[4] = (float)(1 - qq1 - qq3);            o[5] = (float)(il * (q2 * q3 - q0 * q1));
+    o[6] = (float)(il * (q1 * q3 - q0 * q2)); o[7] = (float)(il * (q2 * q3 + q0 * q1)); o[8] = (float)(1 - qq1 - qq2);
+    o[9] = (float)(x[4] - center[0]); o[10] = (float)(x[5] - center[1]); o[11] = (float)(x[6] - center[2]);
+}
+
+struct PairList {
+    std::vector<uint32_t> pairs;     // a | slot_b << 16
+    std::vector<int32_t> orig;
+    int nenv = 0;
+    DevBuf<uint32_t> d_pairs;
+    DevBuf<int32_t> d_orig;
+    void add(int a, int slot, int o, bool env) { pairs.push_back((uint32_t)a | ((uint32_t)slot << 16)); orig.push_back(o); if (env) nenv++; }
+    cudaError_t upload()
+    {
+        cudaError_t e = d_pairs.upload(pairs);
+        if (e != cudaSuccess) return e;
+        return d_orig.upload(orig);
+    }
+};
+
+bool body_attached(const HBody& a, int other)
+{
+    return std::find(a.attached.begin(), a.attached.end(), other) != a.attached.end();
+}
+
+}  // namespace
+
+struct cc_query {
+    cc_scene* scene = nullptr;
+    int body = -1;
+    int nq = 0, ncols = 0, nslots = 0;
+    std::vector<int32_t> quads;              // [npairs][4] {query link, other body, other link, class}
+    std::vector<int32_t> pair_slot;          // [npairs] slot of the other link
+    std::vector<uint8_t> pair_live;          // [npairs] 0: can never collide (disabled / no mesh), kept for indexing only
+    int nenv_total = 0, nself_total = 0;
+    PairList full, mainl, hoisted;
+    bool has_fk = false;
+    std::vector<ccdev::FkStep> steps;
+    std::vector<int32_t> level_start;
+    int max_depth = 0;
+    DevBuf<ccdev::FkStep> d_steps;
+    DevBuf<int32_t> d_level_start, d_slot_root;
+    DevBuf<float> d_env_xf;
+    DevBuf<uint32_t> d_hoisted_mask;
+    std::vector<uint32_t> hoisted_mask;
+    int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
+    int mask_words = 1;
+    double base[8];
+    double center[3];
+    std::vector<double> cur_active;          // current values of the active DOFs
+    // staging for the host-buffer API
+    DevBuf<double> d_q, d_fk;
+    DevBuf<uint32_t> d_verdict, d_mask;
+    DevBuf<int32_t> d_fe, d_fs;
+};
+
+namespace {
+
+int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
+           int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st)
+{
+    cc_scene* S = Q->scene;
+    if (n <= 0) return CC_OK;
+    ccdev::Params P;
+    memset(&P, 0, sizeof(P));
+    P.nodes = S->d_nodes.p; P.tris = S->d_tris.p;
+    P.slot_root = Q->d_slot_root.p; P.env_xf = Q->d_env_xf.p;
+    P.pairs = pl.d_pairs.p; P.pair_orig = pl.d_orig.p;
+    P.steps = Q->d_steps.p; P.level_start = Q->d_level_start.p;
+    P.hoisted_mask = use_hoisted ? Q->d_hoisted_mask.p : nullptr;
+    P.nq = Q->nq; P.nslots = Q->nslots; P.npairs_dev = (int)pl.pairs.size(); P.nenv_dev = pl.nenv;
+    P.nenv_total = Q->nenv_total; P.nsteps = (int)Q->steps.size(); P.max_depth = Q->max_depth; P.ncols = Q->ncols;
+    P.hoisted_first_env = use_hoisted ? Q->hoisted_first_env : 0x7fffffff;
+    P.hoisted_first_self = use_hoisted ? Q->hoisted_first_self : 0x7fffffff;
+    P.mask_words = Q->mask_words;
+    P.flags = flags | (S->counters ? ccdev::kFlagCounters : 0);
+    memcpy(P.base, Q->base, sizeof(P.base));
+    memcpy(P.center, Q->center, sizeof(P.center));
+    P.tri_eps = S->tri_eps;
+    P.q = d_q; P.n = n;
+    P.verdict = d_verdict; P.first_env = d_fe; P.first_self = d_fs; P.pair_mask = d_mask; P.fk_out = d_fk;
+    P.work_counter = S->d_counter_err.p; P.err_flag = S->d_counter_err.p + 1;
+    P.stats = S->d_stats.p;
+    P.spill_cap = 4096;
+
+    const size_t smem = ccdev::warp_smem_bytes(P.nq, P.nsteps) * ccdev::kWarpsPerBlock;
+    if (smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "body has too many links/joints for one warp's shared memory");
+    CC_CUDA(cudaFuncSetAttribute(ccdev::cc_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_check_kernel, ccdev::kWarpsPerBlock * 32, smem));
+    if (per_sm < 1) return fail(CC_ERR_CUDA, "kernel does not fit on an SM");
+    int grid = per_sm * S->num_sms;                       // persistent: a whole number of waves
+    int need = (n + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
+    if (grid > need) grid = need;
+    const int warps = grid * ccdev::kWarpsPerBlock;
+    if (warps > S->spill_warps) {
+        CC_CUDA(S->d_spill.reserve((size_t)warps * 3 * P.spill_cap));
+        S->spill_warps = warps;
+    }
+    P.spill = S->d_spill.p;
+    CC_CUDA(cudaMemsetAsync(S->d_counter_err.p, 0, sizeof(int32_t), st));
+    CC_CUDA(cudaEventRecord(S->ev0, st));
+    ccdev::cc_check_kernel<<<grid, ccdev::kWarpsPerBlock * 32, smem, st>>>(P);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaEventRecord(S->ev1, st));
+    S->ev_pending = true;
+    S->stats.launches++;
+    if (!(flags & ccdev::kFlagFkOnly)) S->stats.configs += (uint64_t)n;
+    return CC_OK;
+}
+
+int check_err_flag(cc_scene* S)
+{
+    int32_t h[2] = {0, 0};
+    CC_CUDA(cudaMemcpy(h, S->d_counter_err.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[1]) {
+        cudaMemset(S->d_counter_err.p + 1, 0, sizeof(int32_t));
+        return fail(CC_ERR_NOMEM, "device traversal stack overflowed its spill area");
+    }
+    return CC_OK;
+}
+
+HBody* get_body(cc_scene* s, int body)
+{
+    if (!s || body < 0 || body >= (int)s->bodies.size() || s->bodies[body]->removed) return nullptr;
+    return s->bodies[body];
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* cc_last_error(void) { return g_err.c_str(); }
+int cc_version(void) { return 100; }
+
+int cc_scene_create(int cuda_device, cc_scene** out)
+{
+    if (!out) return fail(CC_ERR_INVALID, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+    if (cuda_device < 0 || cuda_device >= ndev) return fail(CC_ERR_INVALID, "bad device index");
+    CC_CUDA(cudaSetDevice(cuda_device));
+    cc_scene* s = new cc_scene();
+    s->device = cuda_device;
+    cudaDeviceProp prop;
+    CC_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+    s->num_sms = prop.multiProcessorCount;
+    CC_CUDA(s->d_counter_err.reserve(2));
+    CC_CUDA(cudaMemset(s->d_counter_err.p, 0, 2 * sizeof(int32_t)));
+    CC_CUDA(s->d_stats.reserve(2));
+    CC_CUDA(cudaMemset(s->d_stats.p, 0, 2 * sizeof(unsigned long long)));
+    CC_CUDA(cudaEventCreate(&s->ev0));
+    CC_CUDA(cudaEventCreate(&s->ev1));
+    *out = s;
+    return CC_OK;
+}
+
+int cc_scene_destroy(cc_scene* s)
+{
+    if (!s) return CC_OK;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    delete s;
+    return CC_OK;
+}
+
+int cc_scene_add_body(cc_scene* s, const char* name, int nlinks, int is_robot, int* out_body)
+{
+    if (!s || nlinks < 0 || nlinks > 0xffff) return fail(CC_ERR_INVALID, "bad arguments");
+    HBody* b = new HBody();
+    b->name = name ? name : "";
+    b->is_robot = is_robot != 0;
+    b->links.resize(nlinks);
+    s->bodies.push_back(b);
+    int id = (int)s->bodies.size() - 1;
+    b->attached.push_back(id);
+    if (out_body) *out_body = id;
+    return CC_OK;
+}
+
+int cc_scene_remove_body(cc_scene* s, int body)
+{
+    HBody* b = get_body(s, body);
+    if (!b) return fail(CC_ERR_INVALID, "bad body");
+    b->removed = true;
+    for (HLink& l : b->links) { l.verts.clear(); l.tris.clear(); l.nodes.clear(); l.tridata.clear(); }
+    s->committed = false;
+    return CC_OK;
+}
+
+int cc_body_set_link_mesh(cc_scene* s, int body, int link, const char* link_name, const double* v, int nv,
+                          const int32_t* tris, int ntris)
+{
+    HBody* b = get_body(s, body);
+    if (!b || link < 0 || link >= (int)b->links.size()) return fail(CC_ERR_INVALID, "bad body/link");
+    if (nv < 0 || ntris < 0 || (ntris > 0 && (!v || !tris))) return fail(CC_ERR_INVALID, "bad mesh");
+    for (int i = 0; i < 3 * ntris; ++i)
+        if (tris[i] < 0 || tris[i] >= nv) return fail(CC_ERR_INVALID, "triangle index out of range");
+    HLink& L = b->links[link];
+    L.name = link_name ? link_name : "";
+    L.verts.assign(v, v + 3 * (size_t)nv);
+    L.tris.assign(tris, tris + 3 * (size_t)ntris);
+    L.dirty = true;
+    s->committed = false;
+    return CC_OK;
+}
+
+int cc_body_set_link_enabled(cc_scene* s, int body, const uint8_t* enabled)
+{
+    HBody* b = get_body(s, body);
+    if (!b || !enabled) return fail(CC_ERR_INVALID, "bad arguments");
+    for (size_t i = 0; i < b->links.size(); ++i) b->links[i].enabled = enabled[i] != 0;
+    return CC_OK;
+}
+
+int cc_body_set_link_transforms(cc_scene* s, int body, const double* T8)
+{
+    HBody* b = get_body(s, body);
+    if (!b || !T8) return fail(CC_ERR_INVALID, "bad arguments");
+    for (size_t i = 0; i < b->links.size(); ++i) memcpy(b->links[i].xf, T8 + 8 * i, 8 * sizeof(double));
+    return CC_OK;
+}
+
+int cc_body_set_attached(cc_scene* s, int a, int bb, int attached)
+{
+    HBody* A = get_body(s, a); HBody* B = get_body(s, bb);
+    if (!A || !B) return fail(CC_ERR_INVALID, "bad body");
+    for (int pass = 0; pass < 2; ++pass) {
+        HBody* x = pass ? B : A; int o = pass ? a : bb;
+        auto it = std::find(x->attached.begin(), x->attached.end(), o);
+        if (attached && it == x->attached.end()) x->attached.push_back(o);
+        if (!attached && it != x->attached.end() && o != (pass ? bb : a)) x->attached.erase(it);
+    }
+    return CC_OK;
+}
+
+int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints, const uint8_t* affects)
+{
+    HBody* b = get_body(s, body);
+    if (!b || ndof < 0 || njoints < 0 || (njoints > 0 && !joints) || (ndof > 0 && !affects)) return fail(CC_ERR_INVALID, "bad arguments");
+    const int nl = (int)b->links.size();
+    for (int k = 0; k < njoints; ++k) {
+        const cc_joint& j = joints[k];
+        if (j.parent_link < 0 || j.parent_link >= nl || j.child_link < 0 || j.child_link >= nl) return fail(CC_ERR_INVALID, "joint link out of range");
+        if (j.dof_index >= ndof || j.mimic_dof >= ndof) return fail(CC_ERR_INVALID, "joint dof out of range");
+        if (j.type != CC_JOINT_REVOLUTE && j.type != CC_JOINT_PRISMATIC) return fail(CC_ERR_UNSUPPORTED, "only 1-DOF revolute/prismatic joints");
+    }
+    b->ndof = ndof;
+    b->joints.assign(joints, joints + njoints);
+    b->affects.assign(affects, affects + (size_t)ndof * nl);
+    if ((int)b->dofvals.size() != ndof) b->dofvals.assign(ndof, 0.0);
+    return CC_OK;
+}
+
+int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof)
+{
+    HBody* b = get_body(s, body);
+    if (!b || ndof != b->ndof || (ndof > 0 && !values)) return fail(CC_ERR_INVALID, "bad arguments");
+    b->dofvals.assign(values, values + ndof);
+    return CC_OK;
+}
+
+int cc_body_set_nonadjacent_pairs(cc_scene* s, int body, const int32_t* packed, int n)
+{
+    HBody* b = get_body(s, body);
+    if (!b || n < 0 || (n > 0 && !packed)) return fail(CC_ERR_INVALID, "bad arguments");
+    const int nl = (int)b->links.size();
+    for (int i = 0; i < n; ++i) {
+        int l0 = packed[i] & 0xffff, l1 = (packed[i] >> 16) & 0xffff;
+        if (l0 >= nl || l1 >= nl) return fail(CC_ERR_INVALID, "pair link out of range");
+    }
+    b->nonadjacent.assign(packed, packed + n);
+    return CC_OK;
+}
+
+int cc_scene_commit(cc_scene* s)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    if (s->committed) return CC_OK;
+    CC_CUDA(cudaSetDevice(s->device));
+    std::vector<HNode> nodes;
+    std::vector<float> tris;
+    for (HBody* b : s->bodies) {
+        if (b->removed) continue;
+        for (HLink& L : b->links) {
+            if (L.dirty) { build_link_bvh(L); L.dirty = false; }
+            if (L.nodes.empty()) { L.node_base = L.tri_base = -1; continue; }
+            L.node_base = (int)nodes.size();
+            L.tri_base = (int)(tris.size() / 12);
+            for (const HNode& n : L.nodes) {
+                HNode g = n;
+                if (g.left >= 0) { g.left += L.node_base; g.right += L.node_base; }
+                else { g.left = ~((~g.left) + L.tri_base); g.right = -1; }
+                nodes.push_back(g);
+            }
+            tris.insert(tris.end(), L.tridata.begin(), L.tridata.end());
+        }
+    }
+    s->total_nodes = (int)nodes.size();
+    s->total_tris = (int)(tris.size() / 12);
+    CC_CUDA(cudaDeviceSynchronize());    // no query may be in flight while the arrays are replaced
+    CC_CUDA(s->d_nodes.reserve(nodes.size() * 2 + 2));
+    CC_CUDA(s->d_tris.reserve(tris.size() / 4 + 3));
+    if (!nodes.empty()) CC_CUDA(cudaMemcpy(s->d_nodes.p, nodes.data(), nodes.size() * sizeof(HNode), cudaMemcpyHostToDevice));
+    if (!tris.empty()) CC_CUDA(cudaMemcpy(s->d_tris.p, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+    s->committed = true;
+    return CC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- queries
+static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const std::vector<int>& slot_link,
+                        const int32_t* active, int nactive, bool all_dofs_active, bool allow_hoist)
+{
+    cc_scene* S = Q->scene;
+    HBody* B = S->bodies[Q->body];
+    const int nl = Q->nq;
+    // ---- which links move with the active DOFs
+    std::vector<int> col_of_dof(B->ndof, -1);
+    std::vector<int> act;
+    if (all_dofs_active) { for (int d = 0; d < B->ndof; ++d) act.push_back(d); }
+    else act.assign(active, active + nactive);
+    for (size_t c = 0; c < act.size(); ++c) {
+        if (act[c] < 0 || act[c] >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
+        col_of_dof[act[c]] = (int)c;
+    }
+    Q->ncols = (int)act.size();
+    Q->cur_active.resize(act.size());
+    for (size_t c = 0; c < act.size(); ++c) Q->cur_active[c] = B->dofvals[act[c]];
+    auto affects = [&](int d, int l) { return B->affects[(size_t)d * nl + l] != 0; };
+    std::vector<uint8_t> moves(nl, 0);
+    for (int l = 0; l < nl; ++l)
+        for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
+
+    // ---- FK chain program
+    Q->has_fk = true;
+    Q->steps.clear();
+    if (!B->joints.empty()) {
+        std::vector<int> depth(nl, -1);
+        depth[0] = 0;
+        std::vector<int> sdepth(B->joints.size(), 0);
+        for (size_t k = 0; k < B->joints.size(); ++k) {
+            const cc_joint& j = B->joints[k];
+            if (depth[j.parent_link] < 0) return fail(CC_ERR_INVALID, "joints are not listed parent-before-child from link 0");
+            if (depth[j.child_link] >= 0) return fail(CC_ERR_UNSUPPORTED, "closed kinematic loops are not supported");
+            depth[j.child_link] = depth[j.parent_link] + 1;
+            sdepth[k] = depth[j.child_link];
+        }
+        std::vector<int> ord(B->joints.size());
+        for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int)k;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return sdepth[x] < sdepth[y]; });
+        Q->max_depth = 0;
+        for (int k : ord) {
+            const cc_joint& j = B->joints[k];
+            ccdev::FkStep st;
+            memset(&st, 0, sizeof(st));
+            st.type = j.type; st.parent = j.parent_link; st.child = j.child_link;
+            int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+            st.src_col = srcdof >= 0 ? col_of_dof[srcdof] : -1;
+            st.src_const = srcdof >= 0 ? B->dofvals[srcdof] : 0.0;
+            st.flags = (j.is_static ? 1 : 0) | (j.mimic_dof >= 0 ? 2 : 0) | (j.is_circular ? 4 : 0);
+            st.src_lower = j.lower; st.src_upper = j.upper;
+            bool src_circ = j.is_circular != 0;
+            if (j.mimic_dof >= 0) {
+                // limits of the DOF the equation reads
+                bool found = false;
+                for (const cc_joint& o : B->joints)
+                    if (o.dof_index == j.mimic_dof) { st.src_lower = o.lower; st.src_upper = o.upper; src_circ = o.is_circular != 0; found = true; break; }
+                if (!found) return fail(CC_ERR_INVALID, "mimic source DOF has no joint");
+            } else if (srcdof < 0) {
+                // passive, non-mimic joint: value 0 clamped to its own limits (kinbody.cpp:2262-2275)
+                st.src_const = 0.0;
+            }
+            if (src_circ) st.flags |= 8;
+            st.a = j.mimic_a; st.b = j.mimic_b; st.lower = j.lower; st.upper = j.upper;
+            memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
+            Q->steps.push_back(st);
+            if (sdepth[k] > Q->max_depth) Q->max_depth = sdepth[k];
+        }
+        Q->level_start.assign(Q->max_depth + 2, 0);
+        for (int k : ord) Q->level_start[sdepth[k] + 1]++;
+        for (int d = 0; d <= Q->max_depth; ++d) Q->level_start[d + 1] += Q->level_start[d];
+        for (int l = 1; l < nl; ++l)
+            if (depth[l] < 0 && B->links[l].ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
+    } else {
+        Q->max_depth = 0;
+        Q->level_start.assign(2, 0);
+        for (int l = 1; l < nl; ++l)
+            if (B->links[l].ntris() > 0) Q->has_fk = false;
+    }
+    memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
+    Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
+
+    // ---- slots
+    Q->nslots = (int)slot_body.size();
+    std::vector<int32_t> roots(Q->nslots, 0);
+    std::vector<float> envxf((size_t)std::max(1, Q->nslots - nl) * 12, 0.f);
+    for (int sidx = 0; sidx < Q->nslots; ++sidx) {
+        const HLink& L = S->bodies[slot_body[sidx]]->links[slot_link[sidx]];
+        roots[sidx] = L.node_base < 0 ? 0 : L.node_base;
+        if (sidx >= nl) pose_to_rt32(L.xf, Q->center, &envxf[(size_t)(sidx - nl) * 12]);
+    }
+
+    // ---- split the pair list
+    const int np = (int)Q->quads.size() / 4;
+    Q->mask_words = std::max(1, (np + 31) / 32);
+    for (int p = 0; p < np; ++p) {
+        if (!Q->pair_live[p]) continue;
+        const int a = Q->quads[4 * p], cls = Q->quads[4 * p + 3];
+        const int slot = Q->pair_slot[p];
+        Q->full.add(a, slot, p, cls == 0);
+        bool hoist = false;
+        if (allow_hoist && Q->has_fk) {
+            if (cls == 0) hoist = !moves[a];
+            else {
+                const int b = Q->quads[4 * p + 2];
+                hoist = true;
+                for (int d : act) if (affects(d, a) != affects(d, b)) { hoist = false; break; }
+            }
+        }
+        (hoist ? Q->hoisted : Q->mainl).add(a, slot, p, cls == 0);
+    }
+    CC_CUDA(cudaSetDevice(S->device));
+    CC_CUDA(Q->full.upload()); CC_CUDA(Q->mainl.upload()); CC_CUDA(Q->hoisted.upload());
+    CC_CUDA(Q->d_steps.upload(Q->steps));
+    CC_CUDA(Q->d_level_start.upload(Q->level_start));
+    CC_CUDA(Q->d_slot_root.upload(roots));
+    CC_CUDA(Q->d_env_xf.upload(envxf));
+    Q->hoisted_mask.assign(Q->mask_words, 0u);
+    CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
+
+    // ---- evaluate the hoisted pairs once, with the same kernel, at the current DOF values
+    if (!Q->hoisted.pairs.empty()) {
+        CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, Q->cur_active.size())));
+        if (!Q->cur_active.empty())
+            CC_CUDA(cudaMemcpy(Q->d_q.p, Q->cur_active.data(), Q->cur_active.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CC_CUDA(Q->d_mask.reserve(Q->mask_words));
+        int rc = launch(Q, Q->hoisted, false, Q->d_q.p, 1, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS, nullptr, nullptr,
+                        nullptr, Q->d_mask.p, nullptr, 0);
+        if (rc != CC_OK) return rc;
+        CC_CUDA(cudaMemcpy(Q->hoisted_mask.data(), Q->d_mask.p, Q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        rc = check_err_flag(S);
+        if (rc != CC_OK) return rc;
+        S->stats.configs -= 1;
+        for (int p = 0; p < np; ++p)
+            if (Q->hoisted_mask[p >> 5] & (1u << (p & 31))) {
+                if (p < Q->nenv_total) { if (p < Q->hoisted_first_env) Q->hoisted_first_env = p; }
+                else if (p < Q->hoisted_first_self) Q->hoisted_first_self = p;
+            }
+        CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
+        CC_CUDA(cudaDeviceSynchronize());
+    }
+    return CC_OK;
+}
+
+int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out)
+{
+    HBody* B = get_body(s, body);
+    if (!B || !out || nactive < 0 || (nactive > 0 && !active_dofs)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!s->committed) return fail(CC_ERR_STATE, "cc_scene_commit has not been called since the last mesh change");
+    const int nl = (int)B->links.size();
+    const bool all_active = active_dofs == nullptr;
+    std::vector<int> act;
+    if (all_active) for (int d = 0; d < B->ndof; ++d) act.push_back(d);
+    else act.assign(active_dofs, active_dofs + nactive);
+    for (int d : act) if (d < 0 || d >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
+    // _IsActiveLink (collisionPQP.h:710-735)
+    std::vector<uint8_t> active_link(nl, 1);
+    const bool filter = (options & CC_CO_ActiveDOFs) && B->is_robot;
+    if (filter) {
+        for (int l = 0; l < nl; ++l) {
+            active_link[l] = 0;
+            for (int d : act) if (B->affects[(size_t)d * nl + l]) { active_link[l] = 1; break; }
+        }
+    }
+    cc_query* Q = new cc_query();
+    Q->scene = s; Q->body = body; Q->nq = nl;
+    std::vector<int> slot_body(nl, body), slot_link(nl);
+    for (int l = 0; l < nl; ++l) slot_link[l] = l;
+    // env pairs: other bodies in environment order x query link x other link (collisionPQP.h:448-487)
+    for (int ob = 0; ob < (int)s->bodies.size(); ++ob) {
+        HBody* O = s->bodies[ob];
+        if (O->removed || body_attached(*B, ob)) continue;
+        std::vector<int> oslot(O->links.size(), -1);
+        for (int i = 0; i < nl; ++i) {
+            if (!B->links[i].enabled || !active_link[i] || B->links[i].ntris() == 0) continue;
+            for (int j = 0; j < (int)O->links.size(); ++j) {
+                if (!O->links[j].enabled || O->links[j].ntris() == 0) continue;
+                if (oslot[j] < 0) { oslot[j] = (int)slot_body.size(); slot_body.push_back(ob); slot_link.push_back(j); }
+                Q->quads.insert(Q->quads.end(), {i, ob, j, 0});
+                Q->pair_slot.push_back(oslot[j]);
+                Q->pair_live.push_back(1);
+            }
+        }
+    }
+    Q->nenv_total = (int)Q->quads.size() / 4;
+    // self pairs: non-adjacent list, AO_Enabled [| AO_ActiveDOFs] (collisionPQP.h:364-386, robot.cpp:2023-2084)
+    for (int32_t pk : B->nonadjacent) {
+        int l0 = pk & 0xffff, l1 = (pk >> 16) & 0xffff;
+        if (!B->links[l0].enabled || !B->links[l1].enabled) continue;
+        if (filter) {
+            bool any = false;
+            for (int d : act)
+                if ((B->affects[(size_t)d * nl + l0] != 0) != (B->affects[(size_t)d * nl + l1] != 0)) { any = true; break; }
+            if (!any) continue;
+            if (!active_link[l0] || !active_link[l1]) continue;      // DoPQP's _IsActiveLink on both links
+        }
+        if (B->links[l0].ntris() == 0 || B->links[l1].ntris() == 0) continue;
+        Q->quads.insert(Q->quads.end(), {l0, body, l1, 1});
+        Q->pair_slot.push_back(l1);
+        Q->pair_live.push_back(1);
+    }
+    Q->nself_total = (int)Q->quads.size() / 4 - Q->nenv_total;
+    if (slot_body.size() > 0xffff) { delete Q; return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots"); }
+    int rc = finish_query(Q, slot_body, slot_link, active_dofs, nactive, all_active, true);
+    if (rc != CC_OK) { delete Q; return rc; }
+    *out = Q;
+    return CC_OK;
+}
+
+int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out)
+{
+    HBody* B = get_body(s, body);
+    if (!B || !out || ntriples < 0 || (ntriples > 0 && !triples)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!s->committed) return fail(CC_ERR_STATE, "cc_scene_commit has not been called since the last mesh change");
+    const int nl = (int)B->links.size();
+    cc_query* Q = new cc_query();
+    Q->scene = s; Q->body = body; Q->nq = nl;
+    std::vector<int> slot_body(nl, body), slot_link(nl);
+    for (int l = 0; l < nl; ++l) slot_link[l] = l;
+    // env-class pairs first (index space [0, nenv)), then self-class pairs, each in the given order
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int k = 0; k < ntriples; ++k) {
+            int a = triples[3 * k], ob = triples[3 * k + 1], j = triples[3 * k + 2];
+            HBody* O = get_body(s, ob);
+            if (!O || a < 0 || a >= nl || j < 0 || j >= (int)O->links.size()) { delete Q; return fail(CC_ERR_INVALID, "bad pair triple"); }
+            const bool self = ob == body;
+            if ((pass == 0) == self) continue;
+            Q->quads.insert(Q->quads.end(), {a, ob, j, self ? 1 : 0});
+            // DoPQP: disabled links and links without a model never collide (collisionPQP.h:555-566);
+            // such pairs keep their index but are not sent to the device
+            bool live = B->links[a].enabled && O->links[j].enabled && B->links[a].ntris() > 0 && O->links[j].ntris() > 0;
+            int slot = j;
+            if (!self) {
+                slot = -1;
+                for (int sidx = nl; sidx < (int)slot_body.size(); ++sidx)
+                    if (slot_body[sidx] == ob && slot_link[sidx] == j) { slot = sidx; break; }
+                if (slot < 0) { slot = (int)slot_body.size(); slot_body.push_back(ob); slot_link.push_back(j); }
+            }
+            Q->pair_slot.push_back(slot);
+            Q->pair_live.push_back(live ? 1 : 0);
+        }
+        if (pass == 0) Q->nenv_total = (int)Q->quads.size() / 4;
+    }
+    Q->nself_total = (int)Q->quads.size() / 4 - Q->nenv_total;
+    if (slot_body.size() > 0xffff) { delete Q; return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots"); }
+    int rc = finish_query(Q, slot_body, slot_link, nullptr, 0, true, false);
+    if (rc != CC_OK) { delete Q; return rc; }
+    *out = Q;
+    return CC_OK;
+}
+
+int cc_query_destroy(cc_query* q)
+{
+    if (!q) return CC_OK;
+    cudaSetDevice(q->scene->device);
+    cudaDeviceSynchronize();
+    delete q;
+    return CC_OK;
+}
+
+int cc_query_get_info(const cc_query* q, cc_query_info* info)
+{
+    if (!q || !info) return fail(CC_ERR_INVALID, "bad arguments");
+    info->ndof_active = q->ncols;
+    info->nlinks = q->nq;
+    info->npairs_env = q->nenv_total;
+    info->npairs_self = q->nself_total;
+    info->npairs_hoisted = (int)q->hoisted.pairs.size();
+    info->mask_words = q->mask_words;
+    info->total_nodes = q->scene->total_nodes;
+    info->total_tris = q->scene->total_tris;
+    return CC_OK;
+}
+
+int cc_query_get_pairs(const cc_query* q, int32_t* out)
+{
+    if (!q || !out) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->quads.empty()) memcpy(out, q->quads.data(), q->quads.size() * sizeof(int32_t));
+    return CC_OK;
+}
+
+int cc_check_batch_device(cc_query* q, const double* d_q, int n, int flags, uint32_t* d_verdict, int32_t* d_fe,
+                          int32_t* d_fs, uint32_t* d_mask, void* stream)
+{
+    if (!q || n < 0 || (n > 0 && !d_q && q->ncols > 0)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    CC_CUDA(cudaSetDevice(q->scene->device));
+    const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    return launch(q, q->mainl, true, d_q, n, f, d_verdict, d_fe, d_fs, d_mask, nullptr, (cudaStream_t)stream);
+}
+
+static int run_host(cc_query* q, const double* in, size_t in_doubles, int n, int kflags, bool pose_mode,
+                    uint32_t* verdict, int32_t* fe, int32_t* fs, uint32_t* mask, double* fk)
+{
+    cc_scene* S = q->scene;
+    if (n == 0) return CC_OK;
+    CC_CUDA(cudaSetDevice(S->device));
+    CC_CUDA(q->d_q.reserve(std::max<size_t>(1, in_doubles)));
+    if (in_doubles) CC_CUDA(cudaMemcpyAsync(q->d_q.p, in, in_doubles * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (verdict) CC_CUDA(q->d_verdict.reserve(n));
+    if (fe) CC_CUDA(q->d_fe.reserve(n));
+    if (fs) CC_CUDA(q->d_fs.reserve(n));
+    if (mask) CC_CUDA(q->d_mask.reserve((size_t)n * q->mask_words));
+    if (fk) CC_CUDA(q->d_fk.reserve((size_t)n * q->nq * 8));
+    const PairList& pl = pose_mode ? q->full : q->mainl;
+    int rc = launch(q, pl, !pose_mode, q->d_q.p, n, kflags, verdict ? q->d_verdict.p : nullptr, fe ? q->d_fe.p : nullptr,
+                    fs ? q->d_fs.p : nullptr, mask ? q->d_mask.p : nullptr, fk ? q->d_fk.p : nullptr, 0);
+    if (rc != CC_OK) return rc;
+    if (verdict) CC_CUDA(cudaMemcpyAsync(verdict, q->d_verdict.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+    if (fe) CC_CUDA(cudaMemcpyAsync(fe, q->d_fe.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    if (fs) CC_CUDA(cudaMemcpyAsync(fs, q->d_fs.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    if (mask) CC_CUDA(cudaMemcpyAsync(mask, q->d_mask.p, (size_t)n * q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+    if (fk) CC_CUDA(cudaMemcpyAsync(fk, q->d_fk.p, (size_t)n * q->nq * 8 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    CC_CUDA(cudaStreamSynchronize(0));
+    return check_err_flag(S);
+}
+
+int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags, uint32_t* verdict, int32_t* first_env,
+                   int32_t* first_self, uint32_t* pair_mask)
+{
+    if (!q || n < 0 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    return run_host(q, dof_values, (size_t)n * q->ncols, n, f, false, verdict, first_env, first_self, pair_mask, nullptr);
+}
+
+int cc_check_poses(cc_query* q, const double* T8, int n, int flags, uint32_t* verdict, int32_t* first_env,
+                   int32_t* first_self, uint32_t* pair_mask)
+{
+    if (!q || n < 0 || (n > 0 && !T8)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ccdev::kFlagPoseMode;
+    return run_host(q, T8, (size_t)n * q->nq * 8, n, f, true, verdict, first_env, first_self, pair_mask, nullptr);
+}
+
+int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_T8)
+{
+    if (!q || n < 0 || !out_T8 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics");
+    return run_host(q, dof_values, (size_t)n * q->ncols, n, ccdev::kFlagFkOnly, false, nullptr, nullptr, nullptr, nullptr, out_T8);
+}
+
+int cc_scene_synchronize(cc_scene* s)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    CC_CUDA(cudaSetDevice(s->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    return check_err_flag(s);
+}
+
+int cc_scene_set_counters(cc_scene* s, int enabled)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    s->counters = enabled != 0;
+    return CC_OK;
+}
+
+int cc_scene_set_tri_epsilon(cc_scene* s, double eps)
+{
+    if (!s || eps < 0) return fail(CC_ERR_INVALID, "bad arguments");
+    s->tri_eps = (float)eps;
+    return CC_OK;
+}
+
+int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
+{
+    cc_scene* s = const_cast<cc_scene*>(sc);
+    if (!s || !out) return fail(CC_ERR_INVALID, "bad arguments");
+    CC_CUDA(cudaSetDevice(s->device));
+    if (s->ev_pending) {
+        CC_CUDA(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CC_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->stats.last_kernel_ms = ms;
+        s->ev_pending = false;
+    }
+    unsigned long long h[2] = {0, 0};
+    CC_CUDA(cudaMemcpy(h, s->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    s->stats.bv_tests = h[0]; s->stats.tri_tests = h[1];
+    *out = s->stats;
+    return CC_OK;
+}
+
+}  // extern "C"

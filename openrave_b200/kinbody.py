@@ -459,9 +459,15 @@ class KinBody(object):
         nl = len(self.links)
         for i, l in enumerate(self.links):
             l.index = i
+            if not hasattr(l, "raw_t"):
+                l.raw_t = l.t            # pose as parsed (serialize.py stores the pre-FK state)
         for i, j in enumerate(self.joints):
             j.jointindex = i
             j.dofindex = i
+        for j in self.joints + self.passive_joints:
+            if getattr(j, "raw", None) is None:
+                j.raw = dict(l0=j.links[0].index, l1=j.links[1].index, lower=j.lower, upper=j.upper, axis=j.axis,
+                             anchor=j.anchor, tl=j.t_left_nooffset, tr=j.t_right_nooffset, tlo=j.t_left, tro=j.t_right)
         for j in self.passive_joints:
             j.jointindex = -1
             j.dofindex = -1

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Generate the committed scene fixtures from the reference tree (run in the build container only).
+
+  python tools/make_fixtures.py            # writes tests/golden/scenes/*.npz
+
+Reads /root/reference/src/{data,robots} and /root/reference/models.tgz (extracted to a temp dir);
+nothing under /root/reference is copied verbatim — the outputs are the parsed, flattened scenes.
+"""
+import os
+import sys
+import tarfile
+import tempfile
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from openrave_b200.environment import Environment          # noqa: E402
+from openrave_b200.serialize import save_environment        # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "scenes")
+
+
+def extract_models(dst):
+    t = tarfile.open(os.path.join(REF, "models.tgz"), "r:gz")
+    try:
+        for m in t:
+            if m.isfile():
+                t.extract(m, dst)
+    except Exception as e:          # the archive in the snapshot has trailing garbage after the last member
+        print("models.tgz: stopped at", e)
+
+
+def main():
+    tmp = os.environ.get("OPENRAVE_B200_MODELS") or tempfile.mkdtemp(prefix="orave_models_")
+    if not os.path.isdir(os.path.join(tmp, "models")):
+        extract_models(tmp)
+    os.makedirs(OUT, exist_ok=True)
+    for scene in ("lab1", "wamtest1"):
+        env = Environment(data_dirs=[os.path.join(REF, "src"), tmp])
+        try:
+            env.Load("data/%s.env.xml" % scene)
+        except Exception as e:
+            print("skip %s: %s" % (scene, e))
+            continue
+        path = os.path.join(OUT, scene + ".npz")
+        save_environment(env, path)
+        print("%s: %d bodies, %d tris -> %s (%.1f KB)" % (
+            scene, len(env.GetBodies()), sum(l.idx.shape[0] for b in env.GetBodies() for l in b.links), path,
+            os.path.getsize(path) / 1024.0))
+
+
+if __name__ == "__main__":
+    main()
