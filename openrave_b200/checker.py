@@ -275,6 +275,8 @@ class CudaCollisionChecker(object):
         self._queries = {}
 
     def _sync(self):
+        if self.scene is None:
+            self.InitEnvironment()
         for b in self.env.GetBodies():
             if id(b) not in self._ids:
                 self.InitKinBody(b)

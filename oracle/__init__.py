@@ -151,6 +151,8 @@ class OracleChecker(object):
         self.lib.orc_body_set_link_enabled(self.scene, bid, _ptr(en))
 
     def _sync(self):
+        if not self.scene:
+            self.InitEnvironment()
         for b in self.env.GetBodies():
             if id(b) not in self._ids:
                 self.InitKinBody(b)
