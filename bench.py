@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — collision-checked configs/sec (FK + env + self) on B200, one JSON line on rank 0.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3          # the product arm (CUDA, through the C ABI)
+  python bench.py --impl reference --steps 3 --warmup 1   # the reference arm: pqprave's CPU path on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...       # one rank per GPU, scene replicated, configs sharded
+
+A "step" is one pass of the hot path over one batch of synthetic uniform-random DOF vectors
+(RobotConfigurationSampler semantics) of the workload named in `config.workload`.
+
+  value      configs/s with the inputs already resident in HBM (cc_check_batch_device on torch's stream,
+             CUDA events on that stream, L2 flushed between timed steps)
+  e2e        same metric through the host-buffer entry cc_check_batch (pinned host q -> H2D -> kernel -> D2H of
+             verdict + first pairs), i.e. the call an OpenRAVE-side caller makes
+  roofline   ALGORITHMIC bytes (the reference's own NumBVTests/NumTriTests on the same inputs,
+             f32 layout: 2*64 B per BV test, 2*36 B per triangle test, + 8*ndof + 16) / kernel time, against the
+             measured HBM copy bandwidth.  The reference has no broadphase and enumerates all contacts, the
+             kernel culls and stops at the first contact per pair, so `frac` can exceed 1: it measures how much
+             of the reference's work the kernel avoids, not DRAM utilisation (`traffic` is the physical bytes).
+  cpu_baseline  the oracle (reference-PQP-linked when oracle/_ref exists) timed single-threaded on this host
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene fixture, n configs per step per GPU, seed, description)
+    "wam_lab1_100k": ("lab1", 100000, 1,
+                      "Barrett WAM (11 DOF, 18 links, 31.0k tris) in data/lab1.env.xml (14 bodies, 16.5k tris): 100k uniform-random "
+                      "DOF configs, CheckCollision + CheckSelfCollision (BASELINE.json configs[0]; configs[1] PR2 needs the COLLADA "
+                      "reader, SURVEY.md §8f-1)"),
+}
+METRIC = "collision-checked configs/sec (FK+env+self)"
+UNIT = "configs/s"
+
+
+def load_world(workload):
+    from openrave_b200.environment import Environment
+    scene, n, seed, _ = WORKLOADS[workload]
+    env = Environment()
+    env.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
+    robot = env.GetRobots()[0]
+    return env, robot, n, seed
+
+
+def sample(robot, n, seed):
+    lo, hi = robot.GetDOFLimits()
+    lo, hi = np.array(lo), np.array(hi)
+    rng = np.random.default_rng(seed)
+    return lo + rng.random((n, len(lo))) * (hi - lo)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(env, robot, q, budget_s=12.0, kind=None):
+    """Single-thread pqprave-equivalent configs/s on a bounded prefix of the same batch."""
+    import oracle
+    if kind is None:
+        kind = "reference" if oracle.available("reference") else "port"
+    orc = oracle.OracleChecker(env, kind)
+    orc.InitEnvironment()
+    probe = min(200, len(q))
+    secs, _ = orc.time_batch(robot, q[:probe])
+    m = int(min(len(q), max(probe, budget_s / max(secs / probe, 1e-9))))
+    secs, _ = orc.time_batch(robot, q[:m])
+    ref = orc.check_batch(robot, q[:min(m, 2000)])
+    cnt = ref["counters"].astype(np.float64)
+    return {"value": m / secs, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs)}, cnt.mean(axis=0)
+
+
+def run_reference_arm(args):
+    """pqprave's CPU path (FK + all link pairs, PQP_ALL_CONTACTS, no broadphase) on all host cores,
+    one private scene per worker (the reference's clone-per-thread idiom, ormultithreadedplanning.cpp:27-33)."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    workload = args.workload
+    env, robot, n, seed = load_world(workload)
+    ncores = os.cpu_count() or 1
+    workers = max(1, min(ncores, 64))
+    q = sample(robot, n, seed)
+    # bounded sample per step: ~8 s of work per worker, estimated from a probe
+    orc = oracle.OracleChecker(env, kind)
+    orc.InitEnvironment()
+    secs, _ = orc.time_batch(robot, q[:100])
+    per_worker = int(max(50, min(n // workers, 8.0 / (secs / 100))))
+    m = per_worker * workers
+    ctx = mp.get_context("fork")
+
+    def one_step():
+        with ctx.Pool(workers, initializer=_ref_worker_init, initargs=(workload, kind)) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker_run, [(q[i * per_worker:(i + 1) * per_worker],) for i in range(workers)])
+            wall = time.perf_counter() - t0
+        return max(wall, max(res))
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    ms = 1000.0 * sum(times) / len(times)
+    value = m / (ms / 1000.0)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "description": WORKLOADS[workload][3], "configs_per_step": m,
+                       "note": "bounded sample of the %d-config batch, %d worker processes" % (n, workers)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
+                             "sample": "%d configs per step over %d processes (private scene each)" % (m, workers)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+_REF_STATE = {}
+
+
+def _ref_worker_init(workload, kind):
+    import oracle
+    env, robot, _, _ = load_world(workload)
+    orc = oracle.OracleChecker(env, kind)
+    orc.InitEnvironment()
+    orc.time_batch(robot, np.zeros((1, robot.GetDOF())))   # builds models + pair list before the timed region
+    _REF_STATE.update(env=env, robot=robot, orc=orc)
+
+
+def _ref_worker_run(a):
+    secs, _ = _REF_STATE["orc"].time_batch(_REF_STATE["robot"], a[0])
+    return secs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="wam_lab1_100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from openrave_b200.checker import BATCH_ENV, BATCH_SELF, CudaCollisionChecker
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(args.warmup, 3)
+
+    env, robot, n, seed = load_world(args.workload)
+    ndof = robot.GetDOF()
+    cc = CudaCollisionChecker(env, local_rank)
+    env.SetCollisionChecker(cc)
+    bq = cc.bind(robot)
+    flags = BATCH_ENV | BATCH_SELF
+
+    # weak scaling: every rank owns a full batch (its own seed); the scene is replicated per GPU
+    q_host = sample(robot, n, seed + 1000 * rank)
+    q_pinned = torch.from_numpy(q_host).pin_memory()
+    d_q = q_pinned.cuda(non_blocking=True)
+    d_verdict = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_fe = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_fs = torch.zeros(n, dtype=torch.int32, device="cuda")
+    gathered = [torch.zeros(3 * n, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        bq.check_device(d_q.data_ptr(), n, flags, d_verdict.data_ptr(), d_fe.data_ptr(), d_fs.data_ptr(), 0, stream.cuda_stream)
+        if world > 1:   # only the per-config verdicts and first-contact pairs cross NVLink
+            dist.all_gather(gathered, torch.cat([d_verdict, d_fe, d_fs]))
+
+    v_host = np.zeros(n, dtype=np.uint32)
+    fe_host = np.zeros(n, dtype=np.int32)
+    fs_host = np.zeros(n, dtype=np.int32)
+    q_np = q_pinned.numpy()
+
+    def step_e2e():
+        v, fe, fs, _ = bq.check(q_np, flags)
+        return v
+
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # evict q, results and the BVH from L2 between timed steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    ms = sum(ms_steps) / len(ms_steps)
+    kernel_ms = ms
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # end to end through the host-buffer entry
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v_last = step_e2e()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # device-resident and host-buffer paths must agree
+    assert (d_verdict.cpu().numpy().astype(np.uint32) == v_last).all()
+
+    if rank == 0:
+        stats = cc.GetStatistics()
+        value = world * n / (ms / 1000.0)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "configs_per_step_per_gpu": n,
+                           "ndof": ndof, "pairs_env": bq.info.npairs_env, "pairs_self": bq.info.npairs_self,
+                           "pairs_hoisted": bq.info.npairs_hoisted, "bvh_nodes": bq.info.total_nodes, "tris": bq.info.total_tris,
+                           "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
+                           "parallelism": "configs sharded, scene replicated (dp%d)" % world,
+                           "colliding_fraction": float((v_last != 0).mean())},
+                "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * ndof * 8),
+                        "d2h_bytes_per_step": int(n * 12)},
+                "gpu_launches": int(args.steps),
+                "clocks": sampler.summary(),
+                "wall_s_timed_region": t_wall}
+        peak, peak_src = peaks()
+        base = None
+        cnt = None
+        if not args.no_cpu_baseline and world == 1:
+            base, cnt = cpu_baseline(env, robot, q_host)
+            line["cpu_baseline"] = base
+        if cnt is not None:
+            bytes_per_config = cnt[0] * 2 * 64 + cnt[1] * 2 * 36 + 8 * ndof + 16
+            achieved = n * bytes_per_config / (kernel_ms / 1000.0) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            if os.path.isfile(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "traffic": traffic, "peak_source": peak_src,
+                                "algorithmic_bytes_per_config": bytes_per_config,
+                                "ref_bv_tests_per_config": cnt[0], "ref_tri_tests_per_config": cnt[1],
+                                "note": "algorithmic bytes follow the reference's counters (no broadphase, all contacts); frac > 1 "
+                                        "means the kernel avoids that work by culling/any-hit, see profiles/ for physical utilisation"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
