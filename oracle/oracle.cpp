@@ -7,7 +7,7 @@
 // Parity pin: this restatement is checked (tests/test_oracle_vs_ref.py) against the UNMODIFIED vendored PQP
 // compiled from /root/reference/plugins/pqprave/pqp by oracle/Makefile into oracle/_ref/ (identical contact
 // lists and identical NumBVTests/NumTriTests on random poses), and against the reference's own known-answer
-// tests for lab1 (tests/test_golden_lab1.py <- test/test_collision.py:183-251).
+// tests for lab1 (tests/test_oracle_golden.py <- test/test_collision.py:183-251).
 //
 // What is restated, with the reference lines it follows:
 //   Transform algebra            include/openrave/geometry.h:255-262 (normalize4), :430-446 (rotate),
