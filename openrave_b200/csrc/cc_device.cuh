@@ -1,21 +1,22 @@
 // cc_device.cuh — device side of the batched collision checker (sm_100a only).
 //
-// One persistent kernel, `cc_check_kernel`: each WARP owns one configuration at a time (pulled from a
-// global atomic counter) and runs the whole reference pipeline for it without touching HBM in between:
+// Two kernels per chunk of configurations, both hand-written for B200:
 //
-//   1. batched FK       KinBody::SetDOFValues' joint loop (kinbody.cpp:2286-2481) in FP64: lanes build the
-//                       per-joint local transforms (L * J(q) * R) in parallel, then compose level by level
-//                       through shared memory; link poses stay in shared memory (FP32 R|t, base-centred).
-//   2. broadphase       one lane per (query link, other link) pair of the bound pair table: relative pose +
-//                       15-axis SAT of the two root boxes.  Survivors get a "slot" holding their relative pose.
-//   3. traversal        warp-cooperative dual-BVH descent: a LIFO of (nodeA, nodeB, slot) items lives in
-//                       shared memory, every iteration pops up to 32 items (one per lane), tests them and
-//                       pushes children by ballot/popc compaction.  Nodes are 32-byte link-frame AABBs fetched
-//                       as two 16-byte loads; they are served from L2 (the whole scene is a few MB).
-//   4. narrowphase      leaf x leaf -> PQP's 17-axis triangle SAT (pqp/PQP.cpp:350-459) in FP32 on
-//                       p1-shifted coordinates in link A's frame.
-//   5. verdict          first colliding pair in reference order per class (env / self) by warp min-reduction,
-//                       optional complete pair bitmask.
+//   cc_fk_kernel        ONE THREAD per configuration.  The FK chain program is uniform across the warp, so
+//                       KinBody::SetDOFValues' joint loop (kinbody.cpp:2286-2481) runs divergence-free in FP64 with
+//                       the running transform in registers (the chain is walked depth-first; only branch-point
+//                       links are parked in a coalesced SoA scratch).  Every link pose is emitted as FP32 R|t
+//                       (base-centred) plus its world AABB, then the link-AABB x {environment-AABB, link-AABB}
+//                       broadphase runs over the bound pair table in reference order and leaves one candidate bit
+//                       per pair.  Configurations with no candidate get their verdict here; the rest are appended
+//                       to a work queue.
+//   cc_traverse_kernel  persistent, ONE WARP per queued configuration: candidate bits -> dense batches of 32 root
+//                       pairs (relative pose + 15-axis SAT of the root boxes) -> warp-cooperative dual-BVH descent.
+//                       A stack item names the two CHILDREN of the node being split plus the other node, so one pop
+//                       is one 64-byte + one 32-byte fetch and two independent box tests per lane; leaf x leaf hits
+//                       are parked in a triangle queue and tested 32 at a time with PQP's 17-axis triangle SAT
+//                       (pqp/PQP.cpp:350-459) in FP32.  All warp state lives in registers; the stack, the triangle
+//                       queue and the per-pair relative poses live in 5.7 KB of shared memory per warp.
 //
 // Conservative pruning: node boxes are inflated at build time and |R| entries get +1e-6 like
 // OBB_Disjoint.h:67-78, so FP32 rounding can never prune a true contact; the verdict is the OR of the
@@ -27,10 +28,15 @@
 namespace ccdev {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kStackCap = 512;       // items of shared-memory LIFO per warp
-constexpr int kSpillChunk = 256;     // items moved to / from the global spill area at a time
-constexpr int kNumSlots = 64;        // candidate pairs traversed together
+constexpr int kMinBlocksPerSM = 8;   // 32 warps / SM: registers capped at 64 per thread
+constexpr int kFkThreads = 128;
+constexpr int kStackCap = 384;       // items of shared-memory LIFO per warp
+constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
+constexpr int kNumSlots = 32;        // root pairs traversed together
+constexpr int kTriQCap = 96;         // pending leaf x leaf tests (drained 32 at a time)
+constexpr int kCandCap = 64;         // pending candidate pair indices (drained 32 at a time)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNone = 0x7fffffff;
 
 // flags (low bits mirror cc_batch_flags)
 constexpr int kFlagEnv = 1, kFlagSelf = 2, kFlagAllPairs = 4, kFlagPoseMode = 8, kFlagFkOnly = 16, kFlagCounters = 32;
@@ -40,7 +46,9 @@ struct FkStep {                 // one joint of the chain program, 256 bytes
     int32_t parent, child;
     int32_t src_col;            // column of q feeding this joint (own DOF or the mimic source); -1: constant
     int32_t flags;              // bit0 static, bit1 mimic, bit2 own-circular, bit3 source-circular
-    int32_t pad[3];
+    int32_t load_parent;        // -2: parent pose is the running transform, -1: link 0's pose, >=0: parked pose index
+    int32_t save;               // >=0: park this child's pose (a later step branches off it)
+    int32_t pad;
     double src_const;           // value when src_col < 0
     double src_lower, src_upper;// limits of the source DOF (KinBody::SetDOFValues clamps DOF values first)
     double a, b;                // mimic: value = a*src + b
@@ -50,6 +58,7 @@ struct FkStep {                 // one joint of the chain program, 256 bytes
     double axis[4];
     double pad2;
 };
+static_assert(sizeof(FkStep) == 256, "FkStep layout");
 
 struct Params {
     // scene (device pointers)
@@ -57,18 +66,19 @@ struct Params {
     const float4* tris;         // 3 x float4 per triangle (link frame)
     const int32_t* slot_root;   // root node of every link slot
     const float* env_xf;        // [nslots - nq][12] FP32 R(9, row major)|t(3), base-centred
+    const float* env_aabb;      // [nslots - nq][8]  world AABB {cx cy cz ex ey ez 0 0}, base-centred
+    const float* link_box;      // [nq][8] link-frame root box {cx cy cz ex ey ez has_geometry 0}
     // query
     const uint32_t* pairs;      // device pair list: a | (b << 16), b = slot index
     const int32_t* pair_orig;   // original (reference-order) index of each device pair
-    const FkStep* steps;
-    const int32_t* level_start; // [max_depth + 2] offsets into steps (steps are sorted by depth)
+    const FkStep* steps;        // depth-first order
     const uint32_t* hoisted_mask;
-    int32_t nq, nslots, npairs_dev, nenv_dev, nenv_total, nsteps, max_depth, ncols;
+    int32_t nq, nslots, npairs_dev, nenv_dev, nenv_total, nsteps, ncols, cwords;
     int32_t hoisted_first_env, hoisted_first_self, mask_words, flags;
     double base[8];             // pose of link 0 (kept, kinbody.cpp:2281)
     double center[3];           // subtracted from every translation before the FP32 conversion
     float tri_eps;              // conservative margin of the triangle test (metres), 0 = reference's strict test
-    // io
+    // io (already offset to this chunk)
     const double* q;            // [n][ncols]   (or [n][nq][8] in pose mode)
     int32_t n;
     uint32_t* verdict;
@@ -76,12 +86,18 @@ struct Params {
     int32_t* first_self;
     uint32_t* pair_mask;
     double* fk_out;             // [n][nq][8] or NULL
-    // runtime
-    int32_t* work_counter;
+    // per-chunk scratch
+    float* xf32;                // [cap][nq][12]
+    float* aabb;                // [nq][6][cap]
+    double* fksave;             // [nsave][7][cap]
+    uint32_t* cand;             // [cap][cwords]
+    int32_t* queue;             // [cap]
+    int32_t* counters;          // [0] queue length, [1] traversal work counter
+    int32_t* err_flag;          // set when a traversal overflows its spill area
+    int32_t cap;
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
-    uint32_t* spill;            // [num_warps][3][spill_cap]
+    uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
-    int32_t* err_flag;
 };
 
 // ------------------------------------------------------------------------------------------------ FP64 SE(3)
@@ -126,10 +142,6 @@ __device__ __forceinline__ Xf xf_load(const double* p)
     Xf r; r.q0 = p[0]; r.q1 = p[1]; r.q2 = p[2]; r.q3 = p[3]; r.tx = p[4]; r.ty = p[5]; r.tz = p[6];
     return r;
 }
-__device__ __forceinline__ void xf_store(double* p, const Xf& r)
-{
-    p[0] = r.q0; p[1] = r.q1; p[2] = r.q2; p[3] = r.q3; p[4] = r.tx; p[5] = r.ty; p[6] = r.tz; p[7] = 0.0;
-}
 
 // ------------------------------------------------------------------------------------------------ FP32 tests
 // 15-axis SAT of box A {ca, ea} (identity frame) against box B {cb, eb} placed by (R, t): x_A = R x_B + t.
@@ -146,24 +158,25 @@ __device__ __forceinline__ bool box_overlap(const float* __restrict__ R, const f
     float f10 = fabsf(R[3]) + reps, f11 = fabsf(R[4]) + reps, f12 = fabsf(R[5]) + reps;
     float f20 = fabsf(R[6]) + reps, f21 = fabsf(R[7]) + reps, f22 = fabsf(R[8]) + reps;
     // A's face axes
-    if (fabsf(T0) > eax + ebx * f00 + eby * f01 + ebz * f02) return false;
-    if (fabsf(T1) > eay + ebx * f10 + eby * f11 + ebz * f12) return false;
-    if (fabsf(T2) > eaz + ebx * f20 + eby * f21 + ebz * f22) return false;
+    bool sep = fabsf(T0) > eax + ebx * f00 + eby * f01 + ebz * f02;
+    sep |= fabsf(T1) > eay + ebx * f10 + eby * f11 + ebz * f12;
+    sep |= fabsf(T2) > eaz + ebx * f20 + eby * f21 + ebz * f22;
     // B's face axes
-    if (fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) > ebx + eax * f00 + eay * f10 + eaz * f20) return false;
-    if (fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) > eby + eax * f01 + eay * f11 + eaz * f21) return false;
-    if (fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) > ebz + eax * f02 + eay * f12 + eaz * f22) return false;
+    sep |= fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) > ebx + eax * f00 + eay * f10 + eaz * f20;
+    sep |= fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) > eby + eax * f01 + eay * f11 + eaz * f21;
+    sep |= fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) > ebz + eax * f02 + eay * f12 + eaz * f22;
+    if (sep) return false;
     // edge x edge
-    if (fabsf(T2 * R[3] - T1 * R[6]) > eay * f20 + eaz * f10 + eby * f02 + ebz * f01) return false;
-    if (fabsf(T2 * R[4] - T1 * R[7]) > eay * f21 + eaz * f11 + ebx * f02 + ebz * f00) return false;
-    if (fabsf(T2 * R[5] - T1 * R[8]) > eay * f22 + eaz * f12 + ebx * f01 + eby * f00) return false;
-    if (fabsf(T0 * R[6] - T2 * R[0]) > eax * f20 + eaz * f00 + eby * f12 + ebz * f11) return false;
-    if (fabsf(T0 * R[7] - T2 * R[1]) > eax * f21 + eaz * f01 + ebx * f12 + ebz * f10) return false;
-    if (fabsf(T0 * R[8] - T2 * R[2]) > eax * f22 + eaz * f02 + ebx * f11 + eby * f10) return false;
-    if (fabsf(T1 * R[0] - T0 * R[3]) > eax * f10 + eay * f00 + eby * f22 + ebz * f21) return false;
-    if (fabsf(T1 * R[1] - T0 * R[4]) > eax * f11 + eay * f01 + ebx * f22 + ebz * f20) return false;
-    if (fabsf(T1 * R[2] - T0 * R[5]) > eax * f12 + eay * f02 + ebx * f21 + eby * f20) return false;
-    return true;
+    sep |= fabsf(T2 * R[3] - T1 * R[6]) > eay * f20 + eaz * f10 + eby * f02 + ebz * f01;
+    sep |= fabsf(T2 * R[4] - T1 * R[7]) > eay * f21 + eaz * f11 + ebx * f02 + ebz * f00;
+    sep |= fabsf(T2 * R[5] - T1 * R[8]) > eay * f22 + eaz * f12 + ebx * f01 + eby * f00;
+    sep |= fabsf(T0 * R[6] - T2 * R[0]) > eax * f20 + eaz * f00 + eby * f12 + ebz * f11;
+    sep |= fabsf(T0 * R[7] - T2 * R[1]) > eax * f21 + eaz * f01 + ebx * f12 + ebz * f10;
+    sep |= fabsf(T0 * R[8] - T2 * R[2]) > eax * f22 + eaz * f02 + ebx * f11 + eby * f10;
+    sep |= fabsf(T1 * R[0] - T0 * R[3]) > eax * f10 + eay * f00 + eby * f22 + ebz * f21;
+    sep |= fabsf(T1 * R[1] - T0 * R[4]) > eax * f11 + eay * f01 + ebx * f22 + ebz * f20;
+    sep |= fabsf(T1 * R[2] - T0 * R[5]) > eax * f12 + eay * f02 + ebx * f21 + eby * f20;
+    return !sep;
 }
 
 struct V3 { float x, y, z; };
@@ -216,35 +229,6 @@ __device__ __forceinline__ bool tri_contact(V3 P0, V3 P1, V3 P2, V3 Q0, V3 Q1, V
     return true;
 }
 
-// ------------------------------------------------------------------------------------------------ shared memory
-// Per-warp layout (bytes):  xf32 [nq*48] | slot_rt [kNumSlots*48] | slot_pair [kNumSlots*4] | slot_hit [16]
-//                           | scratch: max(stack 3*kStackCap*4, FK (nq + nsteps)*64)
-__host__ __device__ inline size_t warp_smem_bytes(int nq, int nsteps)
-{
-    size_t fk = (size_t)(nq + nsteps) * 64;
-    size_t st = (size_t)3 * kStackCap * 4;
-    size_t scratch = fk > st ? fk : st;
-    size_t b = (size_t)nq * 48 + (size_t)kNumSlots * 48 + (size_t)kNumSlots * 4 + 16 + scratch;
-    return (b + 15) & ~(size_t)15;
-}
-
-struct WarpState {
-    float* xf32;          // [nq][12]
-    float* slot_rt;       // [kNumSlots][12]
-    int32_t* slot_pair;   // [kNumSlots] original pair index
-    uint32_t* slot_hit;   // [2]
-    uint32_t* st_a;       // [kStackCap]
-    uint32_t* st_b;
-    uint32_t* st_s;
-    double* fk_xf;        // [nq][8]     (aliases the stack)
-    double* fk_m;         // [nsteps][8]
-    uint32_t* spill;      // global [3][spill_cap]
-    int sp;
-    int spill_count;
-    int best_env, best_self;
-    unsigned long long n_bv, n_tri;
-};
-
 __device__ __forceinline__ void relative_pose(const float* A, const float* B, float* R, float* t)
 {
     // x_A = Ra^T (Rb x_B + tb - ta)
@@ -259,354 +243,500 @@ __device__ __forceinline__ void relative_pose(const float* A, const float* B, fl
     t[2] = A[2] * dx + A[5] * dy + A[8] * dz;
 }
 
-// Move the oldest kSpillChunk items to global memory and slide the rest down.
-__device__ __noinline__ void stack_spill(const Params& P, WarpState& w, int lane)
+// ================================================================================================ kernel 1: FK + broadphase
+__host__ __device__ inline size_t fk_smem_bytes(int nq, int nsteps, int nenv)
 {
-    if (w.spill_count + kSpillChunk > P.spill_cap) {
-        if (lane == 0) atomicExch(P.err_flag, 1);
-        w.sp = 0;               // give up on this configuration; the host reports the error
-        __syncwarp();
-        return;
-    }
-    uint32_t* ga = w.spill + w.spill_count;
-    uint32_t* gb = ga + P.spill_cap;
-    uint32_t* gs = gb + P.spill_cap;
-    for (int i = lane; i < kSpillChunk; i += 32) { ga[i] = w.st_a[i]; gb[i] = w.st_b[i]; gs[i] = w.st_s[i]; }
-    w.spill_count += kSpillChunk;
-    int rest = w.sp - kSpillChunk;
-    __syncwarp();
-    for (int base = 0; base < rest; base += 32) {
-        int i = base + lane;
-        uint32_t a = 0, b = 0, s = 0;
-        if (i < rest) { a = w.st_a[kSpillChunk + i]; b = w.st_b[kSpillChunk + i]; s = w.st_s[kSpillChunk + i]; }
-        __syncwarp();
-        if (i < rest) { w.st_a[i] = a; w.st_b[i] = b; w.st_s[i] = s; }
-        __syncwarp();
-    }
-    w.sp = rest;
+    return (size_t)nsteps * sizeof(FkStep) + (size_t)nq * 32 + (size_t)nenv * 32;
 }
 
-__device__ __noinline__ void stack_refill(const Params& P, WarpState& w, int lane)
+// Emit one link pose: optional FP64 copy-out, FP32 R|t (matrixFromQuat, geometry.h:779-800) and the world AABB
+// of the link's root box.
+__device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbox, int c, int l, const Xf& T)
 {
-    int m = w.spill_count < kSpillChunk ? w.spill_count : kSpillChunk;
-    const uint32_t* ga = w.spill + (w.spill_count - m);
-    const uint32_t* gb = ga + P.spill_cap;
-    const uint32_t* gs = gb + P.spill_cap;
-    for (int i = lane; i < m; i += 32) { w.st_a[i] = ga[i]; w.st_b[i] = gb[i]; w.st_s[i] = gs[i]; }
-    w.spill_count -= m;
-    w.sp = m;
-    __syncwarp();
+    if (P.fk_out) {
+        double* dst = P.fk_out + ((size_t)c * P.nq + l) * 8;
+        dst[0] = T.q0; dst[1] = T.q1; dst[2] = T.q2; dst[3] = T.q3; dst[4] = T.tx; dst[5] = T.ty; dst[6] = T.tz; dst[7] = 0.0;
+    }
+    if (P.flags & kFlagFkOnly) return;
+    const double il = 2.0 / (T.q0 * T.q0 + T.q1 * T.q1 + T.q2 * T.q2 + T.q3 * T.q3);
+    const double qq1 = il * T.q1 * T.q1, qq2 = il * T.q2 * T.q2, qq3 = il * T.q3 * T.q3;
+    float R[9], t[3];
+    R[0] = (float)(1 - qq2 - qq3);                      R[1] = (float)(il * (T.q1 * T.q2 - T.q0 * T.q3)); R[2] = (float)(il * (T.q1 * T.q3 + T.q0 * T.q2));
+    R[3] = (float)(il * (T.q1 * T.q2 + T.q0 * T.q3));   R[4] = (float)(1 - qq1 - qq3);                    R[5] = (float)(il * (T.q2 * T.q3 - T.q0 * T.q1));
+    R[6] = (float)(il * (T.q1 * T.q3 - T.q0 * T.q2));   R[7] = (float)(il * (T.q2 * T.q3 + T.q0 * T.q1)); R[8] = (float)(1 - qq1 - qq2);
+    t[0] = (float)(T.tx - P.center[0]); t[1] = (float)(T.ty - P.center[1]); t[2] = (float)(T.tz - P.center[2]);
+    float4* dst = (float4*)(P.xf32 + ((size_t)c * P.nq + l) * 12);
+    dst[0] = make_float4(R[0], R[1], R[2], R[3]);
+    dst[1] = make_float4(R[4], R[5], R[6], R[7]);
+    dst[2] = make_float4(R[8], t[0], t[1], t[2]);
+    const float* lb = s_linkbox + 8 * l;
+    if (lb[6] != 0.f) {
+        const float reps = 1e-6f;
+        const float cx = lb[0], cy = lb[1], cz = lb[2], ex = lb[3], ey = lb[4], ez = lb[5];
+        float* ab = P.aabb + (size_t)l * 6 * P.cap + c;
+        const size_t cs = (size_t)P.cap;
+        ab[0] = fmaf(R[0], cx, fmaf(R[1], cy, fmaf(R[2], cz, t[0])));
+        ab[cs] = fmaf(R[3], cx, fmaf(R[4], cy, fmaf(R[5], cz, t[1])));
+        ab[2 * cs] = fmaf(R[6], cx, fmaf(R[7], cy, fmaf(R[8], cz, t[2])));
+        ab[3 * cs] = (fabsf(R[0]) + reps) * ex + (fabsf(R[1]) + reps) * ey + (fabsf(R[2]) + reps) * ez;
+        ab[4 * cs] = (fabsf(R[3]) + reps) * ex + (fabsf(R[4]) + reps) * ey + (fabsf(R[5]) + reps) * ez;
+        ab[5 * cs] = (fabsf(R[6]) + reps) * ex + (fabsf(R[7]) + reps) * ey + (fabsf(R[8]) + reps) * ez;
+    }
 }
 
-// Drain the item stack: the warp-cooperative dual-tree descent + triangle tests.
-__device__ __forceinline__ void traverse(const Params& P, WarpState& w, int lane)
+// L * J(value) * R of one joint (kinbody.cpp:2404-2478); the value rules follow kinbody.cpp:2149-2224, 2308-2386.
+__device__ __forceinline__ Xf joint_transform(const FkStep& st, const double* __restrict__ qrow)
 {
-    const bool all_pairs = (P.flags & kFlagAllPairs) != 0;
-    const float eps2 = P.tri_eps * P.tri_eps;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (;;) {
-        if (w.sp == 0) {
-            if (w.spill_count > 0) stack_refill(P, w, lane); else break;
+    Xf L = xf_load(st.L);
+    if (st.flags & 1) return L;                      // static joint: right already folded (kinbodyjoint.cpp:1527-1551)
+    double v = st.src_col >= 0 ? qrow[st.src_col] : st.src_const;
+    if (!(st.flags & 8)) {                           // SetDOFValues clamps non-circular DOFs
+        if (v < st.src_lower) v = st.src_lower; else if (v > st.src_upper) v = st.src_upper;
+    }
+    if (st.flags & 2) {                              // mimic
+        const double ev = st.a * v + st.b;
+        v = ev;
+        if (!(st.flags & 4)) {
+            if (ev < st.lower) { if (ev >= st.lower - 1e-7) v = st.lower; else if (ev < st.lower - 5e-4) v = st.lower; }
+            else if (ev > st.upper) { if (ev <= st.upper + 1e-7) v = st.upper; else if (ev > st.upper + 5e-4) v = st.upper; }
         }
-        const int n = w.sp < 32 ? w.sp : 32;
-        bool valid = lane < n;
-        uint32_t a = 0, b = 0, s = 0;
-        if (valid) { int idx = w.sp - 1 - lane; a = w.st_a[idx]; b = w.st_b[idx]; s = w.st_s[idx]; }
-        w.sp -= n;
-        __syncwarp();
-        int pidx = 0;
-        if (valid) {
-            pidx = w.slot_pair[s];
-            bool dead = (w.slot_hit[s >> 5] >> (s & 31)) & 1u;
-            if (!all_pairs) dead |= (pidx < P.nenv_total) ? (pidx > w.best_env) : (pidx > w.best_self);
-            valid = !dead;
+    }
+    Xf J; J.q0 = 1; J.q1 = J.q2 = J.q3 = 0; J.tx = J.ty = J.tz = 0;
+    if (st.type == 1) {
+        // quatFromAxisAngle (geometry.h:673-682)
+        const double len = sqrt(st.axis[0] * st.axis[0] + st.axis[1] * st.axis[1] + st.axis[2] * st.axis[2]);
+        if (len != 0) {
+            double sn, cs; sincos(v * 0.5, &sn, &cs);
+            sn /= len;
+            J.q0 = cs; J.q1 = st.axis[0] * sn; J.q2 = st.axis[1] * sn; J.q3 = st.axis[2] * sn;
         }
-        bool push = false, hit = false;
-        uint32_t c0a = 0, c0b = 0, c1a = 0, c1b = 0;
-        if (valid) {
-            const float4 a0 = __ldg(&P.nodes[2 * a]), a1 = __ldg(&P.nodes[2 * a + 1]);
-            const float4 b0 = __ldg(&P.nodes[2 * b]), b1 = __ldg(&P.nodes[2 * b + 1]);
-            const float* rt = w.slot_rt + 12 * s;
-            float R[9], t[3];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) R[k] = rt[k];
-            t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-            if (P.flags & kFlagCounters) w.n_bv++;
-            if (box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z)) {
-                const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
-                if (la < 0 && lb < 0) {
-                    if (P.flags & kFlagCounters) w.n_tri++;
-                    const float4* ta = P.tris + 3 * (size_t)(~la);
-                    const float4* tb = P.tris + 3 * (size_t)(~lb);
-                    const float4 p0 = __ldg(ta), p1 = __ldg(ta + 1), p2 = __ldg(ta + 2);
-                    const float4 u0 = __ldg(tb), u1 = __ldg(tb + 1), u2 = __ldg(tb + 2);
-                    V3 Q0 = v3(fmaf(R[0], u0.x, fmaf(R[1], u0.y, fmaf(R[2], u0.z, t[0]))),
-                               fmaf(R[3], u0.x, fmaf(R[4], u0.y, fmaf(R[5], u0.z, t[1]))),
-                               fmaf(R[6], u0.x, fmaf(R[7], u0.y, fmaf(R[8], u0.z, t[2]))));
-                    V3 Q1 = v3(fmaf(R[0], u1.x, fmaf(R[1], u1.y, fmaf(R[2], u1.z, t[0]))),
-                               fmaf(R[3], u1.x, fmaf(R[4], u1.y, fmaf(R[5], u1.z, t[1]))),
-                               fmaf(R[6], u1.x, fmaf(R[7], u1.y, fmaf(R[8], u1.z, t[2]))));
-                    V3 Q2 = v3(fmaf(R[0], u2.x, fmaf(R[1], u2.y, fmaf(R[2], u2.z, t[0]))),
-                               fmaf(R[3], u2.x, fmaf(R[4], u2.y, fmaf(R[5], u2.z, t[1]))),
-                               fmaf(R[6], u2.x, fmaf(R[7], u2.y, fmaf(R[8], u2.z, t[2]))));
-                    hit = tri_contact(v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), v3(p2.x, p2.y, p2.z), Q0, Q1, Q2, eps2);
-                } else {
-                    // descend the larger box (PQP.cpp:539-544 compares BV sizes; any rule is verdict-neutral)
-                    const float sa = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z;
-                    const float sb = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
-                    push = true;
-                    if (lb < 0 || (la >= 0 && sa > sb)) {
-                        c0a = (uint32_t)la; c1a = (uint32_t)__float_as_int(a1.w); c0b = b; c1b = b;
-                    } else {
-                        c0a = a; c1a = a; c0b = (uint32_t)lb; c1b = (uint32_t)__float_as_int(b1.w);
-                    }
-                }
+    } else {
+        J.tx = st.axis[0] * v; J.ty = st.axis[1] * v; J.tz = st.axis[2] * v;
+    }
+    return xf_mul(xf_mul(L, J), xf_load(st.R));       // (L * J) * R, kinbody.cpp:2478
+}
+
+__global__ void __launch_bounds__(kFkThreads)
+cc_fk_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FkStep* s_steps = (FkStep*)smem_raw;
+    float* s_linkbox = (float*)(s_steps + P.nsteps);
+    float* s_envbox = s_linkbox + 8 * P.nq;
+    const int nenv = P.nslots - P.nq;
+    {
+        const int4* src = (const int4*)P.steps; int4* dst = (int4*)s_steps;
+        for (int i = threadIdx.x; i < P.nsteps * (int)(sizeof(FkStep) / 16); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 8 * P.nq; i += blockDim.x) s_linkbox[i] = P.link_box[i];
+        for (int i = threadIdx.x; i < 8 * nenv; i += blockDim.x) s_envbox[i] = P.env_aabb[i];
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n) return;
+
+    // ---------------------------------------------------------------- 1. link poses (FP64)
+    if (P.flags & kFlagPoseMode) {
+        const double* src = P.q + (size_t)c * P.nq * 8;
+        for (int l = 0; l < P.nq; ++l) emit_link(P, s_linkbox, c, l, xf_load(src + 8 * l));
+    } else {
+        const Xf base = xf_load(P.base);
+        emit_link(P, s_linkbox, c, 0, base);                  // link 0 keeps its pose (kinbody.cpp:2281)
+        const double* qrow = P.q + (size_t)c * P.ncols;
+        Xf cur = base;
+        const size_t cs = (size_t)P.cap;
+        for (int s = 0; s < P.nsteps; ++s) {
+            const FkStep& st = s_steps[s];
+            if (st.load_parent == -1) cur = base;
+            else if (st.load_parent >= 0) {
+                const double* sv = P.fksave + (size_t)st.load_parent * 7 * cs + c;
+                cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
+                cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
             }
-        }
-        const unsigned hm = __ballot_sync(kFull, hit);
-        if (hm) {
-            if (hit) atomicOr(&w.slot_hit[s >> 5], 1u << (s & 31));
-            int pe = (hit && pidx < P.nenv_total) ? pidx : 0x7fffffff;
-            int ps = (hit && pidx >= P.nenv_total) ? pidx : 0x7fffffff;
-            pe = __reduce_min_sync(kFull, pe);
-            ps = __reduce_min_sync(kFull, ps);
-            if (pe < w.best_env) w.best_env = pe;
-            if (ps < w.best_self) w.best_self = ps;
-        }
-        const unsigned pm = __ballot_sync(kFull, push);
-        if (push) {
-            const int off = w.sp + 2 * __popc(pm & lt_mask);
-            w.st_a[off] = c1a; w.st_b[off] = c1b; w.st_s[off] = s;
-            w.st_a[off + 1] = c0a; w.st_b[off + 1] = c0b; w.st_s[off + 1] = s;
-        }
-        w.sp += 2 * __popc(pm);
-        __syncwarp();
-        if (w.sp > kStackCap - 64) stack_spill(P, w, lane);
-    }
-}
-
-// Write the hit bits of the current slots into the global pair bitmask (all-pairs mode).
-__device__ __forceinline__ void flush_slots(const Params& P, WarpState& w, int lane, int nslots_used, uint32_t* mask_row)
-{
-    if (mask_row) {
-        for (int s = lane; s < nslots_used; s += 32) {
-            if ((w.slot_hit[s >> 5] >> (s & 31)) & 1u) {
-                int p = w.slot_pair[s];
-                atomicOr(&mask_row[p >> 5], 1u << (p & 31));
+            cur = xf_mul(cur, joint_transform(st, qrow));
+            if (st.save >= 0) {
+                double* sv = P.fksave + (size_t)st.save * 7 * cs + c;
+                sv[0] = cur.q0; sv[cs] = cur.q1; sv[2 * cs] = cur.q2; sv[3 * cs] = cur.q3;
+                sv[4 * cs] = cur.tx; sv[5 * cs] = cur.ty; sv[6 * cs] = cur.tz;
             }
+            emit_link(P, s_linkbox, c, st.child, cur);
         }
     }
-    __syncwarp();
-    if (lane < 2) w.slot_hit[lane] = 0;
-    __syncwarp();
+    if (P.flags & kFlagFkOnly) return;
+
+    // ---------------------------------------------------------------- 2. broadphase: world AABBs, reference pair order
+    const size_t cs = (size_t)P.cap;
+    uint32_t* crow = P.cand + (size_t)c * P.cwords;
+    int ncand = 0;
+    int cur_a = -1;
+    float acx = 0, acy = 0, acz = 0, aex = 0, aey = 0, aez = 0;
+    for (int w = 0; w < P.cwords; ++w) {
+        uint32_t bits = 0;
+        const int k0 = w * 32;
+        const int k1 = min(k0 + 32, P.npairs_dev);
+        for (int k = k0; k < k1; ++k) {
+            if (!(P.flags & (k < P.nenv_dev ? kFlagEnv : kFlagSelf))) continue;
+            const uint32_t pr = __ldg(&P.pairs[k]);
+            const int a = pr & 0xffff, sb = pr >> 16;
+            if (a != cur_a) {
+                const float* ab = P.aabb + (size_t)a * 6 * cs + c;
+                acx = ab[0]; acy = ab[cs]; acz = ab[2 * cs]; aex = ab[3 * cs]; aey = ab[4 * cs]; aez = ab[5 * cs];
+                cur_a = a;
+            }
+            float bcx, bcy, bcz, bex, bey, bez;
+            if (sb < P.nq) {
+                const float* bb = P.aabb + (size_t)sb * 6 * cs + c;
+                bcx = bb[0]; bcy = bb[cs]; bcz = bb[2 * cs]; bex = bb[3 * cs]; bey = bb[4 * cs]; bez = bb[5 * cs];
+            } else {
+                const float* bb = s_envbox + 8 * (sb - P.nq);
+                bcx = bb[0]; bcy = bb[1]; bcz = bb[2]; bex = bb[3]; bey = bb[4]; bez = bb[5];
+            }
+            const bool ov = fabsf(acx - bcx) <= aex + bex && fabsf(acy - bcy) <= aey + bey && fabsf(acz - bcz) <= aez + bez;
+            bits |= (ov ? 1u : 0u) << (k - k0);
+        }
+        crow[w] = bits;
+        ncand += __popc(bits);
+    }
+    if (P.pair_mask) {
+        uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
+        for (int i = 0; i < P.mask_words; ++i) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
+    }
+    if (ncand == 0) {
+        // nothing can touch: the verdict is the hoisted pairs' alone
+        uint32_t v = 0;
+        if ((P.flags & kFlagEnv) && P.hoisted_first_env != kNone) v |= 1u;
+        if ((P.flags & kFlagSelf) && P.hoisted_first_self != kNone) v |= 2u;
+        if (P.verdict) P.verdict[c] = v;
+        if (P.first_env) P.first_env[c] = (v & 1u) ? P.hoisted_first_env : -1;
+        if (P.first_self) P.first_self[c] = (v & 2u) ? P.hoisted_first_self : -1;
+    } else {
+        const int pos = atomicAdd(&P.counters[0], 1);
+        P.queue[pos] = c;
+    }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-cc_check_kernel(const __grid_constant__ Params P)
+// ================================================================================================ kernel 2: traversal
+constexpr size_t kWarpSmemBytes = (size_t)kNumSlots * 48 + (size_t)kNumSlots * 4 + (size_t)kStackCap * 8 + (size_t)kTriQCap * 8 +
+                                  (size_t)kCandCap * 4;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
+cc_traverse_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const size_t wbytes = warp_smem_bytes(P.nq, P.nsteps);
-    unsigned char* base = smem_raw + wib * wbytes;
-    WarpState w;
-    w.xf32 = (float*)base;
-    w.slot_rt = w.xf32 + (size_t)P.nq * 12;
-    w.slot_pair = (int32_t*)(w.slot_rt + kNumSlots * 12);
-    w.slot_hit = (uint32_t*)(w.slot_pair + kNumSlots);
-    unsigned char* scratch = (unsigned char*)(w.slot_hit + 4);
-    w.st_a = (uint32_t*)scratch;
-    w.st_b = w.st_a + kStackCap;
-    w.st_s = w.st_b + kStackCap;
-    w.fk_xf = (double*)scratch;
-    w.fk_m = w.fk_xf + (size_t)P.nq * 8;
-    const int gwarp = blockIdx.x * kWarpsPerBlock + wib;
-    w.spill = P.spill + (size_t)gwarp * 3 * P.spill_cap;
-    w.n_bv = 0; w.n_tri = 0;
+    unsigned char* wbase = smem_raw + wib * kWarpSmemBytes;
+    float* slot_rt = (float*)wbase;                               // [kNumSlots][12]
+    int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 12);    // [kNumSlots] original pair index
+    uint2* stack = (uint2*)(slot_pair + kNumSlots);               // [kStackCap] {x | slot<<26, y | side<<31}
+    uint2* triq = stack + kStackCap;                              // [kTriQCap]  {triA | slot<<26, triB}
+    uint32_t* cbuf = (uint32_t*)(triq + kTriQCap);                // [kCandCap]  device pair indices
+    uint2* spill = P.spill + (size_t)(blockIdx.x * kWarpsPerBlock + wib) * P.spill_cap;
+
     const bool all_pairs = (P.flags & kFlagAllPairs) != 0;
+    const bool counters = (P.flags & kFlagCounters) != 0;
+    const float eps2 = P.tri_eps * P.tri_eps;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int qlen = P.counters[0];
+    unsigned long long n_bv = 0, n_tri = 0;
 
     for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(P.work_counter, 1);
-        c = __shfl_sync(kFull, c, 0);
-        if (c >= P.n) break;
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(&P.counters[1], 1);
+        qi = __shfl_sync(kFull, qi, 0);
+        if (qi >= qlen) break;
+        const int c = P.queue[qi];
+        const float* xf = P.xf32 + (size_t)c * P.nq * 12;
+        const uint32_t* crow = P.cand + (size_t)c * P.cwords;
+        uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
 
-        // ---------------------------------------------------------------- 1. link poses (FP64)
-        if (P.flags & kFlagPoseMode) {
-            const double* src = P.q + (size_t)c * P.nq * 8;
-            for (int i = lane; i < P.nq * 8; i += 32) w.fk_xf[i] = src[i];
-        } else {
-            const double* qrow = P.q + (size_t)c * P.ncols;
-            for (int s = lane; s < P.nsteps; s += 32) {
-                const FkStep& st = P.steps[s];
-                Xf L = xf_load(st.L);
-                Xf M;
-                if (st.flags & 1) {
-                    M = L;                                   // static joint: right already folded (kinbodyjoint.cpp:1527-1551)
-                } else {
-                    double v = st.src_col >= 0 ? qrow[st.src_col] : st.src_const;
-                    if (!(st.flags & 8)) {                   // SetDOFValues clamps non-circular DOFs (kinbody.cpp:2149-2224)
-                        if (v < st.src_lower) v = st.src_lower; else if (v > st.src_upper) v = st.src_upper;
-                    }
-                    if (st.flags & 2) {                      // mimic (kinbody.cpp:2308-2386)
-                        double ev = st.a * v + st.b;
-                        v = ev;
-                        if (!(st.flags & 4)) {
-                            if (ev < st.lower) { if (ev >= st.lower - 1e-7) v = st.lower; else if (ev < st.lower - 5e-4) v = st.lower; }
-                            else if (ev > st.upper) { if (ev <= st.upper + 1e-7) v = st.upper; else if (ev > st.upper + 5e-4) v = st.upper; }
-                        }
-                    }
-                    Xf J; J.q0 = 1; J.q1 = J.q2 = J.q3 = 0; J.tx = J.ty = J.tz = 0;
-                    if (st.type == 1) {
-                        // quatFromAxisAngle (geometry.h:673-682)
-                        double len = sqrt(st.axis[0] * st.axis[0] + st.axis[1] * st.axis[1] + st.axis[2] * st.axis[2]);
-                        if (len != 0) {
-                            double sn, cs; sincos(v * 0.5, &sn, &cs);
-                            sn /= len;
-                            J.q0 = cs; J.q1 = st.axis[0] * sn; J.q2 = st.axis[1] * sn; J.q3 = st.axis[2] * sn;
-                        }
-                    } else {
-                        J.tx = st.axis[0] * v; J.ty = st.axis[1] * v; J.tz = st.axis[2] * v;
-                    }
-                    M = xf_mul(xf_mul(L, J), xf_load(st.R));  // (L * J) * R, kinbody.cpp:2478
-                }
-                xf_store(w.fk_m + 8 * s, M);
-            }
-            if (lane < 8) w.fk_xf[lane] = P.base[lane];       // link 0 keeps its pose (kinbody.cpp:2281)
-            __syncwarp();
-            for (int d = 0; d <= P.max_depth; ++d) {
-                const int s0 = P.level_start[d], s1 = P.level_start[d + 1];
-                for (int s = s0 + lane; s < s1; s += 32) {
-                    const FkStep& st = P.steps[s];
-                    Xf T = xf_mul(xf_load(w.fk_xf + 8 * st.parent), xf_load(w.fk_m + 8 * s));
-                    xf_store(w.fk_xf + 8 * st.child, T);
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-        if (P.fk_out) {
-            double* dst = P.fk_out + (size_t)c * P.nq * 8;
-            for (int i = lane; i < P.nq * 8; i += 32) dst[i] = w.fk_xf[i];
-        }
-        if (P.flags & kFlagFkOnly) { __syncwarp(); continue; }
-        // FP32 R|t, base-centred (matrixFromQuat, geometry.h:779-800)
-        for (int l = lane; l < P.nq; l += 32) {
-            const double* x = w.fk_xf + 8 * l;
-            double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
-            double il = 2.0 / (q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-            double qq1 = il * q1 * q1, qq2 = il * q2 * q2, qq3 = il * q3 * q3;
-            float* o = w.xf32 + 12 * l;
-            o[0] = (float)(1 - qq2 - qq3);            o[1] = (float)(il * (q1 * q2 - q0 * q3)); o[2] = (float)(il * (q1 * q3 + q0 * q2));
-            o[3] = (float)(il * (q1 * q2 + q0 * q3)); o[4] = (float)(1 - qq1 - qq3);            o[5] = (float)(il * (q2 * q3 - q0 * q1));
-            o[6] = (float)(il * (q1 * q3 - q0 * q2)); o[7] = (float)(il * (q2 * q3 + q0 * q1)); o[8] = (float)(1 - qq1 - qq2);
-            o[9] = (float)(x[4] - P.center[0]); o[10] = (float)(x[5] - P.center[1]); o[11] = (float)(x[6] - P.center[2]);
-        }
-        __syncwarp();   // from here on the scratch area is the item stack
+        // warp-uniform state, all in registers
+        int sp = 0, spill_count = 0, ntri = 0, ncb = 0;
+        int best_env = P.hoisted_first_env, best_self = P.hoisted_first_self;
+        uint32_t slot_hit = 0;
+        bool failed = false;
 
-        // ---------------------------------------------------------------- 2.+3.+4. pairs
-        w.sp = 0; w.spill_count = 0;
-        w.best_env = P.hoisted_first_env;
-        w.best_self = P.hoisted_first_self;
-        if (lane < 2) w.slot_hit[lane] = 0;
-        uint32_t* mask_row = NULL;
-        if (P.pair_mask) {
-            mask_row = P.pair_mask + (size_t)c * P.mask_words;
-            for (int i = lane; i < P.mask_words; i += 32) mask_row[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
-        }
-        __syncwarp();
-        int nslots_used = 0;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        for (int basek = 0; basek < P.npairs_dev; basek += 32) {
-            const int k = basek + lane;
-            bool cand = false;
-            float R[9], t[3];
-            int orig = 0;
-            uint32_t ra = 0, rb = 0;
-            if (k < P.npairs_dev) {
-                orig = P.pair_orig[k];
-                const bool is_env = k < P.nenv_dev;
-                bool skip = !(P.flags & (is_env ? kFlagEnv : kFlagSelf));
-                if (!all_pairs) skip |= is_env ? (orig > w.best_env) : (orig > w.best_self);
-                if (!skip) {
-                    const uint32_t pr = P.pairs[k];
-                    const int la = pr & 0xffff, lb = pr >> 16;
-                    const float* A = w.xf32 + 12 * la;
-                    float Bx[12];
-                    if (lb < P.nq) {
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) Bx[i] = w.xf32[12 * lb + i];
-                    } else {
-                        const float4* e = (const float4*)(P.env_xf + 12 * (size_t)(lb - P.nq));
-                        float4 e0 = __ldg(e), e1 = __ldg(e + 1), e2 = __ldg(e + 2);
-                        Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
-                        Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
-                    }
-                    relative_pose(A, Bx, R, t);
-                    ra = (uint32_t)P.slot_root[la]; rb = (uint32_t)P.slot_root[lb];
-                    const float4 a0 = __ldg(&P.nodes[2 * ra]), a1 = __ldg(&P.nodes[2 * ra + 1]);
-                    const float4 b0 = __ldg(&P.nodes[2 * rb]), b1 = __ldg(&P.nodes[2 * rb + 1]);
-                    if (P.flags & kFlagCounters) w.n_bv++;
-                    cand = box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
+        for (int w0 = 0; w0 < P.cwords && !failed; w0 += 32) {
+            const uint32_t myword = (w0 + lane < P.cwords) ? crow[w0 + lane] : 0u;
+            unsigned nz = __ballot_sync(kFull, myword != 0u);
+            const bool last_group = w0 + 32 >= P.cwords;
+            while ((nz || (last_group && ncb > 0)) && !failed) {
+                if (nz) {
+                    const int wl = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t m = __shfl_sync(kFull, myword, wl);
+                    if ((m >> lane) & 1u) cbuf[ncb + __popc(m & lt_mask)] = (uint32_t)((w0 + wl) * 32 + lane);
+                    ncb += __popc(m);
+                    __syncwarp();
+                    if (ncb < 32 && (nz || !last_group)) continue;
                 }
-            }
-            const unsigned cm = __ballot_sync(kFull, cand);
-            if (cm) {
-                const int cnt = __popc(cm);
+                // ---------------------------------------------------------------- a batch of <= 32 root pairs
+                const int cnt = ncb < 32 ? ncb : 32;
+                bool cand = false;
+                float R[9], t[3];
+                int orig = 0;
+                uint32_t ra = 0, rb = 0;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+                if (lane < cnt) {
+                    const uint32_t k = cbuf[lane];
+                    orig = __ldg(&P.pair_orig[k]);
+                    const bool is_env = (int)k < P.nenv_dev;
+                    bool skip = false;
+                    if (!all_pairs) skip = is_env ? (orig > best_env) : (orig > best_self);
+                    if (!skip) {
+                        const uint32_t pr = __ldg(&P.pairs[k]);
+                        const int la = pr & 0xffff, lb = pr >> 16;
+                        float A[12], Bx[12];
+                        {
+                            const float4* e = (const float4*)(xf + 12 * la);
+                            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                            A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
+                            A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
+                        }
+                        {
+                            const float4* e = lb < P.nq ? (const float4*)(xf + 12 * lb) : (const float4*)(P.env_xf + 12 * (size_t)(lb - P.nq));
+                            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                            Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
+                            Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
+                        }
+                        relative_pose(A, Bx, R, t);
+                        ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
+                        a0 = __ldg(&P.nodes[2 * ra]); a1 = __ldg(&P.nodes[2 * ra + 1]);
+                        b0 = __ldg(&P.nodes[2 * rb]); b1 = __ldg(&P.nodes[2 * rb + 1]);
+                        if (counters) n_bv++;
+                        cand = box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
+                    }
+                }
+                // drop the consumed candidates
+                {
+                    const int rest = ncb - cnt;
+                    uint32_t mv = 0;
+                    if (lane < rest) mv = cbuf[cnt + lane];
+                    __syncwarp();
+                    if (lane < rest) cbuf[lane] = mv;
+                    ncb = rest;
+                    __syncwarp();
+                }
+                const unsigned cm = __ballot_sync(kFull, cand);
+                if (cm == 0u) continue;
+                const int nsl = __popc(cm);
                 if (cand) {
-                    const int rank = __popc(cm & lt_mask);
-                    const int s = nslots_used + rank;
-                    float* rt = w.slot_rt + 12 * s;
+                    const int s = __popc(cm & lt_mask);
+                    float* rt = slot_rt + 12 * s;
 #pragma unroll
                     for (int i = 0; i < 9; ++i) rt[i] = R[i];
                     rt[9] = t[0]; rt[10] = t[1]; rt[11] = t[2];
-                    w.slot_pair[s] = orig;
-                    // reversed inside the chunk so the lowest pair index is popped first
-                    const int pos = w.sp + (cnt - 1 - rank);
-                    w.st_a[pos] = ra; w.st_b[pos] = rb; w.st_s[pos] = (uint32_t)s;
+                    slot_pair[s] = orig;
                 }
-                nslots_used += cnt;
-                w.sp += cnt;
-            }
-            __syncwarp();
-            const bool last = basek + 32 >= P.npairs_dev;
-            if (nslots_used > kNumSlots - 32 || (last && nslots_used > 0)) {
-                traverse(P, w, lane);
-                flush_slots(P, w, lane, nslots_used, all_pairs ? mask_row : NULL);
-                nslots_used = 0;
+                // first items: both leaves -> triangle queue; else split the larger box (PQP.cpp:539-544 compares BV
+                // sizes; any rule is verdict-neutral).  Reversed so the lowest pair index is popped first.
+                {
+                    const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+                    const bool leafpair = cand && la < 0 && lb < 0;
+                    const bool push = cand && !leafpair;
+                    const unsigned tm = __ballot_sync(kFull, leafpair);
+                    const unsigned pm = __ballot_sync(kFull, push);
+                    const uint32_t s = (uint32_t)__popc(cm & lt_mask);
+                    if (leafpair) triq[ntri + __popc(tm & lt_mask)] = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
+                    if (push) {
+                        const float sa = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z;
+                        const float sb = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
+                        uint2 it;
+                        if (lb < 0 || (la >= 0 && sa > sb)) it = make_uint2((uint32_t)la | (s << 26), rb);
+                        else it = make_uint2((uint32_t)lb | (s << 26), ra | 0x80000000u);
+                        stack[sp + (__popc(pm) - 1 - __popc(pm & lt_mask))] = it;
+                    }
+                    ntri += __popc(tm);
+                    sp += __popc(pm);
+                }
+                __syncwarp();
+
+                // ---------------------------------------------------------------- drain: descent + triangle batches
+                for (;;) {
+                    if (ntri >= 32 || (ntri > 0 && sp == 0 && spill_count == 0)) {
+                        // ---- up to 32 leaf x leaf tests (newest first)
+                        const int tn = ntri < 32 ? ntri : 32;
+                        bool hit = false;
+                        int pidx = 0;
+                        uint32_t s = 0;
+                        if (lane < tn) {
+                            const uint2 e = triq[ntri - 1 - lane];
+                            s = e.x >> 26;
+                            pidx = slot_pair[s];
+                            bool dead = (slot_hit >> s) & 1u;
+                            if (!all_pairs) dead |= (pidx < P.nenv_total) ? (pidx > best_env) : (pidx > best_self);
+                            if (!dead) {
+                                if (counters) n_tri++;
+                                const float4* ta = P.tris + 3 * (size_t)(e.x & 0x3ffffffu);
+                                const float4* tb = P.tris + 3 * (size_t)e.y;
+                                const float4 p0 = __ldg(ta), p1 = __ldg(ta + 1), p2 = __ldg(ta + 2);
+                                const float4 u0 = __ldg(tb), u1 = __ldg(tb + 1), u2 = __ldg(tb + 2);
+                                const float* rt = slot_rt + 12 * s;
+                                const float r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3], r4 = rt[4], r5 = rt[5], r6 = rt[6], r7 = rt[7], r8 = rt[8];
+                                const float t0 = rt[9], t1 = rt[10], t2 = rt[11];
+                                V3 Q0 = v3(fmaf(r0, u0.x, fmaf(r1, u0.y, fmaf(r2, u0.z, t0))), fmaf(r3, u0.x, fmaf(r4, u0.y, fmaf(r5, u0.z, t1))),
+                                           fmaf(r6, u0.x, fmaf(r7, u0.y, fmaf(r8, u0.z, t2))));
+                                V3 Q1 = v3(fmaf(r0, u1.x, fmaf(r1, u1.y, fmaf(r2, u1.z, t0))), fmaf(r3, u1.x, fmaf(r4, u1.y, fmaf(r5, u1.z, t1))),
+                                           fmaf(r6, u1.x, fmaf(r7, u1.y, fmaf(r8, u1.z, t2))));
+                                V3 Q2 = v3(fmaf(r0, u2.x, fmaf(r1, u2.y, fmaf(r2, u2.z, t0))), fmaf(r3, u2.x, fmaf(r4, u2.y, fmaf(r5, u2.z, t1))),
+                                           fmaf(r6, u2.x, fmaf(r7, u2.y, fmaf(r8, u2.z, t2))));
+                                hit = tri_contact(v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), v3(p2.x, p2.y, p2.z), Q0, Q1, Q2, eps2);
+                            }
+                        }
+                        ntri -= tn;
+                        const unsigned hm = __ballot_sync(kFull, hit);
+                        if (hm) {
+                            slot_hit |= __reduce_or_sync(kFull, hit ? (1u << s) : 0u);
+                            const int pe = __reduce_min_sync(kFull, (hit && pidx < P.nenv_total) ? pidx : kNone);
+                            const int ps = __reduce_min_sync(kFull, (hit && pidx >= P.nenv_total) ? pidx : kNone);
+                            if (pe < best_env) best_env = pe;
+                            if (ps < best_self) best_self = ps;
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    if (sp == 0) {
+                        if (spill_count == 0) break;
+                        // refill from the global spill area
+                        const int m = spill_count < kSpillChunk ? spill_count : kSpillChunk;
+                        const uint2* g = spill + (spill_count - m);
+                        for (int i = lane; i < m; i += 32) stack[i] = g[i];
+                        spill_count -= m;
+                        sp = m;
+                        __syncwarp();
+                    }
+                    // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
+                    const int n = sp < 32 ? sp : 32;
+                    bool valid = lane < n;
+                    uint2 it = make_uint2(0u, 0u);
+                    if (valid) it = stack[sp - 1 - lane];
+                    sp -= n;
+                    const uint32_t s = it.x >> 26;
+                    if (valid) {
+                        const int pidx = slot_pair[s];
+                        bool dead = (slot_hit >> s) & 1u;
+                        if (!all_pairs) dead |= (pidx < P.nenv_total) ? (pidx > best_env) : (pidx > best_self);
+                        valid = !dead;
+                    }
+                    __syncwarp();
+                    bool tq0 = false, tq1 = false, ps0 = false, ps1 = false;
+                    uint2 o0 = make_uint2(0u, 0u), o1 = make_uint2(0u, 0u);     // outputs for child 0 / child 1 (tri entry or item)
+                    if (valid) {
+                        const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x7fffffffu;
+                        const bool side = (it.y >> 31) != 0u;                  // false: x is in tree A, true: x is in tree B
+                        const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
+                        const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
+                        const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
+                        const float* rt = slot_rt + 12 * s;
+                        float R[9], t[3];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) R[k] = rt[k];
+                        t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
+                        if (counters) n_bv += 2;
+                        const int lo = __float_as_int(oa.w);
+                        const float so = ob.x * ob.x + ob.y * ob.y + ob.z * ob.z;
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const float4 ca = ch ? c1a : c0a, cb = ch ? c1b : c0b;
+                            const bool ov = side
+                                ? box_overlap(R, t, oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ca.x, ca.y, ca.z, cb.x, cb.y, cb.z)
+                                : box_overlap(R, t, ca.x, ca.y, ca.z, cb.x, cb.y, cb.z, oa.x, oa.y, oa.z, ob.x, ob.y, ob.z);
+                            if (ov) {
+                                const int lc = __float_as_int(ca.w);
+                                uint2 out;
+                                bool tq = false;
+                                if (lc < 0 && lo < 0) {
+                                    tq = true;
+                                    out = side ? make_uint2((uint32_t)(~lo) | (s << 26), (uint32_t)(~lc))
+                                               : make_uint2((uint32_t)(~lc) | (s << 26), (uint32_t)(~lo));
+                                } else {
+                                    const float sc = cb.x * cb.x + cb.y * cb.y + cb.z * cb.z;
+                                    if (lo < 0 || (lc >= 0 && sc > so))
+                                        out = make_uint2((uint32_t)lc | (s << 26), it.y);                               // split the child
+                                    else
+                                        out = make_uint2((uint32_t)lo | (s << 26), (x + ch) | (side ? 0u : 0x80000000u)); // split the other
+                                }
+                                if (ch) { o1 = out; tq1 = tq; ps1 = !tq; } else { o0 = out; tq0 = tq; ps0 = !tq; }
+                            }
+                        }
+                    }
+                    const unsigned t0m = __ballot_sync(kFull, tq0), t1m = __ballot_sync(kFull, tq1);
+                    const unsigned p0m = __ballot_sync(kFull, ps0), p1m = __ballot_sync(kFull, ps1);
+                    if (t0m | t1m) {
+                        int off = ntri + __popc(t0m & lt_mask) + __popc(t1m & lt_mask);
+                        if (tq0) triq[off++] = o0;
+                        if (tq1) triq[off] = o1;
+                        ntri += __popc(t0m) + __popc(t1m);
+                    }
+                    if (p0m | p1m) {
+                        int off = sp + __popc(p0m & lt_mask) + __popc(p1m & lt_mask);
+                        if (ps1) stack[off++] = o1;
+                        if (ps0) stack[off] = o0;
+                        sp += __popc(p0m) + __popc(p1m);
+                    }
+                    __syncwarp();
+                    if (sp > kStackCap - 64) {
+                        // move the oldest kSpillChunk items to global memory and slide the rest down
+                        if (spill_count + kSpillChunk > P.spill_cap) {
+                            if (lane == 0) atomicExch(P.err_flag, 1);
+                            failed = true; sp = 0; ntri = 0; spill_count = 0;        // the host reports the error
+                            __syncwarp();
+                            break;
+                        }
+                        uint2* g = spill + spill_count;
+                        for (int i = lane; i < kSpillChunk; i += 32) g[i] = stack[i];
+                        spill_count += kSpillChunk;
+                        const int rest = sp - kSpillChunk;
+                        __syncwarp();
+                        for (int b = 0; b < rest; b += 32) {
+                            const int i = b + lane;
+                            uint2 v = make_uint2(0u, 0u);
+                            if (i < rest) v = stack[kSpillChunk + i];
+                            __syncwarp();
+                            if (i < rest) stack[i] = v;
+                            __syncwarp();
+                        }
+                        sp = rest;
+                    }
+                }
+                // ---------------------------------------------------------------- publish this batch's hits
+                if (mask_row && slot_hit) {
+                    if (lane < nsl && ((slot_hit >> lane) & 1u)) {
+                        const int p = slot_pair[lane];
+                        atomicOr(&mask_row[p >> 5], 1u << (p & 31));
+                    }
+                }
+                slot_hit = 0;
+                __syncwarp();
             }
         }
 
-        // ---------------------------------------------------------------- 5. verdict
+        // ---------------------------------------------------------------- verdict
         if (lane == 0) {
-            int be = w.best_env, bs = w.best_self;
-            if (all_pairs && mask_row) {
+            int be = best_env, bs = best_self;
+            if (mask_row) {
                 // complete masks: derive the first pairs from the bits
-                be = 0x7fffffff; bs = 0x7fffffff;
-                const int total = P.mask_words * 32;
+                be = kNone; bs = kNone;
                 for (int wd = 0; wd < P.mask_words; ++wd) {
-                    uint32_t m = mask_row[wd];
+                    uint32_t m = __ldcg(&mask_row[wd]);   // bits were set with L2 atomics: bypass L1
                     while (m) {
-                        int bit = __ffs(m) - 1; m &= m - 1;
-                        int p = wd * 32 + bit;
+                        const int bit = __ffs(m) - 1; m &= m - 1;
+                        const int p = wd * 32 + bit;
                         if (p < P.nenv_total) { if (p < be) be = p; } else { if (p < bs) bs = p; }
                     }
-                    (void)total;
                 }
             }
             uint32_t v = 0;
-            if ((P.flags & kFlagEnv) && be != 0x7fffffff) v |= 1u;
-            if ((P.flags & kFlagSelf) && bs != 0x7fffffff) v |= 2u;
+            if ((P.flags & kFlagEnv) && be != kNone) v |= 1u;
+            if ((P.flags & kFlagSelf) && bs != kNone) v |= 2u;
             if (P.verdict) P.verdict[c] = v;
             if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
             if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
         }
         __syncwarp();
     }
-    if (P.flags & kFlagCounters) {
-        unsigned long long bv = w.n_bv, tr = w.n_tri;
-        for (int o = 16; o > 0; o >>= 1) { bv += __shfl_xor_sync(kFull, bv, o); tr += __shfl_xor_sync(kFull, tr, o); }
-        if (lane == 0) { atomicAdd(&P.stats[0], bv); atomicAdd(&P.stats[1], tr); }
+    if (counters) {
+        for (int o = 16; o > 0; o >>= 1) { n_bv += __shfl_xor_sync(kFull, n_bv, o); n_tri += __shfl_xor_sync(kFull, n_tri, o); }
+        if (lane == 0) { atomicAdd(&P.stats[0], n_bv); atomicAdd(&P.stats[1], n_tri); }
     }
 }
 

@@ -96,9 +96,10 @@ struct cc_scene {
     bool committed = false;
     DevBuf<float4> d_nodes, d_tris;
     int total_nodes = 0, total_tris = 0;
-    DevBuf<uint32_t> d_spill;
+    DevBuf<uint2> d_spill;
     int spill_warps = 0;
-    DevBuf<int32_t> d_counter_err;          // [0] work counter, [1] error flag
+    DevBuf<int32_t> d_err;                  // [0] error flag (a traversal overflowed its spill area)
+    int trav_blocks_per_sm = 0;             // occupancy of cc_traverse_kernel (queried once)
     DevBuf<unsigned long long> d_stats;     // [0] bv, [1] tri
     bool counters = false;
     cc_stats stats = {};
@@ -252,12 +253,17 @@ struct cc_query {
     int nenv_total = 0, nself_total = 0;
     PairList full, mainl, hoisted;
     bool has_fk = false;
-    std::vector<ccdev::FkStep> steps;
-    std::vector<int32_t> level_start;
-    int max_depth = 0;
+    std::vector<ccdev::FkStep> steps;       // depth-first order
+    int nsave = 0;                           // link poses parked for later branches
     DevBuf<ccdev::FkStep> d_steps;
-    DevBuf<int32_t> d_level_start, d_slot_root;
-    DevBuf<float> d_env_xf;
+    DevBuf<int32_t> d_slot_root;
+    DevBuf<float> d_env_xf, d_env_aabb, d_link_box;
+    // per-chunk scratch (grown on demand)
+    int chunk_cap = 0;
+    DevBuf<float> d_xf32, d_aabb;
+    DevBuf<double> d_fksave;
+    DevBuf<uint32_t> d_cand;
+    DevBuf<int32_t> d_queue, d_counters;
     DevBuf<uint32_t> d_hoisted_mask;
     std::vector<uint32_t> hoisted_mask;
     int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
@@ -273,6 +279,25 @@ struct cc_query {
 
 namespace {
 
+// Bytes of per-chunk scratch one configuration needs.
+size_t scratch_bytes_per_config(const cc_query* Q, int cwords)
+{
+    return (size_t)Q->nq * 48 + (size_t)Q->nq * 24 + (size_t)Q->nsave * 56 + (size_t)cwords * 4 + 4;
+}
+
+int ensure_scratch(cc_query* Q, int cap, int cwords)
+{
+    if (cap <= Q->chunk_cap) return CC_OK;
+    CC_CUDA(Q->d_xf32.reserve((size_t)cap * Q->nq * 12));
+    CC_CUDA(Q->d_aabb.reserve((size_t)cap * Q->nq * 6));
+    CC_CUDA(Q->d_fksave.reserve((size_t)cap * std::max(1, Q->nsave) * 7));
+    CC_CUDA(Q->d_cand.reserve((size_t)cap * cwords));
+    CC_CUDA(Q->d_queue.reserve((size_t)cap));
+    CC_CUDA(Q->d_counters.reserve(2));
+    Q->chunk_cap = cap;
+    return CC_OK;
+}
+
 int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
            int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st)
 {
@@ -281,57 +306,93 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
     ccdev::Params P;
     memset(&P, 0, sizeof(P));
     P.nodes = S->d_nodes.p; P.tris = S->d_tris.p;
-    P.slot_root = Q->d_slot_root.p; P.env_xf = Q->d_env_xf.p;
+    P.slot_root = Q->d_slot_root.p; P.env_xf = Q->d_env_xf.p; P.env_aabb = Q->d_env_aabb.p; P.link_box = Q->d_link_box.p;
     P.pairs = pl.d_pairs.p; P.pair_orig = pl.d_orig.p;
-    P.steps = Q->d_steps.p; P.level_start = Q->d_level_start.p;
+    P.steps = Q->d_steps.p;
     P.hoisted_mask = use_hoisted ? Q->d_hoisted_mask.p : nullptr;
     P.nq = Q->nq; P.nslots = Q->nslots; P.npairs_dev = (int)pl.pairs.size(); P.nenv_dev = pl.nenv;
-    P.nenv_total = Q->nenv_total; P.nsteps = (int)Q->steps.size(); P.max_depth = Q->max_depth; P.ncols = Q->ncols;
-    P.hoisted_first_env = use_hoisted ? Q->hoisted_first_env : 0x7fffffff;
-    P.hoisted_first_self = use_hoisted ? Q->hoisted_first_self : 0x7fffffff;
+    P.nenv_total = Q->nenv_total; P.nsteps = (int)Q->steps.size(); P.ncols = Q->ncols;
+    P.cwords = std::max(1, (P.npairs_dev + 31) / 32);
+    P.hoisted_first_env = use_hoisted ? Q->hoisted_first_env : ccdev::kNone;
+    P.hoisted_first_self = use_hoisted ? Q->hoisted_first_self : ccdev::kNone;
     P.mask_words = Q->mask_words;
     P.flags = flags | (S->counters ? ccdev::kFlagCounters : 0);
     memcpy(P.base, Q->base, sizeof(P.base));
     memcpy(P.center, Q->center, sizeof(P.center));
     P.tri_eps = S->tri_eps;
-    P.q = d_q; P.n = n;
-    P.verdict = d_verdict; P.first_env = d_fe; P.first_self = d_fs; P.pair_mask = d_mask; P.fk_out = d_fk;
-    P.work_counter = S->d_counter_err.p; P.err_flag = S->d_counter_err.p + 1;
+    P.err_flag = S->d_err.p;
     P.stats = S->d_stats.p;
     P.spill_cap = 4096;
+    const bool fk_only = (flags & ccdev::kFlagFkOnly) != 0;
+    const int row_doubles = (flags & ccdev::kFlagPoseMode) ? Q->nq * 8 : Q->ncols;
 
-    const size_t smem = ccdev::warp_smem_bytes(P.nq, P.nsteps) * ccdev::kWarpsPerBlock;
-    if (smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "body has too many links/joints for one warp's shared memory");
-    CC_CUDA(cudaFuncSetAttribute(ccdev::cc_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_check_kernel, ccdev::kWarpsPerBlock * 32, smem));
-    if (per_sm < 1) return fail(CC_ERR_CUDA, "kernel does not fit on an SM");
-    int grid = per_sm * S->num_sms;                       // persistent: a whole number of waves
-    int need = (n + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
-    if (grid > need) grid = need;
-    const int warps = grid * ccdev::kWarpsPerBlock;
-    if (warps > S->spill_warps) {
-        CC_CUDA(S->d_spill.reserve((size_t)warps * 3 * P.spill_cap));
-        S->spill_warps = warps;
+    // ---- chunking: the scratch of one chunk stays around a GB at most
+    const int cw_alloc = std::max(1, ((int)Q->full.pairs.size() + 31) / 32);   // the largest of this query's pair lists
+    const size_t per_cfg = scratch_bytes_per_config(Q, cw_alloc);
+    int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
+    chunk = std::min(chunk, (n + 127) / 128 * 128);
+    {
+        int rc = ensure_scratch(Q, chunk, cw_alloc);
+        if (rc != CC_OK) return rc;
     }
-    P.spill = S->d_spill.p;
-    CC_CUDA(cudaMemsetAsync(S->d_counter_err.p, 0, sizeof(int32_t), st));
+    P.cap = Q->chunk_cap;
+    P.xf32 = Q->d_xf32.p; P.aabb = Q->d_aabb.p; P.fksave = Q->d_fksave.p; P.cand = Q->d_cand.p; P.queue = Q->d_queue.p;
+    P.counters = Q->d_counters.p;
+
+    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.nslots - P.nq);
+    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
+    if (fk_smem > 48 * 1024)
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+    const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock;
+    if (S->trav_blocks_per_sm == 0) {
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
+        int per_sm = 0;
+        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_traverse_kernel, ccdev::kWarpsPerBlock * 32, tr_smem));
+        if (per_sm < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
+        S->trav_blocks_per_sm = per_sm;
+    }
     CC_CUDA(cudaEventRecord(S->ev0, st));
-    ccdev::cc_check_kernel<<<grid, ccdev::kWarpsPerBlock * 32, smem, st>>>(P);
-    CC_CUDA(cudaGetLastError());
+    for (int off = 0; off < n; off += chunk) {
+        const int m = std::min(chunk, n - off);
+        P.n = m;
+        P.q = d_q ? d_q + (size_t)off * row_doubles : nullptr;
+        P.verdict = d_verdict ? d_verdict + off : nullptr;
+        P.first_env = d_fe ? d_fe + off : nullptr;
+        P.first_self = d_fs ? d_fs + off : nullptr;
+        P.pair_mask = d_mask ? d_mask + (size_t)off * Q->mask_words : nullptr;
+        P.fk_out = d_fk ? d_fk + (size_t)off * Q->nq * 8 : nullptr;
+        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters.p, 0, 2 * sizeof(int32_t), st));
+        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
+        CC_CUDA(cudaGetLastError());
+        S->stats.launches++;
+        if (fk_only) continue;
+        // persistent traversal grid: a whole number of waves, never more warps than configurations
+        int grid = S->trav_blocks_per_sm * S->num_sms;
+        const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
+        if (grid > need) grid = need;
+        const int warps = grid * ccdev::kWarpsPerBlock;
+        if (warps > S->spill_warps) {
+            CC_CUDA(cudaStreamSynchronize(st));      // (first launches only) nobody may still be using the old area
+            CC_CUDA(S->d_spill.reserve((size_t)S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock * P.spill_cap));
+            S->spill_warps = S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock;
+        }
+        P.spill = S->d_spill.p;
+        ccdev::cc_traverse_kernel<<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, st>>>(P);
+        CC_CUDA(cudaGetLastError());
+        S->stats.launches++;
+    }
     CC_CUDA(cudaEventRecord(S->ev1, st));
     S->ev_pending = true;
-    S->stats.launches++;
-    if (!(flags & ccdev::kFlagFkOnly)) S->stats.configs += (uint64_t)n;
+    if (!fk_only) S->stats.configs += (uint64_t)n;
     return CC_OK;
 }
 
 int check_err_flag(cc_scene* S)
 {
-    int32_t h[2] = {0, 0};
-    CC_CUDA(cudaMemcpy(h, S->d_counter_err.p, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h[1]) {
-        cudaMemset(S->d_counter_err.p + 1, 0, sizeof(int32_t));
+    int32_t h = 0;
+    CC_CUDA(cudaMemcpy(&h, S->d_err.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h) {
+        cudaMemset(S->d_err.p, 0, sizeof(int32_t));
         return fail(CC_ERR_NOMEM, "device traversal stack overflowed its spill area");
     }
     return CC_OK;
@@ -365,8 +426,8 @@ int cc_scene_create(int cuda_device, cc_scene** out)
     cudaDeviceProp prop;
     CC_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
     s->num_sms = prop.multiProcessorCount;
-    CC_CUDA(s->d_counter_err.reserve(2));
-    CC_CUDA(cudaMemset(s->d_counter_err.p, 0, 2 * sizeof(int32_t)));
+    CC_CUDA(s->d_err.reserve(1));
+    CC_CUDA(cudaMemset(s->d_err.p, 0, sizeof(int32_t)));
     CC_CUDA(s->d_stats.reserve(2));
     CC_CUDA(cudaMemset(s->d_stats.p, 0, 2 * sizeof(unsigned long long)));
     CC_CUDA(cudaEventCreate(&s->ev0));
@@ -505,6 +566,7 @@ int cc_scene_commit(cc_scene* s)
         for (HLink& L : b->links) {
             if (L.dirty) { build_link_bvh(L); L.dirty = false; }
             if (L.nodes.empty()) { L.node_base = L.tri_base = -1; continue; }
+            if ((nodes.size() & 1) == 0) nodes.push_back(HNode());   // odd base: sibling pairs (odd local index first) are 64-byte aligned
             L.node_base = (int)nodes.size();
             L.tri_base = (int)(tris.size() / 12);
             for (const HNode& n : L.nodes) {
@@ -516,6 +578,8 @@ int cc_scene_commit(cc_scene* s)
             tris.insert(tris.end(), L.tridata.begin(), L.tridata.end());
         }
     }
+    if (nodes.size() >= ((size_t)1 << 26) || tris.size() / 12 >= ((size_t)1 << 26))
+        return fail(CC_ERR_UNSUPPORTED, "scene exceeds 2^26 BVH nodes or triangles");
     s->total_nodes = (int)nodes.size();
     s->total_tris = (int)(tris.size() / 12);
     CC_CUDA(cudaDeviceSynchronize());    // no query may be in flight while the arrays are replaced
@@ -565,10 +629,23 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
             depth[j.child_link] = depth[j.parent_link] + 1;
             sdepth[k] = depth[j.child_link];
         }
-        std::vector<int> ord(B->joints.size());
-        for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int)k;
-        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return sdepth[x] < sdepth[y]; });
-        Q->max_depth = 0;
+        // depth-first order (children in listed order): a child usually follows its parent, so the device keeps the
+        // running transform in registers and parks only the poses later branches start from
+        std::vector<std::vector<int>> kids(nl);
+        for (size_t k = 0; k < B->joints.size(); ++k) kids[B->joints[k].parent_link].push_back((int)k);
+        std::vector<int> ord;
+        {
+            std::vector<std::pair<int, size_t>> stk;     // (link, next child position)
+            stk.push_back(std::make_pair(0, (size_t)0));
+            while (!stk.empty()) {
+                std::pair<int, size_t>& top = stk.back();
+                if (top.second >= kids[top.first].size()) { stk.pop_back(); continue; }
+                const int k = kids[top.first][top.second++];
+                ord.push_back(k);
+                stk.push_back(std::make_pair(B->joints[k].child_link, (size_t)0));
+            }
+        }
+        if (ord.size() != B->joints.size()) return fail(CC_ERR_INVALID, "joint tree is not connected to link 0");
         for (int k : ord) {
             const cc_joint& j = B->joints[k];
             ccdev::FkStep st;
@@ -594,30 +671,66 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
             st.a = j.mimic_a; st.b = j.mimic_b; st.lower = j.lower; st.upper = j.upper;
             memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
             Q->steps.push_back(st);
-            if (sdepth[k] > Q->max_depth) Q->max_depth = sdepth[k];
         }
-        Q->level_start.assign(Q->max_depth + 2, 0);
-        for (int k : ord) Q->level_start[sdepth[k] + 1]++;
-        for (int d = 0; d <= Q->max_depth; ++d) Q->level_start[d + 1] += Q->level_start[d];
+        std::vector<int> save_of_link(nl, -1);
+        Q->nsave = 0;
+        for (size_t i = 0; i < Q->steps.size(); ++i) {
+            ccdev::FkStep& st = Q->steps[i];
+            st.save = -1;
+            if (i > 0 && Q->steps[i - 1].child == st.parent) st.load_parent = -2;
+            else if (st.parent == 0) st.load_parent = -1;
+            else {
+                if (save_of_link[st.parent] < 0) {
+                    save_of_link[st.parent] = Q->nsave++;
+                    for (size_t j = 0; j < i; ++j) if (Q->steps[j].child == st.parent) Q->steps[j].save = save_of_link[st.parent];
+                }
+                st.load_parent = save_of_link[st.parent];
+            }
+        }
         for (int l = 1; l < nl; ++l)
             if (depth[l] < 0 && B->links[l].ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
     } else {
-        Q->max_depth = 0;
-        Q->level_start.assign(2, 0);
         for (int l = 1; l < nl; ++l)
             if (B->links[l].ntris() > 0) Q->has_fk = false;
     }
     memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
     Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
 
-    // ---- slots
+    // ---- slots: root nodes, static poses, broadphase boxes
     Q->nslots = (int)slot_body.size();
     std::vector<int32_t> roots(Q->nslots, 0);
-    std::vector<float> envxf((size_t)std::max(1, Q->nslots - nl) * 12, 0.f);
+    const int nenv = std::max(1, Q->nslots - nl);
+    std::vector<float> envxf((size_t)nenv * 12, 0.f), envbox((size_t)nenv * 8, 0.f), linkbox((size_t)std::max(1, nl) * 8, 0.f);
     for (int sidx = 0; sidx < Q->nslots; ++sidx) {
         const HLink& L = S->bodies[slot_body[sidx]]->links[slot_link[sidx]];
         roots[sidx] = L.node_base < 0 ? 0 : L.node_base;
-        if (sidx >= nl) pose_to_rt32(L.xf, Q->center, &envxf[(size_t)(sidx - nl) * 12]);
+        if (sidx < nl) {
+            if (!L.nodes.empty()) {
+                float* o = &linkbox[(size_t)sidx * 8];
+                for (int k = 0; k < 3; ++k) { o[k] = L.nodes[0].c[k]; o[3 + k] = L.nodes[0].e[k]; }
+                o[6] = 1.0f;
+            }
+        } else {
+            pose_to_rt32(L.xf, Q->center, &envxf[(size_t)(sidx - nl) * 12]);
+            float* o = &envbox[(size_t)(sidx - nl) * 8];
+            if (L.nodes.empty()) { o[0] = o[1] = o[2] = 1e30f; continue; }      // never overlaps anything
+            // world AABB of the (already inflated) root box, in double, rounded outwards
+            const double* x = L.xf;
+            const double il = 2.0 / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+            const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+            const double Rm[9] = {1 - il * (q2 * q2 + q3 * q3), il * (q1 * q2 - q0 * q3), il * (q1 * q3 + q0 * q2),
+                                  il * (q1 * q2 + q0 * q3), 1 - il * (q1 * q1 + q3 * q3), il * (q2 * q3 - q0 * q1),
+                                  il * (q1 * q3 - q0 * q2), il * (q2 * q3 + q0 * q1), 1 - il * (q1 * q1 + q2 * q2)};
+            for (int r = 0; r < 3; ++r) {
+                double c = x[4 + r] - Q->center[r], e = 0;
+                for (int k = 0; k < 3; ++k) { c += Rm[3 * r + k] * (double)L.nodes[0].c[k]; e += (fabs(Rm[3 * r + k]) + 1e-6) * (double)L.nodes[0].e[k]; }
+                const float cf = (float)c;
+                e += fabs(c - (double)cf) + 1e-6;
+                float ef = (float)e;
+                if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
+                o[r] = cf; o[3 + r] = ef;
+            }
+        }
     }
 
     // ---- split the pair list
@@ -642,9 +755,10 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     CC_CUDA(cudaSetDevice(S->device));
     CC_CUDA(Q->full.upload()); CC_CUDA(Q->mainl.upload()); CC_CUDA(Q->hoisted.upload());
     CC_CUDA(Q->d_steps.upload(Q->steps));
-    CC_CUDA(Q->d_level_start.upload(Q->level_start));
     CC_CUDA(Q->d_slot_root.upload(roots));
     CC_CUDA(Q->d_env_xf.upload(envxf));
+    CC_CUDA(Q->d_env_aabb.upload(envbox));
+    CC_CUDA(Q->d_link_box.upload(linkbox));
     Q->hoisted_mask.assign(Q->mask_words, 0u);
     CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
 
