@@ -20,7 +20,7 @@ from .flatten import cc_joint
 from .kinbody import KinBody, Link
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcudacollision.so")
+LIB_PATH = os.environ.get("CUDACOLLISION_LIB") or os.path.join(_HERE, "libcudacollision.so")   # override: A/B builds
 
 CO_Distance, CO_UseTolerance, CO_Contacts, CO_RayAnyHit = 1, 2, 4, 8
 CO_ActiveDOFs, CO_AllLinkCollisions, CO_AllGeometryCollisions, CO_AllGeometryContacts, CO_IgnoreCallbacks = \

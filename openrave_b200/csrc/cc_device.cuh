@@ -23,6 +23,9 @@
 // triangle tests of unpruned pairs, exactly like the reference's (BVH-shape independent).
 #pragma once
 #include <cuda_runtime.h>
+#ifndef CC_EDGE_AXES
+#define CC_EDGE_AXES 0
+#endif
 #include <stdint.h>
 
 namespace ccdev {
@@ -177,6 +180,52 @@ __device__ __forceinline__ bool box_overlap(const float* __restrict__ R, const f
     sep |= fabsf(T1 * R[1] - T0 * R[4]) > eax * f11 + eay * f01 + ebx * f22 + ebz * f20;
     sep |= fabsf(T1 * R[2] - T0 * R[5]) > eax * f12 + eay * f02 + ebx * f21 + eby * f20;
     return !sep;
+}
+
+// The same test for TWO boxes A0, A1 (identity frame: the two children of the node being split) against ONE box B
+// placed by (R, t).  Straight-line code (no early outs: some lane of the warp always needs the late axes), with
+// everything that depends on B alone computed once.  kEdgeAxes = false drops the 9 edge x edge axes: still
+// conservative (a box pair may only be reported overlapping more often), cheaper per test, a few more tests.
+constexpr bool kEdgeAxes = CC_EDGE_AXES;
+__device__ __forceinline__ void box_overlap_pair(const float* __restrict__ R, const float* __restrict__ t,
+                                                 float c0x, float c0y, float c0z, float e0x, float e0y, float e0z,
+                                                 float c1x, float c1y, float c1z, float e1x, float e1y, float e1z,
+                                                 float cbx, float cby, float cbz, float ebx, float eby, float ebz,
+                                                 bool& ov0, bool& ov1)
+{
+    const float reps = 1e-6f;
+    const float Bx = fmaf(R[0], cbx, fmaf(R[1], cby, fmaf(R[2], cbz, t[0])));
+    const float By = fmaf(R[3], cbx, fmaf(R[4], cby, fmaf(R[5], cbz, t[1])));
+    const float Bz = fmaf(R[6], cbx, fmaf(R[7], cby, fmaf(R[8], cbz, t[2])));
+    const float f00 = fabsf(R[0]) + reps, f01 = fabsf(R[1]) + reps, f02 = fabsf(R[2]) + reps;
+    const float f10 = fabsf(R[3]) + reps, f11 = fabsf(R[4]) + reps, f12 = fabsf(R[5]) + reps;
+    const float f20 = fabsf(R[6]) + reps, f21 = fabsf(R[7]) + reps, f22 = fabsf(R[8]) + reps;
+    const float rb0 = ebx * f00 + eby * f01 + ebz * f02;      // B's radius along A's axes
+    const float rb1 = ebx * f10 + eby * f11 + ebz * f12;
+    const float rb2 = ebx * f20 + eby * f21 + ebz * f22;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const float eax = ch ? e1x : e0x, eay = ch ? e1y : e0y, eaz = ch ? e1z : e0z;
+        const float T0 = Bx - (ch ? c1x : c0x), T1 = By - (ch ? c1y : c0y), T2 = Bz - (ch ? c1z : c0z);
+        bool sep = fabsf(T0) > eax + rb0;
+        sep |= fabsf(T1) > eay + rb1;
+        sep |= fabsf(T2) > eaz + rb2;
+        sep |= fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) > ebx + eax * f00 + eay * f10 + eaz * f20;
+        sep |= fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) > eby + eax * f01 + eay * f11 + eaz * f21;
+        sep |= fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) > ebz + eax * f02 + eay * f12 + eaz * f22;
+        if (kEdgeAxes) {
+            sep |= fabsf(T2 * R[3] - T1 * R[6]) > eay * f20 + eaz * f10 + eby * f02 + ebz * f01;
+            sep |= fabsf(T2 * R[4] - T1 * R[7]) > eay * f21 + eaz * f11 + ebx * f02 + ebz * f00;
+            sep |= fabsf(T2 * R[5] - T1 * R[8]) > eay * f22 + eaz * f12 + ebx * f01 + eby * f00;
+            sep |= fabsf(T0 * R[6] - T2 * R[0]) > eax * f20 + eaz * f00 + eby * f12 + ebz * f11;
+            sep |= fabsf(T0 * R[7] - T2 * R[1]) > eax * f21 + eaz * f01 + ebx * f12 + ebz * f10;
+            sep |= fabsf(T0 * R[8] - T2 * R[2]) > eax * f22 + eaz * f02 + ebx * f11 + eby * f10;
+            sep |= fabsf(T1 * R[0] - T0 * R[3]) > eax * f10 + eay * f00 + eby * f22 + ebz * f21;
+            sep |= fabsf(T1 * R[1] - T0 * R[4]) > eax * f11 + eay * f01 + ebx * f22 + ebz * f20;
+            sep |= fabsf(T1 * R[2] - T0 * R[5]) > eax * f12 + eay * f02 + ebx * f21 + eby * f20;
+        }
+        if (ch) ov1 = !sep; else ov0 = !sep;
+    }
 }
 
 struct V3 { float x, y, z; };
@@ -415,7 +464,7 @@ cc_fk_kernel(const __grid_constant__ Params P)
 }
 
 // ================================================================================================ kernel 2: traversal
-constexpr size_t kWarpSmemBytes = (size_t)kNumSlots * 48 + (size_t)kNumSlots * 4 + (size_t)kStackCap * 8 + (size_t)kTriQCap * 8 +
+constexpr size_t kWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 4 + (size_t)kStackCap * 8 + (size_t)kTriQCap * 8 +
                                   (size_t)kCandCap * 4;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
@@ -425,8 +474,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + wib * kWarpSmemBytes;
-    float* slot_rt = (float*)wbase;                               // [kNumSlots][12]
-    int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 12);    // [kNumSlots] original pair index
+    float* slot_rt = (float*)wbase;                               // [kNumSlots][24]: R|t mapping tree B into tree A, then its inverse
+    int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 24);    // [kNumSlots] original pair index
     uint2* stack = (uint2*)(slot_pair + kNumSlots);               // [kStackCap] {x | slot<<26, y | side<<31}
     uint2* triq = stack + kStackCap;                              // [kTriQCap]  {triA | slot<<26, triB}
     uint32_t* cbuf = (uint32_t*)(triq + kTriQCap);                // [kCandCap]  device pair indices
@@ -521,10 +570,19 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 const int nsl = __popc(cm);
                 if (cand) {
                     const int s = __popc(cm & lt_mask);
-                    float* rt = slot_rt + 12 * s;
+                    float* rt = slot_rt + 24 * s;
 #pragma unroll
                     for (int i = 0; i < 9; ++i) rt[i] = R[i];
                     rt[9] = t[0]; rt[10] = t[1]; rt[11] = t[2];
+                    // inverse: x_B = R^T x_A - R^T t (items whose split node lives in tree B use it, so the two
+                    // children always play the un-transformed role and every lane runs the same code)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) rt[12 + 3 * i + j] = R[3 * j + i];
+                    rt[21] = -(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]);
+                    rt[22] = -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]);
+                    rt[23] = -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2]);
                     slot_pair[s] = orig;
                 }
                 // first items: both leaves -> triangle queue; else split the larger box (PQP.cpp:539-544 compares BV
@@ -570,7 +628,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                                 const float4* tb = P.tris + 3 * (size_t)e.y;
                                 const float4 p0 = __ldg(ta), p1 = __ldg(ta + 1), p2 = __ldg(ta + 2);
                                 const float4 u0 = __ldg(tb), u1 = __ldg(tb + 1), u2 = __ldg(tb + 2);
-                                const float* rt = slot_rt + 12 * s;
+                                const float* rt = slot_rt + 24 * s;
                                 const float r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3], r4 = rt[4], r5 = rt[5], r6 = rt[6], r7 = rt[7], r8 = rt[8];
                                 const float t0 = rt[9], t1 = rt[10], t2 = rt[11];
                                 V3 Q0 = v3(fmaf(r0, u0.x, fmaf(r1, u0.y, fmaf(r2, u0.z, t0))), fmaf(r3, u0.x, fmaf(r4, u0.y, fmaf(r5, u0.z, t1))),
@@ -626,7 +684,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
                         const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
                         const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
-                        const float* rt = slot_rt + 12 * s;
+                        const float* rt = slot_rt + 24 * s + (side ? 12 : 0);      // maps the other node into the children's frame
                         float R[9], t[3];
 #pragma unroll
                         for (int k = 0; k < 9; ++k) R[k] = rt[k];
@@ -634,13 +692,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         if (counters) n_bv += 2;
                         const int lo = __float_as_int(oa.w);
                         const float so = ob.x * ob.x + ob.y * ob.y + ob.z * ob.z;
+                        bool ov0, ov1;
+                        box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
+                                         oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
                             const float4 ca = ch ? c1a : c0a, cb = ch ? c1b : c0b;
-                            const bool ov = side
-                                ? box_overlap(R, t, oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ca.x, ca.y, ca.z, cb.x, cb.y, cb.z)
-                                : box_overlap(R, t, ca.x, ca.y, ca.z, cb.x, cb.y, cb.z, oa.x, oa.y, oa.z, ob.x, ob.y, ob.z);
-                            if (ov) {
+                            if (ch ? ov1 : ov0) {
                                 const int lc = __float_as_int(ca.w);
                                 uint2 out;
                                 bool tq = false;
