@@ -183,6 +183,12 @@ int cc_scene_synchronize(cc_scene* s);
  * separating-axis candidate count as touching.  0 (default) = the reference's strict test (pqp/PQP.cpp:366-367). */
 int cc_scene_set_tri_epsilon(cc_scene* s, double eps);
 
+/* Diagnostics: record, for every configuration of the following batches on this query, how many traversal
+ * iterations (32 box-pair tests each) the device spent on it; read the last batch's trace back with
+ * cc_query_get_work_trace (synchronises).  Used by the load-balance studies in profiles/. */
+int cc_query_trace_work(cc_query* q, int enabled);
+int cc_query_get_work_trace(cc_query* q, uint32_t* out_iterations, int n);
+
 /* ---- statistics (PQP_CollideResult::NumBVTests/NumTriTests analogue, pqp/PQP.cpp:489,500) */
 int cc_scene_set_counters(cc_scene* s, int enabled);
 int cc_scene_get_stats(const cc_scene* s, cc_stats* out);

@@ -47,7 +47,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_body_set_attached", "cc_body_set_kinematics", "cc_body_set_dof_values", "cc_body_set_nonadjacent_pairs",
            "cc_scene_commit", "cc_query_create", "cc_query_create_pairs", "cc_query_destroy", "cc_query_get_info",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
-           "cc_scene_synchronize", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats"]
+           "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats"]
 
 _lib = None
 
@@ -84,6 +84,8 @@ def load_library():
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
+    lib.cc_query_trace_work.argtypes = [vp, ci]
+    lib.cc_query_get_work_trace.argtypes = [vp, vp, ci]
     lib.cc_scene_set_tri_epsilon.argtypes = [vp, cd]
     lib.cc_scene_set_counters.argtypes = [vp, ci]
     lib.cc_scene_get_stats.argtypes = [vp, ctypes.POINTER(cc_stats)]
@@ -161,6 +163,14 @@ class BoundQuery(object):
         n = q.shape[0]
         out = np.zeros((n, self.info.nlinks, 8), dtype=np.float64)
         self.checker._ck(self.lib.cc_fk_batch(self.handle, _ptr(q), n, _ptr(out)))
+        return out
+
+    def trace_work(self, enabled=True):
+        self.checker._ck(self.lib.cc_query_trace_work(self.handle, 1 if enabled else 0))
+
+    def work_trace(self, n):
+        out = np.zeros(n, dtype=np.uint32)
+        self.checker._ck(self.lib.cc_query_get_work_trace(self.handle, _ptr(out), n))
         return out
 
     def check_device(self, d_q_ptr, n, flags, d_verdict_ptr, d_fe_ptr, d_fs_ptr, d_mask_ptr=0, stream=0):

@@ -89,6 +89,7 @@ struct Params {
     int32_t* first_self;
     uint32_t* pair_mask;
     double* fk_out;             // [n][nq][8] or NULL
+    uint32_t* work_out;         // [n] or NULL: traversal iterations spent on each configuration (diagnostics)
     // per-chunk scratch
     float* xf32;                // [cap][nq][12]
     float* aabb;                // [nq][6][cap]
@@ -457,6 +458,7 @@ cc_fk_kernel(const __grid_constant__ Params P)
         if (P.verdict) P.verdict[c] = v;
         if (P.first_env) P.first_env[c] = (v & 1u) ? P.hoisted_first_env : -1;
         if (P.first_self) P.first_self[c] = (v & 2u) ? P.hoisted_first_self : -1;
+        if (P.work_out) P.work_out[c] = 0u;
     } else {
         const int pos = atomicAdd(&P.counters[0], 1);
         P.queue[pos] = c;
@@ -503,6 +505,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         int best_env = P.hoisted_first_env, best_self = P.hoisted_first_self;
         uint32_t slot_hit = 0;
         bool failed = false;
+        uint32_t iters = 0;
 
         for (int w0 = 0; w0 < P.cwords && !failed; w0 += 32) {
             const uint32_t myword = (w0 + lane < P.cwords) ? crow[w0 + lane] : 0u;
@@ -664,6 +667,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     }
                     // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
                     const int n = sp < 32 ? sp : 32;
+                    ++iters;
                     bool valid = lane < n;
                     uint2 it = make_uint2(0u, 0u);
                     if (valid) it = stack[sp - 1 - lane];
@@ -789,6 +793,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             if (P.verdict) P.verdict[c] = v;
             if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
             if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
+            if (P.work_out) P.work_out[c] = iters;
         }
         __syncwarp();
     }

@@ -271,6 +271,9 @@ struct cc_query {
     double base[8];
     double center[3];
     std::vector<double> cur_active;          // current values of the active DOFs
+    DevBuf<uint32_t> d_work;                 // optional per-configuration work trace (cc_query_get_work_trace)
+    bool trace_work = false;
+    int work_n = 0;
     // staging for the host-buffer API
     DevBuf<double> d_q, d_fk;
     DevBuf<uint32_t> d_verdict, d_mask;
@@ -351,6 +354,7 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
         if (per_sm < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
         S->trav_blocks_per_sm = per_sm;
     }
+    if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     CC_CUDA(cudaEventRecord(S->ev0, st));
     for (int off = 0; off < n; off += chunk) {
         const int m = std::min(chunk, n - off);
@@ -361,6 +365,7 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
         P.first_self = d_fs ? d_fs + off : nullptr;
         P.pair_mask = d_mask ? d_mask + (size_t)off * Q->mask_words : nullptr;
         P.fk_out = d_fk ? d_fk + (size_t)off * Q->nq * 8 : nullptr;
+        P.work_out = (Q->trace_work && !fk_only) ? Q->d_work.p + off : nullptr;
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters.p, 0, 2 * sizeof(int32_t), st));
         ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
         CC_CUDA(cudaGetLastError());
@@ -920,6 +925,22 @@ int cc_query_get_pairs(const cc_query* q, int32_t* out)
 {
     if (!q || !out) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->quads.empty()) memcpy(out, q->quads.data(), q->quads.size() * sizeof(int32_t));
+    return CC_OK;
+}
+
+int cc_query_trace_work(cc_query* q, int enabled)
+{
+    if (!q) return fail(CC_ERR_INVALID, "query is NULL");
+    q->trace_work = enabled != 0;
+    return CC_OK;
+}
+
+int cc_query_get_work_trace(cc_query* q, uint32_t* out, int n)
+{
+    if (!q || !out || n < 0 || n > q->work_n) return fail(CC_ERR_INVALID, "bad arguments");
+    CC_CUDA(cudaSetDevice(q->scene->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    if (n) CC_CUDA(cudaMemcpy(out, q->d_work.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return CC_OK;
 }
 

@@ -24,3 +24,15 @@ for name, flags in (("env+self", BATCH_ENV | BATCH_SELF), ("env", BATCH_ENV), ("
         print("%-20s counters=%d kernel %.3f ms  bv/config %.1f  tri/config %.2f  colliding %.3f" % (
             name, counters, s1["last_kernel_ms"], (s1["bv_tests"] - s0["bv_tests"]) / 3.0 / n,
             (s1["tri_tests"] - s0["tri_tests"]) / 3.0 / n, (v != 0).mean()))
+
+# per-configuration work distribution (traversal iterations): what the tail of the persistent kernel is made of
+bq.trace_work(True)
+cc.SetCounters(0)
+v, fe, fs, _ = bq.check(q, BATCH_ENV | BATCH_SELF)
+w = bq.work_trace(n).astype(np.int64)
+bq.trace_work(False)
+srt = np.sort(w)[::-1]
+print("work trace: total iterations %d, mean %.1f, zero-work configs %.3f" % (w.sum(), w.mean(), (w == 0).mean()))
+print("  percentiles 50/90/99/99.9/max:", [int(np.percentile(w, p)) for p in (50, 90, 99, 99.9)], int(w.max()))
+print("  top 10:", srt[:10].tolist(), " share of top 0.1%%: %.3f" % (srt[:max(1, n // 1000)].sum() / max(1, w.sum())))
+print("  heaviest configs collide?", [(int(i), int(v[i])) for i in np.argsort(-w)[:6]])
