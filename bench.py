@@ -33,27 +33,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (scene fixture, n configs per step per GPU, seed, description)
-    "wam_lab1_100k": ("lab1", 100000, 1,
+    # name: (scene fixture, n configs per step per GPU, seed, active manipulator or None = all DOFs, description)
+    "pr2_pr2test1_1m": ("pr2test1", 1000000, 2, "rightarm_torso",
+                        "PR2 (robots/pr2-beta-static.zae: 88 links, 39 DOF + 48 passive joints, 51.8k tris) in data/pr2test1.env.xml "
+                        "(9 bodies): 1M uniform-random right-arm(7)+torso(1) configs, the other DOFs at the load pose, "
+                        "CheckCollision + CheckSelfCollision (BASELINE.json configs[1])"),
+    "wam_lab1_100k": ("lab1", 100000, 1, None,
                       "Barrett WAM (11 DOF, 18 links, 31.0k tris) in data/lab1.env.xml (14 bodies, 16.5k tris): 100k uniform-random "
-                      "DOF configs, CheckCollision + CheckSelfCollision (BASELINE.json configs[0]; configs[1] PR2 needs the COLLADA "
-                      "reader, SURVEY.md §8f-1)"),
+                      "DOF configs, CheckCollision + CheckSelfCollision (BASELINE.json configs[0])"),
+    "hironx_table_1m": ("hironxtable", 1000000, 4, None,
+                        "HIRO-NX dual arm (robots/kawada-hironx.zae: 24 links, 23 DOF, 24.1k tris) + data/ikeatable.kinbody.xml: 1M "
+                        "uniform-random configs over all DOFs, self-collision dominated (BASELINE.json configs[3])"),
 }
+DEFAULT_WORKLOAD = "pr2_pr2test1_1m"
 METRIC = "collision-checked configs/sec (FK+env+self)"
 UNIT = "configs/s"
 
 
 def load_world(workload):
     from openrave_b200.environment import Environment
-    scene, n, seed, _ = WORKLOADS[workload]
+    scene, n, seed, manip, _ = WORKLOADS[workload]
     env = Environment()
     env.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
     robot = env.GetRobots()[0]
+    if manip is not None:
+        robot.SetActiveDOFs([m for m in robot.GetManipulators() if m.GetName() == manip][0].GetArmIndices())
     return env, robot, n, seed
 
 
 def sample(robot, n, seed):
-    lo, hi = robot.GetDOFLimits()
+    """RobotConfigurationSampler semantics over the robot's ACTIVE DOFs: lower + u*(upper-lower), u ~ U[0,1)."""
+    lo, hi = robot.GetActiveDOFLimits()
     lo, hi = np.array(lo), np.array(hi)
     rng = np.random.default_rng(seed)
     return lo + rng.random((n, len(lo))) * (hi - lo)
@@ -154,7 +164,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "description": WORKLOADS[workload][3], "configs_per_step": m,
+            "config": {"workload": workload, "description": WORKLOADS[workload][4], "configs_per_step": m,
                        "note": "bounded sample of the %d-config batch, %d worker processes" % (n, workers)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
                              "sample": "%d configs per step over %d processes (private scene each)" % (m, workers)},
@@ -171,7 +181,7 @@ def _ref_worker_init(workload, kind):
     env, robot, _, _ = load_world(workload)
     orc = oracle.OracleChecker(env, kind)
     orc.InitEnvironment()
-    orc.time_batch(robot, np.zeros((1, robot.GetDOF())))   # builds models + pair list before the timed region
+    orc.time_batch(robot, np.zeros((1, robot.GetActiveDOF())))   # builds models + pair list before the timed region
     _REF_STATE.update(env=env, robot=robot, orc=orc)
 
 
@@ -186,7 +196,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="wam_lab1_100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -209,7 +219,7 @@ def main():
     W = max(args.warmup, 3)
 
     env, robot, n, seed = load_world(args.workload)
-    ndof = robot.GetDOF()
+    ndof = robot.GetActiveDOF()
     cc = CudaCollisionChecker(env, local_rank)
     env.SetCollisionChecker(cc)
     bq = cc.bind(robot)
@@ -293,7 +303,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "configs_per_step_per_gpu": n,
+                "config": {"workload": args.workload, "description": WORKLOADS[args.workload][4], "configs_per_step_per_gpu": n,
                            "ndof": ndof, "pairs_env": bq.info.npairs_env, "pairs_self": bq.info.npairs_self,
                            "pairs_hoisted": bq.info.npairs_hoisted, "bvh_nodes": bq.info.total_nodes, "tris": bq.info.total_tris,
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",

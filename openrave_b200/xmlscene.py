@@ -108,6 +108,11 @@ class SceneLoader(object):
         path = self.find_file(filename, None)
         if path is None:
             raise IOError("cannot find %s" % filename)
+        if os.path.splitext(path)[1].lower() in (".zae", ".dae"):
+            from .colladascene import load_collada_into
+            body = Robot(env) if robot else KinBody(env)
+            body.uri = path
+            return load_collada_into(body, path)
         root = self._parse(path)
         body = Robot(env) if (robot or root.tag == "robot") else KinBody(env)
         body.uri = path
@@ -138,6 +143,12 @@ class SceneLoader(object):
         path = self.find_file(fileattr, pdir)
         if path is None:
             raise IOError("cannot find %s (from %s)" % (fileattr, pdir))
+        if os.path.splitext(path)[1].lower() in (".zae", ".dae"):
+            from .colladascene import load_collada_into       # RaveParseColladaURI (xmlreaders-core.cpp:2076-2092)
+            if not body.uri:
+                body.uri = path
+            load_collada_into(body, path)
+            return
         root = self._parse(path)
         if not body.uri:
             body.uri = path

@@ -34,7 +34,7 @@ def main():
     if not os.path.isdir(os.path.join(tmp, "models")):
         extract_models(tmp)
     os.makedirs(OUT, exist_ok=True)
-    for scene in ("lab1", "wamtest1"):
+    for scene in ("lab1", "wamtest1", "pr2test1", "hironxtable"):
         env = Environment(data_dirs=[os.path.join(REF, "src"), tmp])
         try:
             env.Load("data/%s.env.xml" % scene)
