@@ -1,0 +1,214 @@
+"""Edge discretisation: the batched replacement of `DynamicsCollisionConstraint::Check` (linear branch).
+
+The reference checks an edge q0 -> q1 one sample at a time (src/libopenrave/planningutils.cpp:2586-3629):
+  * `bCheckEnd` intervals test q1 FIRST (:2692-2708); then q0 when the interval is closed at the start (:2809-2826);
+  * the number of steps is max over DOFs of int(|dq_i| / resolution_i + 0.99) (:2772-2786), dq from `_diffstatefn`
+    (circular DOFs wrap, robot.cpp:1639-1662);
+  * samples f = start .. numSteps-1 are produced by `_neighstatefn` = AddStatesWithLimitCheck (planner.cpp:88-112, 687) from
+    the previous sample with the delta re-derived from q0 + (f+1) dQ (:3438-3452);
+  * each sample runs `_SetAndCheckState` -> env collision, then self collision (:2317-2368, 2523-2548), optionally again at
+    +/- perturbation * resolution (CFO_CheckWithPerturbation, :2344-2366), and the first failure returns.
+With the default neighbour function the sample sequence does not depend on any collision result, so the whole edge (or
+many edges) is generated up front and sent through `CheckCollisionBatch` in one call; the return code, the failing
+sample and `_fTimeWhenInvalid` are then those of the first failing sample in the reference's order.
+`Check` is that batched path; `CheckSerial` is the literal per-sample loop over any CollisionCheckerBase-shaped checker
+and exists so the two can be compared (tier V6).
+"""
+import math
+
+import numpy as np
+
+IT_Open, IT_OpenStart, IT_OpenEnd, IT_Closed = 0, 1, 2, 3                 # planner.h IntervalType
+CFO_CheckEnvCollisions, CFO_CheckSelfCollisions = 1, 2                    # planner.h:32-33
+CFO_CheckWithPerturbation = 0x00010000                                    # planner.h:37
+CFO_FillCheckedConfiguration = 0x00020000                                 # planner.h:38
+CFO_StateSettingError = 0x80000000                                        # planner.h:44
+G_EPSILON_JOINT_LIMIT = 1e-7                                               # g_fEpsilonJointLimit
+
+
+class ConstraintFilterReturn(object):
+    """planner.h:102-130."""
+
+    def __init__(self):
+        self.Clear()
+
+    def Clear(self):
+        self._configurations = []
+        self._configurationtimes = []
+        self._invalidvalues = []
+        self._fTimeWhenInvalid = 0.0
+        self._returncode = 0
+
+
+class DynamicsCollisionConstraint(object):
+    """planningutils.h DynamicsCollisionConstraint for one robot over its active DOFs (PlannerParameters::SetRobotActiveJoints,
+    planner.cpp:636-697): limits, resolutions and the circular mask come from the robot."""
+
+    def __init__(self, robot, checker, filtermask=CFO_CheckEnvCollisions | CFO_CheckSelfCollisions | CFO_CheckWithPerturbation |
+                 CFO_FillCheckedConfiguration, perturbation=0.1):
+        self.robot = robot
+        self.checker = checker
+        self.filtermask = filtermask
+        self.perturbation = perturbation                                   # planningutils.cpp:2298 default
+        self.active = robot.GetActiveDOFIndices()
+        joints = [robot.joints[d] for d in self.active]
+        self.lower = np.array([j.lower for j in joints])
+        self.upper = np.array([j.upper for j in joints])
+        self.resolution = np.array([j.resolution for j in joints])
+        self.circular = np.array([bool(j.circular) for j in joints])
+
+    # ---- parameter functions
+    def diffstate(self, q1, q0):
+        d = np.array(q1, dtype=np.float64) - np.array(q0, dtype=np.float64)
+        if self.circular.any():                                            # Joint::SubtractValue -> NormalizeCircularAngle
+            w = d[self.circular]
+            w = np.where(w < -math.pi, w + 2 * math.pi * np.ceil((-math.pi - w) / (2 * math.pi)), w)
+            w = np.where(w >= math.pi, w - 2 * math.pi * np.floor((w + math.pi) / (2 * math.pi)), w)
+            d[self.circular] = w
+        return d
+
+    def neighstate(self, q, delta):
+        """AddStatesWithLimitCheck (planner.cpp:88-112): returns (q', deviated)."""
+        q = q + delta
+        dev = bool(((q > self.upper + G_EPSILON_JOINT_LIMIT) | (q < self.lower - G_EPSILON_JOINT_LIMIT)).any())
+        return np.minimum(np.maximum(q, self.lower), self.upper), dev
+
+    def num_steps(self, dQ):
+        steps = np.where(self.resolution != 0, (np.abs(dQ) / np.where(self.resolution != 0, self.resolution, 1.0) + 0.99).astype(np.int64),
+                         (np.abs(dQ) * 100).astype(np.int64))
+        return int(steps.max()) if len(steps) else 0, int(steps.sum())
+
+    # ---- the sample sequence of one edge, in the order the reference checks it
+    def edge_samples(self, q0, q1, interval=IT_Closed):
+        """Returns (samples [m, ndof], times [m], kinds [m]) with kinds 'end' | 'start' | 'step'."""
+        q0 = np.array(q0, dtype=np.float64)
+        q1 = np.array(q1, dtype=np.float64)
+        start = 1 if interval in (IT_Open, IT_OpenStart) else 0
+        check_end = interval in (IT_OpenStart, IT_Closed)
+        out, times, kinds = [], [], []
+        if check_end:
+            out.append(q1.copy()); times.append(1.0); kinds.append('end')
+        dQ = self.diffstate(q1, q0)
+        nsteps, total = self.num_steps(dQ)
+        if total == 0 and start > 0:
+            return np.array(out).reshape(-1, len(q0)), times, kinds
+        if start == 0:
+            out.append(q0.copy()); times.append(0.0); kinds.append('start')
+            start = 1
+        if nsteps == 0:
+            return np.array(out).reshape(-1, len(q0)), times, kinds
+        fisteps = 1.0 / nsteps
+        dQ = dQ * fisteps
+        cur, dev = self.neighstate(q0.copy(), dQ)
+        if dev:
+            raise NotImplementedError("edge leaves the joint limits (NSS_SuccessfulWithDeviation sub-stepping, planningutils.cpp:3454-3519)")
+        for f in range(start, nsteps):
+            out.append(cur.copy()); times.append(f * fisteps); kinds.append('step')
+            prev = q0 + (f + 1) * dQ - cur
+            big = np.abs(prev) > self.resolution
+            if big.any():
+                prev = prev * float((self.resolution[big] / np.abs(prev[big])).min())
+            cur, dev = self.neighstate(cur, prev)
+            if dev:
+                raise NotImplementedError("edge leaves the joint limits (NSS_SuccessfulWithDeviation sub-stepping)")
+        if float(np.sqrt(((cur - q1) ** 2).sum())) > 1e-7:                  # :3524-3541 (SimpleDistanceMetric with unit weights)
+            out.append(cur.copy()); times.append(1.0); kinds.append('step')
+        return np.array(out).reshape(-1, len(q0)), times, kinds
+
+    def _perturbed(self, samples):
+        """CFO_CheckWithPerturbation (:2344-2366): every state is also checked at +/- perturbation*resolution, clamped."""
+        up = np.minimum(np.maximum(samples + self.perturbation * self.resolution, self.lower), self.upper)
+        dn = np.minimum(np.maximum(samples - self.perturbation * self.resolution, self.lower), self.upper)
+        return np.stack([samples, up, dn], axis=1).reshape(-1, samples.shape[1])
+
+    @staticmethod
+    def _code(v):
+        return CFO_CheckEnvCollisions if (v & 1) else (CFO_CheckSelfCollisions if (v & 2) else 0)
+
+    def _finish(self, samples, times, codes, options, filterreturn):
+        """First failing sample in reference order -> return code + ConstraintFilterReturn."""
+        bad = np.nonzero(codes)[0]
+        first = int(bad[0]) if len(bad) else -1
+        if filterreturn is not None:
+            filterreturn.Clear()
+            if first >= 0:
+                filterreturn._returncode = int(codes[first])
+                filterreturn._invalidvalues = samples[first].tolist()
+                filterreturn._fTimeWhenInvalid = float(times[first])
+            if options & CFO_FillCheckedConfiguration:
+                upto = len(samples) if first < 0 else first + 1
+                order = list(range(upto))
+                # time order: the end sample (checked first) is reported last when the whole edge is free (:3613-3624)
+                if first < 0 and len(order) and times[0] == 1.0 and len(order) > 1:
+                    order = order[1:] + [0]
+                filterreturn._configurations = [samples[i].tolist() for i in order]
+                filterreturn._configurationtimes = [float(times[i]) for i in order]
+        return int(codes[first]) if first >= 0 else 0
+
+    # ---- batched path (GPU): one call per edge, or one call for many edges
+    def Check(self, q0, q1, interval=IT_Closed, options=0xffff | CFO_CheckWithPerturbation | CFO_FillCheckedConfiguration,
+              filterreturn=None):
+        return self.CheckMany([(q0, q1)], interval, options, [filterreturn])[0]
+
+    def CheckMany(self, edges, interval=IT_Closed, options=0xffff | CFO_CheckWithPerturbation | CFO_FillCheckedConfiguration,
+                  filterreturns=None):
+        """All samples of all edges in ONE CheckCollisionBatch call (speculative: no early exit inside the batch)."""
+        from .checker import BATCH_ENV, BATCH_SELF
+        opts = options & self.filtermask
+        flags = (BATCH_ENV if opts & CFO_CheckEnvCollisions else 0) | (BATCH_SELF if opts & CFO_CheckSelfCollisions else 0)
+        per_edge, blocks = [], []
+        mult = 3 if (opts & CFO_CheckWithPerturbation) and self.perturbation > 0 else 1
+        for q0, q1 in edges:
+            s, t, _ = self.edge_samples(q0, q1, interval)
+            per_edge.append((s, t))
+            blocks.append(self._perturbed(s) if mult == 3 and len(s) else s)
+        allq = np.concatenate(blocks) if blocks else np.zeros((0, len(self.active)))
+        if len(allq):
+            verdict = self.checker.CheckCollisionBatch(self.robot, allq, flags=flags, active=self.active)["verdict"]
+        else:
+            verdict = np.zeros(0, dtype=np.uint32)
+        rets, pos = [], 0
+        for k, (s, t) in enumerate(per_edge):
+            m = len(s)
+            v = verdict[pos:pos + m * mult].reshape(m, mult) if m else np.zeros((0, mult), dtype=np.uint32)
+            pos += m * mult
+            codes = np.zeros(m, dtype=np.int64)
+            for i in range(m):
+                for c in range(mult):                                    # state, then +perturbation, then -perturbation
+                    code = self._code(int(v[i, c]))
+                    if code:
+                        codes[i] = code
+                        break
+            fr = filterreturns[k] if filterreturns is not None else None
+            rets.append(self._finish(s, t, codes, options, fr))
+        return rets
+
+    # ---- the literal per-sample loop (any CollisionCheckerBase-shaped checker; used as the comparison arm)
+    def CheckSerial(self, q0, q1, interval=IT_Closed, options=0xffff | CFO_CheckWithPerturbation | CFO_FillCheckedConfiguration,
+                    filterreturn=None, env=None):
+        opts = options & self.filtermask
+        env = env or self.robot.GetEnv()
+        s, t, _ = self.edge_samples(q0, q1, interval)
+        saved = self.robot.GetDOFValues()
+        codes = np.zeros(len(s), dtype=np.int64)
+        try:
+            for i in range(len(s)):
+                states = self._perturbed(s[i:i + 1]) if (opts & CFO_CheckWithPerturbation) and self.perturbation > 0 else s[i:i + 1]
+                for q in states:
+                    self.robot.SetDOFValues(q.tolist(), self.active)
+                    if (opts & CFO_CheckEnvCollisions) and env.CheckCollision(self.robot):
+                        codes[i] = CFO_CheckEnvCollisions
+                        break
+                    if (opts & CFO_CheckSelfCollisions) and self.robot.CheckSelfCollision():
+                        codes[i] = CFO_CheckSelfCollisions
+                        break
+                if codes[i]:
+                    break                                                  # the reference returns at the first failure
+        finally:
+            self.robot.SetDOFValues(saved)
+        return self._finish(s, t, codes, options, filterreturn)
+
+
+def CheckPathAllConstraints(constraint, q0, q1, interval=IT_Closed, options=0xffff, filterreturn=None):
+    """PlannerParameters::CheckPathAllConstraints (planner.h:373-379) for positions-only edges."""
+    return constraint.Check(q0, q1, interval, options, filterreturn)

@@ -1,0 +1,681 @@
+// cudacollision.cpp — OpenRAVE plugin `cudacollision`: a CollisionCheckerBase whose every verdict comes from
+// libcudacollision.so (include/cudacollision.h), i.e. from hand-written sm_100a CUDA kernels on a B200.
+//
+//   env->SetCollisionChecker(RaveCreateCollisionChecker(env, "cudacollision"));          // normal plugin path
+//   boost::dynamic_pointer_cast<CudaCollisionChecker>(env->GetCollisionChecker())->CheckCollisionBatch(...)
+//   checker->SendCommand(sout, sinput)  with  "CheckBatch <robot> <n> <flags> <ptr q> <ptr verdict> <ptr firstpairs>"
+//
+// Built against the reference headers (include/openrave/*.h) inside an OpenRAVE source tree or against an installed
+// OpenRAVE (CMakeLists.txt next to this file).  It cannot be compiled in the B200 build container of this repository:
+// libopenrave needs Boost >= 1.67, libxml2 and rapidjson, none of which are present there; the same
+// object model is exercised there through the Python twin openrave_b200/checker.py, which makes the identical
+// sequence of C-ABI calls.
+//
+// Semantics kept (plugins/pqprave/collisionPQP.h): true = collision; report->Reset(options) first (:174-176); every
+// colliding (link1,link2) appended in env-body / link / link order with minDistance = 0 (:476-485, :586-587); first
+// hit only for self collision (:364-386); disabled links, attached bodies, excluded bodies/links skipped (:454-471,
+// :555); CO_ActiveDOFs restricts links and self pairs (:373-377, :710-735); ray queries throw like pqprave's
+// (:331-356); single-state queries read the bodies' CURRENT link transforms and never run FK (:438-447).
+#include <openrave/openrave.h>
+#include <openrave/plugin.h>
+
+#include <boost/bind/bind.hpp>
+#include <boost/lexical_cast.hpp>
+#include <boost/make_shared.hpp>
+
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "cudacollision.h"
+
+using namespace OpenRAVE;
+
+namespace {
+
+// "a*x+b" family -> (a, b); returns false when the equation is not affine in exactly one joint variable.
+// Mimic equations are fparser strings (kinbody.cpp:2308-2386); the WAM hand uses "JF1/3+0.8727", the PR2 gripper "0+x".
+bool ParseAffineMimic(const std::string& eq, const std::string& var, double& a, double& b)
+{
+    // evaluate the expression symbolically as (coef, const) pairs with a tiny recursive-descent parser
+    struct P {
+        const std::string& s; const std::string& var; size_t i; bool ok;
+        P(const std::string& s_, const std::string& v_) : s(s_), var(v_), i(0), ok(true) {}
+        void ws() { while (i < s.size() && isspace((unsigned char)s[i])) ++i; }
+        typedef std::pair<double, double> L;     // coef*x + const
+        L atom() {
+            ws();
+            if (i < s.size() && s[i] == '(') { ++i; L v = expr(); ws(); if (i < s.size() && s[i] == ')') ++i; else ok = false; return v; }
+            if (i < s.size() && (s[i] == '-' || s[i] == '+')) { bool neg = s[i] == '-'; ++i; L v = atom(); return neg ? L(-v.first, -v.second) : v; }
+            if (s.compare(i, var.size(), var) == 0) { i += var.size(); return L(1.0, 0.0); }
+            size_t used = 0;
+            double v = 0;
+            try { v = std::stod(s.substr(i), &used); } catch (...) { ok = false; return L(0, 0); }
+            i += used;
+            return L(0.0, v);
+        }
+        L term() {
+            L v = atom();
+            for (;;) {
+                ws();
+                if (i >= s.size() || (s[i] != '*' && s[i] != '/')) return v;
+                char op = s[i++];
+                L w = atom();
+                if (op == '*') {
+                    if (v.first != 0 && w.first != 0) { ok = false; return v; }
+                    v = L(v.first * w.second + w.first * v.second, v.second * w.second);
+                } else {
+                    if (w.first != 0 || w.second == 0) { ok = false; return v; }
+                    v = L(v.first / w.second, v.second / w.second);
+                }
+            }
+        }
+        L expr() {
+            L v = term();
+            for (;;) {
+                ws();
+                if (i >= s.size() || (s[i] != '+' && s[i] != '-')) return v;
+                char op = s[i++];
+                L w = term();
+                v = op == '+' ? L(v.first + w.first, v.second + w.second) : L(v.first - w.first, v.second - w.second);
+            }
+        }
+    } p(eq, var);
+    P::L r = p.expr();
+    p.ws();
+    if (!p.ok || p.i != eq.size()) return false;
+    a = r.first; b = r.second;
+    return true;
+}
+
+inline void PackTransform(const Transform& t, double* o)
+{
+    o[0] = t.rot.x; o[1] = t.rot.y; o[2] = t.rot.z; o[3] = t.rot.w;       // RaveVector: x holds the scalar part (geometry.h:524)
+    o[4] = t.trans.x; o[5] = t.trans.y; o[6] = t.trans.z; o[7] = 0;
+}
+
+}  // namespace
+
+class CudaCollisionChecker : public CollisionCheckerBase
+{
+    struct BodyInfo : public UserData {
+        KinBodyWeakPtr body;
+        int id;                          // cc body id
+        int transformStamp;              // KinBody::GetUpdateStamp at the last pose upload
+        bool kinematicsDirty, pairsDirty;
+        UserDataPtr cbGeometry, cbEnable, cbAttached, cbJoints, cbActive;
+        BodyInfo() : id(-1), transformStamp(-1), kinematicsDirty(true), pairsDirty(true) {}
+    };
+    typedef boost::shared_ptr<BodyInfo> BodyInfoPtr;
+
+    struct QueryKey {
+        int body; std::vector<int> active; int options;
+        bool operator<(const QueryKey& r) const {
+            if (body != r.body) return body < r.body;
+            if (options != r.options) return options < r.options;
+            return active < r.active;
+        }
+    };
+
+public:
+    CudaCollisionChecker(EnvironmentBasePtr penv, std::istream& sinput) : CollisionCheckerBase(penv), _scene(NULL), _options(0), _device(0)
+    {
+        __description = ":Interface Author: cudacollision\n\nBatched collision checker for NVIDIA B200 (sm_100a): forward kinematics, "
+                        "broadphase, BVH traversal and triangle tests run on the GPU for N configurations per call.";
+        sinput >> _device;
+        _userdatakey = std::string("cudacollision") + boost::lexical_cast<std::string>(this);
+        _Check(cc_scene_create(_device, &_scene));
+        RegisterCommand("CheckBatch", boost::bind(&CudaCollisionChecker::_CheckBatchCommand, this, boost::placeholders::_1, boost::placeholders::_2),
+                        "CheckBatch robotname n flags qptr verdictptr firstpairsptr : batched FK + env + self check of n active-DOF "
+                        "vectors (row-major doubles at qptr); writes uint32 verdicts (bit0 env, bit1 self) and int32[n][4] "
+                        "{env link, env other body index, env other link, self pair packed i|j<<16} (-1 = none)");
+        RegisterCommand("SetTriangleEpsilon", boost::bind(&CudaCollisionChecker::_SetTriEpsCommand, this, boost::placeholders::_1, boost::placeholders::_2),
+                        "conservative margin (m) of the FP32 triangle test, default 0 = the reference's strict test");
+    }
+
+    virtual ~CudaCollisionChecker()
+    {
+        DestroyEnvironment();
+        if (_scene) cc_scene_destroy(_scene);
+    }
+
+    // ------------------------------------------------------------------------------------------ options
+    virtual bool SetCollisionOptions(int options)
+    {
+        if (options & (CO_Distance | CO_UseTolerance | CO_Contacts | CO_RayAnyHit)) return false;   // not provided (cf. fclcollision.cpp:171-180)
+        if (options != _options) { _options = options; _DropQueries(); }
+        return true;
+    }
+    virtual int GetCollisionOptions() const { return _options; }
+    virtual void SetTolerance(dReal) {}
+
+    // ------------------------------------------------------------------------------------------ bodies
+    virtual bool InitEnvironment()
+    {
+        std::vector<KinBodyPtr> vbodies;
+        GetEnv()->GetBodies(vbodies);
+        FOREACHC(it, vbodies) { _InitKinBody(*it); }
+        return true;
+    }
+
+    virtual void DestroyEnvironment()
+    {
+        _DropQueries();
+        std::vector<KinBodyPtr> vbodies;
+        GetEnv()->GetBodies(vbodies);
+        FOREACHC(it, vbodies) { RemoveKinBody(*it); }
+    }
+
+    virtual bool InitKinBody(KinBodyPtr pbody) { return !!_InitKinBody(pbody); }
+
+    virtual void RemoveKinBody(KinBodyPtr pbody)
+    {
+        if (!pbody) return;
+        BodyInfoPtr pinfo = boost::dynamic_pointer_cast<BodyInfo>(pbody->GetUserData(_userdatakey));
+        if (!!pinfo) {
+            cc_scene_remove_body(_scene, pinfo->id);
+            _byid.erase(pinfo->id);
+            pbody->RemoveUserData(_userdatakey);
+            _DropQueries();
+        }
+    }
+
+    /// environment clones create a fresh instance through the plugin and then call Clone (environment-core.h:3657-3662,
+    /// pattern fclcollision.cpp:156-169): copy the options, the scene is rebuilt lazily from the cloned environment
+    virtual void Clone(InterfaceBaseConstPtr preference, int cloningoptions)
+    {
+        CollisionCheckerBase::Clone(preference, cloningoptions);
+        boost::shared_ptr<CudaCollisionChecker const> r = boost::dynamic_pointer_cast<CudaCollisionChecker const>(preference);
+        if (!!r) { _options = r->_options; _DropQueries(); }
+    }
+
+    // ------------------------------------------------------------------------------------------ the batched entry (new)
+    /// q: [n][ndof] active-DOF values of `probot` (RobotBase::SetActiveDOFValues semantics, robot.cpp:1193-1225); the other
+    /// DOFs keep their current values.  flags: CC_BATCH_ENV | CC_BATCH_SELF.  firstpairs may be NULL.
+    /// Replaces the per-sample SetDOFValues + CheckCollision + CheckSelfCollision loop of
+    /// DynamicsCollisionConstraint::Check (planningutils.cpp:3405-3526).
+    int CheckCollisionBatch(RobotBaseConstPtr probot, const dReal* q, int n, int ndof, uint32_t* verdict, int32_t* firstpairs, int flags)
+    {
+        if (probot->GetAffineDOF() != 0) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: affine active DOFs are not batched yet", ORE_NotImplemented);
+        if (ndof != (int)probot->GetActiveDOFIndices().size()) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ndof != active DOF count", ORE_InvalidArguments);
+        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices());
+        std::vector<int32_t> fe(firstpairs ? n : 0), fs(firstpairs ? n : 0);
+        _Check(cc_check_batch(query, q, n, flags, verdict, firstpairs ? fe.data() : NULL, firstpairs ? fs.data() : NULL, NULL));
+        if (firstpairs) {
+            cc_query_info info;
+            cc_query_get_info(query, &info);
+            std::vector<int32_t> quads(4 * (size_t)std::max(1, info.npairs_env + info.npairs_self));
+            cc_query_get_pairs(query, quads.data());
+            for (int i = 0; i < n; ++i) {
+                int32_t* o = firstpairs + 4 * (size_t)i;
+                o[0] = o[1] = o[2] = o[3] = -1;
+                if (fe[i] >= 0) { o[0] = quads[4 * fe[i]]; o[1] = _EnvIndexOf(quads[4 * fe[i] + 1]); o[2] = quads[4 * fe[i] + 2]; }
+                if (fs[i] >= 0) o[3] = quads[4 * fs[i]] | (quads[4 * fs[i] + 2] << 16);
+            }
+        }
+        return 0;
+    }
+
+    // ------------------------------------------------------------------------------------------ single-state overloads
+    virtual bool CheckCollision(KinBodyConstPtr pbody, CollisionReportPtr report = CollisionReportPtr())
+    {
+        std::vector<KinBodyConstPtr> vbodyexcluded;
+        std::vector<KinBody::LinkConstPtr> vlinkexcluded;
+        return CheckCollision(pbody, vbodyexcluded, vlinkexcluded, report);
+    }
+
+    virtual bool CheckCollision(KinBodyConstPtr pbody, const std::vector<KinBodyConstPtr>& vbodyexcluded,
+                                const std::vector<KinBody::LinkConstPtr>& vlinkexcluded, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        // pqprave checks every body attached to pbody (collisionPQP.h:320-327) against every non-attached body
+        std::set<KinBodyConstPtr> attached;
+        pbody->GetAttached(attached);
+        bool bcollision = false;
+        FOREACHC(itatt, attached) {
+            if (vbodyexcluded.empty() && vlinkexcluded.empty() && *itatt == pbody) {
+                bcollision |= _CheckBoundEnv(pbody, report);      // the common case runs through the cached bound query
+            } else {
+                bcollision |= _CheckPairs(*itatt, _EnvTriples(*itatt, attached, vbodyexcluded, vlinkexcluded, NULL), report);
+            }
+            if (bcollision && !report) return true;
+        }
+        return bcollision;
+    }
+
+    virtual bool CheckCollision(KinBodyConstPtr pbody1, KinBodyConstPtr pbody2, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        if (pbody1->IsAttached(*pbody2)) return false;
+        _Synchronize();
+        std::vector<int32_t> triples;
+        const int id2 = _Info(pbody2)->id;
+        FOREACHC(it1, pbody1->GetLinks()) FOREACHC(it2, pbody2->GetLinks()) {
+            triples.push_back((*it1)->GetIndex()); triples.push_back(id2); triples.push_back((*it2)->GetIndex());
+        }
+        return _CheckPairs(pbody1, triples, report);
+    }
+
+    virtual bool CheckCollision(KinBody::LinkConstPtr plink, CollisionReportPtr report = CollisionReportPtr())
+    {
+        std::vector<KinBodyConstPtr> vbodyexcluded;
+        std::vector<KinBody::LinkConstPtr> vlinkexcluded;
+        return CheckCollision(plink, vbodyexcluded, vlinkexcluded, report);
+    }
+
+    virtual bool CheckCollision(KinBody::LinkConstPtr plink1, KinBody::LinkConstPtr plink2, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        _Synchronize();
+        std::vector<int32_t> triples;
+        triples.push_back(plink1->GetIndex()); triples.push_back(_Info(plink2->GetParent())->id); triples.push_back(plink2->GetIndex());
+        return _CheckPairs(plink1->GetParent(), triples, report);
+    }
+
+    virtual bool CheckCollision(KinBody::LinkConstPtr plink, KinBodyConstPtr pbody, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        if (plink->GetParent()->IsAttached(*pbody)) return false;
+        _Synchronize();
+        std::vector<int32_t> triples;
+        const int id2 = _Info(pbody)->id;
+        FOREACHC(it2, pbody->GetLinks()) { triples.push_back(plink->GetIndex()); triples.push_back(id2); triples.push_back((*it2)->GetIndex()); }
+        return _CheckPairs(plink->GetParent(), triples, report);
+    }
+
+    virtual bool CheckCollision(KinBody::LinkConstPtr plink, const std::vector<KinBodyConstPtr>& vbodyexcluded,
+                                const std::vector<KinBody::LinkConstPtr>& vlinkexcluded, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        std::set<KinBodyConstPtr> attached;           // attached bodies are ignored for link queries (collisionchecker.h:250)
+        attached.insert(plink->GetParent());
+        const int only = plink->GetIndex();
+        return _CheckPairs(plink->GetParent(), _EnvTriples(plink->GetParent(), attached, vbodyexcluded, vlinkexcluded, &only), report);
+    }
+
+    virtual bool CheckCollision(const RAY&, KinBody::LinkConstPtr, CollisionReportPtr = CollisionReportPtr())
+    {
+        throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ray collision is not supported", ORE_NotImplemented);
+    }
+    virtual bool CheckCollision(const RAY&, KinBodyConstPtr, CollisionReportPtr = CollisionReportPtr())
+    {
+        throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ray collision is not supported", ORE_NotImplemented);
+    }
+    virtual bool CheckCollision(const RAY&, CollisionReportPtr = CollisionReportPtr())
+    {
+        throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ray collision is not supported", ORE_NotImplemented);
+    }
+
+    virtual bool CheckStandaloneSelfCollision(KinBodyConstPtr pbody, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        if (pbody->GetLinks().size() <= 1) return false;
+        const std::vector<int>* active = NULL;
+        if (pbody->IsRobot() && (_options & CO_ActiveDOFs)) active = &RaveInterfaceConstCast<RobotBase>(pbody)->GetActiveDOFIndices();
+        cc_query* query = _Bind(pbody, active);
+        std::vector<double> T8 = _Poses(pbody);
+        uint32_t verdict = 0; int32_t fs = -1;
+        _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_SELF, &verdict, NULL, &fs, NULL));
+        if ((verdict & CC_VERDICT_SELF) && !!report && fs >= 0) {
+            std::vector<int32_t> quads = _Quads(query);
+            report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * fs]), *pbody->GetLinks().at(quads[4 * fs + 2]));
+            report->minDistance = 0;
+        }
+        return (verdict & CC_VERDICT_SELF) != 0;
+    }
+
+    virtual bool CheckStandaloneSelfCollision(KinBody::LinkConstPtr plink, CollisionReportPtr report = CollisionReportPtr())
+    {
+        if (!!report) report->Reset(_options);
+        KinBodyPtr pbody = plink->GetParent();
+        _Synchronize();
+        const int id = _Info(pbody)->id;
+        std::vector<int32_t> triples;
+        FOREACHC(itset, pbody->GetNonAdjacentLinks(KinBody::AO_Enabled)) {     // collisionPQP.h:388-417
+            const int l0 = *itset & 0xffff, l1 = *itset >> 16;
+            if (l0 == plink->GetIndex() || l1 == plink->GetIndex()) { triples.push_back(l0); triples.push_back(id); triples.push_back(l1); }
+        }
+        return _CheckPairs(pbody, triples, report, true);
+    }
+
+private:
+    // ------------------------------------------------------------------------------------------ helpers
+    void _Check(int rc) const
+    {
+        if (rc != CC_OK) throw OPENRAVE_EXCEPTION_FORMAT("cudacollision error %d: %s", rc % cc_last_error(), ORE_Failed);
+    }
+
+    BodyInfoPtr _Info(KinBodyConstPtr pbody) const
+    {
+        BodyInfoPtr pinfo = boost::dynamic_pointer_cast<BodyInfo>(pbody->GetUserData(_userdatakey));
+        if (!pinfo) throw OPENRAVE_EXCEPTION_FORMAT("body %s is not known to cudacollision", pbody->GetName(), ORE_InvalidState);
+        return pinfo;
+    }
+
+    int _EnvIndexOf(int ccbody) const
+    {
+        std::map<int, KinBodyWeakPtr>::const_iterator it = _byid.find(ccbody);
+        KinBodyPtr p = it == _byid.end() ? KinBodyPtr() : it->second.lock();
+        return !p ? -1 : p->GetEnvironmentBodyIndex();
+    }
+
+    BodyInfoPtr _InitKinBody(KinBodyConstPtr pbody)
+    {
+        BodyInfoPtr pinfo = boost::dynamic_pointer_cast<BodyInfo>(pbody->GetUserData(_userdatakey));
+        if (!!pinfo && pinfo->body.lock() == pbody) return pinfo;     // clones can carry a stale pointer (collisionPQP.h:91-95)
+        pinfo.reset(new BodyInfo());
+        pinfo->body = boost::const_pointer_cast<KinBody>(pbody);
+        _Check(cc_scene_add_body(_scene, pbody->GetName().c_str(), (int)pbody->GetLinks().size(), pbody->IsRobot() ? 1 : 0, &pinfo->id));
+        _UploadMeshes(pbody, pinfo);
+        boost::weak_ptr<BodyInfo> winfo(pinfo);
+        pinfo->cbGeometry = pbody->RegisterChangeCallback(KinBody::Prop_LinkGeometry, boost::bind(&CudaCollisionChecker::_OnGeometry, this, winfo));
+        pinfo->cbEnable = pbody->RegisterChangeCallback(KinBody::Prop_LinkEnable, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, false));
+        pinfo->cbAttached = pbody->RegisterChangeCallback(KinBody::Prop_BodyAttached, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, false));
+        pinfo->cbJoints = pbody->RegisterChangeCallback(KinBody::Prop_Joints | KinBody::Prop_LinkStatic, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, true));
+        pinfo->cbActive = pbody->RegisterChangeCallback(KinBody::Prop_RobotActiveDOFs, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, false));
+        pbody->SetUserData(_userdatakey, pinfo);
+        _byid[pinfo->id] = pinfo->body;
+        _DropQueries();
+        return pinfo;
+    }
+
+    void _UploadMeshes(KinBodyConstPtr pbody, BodyInfoPtr pinfo)
+    {
+        std::vector<double> verts;
+        FOREACHC(itlink, pbody->GetLinks()) {
+            const TriMesh& mesh = (*itlink)->GetCollisionData();                    // link-frame soup (kinbodylink.cpp:1202-1232)
+            verts.resize(3 * mesh.vertices.size());
+            for (size_t i = 0; i < mesh.vertices.size(); ++i) { verts[3 * i] = mesh.vertices[i].x; verts[3 * i + 1] = mesh.vertices[i].y; verts[3 * i + 2] = mesh.vertices[i].z; }
+            _Check(cc_body_set_link_mesh(_scene, pinfo->id, (*itlink)->GetIndex(), (*itlink)->GetName().c_str(), verts.data(),
+                                         (int)mesh.vertices.size(), mesh.indices.data(), (int)mesh.indices.size() / 3));
+        }
+        pinfo->transformStamp = -1;
+    }
+
+    void _OnGeometry(boost::weak_ptr<BodyInfo> winfo)
+    {
+        BodyInfoPtr pinfo = winfo.lock();
+        KinBodyPtr pbody = !pinfo ? KinBodyPtr() : pinfo->body.lock();
+        if (!!pbody) { _UploadMeshes(pbody, pinfo); pinfo->pairsDirty = true; _DropQueries(); }
+    }
+
+    void _OnStructure(boost::weak_ptr<BodyInfo> winfo, bool kinematics)
+    {
+        BodyInfoPtr pinfo = winfo.lock();
+        if (!pinfo) return;
+        pinfo->transformStamp = -1;
+        pinfo->pairsDirty = true;
+        if (kinematics) pinfo->kinematicsDirty = true;
+        _DropQueries();
+    }
+
+    void _DropQueries()
+    {
+        for (std::map<QueryKey, cc_query*>::iterator it = _queries.begin(); it != _queries.end(); ++it) cc_query_destroy(it->second);
+        _queries.clear();
+    }
+
+    /// push poses / enable flags / attachments of every body whose update stamp moved, then commit (idempotent)
+    void _Synchronize()
+    {
+        std::vector<KinBodyPtr> vbodies;
+        GetEnv()->GetBodies(vbodies);
+        bool changed = false;
+        std::vector<double> T8;
+        std::vector<uint8_t> enabled;
+        FOREACHC(itbody, vbodies) {
+            BodyInfoPtr pinfo = _InitKinBody(*itbody);
+            if (pinfo->transformStamp == (*itbody)->GetUpdateStamp()) continue;
+            T8 = _Poses(*itbody);
+            _Check(cc_body_set_link_transforms(_scene, pinfo->id, T8.data()));
+            enabled.resize((*itbody)->GetLinks().size());
+            for (size_t i = 0; i < enabled.size(); ++i) enabled[i] = (*itbody)->GetLinks()[i]->IsEnabled() ? 1 : 0;
+            _Check(cc_body_set_link_enabled(_scene, pinfo->id, enabled.data()));
+            if ((*itbody)->GetDOF() > 0 && !pinfo->kinematicsDirty) {
+                std::vector<dReal> values;
+                (*itbody)->GetDOFValues(values);
+                _Check(cc_body_set_dof_values(_scene, pinfo->id, values.data(), (int)values.size()));
+            }
+            pinfo->transformStamp = (*itbody)->GetUpdateStamp();
+            changed = true;
+        }
+        if (changed) {
+            // attachments (KinBody::IsAttached: grabbed / attached bodies are never checked against each other)
+            for (size_t i = 0; i < vbodies.size(); ++i)
+                for (size_t j = i + 1; j < vbodies.size(); ++j)
+                    _Check(cc_body_set_attached(_scene, _Info(vbodies[i])->id, _Info(vbodies[j])->id, vbodies[i]->IsAttached(*vbodies[j]) ? 1 : 0));
+            _DropQueries();       // bound queries capture static poses and hoisted verdicts
+        }
+        _Check(cc_scene_commit(_scene));
+    }
+
+    std::vector<double> _Poses(KinBodyConstPtr pbody) const
+    {
+        std::vector<Transform> vtrans;
+        pbody->GetLinkTransformations(vtrans);
+        std::vector<double> T8(8 * vtrans.size());
+        for (size_t i = 0; i < vtrans.size(); ++i) PackTransform(vtrans[i], &T8[8 * i]);
+        return T8;
+    }
+
+    /// FK chain program read off the computed KinBody (kinbody.cpp:2286-2481; accessors kinbodyjoint.cpp:1567-1582)
+    void _SyncKinematics(KinBodyConstPtr pbody, BodyInfoPtr pinfo)
+    {
+        if (pinfo->kinematicsDirty) {
+            const std::vector<KinBody::JointPtr>& vjoints = pbody->GetDependencyOrderedJointsAll();
+            std::vector<cc_joint> joints(vjoints.size());
+            for (size_t k = 0; k < vjoints.size(); ++k) {
+                const KinBody::Joint& j = *vjoints[k];
+                cc_joint& o = joints[k];
+                memset(&o, 0, sizeof(o));
+                if (j.GetDOF() != 1) throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: joint %s has %d DOF (1-DOF joints only)", j.GetName() % j.GetDOF(), ORE_NotImplemented);
+                o.type = j.IsRevolute(0) ? CC_JOINT_REVOLUTE : CC_JOINT_PRISMATIC;
+                o.parent_link = !j.GetHierarchyParentLink() ? 0 : j.GetHierarchyParentLink()->GetIndex();
+                o.child_link = j.GetHierarchyChildLink()->GetIndex();
+                o.dof_index = j.GetDOFIndex();
+                o.mimic_dof = -1;
+                o.is_static = j.IsStatic() ? 1 : 0;
+                o.is_circular = j.IsCircular(0) ? 1 : 0;
+                std::vector<dReal> lo, hi;
+                j.GetLimits(lo, hi);
+                o.lower = lo.at(0); o.upper = hi.at(0);
+                PackTransform(j.GetInternalHierarchyLeftTransform(), o.left);
+                PackTransform(j.GetInternalHierarchyRightTransform(), o.right);
+                const Vector& ax = j.GetInternalHierarchyAxis(0);
+                o.axis[0] = ax.x; o.axis[1] = ax.y; o.axis[2] = ax.z;
+                if (j.IsMimic(0) && !j.IsStatic()) {
+                    std::vector<int> vmimicdofs;
+                    j.GetMimicDOFIndices(vmimicdofs, 0);
+                    if (vmimicdofs.size() != 1) throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: mimic joint %s reads %d DOFs", j.GetName() % vmimicdofs.size(), ORE_NotImplemented);
+                    const std::string var = pbody->GetJointFromDOFIndex(vmimicdofs[0])->GetName();
+                    if (!ParseAffineMimic(j.GetMimicEquation(0, 0), var, o.mimic_a, o.mimic_b))
+                        throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: mimic equation '%s' of joint %s is not affine", j.GetMimicEquation(0, 0) % j.GetName(), ORE_NotImplemented);
+                    o.mimic_dof = vmimicdofs[0];
+                    o.dof_index = -1;
+                }
+            }
+            const int ndof = pbody->GetDOF(), nl = (int)pbody->GetLinks().size();
+            std::vector<uint8_t> affects((size_t)std::max(1, ndof) * nl, 0);
+            for (int d = 0; d < ndof; ++d) {
+                const int jointindex = pbody->GetJointFromDOFIndex(d)->GetJointIndex();
+                for (int l = 0; l < nl; ++l) affects[(size_t)d * nl + l] = pbody->DoesAffect(jointindex, l) ? 1 : 0;
+            }
+            _Check(cc_body_set_kinematics(_scene, pinfo->id, ndof, (int)joints.size(), joints.data(), affects.data()));
+            std::vector<dReal> values;
+            pbody->GetDOFValues(values);
+            if (ndof > 0) _Check(cc_body_set_dof_values(_scene, pinfo->id, values.data(), ndof));
+            pinfo->kinematicsDirty = false;
+        }
+        if (pinfo->pairsDirty) {
+            // KinBody::GetNonAdjacentLinks probes the initial pose through CheckCollision(link,link) of THIS checker
+            // (kinbody.cpp:5563-5577), i.e. through the GPU; the list arrives in CompareNonAdjacentFarthest order.
+            const std::vector<int>& pairs = pbody->GetNonAdjacentLinks(0);
+            std::vector<int32_t> packed(pairs.begin(), pairs.end());
+            _Check(cc_body_set_nonadjacent_pairs(_scene, pinfo->id, packed.data(), (int)packed.size()));
+            pinfo->pairsDirty = false;
+        }
+    }
+
+    cc_query* _Bind(KinBodyConstPtr pbody, const std::vector<int>* active)
+    {
+        _Synchronize();
+        BodyInfoPtr pinfo = _Info(pbody);
+        _SyncKinematics(pbody, pinfo);
+        _Check(cc_scene_commit(_scene));
+        QueryKey key;
+        key.body = pinfo->id; key.options = _options;
+        if (active) key.active = *active;
+        std::map<QueryKey, cc_query*>::iterator it = _queries.find(key);
+        if (it != _queries.end()) return it->second;
+        cc_query* query = NULL;
+        std::vector<int32_t> act(key.active.begin(), key.active.end());
+        _Check(cc_query_create(_scene, pinfo->id, active ? act.data() : NULL, (int)act.size(), _options, &query));
+        _queries[key] = query;
+        return query;
+    }
+
+    std::vector<int32_t> _Quads(cc_query* query) const
+    {
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        std::vector<int32_t> quads(4 * (size_t)std::max(1, info.npairs_env + info.npairs_self));
+        cc_query_get_pairs(query, quads.data());
+        return quads;
+    }
+
+    /// env check of one body through its cached bound query, current poses, complete pair mask when a report is wanted
+    bool _CheckBoundEnv(KinBodyConstPtr pbody, CollisionReportPtr report)
+    {
+        const std::vector<int>* active = NULL;
+        if (pbody->IsRobot() && (_options & CO_ActiveDOFs)) active = &RaveInterfaceConstCast<RobotBase>(pbody)->GetActiveDOFIndices();
+        cc_query* query = _Bind(pbody, active);
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        std::vector<double> T8 = _Poses(pbody);
+        std::vector<uint32_t> mask(!report ? 0 : info.mask_words);
+        uint32_t verdict = 0;
+        _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | (!report ? 0 : CC_BATCH_ALL_PAIRS), &verdict, NULL, NULL, !report ? NULL : mask.data()));
+        if ((verdict & CC_VERDICT_ENV) && !!report) _FillReport(pbody, query, mask, info.npairs_env, report);
+        return (verdict & CC_VERDICT_ENV) != 0;
+    }
+
+    void _FillReport(KinBodyConstPtr pbody, cc_query* query, const std::vector<uint32_t>& mask, int npairs, CollisionReportPtr report)
+    {
+        std::vector<int32_t> quads = _Quads(query);
+        for (int p = 0; p < npairs; ++p) {
+            if (!((mask[p >> 5] >> (p & 31)) & 1u)) continue;
+            KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
+            if (!pother) continue;
+            report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));   // collisionPQP.h:586
+        }
+        report->minDistance = 0;                                                                                       // :587
+    }
+
+    /// (link, other body, other link) triples of pbody against the environment in pqprave's order (collisionPQP.h:448-487)
+    std::vector<int32_t> _EnvTriples(KinBodyConstPtr pbody, const std::set<KinBodyConstPtr>& attached, const std::vector<KinBodyConstPtr>& vbodyexcluded,
+                                     const std::vector<KinBody::LinkConstPtr>& vlinkexcluded, const int* onlylink)
+    {
+        _Synchronize();
+        std::vector<KinBodyPtr> vbodies;
+        GetEnv()->GetBodies(vbodies);
+        std::vector<int32_t> triples;
+        const bool activeonly = pbody->IsRobot() && (_options & CO_ActiveDOFs) && !onlylink;
+        RobotBaseConstPtr probot = activeonly ? RaveInterfaceConstCast<RobotBase>(pbody) : RobotBaseConstPtr();
+        FOREACHC(itbody, vbodies) {
+            if (attached.find(*itbody) != attached.end()) continue;
+            if (std::find(vbodyexcluded.begin(), vbodyexcluded.end(), *itbody) != vbodyexcluded.end()) continue;
+            const int id2 = _Info(*itbody)->id;
+            FOREACHC(itlink, pbody->GetLinks()) {
+                if (onlylink && (*itlink)->GetIndex() != *onlylink) continue;
+                if (std::find(vlinkexcluded.begin(), vlinkexcluded.end(), *itlink) != vlinkexcluded.end()) continue;
+                if (activeonly) {                                           // _IsActiveLink (collisionPQP.h:710-735)
+                    bool affected = false;
+                    FOREACHC(itdof, probot->GetActiveDOFIndices())
+                        if (probot->DoesAffect(probot->GetJointFromDOFIndex(*itdof)->GetJointIndex(), (*itlink)->GetIndex())) { affected = true; break; }
+                    if (!affected) continue;
+                }
+                FOREACHC(itlink2, (*itbody)->GetLinks()) {
+                    if (std::find(vlinkexcluded.begin(), vlinkexcluded.end(), *itlink2) != vlinkexcluded.end()) continue;
+                    triples.push_back((*itlink)->GetIndex()); triples.push_back(id2); triples.push_back((*itlink2)->GetIndex());
+                }
+            }
+        }
+        return triples;
+    }
+
+    /// explicit pair list at the bodies' current poses (disabled links never collide: the C ABI keeps their index and skips them)
+    bool _CheckPairs(KinBodyConstPtr pbody, const std::vector<int32_t>& triples, CollisionReportPtr report, bool firstonly = false)
+    {
+        if (triples.empty()) return false;
+        BodyInfoPtr pinfo = _Info(pbody);
+        cc_query* query = NULL;
+        _Check(cc_query_create_pairs(_scene, pinfo->id, triples.data(), (int)triples.size() / 3, &query));
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        std::vector<double> T8 = _Poses(pbody);
+        std::vector<uint32_t> mask(info.mask_words);
+        uint32_t verdict = 0; int32_t fe = -1, fs = -1;
+        int rc = cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | CC_BATCH_SELF | (firstonly ? 0 : CC_BATCH_ALL_PAIRS), &verdict, &fe, &fs, firstonly ? NULL : mask.data());
+        if (rc == CC_OK && verdict && !!report) {
+            if (firstonly) {
+                std::vector<int32_t> quads = _Quads(query);
+                const int p = fs >= 0 ? fs : fe;
+                KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
+                if (!!pother) report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));
+                report->minDistance = 0;
+            } else {
+                _FillReport(pbody, query, mask, info.npairs_env + info.npairs_self, report);
+            }
+        }
+        cc_query_destroy(query);
+        _Check(rc);
+        return verdict != 0;
+    }
+
+    bool _CheckBatchCommand(std::ostream& sout, std::istream& sinput)
+    {
+        std::string robotname;
+        int n = 0, flags = 0;
+        uintptr_t pq = 0, pverdict = 0, ppairs = 0;
+        sinput >> robotname >> n >> flags >> pq >> pverdict >> ppairs;
+        RobotBasePtr probot = GetEnv()->GetRobot(robotname);
+        if (!probot || !sinput) return false;
+        CheckCollisionBatch(probot, (const dReal*)pq, n, probot->GetActiveDOF(), (uint32_t*)pverdict, (int32_t*)ppairs, flags);
+        sout << n;
+        return true;
+    }
+
+    bool _SetTriEpsCommand(std::ostream&, std::istream& sinput)
+    {
+        double eps = 0;
+        sinput >> eps;
+        return !!sinput && cc_scene_set_tri_epsilon(_scene, eps) == CC_OK;
+    }
+
+    cc_scene* _scene;
+    int _options, _device;
+    std::string _userdatakey;
+    std::map<int, KinBodyWeakPtr> _byid;
+    std::map<QueryKey, cc_query*> _queries;
+};
+
+// ---------------------------------------------------------------------------------------------- plugin entry (plugin.h:30-157)
+class CudaCollisionPlugin : public RavePlugin
+{
+public:
+    CudaCollisionPlugin() { _interfaces[PT_CollisionChecker].push_back("cudacollision"); }
+    virtual ~CudaCollisionPlugin() {}
+    virtual InterfaceBasePtr CreateInterface(InterfaceType type, const std::string& interfacename, std::istream& sinput, EnvironmentBasePtr penv)
+    {
+        if (type == PT_CollisionChecker && interfacename == "cudacollision") return boost::make_shared<CudaCollisionChecker>(penv, boost::ref(sinput));
+        return InterfaceBasePtr();
+    }
+    virtual const InterfaceMap& GetInterfaces() const { return _interfaces; }
+    virtual const std::string& GetPluginName() const { static const std::string name("CudaCollisionPlugin"); return name; }
+
+private:
+    InterfaceMap _interfaces;
+};
+
+OPENRAVE_PLUGIN_API RavePlugin* CreatePlugin() { return new CudaCollisionPlugin(); }

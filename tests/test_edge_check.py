@@ -1,0 +1,97 @@
+"""Edge discretisation (openrave_b200/planning.py) against the per-sample loop it replaces (SURVEY.md §7 tier V6).
+
+CPU part (not gpu): the sample sequence obeys the reference's rules (planningutils.cpp:2692-2826, 3300-3454) and the batched
+evaluation returns the same code / failing sample / time as the serial loop when both use the oracle.
+GPU part: the CUDA batched entry vs the oracle's serial loop on random WAM edges."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_scene, sample_configs
+from openrave_b200 import planning as pl
+
+
+class OracleBatchAdapter(object):
+    """Gives the oracle the product's CheckCollisionBatch signature (test-only)."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def CheckCollisionBatch(self, robot, q, flags=3, active=None, all_pairs=False):
+        return self.orc.check_batch(robot, q, active=active, flags=flags)
+
+
+@pytest.fixture(scope="module")
+def wam():
+    env = load_scene("lab1")
+    orc = oracle.OracleChecker(env, "port")
+    env.SetCollisionChecker(orc)
+    robot = env.GetRobots()[0]
+    robot.SetActiveDOFs(robot.GetActiveManipulator().GetArmIndices())
+    return env, robot, orc
+
+
+def test_sample_sequence_rules(wam):
+    env, robot, orc = wam
+    c = pl.DynamicsCollisionConstraint(robot, None)
+    q0 = np.zeros(7)
+    q1 = np.array([0.5, -0.3, 0.2, 0.9, 0.0, 0.1, -0.2])
+    s, t, kinds = c.edge_samples(q0, q1, pl.IT_Closed)
+    nsteps = int((np.abs(q1 - q0) / c.resolution + 0.99).astype(int).max())
+    assert kinds[0] == 'end' and kinds[1] == 'start' and kinds.count('step') == nsteps - 1
+    assert np.allclose(s[0], q1) and np.allclose(s[1], q0)
+    steps = s[2:]
+    assert np.allclose(steps, q0 + np.outer(np.arange(1, nsteps), (q1 - q0) / nsteps), atol=1e-12)
+    assert np.allclose(t[2:], np.arange(1, nsteps) / nsteps)
+    # consecutive samples never move a DOF by more than its resolution
+    full = np.vstack([q0, steps, q1])
+    assert (np.abs(np.diff(full, axis=0)) <= c.resolution + 1e-12).all()
+    s2, t2, k2 = c.edge_samples(q0, q1, pl.IT_Open)
+    assert k2.count('end') == 0 and k2.count('start') == 0 and len(s2) == nsteps - 1
+    s3, _, k3 = c.edge_samples(q0, q0, pl.IT_OpenStart)
+    assert k3 == ['end'] and len(s3) == 1
+    s4, _, k4 = c.edge_samples(q0, q0, pl.IT_Open)
+    assert len(s4) == 0
+
+
+def test_batched_equals_serial_on_oracle(wam):
+    env, robot, orc = wam
+    cb = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    q = sample_configs(robot, 60, seed=3, active=robot.GetActiveDOFIndices())
+    nfail = 0
+    for k in range(0, 60, 2):
+        q0, q1 = q[k], q[k] + 0.15 * (q[k + 1] - q[k])
+        fa, fb = pl.ConstraintFilterReturn(), pl.ConstraintFilterReturn()
+        ra = cb.Check(q0, q1, pl.IT_Closed, filterreturn=fa)
+        rb = cb.CheckSerial(q0, q1, pl.IT_Closed, filterreturn=fb, env=env)
+        assert ra == rb
+        assert fa._invalidvalues == fb._invalidvalues and fa._fTimeWhenInvalid == fb._fTimeWhenInvalid
+        assert fa._configurationtimes == fb._configurationtimes
+        nfail += ra != 0
+    assert 0 < nfail < 30
+
+
+@pytest.mark.gpu
+def test_gpu_edges_equal_oracle_serial(wam):
+    from openrave_b200.checker import CudaCollisionChecker
+    env, robot, orc = wam
+    env2 = load_scene("lab1")
+    robot2 = env2.GetRobots()[0]
+    robot2.SetActiveDOFs(robot2.GetActiveManipulator().GetArmIndices())
+    cc = CudaCollisionChecker(env2, 0)
+    env2.SetCollisionChecker(cc)
+    gpu = pl.DynamicsCollisionConstraint(robot2, cc)
+    cpu = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    q = sample_configs(robot, 400, seed=8, active=robot.GetActiveDOFIndices())
+    edges = [(q[k], q[k] + 0.2 * (q[k + 1] - q[k])) for k in range(0, 400, 2)]
+    frs = [pl.ConstraintFilterReturn() for _ in edges]
+    got = gpu.CheckMany(edges, pl.IT_Closed, filterreturns=frs)          # 200 edges, one kernel pass
+    diff = 0
+    for (q0, q1), g, fr in zip(edges, got, frs):
+        fb = pl.ConstraintFilterReturn()
+        r = cpu.Check(q0, q1, pl.IT_Closed, filterreturn=fb)
+        if r != g or fr._fTimeWhenInvalid != fb._fTimeWhenInvalid:
+            diff += 1
+    # identical except where the first failing sample sits inside the 1e-4 m contact band
+    assert diff <= 2, diff
+    assert 0 < sum(1 for g in got if g) < len(got)
