@@ -4,14 +4,12 @@
 //
 //   cc_fk_kernel        ONE THREAD per configuration.  The FK chain program is uniform across the warp, so
 //                       KinBody::SetDOFValues' joint loop (kinbody.cpp:2286-2481) runs divergence-free in FP64 with
-//                       the running transform in registers (the chain is walked depth-first; only branch-point
-//                       links are parked in a coalesced SoA scratch).  Every link pose is emitted as FP32 R|t
-//                       (base-centred) plus its world AABB, then the link-AABB x {environment-AABB, link-AABB}
-//                       broadphase runs over the bound pair table in reference order and leaves one candidate bit
-//                       per pair.  Configurations with no candidate get their verdict here; the rest are appended
-//                       to a work queue.
-//   cc_traverse_kernel  persistent, ONE WARP per queued configuration: candidate bits -> dense batches of 32 root
-//                       pairs (relative pose + 15-axis SAT of the root boxes) -> warp-cooperative dual-BVH descent.
+//                       the running transform in registers (the chain is walked depth-first and pruned to the links
+//                       the bound pairs need; only branch-point links are parked in a coalesced SoA scratch).  Every
+//                       needed link pose is emitted as FP32 R|t (base-centred) plus its world AABB.
+//   cc_traverse_kernel  persistent, ONE WARP per configuration: link-AABB x {static-AABB, link-AABB} broadphase over
+//                       the bound pair table in reference order, 32 pairs per step -> dense batches of 32 candidate
+//                       root pairs (relative pose + 15-axis SAT of the root boxes) -> warp-cooperative dual-BVH descent.
 //                       A stack item names the two CHILDREN of the node being split plus the other node, so one pop
 //                       is one 64-byte + one 32-byte fetch and two independent box tests per lane; leaf x leaf hits
 //                       are parked in a triangle queue and tested 32 at a time with PQP's 17-axis triangle SAT
@@ -37,7 +35,7 @@ constexpr int kStackCap = 384;       // items of shared-memory LIFO per warp
 constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
 constexpr int kNumSlots = 32;        // root pairs traversed together
 constexpr int kTriQCap = 96;         // pending leaf x leaf tests (drained 32 at a time)
-constexpr int kCandCap = 64;         // pending candidate pair indices (drained 32 at a time)
+constexpr int kCandCap = 96;         // pending candidate pair indices (64 tested per step, drained 32 at a time)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNone = 0x7fffffff;
 
@@ -67,16 +65,18 @@ struct Params {
     // scene (device pointers)
     const float4* nodes;        // 2 x float4 per node: {cx cy cz | left} {ex ey ez | right}
     const float4* tris;         // 3 x float4 per triangle (link frame)
-    const int32_t* slot_root;   // root node of every link slot
-    const float* env_xf;        // [nslots - nq][12] FP32 R(9, row major)|t(3), base-centred
-    const float* env_aabb;      // [nslots - nq][8]  world AABB {cx cy cz ex ey ez 0 0}, base-centred
-    const float* link_box;      // [nq][8] link-frame root box {cx cy cz ex ey ez has_geometry 0}
-    // query
-    const uint32_t* pairs;      // device pair list: a | (b << 16), b = slot index
-    const int32_t* pair_orig;   // original (reference-order) index of each device pair
-    const FkStep* steps;        // depth-first order
+    // plan = (pair list, slot space).  Slots [0, ndyn) are query links whose pose changes per configuration (scratch),
+    // slots [ndyn, ndyn + nstatic) are everything static for this plan: environment links and query links no active DOF moves.
+    const int32_t* slot_root;   // [ndyn + nstatic] root node of every slot
+    const float* st_xf;         // [nstatic][12] FP32 R(9, row major)|t(3), base-centred
+    const float* st_aabb;       // [nstatic][8]  world AABB {cx cy cz 0 ex ey ez 0}, base-centred
+    const float* link_box;      // [ndyn][8] link-frame root box {cx cy cz ex ey ez 1 0}
+    const int32_t* emit_index;  // [nq] link -> dynamic slot, -1: pose not needed
+    const uint32_t* pairs;      // device pair list: slot_a | (slot_b << 16)
+    const int32_t* pair_orig;   // original (reference-order) index of each device pair, increasing within env / self
+    const FkStep* steps;        // depth-first order, pruned to the ancestors of the dynamic slots
     const uint32_t* hoisted_mask;
-    int32_t nq, nslots, npairs_dev, nenv_dev, nenv_total, nsteps, ncols, cwords;
+    int32_t nq, ndyn, nstatic, npairs_dev, nenv_dev, nenv_total, nsteps, ncols;
     int32_t hoisted_first_env, hoisted_first_self, mask_words, flags;
     double base[8];             // pose of link 0 (kept, kinbody.cpp:2281)
     double center[3];           // subtracted from every translation before the FP32 conversion
@@ -91,12 +91,10 @@ struct Params {
     double* fk_out;             // [n][nq][8] or NULL
     uint32_t* work_out;         // [n] or NULL: traversal iterations spent on each configuration (diagnostics)
     // per-chunk scratch
-    float* xf32;                // [cap][nq][12]
-    float* aabb;                // [nq][6][cap]
+    float* xf32;                // [cap][ndyn][12]
+    float* aabb;                // [cap][ndyn][8]
     double* fksave;             // [nsave][7][cap]
-    uint32_t* cand;             // [cap][cwords]
-    int32_t* queue;             // [cap]
-    int32_t* counters;          // [0] queue length, [1] traversal work counter
+    int32_t* counters;          // [0] traversal work counter
     int32_t* err_flag;          // set when a traversal overflows its spill area
     int32_t cap;
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
@@ -293,21 +291,21 @@ __device__ __forceinline__ void relative_pose(const float* A, const float* B, fl
     t[2] = A[2] * dx + A[5] * dy + A[8] * dz;
 }
 
-// ================================================================================================ kernel 1: FK + broadphase
-__host__ __device__ inline size_t fk_smem_bytes(int nq, int nsteps, int nenv)
+// ================================================================================================ kernel 1: FK
+__host__ __device__ inline size_t fk_smem_bytes(int nq, int nsteps, int ndyn)
 {
-    return (size_t)nsteps * sizeof(FkStep) + (size_t)nq * 32 + (size_t)nenv * 32;
+    return (size_t)nsteps * sizeof(FkStep) + (size_t)ndyn * 32 + (size_t)nq * 4;
 }
 
 // Emit one link pose: optional FP64 copy-out, FP32 R|t (matrixFromQuat, geometry.h:779-800) and the world AABB
-// of the link's root box.
-__device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbox, int c, int l, const Xf& T)
+// of the link's root box, both into the dynamic slot `d` of configuration `c` (d < 0: only the copy-out).
+__device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbox, int c, int l, int d, const Xf& T)
 {
     if (P.fk_out) {
         double* dst = P.fk_out + ((size_t)c * P.nq + l) * 8;
         dst[0] = T.q0; dst[1] = T.q1; dst[2] = T.q2; dst[3] = T.q3; dst[4] = T.tx; dst[5] = T.ty; dst[6] = T.tz; dst[7] = 0.0;
     }
-    if (P.flags & kFlagFkOnly) return;
+    if (d < 0 || (P.flags & kFlagFkOnly)) return;
     const double il = 2.0 / (T.q0 * T.q0 + T.q1 * T.q1 + T.q2 * T.q2 + T.q3 * T.q3);
     const double qq1 = il * T.q1 * T.q1, qq2 = il * T.q2 * T.q2, qq3 = il * T.q3 * T.q3;
     float R[9], t[3];
@@ -315,23 +313,19 @@ __device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbo
     R[3] = (float)(il * (T.q1 * T.q2 + T.q0 * T.q3));   R[4] = (float)(1 - qq1 - qq3);                    R[5] = (float)(il * (T.q2 * T.q3 - T.q0 * T.q1));
     R[6] = (float)(il * (T.q1 * T.q3 - T.q0 * T.q2));   R[7] = (float)(il * (T.q2 * T.q3 + T.q0 * T.q1)); R[8] = (float)(1 - qq1 - qq2);
     t[0] = (float)(T.tx - P.center[0]); t[1] = (float)(T.ty - P.center[1]); t[2] = (float)(T.tz - P.center[2]);
-    float4* dst = (float4*)(P.xf32 + ((size_t)c * P.nq + l) * 12);
+    float4* dst = (float4*)(P.xf32 + ((size_t)c * P.ndyn + d) * 12);
     dst[0] = make_float4(R[0], R[1], R[2], R[3]);
     dst[1] = make_float4(R[4], R[5], R[6], R[7]);
     dst[2] = make_float4(R[8], t[0], t[1], t[2]);
-    const float* lb = s_linkbox + 8 * l;
-    if (lb[6] != 0.f) {
-        const float reps = 1e-6f;
-        const float cx = lb[0], cy = lb[1], cz = lb[2], ex = lb[3], ey = lb[4], ez = lb[5];
-        float* ab = P.aabb + (size_t)l * 6 * P.cap + c;
-        const size_t cs = (size_t)P.cap;
-        ab[0] = fmaf(R[0], cx, fmaf(R[1], cy, fmaf(R[2], cz, t[0])));
-        ab[cs] = fmaf(R[3], cx, fmaf(R[4], cy, fmaf(R[5], cz, t[1])));
-        ab[2 * cs] = fmaf(R[6], cx, fmaf(R[7], cy, fmaf(R[8], cz, t[2])));
-        ab[3 * cs] = (fabsf(R[0]) + reps) * ex + (fabsf(R[1]) + reps) * ey + (fabsf(R[2]) + reps) * ez;
-        ab[4 * cs] = (fabsf(R[3]) + reps) * ex + (fabsf(R[4]) + reps) * ey + (fabsf(R[5]) + reps) * ez;
-        ab[5 * cs] = (fabsf(R[6]) + reps) * ex + (fabsf(R[7]) + reps) * ey + (fabsf(R[8]) + reps) * ez;
-    }
+    const float* lb = s_linkbox + 8 * d;
+    const float reps = 1e-6f;
+    const float cx = lb[0], cy = lb[1], cz = lb[2], ex = lb[3], ey = lb[4], ez = lb[5];
+    float4* ab = (float4*)(P.aabb + ((size_t)c * P.ndyn + d) * 8);
+    ab[0] = make_float4(fmaf(R[0], cx, fmaf(R[1], cy, fmaf(R[2], cz, t[0]))), fmaf(R[3], cx, fmaf(R[4], cy, fmaf(R[5], cz, t[1]))),
+                        fmaf(R[6], cx, fmaf(R[7], cy, fmaf(R[8], cz, t[2]))), 0.f);
+    ab[1] = make_float4((fabsf(R[0]) + reps) * ex + (fabsf(R[1]) + reps) * ey + (fabsf(R[2]) + reps) * ez,
+                        (fabsf(R[3]) + reps) * ex + (fabsf(R[4]) + reps) * ey + (fabsf(R[5]) + reps) * ez,
+                        (fabsf(R[6]) + reps) * ex + (fabsf(R[7]) + reps) * ey + (fabsf(R[8]) + reps) * ez, 0.f);
 }
 
 // L * J(value) * R of one joint (kinbody.cpp:2404-2478); the value rules follow kinbody.cpp:2149-2224, 2308-2386.
@@ -372,96 +366,43 @@ cc_fk_kernel(const __grid_constant__ Params P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FkStep* s_steps = (FkStep*)smem_raw;
     float* s_linkbox = (float*)(s_steps + P.nsteps);
-    float* s_envbox = s_linkbox + 8 * P.nq;
-    const int nenv = P.nslots - P.nq;
+    int32_t* s_emit = (int32_t*)(s_linkbox + 8 * P.ndyn);
     {
         const int4* src = (const int4*)P.steps; int4* dst = (int4*)s_steps;
         for (int i = threadIdx.x; i < P.nsteps * (int)(sizeof(FkStep) / 16); i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < 8 * P.nq; i += blockDim.x) s_linkbox[i] = P.link_box[i];
-        for (int i = threadIdx.x; i < 8 * nenv; i += blockDim.x) s_envbox[i] = P.env_aabb[i];
+        for (int i = threadIdx.x; i < 8 * P.ndyn; i += blockDim.x) s_linkbox[i] = P.link_box[i];
+        for (int i = threadIdx.x; i < P.nq; i += blockDim.x) s_emit[i] = P.emit_index[i];
     }
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.n) return;
 
-    // ---------------------------------------------------------------- 1. link poses (FP64)
     if (P.flags & kFlagPoseMode) {
         const double* src = P.q + (size_t)c * P.nq * 8;
-        for (int l = 0; l < P.nq; ++l) emit_link(P, s_linkbox, c, l, xf_load(src + 8 * l));
-    } else {
-        const Xf base = xf_load(P.base);
-        emit_link(P, s_linkbox, c, 0, base);                  // link 0 keeps its pose (kinbody.cpp:2281)
-        const double* qrow = P.q + (size_t)c * P.ncols;
-        Xf cur = base;
-        const size_t cs = (size_t)P.cap;
-        for (int s = 0; s < P.nsteps; ++s) {
-            const FkStep& st = s_steps[s];
-            if (st.load_parent == -1) cur = base;
-            else if (st.load_parent >= 0) {
-                const double* sv = P.fksave + (size_t)st.load_parent * 7 * cs + c;
-                cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
-                cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
-            }
-            cur = xf_mul(cur, joint_transform(st, qrow));
-            if (st.save >= 0) {
-                double* sv = P.fksave + (size_t)st.save * 7 * cs + c;
-                sv[0] = cur.q0; sv[cs] = cur.q1; sv[2 * cs] = cur.q2; sv[3 * cs] = cur.q3;
-                sv[4 * cs] = cur.tx; sv[5 * cs] = cur.ty; sv[6 * cs] = cur.tz;
-            }
-            emit_link(P, s_linkbox, c, st.child, cur);
-        }
+        for (int l = 0; l < P.nq; ++l)
+            if (s_emit[l] >= 0) emit_link(P, s_linkbox, c, l, s_emit[l], xf_load(src + 8 * l));
+        return;
     }
-    if (P.flags & kFlagFkOnly) return;
-
-    // ---------------------------------------------------------------- 2. broadphase: world AABBs, reference pair order
+    const Xf base = xf_load(P.base);
+    emit_link(P, s_linkbox, c, 0, s_emit[0], base);               // link 0 keeps its pose (kinbody.cpp:2281)
+    const double* qrow = P.q + (size_t)c * P.ncols;
+    Xf cur = base;
     const size_t cs = (size_t)P.cap;
-    uint32_t* crow = P.cand + (size_t)c * P.cwords;
-    int ncand = 0;
-    int cur_a = -1;
-    float acx = 0, acy = 0, acz = 0, aex = 0, aey = 0, aez = 0;
-    for (int w = 0; w < P.cwords; ++w) {
-        uint32_t bits = 0;
-        const int k0 = w * 32;
-        const int k1 = min(k0 + 32, P.npairs_dev);
-        for (int k = k0; k < k1; ++k) {
-            if (!(P.flags & (k < P.nenv_dev ? kFlagEnv : kFlagSelf))) continue;
-            const uint32_t pr = __ldg(&P.pairs[k]);
-            const int a = pr & 0xffff, sb = pr >> 16;
-            if (a != cur_a) {
-                const float* ab = P.aabb + (size_t)a * 6 * cs + c;
-                acx = ab[0]; acy = ab[cs]; acz = ab[2 * cs]; aex = ab[3 * cs]; aey = ab[4 * cs]; aez = ab[5 * cs];
-                cur_a = a;
-            }
-            float bcx, bcy, bcz, bex, bey, bez;
-            if (sb < P.nq) {
-                const float* bb = P.aabb + (size_t)sb * 6 * cs + c;
-                bcx = bb[0]; bcy = bb[cs]; bcz = bb[2 * cs]; bex = bb[3 * cs]; bey = bb[4 * cs]; bez = bb[5 * cs];
-            } else {
-                const float* bb = s_envbox + 8 * (sb - P.nq);
-                bcx = bb[0]; bcy = bb[1]; bcz = bb[2]; bex = bb[3]; bey = bb[4]; bez = bb[5];
-            }
-            const bool ov = fabsf(acx - bcx) <= aex + bex && fabsf(acy - bcy) <= aey + bey && fabsf(acz - bcz) <= aez + bez;
-            bits |= (ov ? 1u : 0u) << (k - k0);
+    for (int s = 0; s < P.nsteps; ++s) {
+        const FkStep& st = s_steps[s];
+        if (st.load_parent == -1) cur = base;
+        else if (st.load_parent >= 0) {
+            const double* sv = P.fksave + (size_t)st.load_parent * 7 * cs + c;
+            cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
+            cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
         }
-        crow[w] = bits;
-        ncand += __popc(bits);
-    }
-    if (P.pair_mask) {
-        uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
-        for (int i = 0; i < P.mask_words; ++i) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
-    }
-    if (ncand == 0) {
-        // nothing can touch: the verdict is the hoisted pairs' alone
-        uint32_t v = 0;
-        if ((P.flags & kFlagEnv) && P.hoisted_first_env != kNone) v |= 1u;
-        if ((P.flags & kFlagSelf) && P.hoisted_first_self != kNone) v |= 2u;
-        if (P.verdict) P.verdict[c] = v;
-        if (P.first_env) P.first_env[c] = (v & 1u) ? P.hoisted_first_env : -1;
-        if (P.first_self) P.first_self[c] = (v & 2u) ? P.hoisted_first_self : -1;
-        if (P.work_out) P.work_out[c] = 0u;
-    } else {
-        const int pos = atomicAdd(&P.counters[0], 1);
-        P.queue[pos] = c;
+        cur = xf_mul(cur, joint_transform(st, qrow));
+        if (st.save >= 0) {
+            double* sv = P.fksave + (size_t)st.save * 7 * cs + c;
+            sv[0] = cur.q0; sv[cs] = cur.q1; sv[2 * cs] = cur.q2; sv[3 * cs] = cur.q3;
+            sv[4 * cs] = cur.tx; sv[5 * cs] = cur.ty; sv[6 * cs] = cur.tz;
+        }
+        emit_link(P, s_linkbox, c, st.child, s_emit[st.child], cur);
     }
 }
 
@@ -487,18 +428,22 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const bool counters = (P.flags & kFlagCounters) != 0;
     const float eps2 = P.tri_eps * P.tri_eps;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int qlen = P.counters[0];
     unsigned long long n_bv = 0, n_tri = 0;
 
     for (;;) {
-        int qi = 0;
-        if (lane == 0) qi = atomicAdd(&P.counters[1], 1);
-        qi = __shfl_sync(kFull, qi, 0);
-        if (qi >= qlen) break;
-        const int c = P.queue[qi];
-        const float* xf = P.xf32 + (size_t)c * P.nq * 12;
-        const uint32_t* crow = P.cand + (size_t)c * P.cwords;
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&P.counters[0], 1);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= P.n) break;
+        const float* xf = P.xf32 + (size_t)c * P.ndyn * 12;
+        const float* ab = P.aabb + (size_t)c * P.ndyn * 8;
+        const float* st_ab = P.st_aabb - 8 * (size_t)P.ndyn;     // static slot s lives at st_ab + 8 s
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
+        if (P.pair_mask) {
+            uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
+            for (int i = lane; i < P.mask_words; i += 32) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
+            __syncwarp();
+        }
 
         // warp-uniform state, all in registers
         int sp = 0, spill_count = 0, ntri = 0, ncb = 0;
@@ -506,21 +451,50 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         uint32_t slot_hit = 0;
         bool failed = false;
         uint32_t iters = 0;
+        bool recheck = true;       // a new best may let the broadphase skip the rest of its class
+        int k0 = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+        const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
 
-        for (int w0 = 0; w0 < P.cwords && !failed; w0 += 32) {
-            const uint32_t myword = (w0 + lane < P.cwords) ? crow[w0 + lane] : 0u;
-            unsigned nz = __ballot_sync(kFull, myword != 0u);
-            const bool last_group = w0 + 32 >= P.cwords;
-            while ((nz || (last_group && ncb > 0)) && !failed) {
-                if (nz) {
-                    const int wl = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    const uint32_t m = __shfl_sync(kFull, myword, wl);
-                    if ((m >> lane) & 1u) cbuf[ncb + __popc(m & lt_mask)] = (uint32_t)((w0 + wl) * 32 + lane);
-                    ncb += __popc(m);
-                    __syncwarp();
-                    if (ncb < 32 && (nz || !last_group)) continue;
+        while ((k0 < kend || ncb > 0) && !failed) {
+            if (k0 < kend) {
+                if (!all_pairs && recheck) {
+                    // pairs are in reference order inside each class: once a hit precedes everything left, skip the rest
+                    recheck = false;
+                    if (k0 < P.nenv_dev) { if (best_env < __ldg(&P.pair_orig[k0])) { k0 = P.nenv_dev; recheck = true; continue; } }
+                    else if (best_self < __ldg(&P.pair_orig[k0])) { k0 = kend; continue; }
                 }
+                // ---------------------------------------------------------------- broadphase: 64 pairs, world AABBs
+                const int lim = (k0 < P.nenv_dev && P.nenv_dev < kend) ? P.nenv_dev : kend;     // do not straddle env | self
+                bool ov[2];
+                int kk[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = k0 + 32 * h + lane;
+                    kk[h] = k;
+                    ov[h] = false;
+                    if (k < lim) {
+                        const uint32_t pr = __ldg(&P.pairs[k]);
+                        const int sa = pr & 0xffff, sb = pr >> 16;
+                        const float4* pa = (const float4*)((sa < P.ndyn ? ab : st_ab) + 8 * sa);
+                        const float4* pb = (const float4*)((sb < P.ndyn ? ab : st_ab) + 8 * sb);
+                        const float4 ac = pa[0], ae = pa[1], bc = pb[0], be = pb[1];
+                        ov[h] = fabsf(ac.x - bc.x) <= ae.x + be.x && fabsf(ac.y - bc.y) <= ae.y + be.y && fabsf(ac.z - bc.z) <= ae.z + be.z;
+                    }
+                }
+                k0 = (k0 + 64 < lim) ? k0 + 64 : lim;
+                if (k0 == P.nenv_dev) recheck = true;
+                const unsigned om0 = __ballot_sync(kFull, ov[0]), om1 = __ballot_sync(kFull, ov[1]);
+                if (om0 | om1) {
+                    if (ov[0]) cbuf[ncb + __popc(om0 & lt_mask)] = (uint32_t)kk[0];
+                    ncb += __popc(om0);
+                    if (ov[1]) cbuf[ncb + __popc(om1 & lt_mask)] = (uint32_t)kk[1];
+                    ncb += __popc(om1);
+                    __syncwarp();
+                }
+                if (ncb < 32 && k0 < kend) continue;
+                if (ncb == 0) continue;
+            }
+            {
                 // ---------------------------------------------------------------- a batch of <= 32 root pairs
                 const int cnt = ncb < 32 ? ncb : 32;
                 bool cand = false;
@@ -539,13 +513,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const int la = pr & 0xffff, lb = pr >> 16;
                         float A[12], Bx[12];
                         {
-                            const float4* e = (const float4*)(xf + 12 * la);
+                            const float4* e = la < P.ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - P.ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
                             A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
                         }
                         {
-                            const float4* e = lb < P.nq ? (const float4*)(xf + 12 * lb) : (const float4*)(P.env_xf + 12 * (size_t)(lb - P.nq));
+                            const float4* e = lb < P.ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - P.ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
                             Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
@@ -560,11 +534,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 }
                 // drop the consumed candidates
                 {
-                    const int rest = ncb - cnt;
-                    uint32_t mv = 0;
-                    if (lane < rest) mv = cbuf[cnt + lane];
+                    const int rest = ncb - cnt;                    // <= 63
+                    uint32_t mv0 = 0, mv1 = 0;
+                    if (lane < rest) mv0 = cbuf[cnt + lane];
+                    if (lane + 32 < rest) mv1 = cbuf[cnt + 32 + lane];
                     __syncwarp();
-                    if (lane < rest) cbuf[lane] = mv;
+                    if (lane < rest) cbuf[lane] = mv0;
+                    if (lane + 32 < rest) cbuf[32 + lane] = mv1;
                     ncb = rest;
                     __syncwarp();
                 }
@@ -649,8 +625,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                             slot_hit |= __reduce_or_sync(kFull, hit ? (1u << s) : 0u);
                             const int pe = __reduce_min_sync(kFull, (hit && pidx < P.nenv_total) ? pidx : kNone);
                             const int ps = __reduce_min_sync(kFull, (hit && pidx >= P.nenv_total) ? pidx : kNone);
-                            if (pe < best_env) best_env = pe;
-                            if (ps < best_self) best_self = ps;
+                            if (pe < best_env) { best_env = pe; recheck = true; }
+                            if (ps < best_self) { best_self = ps; recheck = true; }
                         }
                         __syncwarp();
                         continue;

@@ -221,19 +221,18 @@ void pose_to_rt32(const double* x, const double center[3], float* o)
     o[9] = (float)(x[4] - center[0]); o[10] = (float)(x[5] - center[1]); o[11] = (float)(x[6] - center[2]);
 }
 
-struct PairList {
-    std::vector<uint32_t> pairs;     // a | slot_b << 16
+// A plan = one pair list laid out for the device: its slot space (dynamic query links first, then everything static),
+// the FK program pruned to the links it needs, and the static poses / boxes.
+struct Plan {
+    std::vector<uint32_t> pairs;     // slot_a | slot_b << 16
     std::vector<int32_t> orig;
-    int nenv = 0;
+    int nenv = 0, ndyn = 0, nstatic = 0, nsave = 0;
+    std::vector<int32_t> emit;       // [nq] link -> dynamic slot or -1
+    std::vector<ccdev::FkStep> steps;
     DevBuf<uint32_t> d_pairs;
-    DevBuf<int32_t> d_orig;
-    void add(int a, int slot, int o, bool env) { pairs.push_back((uint32_t)a | ((uint32_t)slot << 16)); orig.push_back(o); if (env) nenv++; }
-    cudaError_t upload()
-    {
-        cudaError_t e = d_pairs.upload(pairs);
-        if (e != cudaSuccess) return e;
-        return d_orig.upload(orig);
-    }
+    DevBuf<int32_t> d_orig, d_emit, d_slot_root;
+    DevBuf<float> d_st_xf, d_st_aabb, d_link_box;
+    DevBuf<ccdev::FkStep> d_steps;
 };
 
 bool body_attached(const HBody& a, int other)
@@ -251,19 +250,13 @@ struct cc_query {
     std::vector<int32_t> pair_slot;          // [npairs] slot of the other link
     std::vector<uint8_t> pair_live;          // [npairs] 0: can never collide (disabled / no mesh), kept for indexing only
     int nenv_total = 0, nself_total = 0;
-    PairList full, mainl, hoisted;
+    Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
     bool has_fk = false;
-    std::vector<ccdev::FkStep> steps;       // depth-first order
-    int nsave = 0;                           // link poses parked for later branches
-    DevBuf<ccdev::FkStep> d_steps;
-    DevBuf<int32_t> d_slot_root;
-    DevBuf<float> d_env_xf, d_env_aabb, d_link_box;
-    // per-chunk scratch (grown on demand)
-    int chunk_cap = 0;
+    std::vector<ccdev::FkStep> steps;       // every joint, depth-first order
+    // per-chunk scratch (grown on demand, shared by the plans)
     DevBuf<float> d_xf32, d_aabb;
     DevBuf<double> d_fksave;
-    DevBuf<uint32_t> d_cand;
-    DevBuf<int32_t> d_queue, d_counters;
+    DevBuf<int32_t> d_counters;
     DevBuf<uint32_t> d_hoisted_mask;
     std::vector<uint32_t> hoisted_mask;
     int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
@@ -283,25 +276,21 @@ struct cc_query {
 namespace {
 
 // Bytes of per-chunk scratch one configuration needs.
-size_t scratch_bytes_per_config(const cc_query* Q, int cwords)
+size_t scratch_bytes_per_config(const Plan& pl)
 {
-    return (size_t)Q->nq * 48 + (size_t)Q->nq * 24 + (size_t)Q->nsave * 56 + (size_t)cwords * 4 + 4;
+    return (size_t)pl.ndyn * (48 + 32) + (size_t)pl.nsave * 56;
 }
 
-int ensure_scratch(cc_query* Q, int cap, int cwords)
+int ensure_scratch(cc_query* Q, const Plan& pl, int cap)
 {
-    if (cap <= Q->chunk_cap) return CC_OK;
-    CC_CUDA(Q->d_xf32.reserve((size_t)cap * Q->nq * 12));
-    CC_CUDA(Q->d_aabb.reserve((size_t)cap * Q->nq * 6));
-    CC_CUDA(Q->d_fksave.reserve((size_t)cap * std::max(1, Q->nsave) * 7));
-    CC_CUDA(Q->d_cand.reserve((size_t)cap * cwords));
-    CC_CUDA(Q->d_queue.reserve((size_t)cap));
+    CC_CUDA(Q->d_xf32.reserve((size_t)cap * std::max(1, pl.ndyn) * 12));
+    CC_CUDA(Q->d_aabb.reserve((size_t)cap * std::max(1, pl.ndyn) * 8));
+    CC_CUDA(Q->d_fksave.reserve((size_t)cap * std::max(1, pl.nsave) * 7));
     CC_CUDA(Q->d_counters.reserve(2));
-    Q->chunk_cap = cap;
     return CC_OK;
 }
 
-int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
+int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
            int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st)
 {
     cc_scene* S = Q->scene;
@@ -309,13 +298,13 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
     ccdev::Params P;
     memset(&P, 0, sizeof(P));
     P.nodes = S->d_nodes.p; P.tris = S->d_tris.p;
-    P.slot_root = Q->d_slot_root.p; P.env_xf = Q->d_env_xf.p; P.env_aabb = Q->d_env_aabb.p; P.link_box = Q->d_link_box.p;
+    P.slot_root = pl.d_slot_root.p; P.st_xf = pl.d_st_xf.p; P.st_aabb = pl.d_st_aabb.p; P.link_box = pl.d_link_box.p;
+    P.emit_index = pl.d_emit.p;
     P.pairs = pl.d_pairs.p; P.pair_orig = pl.d_orig.p;
-    P.steps = Q->d_steps.p;
+    P.steps = pl.d_steps.p;
     P.hoisted_mask = use_hoisted ? Q->d_hoisted_mask.p : nullptr;
-    P.nq = Q->nq; P.nslots = Q->nslots; P.npairs_dev = (int)pl.pairs.size(); P.nenv_dev = pl.nenv;
-    P.nenv_total = Q->nenv_total; P.nsteps = (int)Q->steps.size(); P.ncols = Q->ncols;
-    P.cwords = std::max(1, (P.npairs_dev + 31) / 32);
+    P.nq = Q->nq; P.ndyn = pl.ndyn; P.nstatic = pl.nstatic; P.npairs_dev = (int)pl.pairs.size(); P.nenv_dev = pl.nenv;
+    P.nenv_total = Q->nenv_total; P.nsteps = (int)pl.steps.size(); P.ncols = Q->ncols;
     P.hoisted_first_env = use_hoisted ? Q->hoisted_first_env : ccdev::kNone;
     P.hoisted_first_self = use_hoisted ? Q->hoisted_first_self : ccdev::kNone;
     P.mask_words = Q->mask_words;
@@ -330,19 +319,18 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
     const int row_doubles = (flags & ccdev::kFlagPoseMode) ? Q->nq * 8 : Q->ncols;
 
     // ---- chunking: the scratch of one chunk stays around a GB at most
-    const int cw_alloc = std::max(1, ((int)Q->full.pairs.size() + 31) / 32);   // the largest of this query's pair lists
-    const size_t per_cfg = scratch_bytes_per_config(Q, cw_alloc);
+    const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
     int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     {
-        int rc = ensure_scratch(Q, chunk, cw_alloc);
+        int rc = ensure_scratch(Q, pl, chunk);
         if (rc != CC_OK) return rc;
     }
-    P.cap = Q->chunk_cap;
-    P.xf32 = Q->d_xf32.p; P.aabb = Q->d_aabb.p; P.fksave = Q->d_fksave.p; P.cand = Q->d_cand.p; P.queue = Q->d_queue.p;
+    P.cap = chunk;
+    P.xf32 = Q->d_xf32.p; P.aabb = Q->d_aabb.p; P.fksave = Q->d_fksave.p;
     P.counters = Q->d_counters.p;
 
-    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.nslots - P.nq);
+    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
     if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
     if (fk_smem > 48 * 1024)
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
@@ -366,7 +354,7 @@ int launch(cc_query* Q, const PairList& pl, bool use_hoisted, const double* d_q,
         P.pair_mask = d_mask ? d_mask + (size_t)off * Q->mask_words : nullptr;
         P.fk_out = d_fk ? d_fk + (size_t)off * Q->nq * 8 : nullptr;
         P.work_out = (Q->trace_work && !fk_only) ? Q->d_work.p + off : nullptr;
-        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters.p, 0, 2 * sizeof(int32_t), st));
+        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters.p, 0, sizeof(int32_t), st));
         ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
@@ -597,6 +585,114 @@ int cc_scene_commit(cc_scene* s)
 }
 
 // ---------------------------------------------------------------------------------------------- queries
+// world AABB (base-centred) of a link's already inflated root box at its current pose, in double, rounded outwards
+static void static_aabb(const HLink& L, const double center[3], float* o)
+{
+    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    if (L.nodes.empty()) { o[0] = o[1] = o[2] = 1e30f; return; }          // never overlaps anything
+    const double* x = L.xf;
+    const double il = 2.0 / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+    const double Rm[9] = {1 - il * (q2 * q2 + q3 * q3), il * (q1 * q2 - q0 * q3), il * (q1 * q3 + q0 * q2),
+                          il * (q1 * q2 + q0 * q3), 1 - il * (q1 * q1 + q3 * q3), il * (q2 * q3 - q0 * q1),
+                          il * (q1 * q3 - q0 * q2), il * (q2 * q3 + q0 * q1), 1 - il * (q1 * q1 + q2 * q2)};
+    for (int r = 0; r < 3; ++r) {
+        double c = x[4 + r] - center[r], e = 0;
+        for (int k = 0; k < 3; ++k) { c += Rm[3 * r + k] * (double)L.nodes[0].c[k]; e += (fabs(Rm[3 * r + k]) + 1e-6) * (double)L.nodes[0].e[k]; }
+        const float cf = (float)c;
+        e += fabs(c - (double)cf) + 1e-6;
+        float ef = (float)e;
+        if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
+        o[r] = cf; o[4 + r] = ef;
+    }
+}
+
+// Lay one pair list out for the device.  `dynamic[l]`: query link l gets a per-configuration pose (scratch slot); every
+// other link a pair names (environment links, query links no active DOF moves) becomes a static slot at its current pose.
+static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, const std::vector<uint8_t>& dynamic, bool with_fk)
+{
+    cc_scene* S = Q->scene;
+    HBody* B = S->bodies[Q->body];
+    const int nl = Q->nq;
+    pl.emit.assign(std::max(1, nl), -1);
+    pl.ndyn = 0;
+    for (int l = 0; l < nl; ++l) if (dynamic[l]) pl.emit[l] = pl.ndyn++;
+    std::vector<std::pair<int, int>> statics;                // (body, link) in order of first use
+    auto static_slot = [&](int body, int link) {
+        for (size_t i = 0; i < statics.size(); ++i) if (statics[i].first == body && statics[i].second == link) return (int)i;
+        statics.push_back(std::make_pair(body, link));
+        return (int)statics.size() - 1;
+    };
+    std::vector<std::pair<int, int>> enc;                    // (slot_a, static index or -1 - dyn index) resolved after counting
+    pl.pairs.clear(); pl.orig.clear(); pl.nenv = 0;
+    std::vector<int> sa_v, sb_v;
+    for (int p : plist) {
+        const int a = Q->quads[4 * p], ob = Q->quads[4 * p + 1], j = Q->quads[4 * p + 2], cls = Q->quads[4 * p + 3];
+        const int sa = pl.emit[a] >= 0 ? pl.emit[a] : -1 - static_slot(Q->body, a);
+        int sb;
+        if (cls == 1) sb = pl.emit[j] >= 0 ? pl.emit[j] : -1 - static_slot(Q->body, j);
+        else sb = -1 - static_slot(ob, j);
+        sa_v.push_back(sa); sb_v.push_back(sb);
+        pl.orig.push_back(p);
+        if (cls == 0) pl.nenv++;
+    }
+    pl.nstatic = (int)statics.size();
+    if (pl.ndyn + pl.nstatic > 0xffff) return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots");
+    for (size_t i = 0; i < sa_v.size(); ++i) {
+        const uint32_t sa = sa_v[i] >= 0 ? (uint32_t)sa_v[i] : (uint32_t)(pl.ndyn + (-1 - sa_v[i]));
+        const uint32_t sb = sb_v[i] >= 0 ? (uint32_t)sb_v[i] : (uint32_t)(pl.ndyn + (-1 - sb_v[i]));
+        pl.pairs.push_back(sa | (sb << 16));
+    }
+    std::vector<int32_t> roots((size_t)std::max(1, pl.ndyn + pl.nstatic), 0);
+    std::vector<float> linkbox((size_t)std::max(1, pl.ndyn) * 8, 0.f), stxf((size_t)std::max(1, pl.nstatic) * 12, 0.f),
+        staabb((size_t)std::max(1, pl.nstatic) * 8, 0.f);
+    for (int l = 0; l < nl; ++l) {
+        if (pl.emit[l] < 0) continue;
+        const HLink& L = B->links[l];
+        roots[pl.emit[l]] = L.node_base < 0 ? 0 : L.node_base;
+        float* o = &linkbox[(size_t)pl.emit[l] * 8];
+        if (!L.nodes.empty()) { for (int k = 0; k < 3; ++k) { o[k] = L.nodes[0].c[k]; o[3 + k] = L.nodes[0].e[k]; } o[6] = 1.0f; }
+        else { o[0] = o[1] = o[2] = 0.f; o[3] = o[4] = o[5] = -1e30f; }   // no geometry: an AABB that overlaps nothing
+    }
+    for (int i = 0; i < pl.nstatic; ++i) {
+        const HLink& L = S->bodies[statics[i].first]->links[statics[i].second];
+        roots[pl.ndyn + i] = L.node_base < 0 ? 0 : L.node_base;
+        pose_to_rt32(L.xf, Q->center, &stxf[(size_t)i * 12]);
+        static_aabb(L, Q->center, &staabb[(size_t)i * 8]);
+    }
+    // FK program pruned to the ancestors of the dynamic slots
+    pl.steps.clear();
+    pl.nsave = 0;
+    if (with_fk && Q->has_fk) {
+        std::vector<uint8_t> need(nl, 0);
+        for (int i = (int)Q->steps.size() - 1; i >= 0; --i) {
+            const ccdev::FkStep& st = Q->steps[i];
+            if (pl.emit[st.child] >= 0) need[st.child] = 1;
+            if (need[st.child]) need[st.parent] = 1;         // depth-first order: children come after their parent
+        }
+        for (const ccdev::FkStep& st : Q->steps) if (need[st.child]) pl.steps.push_back(st);
+        std::vector<int> save_of_link(nl, -1);
+        for (size_t i = 0; i < pl.steps.size(); ++i) {
+            ccdev::FkStep& st = pl.steps[i];
+            st.save = -1;
+            if (i > 0 && pl.steps[i - 1].child == st.parent) st.load_parent = -2;
+            else if (st.parent == 0) st.load_parent = -1;
+            else {
+                if (save_of_link[st.parent] < 0) {
+                    save_of_link[st.parent] = pl.nsave++;
+                    for (size_t j = 0; j < i; ++j) if (pl.steps[j].child == st.parent) pl.steps[j].save = save_of_link[st.parent];
+                }
+                st.load_parent = save_of_link[st.parent];
+            }
+        }
+    }
+    CC_CUDA(pl.d_pairs.upload(pl.pairs)); CC_CUDA(pl.d_orig.upload(pl.orig)); CC_CUDA(pl.d_emit.upload(pl.emit));
+    CC_CUDA(pl.d_slot_root.upload(roots)); CC_CUDA(pl.d_link_box.upload(linkbox));
+    CC_CUDA(pl.d_st_xf.upload(stxf)); CC_CUDA(pl.d_st_aabb.upload(staabb));
+    CC_CUDA(pl.d_steps.upload(pl.steps));
+    return CC_OK;
+}
+
 static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const std::vector<int>& slot_link,
                         const int32_t* active, int nactive, bool all_dofs_active, bool allow_hoist)
 {
@@ -677,21 +773,6 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
             memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
             Q->steps.push_back(st);
         }
-        std::vector<int> save_of_link(nl, -1);
-        Q->nsave = 0;
-        for (size_t i = 0; i < Q->steps.size(); ++i) {
-            ccdev::FkStep& st = Q->steps[i];
-            st.save = -1;
-            if (i > 0 && Q->steps[i - 1].child == st.parent) st.load_parent = -2;
-            else if (st.parent == 0) st.load_parent = -1;
-            else {
-                if (save_of_link[st.parent] < 0) {
-                    save_of_link[st.parent] = Q->nsave++;
-                    for (size_t j = 0; j < i; ++j) if (Q->steps[j].child == st.parent) Q->steps[j].save = save_of_link[st.parent];
-                }
-                st.load_parent = save_of_link[st.parent];
-            }
-        }
         for (int l = 1; l < nl; ++l)
             if (depth[l] < 0 && B->links[l].ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
     } else {
@@ -701,51 +782,14 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
     Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
 
-    // ---- slots: root nodes, static poses, broadphase boxes
-    Q->nslots = (int)slot_body.size();
-    std::vector<int32_t> roots(Q->nslots, 0);
-    const int nenv = std::max(1, Q->nslots - nl);
-    std::vector<float> envxf((size_t)nenv * 12, 0.f), envbox((size_t)nenv * 8, 0.f), linkbox((size_t)std::max(1, nl) * 8, 0.f);
-    for (int sidx = 0; sidx < Q->nslots; ++sidx) {
-        const HLink& L = S->bodies[slot_body[sidx]]->links[slot_link[sidx]];
-        roots[sidx] = L.node_base < 0 ? 0 : L.node_base;
-        if (sidx < nl) {
-            if (!L.nodes.empty()) {
-                float* o = &linkbox[(size_t)sidx * 8];
-                for (int k = 0; k < 3; ++k) { o[k] = L.nodes[0].c[k]; o[3 + k] = L.nodes[0].e[k]; }
-                o[6] = 1.0f;
-            }
-        } else {
-            pose_to_rt32(L.xf, Q->center, &envxf[(size_t)(sidx - nl) * 12]);
-            float* o = &envbox[(size_t)(sidx - nl) * 8];
-            if (L.nodes.empty()) { o[0] = o[1] = o[2] = 1e30f; continue; }      // never overlaps anything
-            // world AABB of the (already inflated) root box, in double, rounded outwards
-            const double* x = L.xf;
-            const double il = 2.0 / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-            const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
-            const double Rm[9] = {1 - il * (q2 * q2 + q3 * q3), il * (q1 * q2 - q0 * q3), il * (q1 * q3 + q0 * q2),
-                                  il * (q1 * q2 + q0 * q3), 1 - il * (q1 * q1 + q3 * q3), il * (q2 * q3 - q0 * q1),
-                                  il * (q1 * q3 - q0 * q2), il * (q2 * q3 + q0 * q1), 1 - il * (q1 * q1 + q2 * q2)};
-            for (int r = 0; r < 3; ++r) {
-                double c = x[4 + r] - Q->center[r], e = 0;
-                for (int k = 0; k < 3; ++k) { c += Rm[3 * r + k] * (double)L.nodes[0].c[k]; e += (fabs(Rm[3 * r + k]) + 1e-6) * (double)L.nodes[0].e[k]; }
-                const float cf = (float)c;
-                e += fabs(c - (double)cf) + 1e-6;
-                float ef = (float)e;
-                if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
-                o[r] = cf; o[3 + r] = ef;
-            }
-        }
-    }
-
-    // ---- split the pair list
+    // ---- split the pair list and lay the three plans out
     const int np = (int)Q->quads.size() / 4;
     Q->mask_words = std::max(1, (np + 31) / 32);
+    std::vector<int> p_full, p_main, p_hoist;
     for (int p = 0; p < np; ++p) {
         if (!Q->pair_live[p]) continue;
         const int a = Q->quads[4 * p], cls = Q->quads[4 * p + 3];
-        const int slot = Q->pair_slot[p];
-        Q->full.add(a, slot, p, cls == 0);
+        p_full.push_back(p);
         bool hoist = false;
         if (allow_hoist && Q->has_fk) {
             if (cls == 0) hoist = !moves[a];
@@ -755,15 +799,19 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
                 for (int d : act) if (affects(d, a) != affects(d, b)) { hoist = false; break; }
             }
         }
-        (hoist ? Q->hoisted : Q->mainl).add(a, slot, p, cls == 0);
+        (hoist ? p_hoist : p_main).push_back(p);
+    }
+    std::vector<uint8_t> all_dynamic(nl, 1), main_dynamic(nl, 0);
+    for (int p : p_main) {
+        const int a = Q->quads[4 * p];
+        if (moves[a]) main_dynamic[a] = 1;
+        if (Q->quads[4 * p + 3] == 1) { const int b = Q->quads[4 * p + 2]; if (moves[b]) main_dynamic[b] = 1; }
     }
     CC_CUDA(cudaSetDevice(S->device));
-    CC_CUDA(Q->full.upload()); CC_CUDA(Q->mainl.upload()); CC_CUDA(Q->hoisted.upload());
-    CC_CUDA(Q->d_steps.upload(Q->steps));
-    CC_CUDA(Q->d_slot_root.upload(roots));
-    CC_CUDA(Q->d_env_xf.upload(envxf));
-    CC_CUDA(Q->d_env_aabb.upload(envbox));
-    CC_CUDA(Q->d_link_box.upload(linkbox));
+    int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
+    if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
+    if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
+    if (rc != CC_OK) return rc;
     Q->hoisted_mask.assign(Q->mask_words, 0u);
     CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
 
@@ -773,7 +821,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
         if (!Q->cur_active.empty())
             CC_CUDA(cudaMemcpy(Q->d_q.p, Q->cur_active.data(), Q->cur_active.size() * sizeof(double), cudaMemcpyHostToDevice));
         CC_CUDA(Q->d_mask.reserve(Q->mask_words));
-        int rc = launch(Q, Q->hoisted, false, Q->d_q.p, 1, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS, nullptr, nullptr,
+        rc = launch(Q, Q->hoisted, false, Q->d_q.p, 1, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS, nullptr, nullptr,
                         nullptr, Q->d_mask.p, nullptr, 0);
         if (rc != CC_OK) return rc;
         CC_CUDA(cudaMemcpy(Q->hoisted_mask.data(), Q->d_mask.p, Q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -968,7 +1016,7 @@ static int run_host(cc_query* q, const double* in, size_t in_doubles, int n, int
     if (fs) CC_CUDA(q->d_fs.reserve(n));
     if (mask) CC_CUDA(q->d_mask.reserve((size_t)n * q->mask_words));
     if (fk) CC_CUDA(q->d_fk.reserve((size_t)n * q->nq * 8));
-    const PairList& pl = pose_mode ? q->full : q->mainl;
+    const Plan& pl = pose_mode ? q->full : (fk ? q->hoisted : q->mainl);   // FK read-back needs every joint: the unpruned program
     int rc = launch(q, pl, !pose_mode, q->d_q.p, n, kflags, verdict ? q->d_verdict.p : nullptr, fe ? q->d_fe.p : nullptr,
                     fs ? q->d_fs.p : nullptr, mask ? q->d_mask.p : nullptr, fk ? q->d_fk.p : nullptr, 0);
     if (rc != CC_OK) return rc;
