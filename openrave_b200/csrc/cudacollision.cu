@@ -96,8 +96,10 @@ struct cc_scene {
     bool committed = false;
     DevBuf<float4> d_nodes, d_tris;
     int total_nodes = 0, total_tris = 0;
-    DevBuf<uint2> d_spill;
+    DevBuf<uint2> d_spill[2];               // one per pipeline lane (two chunks are in flight at a time)
     int spill_warps = 0;
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     DevBuf<int32_t> d_err;                  // [0] error flag (a traversal overflowed its spill area)
     int trav_blocks_per_sm = 0;             // occupancy of cc_traverse_kernel (queried once)
     DevBuf<unsigned long long> d_stats;     // [0] bv, [1] tri
@@ -111,6 +113,8 @@ struct cc_scene {
         for (HBody* b : bodies) delete b;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (int i = 0; i < 2; ++i) { if (ev_join[i]) cudaEventDestroy(ev_join[i]); if (lane_stream[i]) cudaStreamDestroy(lane_stream[i]); }
     }
 };
 
@@ -254,9 +258,9 @@ struct cc_query {
     bool has_fk = false;
     std::vector<ccdev::FkStep> steps;       // every joint, depth-first order
     // per-chunk scratch (grown on demand, shared by the plans)
-    DevBuf<float> d_xf32, d_aabb;
-    DevBuf<double> d_fksave;
-    DevBuf<int32_t> d_counters;
+    DevBuf<float> d_xf32[2], d_aabb[2];      // two sets: consecutive chunks overlap on two streams
+    DevBuf<double> d_fksave[2];
+    DevBuf<int32_t> d_counters[2];
     DevBuf<uint32_t> d_hoisted_mask;
     std::vector<uint32_t> hoisted_mask;
     int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
@@ -281,12 +285,14 @@ size_t scratch_bytes_per_config(const Plan& pl)
     return (size_t)pl.ndyn * (48 + 32) + (size_t)pl.nsave * 56;
 }
 
-int ensure_scratch(cc_query* Q, const Plan& pl, int cap)
+int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
 {
-    CC_CUDA(Q->d_xf32.reserve((size_t)cap * std::max(1, pl.ndyn) * 12));
-    CC_CUDA(Q->d_aabb.reserve((size_t)cap * std::max(1, pl.ndyn) * 8));
-    CC_CUDA(Q->d_fksave.reserve((size_t)cap * std::max(1, pl.nsave) * 7));
-    CC_CUDA(Q->d_counters.reserve(2));
+    for (int k = 0; k < nsets; ++k) {
+        CC_CUDA(Q->d_xf32[k].reserve((size_t)cap * std::max(1, pl.ndyn) * 12));
+        CC_CUDA(Q->d_aabb[k].reserve((size_t)cap * std::max(1, pl.ndyn) * 8));
+        CC_CUDA(Q->d_fksave[k].reserve((size_t)cap * std::max(1, pl.nsave) * 7));
+        CC_CUDA(Q->d_counters[k].reserve(2));
+    }
     return CC_OK;
 }
 
@@ -314,21 +320,31 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     P.tri_eps = S->tri_eps;
     P.err_flag = S->d_err.p;
     P.stats = S->d_stats.p;
-    P.spill_cap = 4096;
+    P.spill_cap = 2048;
     const bool fk_only = (flags & ccdev::kFlagFkOnly) != 0;
     const int row_doubles = (flags & ccdev::kFlagPoseMode) ? Q->nq * 8 : Q->ncols;
 
-    // ---- chunking: the scratch of one chunk stays around a GB at most
+    // ---- chunking.  Big batches are cut into >= 4 chunks that alternate between two internal streams: while the
+    // persistent traversal kernel of chunk i drains its last (long) configurations, the FK kernel and the traversal
+    // blocks of chunk i+1 fill the SMs it has already left.  Scratch per set stays around half a GB at most.
     const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
-    int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
+    int chunk = (int)std::min<size_t>(131072, std::max<size_t>(1024, ((size_t)1 << 29) / per_cfg));
+    if (n >= 262144) chunk = std::min(chunk, std::max(65536, ((n + 3) / 4 + 127) / 128 * 128));   // smaller chunks only multiply tails
     chunk = std::min(chunk, (n + 127) / 128 * 128);
+    const int nchunks = (n + chunk - 1) / chunk;
+    const bool overlap = nchunks >= 2;
     {
-        int rc = ensure_scratch(Q, pl, chunk);
+        int rc = ensure_scratch(Q, pl, chunk, overlap ? 2 : 1);
         if (rc != CC_OK) return rc;
     }
     P.cap = chunk;
-    P.xf32 = Q->d_xf32.p; P.aabb = Q->d_aabb.p; P.fksave = Q->d_fksave.p;
-    P.counters = Q->d_counters.p;
+    if (overlap && !S->lane_stream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
+            CC_CUDA(cudaEventCreateWithFlags(&S->ev_join[i], cudaEventDisableTiming));
+        }
+        CC_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+    }
 
     const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
     if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
@@ -343,9 +359,23 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         S->trav_blocks_per_sm = per_sm;
     }
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
+    // spill areas: one per pipeline lane, sized for a full persistent grid
+    const int full_warps = S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock;
+    if (!fk_only && (S->spill_warps < full_warps || (overlap && !S->d_spill[1].p))) {
+        CC_CUDA(cudaDeviceSynchronize());            // (first launches only) nobody may still be using the old areas
+        for (int k = 0; k < (overlap ? 2 : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
+        S->spill_warps = full_warps;
+    }
     CC_CUDA(cudaEventRecord(S->ev0, st));
-    for (int off = 0; off < n; off += chunk) {
+    if (overlap) {
+        CC_CUDA(cudaEventRecord(S->ev_fork, st));
+        for (int i = 0; i < 2; ++i) CC_CUDA(cudaStreamWaitEvent(S->lane_stream[i], S->ev_fork, 0));
+    }
+    int ci = 0;
+    for (int off = 0; off < n; off += chunk, ++ci) {
         const int m = std::min(chunk, n - off);
+        const int k = overlap ? (ci & 1) : 0;
+        cudaStream_t cs = overlap ? S->lane_stream[k] : st;
         P.n = m;
         P.q = d_q ? d_q + (size_t)off * row_doubles : nullptr;
         P.verdict = d_verdict ? d_verdict + off : nullptr;
@@ -354,8 +384,10 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.pair_mask = d_mask ? d_mask + (size_t)off * Q->mask_words : nullptr;
         P.fk_out = d_fk ? d_fk + (size_t)off * Q->nq * 8 : nullptr;
         P.work_out = (Q->trace_work && !fk_only) ? Q->d_work.p + off : nullptr;
-        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters.p, 0, sizeof(int32_t), st));
-        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
+        P.xf32 = Q->d_xf32[k].p; P.aabb = Q->d_aabb[k].p; P.fksave = Q->d_fksave[k].p;
+        P.counters = Q->d_counters[k].p;
+        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
+        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
         if (fk_only) continue;
@@ -363,16 +395,16 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         int grid = S->trav_blocks_per_sm * S->num_sms;
         const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
         if (grid > need) grid = need;
-        const int warps = grid * ccdev::kWarpsPerBlock;
-        if (warps > S->spill_warps) {
-            CC_CUDA(cudaStreamSynchronize(st));      // (first launches only) nobody may still be using the old area
-            CC_CUDA(S->d_spill.reserve((size_t)S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock * P.spill_cap));
-            S->spill_warps = S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock;
-        }
-        P.spill = S->d_spill.p;
-        ccdev::cc_traverse_kernel<<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, st>>>(P);
+        P.spill = S->d_spill[k].p;
+        ccdev::cc_traverse_kernel<<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
+    }
+    if (overlap) {
+        for (int i = 0; i < 2; ++i) {
+            CC_CUDA(cudaEventRecord(S->ev_join[i], S->lane_stream[i]));
+            CC_CUDA(cudaStreamWaitEvent(st, S->ev_join[i], 0));
+        }
     }
     CC_CUDA(cudaEventRecord(S->ev1, st));
     S->ev_pending = true;
