@@ -44,6 +44,10 @@ WORKLOADS = {
     "hironx_table_1m": ("hironxtable", 1000000, 4, None,
                         "HIRO-NX dual arm (robots/kawada-hironx.zae: 24 links, 23 DOF, 24.1k tris) + data/ikeatable.kinbody.xml: 1M "
                         "uniform-random configs over all DOFs, self-collision dominated (BASELINE.json configs[3])"),
+    "wam_clutter200_1250k": ("clutter:200:22", 1250000, 5, "arm",
+                             "Barrett WAM arm (7 active DOF, segway base disabled) vs synthetic clutter of 200 obstacles x 9 680-triangle "
+                             "geodesic spheres (1.94M tris, 217 MB of BVH + triangles: larger than L2), 1.25M configs per GPU = 10M "
+                             "sharded over 8 GPUs (BASELINE.json configs[4]; scene generated from seed 5 by openrave_b200/clutter.py)"),
 }
 DEFAULT_WORKLOAD = "pr2_pr2test1_1m"
 METRIC = "collision-checked configs/sec (FK+env+self)"
@@ -53,6 +57,11 @@ UNIT = "configs/s"
 def load_world(workload):
     from openrave_b200.environment import Environment
     scene, n, seed, manip, _ = WORKLOADS[workload]
+    if scene.startswith("clutter:"):
+        from openrave_b200 import clutter
+        _, nob, freq = scene.split(":")
+        env, robot = clutter.make_clutter_environment(clutter.default_fixture(), nobstacles=int(nob), freq=int(freq), seed=seed)
+        return env, robot, n, seed
     env = Environment()
     env.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
     robot = env.GetRobots()[0]
@@ -258,6 +267,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    launches0 = cc.GetStatistics()["launches"]
     evs = []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -271,6 +281,7 @@ def main():
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
+    launches_timed = cc.GetStatistics()["launches"] - launches0    # cc_fk_kernel + cc_traverse_kernel per chunk
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     ms = sum(ms_steps) / len(ms_steps)
     kernel_ms = ms
@@ -311,7 +322,7 @@ def main():
                            "colliding_fraction": float((v_last != 0).mean())},
                 "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * ndof * 8),
                         "d2h_bytes_per_step": int(n * 12)},
-                "gpu_launches": int(args.steps),
+                "gpu_launches": int(launches_timed),
                 "clocks": sampler.summary(),
                 "wall_s_timed_region": t_wall}
         peak, peak_src = peaks()
@@ -324,9 +335,9 @@ def main():
             bytes_per_config = cnt[0] * 2 * 64 + cnt[1] * 2 * 36 + 8 * ndof + 16
             achieved = n * bytes_per_config / (kernel_ms / 1000.0) / 1e9
             traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-            if os.path.isfile(tp):
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+            if os.path.isfile(tp):   # dram bytes of one step's kernels, from the committed `ncu --set full` capture
+                traffic = json.load(open(tp)).get("dram_bytes_per_step")
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                 "traffic": traffic, "peak_source": peak_src,
                                 "algorithmic_bytes_per_config": bytes_per_config,
