@@ -8,7 +8,9 @@ import bench
 from openrave_b200.checker import CudaCollisionChecker, BATCH_ENV, BATCH_SELF, BATCH_ALL_PAIRS
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-env, robot, _, seed = bench.load_world("wam_lab1_100k")
+workload = sys.argv[2] if len(sys.argv) > 2 else "wam_lab1_100k"
+env, robot, _, seed = bench.load_world(workload)
+print("==", workload, n)
 cc = CudaCollisionChecker(env, 0)
 env.SetCollisionChecker(cc)
 q = bench.sample(robot, n, seed)
@@ -36,3 +38,6 @@ print("work trace: total iterations %d, mean %.1f, zero-work configs %.3f" % (w.
 print("  percentiles 50/90/99/99.9/max:", [int(np.percentile(w, p)) for p in (50, 90, 99, 99.9)], int(w.max()))
 print("  top 10:", srt[:10].tolist(), " share of top 0.1%%: %.3f" % (srt[:max(1, n // 1000)].sum() / max(1, w.sum())))
 print("  heaviest configs collide?", [(int(i), int(v[i])) for i in np.argsort(-w)[:6]])
+for name, sel in (("free", v == 0), ("env only", v == 1), ("self only", v == 2), ("both", v == 3)):
+    if sel.any():
+        print("  %-10s share %.3f  mean iterations %.1f  share of work %.3f" % (name, sel.mean(), w[sel].mean(), w[sel].sum() / max(1, w.sum())))
