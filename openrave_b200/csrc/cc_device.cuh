@@ -24,6 +24,13 @@
 #ifndef CC_EDGE_AXES
 #define CC_EDGE_AXES 0
 #endif
+#ifndef CC_TRI_T1
+#define CC_TRI_T1 16     // queued leaf pairs that trigger a face-normal pass (contacts found early prune the most work:
+                         // measured 16/8 > 32/16 > 32/32 on all workloads, profiles/r01c_ab_tri.log)
+#endif
+#ifndef CC_TRI_T2
+#define CC_TRI_T2 8      // survivors that trigger an edge-axes pass
+#endif
 #include <stdint.h>
 
 namespace ccdev {
@@ -31,11 +38,13 @@ namespace ccdev {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMinBlocksPerSM = 8;   // 32 warps / SM: registers capped at 64 per thread
 constexpr int kFkThreads = 128;
-constexpr int kStackCap = 384;       // items of shared-memory LIFO per warp
+constexpr int kStackCap = 320;       // items of shared-memory LIFO per warp
 constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
 constexpr int kNumSlots = 32;        // root pairs traversed together
 constexpr int kTriQCap = 96;         // pending leaf x leaf tests (drained 32 at a time)
-constexpr int kCandCap = 96;         // pending candidate pair indices (64 tested per step, drained 32 at a time)
+constexpr int kTriQ2Cap = 64;        // leaf x leaf tests that survived the two face-normal axes (15 axes left, drained 32 at a time)
+constexpr int kBroadPerLane = 4;     // broadphase pairs per lane per step (independent loads in flight)
+constexpr int kCandCap = 32 * kBroadPerLane + 32;   // pending candidate pair indices (a step only runs with < 32 pending)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNone = 0x7fffffff;
 
@@ -248,17 +257,24 @@ __device__ __forceinline__ bool axis_overlaps(V3 ax, V3 p1, V3 p2, V3 q0, V3 q1,
     return gap * gap <= eps2 * dot(ax, ax);
 }
 
-// TriContact (pqp/PQP.cpp:375-459): 17 axes in the reference's order n1, m1, e_i x f_j, e_i x n1, f_i x m1.
-__device__ __forceinline__ bool tri_contact(V3 P0, V3 P1, V3 P2, V3 Q0, V3 Q1, V3 Q2, float eps2)
+// TriContact (pqp/PQP.cpp:375-459): 17 axes n1, m1, e_i x f_j, e_i x n1, f_i x m1.  The verdict is the AND over all axes,
+// so the test is cut in two: the two face normals (which separate most non-touching leaf pairs) run on every queued pair,
+// the other 15 axes only on the survivors, re-batched 32 at a time so the expensive part runs on full warps.
+// p1, p2, q0, q1, q2 are the vertices after the shift by -P0 (P0 is the origin).
+__device__ __forceinline__ bool tri_contact_normals(V3 p1, V3 p2, V3 q0, V3 q1, V3 q2, float eps2)
 {
-    V3 p1 = P1 - P0, p2 = P2 - P0;
-    V3 q0 = Q0 - P0, q1 = Q1 - P0, q2 = Q2 - P0;
+    V3 n1 = cross(p1, p2 - p1);
+    if (!axis_overlaps(n1, p1, p2, q0, q1, q2, eps2)) return false;
+    V3 m1 = cross(q1 - q0, q2 - q1);
+    return axis_overlaps(m1, p1, p2, q0, q1, q2, eps2);
+}
+
+__device__ __forceinline__ bool tri_contact_edges(V3 p1, V3 p2, V3 q0, V3 q1, V3 q2, float eps2)
+{
     V3 e1 = p1, e2 = p2 - p1, e3 = v3(-p2.x, -p2.y, -p2.z);
     V3 f1 = q1 - q0, f2 = q2 - q1, f3 = q0 - q2;
     V3 n1 = cross(e1, e2);
-    if (!axis_overlaps(n1, p1, p2, q0, q1, q2, eps2)) return false;
     V3 m1 = cross(f1, f2);
-    if (!axis_overlaps(m1, p1, p2, q0, q1, q2, eps2)) return false;
     if (!axis_overlaps(cross(e1, f1), p1, p2, q0, q1, q2, eps2)) return false;
     if (!axis_overlaps(cross(e1, f2), p1, p2, q0, q1, q2, eps2)) return false;
     if (!axis_overlaps(cross(e1, f3), p1, p2, q0, q1, q2, eps2)) return false;
@@ -275,6 +291,26 @@ __device__ __forceinline__ bool tri_contact(V3 P0, V3 P1, V3 P2, V3 Q0, V3 Q1, V
     if (!axis_overlaps(cross(f2, m1), p1, p2, q0, q1, q2, eps2)) return false;
     if (!axis_overlaps(cross(f3, m1), p1, p2, q0, q1, q2, eps2)) return false;
     return true;
+}
+
+// Vertices of one queued leaf pair in tree A's frame, shifted by -P0.
+__device__ __forceinline__ void load_tri_pair(const float4* __restrict__ tris, const float* __restrict__ rt, uint32_t ta_idx, uint32_t tb_idx,
+                                              V3& p1, V3& p2, V3& q0, V3& q1, V3& q2)
+{
+    const float4* ta = tris + 3 * (size_t)ta_idx;
+    const float4* tb = tris + 3 * (size_t)tb_idx;
+    const float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2);
+    const float4 u0 = __ldg(tb), u1 = __ldg(tb + 1), u2 = __ldg(tb + 2);
+    const float r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3], r4 = rt[4], r5 = rt[5], r6 = rt[6], r7 = rt[7], r8 = rt[8];
+    const float t0 = rt[9] - a0.x, t1 = rt[10] - a0.y, t2 = rt[11] - a0.z;
+    p1 = v3(a1.x - a0.x, a1.y - a0.y, a1.z - a0.z);
+    p2 = v3(a2.x - a0.x, a2.y - a0.y, a2.z - a0.z);
+    q0 = v3(fmaf(r0, u0.x, fmaf(r1, u0.y, fmaf(r2, u0.z, t0))), fmaf(r3, u0.x, fmaf(r4, u0.y, fmaf(r5, u0.z, t1))),
+            fmaf(r6, u0.x, fmaf(r7, u0.y, fmaf(r8, u0.z, t2))));
+    q1 = v3(fmaf(r0, u1.x, fmaf(r1, u1.y, fmaf(r2, u1.z, t0))), fmaf(r3, u1.x, fmaf(r4, u1.y, fmaf(r5, u1.z, t1))),
+            fmaf(r6, u1.x, fmaf(r7, u1.y, fmaf(r8, u1.z, t2))));
+    q2 = v3(fmaf(r0, u2.x, fmaf(r1, u2.y, fmaf(r2, u2.z, t0))), fmaf(r3, u2.x, fmaf(r4, u2.y, fmaf(r5, u2.z, t1))),
+            fmaf(r6, u2.x, fmaf(r7, u2.y, fmaf(r8, u2.z, t2))));
 }
 
 __device__ __forceinline__ void relative_pose(const float* A, const float* B, float* R, float* t)
@@ -408,7 +444,27 @@ cc_fk_kernel(const __grid_constant__ Params P)
 
 // ================================================================================================ kernel 2: traversal
 constexpr size_t kWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 4 + (size_t)kStackCap * 8 + (size_t)kTriQCap * 8 +
-                                  (size_t)kCandCap * 4;
+                                  (size_t)kTriQ2Cap * 8 + (size_t)kCandCap * 4;
+
+// Warp-cooperative in-place compaction of a queue of {x | slot << 26, y} entries: drops the entries of slots that are dead
+// (their pair already has a contact, or a pair that precedes them in reference order has one).  Runs only when a contact
+// was just found, so the descent loop itself never has to ask whether an item is still wanted.
+__device__ __forceinline__ int filter_queue(uint2* q, int count, uint32_t dead_slots, int lane, unsigned lt_mask)
+{
+    int w = 0;
+    for (int b = 0; b < count; b += 32) {
+        const int i = b + lane;
+        uint2 it = make_uint2(0u, 0u);
+        bool keep = false;
+        if (i < count) { it = q[i]; keep = !((dead_slots >> (it.x >> 26)) & 1u); }
+        const unsigned m = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) q[w + __popc(m & lt_mask)] = it;
+        w += __popc(m);
+        __syncwarp();
+    }
+    return w;
+}
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
@@ -421,13 +477,15 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 24);    // [kNumSlots] original pair index
     uint2* stack = (uint2*)(slot_pair + kNumSlots);               // [kStackCap] {x | slot<<26, y | side<<31}
     uint2* triq = stack + kStackCap;                              // [kTriQCap]  {triA | slot<<26, triB}
-    uint32_t* cbuf = (uint32_t*)(triq + kTriQCap);                // [kCandCap]  device pair indices
+    uint2* triq2 = triq + kTriQCap;                               // [kTriQ2Cap] same, after the face-normal axes
+    uint32_t* cbuf = (uint32_t*)(triq2 + kTriQ2Cap);              // [kCandCap]  device pair indices
     uint2* spill = P.spill + (size_t)(blockIdx.x * kWarpsPerBlock + wib) * P.spill_cap;
 
     const bool all_pairs = (P.flags & kFlagAllPairs) != 0;
     const bool counters = (P.flags & kFlagCounters) != 0;
     const float eps2 = P.tri_eps * P.tri_eps;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const int nenv_dev = P.nenv_dev, nenv_total = P.nenv_total, ndyn = P.ndyn;
     unsigned long long n_bv = 0, n_tri = 0;
 
     for (;;) {
@@ -435,9 +493,9 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         if (lane == 0) c = atomicAdd(&P.counters[0], 1);
         c = __shfl_sync(kFull, c, 0);
         if (c >= P.n) break;
-        const float* xf = P.xf32 + (size_t)c * P.ndyn * 12;
-        const float* ab = P.aabb + (size_t)c * P.ndyn * 8;
-        const float* st_ab = P.st_aabb - 8 * (size_t)P.ndyn;     // static slot s lives at st_ab + 8 s
+        const float* xf = P.xf32 + (size_t)c * ndyn * 12;
+        const float* ab = P.aabb + (size_t)c * ndyn * 8;
+        const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;       // static slot s lives at st_ab + 8 s
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
         if (P.pair_mask) {
             uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
@@ -446,51 +504,54 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         }
 
         // warp-uniform state, all in registers
-        int sp = 0, spill_count = 0, ntri = 0, ncb = 0;
+        int sp = 0, spill_count = 0, ntri = 0, ntri2 = 0, ncb = 0;
         int best_env = P.hoisted_first_env, best_self = P.hoisted_first_self;
-        uint32_t slot_hit = 0;
+        uint32_t slot_hit = 0;     // slots of the current batch of root pairs with a contact
+        uint32_t slot_dead = 0;    // slots whose items are no longer wanted (contact found, or preceded by a contact); non-zero
+                                   // also means refills from the spill area have to be filtered
         bool failed = false;
         uint32_t iters = 0;
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
-        int k0 = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
-        const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+        int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
+        const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : nenv_dev;
 
         while ((k0 < kend || ncb > 0) && !failed) {
-            if (k0 < kend) {
+            if (k0 < kend && ncb < 32) {
                 if (!all_pairs && recheck) {
                     // pairs are in reference order inside each class: once a hit precedes everything left, skip the rest
                     recheck = false;
-                    if (k0 < P.nenv_dev) { if (best_env < __ldg(&P.pair_orig[k0])) { k0 = P.nenv_dev; recheck = true; continue; } }
+                    if (k0 < nenv_dev) { if (best_env < __ldg(&P.pair_orig[k0])) { k0 = nenv_dev; recheck = true; continue; } }
                     else if (best_self < __ldg(&P.pair_orig[k0])) { k0 = kend; continue; }
                 }
-                // ---------------------------------------------------------------- broadphase: 64 pairs, world AABBs
-                const int lim = (k0 < P.nenv_dev && P.nenv_dev < kend) ? P.nenv_dev : kend;     // do not straddle env | self
-                bool ov[2];
-                int kk[2];
+                // ------------------------------------------------------------ broadphase: 32 x kBroadPerLane pairs, world AABBs
+                const int lim = (k0 < nenv_dev && nenv_dev < kend) ? nenv_dev : kend;     // do not straddle env | self
+                uint32_t pr[kBroadPerLane];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < kBroadPerLane; ++h) {
                     const int k = k0 + 32 * h + lane;
-                    kk[h] = k;
+                    pr[h] = k < lim ? __ldg(&P.pairs[k]) : 0xffffffffu;
+                }
+                bool ov[kBroadPerLane];
+#pragma unroll
+                for (int h = 0; h < kBroadPerLane; ++h) {
                     ov[h] = false;
-                    if (k < lim) {
-                        const uint32_t pr = __ldg(&P.pairs[k]);
-                        const int sa = pr & 0xffff, sb = pr >> 16;
-                        const float4* pa = (const float4*)((sa < P.ndyn ? ab : st_ab) + 8 * sa);
-                        const float4* pb = (const float4*)((sb < P.ndyn ? ab : st_ab) + 8 * sb);
+                    if (pr[h] != 0xffffffffu) {
+                        const int sa = pr[h] & 0xffff, sb = pr[h] >> 16;
+                        const float4* pa = (const float4*)((sa < ndyn ? ab : st_ab) + 8 * sa);
+                        const float4* pb = (const float4*)((sb < ndyn ? ab : st_ab) + 8 * sb);
                         const float4 ac = pa[0], ae = pa[1], bc = pb[0], be = pb[1];
                         ov[h] = fabsf(ac.x - bc.x) <= ae.x + be.x && fabsf(ac.y - bc.y) <= ae.y + be.y && fabsf(ac.z - bc.z) <= ae.z + be.z;
                     }
                 }
-                k0 = (k0 + 64 < lim) ? k0 + 64 : lim;
-                if (k0 == P.nenv_dev) recheck = true;
-                const unsigned om0 = __ballot_sync(kFull, ov[0]), om1 = __ballot_sync(kFull, ov[1]);
-                if (om0 | om1) {
-                    if (ov[0]) cbuf[ncb + __popc(om0 & lt_mask)] = (uint32_t)kk[0];
-                    ncb += __popc(om0);
-                    if (ov[1]) cbuf[ncb + __popc(om1 & lt_mask)] = (uint32_t)kk[1];
-                    ncb += __popc(om1);
-                    __syncwarp();
+#pragma unroll
+                for (int h = 0; h < kBroadPerLane; ++h) {
+                    const unsigned om = __ballot_sync(kFull, ov[h]);
+                    if (ov[h]) cbuf[ncb + __popc(om & lt_mask)] = (uint32_t)(k0 + 32 * h + lane);
+                    ncb += __popc(om);
                 }
+                __syncwarp();
+                k0 = (k0 + 32 * kBroadPerLane < lim) ? k0 + 32 * kBroadPerLane : lim;
+                if (k0 == nenv_dev) recheck = true;
                 if (ncb < 32 && k0 < kend) continue;
                 if (ncb == 0) continue;
             }
@@ -505,7 +566,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 if (lane < cnt) {
                     const uint32_t k = cbuf[lane];
                     orig = __ldg(&P.pair_orig[k]);
-                    const bool is_env = (int)k < P.nenv_dev;
+                    const bool is_env = (int)k < nenv_dev;
                     bool skip = false;
                     if (!all_pairs) skip = is_env ? (orig > best_env) : (orig > best_self);
                     if (!skip) {
@@ -513,13 +574,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const int la = pr & 0xffff, lb = pr >> 16;
                         float A[12], Bx[12];
                         {
-                            const float4* e = la < P.ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - P.ndyn));
+                            const float4* e = la < ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
                             A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
                         }
                         {
-                            const float4* e = lb < P.ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - P.ndyn));
+                            const float4* e = lb < ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
                             Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
@@ -534,13 +595,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 }
                 // drop the consumed candidates
                 {
-                    const int rest = ncb - cnt;                    // <= 63
-                    uint32_t mv0 = 0, mv1 = 0;
-                    if (lane < rest) mv0 = cbuf[cnt + lane];
-                    if (lane + 32 < rest) mv1 = cbuf[cnt + 32 + lane];
+                    const int rest = ncb - cnt;
+                    uint32_t mv[kBroadPerLane];
+#pragma unroll
+                    for (int h = 0; h < kBroadPerLane; ++h) mv[h] = (32 * h + lane < rest) ? cbuf[cnt + 32 * h + lane] : 0u;
                     __syncwarp();
-                    if (lane < rest) cbuf[lane] = mv0;
-                    if (lane + 32 < rest) cbuf[32 + lane] = mv1;
+#pragma unroll
+                    for (int h = 0; h < kBroadPerLane; ++h) if (32 * h + lane < rest) cbuf[32 * h + lane] = mv[h];
                     ncb = rest;
                     __syncwarp();
                 }
@@ -575,10 +636,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     const uint32_t s = (uint32_t)__popc(cm & lt_mask);
                     if (leafpair) triq[ntri + __popc(tm & lt_mask)] = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
                     if (push) {
-                        const float sa = a1.x * a1.x + a1.y * a1.y + a1.z * a1.z;
-                        const float sb = b1.x * b1.x + b1.y * b1.y + b1.z * b1.z;
                         uint2 it;
-                        if (lb < 0 || (la >= 0 && sa > sb)) it = make_uint2((uint32_t)la | (s << 26), rb);
+                        if (lb < 0 || (la >= 0 && a1.w > b1.w)) it = make_uint2((uint32_t)la | (s << 26), rb);
                         else it = make_uint2((uint32_t)lb | (s << 26), ra | 0x80000000u);
                         stack[sp + (__popc(pm) - 1 - __popc(pm & lt_mask))] = it;
                     }
@@ -589,46 +648,53 @@ cc_traverse_kernel(const __grid_constant__ Params P)
 
                 // ---------------------------------------------------------------- drain: descent + triangle batches
                 for (;;) {
-                    if (ntri >= 32 || (ntri > 0 && sp == 0 && spill_count == 0)) {
-                        // ---- up to 32 leaf x leaf tests (newest first)
-                        const int tn = ntri < 32 ? ntri : 32;
-                        bool hit = false;
-                        int pidx = 0;
-                        uint32_t s = 0;
+                    const bool stack_empty = sp == 0 && spill_count == 0;
+                    const bool run_edges = ntri2 >= CC_TRI_T2 || (ntri2 > 0 && ntri == 0 && stack_empty);
+                    if (run_edges || ntri >= CC_TRI_T1 || (ntri > 0 && stack_empty)) {
+                        // ---- up to 32 queued leaf pairs (newest first): the 15 edge axes of survivors, or the 2 face normals
+                        uint2* q = run_edges ? triq2 : triq;
+                        const int have = run_edges ? ntri2 : ntri;
+                        const int tn = have < 32 ? have : 32;
+                        bool pass = false;
+                        uint2 e = make_uint2(0u, 0u);
                         if (lane < tn) {
-                            const uint2 e = triq[ntri - 1 - lane];
-                            s = e.x >> 26;
-                            pidx = slot_pair[s];
-                            bool dead = (slot_hit >> s) & 1u;
-                            if (!all_pairs) dead |= (pidx < P.nenv_total) ? (pidx > best_env) : (pidx > best_self);
-                            if (!dead) {
-                                if (counters) n_tri++;
-                                const float4* ta = P.tris + 3 * (size_t)(e.x & 0x3ffffffu);
-                                const float4* tb = P.tris + 3 * (size_t)e.y;
-                                const float4 p0 = __ldg(ta), p1 = __ldg(ta + 1), p2 = __ldg(ta + 2);
-                                const float4 u0 = __ldg(tb), u1 = __ldg(tb + 1), u2 = __ldg(tb + 2);
-                                const float* rt = slot_rt + 24 * s;
-                                const float r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3], r4 = rt[4], r5 = rt[5], r6 = rt[6], r7 = rt[7], r8 = rt[8];
-                                const float t0 = rt[9], t1 = rt[10], t2 = rt[11];
-                                V3 Q0 = v3(fmaf(r0, u0.x, fmaf(r1, u0.y, fmaf(r2, u0.z, t0))), fmaf(r3, u0.x, fmaf(r4, u0.y, fmaf(r5, u0.z, t1))),
-                                           fmaf(r6, u0.x, fmaf(r7, u0.y, fmaf(r8, u0.z, t2))));
-                                V3 Q1 = v3(fmaf(r0, u1.x, fmaf(r1, u1.y, fmaf(r2, u1.z, t0))), fmaf(r3, u1.x, fmaf(r4, u1.y, fmaf(r5, u1.z, t1))),
-                                           fmaf(r6, u1.x, fmaf(r7, u1.y, fmaf(r8, u1.z, t2))));
-                                V3 Q2 = v3(fmaf(r0, u2.x, fmaf(r1, u2.y, fmaf(r2, u2.z, t0))), fmaf(r3, u2.x, fmaf(r4, u2.y, fmaf(r5, u2.z, t1))),
-                                           fmaf(r6, u2.x, fmaf(r7, u2.y, fmaf(r8, u2.z, t2))));
-                                hit = tri_contact(v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), v3(p2.x, p2.y, p2.z), Q0, Q1, Q2, eps2);
-                            }
+                            e = q[have - 1 - lane];
+                            V3 p1, p2, q0, q1, q2;
+                            load_tri_pair(P.tris, slot_rt + 24 * (e.x >> 26), e.x & 0x3ffffffu, e.y, p1, p2, q0, q1, q2);
+                            if (run_edges) pass = tri_contact_edges(p1, p2, q0, q1, q2, eps2);
+                            else { if (counters) n_tri++; pass = tri_contact_normals(p1, p2, q0, q1, q2, eps2); }
                         }
-                        ntri -= tn;
-                        const unsigned hm = __ballot_sync(kFull, hit);
-                        if (hm) {
-                            slot_hit |= __reduce_or_sync(kFull, hit ? (1u << s) : 0u);
-                            const int pe = __reduce_min_sync(kFull, (hit && pidx < P.nenv_total) ? pidx : kNone);
-                            const int ps = __reduce_min_sync(kFull, (hit && pidx >= P.nenv_total) ? pidx : kNone);
+                        const unsigned pmask = __ballot_sync(kFull, pass);
+                        if (!run_edges) {
+                            ntri -= tn;
+                            if (pmask) {
+                                __syncwarp();
+                                if (pass) triq2[ntri2 + __popc(pmask & lt_mask)] = e;
+                                ntri2 += __popc(pmask);
+                                __syncwarp();
+                            }
+                            continue;
+                        }
+                        ntri2 -= tn;
+                        if (pmask) {
+                            // contacts: record them, then purge everything that no longer matters from the queues
+                            const uint32_t s = e.x >> 26;
+                            const int pidx = pass ? slot_pair[s] : kNone;
+                            slot_hit |= __reduce_or_sync(kFull, pass ? (1u << s) : 0u);
+                            const int pe = __reduce_min_sync(kFull, (pass && pidx < nenv_total) ? pidx : kNone);
+                            const int ps = __reduce_min_sync(kFull, (pass && pidx >= nenv_total) ? pidx : kNone);
                             if (pe < best_env) { best_env = pe; recheck = true; }
                             if (ps < best_self) { best_self = ps; recheck = true; }
+                            slot_dead |= slot_hit;
+                            if (!all_pairs) {
+                                bool d = false;
+                                if (lane < nsl) { const int p = slot_pair[lane]; d = (p < nenv_total) ? (p > best_env) : (p > best_self); }
+                                slot_dead |= __ballot_sync(kFull, d);
+                            }
+                            sp = filter_queue(stack, sp, slot_dead, lane, lt_mask);
+                            ntri = filter_queue(triq, ntri, slot_dead, lane, lt_mask);
+                            ntri2 = filter_queue(triq2, ntri2, slot_dead, lane, lt_mask);
                         }
-                        __syncwarp();
                         continue;
                     }
                     if (sp == 0) {
@@ -640,58 +706,49 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         spill_count -= m;
                         sp = m;
                         __syncwarp();
+                        if (slot_dead) { sp = filter_queue(stack, sp, slot_dead, lane, lt_mask); if (sp == 0) continue; }
                     }
                     // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
                     const int n = sp < 32 ? sp : 32;
                     ++iters;
-                    bool valid = lane < n;
+                    const bool valid = lane < n;
                     uint2 it = make_uint2(0u, 0u);
                     if (valid) it = stack[sp - 1 - lane];
                     sp -= n;
-                    const uint32_t s = it.x >> 26;
-                    if (valid) {
-                        const int pidx = slot_pair[s];
-                        bool dead = (slot_hit >> s) & 1u;
-                        if (!all_pairs) dead |= (pidx < P.nenv_total) ? (pidx > best_env) : (pidx > best_self);
-                        valid = !dead;
-                    }
                     __syncwarp();
                     bool tq0 = false, tq1 = false, ps0 = false, ps1 = false;
                     uint2 o0 = make_uint2(0u, 0u), o1 = make_uint2(0u, 0u);     // outputs for child 0 / child 1 (tri entry or item)
                     if (valid) {
+                        const uint32_t sbits = it.x & 0xfc000000u;
                         const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x7fffffffu;
                         const bool side = (it.y >> 31) != 0u;                  // false: x is in tree A, true: x is in tree B
                         const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
                         const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
                         const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
-                        const float* rt = slot_rt + 24 * s + (side ? 12 : 0);      // maps the other node into the children's frame
+                        const float* rt = slot_rt + 24 * (it.x >> 26) + (side ? 12 : 0);      // maps the other node into the children's frame
                         float R[9], t[3];
 #pragma unroll
                         for (int k = 0; k < 9; ++k) R[k] = rt[k];
                         t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
                         if (counters) n_bv += 2;
                         const int lo = __float_as_int(oa.w);
-                        const float so = ob.x * ob.x + ob.y * ob.y + ob.z * ob.z;
                         bool ov0, ov1;
                         box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
                                          oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
-                            const float4 ca = ch ? c1a : c0a, cb = ch ? c1b : c0b;
                             if (ch ? ov1 : ov0) {
-                                const int lc = __float_as_int(ca.w);
+                                const int lc = __float_as_int(ch ? c1a.w : c0a.w);
+                                const float sc = ch ? c1b.w : c0b.w;            // |e|^2 of the child, of the other node: ob.w
                                 uint2 out;
-                                bool tq = false;
-                                if (lc < 0 && lo < 0) {
-                                    tq = true;
-                                    out = side ? make_uint2((uint32_t)(~lo) | (s << 26), (uint32_t)(~lc))
-                                               : make_uint2((uint32_t)(~lc) | (s << 26), (uint32_t)(~lo));
+                                const bool tq = lc < 0 && lo < 0;
+                                if (tq) {
+                                    out = side ? make_uint2((uint32_t)(~lo) | sbits, (uint32_t)(~lc))
+                                               : make_uint2((uint32_t)(~lc) | sbits, (uint32_t)(~lo));
+                                } else if (lo < 0 || (lc >= 0 && sc > ob.w)) {
+                                    out = make_uint2((uint32_t)lc | sbits, it.y);                                     // split the child
                                 } else {
-                                    const float sc = cb.x * cb.x + cb.y * cb.y + cb.z * cb.z;
-                                    if (lo < 0 || (lc >= 0 && sc > so))
-                                        out = make_uint2((uint32_t)lc | (s << 26), it.y);                               // split the child
-                                    else
-                                        out = make_uint2((uint32_t)lo | (s << 26), (x + ch) | (side ? 0u : 0x80000000u)); // split the other
+                                    out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));     // split the other
                                 }
                                 if (ch) { o1 = out; tq1 = tq; ps1 = !tq; } else { o0 = out; tq0 = tq; ps0 = !tq; }
                             }
@@ -716,7 +773,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         // move the oldest kSpillChunk items to global memory and slide the rest down
                         if (spill_count + kSpillChunk > P.spill_cap) {
                             if (lane == 0) atomicExch(P.err_flag, 1);
-                            failed = true; sp = 0; ntri = 0; spill_count = 0;        // the host reports the error
+                            failed = true; sp = 0; ntri = 0; ntri2 = 0; spill_count = 0;        // the host reports the error
                             __syncwarp();
                             break;
                         }
@@ -743,7 +800,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         atomicOr(&mask_row[p >> 5], 1u << (p & 31));
                     }
                 }
-                slot_hit = 0;
+                slot_hit = 0; slot_dead = 0;
                 __syncwarp();
             }
         }
@@ -759,7 +816,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     while (m) {
                         const int bit = __ffs(m) - 1; m &= m - 1;
                         const int p = wd * 32 + bit;
-                        if (p < P.nenv_total) { if (p < be) be = p; } else { if (p < bs) bs = p; }
+                        if (p < nenv_total) { if (p < be) be = p; } else { if (p < bs) bs = p; }
                     }
                 }
             }

@@ -8,6 +8,7 @@
 //   * launch ccdev::cc_check_kernel (cc_device.cuh) on the caller's stream.
 // There is NO CPU collision path here: without a CUDA device every query entry point fails with CC_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -34,7 +35,9 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ host scene
-struct HNode { float c[3]; int32_t left; float e[3]; int32_t right; };   // matches the device's 2 x float4
+// matches the device's 2 x float4; the right child is always left + 1, so the last word carries |e|^2 (the "size" the
+// descent rule compares) instead
+struct HNode { float c[3]; int32_t left; float e[3]; float size2; };
 static_assert(sizeof(HNode) == 32, "node layout");
 
 struct HLink {
@@ -150,6 +153,7 @@ struct Builder {
             if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
             n.c[k] = cf; n.e[k] = ef;
         }
+        n.size2 = n.e[0] * n.e[0] + n.e[1] * n.e[1] + n.e[2] * n.e[2];
     }
 
     void build(int node, int first, int count)
@@ -159,7 +163,6 @@ struct Builder {
         fill_box(nodes[node], mn, mx);
         if (count == 1) {
             nodes[node].left = ~order[first];
-            nodes[node].right = -1;
             return;
         }
         // split the centroid bounds at the midpoint of the longest axis; fall back to the median
@@ -181,7 +184,7 @@ struct Builder {
         }
         int l = (int)nodes.size();
         nodes.push_back(HNode()); nodes.push_back(HNode());
-        nodes[node].left = l; nodes[node].right = l + 1;
+        nodes[node].left = l;
         build(l, first, nleft);
         build(l + 1, first + nleft, count - nleft);
     }
@@ -350,12 +353,17 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
     if (fk_smem > 48 * 1024)
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
-    const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock;
+    // CC_TUNE_EXTRA_SMEM (bytes per block) is a profiling knob: it trades resident traversal blocks for L1 capacity
+    static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
+    const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
         int per_sm = 0;
         CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_traverse_kernel, ccdev::kWarpsPerBlock * 32, tr_smem));
         if (per_sm < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
+        if (getenv("CC_TUNE_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(getenv("CC_TUNE_BLOCKS_PER_SM"))));
+        if (getenv("CC_TUNE_CARVEOUT"))
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
         S->trav_blocks_per_sm = per_sm;
     }
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
@@ -596,8 +604,8 @@ int cc_scene_commit(cc_scene* s)
             L.tri_base = (int)(tris.size() / 12);
             for (const HNode& n : L.nodes) {
                 HNode g = n;
-                if (g.left >= 0) { g.left += L.node_base; g.right += L.node_base; }
-                else { g.left = ~((~g.left) + L.tri_base); g.right = -1; }
+                if (g.left >= 0) g.left += L.node_base;
+                else g.left = ~((~g.left) + L.tri_base);
                 nodes.push_back(g);
             }
             tris.insert(tris.end(), L.tridata.begin(), L.tridata.end());
