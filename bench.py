@@ -250,13 +250,13 @@ def main():
         if world > 1:   # only the per-config verdicts and first-contact pairs cross NVLink
             dist.all_gather(gathered, torch.cat([d_verdict, d_fe, d_fs]))
 
-    v_host = np.zeros(n, dtype=np.uint32)
-    fe_host = np.zeros(n, dtype=np.int32)
-    fs_host = np.zeros(n, dtype=np.int32)
+    # the caller-side buffers of the host entry: page-locked (cc_host_alloc), reused every step
+    from openrave_b200.checker import PinnedArray
+    pin_v, pin_fe, pin_fs = PinnedArray(n, np.uint32), PinnedArray(n, np.int32), PinnedArray(n, np.int32)
     q_np = q_pinned.numpy()
 
     def step_e2e():
-        v, fe, fs, _ = bq.check(q_np, flags)
+        v, fe, fs, _ = bq.check(q_np, flags, out=(pin_v.array, pin_fe.array, pin_fs.array))
         return v
 
     for _ in range(W):

@@ -23,6 +23,7 @@
 #ifndef CUDACOLLISION_H
 #define CUDACOLLISION_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -175,6 +176,14 @@ int cc_check_poses(cc_query* q, const double* link_transforms8, int n, int flags
                    uint32_t* verdict, int32_t* first_env, int32_t* first_self, uint32_t* pair_mask);
 /* Batched KinBody::SetDOFValues: out [n][nlinks][8] doubles (validation of the 1e-6 m / 1e-6 rad bound). */
 int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_transforms8);
+
+/* Page-locked host buffers for the host-buffer entry points (cc_check_batch, cc_check_poses, cc_fk_batch).  Those calls
+ * cut a big batch into chunks and copy each chunk's inputs / results on the chunk's own stream; with buffers from
+ * cc_host_alloc the copies overlap the kernels of the neighbouring chunk.  Ordinary (pageable) memory stays valid
+ * everywhere, it only serialises the copies.  The plugin keeps one set per checker for the planners' edge batches
+ * (the std::vector<dReal> the per-sample loop fills, planningutils.cpp:3405-3454). */
+int cc_host_alloc(size_t bytes, void** out);
+int cc_host_free(void* p);
 
 /* Wait for everything enqueued by cc_check_batch_device on this scene's device and report asynchronous
  * failures (CC_ERR_NOMEM if a traversal overflowed its spill area). */

@@ -47,7 +47,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_body_set_attached", "cc_body_set_kinematics", "cc_body_set_dof_values", "cc_body_set_nonadjacent_pairs",
            "cc_scene_commit", "cc_query_create", "cc_query_create_pairs", "cc_query_destroy", "cc_query_get_info",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
-           "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats"]
+           "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
+           "cc_host_alloc", "cc_host_free"]
 
 _lib = None
 
@@ -89,12 +90,38 @@ def load_library():
     lib.cc_scene_set_tri_epsilon.argtypes = [vp, cd]
     lib.cc_scene_set_counters.argtypes = [vp, ci]
     lib.cc_scene_get_stats.argtypes = [vp, ctypes.POINTER(cc_stats)]
+    lib.cc_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.cc_host_free.argtypes = [vp]
     _lib = lib
     return lib
 
 
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class PinnedArray(object):
+    """A numpy view over a page-locked buffer from cc_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        if self.lib.cc_host_alloc(max(nbytes, 1), ctypes.byref(p)) != 0:
+            raise CudaCollisionError((self.lib.cc_last_error() or b"").decode())
+        self.ptr = p
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self.lib.cc_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 class BoundQuery(object):
@@ -138,12 +165,18 @@ class BoundQuery(object):
         out[ok, 1] = self.pairs[idx[ok], 2]
         return out
 
-    def check(self, q, flags=BATCH_ENV | BATCH_SELF, want_mask=False):
+    def check(self, q, flags=BATCH_ENV | BATCH_SELF, want_mask=False, out=None):
+        """`out` = (verdict u32[n], first_env i32[n], first_self i32[n]) lets a caller reuse (pinned) result buffers."""
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
         n = q.shape[0]
-        verdict = np.zeros(n, dtype=np.uint32)
-        fe = np.zeros(n, dtype=np.int32)
-        fs = np.zeros(n, dtype=np.int32)
+        if out is not None:
+            verdict, fe, fs = out
+            assert verdict.dtype == np.uint32 and fe.dtype == np.int32 and fs.dtype == np.int32
+            assert len(verdict) >= n and len(fe) >= n and len(fs) >= n
+        else:
+            verdict = np.zeros(n, dtype=np.uint32)
+            fe = np.zeros(n, dtype=np.int32)
+            fs = np.zeros(n, dtype=np.int32)
         mask = np.zeros((n, self.info.mask_words), dtype=np.uint32) if want_mask else None
         self.checker._ck(self.lib.cc_check_batch(self.handle, _ptr(q), n, flags, _ptr(verdict), _ptr(fe), _ptr(fs), _ptr(mask)))
         return verdict, fe, fs, mask

@@ -299,8 +299,20 @@ int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
     return CC_OK;
 }
 
+// Host buffers of the host-buffer entry points: when given, every chunk copies its own slice in before its FK kernel and
+// its results out after its traversal kernel, on the chunk's lane stream, so the transfers of one chunk overlap the kernels
+// of the other lane (pinned buffers from cc_host_alloc make the copies truly asynchronous; pageable ones still work).
+struct HostIO {
+    const double* in = nullptr;
+    uint32_t* verdict = nullptr;
+    int32_t* fe = nullptr;
+    int32_t* fs = nullptr;
+    uint32_t* mask = nullptr;
+    double* fk = nullptr;
+};
+
 int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
-           int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st)
+           int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st, const HostIO* hio = nullptr)
 {
     cc_scene* S = Q->scene;
     if (n <= 0) return CC_OK;
@@ -379,11 +391,31 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         CC_CUDA(cudaEventRecord(S->ev_fork, st));
         for (int i = 0; i < 2; ++i) CC_CUDA(cudaStreamWaitEvent(S->lane_stream[i], S->ev_fork, 0));
     }
+    // results of chunk i go back to the host only after chunk i+1 has been enqueued: a copy into pageable memory blocks
+    // the calling thread, and the device must already have the next chunk's work queued by then
+    int pend_off = -1, pend_m = 0;
+    cudaStream_t pend_cs = nullptr;
+    auto copy_out = [&](int off, int m, cudaStream_t cs) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (hio->verdict && e == cudaSuccess) e = cudaMemcpyAsync(hio->verdict + off, d_verdict + off, (size_t)m * 4, cudaMemcpyDeviceToHost, cs);
+        if (hio->fe && e == cudaSuccess) e = cudaMemcpyAsync(hio->fe + off, d_fe + off, (size_t)m * 4, cudaMemcpyDeviceToHost, cs);
+        if (hio->fs && e == cudaSuccess) e = cudaMemcpyAsync(hio->fs + off, d_fs + off, (size_t)m * 4, cudaMemcpyDeviceToHost, cs);
+        if (hio->mask && e == cudaSuccess)
+            e = cudaMemcpyAsync(hio->mask + (size_t)off * Q->mask_words, d_mask + (size_t)off * Q->mask_words,
+                                (size_t)m * Q->mask_words * 4, cudaMemcpyDeviceToHost, cs);
+        if (hio->fk && e == cudaSuccess)
+            e = cudaMemcpyAsync(hio->fk + (size_t)off * Q->nq * 8, d_fk + (size_t)off * Q->nq * 8, (size_t)m * Q->nq * 64,
+                                cudaMemcpyDeviceToHost, cs);
+        return e;
+    };
     int ci = 0;
     for (int off = 0; off < n; off += chunk, ++ci) {
         const int m = std::min(chunk, n - off);
         const int k = overlap ? (ci & 1) : 0;
         cudaStream_t cs = overlap ? S->lane_stream[k] : st;
+        if (hio && hio->in && row_doubles > 0)
+            CC_CUDA(cudaMemcpyAsync(const_cast<double*>(d_q) + (size_t)off * row_doubles, hio->in + (size_t)off * row_doubles,
+                                    (size_t)m * row_doubles * sizeof(double), cudaMemcpyHostToDevice, cs));
         P.n = m;
         P.q = d_q ? d_q + (size_t)off * row_doubles : nullptr;
         P.verdict = d_verdict ? d_verdict + off : nullptr;
@@ -398,7 +430,10 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
-        if (fk_only) continue;
+        if (fk_only) {
+            if (hio) CC_CUDA(copy_out(off, m, cs));
+            continue;
+        }
         // persistent traversal grid: a whole number of waves, never more warps than configurations
         int grid = S->trav_blocks_per_sm * S->num_sms;
         const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
@@ -407,7 +442,12 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         ccdev::cc_traverse_kernel<<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
+        if (hio) {
+            if (pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
+            pend_off = off; pend_m = m; pend_cs = cs;
+        }
     }
+    if (hio && pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
     if (overlap) {
         for (int i = 0; i < 2; ++i) {
             CC_CUDA(cudaEventRecord(S->ev_join[i], S->lane_stream[i]));
@@ -1050,21 +1090,17 @@ static int run_host(cc_query* q, const double* in, size_t in_doubles, int n, int
     if (n == 0) return CC_OK;
     CC_CUDA(cudaSetDevice(S->device));
     CC_CUDA(q->d_q.reserve(std::max<size_t>(1, in_doubles)));
-    if (in_doubles) CC_CUDA(cudaMemcpyAsync(q->d_q.p, in, in_doubles * sizeof(double), cudaMemcpyHostToDevice, 0));
     if (verdict) CC_CUDA(q->d_verdict.reserve(n));
     if (fe) CC_CUDA(q->d_fe.reserve(n));
     if (fs) CC_CUDA(q->d_fs.reserve(n));
     if (mask) CC_CUDA(q->d_mask.reserve((size_t)n * q->mask_words));
     if (fk) CC_CUDA(q->d_fk.reserve((size_t)n * q->nq * 8));
     const Plan& pl = pose_mode ? q->full : (fk ? q->hoisted : q->mainl);   // FK read-back needs every joint: the unpruned program
+    HostIO hio;
+    hio.in = in_doubles ? in : nullptr; hio.verdict = verdict; hio.fe = fe; hio.fs = fs; hio.mask = mask; hio.fk = fk;
     int rc = launch(q, pl, !pose_mode, q->d_q.p, n, kflags, verdict ? q->d_verdict.p : nullptr, fe ? q->d_fe.p : nullptr,
-                    fs ? q->d_fs.p : nullptr, mask ? q->d_mask.p : nullptr, fk ? q->d_fk.p : nullptr, 0);
+                    fs ? q->d_fs.p : nullptr, mask ? q->d_mask.p : nullptr, fk ? q->d_fk.p : nullptr, 0, &hio);
     if (rc != CC_OK) return rc;
-    if (verdict) CC_CUDA(cudaMemcpyAsync(verdict, q->d_verdict.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
-    if (fe) CC_CUDA(cudaMemcpyAsync(fe, q->d_fe.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    if (fs) CC_CUDA(cudaMemcpyAsync(fs, q->d_fs.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    if (mask) CC_CUDA(cudaMemcpyAsync(mask, q->d_mask.p, (size_t)n * q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
-    if (fk) CC_CUDA(cudaMemcpyAsync(fk, q->d_fk.p, (size_t)n * q->nq * 8 * sizeof(double), cudaMemcpyDeviceToHost, 0));
     CC_CUDA(cudaStreamSynchronize(0));
     return check_err_flag(S);
 }
@@ -1093,6 +1129,20 @@ int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_T8)
     if (!q || n < 0 || !out_T8 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics");
     return run_host(q, dof_values, (size_t)n * q->ncols, n, ccdev::kFlagFkOnly, false, nullptr, nullptr, nullptr, nullptr, out_T8);
+}
+
+int cc_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(CC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    CC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return CC_OK;
+}
+
+int cc_host_free(void* p)
+{
+    if (p) CC_CUDA(cudaFreeHost(p));
+    return CC_OK;
 }
 
 int cc_scene_synchronize(cc_scene* s)
