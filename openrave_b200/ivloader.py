@@ -17,6 +17,12 @@ transform nodes, so `_load_iv_binary` restates just that: big-endian MFVec3f `ve
 strips (i, i+1, i+2) cut at -1, degenerate triangles kept (verdict-neutral).  No Coin here => this mesh is "parity
 unpinned" at the vertex level; it is pinned only through the scene-level checks in tests/.
 
+ASCII files that pull other files in through `File { name "..." }` nodes (models/objects/ketchup.iv in
+data/wamtest1.env.xml) carry nothing ivcon can read; Coin resolves the include relative to the including file and applies
+the transform nodes accumulated inside the enclosing `Separator` (RotationXYZ, Transform{translation, rotation,
+scaleFactor}, Translation, Rotation, Scale; each right-multiplies the current matrix, SoSeparator restores it on exit).
+`_load_iv_graph` restates that for exactly those node types ("parity unpinned" at the vertex level, as above).
+
 Load-time tooling (scene ingestion is not part of the per-config hot path).
 """
 import ctypes
@@ -72,6 +78,90 @@ def _load_iv_binary(path, data):
     return np.concatenate(verts), np.asarray(tris, dtype=np.int32).reshape(-1, 3)
 
 
+_TOKEN_RE = re.compile(r'"[^"]*"|[{}\[\]]|[^\s{}\[\]]+')
+
+
+def _axis_angle(axis, angle):
+    axis = np.asarray(axis, dtype=np.float64)
+    n = np.linalg.norm(axis)
+    if n == 0:
+        return np.eye(3)
+    x, y, z = axis / n
+    c, s = np.cos(angle), np.sin(angle)
+    C = 1 - c
+    return np.array([[c + x * x * C, x * y * C - z * s, x * z * C + y * s],
+                     [y * x * C + z * s, c + y * y * C, y * z * C - x * s],
+                     [z * x * C - y * s, z * y * C + x * s, c + z * z * C]])
+
+
+def _load_iv_graph(path, text):
+    """Separator / transform / File walker (Coin semantics) for ASCII files that include other files."""
+    import os
+    toks = _TOKEN_RE.findall(re.sub(r"#[^\n]*", "", text))
+    verts, tris, base = [], [], 0
+    stack, cur = [], np.eye(4)
+    i = 0
+
+    def fields(j):
+        """tokens of the node body starting after '{' at j -> (dict field -> [tokens], index after '}')."""
+        out, depth, name = {}, 1, None
+        while j < len(toks) and depth:
+            t = toks[j]
+            if t == "{":
+                depth += 1
+            elif t == "}":
+                depth -= 1
+            elif depth == 1:
+                if re.match(r"^[A-Za-z_]\w*$", t) and (name is None or t[0].islower() and not out[name] or
+                                                      t in ("translation", "rotation", "scaleFactor", "axis", "angle", "name")):
+                    name = t
+                    out[name] = []
+                elif name is not None:
+                    out[name].append(t)
+            j += 1
+        return out, j
+
+    while i < len(toks):
+        t = toks[i]
+        if t == "Separator" and i + 1 < len(toks) and toks[i + 1] == "{":
+            stack.append(cur.copy())
+            i += 2
+            continue
+        if t == "}":
+            if stack:
+                cur = stack.pop()
+            i += 1
+            continue
+        if i + 1 < len(toks) and toks[i + 1] == "{":
+            f, nxt = fields(i + 2)
+            M = np.eye(4)
+            if t == "RotationXYZ":
+                ax = {"X": (1, 0, 0), "Y": (0, 1, 0), "Z": (0, 0, 1)}[f.get("axis", ["X"])[0]]
+                M[:3, :3] = _axis_angle(ax, float(f.get("angle", ["0"])[0]))
+            elif t in ("Transform", "Translation", "Rotation", "Scale"):
+                if "translation" in f:
+                    M[:3, 3] = [float(x) for x in f["translation"][:3]]
+                if "rotation" in f:
+                    r = [float(x) for x in f["rotation"][:4]]
+                    M[:3, :3] = _axis_angle(r[:3], r[3])
+                if "scaleFactor" in f:
+                    M[:3, :3] = M[:3, :3] @ np.diag([float(x) for x in f["scaleFactor"][:3]])
+            elif t == "File":
+                sub = os.path.join(os.path.dirname(path), f["name"][0].strip('"'))
+                v, idx = load_iv(sub)
+                v = (v.astype(np.float64) @ cur[:3, :3].T + cur[:3, 3]).astype(np.float32)
+                verts.append(v)
+                tris.append(idx + base)
+                base += len(v)
+            cur = cur @ M
+            i = nxt
+            continue
+        i += 1
+    if not verts:
+        raise ValueError("%s: no Coordinate3 points" % path)
+    return np.concatenate(verts), np.concatenate(tris).astype(np.int32)
+
+
 def load_iv(path):
     """Return (vertices float32 [nv,3], indices int32 [nt,3])."""
     with open(path, "rb") as f:
@@ -83,6 +173,8 @@ def load_iv(path):
     if not text.startswith("#Inventor"):
         raise ValueError("%s: not an ASCII Inventor file" % path)
     chunks = [_parse_floats32(m.group(1)) for m in _POINT_RE.finditer(text)]
+    if not chunks and re.search(r"\bFile\s*\{", text):
+        return _load_iv_graph(path, text)
     if not chunks:
         raise ValueError("%s: no Coordinate3 points" % path)
     # ivcon carries a partially filled xyz triple across lists only within one list; every list in
