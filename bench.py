@@ -49,6 +49,14 @@ WORKLOADS = {
                              "geodesic spheres (1.94M tris, 217 MB of BVH + triangles: larger than L2), 1.25M configs per GPU = 10M "
                              "sharded over 8 GPUs (BASELINE.json configs[4]; scene generated from seed 5 by openrave_b200/clutter.py)"),
 }
+# BASELINE.json configs[2]: plans/s of BiRRT + the default linear smoother, edge checks batched (csrc/cc_planner.cpp)
+PLAN_WORKLOADS = {
+    "wam_wamtest1_birrt100": ("wamtest1", 100, 3,
+                              "BiRRT (rplanners) on the Barrett WAM arm (7 DOF) in data/wamtest1.env.xml: 100 start/goal pairs drawn from "
+                              "collision-free uniform samples (seed 3), step 0.04, <= 10000 iterations, goal bias 0.01, 10 _SimpleOptimizePath "
+                              "shortcuts + 100 linearsmoother iterations; all problems advance in lockstep, every Extend ray / shortcut of "
+                              "every live problem goes through one cc_check_batch call per round (BASELINE.json configs[2])"),
+}
 DEFAULT_WORKLOAD = "pr2_pr2test1_1m"
 METRIC = "collision-checked configs/sec (FK+env+self)"
 UNIT = "configs/s"
@@ -199,16 +207,178 @@ def _ref_worker_run(a):
     return secs
 
 
+def plan_problems(scene, nproblems, seed, rank, checker_factory):
+    """Start/goal pairs = consecutive collision-free samples of the seeded uniform stream (RobotConfigurationSampler semantics),
+    classified by the checker the arm runs on."""
+    from openrave_b200.environment import Environment
+    env = Environment()
+    env.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
+    robot = env.GetRobots()[0]
+    robot.SetActiveDOFs(robot.GetActiveManipulator().GetArmIndices())
+    checker = checker_factory(env)
+    env.SetCollisionChecker(checker)
+    q = sample(robot, 8 * nproblems + 64, seed + 1000 * rank)
+    return env, robot, checker, q
+
+
+def run_birrt(args):
+    """plans/s: `steps` timed repetitions of planning all problems of the workload (fresh trees every step)."""
+    import torch
+    import torch.distributed as dist
+    from openrave_b200 import planning as pl
+    from openrave_b200.checker import CudaCollisionChecker
+    scene, nproblems, seed, desc = PLAN_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(args.warmup, 3)
+    env, robot, cc, q = plan_problems(scene, nproblems, seed, rank, lambda e: CudaCollisionChecker(e, local_rank))
+    free = q[cc.CheckCollisionBatch(robot, q)["verdict"] == 0]
+    starts, goals = free[0:2 * nproblems:2].copy(), free[1:2 * nproblems:2].copy()
+    seeds = np.arange(nproblems, dtype=np.uint32) + 1000 * rank
+    P = pl.BirrtPlanner(robot, cc)
+    for _ in range(W):
+        res = P.PlanBatch(starts, goals, seeds)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    launches0 = cc.GetStatistics()["launches"]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = P.PlanBatch(starts, goals, seeds)      # host buffers in, paths out: the call a planner user makes
+    torch.cuda.synchronize()
+    secs = (time.perf_counter() - t0) / args.steps
+    launches = cc.GetStatistics()["launches"] - launches0
+    if world > 1:
+        t = torch.tensor([secs], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank == 0:
+        tot = P.totals
+        solved = sum(1 for r in res if r["status"] == pl.PLAN_SOLVED)
+        value = world * nproblems / secs
+        ndof = len(robot.GetActiveDOFIndices())
+        line = {"metric": "BiRRT plans/sec (batched CheckPathAllConstraints)", "value": value, "unit": "plans/s", "n_gpus": world,
+                "steps": args.steps, "warmup": W, "ms_per_step": 1000.0 * secs, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": desc, "problems_per_step_per_gpu": nproblems, "ndof": ndof,
+                           "solved": solved, "rounds": tot["rounds"], "configs_submitted": tot["configs_submitted"],
+                           "configs_serial_equivalent": tot["configs_serial"],
+                           "mean_iterations": float(np.mean([r["iterations"] for r in res])),
+                           "mean_waypoints": float(np.mean([r["waypoints"] for r in res])),
+                           "configs_per_s": world * tot["configs_submitted"] / secs,
+                           "l2": "scene (5 MB) stays L2-resident across rounds, as it does in a planner",
+                           "timing": "host wall clock around cc_birrt_plan_batch (planner host + H2D + kernels + D2H), max over ranks",
+                           "parallelism": "problems sharded, scene replicated (dp%d)" % world},
+                "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": int(tot["configs_submitted"] * ndof * 8),
+                        "d2h_bytes_per_step": int(tot["configs_submitted"] * 4)},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "roofline": None}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = birrt_cpu_baseline(scene, nproblems, seed, starts, goals, seeds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def birrt_cpu_baseline(scene, nproblems, seed, starts, goals, seeds, budget_s=15.0):
+    """The same planner host with the reference's serial, early-exit edge loop on the CPU oracle (1 thread), on a prefix of
+    the same problems sized to ~budget_s."""
+    import oracle
+    from openrave_b200 import planning as pl
+    kind = "reference" if oracle.available("reference") else "port"
+    env, robot, orc, _ = plan_problems(scene, nproblems, seed, 0, lambda e: oracle.OracleChecker(e, kind))
+    orc.InitEnvironment()
+    fn, blk = orc.group_checker(robot)
+    P = pl.BirrtPlanner(robot, (fn, blk))
+    t0 = time.perf_counter()
+    P.PlanBatch(starts[:2], goals[:2], seeds[:2])
+    per = max((time.perf_counter() - t0) / 2, 1e-4)
+    m = int(max(2, min(nproblems, budget_s / per)))
+    t0 = time.perf_counter()
+    P.PlanBatch(starts[:m], goals[:m], seeds[:m])
+    secs = time.perf_counter() - t0
+    return {"value": m / secs, "unit": "plans/s", "cores": 1, "kind": kind,
+            "sample": "first %d of the %d problems, serial early-exit edge checks, 1 thread, %.1f s (%d configs)" % (
+                m, nproblems, secs, P.totals["configs_serial"])}
+
+
+def run_birrt_reference(args):
+    """Reference arm for the plans/s workload: one planner + private oracle scene per host core, problems split."""
+    import multiprocessing as mp
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    from openrave_b200 import planning as pl  # noqa: F401
+    kind = "reference" if oracle.available("reference") else "port"
+    scene, nproblems, seed, desc = PLAN_WORKLOADS[args.workload]
+    env, robot, orc, q = plan_problems(scene, nproblems, seed, 0, lambda e: oracle.OracleChecker(e, kind))
+    orc.InitEnvironment()
+    free = q[orc.check_batch(robot, q)["verdict"] == 0]
+    starts, goals = free[0:2 * nproblems:2].copy(), free[1:2 * nproblems:2].copy()
+    seeds = np.arange(nproblems, dtype=np.uint32)
+    workers = max(1, min(os.cpu_count() or 1, 64, nproblems))
+    ctx = mp.get_context("fork")
+    chunks = [(starts[i::workers], goals[i::workers], seeds[i::workers]) for i in range(workers)]
+
+    def one_step():
+        with ctx.Pool(workers, initializer=_birrt_worker_init, initargs=(scene, nproblems, seed, kind)) as pool:
+            t0 = time.perf_counter()
+            pool.map(_birrt_worker_run, chunks)
+            return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    secs = sum(times) / len(times)
+    value = nproblems / secs
+    print(json.dumps({"impl": "reference", "metric": "BiRRT plans/sec (batched CheckPathAllConstraints)", "value": value,
+                      "unit": "plans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * secs,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": args.workload, "description": desc, "problems_per_step": nproblems},
+                      "cpu_baseline": {"value": value, "unit": "plans/s", "cores": workers, "kind": kind,
+                                       "sample": "all %d problems over %d processes, serial early-exit edge checks" % (nproblems, workers)},
+                      "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def _birrt_worker_init(scene, nproblems, seed, kind):
+    import oracle
+    from openrave_b200 import planning as pl
+    env, robot, orc, _ = plan_problems(scene, nproblems, seed, 0, lambda e: oracle.OracleChecker(e, kind))
+    orc.InitEnvironment()
+    fn, blk = orc.group_checker(robot)
+    _REF_STATE.update(env=env, robot=robot, orc=orc, planner=pl.BirrtPlanner(robot, (fn, blk)), blk=blk)
+
+
+def _birrt_worker_run(a):
+    s, g, sd = a
+    if len(s):
+        _REF_STATE["planner"].PlanBatch(s, g, sd)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(PLAN_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload in PLAN_WORKLOADS:
+        (run_birrt_reference if args.impl == "reference" else run_birrt)(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return

@@ -202,6 +202,93 @@ int cc_query_get_work_trace(cc_query* q, uint32_t* out_iterations, int n);
 int cc_scene_set_counters(cc_scene* s, int enabled);
 int cc_scene_get_stats(const cc_scene* s, cc_stats* out);
 
+
+/* ==== planners on the batched entry (BASELINE.json configs[2]) =========================================
+ * The reference's RRT family spends its time in PlannerParameters::CheckPathAllConstraints (planner.h:373-379) ->
+ * DynamicsCollisionConstraint::Check (planningutils.cpp:2586-3629), one sample at a time.  These entry points run the same
+ * planners with every edge check going through cc_check_batch:
+ *   - one SpatialTree::Extend (plugins/rplanners/rplanners.h:308-460) is a ray of up to 100 steps whose configurations do
+ *     not depend on any collision result, so the whole ray is checked in one batch and the first failing step decides how
+ *     many nodes are added (identical outcome to the serial loop);
+ *   - `nproblems` independent planning problems advance in lockstep: each round gathers the pending ray / shortcut of every
+ *     live problem into ONE cc_check_batch call.
+ * Replaces, per problem: BirrtPlanner::InitPlan/PlanPath/_ExtractPath (plugins/rplanners/rrt.h:279-659),
+ * RrtPlanner::_SimpleOptimizePath (rrt.h:151-240) and the default post-processor LinearSmoother::_OptimizePath /
+ * _OptimizePathSingleDOF / SegmentFeasible (plugins/rplanners/linearsmoother.cpp:279-559, 1235-1263; retiming is not part
+ * of this path). */
+typedef struct cc_planner cc_planner;
+
+/* The configuration space PlannerParameters::SetRobotActiveJoints builds (planner.cpp:650-697): limits, resolutions,
+ * DOF weights of SimpleDistanceMetric (planningutils.cpp:4705-4723) and the circular mask of SubtractDOFValues
+ * (kinbody.cpp:1357-1394).  All arrays have ndof entries and are copied. */
+typedef struct cc_cspace {
+    int32_t ndof;
+    int32_t reserved;
+    const double* lower;
+    const double* upper;
+    const double* resolution;
+    const double* weights;
+    const uint8_t* circular;
+} cc_cspace;
+
+typedef struct cc_birrt_params {
+    double step_length;              /* PlannerParameters::_fStepLength, default 0.04 (planner.cpp:315) */
+    double goal_bias;                /* BirrtPlanner::_fGoalBiasProb = 0.01 (rrt.h:315) */
+    double point_tolerance;          /* TrajectoryTimingParameters::_pointtolerance = 0.2 (plannerparameters.h:455) */
+    int32_t max_iterations;          /* _nMaxIterations, <= 0 -> 10000 (rrt.h:358-359) */
+    int32_t path_optimize_iterations;/* _ExtractPath calls _SimpleOptimizePath(path, 10) (rrt.h:647) */
+    int32_t smoother_iterations;     /* linearsmoother _nMaxIterations, reference default 100; 0 = no post-processing */
+    int32_t max_extend_steps;        /* Extend's "avoid infinite loops" bound, 100 (rplanners.h:324) */
+    int32_t speculate_steps;         /* steps of a ray sent per round (<= 0: the whole ray) */
+    int32_t reserved;
+} cc_birrt_params;
+
+enum cc_plan_status { CC_PLAN_FAILED = 0, CC_PLAN_SOLVED = 1, CC_PLAN_BAD_INITIAL = 2, CC_PLAN_BAD_GOAL = 3 };
+
+typedef struct cc_plan_result {
+    int32_t status;                  /* cc_plan_status */
+    int32_t iterations;              /* main-loop passes (the reference logs iter/3) */
+    int32_t nodes_forward, nodes_backward;
+    int32_t waypoints_raw;           /* after _ExtractPath (incl. _SimpleOptimizePath) */
+    int32_t waypoints;               /* after the linear smoother */
+    int32_t rounds;                  /* lockstep rounds this problem took part in */
+    int32_t reserved;
+    double length_raw, length;       /* sum of SimpleDistanceMetric over consecutive waypoints */
+    uint64_t configs_submitted;      /* configurations sent to the checker for this problem */
+    uint64_t configs_serial;         /* configurations the serial per-sample loop would have checked (up to each first failure) */
+} cc_plan_result;
+
+/* A checker for groups of ordered segments.  Configurations q[nconfigs][ndof]; segment s owns configurations
+ * [segment_begin[s], segment_begin[s+1]) in the order the reference checks them; group g owns segments
+ * [group_begin[g], group_begin[g+1]).  For every group the callee reports the first segment holding a colliding
+ * configuration (-1 if none), the cc_verdict_bits of that configuration, and the global index of that configuration.
+ * It may stop inside a group at its first failure (what the serial reference does). */
+typedef int (*cc_group_check_fn)(void* user, const double* q, int nconfigs, int ndof,
+                                 const int32_t* group_begin, int ngroups, const int32_t* segment_begin, int nsegments,
+                                 int32_t* first_fail_segment, int32_t* fail_verdict, int32_t* first_fail_config);
+
+int cc_planner_create(const cc_cspace* space, cc_planner** out);
+int cc_planner_destroy(cc_planner* p);
+/* Edge checks through cc_check_batch on `q` (its active DOFs must be the planner's DOFs, in order). */
+int cc_planner_set_query(cc_planner* p, cc_query* q);
+/* Edge checks through a caller-supplied checker (the test harness plugs the CPU oracle in here). */
+int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user);
+/* The sample sequence DynamicsCollisionConstraint::Check visits for the edge q0 -> q1 (planningutils.cpp:2692-2835,
+ * 3405-3454), in checking order.  interval: 0 IT_Open, 1 IT_OpenStart, 2 IT_OpenEnd, 3 IT_Closed (planner.h).  Writes at
+ * most max_configs rows to out_configs (may be NULL) and returns the count in *out_count; -1 there = the edge leaves the
+ * joint limits (state-setting error). */
+int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, int interval,
+                            double* out_configs, int max_configs, int* out_count);
+/* BiRRT + path shortcutting for nproblems (start, goal) pairs in lockstep.  starts/goals: [nproblems][ndof];
+ * seeds[nproblems] = PlannerParameters::_nRandomGeneratorSeed per problem.  results[nproblems] is filled; the paths stay in
+ * the planner until the next call and are read with cc_planner_get_path. */
+int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts,
+                        const double* goals, const uint32_t* seeds, cc_plan_result* results);
+/* which: 0 = smoothed path, 1 = raw path.  Copies up to max_waypoints rows; *out_waypoints = the path's length. */
+int cc_planner_get_path(const cc_planner* p, int problem, int which, double* out, int max_waypoints, int* out_waypoints);
+/* Totals of the last cc_birrt_plan_batch: rounds, checker calls, configurations submitted, serial-equivalent configurations. */
+int cc_planner_get_totals(const cc_planner* p, uint64_t* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,865 @@
+// cc_planner.cpp — BiRRT + linear shortcutting on the batched collision entry (host side, C++20).
+//
+// What the reference does (paths relative to the OpenRAVE tree) and what this file restates:
+//   plugins/rplanners/rrt.h:279-368   BirrtPlanner::InitPlan        start/goal validation, tree roots
+//   plugins/rplanners/rrt.h:370-540   BirrtPlanner::PlanPath        sample / extend A / extend B toward A / swap
+//   plugins/rplanners/rplanners.h:308-460  SpatialTree::Extend      step-length ray toward the target, <= 100 steps
+//   plugins/rplanners/rrt.h:151-240   RrtPlanner::_SimpleOptimizePath   10 random shortcuts on the raw path
+//   plugins/rplanners/rrt.h:617-659   BirrtPlanner::_ExtractPath
+//   plugins/rplanners/linearsmoother.cpp:279-383, 385-559, 1235-1263   LinearSmoother (default post-processor)
+//   src/libopenrave/planningutils.cpp:2586-3629  DynamicsCollisionConstraint::Check, linear branch (the sample sequence)
+//   src/libopenrave/planner.cpp:88-112, 650-697  AddStatesWithLimitCheck, SetRobotActiveJoints
+//   plugins/basesamplers/mt19937ar.h:101-162, robotconfiguration.cpp:81-112   the samplers
+//
+// What is different by design: the reference evaluates one configuration at a time and stops at the first failure.  Here
+// every planning problem is a coroutine that suspends whenever it needs a verdict; the driver collects the pending request
+// of every live problem (a "group" of ordered segments), sends all of them through ONE cc_check_batch call, and resumes
+// the problems with the index of their first failing segment.  The configurations of an Extend ray, a shortcut or a
+// smoother candidate never depend on a collision result inside the same request, so the outcome equals the serial loop's.
+// The nearest-neighbour structure is an exact linear scan (the reference's cover tree, rplanners.h:170-860, returns the
+// same node up to ties); insertion refuses a node closer than 0.001 * step to its nearest neighbour like _InsertRecursive.
+#include <algorithm>
+#include <cmath>
+#include <coroutine>
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <random>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/cudacollision.h"
+
+extern "C" void cc_internal_set_error(const char* msg);   // cudacollision.cu (thread-local cc_last_error text)
+
+namespace {
+
+int fail(int code, const char* msg) { cc_internal_set_error(msg); return code; }
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kEpsilon = 1e-15;                               // g_fEpsilon for dReal = double (openrave.h:130)
+const double kEpsilonLinear = std::pow(kEpsilon, 0.9);           // libopenrave.h:140
+const double kEpsilonJointLimit = std::pow(kEpsilon, 0.8);       // libopenrave.h:141
+const double kEpsilonDotProduct = std::pow(kEpsilon, 0.8);       // rrt.h:22
+enum Interval { IT_Open = 0, IT_OpenStart = 1, IT_OpenEnd = 2, IT_Closed = 3 };
+
+// ------------------------------------------------------------------------------------------------ configuration space
+struct CSpace {
+    int n = 0;
+    std::vector<double> lo, hi, res, w2;
+    std::vector<uint8_t> circ;
+    bool any_circular = false;
+
+    // KinBody::SubtractDOFValues (kinbody.cpp:1357-1394): a <- a - b, circular DOFs wrapped into [-pi, pi)
+    void diff(double* a, const double* b) const
+    {
+        for (int i = 0; i < n; ++i) {
+            double d = a[i] - b[i];
+            if (any_circular && circ[i]) {
+                if (d < -kPi) d += 2 * kPi * std::ceil((-kPi - d) / (2 * kPi));
+                else if (d >= kPi) d -= 2 * kPi * std::floor((d + kPi) / (2 * kPi));
+            }
+            a[i] = d;
+        }
+    }
+    // SimpleDistanceMetric::Eval (planningutils.cpp:4714-4723)
+    double dist(const double* c0, const double* c1) const
+    {
+        double s = 0;
+        for (int i = 0; i < n; ++i) {
+            double d = c0[i] - c1[i];
+            if (any_circular && circ[i]) {
+                if (d < -kPi) d += 2 * kPi * std::ceil((-kPi - d) / (2 * kPi));
+                else if (d >= kPi) d -= 2 * kPi * std::floor((d + kPi) / (2 * kPi));
+            }
+            s += w2[i] * d * d;
+        }
+        return std::sqrt(s);
+    }
+    // AddStatesWithLimitCheck (planner.cpp:88-112): returns true when the clamp moved q by more than the joint epsilon
+    bool neigh(double* q, const double* delta) const
+    {
+        bool deviated = false;
+        for (int i = 0; i < n; ++i) {
+            q[i] += delta[i];
+            if (q[i] > hi[i]) { if (q[i] > hi[i] + kEpsilonJointLimit) deviated = true; q[i] = hi[i]; }
+            else if (q[i] < lo[i]) { if (q[i] < lo[i] - kEpsilonJointLimit) deviated = true; q[i] = lo[i]; }
+        }
+        return deviated;
+    }
+};
+
+// mt19937 sampler (plugins/basesamplers/mt19937ar.h): same generator as std::mt19937 seeded with init_genrand(seed); the
+// float constants 1.0f/4294967295.0f and 1.0f/4294967296.0f both round to 2^-32.
+struct Sampler {
+    std::mt19937 gen;
+    explicit Sampler(uint32_t seed = 0) : gen(seed) {}
+    uint32_t u32() { return (uint32_t)gen(); }
+    double real(Interval it = IT_Closed)
+    {
+        const double k = 1.0 / 4294967296.0;
+        const double r = (double)u32();
+        if (it == IT_Open) return (r + 0.5) * k;
+        if (it == IT_OpenStart) return (r + 1.0) * k;
+        return r * k;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ edge sample sequence
+// DynamicsCollisionConstraint::Check, positions-only linear branch.  Order: q1 first when the interval is closed at the
+// end (:2692-2708), then q0 when closed at the start (:2809-2826), then steps start..numSteps-1 produced by repeated
+// _neighstatefn from the previous sample (:3405-3454), then the residual sample when the walk did not land on q1 (:3524).
+// Returns the number of appended configurations or -1 when a step leaves the joint limits.
+int edge_samples(const CSpace& cs, const double* q0, const double* q1, int interval, std::vector<double>& out,
+                 std::vector<double>* times = nullptr)
+{
+    const int n = cs.n;
+    int start = (interval == IT_Open || interval == IT_OpenStart) ? 1 : 0;
+    const bool check_end = (interval == IT_OpenStart || interval == IT_Closed);
+    int count = 0;
+    auto push = [&](const double* q, double t) { out.insert(out.end(), q, q + n); if (times) times->push_back(t); ++count; };
+    if (check_end) push(q1, 1.0);
+    std::vector<double> dQ(q1, q1 + n);
+    cs.diff(dQ.data(), q0);
+    int nsteps = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+        int s = cs.res[i] != 0 ? (int)(std::fabs(dQ[i]) / cs.res[i] + 0.99) : (int)(std::fabs(dQ[i]) * 100);
+        total += s;
+        nsteps = std::max(nsteps, s);
+    }
+    if (total == 0 && start > 0) return count;
+    if (start == 0) { push(q0, 0.0); start = 1; }
+    if (nsteps == 0) return count;
+    const double fisteps = 1.0 / nsteps;
+    for (int i = 0; i < n; ++i) dQ[i] *= fisteps;
+    std::vector<double> cur(q0, q0 + n), d(n);
+    if (cs.neigh(cur.data(), dQ.data())) return -1;
+    for (int f = start; f < nsteps; ++f) {
+        push(cur.data(), f * fisteps);
+        double scale = 1.0;
+        bool big = false;
+        for (int i = 0; i < n; ++i) {
+            d[i] = q0[i] + (f + 1) * dQ[i] - cur[i];
+            if (std::fabs(d[i]) > cs.res[i]) { scale = big ? std::min(scale, cs.res[i] / std::fabs(d[i])) : cs.res[i] / std::fabs(d[i]); big = true; }
+        }
+        if (big) for (int i = 0; i < n; ++i) d[i] *= scale;
+        if (cs.neigh(cur.data(), d.data())) return -1;
+    }
+    double e = 0;
+    for (int i = 0; i < n; ++i) e += (cur[i] - q1[i]) * (cur[i] - q1[i]);
+    if (std::sqrt(e) > 1e-7) push(cur.data(), 1.0);
+    return count;
+}
+
+// ------------------------------------------------------------------------------------------------ request / coroutine glue
+struct Group {                       // one request of one problem: ordered segments of ordered configurations
+    std::vector<double> q;
+    std::vector<int32_t> seg_begin;  // [nseg + 1], in configurations, local to the group
+    bool state_error = false;        // a segment could not be sampled (edge left the limits): treated as a failure of that segment
+    int error_segment = -1;
+    void clear() { q.clear(); seg_begin.assign(1, 0); state_error = false; error_segment = -1; }
+    int nseg() const { return (int)seg_begin.size() - 1; }
+};
+
+struct CheckReply { int first_fail_segment = -1; int verdict = 0; };
+
+struct Problem;
+
+template <class T>
+struct Task {
+    struct promise_type {
+        T value{};
+        std::coroutine_handle<> continuation;
+        Task get_return_object() { return Task{std::coroutine_handle<promise_type>::from_promise(*this)}; }
+        std::suspend_always initial_suspend() noexcept { return {}; }
+        struct Final {
+            bool await_ready() noexcept { return false; }
+            std::coroutine_handle<> await_suspend(std::coroutine_handle<promise_type> h) noexcept
+            {
+                auto c = h.promise().continuation;
+                return c ? c : std::noop_coroutine();
+            }
+            void await_resume() noexcept {}
+        };
+        Final final_suspend() noexcept { return {}; }
+        void return_value(T v) { value = std::move(v); }
+        void unhandled_exception() { std::terminate(); }
+    };
+    std::coroutine_handle<promise_type> h;
+    explicit Task(std::coroutine_handle<promise_type> hh) : h(hh) {}
+    Task(Task&& o) noexcept : h(o.h) { o.h = nullptr; }
+    Task(const Task&) = delete;
+    ~Task() { if (h) h.destroy(); }
+    bool await_ready() const noexcept { return false; }
+    std::coroutine_handle<> await_suspend(std::coroutine_handle<> c) noexcept { h.promise().continuation = c; return h; }
+    T await_resume() { return std::move(h.promise().value); }
+};
+
+// ------------------------------------------------------------------------------------------------ RRT tree
+struct Tree {
+    int dof = 0;
+    bool fromgoal = false;
+    double step = 0.04, mindist = 0;
+    std::vector<double> q;          // [nodes][dof]
+    std::vector<int32_t> parent;
+    std::vector<uint32_t> userdata;
+    int size() const { return (int)parent.size(); }
+    const double* cfg(int i) const { return &q[(size_t)i * dof]; }
+    int nearest(const CSpace& cs, const double* target, double* dist_out = nullptr) const
+    {
+        int best = -1;
+        double bd = INFINITY;
+        for (int i = 0; i < size(); ++i) {
+            const double d = cs.dist(cfg(i), target);
+            if (d < bd) { bd = d; best = i; }
+        }
+        if (dist_out) *dist_out = bd;
+        return best;
+    }
+    // _InsertNode (rplanners.h:710-738): -1 when a node within _mindistance already exists
+    int insert(const CSpace& cs, int par, const double* c, uint32_t ud)
+    {
+        if (size() > 0) {
+            double d;
+            nearest(cs, c, &d);
+            if (d <= mindist) return -1;
+        }
+        q.insert(q.end(), c, c + dof);
+        parent.push_back(par);
+        userdata.push_back(ud);
+        return size() - 1;
+    }
+};
+
+enum ExtendType { ET_Failed = 0, ET_Sucess = 1, ET_Connected = 2 };
+
+struct PathList {   // LinearSmoother's list< pair<config, distance-from-previous> >
+    struct Node { std::vector<double> q; double d; };
+    std::list<Node> nodes;
+};
+
+}  // namespace
+
+struct cc_planner {
+    CSpace cs;
+    cc_query* query = nullptr;
+    cc_group_check_fn fn = nullptr;
+    void* user = nullptr;
+    std::vector<std::unique_ptr<Problem>> problems;
+    uint64_t totals[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+struct Problem {
+    const CSpace* cs = nullptr;
+    cc_birrt_params prm{};
+    std::vector<double> start, goal;
+    uint32_t seed = 0;
+    cc_plan_result res{};
+    std::vector<double> path_raw, path;       // flat [waypoints][dof]
+
+    // request / reply mailbox
+    Group group;
+    CheckReply reply;
+    std::coroutine_handle<> waiting;
+    bool has_request = false, done = false;
+
+    struct CheckAwait {
+        Problem* p;
+        bool await_ready() const noexcept { return false; }
+        void await_suspend(std::coroutine_handle<> h) noexcept { p->waiting = h; p->has_request = true; }
+        CheckReply await_resume() noexcept { return p->reply; }
+    };
+    // submit the group built in `group`; an empty group needs no checker
+    CheckAwait check() { return CheckAwait{this}; }
+
+    Tree fwd, bwd;
+    Sampler uniform, config;
+
+    int ndof() const { return cs->n; }
+
+    // one segment = one CheckPathAllConstraints call
+    void add_edge(const double* q0, const double* q1, int interval, std::vector<double>* times = nullptr)
+    {
+        const size_t before = group.q.size();
+        const int c = edge_samples(*cs, q0, q1, interval, group.q, times);
+        if (c < 0) {
+            group.q.resize(before);
+            if (!group.state_error) { group.state_error = true; group.error_segment = group.nseg(); }
+        }
+        group.seg_begin.push_back((int32_t)(group.q.size() / ndof()));
+    }
+
+    // RobotConfigurationSampler::SampleSequence (robotconfiguration.cpp:81-112) over its own mt19937
+    void sample_config(std::vector<double>& out)
+    {
+        out.resize(ndof());
+        for (int i = 0; i < ndof(); ++i) {
+            const double u = config.real(IT_Closed);
+            out[i] = cs->circ[i] ? -kPi + 2 * kPi * u : cs->lo[i] + u * (cs->hi[i] - cs->lo[i]);
+        }
+    }
+
+    // SpatialTree::Extend.  The ray c0 -> c1 -> ... is generated up front (it depends on the target only); chunks of
+    // `speculate_steps` steps are submitted, one segment per step, and nodes are inserted for the steps before the first
+    // failing one.
+    Task<int> extend(Tree& tree, const std::vector<double>& target, int& lastnode)
+    {
+        const int n = ndof();
+        const int nn = tree.nearest(*cs, target.data());
+        if (nn < 0) co_return (int)ET_Failed;
+        int pnode = nn;
+        lastnode = nn;
+        bool added = false;
+        std::vector<double> cur(tree.cfg(nn), tree.cfg(nn) + n), nxt(n), delta(n);
+        const int maxsteps = prm.max_extend_steps > 0 ? prm.max_extend_steps : 100;
+        const int chunk = prm.speculate_steps > 0 ? prm.speculate_steps : maxsteps;
+        int iter = 0;
+        int terminal = -1;                      // set when the ray ends without needing a check
+        while (iter < maxsteps && terminal < 0) {
+            // ---- generate up to `chunk` steps
+            group.clear();
+            std::vector<double> ray;            // the new configuration of every generated step
+            std::vector<double> c = cur;
+            int end_code = -1;                  // how the generation stopped: -1 = chunk/bound exhausted
+            int gen = 0;
+            while (gen < chunk && iter + gen < maxsteps) {
+                double fdist = cs->dist(c.data(), target.data());
+                if (fdist > tree.step) fdist = tree.step / fdist;
+                else if (fdist <= 0.01 * tree.step) { end_code = ET_Connected; break; }
+                else fdist = 1;
+                nxt = c;
+                delta = target;
+                cs->diff(delta.data(), c.data());
+                for (int i = 0; i < n; ++i) delta[i] *= fdist;
+                cs->neigh(nxt.data(), delta.data());            // NSS_Failed never happens for the default neighbour function
+                if (cs->dist(c.data(), nxt.data()) <= 0.01 * tree.step) { end_code = 100; break; }   // did not move
+                if (tree.fromgoal) add_edge(nxt.data(), c.data(), IT_OpenEnd);
+                else add_edge(c.data(), nxt.data(), IT_OpenStart);
+                ray.insert(ray.end(), nxt.begin(), nxt.end());
+                c = nxt;
+                ++gen;
+            }
+            int passed = gen;
+            if (gen > 0) {
+                CheckReply r = co_await check();
+                if (r.first_fail_segment >= 0) passed = r.first_fail_segment;
+            }
+            for (int s = 0; s < passed; ++s) {
+                const int id = tree.insert(*cs, pnode, &ray[(size_t)s * n], 0);
+                if (id >= 0) { pnode = id; lastnode = id; added = true; }
+            }
+            if (passed < gen) { terminal = added ? ET_Sucess : ET_Failed; break; }
+            iter += gen;
+            cur = c;
+            if (end_code == ET_Connected) { terminal = ET_Connected; break; }
+            if (end_code == 100) { terminal = added ? ET_Sucess : ET_Failed; break; }
+        }
+        if (terminal < 0) terminal = added ? ET_Sucess : ET_Failed;
+        co_return terminal;
+    }
+
+    double path_length(const std::vector<double>& p) const
+    {
+        const int n = ndof();
+        double L = 0;
+        for (size_t i = 1; i < p.size() / n; ++i) L += cs->dist(&p[(i - 1) * n], &p[i * n]);
+        return L;
+    }
+
+    // RrtPlanner::_SimpleOptimizePath (rrt.h:151-240) on a flat path
+    Task<int> simple_optimize(std::vector<double>& p, int numiterations)
+    {
+        const int n = ndof();
+        if ((int)p.size() <= 2 * n) co_return 0;
+        int nrejected = 0, curiter = numiterations;
+        std::vector<double> vstart(n), vend(n), d0(n), d1(n), times;
+        while (curiter > 0 && nrejected < (int)p.size() + 4 * n) {
+            --curiter;
+            const int npts = (int)p.size() / n;
+            const int endIndex = 2 + (int)(uniform.u32() % (uint32_t)(npts - 2));
+            const int startIndex = (int)(uniform.u32() % (uint32_t)(endIndex - 1));
+            nrejected++;
+            std::copy(p.begin() + (size_t)startIndex * n, p.begin() + (size_t)(startIndex + 1) * n, vstart.begin());
+            std::copy(p.begin() + (size_t)(endIndex - 1) * n, p.begin() + (size_t)endIndex * n, vend.begin());
+            d0 = vend;
+            cs->diff(d0.data(), vstart.data());
+            const int mid = startIndex + (endIndex - startIndex) / 2;
+            std::copy(p.begin() + (size_t)mid * n, p.begin() + (size_t)(mid + 1) * n, d1.begin());
+            cs->diff(d1.data(), vstart.data());
+            double dot = 0, l0 = 0, l1 = 0;
+            for (int i = 0; i < n; ++i) { dot += d0[i] * d1[i]; l0 += d0[i] * d0[i]; l1 += d1[i] * d1[i]; }
+            if (!(std::fabs(dot * dot - l0 * l1) > kEpsilonDotProduct)) continue;       // colinear: nothing to gain
+            group.clear();
+            times.clear();
+            add_edge(vstart.data(), vend.data(), IT_Open, &times);
+            bool failed = group.state_error;
+            if (!failed && group.q.size() > 0) {
+                CheckReply r = co_await check();
+                failed = r.first_fail_segment >= 0;
+            }
+            if (failed) {
+                if (nrejected++ > (int)p.size() + 8) break;
+                continue;
+            }
+            // the checked configurations replace [startIndex+1, endIndex) — the slot of vend included (rrt.h:214-231)
+            std::vector<double> np(p.begin(), p.begin() + (size_t)(startIndex + 1) * n);
+            np.insert(np.end(), group.q.begin(), group.q.end());
+            np.insert(np.end(), p.begin() + (size_t)endIndex * n, p.end());
+            p.swap(np);
+            nrejected = 0;
+            if ((int)p.size() <= 2 * n) co_return 0;
+        }
+        co_return 0;
+    }
+
+    // LinearSmoother::SegmentFeasible (linearsmoother.cpp:1235-1263): the segment and its +/- pointtolerance * resolution copies
+    void add_feasible_segments(const double* a, const double* b, int interval)
+    {
+        const int n = ndof();
+        std::vector<double> an(n), bn(n);
+        const double pert[3] = {0, prm.point_tolerance, -prm.point_tolerance};
+        for (double f : pert) {
+            for (int i = 0; i < n; ++i) {
+                an[i] = std::min(std::max(a[i] + f * cs->res[i], cs->lo[i]), cs->hi[i]);
+                bn[i] = std::min(std::max(b[i] + f * cs->res[i], cs->lo[i]), cs->hi[i]);
+            }
+            add_edge(an.data(), bn.data(), interval);
+        }
+    }
+
+    struct Span {   // the random sub-path both smoother passes pick (linearsmoother.cpp:293-325)
+        std::list<PathList::Node>::iterator itstart, itstartprev, itend, itendprev;
+        double fstartdist, fenddist, fstartdelta, fenddelta;
+        int numnodes;
+        bool degenerate;
+    };
+    Span pick_span(PathList& lp, double totaldist, Sampler& rs) const
+    {
+        Span s;
+        s.fstartdist = std::max(0.0, totaldist - prm.step_length) * rs.real(IT_OpenEnd);
+        s.fenddist = s.fstartdist + (totaldist - s.fstartdist) * rs.real(IT_OpenStart);
+        s.fstartdelta = s.fenddelta = 0;
+        double fcur = 0;
+        s.itstartprev = s.itstart = lp.nodes.begin();
+        while (s.itstart != lp.nodes.end()) {
+            if (s.fstartdist >= fcur && s.fstartdist < fcur + s.itstart->d) { s.fstartdelta = s.fstartdist - fcur; break; }
+            fcur += s.itstart->d;
+            s.itstartprev = s.itstart;
+            ++s.itstart;
+        }
+        s.itendprev = s.itstartprev;
+        s.itend = s.itstart;
+        s.numnodes = 0;
+        while (s.itend != lp.nodes.end()) {
+            if (s.fenddist >= fcur && s.fenddist < fcur + s.itend->d) { s.fenddelta = s.fenddist - fcur; break; }
+            fcur += s.itend->d;
+            s.itendprev = s.itend;
+            ++s.itend;
+            ++s.numnodes;
+        }
+        s.degenerate = (s.itstart == s.itend) || s.itstart == lp.nodes.end() || s.itend == lp.nodes.end();
+        return s;
+    }
+
+    // LinearSmoother::_OptimizePath (linearsmoother.cpp:279-383)
+    Task<double> smooth_shortcut(PathList& lp, double totaldist, int maxiter, Sampler& rs)
+    {
+        const int n = ndof();
+        std::vector<double> vs(n), ve(n);
+        int nrejected = 0;
+        for (int it = 0; it < maxiter; ++it) {
+            if (nrejected >= 20) break;
+            Span s = pick_span(lp, totaldist, rs);
+            if (s.degenerate) continue;
+            nrejected++;
+            if (s.itstart == lp.nodes.begin()) vs = s.itstart->q;
+            else {
+                const double f = s.fstartdelta / s.itstart->d;
+                for (int i = 0; i < n; ++i) vs[i] = s.itstart->q[i] * f + s.itstartprev->q[i] * (1 - f);
+            }
+            if (s.itend == std::prev(lp.nodes.end())) ve = s.itend->q;
+            else {
+                const double f = s.fenddelta / s.itend->d;
+                for (int i = 0; i < n; ++i) ve[i] = s.itend->q[i] * f + s.itendprev->q[i] * (1 - f);
+            }
+            const double newdist = cs->dist(vs.data(), ve.data());
+            if (newdist > s.fenddist - s.fstartdist - 0.5 * prm.step_length) continue;
+            group.clear();
+            add_feasible_segments(vs.data(), ve.data(), IT_Open);
+            bool failed = group.state_error;
+            if (!failed && group.q.size() > 0) {
+                CheckReply r = co_await check();
+                failed = r.first_fail_segment >= 0;
+            }
+            if (failed) continue;
+            lp.nodes.insert(s.itstart, PathList::Node{vs, s.fstartdelta});
+            s.itend->d -= s.fenddelta;
+            s.itend = lp.nodes.insert(s.itend, PathList::Node{ve, newdist});
+            lp.nodes.erase(s.itstart, s.itend);
+            totaldist += newdist - (s.fenddist - s.fstartdist);
+            nrejected = 0;
+        }
+        co_return totaldist;
+    }
+
+    // LinearSmoother::_OptimizePathSingleDOF (linearsmoother.cpp:385-559): straighten ONE DOF over a random sub-path
+    Task<double> smooth_single_dof(PathList& lp, double totaldist, int maxiter, Sampler& rs)
+    {
+        const int n = ndof();
+        std::vector<PathList::Node> pv;
+        int nrejected = 0;
+        for (int it = 0; it < maxiter; ++it) {
+            if (nrejected >= 20) break;
+            Span s = pick_span(lp, totaldist, rs);
+            const uint32_t idof = rs.u32() % (uint32_t)n;
+            if (s.degenerate) continue;
+            nrejected++;
+            pv.assign(s.numnodes + 2, PathList::Node{std::vector<double>(n), 0});
+            if (std::fabs(s.fstartdelta) <= kEpsilonLinear) pv[0] = PathList::Node{s.itstart->q, 0};
+            else {
+                const double f = s.fstartdelta / s.itstart->d;
+                for (int i = 0; i < n; ++i) pv[0].q[i] = s.itstart->q[i] * f + s.itstartprev->q[i] * (1 - f);
+            }
+            if (std::fabs(s.fenddelta - s.itend->d) <= kEpsilonLinear) pv[s.numnodes + 1] = *s.itend;
+            else {
+                pv[s.numnodes + 1].d = s.fenddelta;
+                const double f = s.fenddelta / s.itend->d;
+                for (int i = 0; i < n; ++i) pv[s.numnodes + 1].q[i] = s.itend->q[i] * f + s.itendprev->q[i] * (1 - f);
+            }
+            const double v0 = pv[0].q[idof], v1 = pv[s.numnodes + 1].q[idof];
+            const double fdelta = (v1 - v0) / (s.fenddist - s.fstartdist);
+            double fcur = 0, newdist = 0;
+            auto itn = s.itstart;
+            int k = 0;
+            do {
+                if (k == 0) fcur = itn->d - s.fstartdelta; else fcur += itn->d;
+                pv[k + 1].q = itn->q;
+                pv[k + 1].q[idof] = v0 + fcur * fdelta;
+                pv[k + 1].d = cs->dist(pv[k].q.data(), pv[k + 1].q.data());
+                newdist += pv[k + 1].d;
+                ++itn;
+                ++k;
+            } while (itn != s.itend);
+            pv[s.numnodes + 1].d = cs->dist(pv[s.numnodes].q.data(), pv[s.numnodes + 1].q.data());
+            newdist += pv[s.numnodes + 1].d;
+            if (newdist > s.fenddist - s.fstartdist - 0.5 * prm.step_length) continue;
+            group.clear();
+            for (size_t i = 0; i + 1 < pv.size(); ++i)
+                add_feasible_segments(pv[i].q.data(), pv[i + 1].q.data(), i + 2 == pv.size() ? IT_Open : IT_OpenStart);
+            bool failed = group.state_error;
+            if (!failed && group.q.size() > 0) {
+                CheckReply r = co_await check();
+                failed = r.first_fail_segment >= 0;
+            }
+            if (failed) continue;
+            if (std::fabs(s.fstartdelta) > kEpsilonLinear) {
+                pv[0].d = s.fstartdelta;
+                lp.nodes.insert(s.itstart, pv[0]);
+            }
+            itn = s.itstart;
+            k = 1;
+            do { *itn = pv[k++]; ++itn; } while (itn != s.itend);
+            if (std::fabs(s.fenddelta - s.itend->d) > kEpsilonLinear) {
+                lp.nodes.insert(s.itend, pv[s.numnodes + 1]);
+                s.itend->d -= s.fenddelta;
+            }
+            totaldist += newdist - (s.fenddist - s.fstartdist);
+            nrejected = 0;
+        }
+        co_return totaldist;
+    }
+
+    // LinearSmoother::PlanPath (linearsmoother.cpp:104-262), _nUseSingleDOFSmoothing == 1: 8/10 shortcuts, 2/10 single-DOF
+    Task<int> smooth(const std::vector<double>& in, std::vector<double>& out)
+    {
+        const int n = ndof();
+        Sampler rs(seed);
+        PathList lp;
+        double total = 0;
+        lp.nodes.push_back(PathList::Node{std::vector<double>(in.begin(), in.begin() + n), 0});
+        for (size_t i = 1; i < in.size() / n; ++i) {
+            const double d = cs->dist(lp.nodes.back().q.data(), &in[i * n]);
+            if (d > 0) { lp.nodes.push_back(PathList::Node{std::vector<double>(in.begin() + i * n, in.begin() + (i + 1) * n), d}); total += d; }
+        }
+        const int iters = prm.smoother_iterations;
+        if (lp.nodes.size() > 1) {
+            const double d1 = co_await smooth_shortcut(lp, total, iters * 8 / 10, rs);
+            co_await smooth_single_dof(lp, d1, iters * 2 / 10, rs);
+        }
+        out.clear();
+        for (auto& nd : lp.nodes) out.insert(out.end(), nd.q.begin(), nd.q.end());
+        if (lp.nodes.size() <= 1) out.insert(out.end(), in.end() - n, in.end());
+        co_return 0;
+    }
+
+    // BirrtPlanner::InitPlan + PlanPath for one start and one goal
+    Task<int> plan()
+    {
+        const int n = ndof();
+        uniform = Sampler(seed);
+        config = Sampler(seed);
+        for (Tree* t : {&fwd, &bwd}) {
+            t->dof = n;
+            t->step = prm.step_length;
+            t->mindist = 0.001 * prm.step_length;
+        }
+        fwd.fromgoal = false;
+        bwd.fromgoal = true;
+        // initial and goal configurations: CheckPathAllConstraints(v, v, IT_OpenStart) (rrt.h:78, 325)
+        group.clear();
+        add_edge(start.data(), start.data(), IT_OpenStart);
+        CheckReply r = co_await check();
+        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_INITIAL; co_return 0; }
+        fwd.insert(*cs, -1, start.data(), 0);
+        group.clear();
+        add_edge(goal.data(), goal.data(), IT_OpenStart);
+        r = co_await check();
+        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }
+        bwd.insert(*cs, -1, goal.data(), 0);
+
+        const int maxiter = prm.max_iterations > 0 ? prm.max_iterations : 10000;
+        Tree* A = &fwd;
+        Tree* B = &bwd;
+        int ia = -1, ib = -1, iter = 0;
+        bool sample_goal = true, solved = false;
+        std::vector<double> target;
+        while (!solved && iter < 3 * maxiter) {
+            ++iter;
+            res.iterations++;
+            target.clear();
+            if (sample_goal || uniform.real(IT_Closed) < prm.goal_bias) {
+                sample_goal = false;
+                (void)uniform.u32();              // one goal: its index draw is still consumed (rrt.h:441-444)
+                target.assign(goal.begin(), goal.end());
+            }
+            if (target.empty()) sample_config(target);
+            int et = co_await extend(*A, target, ia);
+            if (et == ET_Failed) {
+                if (iter > 3 * maxiter) break;
+                continue;
+            }
+            std::vector<double> toward(A->cfg(ia), A->cfg(ia) + n);
+            et = co_await extend(*B, toward, ib);
+            if (et == ET_Connected) { solved = true; break; }
+            std::swap(A, B);
+            iter += 3;
+            if (iter > 3 * maxiter) break;
+        }
+        res.nodes_forward = fwd.size();
+        res.nodes_backward = bwd.size();
+        if (!solved) { res.status = CC_PLAN_FAILED; co_return 0; }
+        // _ExtractPath: forward chain root -> connection, then backward chain connection -> root
+        const int cf = (A == &fwd) ? ia : ib, cb = (A == &bwd) ? ia : ib;
+        std::vector<int> chain;
+        for (int i = cf; i >= 0; i = fwd.parent[i]) chain.push_back(i);
+        path_raw.clear();
+        for (auto it = chain.rbegin(); it != chain.rend(); ++it) path_raw.insert(path_raw.end(), fwd.cfg(*it), fwd.cfg(*it) + n);
+        for (int i = cb; i >= 0; i = bwd.parent[i]) path_raw.insert(path_raw.end(), bwd.cfg(i), bwd.cfg(i) + n);
+        co_await simple_optimize(path_raw, prm.path_optimize_iterations);
+        res.waypoints_raw = (int)path_raw.size() / n;
+        res.length_raw = path_length(path_raw);
+        if (prm.smoother_iterations > 0) co_await smooth(path_raw, path);
+        else path = path_raw;
+        res.waypoints = (int)path.size() / n;
+        res.length = path_length(path);
+        res.status = CC_PLAN_SOLVED;
+        co_return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ the GPU checker
+// All configurations of all groups in one cc_check_batch call (speculative: nothing stops early), then the first failing
+// segment of every group in the reference's order.
+int gpu_group_check(cc_query* q, const double* cfg, int nconfigs, const int32_t* group_begin, int ngroups,
+                    const int32_t* segment_begin, int32_t* first_fail_segment, int32_t* fail_verdict, int32_t* first_fail_config,
+                    std::vector<uint32_t>& verdict)
+{
+    verdict.resize((size_t)std::max(nconfigs, 1));
+    if (nconfigs > 0) {
+        const int rc = cc_check_batch(q, cfg, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF, verdict.data(), nullptr, nullptr, nullptr);
+        if (rc != CC_OK) return rc;
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        first_fail_segment[g] = -1;
+        fail_verdict[g] = 0;
+        first_fail_config[g] = -1;
+        for (int s = group_begin[g]; s < group_begin[g + 1] && first_fail_segment[g] < 0; ++s)
+            for (int c = segment_begin[s]; c < segment_begin[s + 1]; ++c)
+                if (verdict[c]) { first_fail_segment[g] = s - group_begin[g]; fail_verdict[g] = (int32_t)verdict[c]; first_fail_config[g] = c; break; }
+    }
+    return CC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cc_planner_create(const cc_cspace* space, cc_planner** out)
+{
+    if (!space || !out || space->ndof <= 0 || !space->lower || !space->upper || !space->resolution)
+        return fail(CC_ERR_INVALID, "cc_planner_create: bad configuration space");
+    auto* p = new cc_planner();
+    CSpace& cs = p->cs;
+    cs.n = space->ndof;
+    cs.lo.assign(space->lower, space->lower + cs.n);
+    cs.hi.assign(space->upper, space->upper + cs.n);
+    cs.res.assign(space->resolution, space->resolution + cs.n);
+    cs.w2.assign(cs.n, 1.0);
+    if (space->weights) for (int i = 0; i < cs.n; ++i) cs.w2[i] = space->weights[i] * space->weights[i];
+    cs.circ.assign(cs.n, 0);
+    if (space->circular) cs.circ.assign(space->circular, space->circular + cs.n);
+    cs.any_circular = std::any_of(cs.circ.begin(), cs.circ.end(), [](uint8_t c) { return c != 0; });
+    *out = p;
+    return CC_OK;
+}
+
+int cc_planner_destroy(cc_planner* p)
+{
+    delete p;
+    return CC_OK;
+}
+
+int cc_planner_set_query(cc_planner* p, cc_query* q)
+{
+    if (!p || !q) return fail(CC_ERR_INVALID, "cc_planner_set_query: NULL argument");
+    cc_query_info info;
+    const int rc = cc_query_get_info(q, &info);
+    if (rc != CC_OK) return rc;
+    if (info.ndof_active != p->cs.n) return fail(CC_ERR_INVALID, "cc_planner_set_query: the query's active DOFs differ from the planner's");
+    p->query = q;
+    p->fn = nullptr;
+    return CC_OK;
+}
+
+int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user)
+{
+    if (!p || !fn) return fail(CC_ERR_INVALID, "cc_planner_set_checker: NULL argument");
+    p->fn = fn;
+    p->user = user;
+    p->query = nullptr;
+    return CC_OK;
+}
+
+int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, int interval, double* out_configs, int max_configs,
+                            int* out_count)
+{
+    if (!p || !q0 || !q1 || !out_count || interval < 0 || interval > 3) return fail(CC_ERR_INVALID, "cc_planner_edge_samples: bad arguments");
+    std::vector<double> buf;
+    const int c = edge_samples(p->cs, q0, q1, interval, buf);
+    *out_count = c;
+    if (c > 0 && out_configs) std::memcpy(out_configs, buf.data(), sizeof(double) * p->cs.n * (size_t)std::min(c, std::max(max_configs, 0)));
+    return CC_OK;
+}
+
+int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts, const double* goals,
+                        const uint32_t* seeds, cc_plan_result* results)
+{
+    if (!p || !params || nproblems < 0 || (nproblems > 0 && (!starts || !goals || !results)))
+        return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: bad arguments");
+    if (!p->query && !p->fn) return fail(CC_ERR_STATE, "cc_birrt_plan_batch: no checker bound (cc_planner_set_query)");
+    if (!(params->step_length > 0)) return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: step_length must be > 0");
+    const int n = p->cs.n;
+    p->problems.clear();
+    std::vector<Task<int>> tasks;
+    tasks.reserve(nproblems);
+    for (int k = 0; k < nproblems; ++k) {
+        auto pr = std::make_unique<Problem>();
+        pr->cs = &p->cs;
+        pr->prm = *params;
+        pr->start.assign(starts + (size_t)k * n, starts + (size_t)(k + 1) * n);
+        pr->goal.assign(goals + (size_t)k * n, goals + (size_t)(k + 1) * n);
+        pr->seed = seeds ? seeds[k] : 0;
+        std::memset(&pr->res, 0, sizeof(pr->res));
+        p->problems.push_back(std::move(pr));
+    }
+    for (int k = 0; k < nproblems; ++k) tasks.push_back(p->problems[k]->plan());
+    std::memset(p->totals, 0, sizeof(p->totals));
+
+    // start every coroutine: each runs until its first request (or to completion)
+    for (int k = 0; k < nproblems; ++k) {
+        tasks[k].h.resume();
+        if (tasks[k].h.done()) p->problems[k]->done = true;
+    }
+    std::vector<double> q;
+    std::vector<int32_t> group_begin, seg_begin, ffs, fv, ffc;
+    std::vector<int> owner;
+    std::vector<uint32_t> verdict;
+    for (;;) {
+        q.clear();
+        group_begin.assign(1, 0);
+        seg_begin.assign(1, 0);
+        owner.clear();
+        for (int k = 0; k < nproblems; ++k) {
+            Problem& pr = *p->problems[k];
+            if (pr.done || !pr.has_request) continue;
+            const int base = (int)(q.size() / n);
+            q.insert(q.end(), pr.group.q.begin(), pr.group.q.end());
+            for (int s = 1; s <= pr.group.nseg(); ++s) seg_begin.push_back(base + pr.group.seg_begin[s]);
+            group_begin.push_back((int32_t)seg_begin.size() - 1);
+            owner.push_back(k);
+        }
+        if (owner.empty()) break;
+        const int ngroups = (int)owner.size(), nconfigs = (int)(q.size() / n);
+        ffs.assign(ngroups, -1);
+        fv.assign(ngroups, 0);
+        ffc.assign(ngroups, -1);
+        int rc;
+        if (p->query) rc = gpu_group_check(p->query, q.data(), nconfigs, group_begin.data(), ngroups, seg_begin.data(), ffs.data(), fv.data(), ffc.data(), verdict);
+        else rc = p->fn(p->user, q.data(), nconfigs, n, group_begin.data(), ngroups, seg_begin.data(), (int)seg_begin.size() - 1, ffs.data(), fv.data(), ffc.data());
+        if (rc != CC_OK) {
+            if (!p->query) cc_internal_set_error("cc_birrt_plan_batch: the checker callback failed");
+            p->problems.clear();
+            return rc;
+        }
+        p->totals[0] += 1;
+        p->totals[1] += 1;
+        p->totals[2] += (uint64_t)nconfigs;
+        for (int g = 0; g < ngroups; ++g) {
+            Problem& pr = *p->problems[owner[g]];
+            const int cbeg = seg_begin[group_begin[g]], cend = seg_begin[group_begin[g + 1]];
+            int ff = ffs[g];
+            uint64_t serial = (ff >= 0 && ffc[g] >= 0) ? (uint64_t)(ffc[g] - cbeg + 1) : (uint64_t)(cend - cbeg);
+            // a segment that could not be sampled fails where it stands unless an earlier segment already did
+            if (pr.group.state_error && (ff < 0 || ff >= pr.group.error_segment)) {
+                ff = pr.group.error_segment;
+                serial = (uint64_t)(seg_begin[group_begin[g] + ff] - cbeg);
+            }
+            pr.res.configs_submitted += (uint64_t)(cend - cbeg);
+            pr.res.configs_serial += serial;
+            pr.res.rounds++;
+            p->totals[3] += serial;
+            pr.reply.first_fail_segment = ff;
+            pr.reply.verdict = fv[g];
+            pr.has_request = false;
+            auto h = pr.waiting;
+            pr.waiting = nullptr;
+            h.resume();
+            if (tasks[owner[g]].h.done()) pr.done = true;
+        }
+    }
+    for (int k = 0; k < nproblems; ++k) results[k] = p->problems[k]->res;
+    return CC_OK;
+}
+
+int cc_planner_get_path(const cc_planner* p, int problem, int which, double* out, int max_waypoints, int* out_waypoints)
+{
+    if (!p || problem < 0 || problem >= (int)p->problems.size() || !out_waypoints) return fail(CC_ERR_INVALID, "cc_planner_get_path: bad arguments");
+    const std::vector<double>& path = which == 1 ? p->problems[problem]->path_raw : p->problems[problem]->path;
+    const int n = p->cs.n, w = (int)path.size() / n;
+    *out_waypoints = w;
+    if (out && max_waypoints > 0) std::memcpy(out, path.data(), sizeof(double) * n * (size_t)std::min(w, max_waypoints));
+    return CC_OK;
+}
+
+int cc_planner_get_totals(const cc_planner* p, uint64_t* out4)
+{
+    if (!p || !out4) return fail(CC_ERR_INVALID, "cc_planner_get_totals: bad arguments");
+    std::memcpy(out4, p->totals, sizeof(p->totals));
+    return CC_OK;
+}
+
+}  // extern "C"

@@ -482,6 +482,9 @@ HBody* get_body(cc_scene* s, int body)
 // ================================================================================================ C ABI
 extern "C" {
 
+// used by the other translation units of this library (cc_planner.cpp) so that cc_last_error stays one per thread
+void cc_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
 const char* cc_last_error(void) { return g_err.c_str(); }
 int cc_version(void) { return 100; }
 

@@ -212,3 +212,140 @@ class DynamicsCollisionConstraint(object):
 def CheckPathAllConstraints(constraint, q0, q1, interval=IT_Closed, options=0xffff, filterreturn=None):
     """PlannerParameters::CheckPathAllConstraints (planner.h:373-379) for positions-only edges."""
     return constraint.Check(q0, q1, interval, options, filterreturn)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BiRRT + linear shortcutting in lockstep over the batched entry (libcudacollision.so: csrc/cc_planner.cpp)
+
+import ctypes
+
+
+class cc_cspace(ctypes.Structure):
+    _fields_ = [("ndof", ctypes.c_int32), ("reserved", ctypes.c_int32), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p),
+                ("resolution", ctypes.c_void_p), ("weights", ctypes.c_void_p), ("circular", ctypes.c_void_p)]
+
+
+class cc_birrt_params(ctypes.Structure):
+    _fields_ = [("step_length", ctypes.c_double), ("goal_bias", ctypes.c_double), ("point_tolerance", ctypes.c_double),
+                ("max_iterations", ctypes.c_int32), ("path_optimize_iterations", ctypes.c_int32),
+                ("smoother_iterations", ctypes.c_int32), ("max_extend_steps", ctypes.c_int32), ("speculate_steps", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class cc_plan_result(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("iterations", ctypes.c_int32), ("nodes_forward", ctypes.c_int32),
+                ("nodes_backward", ctypes.c_int32), ("waypoints_raw", ctypes.c_int32), ("waypoints", ctypes.c_int32),
+                ("rounds", ctypes.c_int32), ("reserved", ctypes.c_int32), ("length_raw", ctypes.c_double),
+                ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64)]
+
+
+PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
+PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
+                   "cc_planner_edge_samples", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+
+
+def _planner_lib():
+    from .checker import load_library
+    lib = load_library()
+    if getattr(lib, "_planner_ready", False):
+        return lib
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.cc_planner_create.argtypes = [ctypes.POINTER(cc_cspace), ctypes.POINTER(vp)]
+    lib.cc_planner_destroy.argtypes = [vp]
+    lib.cc_planner_set_query.argtypes = [vp, vp]
+    lib.cc_planner_set_checker.argtypes = [vp, vp, vp]
+    lib.cc_planner_edge_samples.argtypes = [vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
+    lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_planner_get_totals.argtypes = [vp, vp]
+    lib._planner_ready = True
+    return lib
+
+
+class BirrtPlanner(object):
+    """RaveCreatePlanner(env, 'birrt') on the batched collision entry, for one robot over its active DOFs.
+
+    `checker` is a CudaCollisionChecker (edge checks go through cc_check_batch) or a pair (function pointer, user block)
+    with the cc_group_check_fn signature (the tests plug the oracle's serial loop in that way).  `PlanBatch` runs many
+    (start, goal) problems in lockstep; `PlanPath` is the single-problem call of the reference API."""
+
+    def __init__(self, robot, checker, step_length=0.04, max_iterations=10000, goal_bias=0.01, smoother_iterations=100,
+                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=0):
+        self.lib = _planner_lib()
+        self.robot = robot
+        self.active = list(robot.GetActiveDOFIndices())
+        joints = [robot.joints[d] for d in self.active]
+        self._lo = np.array([j.lower for j in joints], dtype=np.float64)
+        self._hi = np.array([j.upper for j in joints], dtype=np.float64)
+        self._res = np.array([j.resolution for j in joints], dtype=np.float64)
+        self._w = np.array([j.weight for j in joints], dtype=np.float64)
+        self._circ = np.array([1 if j.circular else 0 for j in joints], dtype=np.uint8)
+        self.ndof = len(self.active)
+        sp = cc_cspace(self.ndof, 0, self._lo.ctypes.data, self._hi.ctypes.data, self._res.ctypes.data, self._w.ctypes.data,
+                       self._circ.ctypes.data)
+        h = ctypes.c_void_p()
+        self._ck(self.lib.cc_planner_create(ctypes.byref(sp), ctypes.byref(h)))
+        self.handle = h
+        self.params = cc_birrt_params(step_length, goal_bias, point_tolerance, max_iterations, path_optimize_iterations,
+                                      smoother_iterations, 100, speculate_steps, 0)
+        self._keep = None
+        if isinstance(checker, tuple):
+            fn, blk = checker
+            self._keep = (fn, blk)
+            self._ck(self.lib.cc_planner_set_checker(h, fn, ctypes.addressof(blk)))
+        else:
+            bq = checker.bind(robot, self.active)
+            self._keep = bq
+            self._ck(self.lib.cc_planner_set_query(h, bq.handle))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("cudacollision planner error %d: %s" % (rc, (self.lib.cc_last_error() or b"").decode()))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.cc_planner_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def EdgeSamples(self, q0, q1, interval=IT_Closed):
+        q0 = np.ascontiguousarray(q0, dtype=np.float64)
+        q1 = np.ascontiguousarray(q1, dtype=np.float64)
+        cnt = ctypes.c_int(0)
+        self._ck(self.lib.cc_planner_edge_samples(self.handle, q0.ctypes.data, q1.ctypes.data, interval, None, 0, ctypes.byref(cnt)))
+        if cnt.value < 0:
+            return None
+        out = np.zeros((max(cnt.value, 1), self.ndof))
+        self._ck(self.lib.cc_planner_edge_samples(self.handle, q0.ctypes.data, q1.ctypes.data, interval, out.ctypes.data,
+                                                  cnt.value, ctypes.byref(cnt)))
+        return out[:cnt.value]
+
+    def PlanBatch(self, starts, goals, seeds=None):
+        """Returns a list of dicts (status, iterations, path [w, ndof], path_raw, lengths, config counts) + totals."""
+        starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, self.ndof)
+        goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, self.ndof)
+        k = starts.shape[0]
+        seeds = np.zeros(k, dtype=np.uint32) if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        res = (cc_plan_result * max(k, 1))()
+        self._ck(self.lib.cc_birrt_plan_batch(self.handle, ctypes.byref(self.params), k, starts.ctypes.data, goals.ctypes.data,
+                                              seeds.ctypes.data, ctypes.addressof(res)))
+        out = []
+        for i in range(k):
+            r = res[i]
+            d = dict((f, getattr(r, f)) for f, _ in cc_plan_result._fields_ if f != "reserved")
+            for which, key in ((0, "path"), (1, "path_raw")):
+                w = ctypes.c_int(0)
+                self._ck(self.lib.cc_planner_get_path(self.handle, i, which, None, 0, ctypes.byref(w)))
+                p = np.zeros((max(w.value, 1), self.ndof))
+                self._ck(self.lib.cc_planner_get_path(self.handle, i, which, p.ctypes.data, w.value, ctypes.byref(w)))
+                d[key] = p[:w.value]
+            out.append(d)
+        tot = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.cc_planner_get_totals(self.handle, tot.ctypes.data))
+        self.totals = dict(rounds=int(tot[0]), checker_calls=int(tot[1]), configs_submitted=int(tot[2]), configs_serial=int(tot[3]))
+        return out
+
+    def PlanPath(self, start, goal, seed=0):
+        return self.PlanBatch([start], [goal], [seed])[0]

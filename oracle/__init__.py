@@ -29,6 +29,13 @@ class OrcOptions(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class OrcGroupChecker(ctypes.Structure):
+    """`user` block of orc_group_check (oracle.cpp): the serial per-sample edge loop behind cc_group_check_fn."""
+    _fields_ = [("scene", ctypes.c_void_p), ("active", ctypes.c_void_p), ("body", ctypes.c_int32), ("nactive", ctypes.c_int32),
+                ("options", ctypes.c_int32), ("reserved", ctypes.c_int32), ("configs_checked", ctypes.c_uint64),
+                ("seconds", ctypes.c_double)]
+
+
 def build(ref=True):
     """Compile the oracle with its Makefile (idempotent).  The reference-linked variant needs
     /root/reference and is skipped silently where that tree does not exist (the GPU box uses the
@@ -231,6 +238,18 @@ class OracleChecker(object):
         secs = self.lib.orc_time_batch(self.scene, bid, _ptr(act), len(active), self._options, flags, _ptr(q),
                                        q.shape[0], _ptr(verdict))
         return secs, verdict
+
+    def group_checker(self, body, active=None):
+        """(function pointer, user block) for cc_planner_set_checker: the reference's serial, early-exit edge loop on this
+        oracle.  Keep the returned block alive while the planner uses it; it accumulates configs_checked / seconds."""
+        self._sync()
+        bid = self._sync_kinematics(body)
+        if active is None:
+            active = body.GetActiveDOFIndices() if body.is_robot else list(range(body.GetDOF()))
+        act = np.array(active, dtype=np.int32)
+        blk = OrcGroupChecker(self.scene, act.ctypes.data, bid, len(act), self._options, 0, 0, 0.0)
+        blk._keep = act
+        return ctypes.cast(self.lib.orc_group_check, ctypes.c_void_p), blk
 
     def scene_handle(self, body):
         self._sync()

@@ -1187,6 +1187,44 @@ double orc_time_batch(void* sp, int body, const int32_t* active, int nactive, in
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// The serial per-sample loop of DynamicsCollisionConstraint::Check (src/libopenrave/planningutils.cpp:3405-3454,
+// _SetAndCheckState :2317-2368) behind the planner library's cc_group_check_fn signature: every group is walked segment
+// by segment, configuration by configuration, in the given order, and abandoned at its first colliding configuration —
+// exactly what the reference's planners pay for an edge.  `user` points at an OrcGroupChecker.
+struct OrcGroupChecker {
+    void* scene;
+    const int32_t* active;
+    int32_t body, nactive, options, reserved;
+    uint64_t configs_checked;     // accumulated over calls
+    double seconds;               // accumulated over calls
+};
+
+int orc_group_check(void* user, const double* q, int nconfigs, int ndof, const int32_t* group_begin, int ngroups,
+                    const int32_t* segment_begin, int nsegments, int32_t* first_fail_segment, int32_t* fail_verdict,
+                    int32_t* first_fail_config)
+{
+    OrcGroupChecker* u = (OrcGroupChecker*)user;
+    (void)nconfigs; (void)nsegments;
+    if (ndof != u->nactive) return 1;
+    OrcOptions o; memset(&o, 0, sizeof(o));
+    o.options = u->options; o.flags = CC_BATCH_ENV | CC_BATCH_SELF;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < ngroups; ++g) {
+        first_fail_segment[g] = -1; fail_verdict[g] = 0; first_fail_config[g] = -1;
+        for (int sgm = group_begin[g]; sgm < group_begin[g + 1] && first_fail_segment[g] < 0; ++sgm) {
+            for (int c = segment_begin[sgm]; c < segment_begin[sgm + 1]; ++c) {
+                uint32_t v = 0;
+                orc_check_batch(u->scene, u->body, u->active, u->nactive, &o, q + (size_t)c * ndof, 1, &v, NULL, NULL, NULL, NULL, NULL,
+                                NULL, 0, NULL, NULL);
+                u->configs_checked++;
+                if (v) { first_fail_segment[g] = sgm - group_begin[g]; fail_verdict[g] = (int32_t)v; first_fail_config[g] = c; break; }
+            }
+        }
+    }
+    u->seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
 // Raw model-vs-model query for pinning the restatement against the reference build:
 // returns contacts; fills counters {bv, tri}; optional sorted contact list as id pairs.
 int64_t orc_collide_pair(void* sp, int body1, int link1, const double* T1_8, int body2, int link2, const double* T2_8,

@@ -1,0 +1,148 @@
+"""BiRRT + linear shortcutting on the batched entry (csrc/cc_planner.cpp) — BASELINE.json configs[2], SURVEY.md §8 f2.
+
+The reference planner (plugins/rplanners/rrt.h:279-659, rplanners.h:308-460, linearsmoother.cpp) checks one configuration at
+a time.  The library plans with whole Extend rays / shortcuts per checker call and many problems in lockstep; these tests
+pin that restructuring: (CPU) with the oracle's serial early-exit loop plugged in as the checker, plans are valid,
+deterministic, and independent of batching (lockstep width, ray chunking); (GPU) the CUDA checker produces the same plans as
+the oracle's serial loop, waypoint for waypoint."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_scene, sample_configs
+from openrave_b200 import planning as pl
+from test_edge_check import OracleBatchAdapter
+
+
+def _world(scene):
+    env = load_scene(scene)
+    robot = env.GetRobots()[0]
+    robot.SetActiveDOFs(robot.GetActiveManipulator().GetArmIndices())
+    orc = oracle.OracleChecker(env, "port")
+    env.SetCollisionChecker(orc)
+    return env, robot, orc
+
+
+def _free_pairs(robot, orc, k, seed):
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 6 * k + 20, seed=seed, active=act)
+    free = q[orc.check_batch(robot, q, active=act)["verdict"] == 0]
+    assert len(free) >= 2 * k
+    return free[0:2 * k:2].copy(), free[1:2 * k:2].copy()
+
+
+@pytest.fixture(scope="module")
+def wamtest1():
+    return _world("wamtest1")
+
+
+def test_edge_samples_equal_python_restatement(wamtest1):
+    env, robot, orc = wamtest1
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    c = pl.DynamicsCollisionConstraint(robot, None)
+    q = sample_configs(robot, 40, seed=11, active=robot.GetActiveDOFIndices())
+    for k in range(0, 40, 2):
+        q1 = q[k] + 0.3 * (q[k + 1] - q[k])
+        for interval in (pl.IT_Open, pl.IT_OpenStart, pl.IT_OpenEnd, pl.IT_Closed):
+            a = P.EdgeSamples(q[k], q1, interval)
+            b, _, _ = c.edge_samples(q[k], q1, interval)
+            assert a.shape == b.shape and np.array_equal(a, b)
+    assert len(P.EdgeSamples(q[0], q[0], pl.IT_Open)) == 0
+    assert len(P.EdgeSamples(q[0], q[0], pl.IT_OpenStart)) == 1
+
+
+def test_plans_are_valid_and_deterministic(wamtest1):
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 8, seed=3)
+    fn, blk = orc.group_checker(robot)
+    P = pl.BirrtPlanner(robot, (fn, blk))
+    res = P.PlanBatch(starts, goals, seeds=np.arange(8))
+    assert blk.configs_checked == P.totals["configs_serial"]        # the serial loop stops exactly where the count says
+    assert P.totals["configs_submitted"] >= P.totals["configs_serial"]
+    cons = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    nsmoothed = 0
+    for r, s, g in zip(res, starts, goals):
+        assert r["status"] == pl.PLAN_SOLVED
+        for key in ("path", "path_raw"):
+            p = r[key]
+            assert np.array_equal(p[0], s) and np.array_equal(p[-1], g)
+            assert (p >= cons.lower - 1e-12).all() and (p <= cons.upper + 1e-12).all()
+        p = r["path"]
+        assert r["length"] <= r["length_raw"] + 1e-9
+        nsmoothed += r["length"] < r["length_raw"] - 1e-6
+        # every waypoint and every edge between waypoints is collision free at the joint resolutions
+        assert not orc.check_batch(robot, p)["verdict"].any()
+        edges = [(p[i], p[i + 1]) for i in range(len(p) - 1)]
+        assert not any(cons.CheckMany(edges, pl.IT_Open, options=0xffff))
+    assert nsmoothed >= 1
+    again = P.PlanBatch(starts, goals, seeds=np.arange(8))
+    for a, b in zip(res, again):
+        assert np.array_equal(a["path"], b["path"]) and a["iterations"] == b["iterations"]
+    other = P.PlanBatch(starts[:2], goals[:2], seeds=[100, 101])
+    assert any(o["iterations"] != r["iterations"] or not np.array_equal(o["path_raw"], r["path_raw"]) for o, r in zip(other, res))
+
+
+def test_lockstep_and_ray_chunking_do_not_change_plans(wamtest1):
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 6, seed=5)
+    seeds = np.arange(6) + 40
+    ref = pl.BirrtPlanner(robot, orc.group_checker(robot)).PlanBatch(starts, goals, seeds)
+    solo = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    for k in range(6):
+        r = solo.PlanPath(starts[k], goals[k], int(seeds[k]))
+        assert np.array_equal(r["path"], ref[k]["path"]) and r["configs_serial"] == ref[k]["configs_serial"]
+    chunked = pl.BirrtPlanner(robot, orc.group_checker(robot), speculate_steps=7)
+    got = chunked.PlanBatch(starts, goals, seeds)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a["path"], b["path"]) and np.array_equal(a["path_raw"], b["path_raw"])
+        assert a["configs_serial"] == b["configs_serial"] and a["configs_submitted"] <= b["configs_submitted"]
+        assert a["rounds"] >= b["rounds"]
+
+
+def test_colliding_endpoints_are_refused(wamtest1):
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 200, seed=9, active=act)
+    v = orc.check_batch(robot, q, active=act)["verdict"]
+    bad, good = q[v != 0][0], q[v == 0]
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    res = P.PlanBatch([bad, good[0], good[1]], [good[2], bad, good[3]], seeds=[1, 2, 3])
+    assert [r["status"] for r in res] == [pl.PLAN_BAD_INITIAL, pl.PLAN_BAD_GOAL, pl.PLAN_SOLVED]
+    assert len(res[0]["path"]) == 0
+
+
+def test_iteration_budget_is_respected():
+    """Segway-mounted WAM in lab1 with a tiny iteration budget: unsolved problems report CC_PLAN_FAILED, never a path."""
+    env, robot, orc = _world("lab1")
+    starts, goals = _free_pairs(robot, orc, 6, seed=21)
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot), max_iterations=1, smoother_iterations=0)
+    res = P.PlanBatch(starts, goals, seeds=np.arange(6))
+    for r in res:
+        assert r["status"] in (pl.PLAN_SOLVED, pl.PLAN_FAILED)
+        assert (len(r["path"]) > 0) == (r["status"] == pl.PLAN_SOLVED)
+        assert r["iterations"] <= 3
+
+
+@pytest.mark.gpu
+def test_gpu_plans_equal_oracle_serial_plans(wamtest1):
+    from openrave_b200.checker import CudaCollisionChecker
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 24, seed=3)
+    seeds = np.arange(24)
+    cpu = pl.BirrtPlanner(robot, orc.group_checker(robot)).PlanBatch(starts, goals, seeds)
+    env2 = load_scene("wamtest1")
+    robot2 = env2.GetRobots()[0]
+    robot2.SetActiveDOFs(robot2.GetActiveManipulator().GetArmIndices())
+    cc = CudaCollisionChecker(env2, 0)
+    env2.SetCollisionChecker(cc)
+    launches0 = cc.GetStatistics()["launches"]
+    P = pl.BirrtPlanner(robot2, cc)
+    gpu = P.PlanBatch(starts, goals, seeds)
+    assert cc.GetStatistics()["launches"] > launches0                # the verdicts came from the CUDA kernels
+    same = sum(1 for a, b in zip(cpu, gpu) if a["status"] == b["status"] and np.array_equal(a["path"], b["path"])
+               and a["configs_serial"] == b["configs_serial"])
+    # a plan can only differ where some sample sat inside the 1e-4 m contact band
+    assert same >= 23, same
+    assert all(r["status"] == pl.PLAN_SOLVED for r in gpu)
+    for r in gpu:
+        assert not orc.check_batch(robot, r["path"])["verdict"].any()
