@@ -129,6 +129,21 @@ int cc_body_set_link_transforms(cc_scene* s, int body, const double* transforms8
 /* KinBody::IsAttached (grabbed / attached bodies are never checked against each other) */
 int cc_body_set_attached(cc_scene* s, int body_a, int body_b, int attached);
 
+/* KinBody::Grab / Release / ReleaseAllGrabbed (src/libopenrave/kinbodygrab.cpp).  From now on the links of `grabbed_body`
+ * ride on `link` of `body`: T(grabbed link k) = T(link) * rel_transforms8[k] (KinBody::_UpdateGrabbedBodies), in queries
+ * bound on `body` AFTER this call:
+ *   - they are query links too: cc_query_info.nlinks counts them after the body's own links, cc_check_poses / cc_fk_batch
+ *     rows carry them, cc_query_get_links names them;
+ *   - env pairs: the grabbed body's links against every non-attached body (collisionPQP.h:314-329 walks all attached bodies);
+ *   - self pairs (KinBody::CheckSelfCollision, kinbodycollision.cpp:83-205): every link listed in `noncolliding_links`
+ *     ((body, link) pairs: Grabbed::_listNonCollidingLinksWhenGrabbed, i.e. links of `body` and of its other grabbed bodies
+ *     that did not touch the grabbed body at grab time) x the grabbed body's links, the grabbed body's own non-adjacent
+ *     pairs, and grabbed-vs-grabbed pairs.
+ * Also marks the two bodies attached.  cc_body_release_grabbed with grabbed_body < 0 releases everything. */
+int cc_body_set_grabbed(cc_scene* s, int body, int grabbed_body, int link, const double* rel_transforms8,
+                        const int32_t* noncolliding_links, int n_noncolliding);
+int cc_body_release_grabbed(cc_scene* s, int body, int grabbed_body);
+
 /* ---- kinematics of a body, read off a computed KinBody (used by the batched entry only) */
 int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints_in_fk_order,
                            const uint8_t* dof_affects_link /* [ndof][nlinks], KinBody::DoesAffect != 0 */);
@@ -154,6 +169,8 @@ int cc_query_destroy(cc_query* q);
 int cc_query_get_info(const cc_query* q, cc_query_info* info);
 /* pair index -> {query link, other body, other link, 0=env|1=self}, [npairs][4] */
 int cc_query_get_pairs(const cc_query* q, int32_t* out_quads);
+/* query link index -> {body, link}, [nlinks][2]: the body's own links first, then the links of its grabbed bodies */
+int cc_query_get_links(const cc_query* q, int32_t* out_pairs);
 
 /* ---- the batched entry (new; SURVEY.md §8b "Batched entry").  q is row-major [n][ndof_active] doubles of
  * ACTIVE DOF values (RobotBase::SetActiveDOFValues semantics, robot.cpp:1193-1225); the other DOFs keep

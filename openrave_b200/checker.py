@@ -48,7 +48,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_scene_commit", "cc_query_create", "cc_query_create_pairs", "cc_query_destroy", "cc_query_get_info",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
-           "cc_host_alloc", "cc_host_free"]
+           "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links"]
 
 _lib = None
 
@@ -72,6 +72,9 @@ def load_library():
     lib.cc_body_set_link_transforms.argtypes = [vp, ci, vp]
     lib.cc_body_set_attached.argtypes = [vp, ci, ci, ci]
     lib.cc_body_set_kinematics.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.cc_body_set_grabbed.argtypes = [vp, ci, ci, ci, vp, vp, ci]
+    lib.cc_body_release_grabbed.argtypes = [vp, ci, ci]
+    lib.cc_query_get_links.argtypes = [vp, vp]
     lib.cc_body_set_dof_values.argtypes = [vp, ci, vp, ci]
     lib.cc_body_set_nonadjacent_pairs.argtypes = [vp, ci, vp, ci]
     lib.cc_scene_commit.argtypes = [vp]
@@ -139,6 +142,16 @@ class BoundQuery(object):
         self.pairs = np.zeros((max(self.npairs, 1), 4), dtype=np.int32)
         checker._ck(self.lib.cc_query_get_pairs(handle, _ptr(self.pairs)))
         self.pairs = self.pairs[:self.npairs]
+        # query link index -> (body id, link): the body's own links, then its grabbed bodies' links
+        self.links = np.zeros((max(info.nlinks, 1), 2), dtype=np.int32)
+        checker._ck(self.lib.cc_query_get_links(handle, _ptr(self.links)))
+        self.links = self.links[:info.nlinks]
+        self.nlinks_body = len(body.links)
+
+    def link_of(self, qindex):
+        """Query link index -> Link object (a grabbed body's link when qindex >= the body's link count)."""
+        b, l = self.links[qindex]
+        return self.checker.body_from_id(int(b)).links[int(l)]
 
     def close(self):
         if self.handle:
@@ -229,6 +242,7 @@ class CudaCollisionChecker(object):
         self._options = 0
         self._queries = {}
         self._epoch = 0
+        self._grab_epochs = {}
         self._create_scene()
 
     # ---- plumbing
@@ -269,6 +283,7 @@ class CudaCollisionChecker(object):
             self.scene = None
         self._create_scene()
         self._ids, self._bodies, self._dirty, self._kin_dirty = {}, {}, set(), set()
+        self._grab_epochs = {}
         for b in self.env.GetBodies():
             self.InitKinBody(b)
         return True
@@ -334,6 +349,14 @@ class CudaCollisionChecker(object):
                     cur = np.array(b.GetDOFValues(), dtype=np.float64)
                     self._ck(self.lib.cc_body_set_dof_values(self.scene, bid, _ptr(cur), b.GetDOF()))
         self._dirty.clear()
+        for b in self.env.GetBodies():
+            ep = getattr(b, "grab_epoch", 0)
+            if self._grab_epochs.get(id(b), 0) != ep:
+                bid = self._ids[id(b)]
+                self._ck(self.lib.cc_body_release_grabbed(self.scene, bid, -1))
+                for gid, link, rel, nc in flatten.grab_tables(b, lambda k: self._ids[id(k)]):
+                    self._ck(self.lib.cc_body_set_grabbed(self.scene, bid, gid, link, _ptr(rel), _ptr(nc) if len(nc) else None, len(nc)))
+                self._grab_epochs[id(b)] = ep
         self._ck(self.lib.cc_scene_commit(self.scene))
 
     def _sync_kinematics(self, body, need_pairs=True):
@@ -357,6 +380,9 @@ class CudaCollisionChecker(object):
         """cc_query_create for (body, active DOFs, options); cached until the scene changes."""
         self._sync()
         bid = self._sync_kinematics(body)
+        for g in getattr(body, "grabbed", []):          # grabbedBody.CheckSelfCollision needs its non-adjacent list
+            if len(g.body.links) > 1:
+                self._sync_kinematics(g.body)
         opts = self._options if options is None else options
         if active is None and body.is_robot and body.active_dofs is not None:
             active = body.GetActiveDOFIndices()
@@ -435,7 +461,7 @@ class CudaCollisionChecker(object):
             report.Reset(self._options)
         if isinstance(a, KinBody) and b is None:
             bq = self.bind(a)
-            T = flatten.transforms8(a.GetLinkTransformations())[None]
+            T = flatten.transforms8(a.GetQueryLinkTransformations())[None]
             want_all = report is not None
             verdict, fe, _, mask = bq.check_poses(T, BATCH_ENV | (BATCH_ALL_PAIRS if want_all else 0), want_mask=want_all)
             hit = bool(verdict[0] & 1)
@@ -443,7 +469,7 @@ class CudaCollisionChecker(object):
                 for p in range(bq.info.npairs_env):
                     if (mask[0, p >> 5] >> (p & 31)) & 1:
                         l1, ob, l2, _ = bq.pairs[p]
-                        report.AddLinkCollision(a.links[l1], self._bodies[ob].links[l2])
+                        report.AddLinkCollision(bq.link_of(l1), self._bodies[ob].links[l2])
                 report.minDistance = 0
             return hit
         if isinstance(a, KinBody) and isinstance(b, KinBody):
@@ -495,13 +521,17 @@ class CudaCollisionChecker(object):
         if report is not None:
             report.Reset(self._options)
         bq = self.bind(body)
-        T = flatten.transforms8(body.GetLinkTransformations())[None]
+        T = flatten.transforms8(body.GetQueryLinkTransformations())[None]
         verdict, _, fs, _ = bq.check_poses(T, BATCH_SELF)
-        hit = bool(verdict[0] & 2)
-        if hit and report is not None:
+        # the body's own non-adjacent pairs come first in the pair order: a first hit among them is the standalone verdict
+        # (pairs that involve grabbed links belong to KinBody::CheckSelfCollision, not to this call)
+        hit = False
+        if verdict[0] & 2:
             l0, l1 = bq.decode_self(fs)[0]
-            report.AddLinkCollision(body.links[l0], body.links[l1])
-            report.minDistance = 0
+            hit = l0 < bq.nlinks_body and l1 < bq.nlinks_body
+            if hit and report is not None:
+                report.AddLinkCollision(body.links[l0], body.links[l1])
+                report.minDistance = 0
         return hit
 
 

@@ -64,6 +64,13 @@ struct HBody {
     std::vector<uint8_t> affects;      // [ndof][nlinks]
     std::vector<double> dofvals;
     std::vector<int32_t> nonadjacent;
+    // KinBody::_vGrabbedBodies in grab order (kinbodygrab.cpp): the grabbed body's links ride on `link` of this body
+    struct Grab {
+        int body = -1, link = -1;
+        std::vector<double> rel;            // [links of the grabbed body][8], pose of each relative to the grabbing link
+        std::vector<int32_t> noncolliding;  // (body, link) pairs: Grabbed::_listNonCollidingLinksWhenGrabbed
+    };
+    std::vector<Grab> grabs;
 };
 
 const float kBoxInflate = 1e-5f;   // metres added to every half extent (conservative pruning, see cc_device.cuh)
@@ -252,7 +259,11 @@ bool body_attached(const HBody& a, int other)
 struct cc_query {
     cc_scene* scene = nullptr;
     int body = -1;
-    int nq = 0, ncols = 0, nslots = 0;
+    int nq = 0, ncols = 0, nslots = 0;     // nq: query links = the body's links, then the links of every grabbed body
+    std::vector<int> ql_body, ql_link;       // [nq] which (body, link) a query link is
+    std::vector<int> ql_host;                // [nq] the body link whose motion it follows (itself for the body's own links)
+    std::vector<int> ql_grab;                // [nq] index into HBody::grabs, -1 for the body's own links
+    const HLink& qlink(int l) const;
     std::vector<int32_t> quads;              // [npairs][4] {query link, other body, other link, class}
     std::vector<int32_t> pair_slot;          // [npairs] slot of the other link
     std::vector<uint8_t> pair_live;          // [npairs] 0: can never collide (disabled / no mesh), kept for indexing only
@@ -279,6 +290,8 @@ struct cc_query {
     DevBuf<uint32_t> d_verdict, d_mask;
     DevBuf<int32_t> d_fe, d_fs;
 };
+
+const HLink& cc_query::qlink(int l) const { return scene->bodies[ql_body[l]]->links[ql_link[l]]; }
 
 namespace {
 
@@ -591,6 +604,39 @@ int cc_body_set_attached(cc_scene* s, int a, int bb, int attached)
     return CC_OK;
 }
 
+int cc_body_set_grabbed(cc_scene* s, int body, int grabbed_body, int link, const double* rel8, const int32_t* noncolliding,
+                        int n_noncolliding)
+{
+    HBody* B = get_body(s, body); HBody* G = get_body(s, grabbed_body);
+    if (!B || !G || body == grabbed_body || link < 0 || link >= (int)B->links.size() || !rel8 || n_noncolliding < 0 ||
+        (n_noncolliding > 0 && !noncolliding))
+        return fail(CC_ERR_INVALID, "bad arguments");
+    for (int k = 0; k < n_noncolliding; ++k) {
+        HBody* O = get_body(s, noncolliding[2 * k]);
+        if (!O || noncolliding[2 * k + 1] < 0 || noncolliding[2 * k + 1] >= (int)O->links.size()) return fail(CC_ERR_INVALID, "bad non-colliding link");
+    }
+    HBody::Grab* g = nullptr;
+    for (HBody::Grab& x : B->grabs) if (x.body == grabbed_body) g = &x;
+    if (!g) { B->grabs.push_back(HBody::Grab()); g = &B->grabs.back(); }
+    g->body = grabbed_body; g->link = link;
+    g->rel.assign(rel8, rel8 + 8 * G->links.size());
+    g->noncolliding.assign(noncolliding, noncolliding + 2 * (size_t)n_noncolliding);
+    return cc_body_set_attached(s, body, grabbed_body, 1);
+}
+
+int cc_body_release_grabbed(cc_scene* s, int body, int grabbed_body)
+{
+    HBody* B = get_body(s, body);
+    if (!B) return fail(CC_ERR_INVALID, "bad body");
+    for (size_t i = 0; i < B->grabs.size();) {
+        if (grabbed_body < 0 || B->grabs[i].body == grabbed_body) {
+            if (get_body(s, B->grabs[i].body)) cc_body_set_attached(s, body, B->grabs[i].body, 0);
+            B->grabs.erase(B->grabs.begin() + i);
+        } else ++i;
+    }
+    return CC_OK;
+}
+
 int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints, const uint8_t* affects)
 {
     HBody* b = get_body(s, body);
@@ -711,9 +757,9 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
     std::vector<int> sa_v, sb_v;
     for (int p : plist) {
         const int a = Q->quads[4 * p], ob = Q->quads[4 * p + 1], j = Q->quads[4 * p + 2], cls = Q->quads[4 * p + 3];
-        const int sa = pl.emit[a] >= 0 ? pl.emit[a] : -1 - static_slot(Q->body, a);
+        const int sa = pl.emit[a] >= 0 ? pl.emit[a] : -1 - static_slot(Q->ql_body[a], Q->ql_link[a]);
         int sb;
-        if (cls == 1) sb = pl.emit[j] >= 0 ? pl.emit[j] : -1 - static_slot(Q->body, j);
+        if (cls == 1) sb = pl.emit[j] >= 0 ? pl.emit[j] : -1 - static_slot(Q->ql_body[j], Q->ql_link[j]);
         else sb = -1 - static_slot(ob, j);
         sa_v.push_back(sa); sb_v.push_back(sb);
         pl.orig.push_back(p);
@@ -731,7 +777,7 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         staabb((size_t)std::max(1, pl.nstatic) * 8, 0.f);
     for (int l = 0; l < nl; ++l) {
         if (pl.emit[l] < 0) continue;
-        const HLink& L = B->links[l];
+        const HLink& L = Q->qlink(l);
         roots[pl.emit[l]] = L.node_base < 0 ? 0 : L.node_base;
         float* o = &linkbox[(size_t)pl.emit[l] * 8];
         if (!L.nodes.empty()) { for (int k = 0; k < 3; ++k) { o[k] = L.nodes[0].c[k]; o[3 + k] = L.nodes[0].e[k]; } o[6] = 1.0f; }
@@ -782,6 +828,19 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     cc_scene* S = Q->scene;
     HBody* B = S->bodies[Q->body];
     const int nl = Q->nq;
+    const int nlb = (int)B->links.size();
+    // the joint list of the query: the body's joints, then one static joint per grabbed link hanging off its grabbing link
+    // (KinBody::_UpdateGrabbedBodies: T(grabbed link) = T(grabbing link) * relative pose)
+    std::vector<cc_joint> joints(B->joints);
+    for (int l = nlb; l < nl; ++l) {
+        const HBody::Grab& g = B->grabs[Q->ql_grab[l]];
+        cc_joint j;
+        memset(&j, 0, sizeof(j));
+        j.type = CC_JOINT_REVOLUTE; j.parent_link = g.link; j.child_link = l; j.dof_index = -1; j.mimic_dof = -1; j.is_static = 1;
+        memcpy(j.left, &g.rel[8 * (size_t)Q->ql_link[l]], 8 * sizeof(double));
+        j.right[0] = 1.0;
+        joints.push_back(j);
+    }
     // ---- which links move with the active DOFs
     std::vector<int> col_of_dof(B->ndof, -1);
     std::vector<int> act;
@@ -794,7 +853,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     Q->ncols = (int)act.size();
     Q->cur_active.resize(act.size());
     for (size_t c = 0; c < act.size(); ++c) Q->cur_active[c] = B->dofvals[act[c]];
-    auto affects = [&](int d, int l) { return B->affects[(size_t)d * nl + l] != 0; };
+    auto affects = [&](int d, int l) { return B->affects[(size_t)d * nlb + Q->ql_host[l]] != 0; };
     std::vector<uint8_t> moves(nl, 0);
     for (int l = 0; l < nl; ++l)
         for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
@@ -802,12 +861,12 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     // ---- FK chain program
     Q->has_fk = true;
     Q->steps.clear();
-    if (!B->joints.empty()) {
+    if (!joints.empty()) {
         std::vector<int> depth(nl, -1);
         depth[0] = 0;
-        std::vector<int> sdepth(B->joints.size(), 0);
-        for (size_t k = 0; k < B->joints.size(); ++k) {
-            const cc_joint& j = B->joints[k];
+        std::vector<int> sdepth(joints.size(), 0);
+        for (size_t k = 0; k < joints.size(); ++k) {
+            const cc_joint& j = joints[k];
             if (depth[j.parent_link] < 0) return fail(CC_ERR_INVALID, "joints are not listed parent-before-child from link 0");
             if (depth[j.child_link] >= 0) return fail(CC_ERR_UNSUPPORTED, "closed kinematic loops are not supported");
             depth[j.child_link] = depth[j.parent_link] + 1;
@@ -816,7 +875,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
         // depth-first order (children in listed order): a child usually follows its parent, so the device keeps the
         // running transform in registers and parks only the poses later branches start from
         std::vector<std::vector<int>> kids(nl);
-        for (size_t k = 0; k < B->joints.size(); ++k) kids[B->joints[k].parent_link].push_back((int)k);
+        for (size_t k = 0; k < joints.size(); ++k) kids[joints[k].parent_link].push_back((int)k);
         std::vector<int> ord;
         {
             std::vector<std::pair<int, size_t>> stk;     // (link, next child position)
@@ -826,12 +885,12 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
                 if (top.second >= kids[top.first].size()) { stk.pop_back(); continue; }
                 const int k = kids[top.first][top.second++];
                 ord.push_back(k);
-                stk.push_back(std::make_pair(B->joints[k].child_link, (size_t)0));
+                stk.push_back(std::make_pair(joints[k].child_link, (size_t)0));
             }
         }
-        if (ord.size() != B->joints.size()) return fail(CC_ERR_INVALID, "joint tree is not connected to link 0");
+        if (ord.size() != joints.size()) return fail(CC_ERR_INVALID, "joint tree is not connected to link 0");
         for (int k : ord) {
-            const cc_joint& j = B->joints[k];
+            const cc_joint& j = joints[k];
             ccdev::FkStep st;
             memset(&st, 0, sizeof(st));
             st.type = j.type; st.parent = j.parent_link; st.child = j.child_link;
@@ -844,7 +903,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
             if (j.mimic_dof >= 0) {
                 // limits of the DOF the equation reads
                 bool found = false;
-                for (const cc_joint& o : B->joints)
+                for (const cc_joint& o : joints)
                     if (o.dof_index == j.mimic_dof) { st.src_lower = o.lower; st.src_upper = o.upper; src_circ = o.is_circular != 0; found = true; break; }
                 if (!found) return fail(CC_ERR_INVALID, "mimic source DOF has no joint");
             } else if (srcdof < 0) {
@@ -857,10 +916,10 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
             Q->steps.push_back(st);
         }
         for (int l = 1; l < nl; ++l)
-            if (depth[l] < 0 && B->links[l].ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
+            if (depth[l] < 0 && Q->qlink(l).ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
     } else {
         for (int l = 1; l < nl; ++l)
-            if (B->links[l].ntris() > 0) Q->has_fk = false;
+            if (Q->qlink(l).ntris() > 0) Q->has_fk = false;
     }
     memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
     Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
@@ -927,60 +986,122 @@ int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nacti
     HBody* B = get_body(s, body);
     if (!B || !out || nactive < 0 || (nactive > 0 && !active_dofs)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!s->committed) return fail(CC_ERR_STATE, "cc_scene_commit has not been called since the last mesh change");
-    const int nl = (int)B->links.size();
+    const int nlb = (int)B->links.size();
     const bool all_active = active_dofs == nullptr;
     std::vector<int> act;
     if (all_active) for (int d = 0; d < B->ndof; ++d) act.push_back(d);
     else act.assign(active_dofs, active_dofs + nactive);
     for (int d : act) if (d < 0 || d >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
-    // _IsActiveLink (collisionPQP.h:710-735)
+    cc_query* Q = new cc_query();
+    Q->scene = s; Q->body = body;
+    // query links: the body's own, then every grabbed body's in grab order
+    for (int l = 0; l < nlb; ++l) { Q->ql_body.push_back(body); Q->ql_link.push_back(l); Q->ql_host.push_back(l); Q->ql_grab.push_back(-1); }
+    std::vector<int> grab_base(B->grabs.size(), 0);
+    for (size_t g = 0; g < B->grabs.size(); ++g) {
+        HBody* G = get_body(s, B->grabs[g].body);
+        if (!G || B->grabs[g].rel.size() != 8 * G->links.size()) { delete Q; return fail(CC_ERR_STATE, "grabbed body changed since cc_body_set_grabbed"); }
+        grab_base[g] = (int)Q->ql_body.size();
+        for (int l = 0; l < (int)G->links.size(); ++l) {
+            Q->ql_body.push_back(B->grabs[g].body); Q->ql_link.push_back(l); Q->ql_host.push_back(B->grabs[g].link); Q->ql_grab.push_back((int)g);
+        }
+    }
+    const int nl = (int)Q->ql_body.size();
+    Q->nq = nl;
+    if (nl > 0xffff) { delete Q; return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots"); }
+    auto query_index = [&](int b, int l) -> int {       // (body, link) -> query link index, -1 if it is not one
+        if (b == body) return l < nlb ? l : -1;
+        for (size_t g = 0; g < B->grabs.size(); ++g)
+            if (B->grabs[g].body == b) return l < (int)s->bodies[b]->links.size() ? grab_base[g] + l : -1;
+        return -1;
+    };
+    // _IsActiveLink (collisionPQP.h:710-735): only links of the active robot itself are filtered, grabbed links never
     std::vector<uint8_t> active_link(nl, 1);
     const bool filter = (options & CC_CO_ActiveDOFs) && B->is_robot;
     if (filter) {
-        for (int l = 0; l < nl; ++l) {
+        for (int l = 0; l < nlb; ++l) {
             active_link[l] = 0;
-            for (int d : act) if (B->affects[(size_t)d * nl + l]) { active_link[l] = 1; break; }
+            for (int d : act) if (B->affects[(size_t)d * nlb + l]) { active_link[l] = 1; break; }
         }
     }
-    cc_query* Q = new cc_query();
-    Q->scene = s; Q->body = body; Q->nq = nl;
-    std::vector<int> slot_body(nl, body), slot_link(nl);
-    for (int l = 0; l < nl; ++l) slot_link[l] = l;
-    // env pairs: other bodies in environment order x query link x other link (collisionPQP.h:448-487)
-    for (int ob = 0; ob < (int)s->bodies.size(); ++ob) {
-        HBody* O = s->bodies[ob];
-        if (O->removed || body_attached(*B, ob)) continue;
-        std::vector<int> oslot(O->links.size(), -1);
-        for (int i = 0; i < nl; ++i) {
-            if (!B->links[i].enabled || !active_link[i] || B->links[i].ntris() == 0) continue;
-            for (int j = 0; j < (int)O->links.size(); ++j) {
-                if (!O->links[j].enabled || O->links[j].ntris() == 0) continue;
-                if (oslot[j] < 0) { oslot[j] = (int)slot_body.size(); slot_body.push_back(ob); slot_link.push_back(j); }
-                Q->quads.insert(Q->quads.end(), {i, ob, j, 0});
-                Q->pair_slot.push_back(oslot[j]);
-                Q->pair_live.push_back(1);
+    auto in_attached_set = [&](int ob) {                 // KinBody::GetAttached is transitive: the body, its attachments, its grabs
+        if (body_attached(*B, ob)) return true;
+        for (const HBody::Grab& g : B->grabs) if (g.body == ob || body_attached(*s->bodies[g.body], ob)) return true;
+        return false;
+    };
+    // env pairs: every attached body (the query body first, then its grabbed bodies in grab order; the reference walks a
+    // pointer-ordered std::set, collisionPQP.h:314-329) x other bodies in environment order x its link x other link
+    // (collisionPQP.h:448-487)
+    for (int att = -1; att < (int)B->grabs.size(); ++att) {
+        const int qb = att < 0 ? body : B->grabs[att].body;
+        const int q0 = att < 0 ? 0 : grab_base[att];
+        const HBody* QB = s->bodies[qb];
+        for (int ob = 0; ob < (int)s->bodies.size(); ++ob) {
+            HBody* O = s->bodies[ob];
+            if (O->removed || in_attached_set(ob)) continue;
+            for (int i = 0; i < (int)QB->links.size(); ++i) {
+                if (!QB->links[i].enabled || !active_link[q0 + i] || QB->links[i].ntris() == 0) continue;
+                for (int j = 0; j < (int)O->links.size(); ++j) {
+                    if (!O->links[j].enabled || O->links[j].ntris() == 0) continue;
+                    Q->quads.insert(Q->quads.end(), {q0 + i, ob, j, 0});
+                    Q->pair_slot.push_back(0);
+                    Q->pair_live.push_back(1);
+                }
             }
         }
     }
     Q->nenv_total = (int)Q->quads.size() / 4;
+    auto add_self = [&](int a, int b) {
+        const HLink& La = Q->qlink(a); const HLink& Lb = Q->qlink(b);
+        if (!La.enabled || !Lb.enabled || La.ntris() == 0 || Lb.ntris() == 0) return;
+        if (!active_link[a] || !active_link[b]) return;              // DoPQP's _IsActiveLink on both links
+        Q->quads.insert(Q->quads.end(), {a, body, b, 1});
+        Q->pair_slot.push_back(b);
+        Q->pair_live.push_back(1);
+    };
     // self pairs: non-adjacent list, AO_Enabled [| AO_ActiveDOFs] (collisionPQP.h:364-386, robot.cpp:2023-2084)
     for (int32_t pk : B->nonadjacent) {
         int l0 = pk & 0xffff, l1 = (pk >> 16) & 0xffff;
-        if (!B->links[l0].enabled || !B->links[l1].enabled) continue;
         if (filter) {
             bool any = false;
             for (int d : act)
-                if ((B->affects[(size_t)d * nl + l0] != 0) != (B->affects[(size_t)d * nl + l1] != 0)) { any = true; break; }
+                if ((B->affects[(size_t)d * nlb + l0] != 0) != (B->affects[(size_t)d * nlb + l1] != 0)) { any = true; break; }
             if (!any) continue;
-            if (!active_link[l0] || !active_link[l1]) continue;      // DoPQP's _IsActiveLink on both links
         }
-        if (B->links[l0].ntris() == 0 || B->links[l1].ntris() == 0) continue;
-        Q->quads.insert(Q->quads.end(), {l0, body, l1, 1});
-        Q->pair_slot.push_back(l1);
-        Q->pair_live.push_back(1);
+        add_self(l0, l1);
+    }
+    // grabbed bodies (KinBody::CheckSelfCollision, kinbodycollision.cpp:83-205): per grabbed body, in grab order,
+    //   its non-colliding links x its own links, its own non-adjacent pairs, then the later grabbed bodies link by link
+    auto listed = [&](const HBody::Grab& g, int b, int l) {
+        for (size_t k = 0; k + 1 < g.noncolliding.size(); k += 2) if (g.noncolliding[k] == b && g.noncolliding[k + 1] == l) return true;
+        return false;
+    };
+    for (size_t g1 = 0; g1 < B->grabs.size(); ++g1) {
+        const HBody::Grab& G1 = B->grabs[g1];
+        const HBody* GB1 = s->bodies[G1.body];
+        bool any_enabled = false;
+        for (const HLink& L : GB1->links) any_enabled |= L.enabled;
+        if (!any_enabled) continue;                                  // grabbedBody1.IsEnabled()
+        for (size_t k = 0; k + 1 < G1.noncolliding.size(); k += 2) {
+            const int a = query_index(G1.noncolliding[k], G1.noncolliding[k + 1]);
+            if (a < 0) continue;                                     // a link of a body that is no longer grabbed
+            for (int l = 0; l < (int)GB1->links.size(); ++l) add_self(a, grab_base[g1] + l);
+        }
+        for (int32_t pk : GB1->nonadjacent) add_self(grab_base[g1] + (pk & 0xffff), grab_base[g1] + ((pk >> 16) & 0xffff));
+        for (size_t g2 = g1 + 1; g2 < B->grabs.size(); ++g2) {
+            const HBody::Grab& G2 = B->grabs[g2];
+            const HBody* GB2 = s->bodies[G2.body];
+            bool en2 = false;
+            for (const HLink& L : GB2->links) en2 |= L.enabled;
+            if (!en2) continue;
+            for (int l2 = 0; l2 < (int)GB2->links.size(); ++l2) {
+                if (!GB2->links[l2].enabled || listed(G1, G2.body, l2)) continue;     // already checked through G1's list
+                for (int l1 = 0; l1 < (int)GB1->links.size(); ++l1)
+                    if (GB1->links[l1].enabled && listed(G2, G1.body, l1)) add_self(grab_base[g1] + l1, grab_base[g2] + l2);
+            }
+        }
     }
     Q->nself_total = (int)Q->quads.size() / 4 - Q->nenv_total;
-    if (slot_body.size() > 0xffff) { delete Q; return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots"); }
+    std::vector<int> slot_body, slot_link;
     int rc = finish_query(Q, slot_body, slot_link, active_dofs, nactive, all_active, true);
     if (rc != CC_OK) { delete Q; return rc; }
     *out = Q;
@@ -997,6 +1118,7 @@ int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntr
     Q->scene = s; Q->body = body; Q->nq = nl;
     std::vector<int> slot_body(nl, body), slot_link(nl);
     for (int l = 0; l < nl; ++l) slot_link[l] = l;
+    for (int l = 0; l < nl; ++l) { Q->ql_body.push_back(body); Q->ql_link.push_back(l); Q->ql_host.push_back(l); Q->ql_grab.push_back(-1); }
     // env-class pairs first (index space [0, nenv)), then self-class pairs, each in the given order
     for (int pass = 0; pass < 2; ++pass) {
         for (int k = 0; k < ntriples; ++k) {
@@ -1056,6 +1178,13 @@ int cc_query_get_pairs(const cc_query* q, int32_t* out)
 {
     if (!q || !out) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->quads.empty()) memcpy(out, q->quads.data(), q->quads.size() * sizeof(int32_t));
+    return CC_OK;
+}
+
+int cc_query_get_links(const cc_query* q, int32_t* out)
+{
+    if (!q || !out) return fail(CC_ERR_INVALID, "bad arguments");
+    for (int l = 0; l < q->nq; ++l) { out[2 * l] = q->ql_body[l]; out[2 * l + 1] = q->ql_link[l]; }
     return CC_OK;
 }
 

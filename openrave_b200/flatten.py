@@ -85,3 +85,15 @@ def affects_table(body):
         for l in range(nl):
             out[d, l] = 1 if body.DoesAffect(d, l) else 0
     return out
+
+
+def grab_tables(body, body_id):
+    """KinBody::_vGrabbedBodies -> the arguments of cc_body_set_grabbed, one tuple per grabbed body in grab order:
+    (grabbed body id, grabbing link index, rel [nlinks, 8] float64, noncolliding [(body id, link index)] int32 [m, 2]).
+    `body_id(kinbody)` maps a KinBody to the checker's body id."""
+    out = []
+    for g in getattr(body, "grabbed", []):
+        rel = transforms8(g.t_rel)
+        nc = np.array([(body_id(l.body), l.index) for l in g.noncolliding], dtype=np.int32).reshape(-1, 2)
+        out.append((body_id(g.body), g.link.index, rel, nc))
+    return out

@@ -386,6 +386,7 @@ class KinBody(object):
         self.joints_affecting_links = None
         self.link_depths = []
         self.attached = []          # bodies rigidly attached through the environment (KinBody::GetAttached)
+        self.grabbed = []           # KinBody::_vGrabbedBodies, in grab order
         self.uri = ""
 
     # --- openravepy-style accessors
@@ -442,8 +443,121 @@ class KinBody(object):
         return any(l.enabled for l in self.links)
 
     def _notify_transform_changed(self):
+        self._update_grabbed_bodies()
         if self.env is not None:
             self.env._body_changed(self)
+
+    # --- grabbing (src/libopenrave/kinbodygrab.cpp) -------------------------------------------------
+    def rigidly_attached_links(self, link):
+        """Link::GetRigidlyAttachedLinks: the links joined to `link` through static joints (itself included)."""
+        group = {link.index}
+        changed = True
+        while changed:
+            changed = False
+            for j in self.all_joints():
+                if j.IsStatic():
+                    a, b = j.links[0].index, j.links[1].index
+                    if (a in group) != (b in group):
+                        group.update((a, b))
+                        changed = True
+        return [self.links[i] for i in sorted(group)]
+
+    def Grab(self, body, link, links_to_ignore=()):
+        """KinBody::Grab(pGrabbedBody, pGrabbingLink, setGrabberLinksToIgnore) (kinbodygrab.cpp:204-330): the body follows `link`
+        from now on; Grabbed::ComputeListNonCollidingLinks (:63-200) is evaluated here, at the grab-time state, with every
+        link of both bodies enabled and the body not yet attached."""
+        if body is self or link.body is not self:
+            raise ValueError("Grab: bad body / link")
+        self.Release(body)
+        cc = self.env.GetCollisionChecker() if self.env is not None else None
+        if cc is None:
+            raise RuntimeError("Grab needs a collision checker (the non-colliding link list is a collision query)")
+        g = Grabbed(body, link, set(int(i) for i in links_to_ignore))
+        saved = [(l, l.enabled) for l in self.links + body.links] + [(l, l.enabled) for o in self.grabbed for l in o.body.links]
+        for l, _ in saved:
+            l.enabled = True
+        for b in [self, body] + [o.body for o in self.grabbed]:
+            b._reset_collision_cache()
+        try:
+            rigid = set(l.index for l in self.rigidly_attached_links(link))
+            for l in self.links:
+                if l.index in rigid or l.index in g.ignore:
+                    continue
+                if not cc.CheckCollision(l, body):
+                    g.noncolliding.append(l)
+            for o in self.grabbed:
+                if o.link.index in rigid:       # constant relative pose: never checked against each other
+                    continue
+                for l in o.body.links:
+                    if not cc.CheckCollision(l, body):
+                        g.noncolliding.append(l)
+        finally:
+            for l, e in saved:
+                l.enabled = e
+            for b in [self, body] + [o.body for o in self.grabbed]:
+                b._reset_collision_cache()
+        self.grabbed.append(g)
+        for a, b in ((self, body), (body, self)):
+            if b not in a.attached:
+                a.attached.append(b)
+        self._grab_changed()
+        return True
+
+    def Release(self, body):
+        for g in list(self.grabbed):
+            if g.body is body:
+                self.grabbed.remove(g)
+                if body in self.attached:
+                    self.attached.remove(body)
+                if self in body.attached:
+                    body.attached.remove(self)
+                for o in self.grabbed:            # its links leave the other grabbed bodies' lists
+                    o.noncolliding = [l for l in o.noncolliding if l.body is not body]
+                self._grab_changed()
+
+    def ReleaseAllGrabbed(self):
+        for g in list(self.grabbed):
+            self.Release(g.body)
+
+    def GetGrabbed(self):
+        return [g.body for g in self.grabbed]
+
+    def IsGrabbing(self, body):
+        return any(g.body is body for g in self.grabbed)
+
+    def IsAttached(self, body):
+        """KinBody::IsAttached: transitive over attachments."""
+        seen, todo = {id(self)}, [self]
+        while todo:
+            for o in todo.pop().attached:
+                if o is body:
+                    return True
+                if id(o) not in seen:
+                    seen.add(id(o))
+                    todo.append(o)
+        return body is self
+
+    def _grab_changed(self):
+        self.grab_epoch = getattr(self, "grab_epoch", 0) + 1
+        if self.env is not None:
+            self.env._body_changed(self)
+
+    def _update_grabbed_bodies(self):
+        """KinBody::_UpdateGrabbedBodies: every grabbed link = grabbing link * relative pose."""
+        for g in self.grabbed:
+            for l, rel in zip(g.body.links, g.t_rel):
+                l.t = rm.t_mul(g.link.t, rel)
+            g.body._update_grabbed_bodies()
+            if g.body.env is not None:
+                g.body.env._body_changed(g.body)
+
+    def GetQueryLinkTransformations(self):
+        """The body's link transforms followed by those of its grabbed bodies in grab order: the row layout of the
+        checkers' pose-mode entries (cc_check_poses) when bodies are grabbed."""
+        ts = [l.t for l in self.links]
+        for g in self.grabbed:
+            ts += [l.t for l in g.body.links]
+        return ts
 
     def _reset_collision_cache(self):
         self._nonadjacent_cache = {k: v for k, v in self._nonadjacent_cache.items() if k[1] == 0}
@@ -698,9 +812,44 @@ class KinBody(object):
         return self._nonadjacent_cache[(ck, adjacentoptions)]
 
     def CheckSelfCollision(self, report=None, collisionchecker=None):
-        """KinBody::CheckSelfCollision (kinbodycollision.cpp:21-81) without grabbed bodies."""
+        """KinBody::CheckSelfCollision (kinbodycollision.cpp:21-223): the standalone check, then per grabbed body its
+        non-colliding links x its links, its own self collision, and the later grabbed bodies link by link.  This is the
+        literal per-call loop; the batched entry evaluates the same pair set in one pass (cc_query_create)."""
         cc = collisionchecker if collisionchecker is not None else self.env.GetCollisionChecker()
-        return cc.CheckStandaloneSelfCollision(self, report)
+        if cc.CheckStandaloneSelfCollision(self, report):
+            return True
+        for i1, g1 in enumerate(self.grabbed):
+            if not g1.body.IsEnabled():
+                continue
+            for rl in g1.noncolliding:
+                for gl in g1.body.links:
+                    if cc.CheckCollision(rl, gl, report=report):
+                        return True
+            if g1.body.CheckSelfCollision(report, cc):
+                return True
+            for g2 in self.grabbed[i1 + 1:]:
+                if not g2.body.IsEnabled():
+                    continue
+                for l2 in g2.body.links:
+                    if not l2.enabled or any(l2 is x for x in g1.noncolliding):
+                        continue
+                    for l1 in g1.body.links:
+                        if l1.enabled and any(l1 is x for x in g2.noncolliding):
+                            if cc.CheckCollision(l1, l2, report=report):
+                                return True
+        return False
+
+
+class Grabbed(object):
+    """One entry of KinBody::_vGrabbedBodies (kinbodygrab.h)."""
+
+    def __init__(self, body, link, ignore):
+        self.body = body
+        self.link = link
+        self.ignore = ignore
+        tinv = rm.t_inv(link.t)
+        self.t_rel = [rm.t_mul(tinv, l.t) for l in body.links]
+        self.noncolliding = []          # _listNonCollidingLinksWhenGrabbed: links of the grabber and of its other grabbed bodies
 
 
 def _pair(a, b):

@@ -69,6 +69,8 @@ def _load(kind):
     lib.orc_body_set_link_enabled.argtypes = [vp, ci, vp]
     lib.orc_body_set_link_transforms.argtypes = [vp, ci, vp]
     lib.orc_body_set_attached.argtypes = [vp, ci, ci, ci]
+    lib.orc_body_set_grabbed.argtypes = [vp, ci, ci, ci, vp, vp, ci]
+    lib.orc_body_release_grabbed.argtypes = [vp, ci, ci]
     lib.orc_body_set_removed.argtypes = [vp, ci, ci]
     lib.orc_body_set_kinematics.argtypes = [vp, ci, ci, ci, vp, vp, vp]
     lib.orc_body_set_nonadjacent_pairs.argtypes = [vp, ci, vp, ci]
@@ -166,6 +168,18 @@ class OracleChecker(object):
             if id(b) in self._dirty:
                 self._sync_body(b)
         self._dirty.clear()
+        epochs = self.__dict__.setdefault("_grab_epochs", {})
+        for b in self.env.GetBodies():
+            ep = getattr(b, "grab_epoch", 0)
+            if epochs.get(id(b), 0) != ep:
+                bid = self._ids[id(b)]
+                self.lib.orc_body_release_grabbed(self.scene, bid, -1)
+                for gid, link, rel, nc in flatten.grab_tables(b, lambda k: self._ids[id(k)]):
+                    self.lib.orc_body_set_grabbed(self.scene, bid, gid, link, _ptr(rel), _ptr(nc) if len(nc) else None, len(nc))
+                epochs[id(b)] = ep
+                for g in b.grabbed:
+                    if len(g.body.links) > 1:
+                        self._sync_kinematics(g.body)
 
     def _sync_kinematics(self, body):
         bid = self._ids[id(body)]
@@ -210,7 +224,7 @@ class OracleChecker(object):
         else:
             q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active))
             n = q.shape[0]
-        nl = len(body.links)
+        nl = len(body.links) + sum(len(g.body.links) for g in getattr(body, "grabbed", []))   # grabbed links follow the body's own
         verdict = np.zeros(n, dtype=np.uint32)
         fe = np.zeros((n, 3), dtype=np.int32)
         fs = np.zeros((n, 2), dtype=np.int32)
@@ -262,12 +276,13 @@ class OracleChecker(object):
             report.Reset(self._options)
         if isinstance(a, KinBody) and b is None:
             res = self.check_batch(a, None, flags=BATCH_ENV, report=report is not None,
-                                   poses=flatten.transforms8(a.GetLinkTransformations())[None])
+                                   poses=flatten.transforms8(a.GetQueryLinkTransformations())[None])
             hit = bool(res["verdict"][0] & 1)
             if report is not None and hit:
                 bodies = self._bodies_by_id()
+                qlinks = list(a.links) + [l for g in a.grabbed for l in g.body.links]
                 for _, l1, ob, l2 in res["env_pairs"]:
-                    report.AddLinkCollision(a.links[l1], bodies[ob].links[l2])
+                    report.AddLinkCollision(qlinks[l1], bodies[ob].links[l2])
                 report.minDistance = 0
             return hit
         if isinstance(a, Link) and isinstance(b, Link):
@@ -334,10 +349,11 @@ class OracleChecker(object):
             return False
         if report is not None:
             report.Reset(self._options)
-        res = self.check_batch(body, None, flags=BATCH_SELF, poses=flatten.transforms8(body.GetLinkTransformations())[None])
-        hit = bool(res["verdict"][0] & 2)
+        res = self.check_batch(body, None, flags=BATCH_SELF, poses=flatten.transforms8(body.GetQueryLinkTransformations())[None])
+        # the standalone check stops at the body's own non-adjacent pairs; a first hit on a grabbed link is not one of them
+        l0, l1 = res["first_self"][0]
+        hit = bool(res["verdict"][0] & 2) and l0 < len(body.links) and l1 < len(body.links)
         if hit and report is not None:
-            l0, l1 = res["first_self"][0]
             report.AddLinkCollision(body.links[l0], body.links[l1])
             report.minDistance = 0
         return hit

@@ -859,6 +859,12 @@ struct Body {
     std::vector<uint8_t> affects;     // [ndof][nlinks]
     std::vector<int32_t> nonadjacent; // packed, reference order
     std::vector<double> dofvals;      // current values of all DOFs (used for the inactive ones)
+    struct Grab {                     // KinBody::_vGrabbedBodies entry (kinbodygrab.cpp)
+        int body, link;
+        std::vector<Xf> rel;          // pose of every grabbed link relative to the grabbing link
+        std::vector<int32_t> noncolliding;   // (body, link) pairs: _listNonCollidingLinksWhenGrabbed
+    };
+    std::vector<Grab> grabs;
     Body() : is_robot(false), removed(false), ndof(0) {}
     ~Body() { for (size_t i = 0; i < links.size(); ++i) delete links[i]; }
 };
@@ -1028,6 +1034,31 @@ int orc_body_set_attached(void* sp, int a, int b, int attached)
     return 0;
 }
 
+int orc_body_set_grabbed(void* sp, int body, int grabbed, int link, const double* rel8, const int32_t* noncolliding, int n)
+{
+    Scene* s = (Scene*)sp;
+    Body* b = s->bodies[body];
+    Body::Grab* g = NULL;
+    for (size_t i = 0; i < b->grabs.size(); ++i) if (b->grabs[i].body == grabbed) g = &b->grabs[i];
+    if (!g) { b->grabs.push_back(Body::Grab()); g = &b->grabs.back(); }
+    g->body = grabbed; g->link = link;
+    const size_t ng = s->bodies[grabbed]->links.size();
+    g->rel.resize(ng);
+    for (size_t k = 0; k < ng; ++k) { memcpy(g->rel[k].q, rel8 + 8 * k, 32); memcpy(g->rel[k].t, rel8 + 8 * k + 4, 24); }
+    g->noncolliding.assign(noncolliding, noncolliding + 2 * (size_t)n);
+    return orc_body_set_attached(sp, body, grabbed, 1);
+}
+
+int orc_body_release_grabbed(void* sp, int body, int grabbed)
+{
+    Body* b = ((Scene*)sp)->bodies[body];
+    for (size_t i = 0; i < b->grabs.size();) {
+        if (grabbed < 0 || b->grabs[i].body == grabbed) { orc_body_set_attached(sp, body, b->grabs[i].body, 0); b->grabs.erase(b->grabs.begin() + i); }
+        else ++i;
+    }
+    return 0;
+}
+
 int orc_body_set_removed(void* sp, int body, int removed) { ((Scene*)sp)->bodies[body]->removed = removed != 0; return 0; }
 
 int orc_body_set_kinematics(void* sp, int body, int ndof, int njoints, const cc_joint* joints, const uint8_t* affects,
@@ -1099,18 +1130,32 @@ int orc_check_batch(void* sp, int body, const int32_t* active, int nactive, cons
     std::vector<double> vals(b->dofvals);
     std::vector<Xf> xf;
     int64_t nout = 0;
+    // query links: the body's own, then the links of its grabbed bodies in grab order (same layout as the product's
+    // cc_query_get_links); qb/ql name them, gbase[g] is where grabbed body g starts
+    std::vector<Body*> qb; std::vector<int> ql; std::vector<size_t> gbase(b->grabs.size(), 0);
+    for (size_t i = 0; i < nl; ++i) { qb.push_back(b); ql.push_back((int)i); }
+    for (size_t g = 0; g < b->grabs.size(); ++g) {
+        gbase[g] = qb.size();
+        Body* G = s->bodies[b->grabs[g].body];
+        for (size_t k = 0; k < G->links.size(); ++k) { qb.push_back(G); ql.push_back((int)k); }
+    }
+    const size_t nle = qb.size();
     for (int c = 0; c < n; ++c) {
         if (opt->pose_mode) {
-            xf.resize(nl);
-            const double* T8 = q + (size_t)c * nl * 8;
-            for (size_t i = 0; i < nl; ++i) { memcpy(xf[i].q, T8 + 8 * i, 32); memcpy(xf[i].t, T8 + 8 * i + 4, 24); }
+            xf.resize(nle);
+            const double* T8 = q + (size_t)c * nle * 8;
+            for (size_t i = 0; i < nle; ++i) { memcpy(xf[i].q, T8 + 8 * i, 32); memcpy(xf[i].t, T8 + 8 * i + 4, 24); }
         } else {
             for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * nactive + a];
             forward_kinematics(*b, &vals[0], b->xf[0], xf);
+            // KinBody::_UpdateGrabbedBodies: grabbed links follow their grabbing link
+            xf.resize(nle);
+            for (size_t g = 0; g < b->grabs.size(); ++g)
+                for (size_t k = 0; k < b->grabs[g].rel.size(); ++k) xf[gbase[g] + k] = xf_mul(xf[b->grabs[g].link], b->grabs[g].rel[k]);
         }
         if (fk_out) {
-            for (size_t i = 0; i < nl; ++i) {
-                double* o = fk_out + ((size_t)c * nl + i) * 8;
+            for (size_t i = 0; i < nle; ++i) {
+                double* o = fk_out + ((size_t)c * nle + i) * 8;
                 memcpy(o, xf[i].q, 32); memcpy(o + 4, xf[i].t, 24); o[7] = 0;
             }
         }
@@ -1120,46 +1165,104 @@ int orc_check_batch(void* sp, int body, const int32_t* active, int nactive, cons
         double pen = 0; bool near = false;
         if (opt->flags & CC_BATCH_ENV) {
             bool done = false;
-            for (size_t ob = 0; ob < s->bodies.size() && !done; ++ob) {
-                Body* o = s->bodies[ob];
-                if (o->removed || is_attached(*b, (int)ob)) continue;
-                for (size_t i = 0; i < nl && !done; ++i) {
-                    for (size_t j = 0; j < o->links.size() && !done; ++j) {
-                        if (!b->enabled[i] || !o->enabled[j]) continue;
-                        if (!act[i]) continue;
-                        if (!b->links[i]->valid || !o->links[j]->valid) continue;
-                        PairResult r = collide_links(xf[i], *b->links[i], o->xf[j], *o->links[j], false, opt->want_band != 0);
-                        bv += r.bv_tests; tt += r.tri_tests;
-                        if (r.contacts > 0) {
-                            if (!(v & CC_VERDICT_ENV)) { fe[0] = (int)i; fe[1] = (int)ob; fe[2] = (int)j; }
-                            v |= CC_VERDICT_ENV;
-                            if (r.max_penetration > pen) pen = r.max_penetration;
-                            if (env_pairs_out && nout < env_pairs_cap) {
-                                int32_t* e = env_pairs_out + 4 * nout;
-                                e[0] = c; e[1] = (int)i; e[2] = (int)ob; e[3] = (int)j;
+            // CheckCollision(body): every attached body (here: the body, then its grabbed bodies) through CheckCollisionP
+            // (collisionPQP.h:314-329, 432-498)
+            for (int att = -1; att < (int)b->grabs.size() && !done; ++att) {
+                Body* a1 = att < 0 ? b : s->bodies[b->grabs[att].body];
+                const size_t base = att < 0 ? 0 : gbase[att];
+                for (size_t ob = 0; ob < s->bodies.size() && !done; ++ob) {
+                    Body* o = s->bodies[ob];
+                    if (o->removed) continue;
+                    bool attached = is_attached(*b, (int)ob);                      // GetAttached is transitive
+                    for (size_t g = 0; g < b->grabs.size() && !attached; ++g)
+                        attached = b->grabs[g].body == (int)ob || is_attached(*s->bodies[b->grabs[g].body], (int)ob);
+                    if (attached) continue;
+                    for (size_t i = 0; i < a1->links.size() && !done; ++i) {
+                        for (size_t j = 0; j < o->links.size() && !done; ++j) {
+                            if (!a1->enabled[i] || !o->enabled[j]) continue;
+                            if (att < 0 && !act[i]) continue;
+                            if (!a1->links[i]->valid || !o->links[j]->valid) continue;
+                            PairResult r = collide_links(xf[base + i], *a1->links[i], o->xf[j], *o->links[j], false, opt->want_band != 0);
+                            bv += r.bv_tests; tt += r.tri_tests;
+                            if (r.contacts > 0) {
+                                if (!(v & CC_VERDICT_ENV)) { fe[0] = (int)(base + i); fe[1] = (int)ob; fe[2] = (int)j; }
+                                v |= CC_VERDICT_ENV;
+                                if (r.max_penetration > pen) pen = r.max_penetration;
+                                if (env_pairs_out && nout < env_pairs_cap) {
+                                    int32_t* e = env_pairs_out + 4 * nout;
+                                    e[0] = c; e[1] = (int)(base + i); e[2] = (int)ob; e[3] = (int)j;
+                                }
+                                if (opt->report) nout++;
+                                if (!opt->report) done = true;
+                            } else if (opt->want_band && !near) {
+                                near = links_within(xf[base + i], *a1->links[i], o->xf[j], *o->links[j], opt->band);
                             }
-                            if (opt->report) nout++;
-                            if (!opt->report) done = true;
-                        } else if (opt->want_band && !near) {
-                            near = links_within(xf[i], *b->links[i], o->xf[j], *o->links[j], opt->band);
                         }
                     }
                 }
             }
         }
         if (opt->flags & CC_BATCH_SELF) {
-            for (size_t k = 0; k < spairs.size(); ++k) {
-                int l0 = spairs[k] & 0xffff, l1 = (spairs[k] >> 16) & 0xffff;
-                if (!act[l0] || !act[l1]) continue;
-                if (!b->links[l0]->valid || !b->links[l1]->valid) continue;
-                PairResult r = collide_links(xf[l0], *b->links[l0], xf[l1], *b->links[l1], false, opt->want_band != 0);
-                bv += r.bv_tests; tt += r.tri_tests;
-                if (r.contacts > 0) {
-                    v |= CC_VERDICT_SELF; fs[0] = l0; fs[1] = l1;
-                    if (r.max_penetration > pen) pen = r.max_penetration;
-                    break;
-                } else if (opt->want_band && !near) {
-                    near = links_within(xf[l0], *b->links[l0], xf[l1], *b->links[l1], opt->band);
+            // one link pair of the query (DoPQP: both enabled, both active, both with a model); true = contact
+            struct SelfCheck {
+                const std::vector<Body*>& qb; const std::vector<int>& ql; const std::vector<Xf>& xf; const std::vector<uint8_t>& act;
+                size_t nl; const OrcOptions* opt; int64_t& bv; int64_t& tt; double& pen; bool& near; uint32_t& v; int* fs;
+                bool operator()(size_t a, size_t b2) const
+                {
+                    const LinkModel& la = *qb[a]->links[ql[a]]; const LinkModel& lb = *qb[b2]->links[ql[b2]];
+                    if (!qb[a]->enabled[ql[a]] || !qb[b2]->enabled[ql[b2]]) return false;
+                    if ((a < nl && !act[a]) || (b2 < nl && !act[b2])) return false;
+                    if (!la.valid || !lb.valid) return false;
+                    PairResult r = collide_links(xf[a], la, xf[b2], lb, false, opt->want_band != 0);
+                    bv += r.bv_tests; tt += r.tri_tests;
+                    if (r.contacts > 0) {
+                        v |= CC_VERDICT_SELF; fs[0] = (int)a; fs[1] = (int)b2;
+                        if (r.max_penetration > pen) pen = r.max_penetration;
+                        return true;
+                    }
+                    if (opt->want_band && !near) near = links_within(xf[a], la, xf[b2], lb, opt->band);
+                    return false;
+                }
+            } check = {qb, ql, xf, act, nl, opt, bv, tt, pen, near, v, fs};
+            bool hit = false;
+            // CheckStandaloneSelfCollision (collisionPQP.h:364-386)
+            for (size_t k = 0; k < spairs.size() && !hit; ++k) hit = check(spairs[k] & 0xffff, (spairs[k] >> 16) & 0xffff);
+            // grabbed bodies (KinBody::CheckSelfCollision, kinbodycollision.cpp:83-205)
+            for (size_t g1 = 0; g1 < b->grabs.size() && !hit; ++g1) {
+                const Body::Grab& G1 = b->grabs[g1];
+                Body* B1 = s->bodies[G1.body];
+                bool en1 = false;
+                for (size_t k = 0; k < B1->enabled.size(); ++k) en1 |= B1->enabled[k] != 0;
+                if (!en1) continue;
+                for (size_t k = 0; k + 1 < G1.noncolliding.size() && !hit; k += 2) {
+                    // the listed link: one of the body's own, or a link of another body it still grabs
+                    size_t a = nle;
+                    if (G1.noncolliding[k] == body) a = (size_t)G1.noncolliding[k + 1];
+                    else for (size_t g = 0; g < b->grabs.size(); ++g) if (b->grabs[g].body == G1.noncolliding[k]) a = gbase[g] + G1.noncolliding[k + 1];
+                    if (a >= nle) continue;
+                    for (size_t l = 0; l < B1->links.size() && !hit; ++l) hit = check(a, gbase[g1] + l);
+                }
+                // grabbedBody1.CheckSelfCollision: its own non-adjacent list
+                for (size_t k = 0; k < B1->nonadjacent.size() && !hit; ++k)
+                    hit = check(gbase[g1] + (B1->nonadjacent[k] & 0xffff), gbase[g1] + ((B1->nonadjacent[k] >> 16) & 0xffff));
+                for (size_t g2 = g1 + 1; g2 < b->grabs.size() && !hit; ++g2) {
+                    const Body::Grab& G2 = b->grabs[g2];
+                    Body* B2 = s->bodies[G2.body];
+                    bool en2 = false;
+                    for (size_t k = 0; k < B2->enabled.size(); ++k) en2 |= B2->enabled[k] != 0;
+                    if (!en2) continue;
+                    for (size_t l2 = 0; l2 < B2->links.size() && !hit; ++l2) {
+                        if (!B2->enabled[l2]) continue;
+                        bool in1 = false;
+                        for (size_t k = 0; k + 1 < G1.noncolliding.size(); k += 2) in1 |= G1.noncolliding[k] == G2.body && G1.noncolliding[k + 1] == (int)l2;
+                        if (in1) continue;
+                        for (size_t l1 = 0; l1 < B1->links.size() && !hit; ++l1) {
+                            if (!B1->enabled[l1]) continue;
+                            bool in2 = false;
+                            for (size_t k = 0; k + 1 < G2.noncolliding.size(); k += 2) in2 |= G2.noncolliding[k] == G1.body && G2.noncolliding[k + 1] == (int)l1;
+                            if (in2) hit = check(gbase[g1] + l1, gbase[g2] + l2);
+                        }
+                    }
                 }
             }
         }
