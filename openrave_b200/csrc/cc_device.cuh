@@ -50,6 +50,7 @@ constexpr int kNone = 0x7fffffff;
 
 // flags (low bits mirror cc_batch_flags)
 constexpr int kFlagEnv = 1, kFlagSelf = 2, kFlagAllPairs = 4, kFlagPoseMode = 8, kFlagFkOnly = 16, kFlagCounters = 32;
+constexpr int kFlagInitOutputs = 64;   // split traversal: the FK kernel initialises the outputs the traversal combines into
 
 struct FkStep {                 // one joint of the chain program, 256 bytes
     int32_t type;               // 1 revolute, 2 prismatic
@@ -109,6 +110,12 @@ struct Params {
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
+    // split traversal (small batches): every configuration becomes `split` work items, item `part` owning the pairs
+    // [part_begin[part], part_begin[part + 1]) of `pairs` / `pair_orig` (round-robin blocks of the reference order, env pairs
+    // first: part_nenv[part] of them); results are combined with atomics into outputs the FK kernel initialised
+    int32_t split;
+    const int32_t* part_begin;  // [split + 1]
+    const int32_t* part_nenv;   // [split]
 };
 
 // ------------------------------------------------------------------------------------------------ FP64 SE(3)
@@ -413,6 +420,16 @@ cc_fk_kernel(const __grid_constant__ Params P)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.n) return;
 
+    if (P.flags & kFlagInitOutputs) {
+        if (P.verdict) P.verdict[c] = 0u;
+        if (P.first_env) P.first_env[c] = -1;
+        if (P.first_self) P.first_self[c] = -1;
+        if (P.work_out) P.work_out[c] = 0u;
+        if (P.pair_mask) {
+            uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
+            for (int i = 0; i < P.mask_words; ++i) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
+        }
+    }
     if (P.flags & kFlagPoseMode) {
         const double* src = P.q + (size_t)c * P.nq * 8;
         for (int l = 0; l < P.nq; ++l)
@@ -466,6 +483,10 @@ __device__ __forceinline__ int filter_queue(uint2* q, int count, uint32_t dead_s
     return w;
 }
 
+// kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,
+// each over its own share of the pair list, outputs merged with atomics (small batches: the latency of a batch is the
+// traversal of its slowest configuration, so that one is spread over several warps).
+template <bool kSplit>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -485,19 +506,32 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const bool counters = (P.flags & kFlagCounters) != 0;
     const float eps2 = P.tri_eps * P.tri_eps;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int nenv_dev = P.nenv_dev, nenv_total = P.nenv_total, ndyn = P.ndyn;
+    const int nenv_total = P.nenv_total, ndyn = P.ndyn;
+    int nenv_dev = P.nenv_dev, npairs_dev = P.npairs_dev;
+    const uint32_t* pairs = P.pairs;
+    const int32_t* pair_orig = P.pair_orig;
+    const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
 
     for (;;) {
         int c = 0;
         if (lane == 0) c = atomicAdd(&P.counters[0], 1);
         c = __shfl_sync(kFull, c, 0);
-        if (c >= P.n) break;
+        if (c >= nwork) break;
+        if (kSplit) {
+            const int w = c;
+            c = w / P.split;
+            const int part = w - c * P.split;
+            const int pb = __ldg(&P.part_begin[part]);
+            pairs = P.pairs + pb; pair_orig = P.pair_orig + pb;
+            npairs_dev = __ldg(&P.part_begin[part + 1]) - pb;
+            nenv_dev = __ldg(&P.part_nenv[part]);
+        }
         const float* xf = P.xf32 + (size_t)c * ndyn * 12;
         const float* ab = P.aabb + (size_t)c * ndyn * 8;
         const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;       // static slot s lives at st_ab + 8 s
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
-        if (P.pair_mask) {
+        if (!kSplit && P.pair_mask) {
             uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
             for (int i = lane; i < P.mask_words; i += 32) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
             __syncwarp();
@@ -513,15 +547,15 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         uint32_t iters = 0;
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
         int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
-        const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : nenv_dev;
+        const int kend = (P.flags & kFlagSelf) ? npairs_dev : nenv_dev;
 
         while ((k0 < kend || ncb > 0) && !failed) {
             if (k0 < kend && ncb < 32) {
                 if (!all_pairs && recheck) {
                     // pairs are in reference order inside each class: once a hit precedes everything left, skip the rest
                     recheck = false;
-                    if (k0 < nenv_dev) { if (best_env < __ldg(&P.pair_orig[k0])) { k0 = nenv_dev; recheck = true; continue; } }
-                    else if (best_self < __ldg(&P.pair_orig[k0])) { k0 = kend; continue; }
+                    if (k0 < nenv_dev) { if (best_env < __ldg(&pair_orig[k0])) { k0 = nenv_dev; recheck = true; continue; } }
+                    else if (best_self < __ldg(&pair_orig[k0])) { k0 = kend; continue; }
                 }
                 // ------------------------------------------------------------ broadphase: 32 x kBroadPerLane pairs, world AABBs
                 const int lim = (k0 < nenv_dev && nenv_dev < kend) ? nenv_dev : kend;     // do not straddle env | self
@@ -529,7 +563,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
 #pragma unroll
                 for (int h = 0; h < kBroadPerLane; ++h) {
                     const int k = k0 + 32 * h + lane;
-                    pr[h] = k < lim ? __ldg(&P.pairs[k]) : 0xffffffffu;
+                    pr[h] = k < lim ? __ldg(&pairs[k]) : 0xffffffffu;
                 }
                 bool ov[kBroadPerLane];
 #pragma unroll
@@ -565,12 +599,12 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
                 if (lane < cnt) {
                     const uint32_t k = cbuf[lane];
-                    orig = __ldg(&P.pair_orig[k]);
+                    orig = __ldg(&pair_orig[k]);
                     const bool is_env = (int)k < nenv_dev;
                     bool skip = false;
                     if (!all_pairs) skip = is_env ? (orig > best_env) : (orig > best_self);
                     if (!skip) {
-                        const uint32_t pr = __ldg(&P.pairs[k]);
+                        const uint32_t pr = __ldg(&pairs[k]);
                         const int la = pr & 0xffff, lb = pr >> 16;
                         float A[12], Bx[12];
                         {
@@ -823,10 +857,18 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             uint32_t v = 0;
             if ((P.flags & kFlagEnv) && be != kNone) v |= 1u;
             if ((P.flags & kFlagSelf) && bs != kNone) v |= 2u;
-            if (P.verdict) P.verdict[c] = v;
-            if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
-            if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
-            if (P.work_out) P.work_out[c] = iters;
+            if (kSplit) {
+                // merge with the other work items of this configuration (-1 reads as the largest unsigned value)
+                if (v && P.verdict) atomicOr(&P.verdict[c], v);
+                if ((v & 1u) && P.first_env) atomicMin((unsigned int*)&P.first_env[c], (unsigned int)be);
+                if ((v & 2u) && P.first_self) atomicMin((unsigned int*)&P.first_self[c], (unsigned int)bs);
+                if (P.work_out) atomicAdd(&P.work_out[c], iters);
+            } else {
+                if (P.verdict) P.verdict[c] = v;
+                if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
+                if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
+                if (P.work_out) P.work_out[c] = iters;
+            }
         }
         __syncwarp();
     }

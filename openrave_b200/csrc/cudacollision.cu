@@ -247,6 +247,9 @@ struct Plan {
     DevBuf<int32_t> d_orig, d_emit, d_slot_root;
     DevBuf<float> d_st_xf, d_st_aabb, d_link_box;
     DevBuf<ccdev::FkStep> d_steps;
+    // split traversal tables for S = 2, 4, 8 (index log2(S) - 1), built with the plan
+    struct Split { DevBuf<uint32_t> d_pairs; DevBuf<int32_t> d_orig, d_part_begin, d_part_nenv; };
+    Split split[3];
 };
 
 bool body_attached(const HBody& a, int other)
@@ -382,18 +385,39 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
-        int per_sm = 0;
-        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_traverse_kernel, ccdev::kWarpsPerBlock * 32, tr_smem));
-        if (per_sm < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
+        int per_sm = 0, per_sm_split = 0;
+        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_traverse_kernel<false>, ccdev::kWarpsPerBlock * 32, tr_smem));
+        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_split, ccdev::cc_traverse_kernel<true>, ccdev::kWarpsPerBlock * 32, tr_smem));
+        if (per_sm < 1 || per_sm_split < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
+        per_sm = std::min(per_sm, per_sm_split);
         if (getenv("CC_TUNE_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(getenv("CC_TUNE_BLOCKS_PER_SM"))));
-        if (getenv("CC_TUNE_CARVEOUT"))
-            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
+        if (getenv("CC_TUNE_CARVEOUT")) {
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
+        }
         S->trav_blocks_per_sm = per_sm;
     }
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     // spill areas: one per pipeline lane, sized for a full persistent grid
     const int full_warps = S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock;
+    // small batches: spread every configuration over 2, 4 or 8 warps (as many as keep the work items within ~2 waves and
+    // leave each part at least one block of 32 pairs); CC_TUNE_SPLIT forces a value (1 = off)
+    int split = 1;
+    if (!fk_only) {
+        static const int forced = getenv("CC_TUNE_SPLIT") ? atoi(getenv("CC_TUNE_SPLIT")) : 0;
+        const int by_load = (int)std::min<long long>(8, (2LL * full_warps) / std::max(1, n));
+        const int by_pairs = ((int)pl.pairs.size() + 31) / 32;
+        int want = forced > 0 ? forced : std::min(by_load, by_pairs);
+        while (split * 2 <= want && split < 8) split *= 2;
+    }
+    const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
+    if (sp) {
+        P.pairs = sp->d_pairs.p; P.pair_orig = sp->d_orig.p; P.part_begin = sp->d_part_begin.p; P.part_nenv = sp->d_part_nenv.p;
+        P.split = split;
+        P.flags |= ccdev::kFlagInitOutputs;
+    } else P.split = 1;
     if (!fk_only && (S->spill_warps < full_warps || (overlap && !S->d_spill[1].p))) {
         CC_CUDA(cudaDeviceSynchronize());            // (first launches only) nobody may still be using the old areas
         for (int k = 0; k < (overlap ? 2 : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
@@ -449,10 +473,11 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         }
         // persistent traversal grid: a whole number of waves, never more warps than configurations
         int grid = S->trav_blocks_per_sm * S->num_sms;
-        const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
+        const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        ccdev::cc_traverse_kernel<<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        if (split > 1) ccdev::cc_traverse_kernel<true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        else ccdev::cc_traverse_kernel<false><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
         if (hio) {
@@ -819,6 +844,21 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
     CC_CUDA(pl.d_slot_root.upload(roots)); CC_CUDA(pl.d_link_box.upload(linkbox));
     CC_CUDA(pl.d_st_xf.upload(stxf)); CC_CUDA(pl.d_st_aabb.upload(staabb));
     CC_CUDA(pl.d_steps.upload(pl.steps));
+    // split tables: part k of S takes every S-th block of 32 pairs of each class (env first), reference order kept
+    for (int si = 0; si < 3; ++si) {
+        const int S = 2 << si;
+        std::vector<uint32_t> sp; std::vector<int32_t> so, pb(1, 0), pn;
+        const int np = (int)pl.pairs.size();
+        for (int k = 0; k < S; ++k) {
+            int ne = 0;
+            for (int i = 0; i < pl.nenv; ++i) if ((i / 32) % S == k) { sp.push_back(pl.pairs[i]); so.push_back(pl.orig[i]); ++ne; }
+            for (int i = pl.nenv; i < np; ++i) if (((i - pl.nenv) / 32) % S == k) { sp.push_back(pl.pairs[i]); so.push_back(pl.orig[i]); }
+            pn.push_back(ne);
+            pb.push_back((int32_t)sp.size());
+        }
+        CC_CUDA(pl.split[si].d_pairs.upload(sp)); CC_CUDA(pl.split[si].d_orig.upload(so));
+        CC_CUDA(pl.split[si].d_part_begin.upload(pb)); CC_CUDA(pl.split[si].d_part_nenv.upload(pn));
+    }
     return CC_OK;
 }
 
