@@ -194,6 +194,22 @@ int cc_check_poses(cc_query* q, const double* link_transforms8, int n, int flags
 /* Batched KinBody::SetDOFValues: out [n][nlinks][8] doubles (validation of the 1e-6 m / 1e-6 rad bound). */
 int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_transforms8);
 
+/* ---- CO_Distance (collisionPQP.h:622-648: PQP_Distance on every link pair the query visits, CollisionReport::minDistance
+ * = the smallest, with the two closest points as contact 0 of that pair).  For every configuration: the minimum separation
+ * over the query's env pairs (CC_BATCH_ENV) and self pairs (CC_BATCH_SELF), 0 when some pair touches or penetrates.
+ *   max_distance      search radius in metres (pairs farther apart are not refined; the result is then max_distance),
+ *                     <= 0: unbounded
+ *   min_distance[n]   metres (1e30 when the query has no pair at all)
+ *   min_pair[n]       pair index (cc_query_get_pairs) attaining it, -1 when none; may be NULL
+ *   closest_points    [n][6] world coordinates: the point on the query link, the point on the other link; may be NULL
+ * The value is the exact minimum evaluated in FP32 (a few 1e-6 m), i.e. PQP_Distance with rel_err = abs_err = 0; pqprave's
+ * own call uses rel_err 200 / abs_err 0.001 (collisionPQP.h:48-49) and returns an upper estimate of this number. */
+int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance,
+                      double* min_distance, int32_t* min_pair, double* closest_points);
+/* Same for given link transforms [n][nlinks][8] (single-state queries: CheckCollision(body, report) with CO_Distance). */
+int cc_distance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double max_distance,
+                      double* min_distance, int32_t* min_pair, double* closest_points);
+
 /* Page-locked host buffers for the host-buffer entry points (cc_check_batch, cc_check_poses, cc_fk_batch).  Those calls
  * cut a big batch into chunks and copy each chunk's inputs / results on the chunk's own stream; with buffers from
  * cc_host_alloc the copies overlap the kernels of the neighbouring chunk.  Ordinary (pageable) memory stays valid

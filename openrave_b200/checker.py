@@ -48,7 +48,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_scene_commit", "cc_query_create", "cc_query_create_pairs", "cc_query_destroy", "cc_query_get_info",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
-           "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links"]
+           "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
+           "cc_distance_batch", "cc_distance_poses"]
 
 _lib = None
 
@@ -87,6 +88,8 @@ def load_library():
     lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
+    lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, vp, vp, vp]
+    lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, vp, vp, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
     lib.cc_query_trace_work.argtypes = [vp, ci]
     lib.cc_query_get_work_trace.argtypes = [vp, vp, ci]
@@ -204,6 +207,28 @@ class BoundQuery(object):
         self.checker._ck(self.lib.cc_check_poses(self.handle, _ptr(T8), n, flags, _ptr(verdict), _ptr(fe), _ptr(fs), _ptr(mask)))
         return verdict, fe, fs, mask
 
+    def distance(self, q=None, flags=BATCH_ENV | BATCH_SELF, max_distance=0.0, poses=None, want_points=True):
+        """CO_Distance for n configurations (or n sets of link transforms): (distance [n], pair index [n], points [n, 6])."""
+        if poses is not None:
+            a = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
+            fn = self.lib.cc_distance_poses
+        else:
+            a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+            fn = self.lib.cc_distance_batch
+        n = a.shape[0]
+        dist = np.zeros(n, dtype=np.float64)
+        pair = np.zeros(n, dtype=np.int32)
+        pts = np.zeros((n, 6), dtype=np.float64) if want_points else None
+        self.checker._ck(fn(self.handle, _ptr(a), n, flags, float(max_distance), _ptr(dist), _ptr(pair), _ptr(pts)))
+        return dist, pair, pts
+
+    def decode_pair(self, idx):
+        """pair indices -> [n, 3] {query link, other body id, other link} (oracle layout), -1 rows where idx < 0."""
+        out = np.full((len(idx), 3), -1, dtype=np.int32)
+        ok = idx >= 0
+        out[ok] = self.pairs[idx[ok], 0:3]
+        return out
+
     def fk(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
         n = q.shape[0]
@@ -263,8 +288,8 @@ class CudaCollisionChecker(object):
 
     # ---- CollisionCheckerBase surface (collisionchecker.h:200-237)
     def SetCollisionOptions(self, options):
-        if options & (CO_Distance | CO_UseTolerance | CO_Contacts):
-            return False   # distance / tolerance / contact points are not provided by this checker yet
+        if options & (CO_UseTolerance | CO_Contacts):
+            return False   # tolerance counts / contact points of colliding pairs are not provided by this checker
         if options != self._options:
             self._options = int(options)
             self._invalidate()
@@ -434,6 +459,27 @@ class CudaCollisionChecker(object):
         return dict(verdict=verdict, first_env=bq.decode_env(fe), first_self=bq.decode_self(fs), mask=mask, query=bq,
                     first_env_index=fe, first_self_index=fs)
 
+    def DistanceBatch(self, robot, q, flags=BATCH_ENV | BATCH_SELF, active=None, max_distance=0.0):
+        """Minimum separation of N configurations: dict(distance [n], pair [n,3] {query link, other body id, other link},
+        points [n,6] world closest points)."""
+        bq = self.bind(robot, active)
+        dist, pair, pts = bq.distance(q, flags, max_distance)
+        return dict(distance=dist, pair=bq.decode_pair(pair), pair_index=pair, points=pts, query=bq)
+
+    def _fill_distance(self, bq, body, flags, report):
+        """CO_Distance on a single-state query (collisionPQP.h:622-648): minDistance, the closest link pair, one contact."""
+        T = flatten.transforms8(body.GetQueryLinkTransformations())[None]
+        dist, pair, pts = bq.distance(poses=T, flags=flags)
+        if pair[0] >= 0 and dist[0] < report.minDistance:
+            report.minDistance = float(dist[0])
+            l1, ob, l2, _ = bq.pairs[pair[0]]
+            other = bq.link_of(l2) if bq.pairs[pair[0], 3] == 1 else self._bodies[ob].links[l2]
+            report.AddLinkCollision(bq.link_of(l1), other)
+            p1, p2 = pts[0, 0:3], pts[0, 3:6]
+            depth = float(np.linalg.norm(p2 - p1))
+            norm = (p2 - p1) / depth if depth > 0 else np.zeros(3)
+            report.contacts = [(p1.copy(), norm, -depth)]
+
     def ForwardKinematicsBatch(self, robot, q, active=None):
         return self.bind(robot, active).fk(q)
 
@@ -471,6 +517,8 @@ class CudaCollisionChecker(object):
                         l1, ob, l2, _ = bq.pairs[p]
                         report.AddLinkCollision(bq.link_of(l1), self._bodies[ob].links[l2])
                 report.minDistance = 0
+            if report is not None and (self._options & CO_Distance) and not hit:
+                self._fill_distance(bq, a, BATCH_ENV, report)
             return hit
         if isinstance(a, KinBody) and isinstance(b, KinBody):
             triples = [(l1.index, self.body_id(b), l2.index) for l1 in a.links for l2 in b.links]
@@ -532,6 +580,8 @@ class CudaCollisionChecker(object):
             if hit and report is not None:
                 report.AddLinkCollision(body.links[l0], body.links[l1])
                 report.minDistance = 0
+        if report is not None and (self._options & CO_Distance) and not hit and not getattr(body, "grabbed", []):
+            self._fill_distance(bq, body, BATCH_SELF, report)
         return hit
 
 

@@ -1,0 +1,348 @@
+// cc_distance.cuh — minimum separation per configuration (CO_Distance), sm_100a.
+//
+// Reference path (paths relative to the OpenRAVE tree): with CO_Distance pqprave runs PQP_Distance on every link pair a query
+// visits and keeps the smallest result together with the two closest points (plugins/pqprave/collisionPQP.h:622-648;
+// PQP_Distance / DistanceRecurse plugins/pqprave/pqp/PQP.cpp:663-945, TriDist plugins/pqprave/pqp/TriDist.cpp).  pqprave calls it
+// with rel_err = 200, abs_err = 0.001 (collisionPQP.h:48-49): an approximate search whose answer depends on the RSS tree and
+// the visiting order.  This kernel computes the EXACT minimum (what PQP_Distance returns with both tolerances 0) in FP32:
+// |result - exact| is a few 1e-6 m for metre-sized scenes, and result <= the reference's approximate answer + that error.
+//
+// One warp per configuration (persistent, work counter), branch and bound over the dual AABB trees of all link pairs at once:
+//   1. every pair's world-AABB gap (from the FK kernel's boxes) gives a lower bound; the pair with the smallest bound is
+//      descended first so that the running minimum `best2` is tight before the other pairs are looked at;
+//   2. pairs whose bound is below best2 are descended 32 at a time (one relative pose per slot in shared memory);
+//   3. an iteration pops up to 32 (nodeA, nodeB) items, each lane bounds its box pair from below (sum of squared gaps along
+//      A's three axes and along B's three axes, the larger of the two), drops it when the bound reaches best2, runs the exact
+//      triangle-triangle distance on leaf pairs (9 edge-edge + 6 vertex-face candidates, 0 when the 17-axis test reports
+//      contact) and otherwise pushes the two children of the larger box;
+//   4. a warp min-reduction keeps best2, the pair and the closest points.
+// Boxes are inflated by 1e-5 m at build time, so a lower bound can only be too small: nothing that could hold the minimum
+// is pruned by rounding.
+#pragma once
+#include "cc_device.cuh"
+
+namespace ccdev {
+
+constexpr int kDistStackCap = 1024;                 // items per warp
+constexpr size_t kDistWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 8 + (size_t)kDistStackCap * 8 + 32 * 4;
+
+struct DistOut {
+    double* min_distance;       // [n] metres; dist_max when nothing is closer (1e30 when dist_max <= 0 and there is no pair)
+    int32_t* min_pair;          // [n] reference-order pair index attaining it, -1 when none
+    double* points;             // [n][6] closest points in world coordinates (on the query link, on the other link), or NULL
+    float dist_max;             // search radius, <= 0: unbounded
+};
+
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+
+// closest points of segments [p, p + d1] and [q, q + d2] (clamped quadratic minimisation)
+__device__ __forceinline__ float seg_seg(V3 p, V3 d1, V3 q, V3 d2, V3& c1, V3& c2)
+{
+    const V3 r = p - q;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    float s, t;
+    const float tiny = 1e-20f;
+    if (a <= tiny && e <= tiny) { s = t = 0.f; }
+    else if (a <= tiny) { s = 0.f; t = fminf(fmaxf(f / e, 0.f), 1.f); }
+    else {
+        const float c = dot(d1, r);
+        if (e <= tiny) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+        else {
+            const float b = dot(d1, d2);
+            const float den = a * e - b * b;
+            s = den > tiny * a * e ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+            else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+        }
+    }
+    c1 = p + d1 * s;
+    c2 = q + d2 * t;
+    const V3 d = c1 - c2;
+    return dot(d, d);
+}
+
+// closest point of triangle (a, b, c) to p (Voronoi-region walk)
+__device__ __forceinline__ V3 closest_on_triangle(V3 p, V3 a, V3 b, V3 c)
+{
+    const V3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return a;
+    const V3 bp = p - b;
+    const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) return a + ab * (d1 / (d1 - d3));
+    const V3 cp = p - c;
+    const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) return a + ac * (d2 / (d2 - d6));
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) return b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6)));
+    const float den = 1.f / (va + vb + vc);
+    return a + ab * (vb * den) + ac * (vc * den);
+}
+
+// Exact squared distance of triangles P = (0, p1, p2) and Q = (q0, q1, q2) with the closest points (same shifted frame).
+__device__ __forceinline__ float tri_tri_dist2(V3 p1, V3 p2, V3 q0, V3 q1, V3 q2, V3& cp, V3& cq)
+{
+    const V3 P[3] = {v3(0.f, 0.f, 0.f), p1, p2};
+    const V3 Q[3] = {q0, q1, q2};
+    float best = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const V3 pa = P[i], pd = P[(i + 1) % 3] - P[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            V3 c1, c2;
+            const float d = seg_seg(pa, pd, Q[j], Q[(j + 1) % 3] - Q[j], c1, c2);
+            if (d < best) { best = d; cp = c1; cq = c2; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const V3 c = closest_on_triangle(P[i], q0, q1, q2);
+        const V3 d = P[i] - c;
+        const float dd = dot(d, d);
+        if (dd < best) { best = dd; cp = P[i]; cq = c; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const V3 c = closest_on_triangle(Q[i], P[0], p1, p2);
+        const V3 d = Q[i] - c;
+        const float dd = dot(d, d);
+        if (dd < best) { best = dd; cp = c; cq = Q[i]; }
+    }
+    // interpenetrating triangles (an edge of one through the interior of the other) have no zero among the 15 candidates
+    if (best > 0.f && tri_contact_normals(p1, p2, q0, q1, q2, 0.f) && tri_contact_edges(p1, p2, q0, q1, q2, 0.f)) { best = 0.f; cq = cp; }
+    return best;
+}
+
+// lower bound of the squared distance between box A {ca, ea} (identity frame) and box B {cb, eb} placed by (R, t)
+__device__ __forceinline__ float box_gap2(const float* __restrict__ R, const float* __restrict__ t, float4 ac, float4 ae, float4 bc, float4 be)
+{
+    const float slack = 2e-6f;
+    const float T0 = fmaf(R[0], bc.x, fmaf(R[1], bc.y, fmaf(R[2], bc.z, t[0]))) - ac.x;
+    const float T1 = fmaf(R[3], bc.x, fmaf(R[4], bc.y, fmaf(R[5], bc.z, t[1]))) - ac.y;
+    const float T2 = fmaf(R[6], bc.x, fmaf(R[7], bc.y, fmaf(R[8], bc.z, t[2]))) - ac.z;
+    const float f00 = fabsf(R[0]), f01 = fabsf(R[1]), f02 = fabsf(R[2]);
+    const float f10 = fabsf(R[3]), f11 = fabsf(R[4]), f12 = fabsf(R[5]);
+    const float f20 = fabsf(R[6]), f21 = fabsf(R[7]), f22 = fabsf(R[8]);
+    const float g0 = fmaxf(0.f, fabsf(T0) - (ae.x + be.x * f00 + be.y * f01 + be.z * f02) - slack);
+    const float g1 = fmaxf(0.f, fabsf(T1) - (ae.y + be.x * f10 + be.y * f11 + be.z * f12) - slack);
+    const float g2 = fmaxf(0.f, fabsf(T2) - (ae.z + be.x * f20 + be.y * f21 + be.z * f22) - slack);
+    const float h0 = fmaxf(0.f, fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) - (be.x + ae.x * f00 + ae.y * f10 + ae.z * f20) - slack);
+    const float h1 = fmaxf(0.f, fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) - (be.y + ae.x * f01 + ae.y * f11 + ae.z * f21) - slack);
+    const float h2 = fmaxf(0.f, fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) - (be.z + ae.x * f02 + ae.y * f12 + ae.z * f22) - slack);
+    return fmaxf(g0 * g0 + g1 * g1 + g2 * g2, h0 * h0 + h1 * h1 + h2 * h2);
+}
+
+__device__ __forceinline__ float aabb_gap2(const float4 ac, const float4 ae, const float4 bc, const float4 be)
+{
+    const float g0 = fmaxf(0.f, fabsf(ac.x - bc.x) - (ae.x + be.x));
+    const float g1 = fmaxf(0.f, fabsf(ac.y - bc.y) - (ae.y + be.y));
+    const float g2 = fmaxf(0.f, fabsf(ac.z - bc.z) - (ae.z + be.z));
+    return g0 * g0 + g1 * g1 + g2 * g2;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ DistOut D)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + wib * kDistWarpSmemBytes;
+    float* slot_rt = (float*)wbase;                               // [kNumSlots][24]: B into A, then A into B (unused half kept for layout)
+    int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 24);    // [kNumSlots] reference pair index
+    int32_t* slot_la = slot_pair + kNumSlots;                     // [kNumSlots] plan slot of link a (to place the closest points)
+    uint2* stack = (uint2*)(slot_la + kNumSlots);                 // [kDistStackCap] {nodeA | slot << 26, nodeB}
+    uint32_t* cbuf = (uint32_t*)(stack + kDistStackCap);          // [32] candidate device pair indices
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int ndyn = P.ndyn;
+    const float best_init = D.dist_max > 0.f ? D.dist_max * D.dist_max : 3.0e38f;
+
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&P.counters[0], 1);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= P.n) break;
+        const float* xf = P.xf32 + (size_t)c * ndyn * 12;
+        const float* ab = P.aabb + (size_t)c * ndyn * 8;
+        const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;
+        const int k_begin = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+        const int k_end = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+
+        float best2 = best_init;             // warp-uniform
+        int best_pair = -1, best_la = 0;
+        V3 best_p = v3(0.f, 0.f, 0.f), best_q = best_p;     // closest points in link a's frame (warp-uniform copies)
+
+        auto pair_bound = [&](int k) -> float {
+            const uint32_t pr = __ldg(&P.pairs[k]);
+            const int sa = pr & 0xffff, sb = pr >> 16;
+            const float4* pa = (const float4*)((sa < ndyn ? ab : st_ab) + 8 * sa);
+            const float4* pb = (const float4*)((sb < ndyn ? ab : st_ab) + 8 * sb);
+            return aabb_gap2(pa[0], pa[1], pb[0], pb[1]);
+        };
+
+        // ---- the most promising pair first
+        int first_k = -1;
+        {
+            float lb = 3.0e38f; int kk = -1;
+            for (int k = k_begin + lane; k < k_end; k += 32) { const float b = pair_bound(k); if (b < lb) { lb = b; kk = k; } }
+            const unsigned key = __reduce_min_sync(kFull, __float_as_uint(lb));
+            const unsigned who = __ballot_sync(kFull, __float_as_uint(lb) == key && kk >= 0);
+            if (who) first_k = __shfl_sync(kFull, kk, __ffs(who) - 1);
+        }
+
+        int k0 = k_begin;
+        bool did_first = first_k < 0;
+        while (!did_first || k0 < k_end) {
+            // ---- gather up to 32 root pairs whose AABB bound is still below best2
+            int ncb = 0;
+            if (!did_first) { if (lane == 0) cbuf[0] = (uint32_t)first_k; ncb = 1; did_first = true; }
+            else {
+                while (k0 < k_end && ncb == 0) {
+                    const int k = k0 + lane;
+                    const bool want = k < k_end && k != first_k && pair_bound(k) < best2;
+                    const unsigned m = __ballot_sync(kFull, want);
+                    if (want) cbuf[__popc(m & lt_mask)] = (uint32_t)k;
+                    ncb = __popc(m);
+                    k0 += 32;
+                }
+                if (ncb == 0) break;
+            }
+            __syncwarp();
+            int sp = 0;
+            {
+                bool cand = false;
+                uint32_t ra = 0, rb = 0;
+                if (lane < ncb) {
+                    const uint32_t k = cbuf[lane];
+                    const uint32_t pr = __ldg(&P.pairs[k]);
+                    const int la = pr & 0xffff, lb = pr >> 16;
+                    float A[12], Bx[12], R[9], t[3];
+                    {
+                        const float4* e = la < ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
+                        const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                        A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
+                        A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
+                    }
+                    {
+                        const float4* e = lb < ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
+                        const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                        Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
+                        Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
+                    }
+                    relative_pose(A, Bx, R, t);
+                    float* rt = slot_rt + 24 * lane;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) rt[i] = R[i];
+                    rt[9] = t[0]; rt[10] = t[1]; rt[11] = t[2];
+                    slot_pair[lane] = __ldg(&P.pair_orig[k]);
+                    slot_la[lane] = la;
+                    ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
+                    cand = true;
+                }
+                const unsigned cm = __ballot_sync(kFull, cand);
+                if (cand) stack[__popc(cm & lt_mask)] = make_uint2(ra | ((uint32_t)lane << 26), rb);
+                sp = __popc(cm);
+            }
+            __syncwarp();
+
+            // ---- drain
+            while (sp > 0) {
+                // near the capacity only one item is expanded per iteration (a single path cannot overflow the margin)
+                const int width = sp > kDistStackCap - 160 ? 1 : 32;
+                const int n = sp < width ? sp : width;
+                const bool valid = lane < n;
+                uint2 it = make_uint2(0u, 0u);
+                if (valid) it = stack[sp - 1 - lane];
+                sp -= n;
+                __syncwarp();
+                bool push = false;
+                uint2 o0 = make_uint2(0u, 0u), o1 = o0;
+                float d2 = 3.0e38f;
+                V3 cp = v3(0.f, 0.f, 0.f), cq = cp;
+                const uint32_t s = it.x >> 26;
+                if (valid) {
+                    const uint32_t x = it.x & 0x3ffffffu, y = it.y;
+                    const float4 a0 = __ldg(&P.nodes[2 * x]), a1 = __ldg(&P.nodes[2 * x + 1]);
+                    const float4 b0 = __ldg(&P.nodes[2 * y]), b1 = __ldg(&P.nodes[2 * y + 1]);
+                    const float* rt = slot_rt + 24 * s;
+                    float R[9], t[3];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) R[k] = rt[k];
+                    t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
+                    if (box_gap2(R, t, a0, a1, b0, b1) < best2) {
+                        const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+                        if (la < 0 && lb < 0) {
+                            const float4* ta = P.tris + 3 * (size_t)(~la);
+                            const float4 v0 = __ldg(ta);
+                            V3 p1, p2, q0, q1, q2;
+                            load_tri_pair(P.tris, rt, (uint32_t)(~la), (uint32_t)(~lb), p1, p2, q0, q1, q2);
+                            d2 = tri_tri_dist2(p1, p2, q0, q1, q2, cp, cq);
+                            const V3 org = v3(v0.x, v0.y, v0.z);
+                            cp = cp + org; cq = cq + org;
+                        } else {
+                            push = true;
+                            if (lb < 0 || (la >= 0 && a1.w > b1.w)) {
+                                o0 = make_uint2((uint32_t)la | (s << 26), y);
+                                o1 = make_uint2((uint32_t)(la + 1) | (s << 26), y);
+                            } else {
+                                o0 = make_uint2(x | (s << 26), (uint32_t)lb);
+                                o1 = make_uint2(x | (s << 26), (uint32_t)(lb + 1));
+                            }
+                        }
+                    }
+                }
+                // new minimum?
+                const unsigned key = __reduce_min_sync(kFull, __float_as_uint(d2));
+                if (__uint_as_float(key) < best2) {
+                    const unsigned who = __ballot_sync(kFull, __float_as_uint(d2) == key);
+                    const int src = __ffs(who) - 1;
+                    best2 = __uint_as_float(key);
+                    const uint32_t bs = __shfl_sync(kFull, s, src);
+                    best_pair = slot_pair[bs];
+                    best_la = slot_la[bs];
+                    best_p = v3(__shfl_sync(kFull, cp.x, src), __shfl_sync(kFull, cp.y, src), __shfl_sync(kFull, cp.z, src));
+                    best_q = v3(__shfl_sync(kFull, cq.x, src), __shfl_sync(kFull, cq.y, src), __shfl_sync(kFull, cq.z, src));
+                }
+                const unsigned pm = __ballot_sync(kFull, push);
+                if (push) {
+                    const int at = sp + 2 * __popc(pm & lt_mask);
+                    stack[at] = o0; stack[at + 1] = o1;
+                }
+                sp += 2 * __popc(pm);
+                __syncwarp();
+                if (best2 == 0.f) sp = 0;          // touching / penetrating: nothing can be smaller
+            }
+            if (best2 == 0.f) break;
+        }
+
+        if (lane == 0) {
+            double dist = best_pair >= 0 ? (double)sqrtf(best2) : (D.dist_max > 0.f ? (double)D.dist_max : 1e30);
+            D.min_distance[c] = dist;
+            if (D.min_pair) D.min_pair[c] = best_pair;
+            if (D.points) {
+                double* o = D.points + 6 * (size_t)c;
+                if (best_pair >= 0) {
+                    const float* A = best_la < ndyn ? xf + 12 * best_la : P.st_xf + 12 * (size_t)(best_la - ndyn);
+                    const V3 pts[2] = {best_p, best_q};
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        o[3 * k + 0] = (double)(A[0] * pts[k].x + A[1] * pts[k].y + A[2] * pts[k].z + A[9]) + P.center[0];
+                        o[3 * k + 1] = (double)(A[3] * pts[k].x + A[4] * pts[k].y + A[5] * pts[k].z + A[10]) + P.center[1];
+                        o[3 * k + 2] = (double)(A[6] * pts[k].x + A[7] * pts[k].y + A[8] * pts[k].z + A[11]) + P.center[2];
+                    }
+                } else {
+                    for (int k = 0; k < 6; ++k) o[k] = 0.0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace ccdev

@@ -20,6 +20,7 @@
 
 #include "../../include/cudacollision.h"
 #include "cc_device.cuh"
+#include "cc_distance.cuh"
 
 namespace {
 
@@ -272,6 +273,11 @@ struct cc_query {
     std::vector<uint8_t> pair_live;          // [npairs] 0: can never collide (disabled / no mesh), kept for indexing only
     int nenv_total = 0, nself_total = 0;
     Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
+    Plan dist;                               // distance queries in FK mode: every live pair, nothing hoisted (built on first use)
+    bool dist_ready = false;
+    std::vector<int> p_full;                 // indices of the live pairs
+    DevBuf<double> d_dist, d_dpts;
+    DevBuf<int32_t> d_dpair;
     bool has_fk = false;
     std::vector<ccdev::FkStep> steps;       // every joint, depth-first order
     // per-chunk scratch (grown on demand, shared by the plans)
@@ -327,12 +333,10 @@ struct HostIO {
     double* fk = nullptr;
 };
 
-int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
-           int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st, const HostIO* hio = nullptr)
+// Everything of ccdev::Params that depends on the query and the plan only (io pointers and scratch are set per chunk).
+void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev::Params& P)
 {
     cc_scene* S = Q->scene;
-    if (n <= 0) return CC_OK;
-    ccdev::Params P;
     memset(&P, 0, sizeof(P));
     P.nodes = S->d_nodes.p; P.tris = S->d_tris.p;
     P.slot_root = pl.d_slot_root.p; P.st_xf = pl.d_st_xf.p; P.st_aabb = pl.d_st_aabb.p; P.link_box = pl.d_link_box.p;
@@ -352,6 +356,16 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     P.err_flag = S->d_err.p;
     P.stats = S->d_stats.p;
     P.spill_cap = 2048;
+    P.split = 1;
+}
+
+int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
+           int32_t* d_fe, int32_t* d_fs, uint32_t* d_mask, double* d_fk, cudaStream_t st, const HostIO* hio = nullptr)
+{
+    cc_scene* S = Q->scene;
+    if (n <= 0) return CC_OK;
+    ccdev::Params P;
+    init_params(Q, pl, use_hoisted, flags, P);
     const bool fk_only = (flags & ccdev::kFlagFkOnly) != 0;
     const int row_doubles = (flags & ccdev::kFlagPoseMode) ? Q->nq * 8 : Q->ncols;
 
@@ -495,6 +509,64 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     CC_CUDA(cudaEventRecord(S->ev1, st));
     S->ev_pending = true;
     if (!fk_only) S->stats.configs += (uint64_t)n;
+    return CC_OK;
+}
+
+// Minimum separation of n configurations (host buffers in and out, one stream, synchronous): FK kernel, then the
+// branch-and-bound distance kernel of cc_distance.cuh, chunk by chunk.
+int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h_in, int n, int flags, double max_distance,
+                    double* h_dist, int32_t* h_pair, double* h_pts)
+{
+    cc_scene* S = Q->scene;
+    if (n <= 0) return CC_OK;
+    CC_CUDA(cudaSetDevice(S->device));
+    ccdev::Params P;
+    init_params(Q, pl, false, (flags & (CC_BATCH_ENV | CC_BATCH_SELF)) | (pose_mode ? ccdev::kFlagPoseMode : 0), P);
+    const int row_doubles = pose_mode ? Q->nq * 8 : Q->ncols;
+    const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
+    int chunk = (int)std::min<size_t>(65536, std::max<size_t>(1024, ((size_t)1 << 29) / per_cfg));
+    chunk = std::min(chunk, (n + 127) / 128 * 128);
+    int rc = ensure_scratch(Q, pl, chunk, 1);
+    if (rc != CC_OK) return rc;
+    P.cap = chunk;
+    CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, (size_t)chunk * row_doubles)));
+    CC_CUDA(Q->d_dist.reserve(chunk)); CC_CUDA(Q->d_dpair.reserve(chunk)); CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
+    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
+    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
+    if (fk_smem > 48 * 1024)
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+    const size_t d_smem = ccdev::kDistWarpSmemBytes * ccdev::kWarpsPerBlock;
+    static int dist_blocks_per_sm = 0;
+    if (dist_blocks_per_sm == 0) {
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
+        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dist_blocks_per_sm, ccdev::cc_distance_kernel, ccdev::kWarpsPerBlock * 32, d_smem));
+        if (dist_blocks_per_sm < 1) { dist_blocks_per_sm = 0; return fail(CC_ERR_CUDA, "distance kernel does not fit on an SM"); }
+    }
+    ccdev::DistOut D;
+    D.min_distance = Q->d_dist.p; D.min_pair = Q->d_dpair.p; D.points = h_pts ? Q->d_dpts.p : nullptr;
+    D.dist_max = max_distance > 0 ? (float)max_distance : 0.f;
+    cudaStream_t st = 0;
+    for (int off = 0; off < n; off += chunk) {
+        const int m = std::min(chunk, n - off);
+        if (row_doubles > 0)
+            CC_CUDA(cudaMemcpyAsync(Q->d_q.p, h_in + (size_t)off * row_doubles, (size_t)m * row_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+        P.n = m;
+        P.q = Q->d_q.p;
+        P.xf32 = Q->d_xf32[0].p; P.aabb = Q->d_aabb[0].p; P.fksave = Q->d_fksave[0].p; P.counters = Q->d_counters[0].p;
+        CC_CUDA(cudaMemsetAsync(Q->d_counters[0].p, 0, sizeof(int32_t), st));
+        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
+        CC_CUDA(cudaGetLastError());
+        int grid = dist_blocks_per_sm * S->num_sms;
+        const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
+        if (grid > need) grid = need;
+        ccdev::cc_distance_kernel<<<grid, ccdev::kWarpsPerBlock * 32, d_smem, st>>>(P, D);
+        CC_CUDA(cudaGetLastError());
+        S->stats.launches += 2;
+        CC_CUDA(cudaMemcpyAsync(h_dist + off, Q->d_dist.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h_pair) CC_CUDA(cudaMemcpyAsync(h_pair + off, Q->d_dpair.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (h_pts) CC_CUDA(cudaMemcpyAsync(h_pts + (size_t)off * 6, Q->d_dpts.p, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaStreamSynchronize(st));
+    }
     return CC_OK;
 }
 
@@ -990,6 +1062,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
         if (Q->quads[4 * p + 3] == 1) { const int b = Q->quads[4 * p + 2]; if (moves[b]) main_dynamic[b] = 1; }
     }
     CC_CUDA(cudaSetDevice(S->device));
+    Q->p_full = p_full;
     int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
     if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
@@ -1301,6 +1374,31 @@ int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_T8)
     if (!q || n < 0 || !out_T8 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics");
     return run_host(q, dof_values, (size_t)n * q->ncols, n, ccdev::kFlagFkOnly, false, nullptr, nullptr, nullptr, nullptr, out_T8);
+}
+
+int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance, double* min_distance,
+                      int32_t* min_pair, double* closest_points)
+{
+    if (!q || n < 0 || !min_distance || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_distance_poses");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    if (!q->dist_ready) {
+        CC_CUDA(cudaSetDevice(q->scene->device));
+        std::vector<uint8_t> all_dynamic(q->nq, 1);
+        int rc = build_plan(q, q->dist, q->p_full, all_dynamic, true);
+        if (rc != CC_OK) return rc;
+        CC_CUDA(cudaDeviceSynchronize());
+        q->dist_ready = true;
+    }
+    return launch_distance(q, q->dist, false, dof_values, n, flags, max_distance, min_distance, min_pair, closest_points);
+}
+
+int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double max_distance, double* min_distance,
+                      int32_t* min_pair, double* closest_points)
+{
+    if (!q || n < 0 || !min_distance || (n > 0 && !T8)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    return launch_distance(q, q->full, true, T8, n, flags, max_distance, min_distance, min_pair, closest_points);
 }
 
 int cc_host_alloc(size_t bytes, void** out)

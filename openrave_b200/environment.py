@@ -27,6 +27,7 @@ class CollisionReport(object):
         self.minDistance = 1e20
         self.numCols = 0
         self.nNumValidCollisions = 0
+        self.contacts = []            # CO_Distance: [(pos, norm, depth)] of the closest pair (collisionPQP.h:633-647)
 
     def AddLinkCollision(self, link1, link2):
         """collisionchecker.cpp:577-596 — duplicates are not appended twice."""

@@ -77,6 +77,7 @@ def _load(kind):
     lib.orc_check_link_pairs.argtypes = [vp, ci, vp, vp, ci, vp]
     lib.orc_check_batch.argtypes = [vp, ci, vp, ci, ctypes.POINTER(OrcOptions), vp, ci, vp, vp, vp, vp, vp, vp, vp,
                                     ctypes.c_int64, vp, vp]
+    lib.orc_distance_batch.argtypes = [vp, ci, vp, ci, vp, vp, ci, cd, vp, vp]
     lib.orc_time_batch.restype = cd
     lib.orc_time_batch.argtypes = [vp, ci, vp, ci, ci, ci, vp, ci, vp]
     lib.orc_collide_pair.restype = ctypes.c_int64
@@ -240,6 +241,28 @@ class OracleChecker(object):
                                  _ptr(ep) if report else None, cap, ctypes.addressof(nep), _ptr(fk))
         return dict(verdict=verdict, first_env=fe, first_self=fs, counters=cnt, penetration=pen, near=near,
                     env_pairs=ep[:min(nep.value, cap)] if report else None, fk=fk)
+
+    def distance_batch(self, body, q, active=None, flags=BATCH_ENV | BATCH_SELF, max_distance=0.0, poses=None):
+        """Exact minimum separation per configuration (PQP_Distance with both tolerances 0 over every visited pair):
+        dict(distance [n], pair [n, 3] {query link, other body, other link})."""
+        self._sync()
+        bid = self._sync_kinematics(body)
+        if active is None:
+            active = body.GetActiveDOFIndices() if body.is_robot else list(range(body.GetDOF()))
+        act = np.array(active, dtype=np.int32)
+        opt = OrcOptions(self._options, flags, 0, 0, 0.0, 0, 0)
+        if poses is not None:
+            q = np.ascontiguousarray(poses, dtype=np.float64)
+            n = q.shape[0]
+            opt.pose_mode = 1
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active))
+            n = q.shape[0]
+        dist = np.zeros(n, dtype=np.float64)
+        pair = np.zeros((n, 3), dtype=np.int32)
+        self.lib.orc_distance_batch(self.scene, bid, _ptr(act), len(active), ctypes.byref(opt), _ptr(q), n,
+                                    float(max_distance), _ptr(dist), _ptr(pair))
+        return dict(distance=dist, pair=pair)
 
     def time_batch(self, body, q, active=None, flags=BATCH_ENV | BATCH_SELF):
         self._sync()

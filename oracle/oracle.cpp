@@ -843,6 +843,93 @@ static bool links_within(const Xf& x1, const LinkModel& l1, const Xf& x2, const 
 #endif
 }
 
+// Exact minimum distance of two link models (PQP_Distance with rel_err = abs_err = 0, pqp/PQP.cpp:663-945): in the restated
+// build a branch and bound over the two OBB trees — the separation of two boxes along A's and along B's face axes bounds
+// their distance from below, the nearer child is descended first (DistanceRecurse's rule), leaves run the exact triangle
+// distance above.  `best` carries the running minimum in and out.
+#ifndef ORACLE_USE_REF_PQP
+static double obb_gap(const Mat R, const double T[3], const double a[3], const double b[3])
+{
+    double ga = 0, gb = 0;
+    for (int i = 0; i < 3; ++i) {
+        double g = fabs(T[i]) - (a[i] + b[0] * fabs(R[i][0]) + b[1] * fabs(R[i][1]) + b[2] * fabs(R[i][2]));
+        if (g > 0) ga += g * g;
+        double tb = T[0] * R[0][i] + T[1] * R[1][i] + T[2] * R[2][i];
+        g = fabs(tb) - (b[i] + a[0] * fabs(R[0][i]) + a[1] * fabs(R[1][i]) + a[2] * fabs(R[2][i]));
+        if (g > 0) gb += g * g;
+    }
+    return sqrt(ga > gb ? ga : gb);
+}
+
+static void distance_descend(const Model& m1, const Model& m2, const Mat Rrel, const double Trel[3],
+                             const Mat R, const double T[3], int b1, int b2, double& best)
+{
+    const Node& n1 = m1.nodes[b1];
+    const Node& n2 = m2.nodes[b2];
+    bool l1 = n1.leaf(), l2 = n2.leaf();
+    if (l1 && l2) {
+        const Tri& t1 = m1.tris[-n1.first_child - 1];
+        const Tri& t2 = m2.tris[-n2.first_child - 1];
+        double q[3][3];
+        for (int v = 0; v < 3; ++v) mat_vec_add(q[v], Rrel, t2.p[v], Trel);
+        double d = tri_tri_dist(t1.p, q);
+        if (d < best) best = d;
+        return;
+    }
+    Mat Rc[2]; double Tc[2][3], Tt[3], lb[2];
+    int ia[2], ib[2];
+    if (l2 || (!l1 && (n1.size > n2.size))) {
+        int c1 = n1.first_child;
+        for (int k = 0; k < 2; ++k) {
+            const Node& ch = m1.nodes[c1 + k];
+            mat_tmul(Rc[k], ch.R, R);
+            Tt[0] = T[0] - ch.To[0]; Tt[1] = T[1] - ch.To[1]; Tt[2] = T[2] - ch.To[2];
+            mat_tvec(Tc[k], ch.R, Tt);
+            ia[k] = c1 + k; ib[k] = b2;
+            lb[k] = obb_gap(Rc[k], Tc[k], ch.d, n2.d);
+        }
+    } else {
+        int c1 = n2.first_child;
+        for (int k = 0; k < 2; ++k) {
+            const Node& ch = m2.nodes[c1 + k];
+            mat_mul(Rc[k], R, ch.R);
+            mat_vec_add(Tc[k], R, ch.To, T);
+            ia[k] = b1; ib[k] = c1 + k;
+            lb[k] = obb_gap(Rc[k], Tc[k], n1.d, ch.d);
+        }
+    }
+    const int first = lb[1] < lb[0] ? 1 : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int k = pass == 0 ? first : 1 - first;
+        if (lb[k] < best) distance_descend(m1, m2, Rrel, Trel, Rc[k], Tc[k], ia[k], ib[k], best);
+    }
+}
+#endif
+
+static double links_distance(const Xf& x1, const LinkModel& l1, const Xf& x2, const LinkModel& l2, double best)
+{
+    double R1[3][3], T1[3], R2[3][3], T2[3];
+    xf_to_RT(x1, R1, T1);
+    xf_to_RT(x2, R2, T2);
+#ifdef ORACLE_USE_REF_PQP
+    PQP_DistanceResult res;
+    PQP_Distance(&res, R1, T1, l1.pm, R2, T2, l2.pm, 0.0, 0.0);
+    return res.Distance() < best ? res.Distance() : best;
+#else
+    Mat Rrel; double Trel[3], Tt[3] = {T2[0] - T1[0], T2[1] - T1[1], T2[2] - T1[2]};
+    mat_tmul(Rrel, R1, R2);
+    mat_tvec(Trel, R1, Tt);
+    Mat Rtemp, R; double T[3];
+    mat_mul(Rtemp, Rrel, l2.m.nodes[0].R);
+    mat_tmul(R, l1.m.nodes[0].R, Rtemp);
+    mat_vec_add(Tt, Rrel, l2.m.nodes[0].To, Trel);
+    Tt[0] -= l1.m.nodes[0].To[0]; Tt[1] -= l1.m.nodes[0].To[1]; Tt[2] -= l1.m.nodes[0].To[2];
+    mat_tvec(T, l1.m.nodes[0].R, Tt);
+    if (obb_gap(R, T, l1.m.nodes[0].d, l2.m.nodes[0].d) < best) distance_descend(l1.m, l2.m, Rrel, Trel, R, T, 0, 0, best);
+    return best;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Scene: bodies in environment order, links with models and current transforms, kinematics
 // ------------------------------------------------------------------------------------------------
@@ -1274,6 +1361,79 @@ int orc_check_batch(void* sp, int body, const int32_t* active, int nactive, cons
         if (near_contact) near_contact[c] = near ? 1 : 0;
     }
     if (n_env_pairs) *n_env_pairs = nout;
+    return 0;
+}
+
+// CO_Distance over a batch (collisionPQP.h:622-648 applied to every pair the query visits): the exact minimum separation per
+// configuration over the env pairs (flags & 1) and the self pairs (flags & 2), and the pair attaining it as
+// {query link, other body, other link} (other body = the query body for self pairs).  Grabbed bodies follow the same
+// query-link layout as orc_check_batch.
+int orc_distance_batch(void* sp, int body, const int32_t* active, int nactive, const OrcOptions* opt,
+                       const double* q, int n, double max_distance, double* min_distance, int32_t* min_pair3)
+{
+    Scene* s = (Scene*)sp;
+    Body* b = s->bodies[body];
+    const size_t nl = b->links.size();
+    std::vector<uint8_t> act;
+    active_links(*b, active, nactive, opt->options, act);
+    std::vector<int32_t> spairs;
+    self_pairs(*b, active, nactive, opt->options, spairs);
+    std::vector<double> vals(b->dofvals);
+    std::vector<Xf> xf;
+    std::vector<Body*> qb; std::vector<int> ql; std::vector<size_t> gbase(b->grabs.size(), 0);
+    for (size_t i = 0; i < nl; ++i) { qb.push_back(b); ql.push_back((int)i); }
+    for (size_t g = 0; g < b->grabs.size(); ++g) {
+        gbase[g] = qb.size();
+        Body* G = s->bodies[b->grabs[g].body];
+        for (size_t k = 0; k < G->links.size(); ++k) { qb.push_back(G); ql.push_back((int)k); }
+    }
+    const size_t nle = qb.size();
+    for (int c = 0; c < n; ++c) {
+        if (opt->pose_mode) {
+            xf.resize(nle);
+            const double* T8 = q + (size_t)c * nle * 8;
+            for (size_t i = 0; i < nle; ++i) { memcpy(xf[i].q, T8 + 8 * i, 32); memcpy(xf[i].t, T8 + 8 * i + 4, 24); }
+        } else {
+            for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * nactive + a];
+            forward_kinematics(*b, &vals[0], b->xf[0], xf);
+            xf.resize(nle);
+            for (size_t g = 0; g < b->grabs.size(); ++g)
+                for (size_t k = 0; k < b->grabs[g].rel.size(); ++k) xf[gbase[g] + k] = xf_mul(xf[b->grabs[g].link], b->grabs[g].rel[k]);
+        }
+        double best = max_distance > 0 ? max_distance : 1e30;
+        int bp[3] = {-1, -1, -1};
+        if (opt->flags & CC_BATCH_ENV) {
+            for (int att = -1; att < (int)b->grabs.size(); ++att) {
+                Body* a1 = att < 0 ? b : s->bodies[b->grabs[att].body];
+                const size_t base = att < 0 ? 0 : gbase[att];
+                for (size_t ob = 0; ob < s->bodies.size(); ++ob) {
+                    Body* o = s->bodies[ob];
+                    if (o->removed) continue;
+                    bool attached = is_attached(*b, (int)ob);
+                    for (size_t g = 0; g < b->grabs.size() && !attached; ++g)
+                        attached = b->grabs[g].body == (int)ob || is_attached(*s->bodies[b->grabs[g].body], (int)ob);
+                    if (attached) continue;
+                    for (size_t i = 0; i < a1->links.size(); ++i)
+                        for (size_t j = 0; j < o->links.size(); ++j) {
+                            if (!a1->enabled[i] || !o->enabled[j] || (att < 0 && !act[i])) continue;
+                            if (!a1->links[i]->valid || !o->links[j]->valid) continue;
+                            double d = links_distance(xf[base + i], *a1->links[i], o->xf[j], *o->links[j], best);
+                            if (d < best) { best = d; bp[0] = (int)(base + i); bp[1] = (int)ob; bp[2] = (int)j; }
+                        }
+                }
+            }
+        }
+        if (opt->flags & CC_BATCH_SELF) {
+            for (size_t k = 0; k < spairs.size(); ++k) {
+                int l0 = spairs[k] & 0xffff, l1 = (spairs[k] >> 16) & 0xffff;
+                if (!act[l0] || !act[l1] || !b->links[l0]->valid || !b->links[l1]->valid) continue;
+                double d = links_distance(xf[l0], *b->links[l0], xf[l1], *b->links[l1], best);
+                if (d < best) { best = d; bp[0] = l0; bp[1] = body; bp[2] = l1; }
+            }
+        }
+        min_distance[c] = best;
+        if (min_pair3) { min_pair3[3 * c] = bp[0]; min_pair3[3 * c + 1] = bp[1]; min_pair3[3 * c + 2] = bp[2]; }
+    }
     return 0;
 }
 
