@@ -57,6 +57,12 @@ PLAN_WORKLOADS = {
                               "shortcuts + 100 linearsmoother iterations; all problems advance in lockstep, every Extend ray / shortcut of "
                               "every live problem goes through one cc_check_batch call per round (BASELINE.json configs[2])"),
 }
+# CO_Distance: minimum separation per configuration
+DIST_WORKLOADS = {
+    "wam_lab1_distance_100k": ("lab1", 100000, 1, "arm",
+                               "Barrett WAM in data/lab1.env.xml, CO_ActiveDOFs on the 7 arm DOFs: minimum separation (env + self pairs) of "
+                               "100k uniform-random arm configurations, exact (PQP_Distance with rel_err = abs_err = 0) in FP32"),
+}
 DEFAULT_WORKLOAD = "pr2_pr2test1_1m"
 METRIC = "collision-checked configs/sec (FK+env+self)"
 UNIT = "configs/s"
@@ -205,6 +211,98 @@ def _ref_worker_init(workload, kind):
 def _ref_worker_run(a):
     secs, _ = _REF_STATE["orc"].time_batch(_REF_STATE["robot"], a[0])
     return secs
+
+
+def run_distance(args):
+    """distance-checked configs/s through cc_distance_batch (host buffers in and out: this entry has no device-pointer
+    flavour yet, so `value` and `e2e` are the same measurement)."""
+    import torch
+    from openrave_b200.checker import CO_ActiveDOFs, CudaCollisionChecker
+    scene, n, seed, manip, desc = DIST_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from openrave_b200.environment import Environment
+    env = Environment()
+    env.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
+    robot = env.GetRobots()[0]
+    arm = robot.GetActiveManipulator().GetArmIndices()
+    robot.SetActiveDOFs(arm)
+    cc = CudaCollisionChecker(env, local_rank)
+    env.SetCollisionChecker(cc)
+    cc.SetCollisionOptions(CO_ActiveDOFs)
+    q = sample(robot, n, seed + 1000 * rank)
+    bq = cc.bind(robot)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        d, pair, pts = bq.distance(q)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    launches0 = cc.GetStatistics()["launches"]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d, pair, pts = bq.distance(q)
+    secs = (time.perf_counter() - t0) / args.steps
+    launches = cc.GetStatistics()["launches"] - launches0
+    if world > 1:
+        t = torch.tensor([secs], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank == 0:
+        value = world * n / secs
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d_apx, _, _ = bq.distance(q, rel_err=200.0, abs_err=0.001)       # pqprave's own tolerances (collisionPQP.h:48-49)
+        secs_apx = (time.perf_counter() - t0) / args.steps
+        line = {"metric": "distance-checked configs/sec (FK + min separation over env+self pairs)", "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": 1000 * secs, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": desc, "configs_per_step_per_gpu": n, "ndof": len(arm),
+                           "pairs_env": bq.info.npairs_env, "pairs_self": bq.info.npairs_self,
+                           "mean_distance": float(d.mean()), "zero_fraction": float((d == 0).mean()),
+                           "configs_per_s_with_pqprave_tolerances": world * n / secs_apx,
+                           "mean_distance_with_pqprave_tolerances": float(d_apx.mean()),
+                           "timing": "host wall clock around cc_distance_batch (H2D + FK kernel + distance kernel + D2H), max over ranks",
+                           "l2": "inputs larger than nothing: scene L2-resident by design (5 MB); q/results stream through HBM"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n * len(arm) * 8), "d2h_bytes_per_step": int(n * 60)},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": None}
+        if not args.no_cpu_baseline:
+            import oracle
+            m = 2000
+            base = {}
+            for kind in (["reference"] if oracle.available("reference") else []) + ["port"]:
+                env2 = Environment()
+                env2.Load(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".npz"))
+                r2 = env2.GetRobots()[0]
+                r2.SetActiveDOFs(arm)
+                orc = oracle.OracleChecker(env2, kind)
+                env2.SetCollisionChecker(orc)
+                orc.SetCollisionOptions(CO_ActiveDOFs)
+                mm = 200 if kind == "reference" else m
+                orc.distance_batch(r2, q[:4], active=arm)
+                t0 = time.perf_counter()
+                ref = orc.distance_batch(r2, q[:mm], active=arm)
+                dt = time.perf_counter() - t0
+                base[kind] = mm / dt
+                assert np.abs(ref["distance"] - d[:mm]).max() < 2e-5
+            kind = "reference" if "reference" in base else "port"
+            line["cpu_baseline"] = {"value": base[kind], "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": "first %d configs, 1 thread; 'reference' = unmodified PQP_Distance(rel_err=abs_err=0) on every "
+                                              "visited pair, 'port' = the oracle's restated branch and bound carrying the running minimum "
+                                              "across pairs (%.0f configs/s)" % (200 if kind == "reference" else m, base["port"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def plan_problems(scene, nproblems, seed, rank, checker_factory):
@@ -372,10 +470,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(PLAN_WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(PLAN_WORKLOADS) + sorted(DIST_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload in DIST_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "distance workload: the CPU arm is reported inline as cpu_baseline"}))
+            return
+        run_distance(args)
+        return
     if args.workload in PLAN_WORKLOADS:
         (run_birrt_reference if args.impl == "reference" else run_birrt)(args)
         return

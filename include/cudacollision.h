@@ -199,16 +199,18 @@ int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_transf
  * over the query's env pairs (CC_BATCH_ENV) and self pairs (CC_BATCH_SELF), 0 when some pair touches or penetrates.
  *   max_distance      search radius in metres (pairs farther apart are not refined; the result is then max_distance),
  *                     <= 0: unbounded
+ *   rel_err, abs_err  PQP_Distance's tolerances (pqp/PQP.cpp:717-721): 0, 0 = exact; with them the result r obeys
+ *                     exact <= r <= max(exact + abs_err, exact * (1 + rel_err)) and the search visits far fewer boxes
+ *                     (pqprave itself runs with 200 and 0.001, collisionPQP.h:48-49)
  *   min_distance[n]   metres (1e30 when the query has no pair at all)
  *   min_pair[n]       pair index (cc_query_get_pairs) attaining it, -1 when none; may be NULL
  *   closest_points    [n][6] world coordinates: the point on the query link, the point on the other link; may be NULL
- * The value is the exact minimum evaluated in FP32 (a few 1e-6 m), i.e. PQP_Distance with rel_err = abs_err = 0; pqprave's
- * own call uses rel_err 200 / abs_err 0.001 (collisionPQP.h:48-49) and returns an upper estimate of this number. */
-int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance,
-                      double* min_distance, int32_t* min_pair, double* closest_points);
+ * With both tolerances 0 the value is the exact minimum evaluated in FP32 (a few 1e-6 m). */
+int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance, double rel_err,
+                      double abs_err, double* min_distance, int32_t* min_pair, double* closest_points);
 /* Same for given link transforms [n][nlinks][8] (single-state queries: CheckCollision(body, report) with CO_Distance). */
-int cc_distance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double max_distance,
-                      double* min_distance, int32_t* min_pair, double* closest_points);
+int cc_distance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double max_distance, double rel_err,
+                      double abs_err, double* min_distance, int32_t* min_pair, double* closest_points);
 
 /* Page-locked host buffers for the host-buffer entry points (cc_check_batch, cc_check_poses, cc_fk_batch).  Those calls
  * cut a big batch into chunks and copy each chunk's inputs / results on the chunk's own stream; with buffers from

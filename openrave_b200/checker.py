@@ -88,8 +88,8 @@ def load_library():
     lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
-    lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, vp, vp, vp]
-    lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, vp, vp, vp]
+    lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
+    lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
     lib.cc_query_trace_work.argtypes = [vp, ci]
     lib.cc_query_get_work_trace.argtypes = [vp, vp, ci]
@@ -207,7 +207,8 @@ class BoundQuery(object):
         self.checker._ck(self.lib.cc_check_poses(self.handle, _ptr(T8), n, flags, _ptr(verdict), _ptr(fe), _ptr(fs), _ptr(mask)))
         return verdict, fe, fs, mask
 
-    def distance(self, q=None, flags=BATCH_ENV | BATCH_SELF, max_distance=0.0, poses=None, want_points=True):
+    def distance(self, q=None, flags=BATCH_ENV | BATCH_SELF, max_distance=0.0, poses=None, want_points=True, rel_err=0.0,
+                 abs_err=0.0):
         """CO_Distance for n configurations (or n sets of link transforms): (distance [n], pair index [n], points [n, 6])."""
         if poses is not None:
             a = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
@@ -219,7 +220,8 @@ class BoundQuery(object):
         dist = np.zeros(n, dtype=np.float64)
         pair = np.zeros(n, dtype=np.int32)
         pts = np.zeros((n, 6), dtype=np.float64) if want_points else None
-        self.checker._ck(fn(self.handle, _ptr(a), n, flags, float(max_distance), _ptr(dist), _ptr(pair), _ptr(pts)))
+        self.checker._ck(fn(self.handle, _ptr(a), n, flags, float(max_distance), float(rel_err), float(abs_err), _ptr(dist),
+                            _ptr(pair), _ptr(pts)))
         return dist, pair, pts
 
     def decode_pair(self, idx):
@@ -459,11 +461,11 @@ class CudaCollisionChecker(object):
         return dict(verdict=verdict, first_env=bq.decode_env(fe), first_self=bq.decode_self(fs), mask=mask, query=bq,
                     first_env_index=fe, first_self_index=fs)
 
-    def DistanceBatch(self, robot, q, flags=BATCH_ENV | BATCH_SELF, active=None, max_distance=0.0):
+    def DistanceBatch(self, robot, q, flags=BATCH_ENV | BATCH_SELF, active=None, max_distance=0.0, rel_err=0.0, abs_err=0.0):
         """Minimum separation of N configurations: dict(distance [n], pair [n,3] {query link, other body id, other link},
         points [n,6] world closest points)."""
         bq = self.bind(robot, active)
-        dist, pair, pts = bq.distance(q, flags, max_distance)
+        dist, pair, pts = bq.distance(q, flags, max_distance, rel_err=rel_err, abs_err=abs_err)
         return dict(distance=dist, pair=bq.decode_pair(pair), pair_index=pair, points=pts, query=bq)
 
     def _fill_distance(self, bq, body, flags, report):

@@ -4,8 +4,9 @@
 // visits and keeps the smallest result together with the two closest points (plugins/pqprave/collisionPQP.h:622-648;
 // PQP_Distance / DistanceRecurse plugins/pqprave/pqp/PQP.cpp:663-945, TriDist plugins/pqprave/pqp/TriDist.cpp).  pqprave calls it
 // with rel_err = 200, abs_err = 0.001 (collisionPQP.h:48-49): an approximate search whose answer depends on the RSS tree and
-// the visiting order.  This kernel computes the EXACT minimum (what PQP_Distance returns with both tolerances 0) in FP32:
-// |result - exact| is a few 1e-6 m for metre-sized scenes, and result <= the reference's approximate answer + that error.
+// the visiting order.  With rel_err = abs_err = 0 this kernel computes the EXACT minimum (what PQP_Distance returns with both
+// tolerances 0) in FP32: |result - exact| is a few 1e-6 m for metre-sized scenes.  Non-zero tolerances apply PQP's pruning rule
+// (pqp/PQP.cpp:717-721) to the running minimum, so the result r obeys exact <= r <= max(exact + abs_err, exact * (1 + rel_err)).
 //
 // One warp per configuration (persistent, work counter), branch and bound over the dual AABB trees of all link pairs at once:
 //   1. every pair's world-AABB gap (from the FK kernel's boxes) gives a lower bound; the pair with the smallest bound is
@@ -31,6 +32,9 @@ struct DistOut {
     int32_t* min_pair;          // [n] reference-order pair index attaining it, -1 when none
     double* points;             // [n][6] closest points in world coordinates (on the query link, on the other link), or NULL
     float dist_max;             // search radius, <= 0: unbounded
+    // PQP_Distance's tolerances (pqp/PQP.cpp:717-721, 776): a box pair is skipped when its bound d satisfies
+    // d + abs_err >= best or d * (1 + rel_err) >= best, so the result r obeys exact <= r <= max(exact + abs_err, exact * (1 + rel_err))
+    float rel_err, abs_err;
 };
 
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -162,6 +166,8 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
     const unsigned lt_mask = (1u << lane) - 1u;
     const int ndyn = P.ndyn;
     const float best_init = D.dist_max > 0.f ? D.dist_max * D.dist_max : 3.0e38f;
+    const bool approx = D.rel_err > 0.f || D.abs_err > 0.f;
+    const float inv_rel = 1.f / (1.f + fmaxf(D.rel_err, 0.f));
 
     for (;;) {
         int c = 0;
@@ -175,6 +181,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
         const int k_end = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
 
         float best2 = best_init;             // warp-uniform
+        float thr2 = best_init;              // squared pruning threshold: best2 itself, or tightened by the tolerances
         int best_pair = -1, best_la = 0;
         V3 best_p = v3(0.f, 0.f, 0.f), best_q = best_p;     // closest points in link a's frame (warp-uniform copies)
 
@@ -205,7 +212,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
             else {
                 while (k0 < k_end && ncb == 0) {
                     const int k = k0 + lane;
-                    const bool want = k < k_end && k != first_k && pair_bound(k) < best2;
+                    const bool want = k < k_end && k != first_k && pair_bound(k) < thr2;
                     const unsigned m = __ballot_sync(kFull, want);
                     if (want) cbuf[__popc(m & lt_mask)] = (uint32_t)k;
                     ncb = __popc(m);
@@ -275,7 +282,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
 #pragma unroll
                     for (int k = 0; k < 9; ++k) R[k] = rt[k];
                     t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-                    if (box_gap2(R, t, a0, a1, b0, b1) < best2) {
+                    if (box_gap2(R, t, a0, a1, b0, b1) < thr2) {
                         const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
                         if (la < 0 && lb < 0) {
                             const float4* ta = P.tris + 3 * (size_t)(~la);
@@ -303,6 +310,12 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                     const unsigned who = __ballot_sync(kFull, __float_as_uint(d2) == key);
                     const int src = __ffs(who) - 1;
                     best2 = __uint_as_float(key);
+                    thr2 = best2;
+                    if (approx && best2 < 1.0e37f) {
+                        const float b = sqrtf(best2);
+                        const float th = fmaxf(0.f, fminf(b - D.abs_err, b * inv_rel));
+                        thr2 = th * th;
+                    }
                     const uint32_t bs = __shfl_sync(kFull, s, src);
                     best_pair = slot_pair[bs];
                     best_la = slot_la[bs];

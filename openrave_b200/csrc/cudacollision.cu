@@ -515,7 +515,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
 // Minimum separation of n configurations (host buffers in and out, one stream, synchronous): FK kernel, then the
 // branch-and-bound distance kernel of cc_distance.cuh, chunk by chunk.
 int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h_in, int n, int flags, double max_distance,
-                    double* h_dist, int32_t* h_pair, double* h_pts)
+                    double rel_err, double abs_err, double* h_dist, int32_t* h_pair, double* h_pts)
 {
     cc_scene* S = Q->scene;
     if (n <= 0) return CC_OK;
@@ -545,6 +545,8 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     ccdev::DistOut D;
     D.min_distance = Q->d_dist.p; D.min_pair = Q->d_dpair.p; D.points = h_pts ? Q->d_dpts.p : nullptr;
     D.dist_max = max_distance > 0 ? (float)max_distance : 0.f;
+    D.rel_err = rel_err > 0 ? (float)rel_err : 0.f;
+    D.abs_err = abs_err > 0 ? (float)abs_err : 0.f;
     cudaStream_t st = 0;
     for (int off = 0; off < n; off += chunk) {
         const int m = std::min(chunk, n - off);
@@ -1376,8 +1378,8 @@ int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_T8)
     return run_host(q, dof_values, (size_t)n * q->ncols, n, ccdev::kFlagFkOnly, false, nullptr, nullptr, nullptr, nullptr, out_T8);
 }
 
-int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance, double* min_distance,
-                      int32_t* min_pair, double* closest_points)
+int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance, double rel_err,
+                      double abs_err, double* min_distance, int32_t* min_pair, double* closest_points)
 {
     if (!q || n < 0 || !min_distance || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_distance_poses");
@@ -1390,15 +1392,15 @@ int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, d
         CC_CUDA(cudaDeviceSynchronize());
         q->dist_ready = true;
     }
-    return launch_distance(q, q->dist, false, dof_values, n, flags, max_distance, min_distance, min_pair, closest_points);
+    return launch_distance(q, q->dist, false, dof_values, n, flags, max_distance, rel_err, abs_err, min_distance, min_pair, closest_points);
 }
 
-int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double max_distance, double* min_distance,
-                      int32_t* min_pair, double* closest_points)
+int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double max_distance, double rel_err, double abs_err,
+                      double* min_distance, int32_t* min_pair, double* closest_points)
 {
     if (!q || n < 0 || !min_distance || (n > 0 && !T8)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
-    return launch_distance(q, q->full, true, T8, n, flags, max_distance, min_distance, min_pair, closest_points);
+    return launch_distance(q, q->full, true, T8, n, flags, max_distance, rel_err, abs_err, min_distance, min_pair, closest_points);
 }
 
 int cc_host_alloc(size_t bytes, void** out)

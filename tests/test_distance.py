@@ -86,6 +86,11 @@ def test_gpu_distance_equals_oracle(arm_only):
     # search radius
     capped = cc.DistanceBatch(robot2, q[:500], active=active, max_distance=0.05)
     assert np.abs(capped["distance"] - np.minimum(ref["distance"][:500], 0.05)).max() < TOL
+    # PQP_Distance's tolerances: exact <= r <= max(exact + abs_err, exact * (1 + rel_err)); pqprave's own setting last
+    for rel, ab in ((0.5, 0.0), (0.0, 0.005), (200.0, 0.001)):
+        ap = cc.DistanceBatch(robot2, q[:1000], active=active, rel_err=rel, abs_err=ab)["distance"]
+        ex = ref["distance"][:1000]
+        assert (ap >= ex - TOL).all() and (ap <= np.maximum(ex + ab, ex * (1 + rel)) + TOL).all()
     # env only / self only
     for flags in (1, 2):
         r1 = orc.distance_batch(robot, q[:300], active=active, flags=flags)
