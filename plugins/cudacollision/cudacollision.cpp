@@ -103,9 +103,9 @@ class CudaCollisionChecker : public CollisionCheckerBase
         KinBodyWeakPtr body;
         int id;                          // cc body id
         int transformStamp;              // KinBody::GetUpdateStamp at the last pose upload
-        bool kinematicsDirty, pairsDirty;
-        UserDataPtr cbGeometry, cbEnable, cbAttached, cbJoints, cbActive;
-        BodyInfo() : id(-1), transformStamp(-1), kinematicsDirty(true), pairsDirty(true) {}
+        bool kinematicsDirty, pairsDirty, grabbedDirty;
+        UserDataPtr cbGeometry, cbEnable, cbAttached, cbJoints, cbActive, cbGrabbed;
+        BodyInfo() : id(-1), transformStamp(-1), kinematicsDirty(true), pairsDirty(true), grabbedDirty(true) {}
     };
     typedef boost::shared_ptr<BodyInfo> BodyInfoPtr;
 
@@ -143,7 +143,7 @@ public:
     // ------------------------------------------------------------------------------------------ options
     virtual bool SetCollisionOptions(int options)
     {
-        if (options & (CO_Distance | CO_UseTolerance | CO_Contacts | CO_RayAnyHit)) return false;   // not provided (cf. fclcollision.cpp:171-180)
+        if (options & (CO_UseTolerance | CO_Contacts | CO_RayAnyHit)) return false;   // not provided (cf. fclcollision.cpp:171-180)
         if (options != _options) { _options = options; _DropQueries(); }
         return true;
     }
@@ -234,8 +234,11 @@ public:
         pbody->GetAttached(attached);
         bool bcollision = false;
         FOREACHC(itatt, attached) {
-            if (vbodyexcluded.empty() && vlinkexcluded.empty() && *itatt == pbody) {
+            const bool bcommon = vbodyexcluded.empty() && vlinkexcluded.empty();
+            if (bcommon && *itatt == pbody) {
                 bcollision |= _CheckBoundEnv(pbody, report);      // the common case runs through the cached bound query
+            } else if (bcommon && !!pbody->IsGrabbing(**itatt)) {
+                continue;                                         // its links are query links of pbody's bound query (cc_body_set_grabbed)
             } else {
                 bcollision |= _CheckPairs(*itatt, _EnvTriples(*itatt, attached, vbodyexcluded, vlinkexcluded, NULL), report);
             }
@@ -314,15 +317,25 @@ public:
         const std::vector<int>* active = NULL;
         if (pbody->IsRobot() && (_options & CO_ActiveDOFs)) active = &RaveInterfaceConstCast<RobotBase>(pbody)->GetActiveDOFIndices();
         cc_query* query = _Bind(pbody, active);
-        std::vector<double> T8 = _Poses(pbody);
+        std::vector<double> T8 = _QueryPoses(query);
         uint32_t verdict = 0; int32_t fs = -1;
         _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_SELF, &verdict, NULL, &fs, NULL));
-        if ((verdict & CC_VERDICT_SELF) && !!report && fs >= 0) {
+        // the body's own non-adjacent pairs come first in the pair order: a first hit that names a grabbed link belongs to
+        // KinBody::CheckSelfCollision's grabbed loops (kinbodycollision.cpp:83-205), not to the standalone check
+        bool bhit = false;
+        if ((verdict & CC_VERDICT_SELF) && fs >= 0) {
             std::vector<int32_t> quads = _Quads(query);
-            report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * fs]), *pbody->GetLinks().at(quads[4 * fs + 2]));
-            report->minDistance = 0;
+            const int nl = (int)pbody->GetLinks().size();
+            bhit = quads[4 * fs] < nl && quads[4 * fs + 2] < nl;
+            if (bhit && !!report) {
+                report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * fs]), *pbody->GetLinks().at(quads[4 * fs + 2]));
+                report->minDistance = 0;
+            }
         }
-        return (verdict & CC_VERDICT_SELF) != 0;
+        std::vector<KinBodyPtr> vgrabbed;
+        pbody->GetGrabbed(vgrabbed);
+        if (!bhit && !!report && (_options & CO_Distance) && vgrabbed.empty()) _FillDistance(query, T8, CC_BATCH_SELF, report);
+        return bhit;
     }
 
     virtual bool CheckStandaloneSelfCollision(KinBody::LinkConstPtr plink, CollisionReportPtr report = CollisionReportPtr())
@@ -374,6 +387,7 @@ private:
         pinfo->cbAttached = pbody->RegisterChangeCallback(KinBody::Prop_BodyAttached, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, false));
         pinfo->cbJoints = pbody->RegisterChangeCallback(KinBody::Prop_Joints | KinBody::Prop_LinkStatic, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, true));
         pinfo->cbActive = pbody->RegisterChangeCallback(KinBody::Prop_RobotActiveDOFs, boost::bind(&CudaCollisionChecker::_OnStructure, this, winfo, false));
+        pinfo->cbGrabbed = pbody->RegisterChangeCallback(KinBody::Prop_RobotGrabbed, boost::bind(&CudaCollisionChecker::_OnGrabbed, this, winfo));
         pbody->SetUserData(_userdatakey, pinfo);
         _byid[pinfo->id] = pinfo->body;
         _DropQueries();
@@ -398,6 +412,108 @@ private:
         BodyInfoPtr pinfo = winfo.lock();
         KinBodyPtr pbody = !pinfo ? KinBodyPtr() : pinfo->body.lock();
         if (!!pbody) { _UploadMeshes(pbody, pinfo); pinfo->pairsDirty = true; _DropQueries(); }
+    }
+
+    void _OnGrabbed(boost::weak_ptr<BodyInfo> winfo)
+    {
+        BodyInfoPtr pinfo = winfo.lock();
+        if (!pinfo) return;
+        pinfo->grabbedDirty = true;
+        _DropQueries();
+    }
+
+    /// KinBody::_vGrabbedBodies -> cc_body_set_grabbed.  The reference evaluates Grabbed::_listNonCollidingLinksWhenGrabbed
+    /// lazily at the state saved when Grab was called (kinbodygrab.cpp:63-200); that list is private, so it is recomputed
+    /// here with this checker at the first query after the grab (the same state in the usual Grab -> plan sequence): links
+    /// of the grabber that are not rigidly attached to the grabbing link, not in the ignore set and not touching the
+    /// grabbed body, plus the non-touching links of the other grabbed bodies.
+    void _SyncGrabbed(KinBodyConstPtr pbody, BodyInfoPtr pinfo)
+    {
+        if (!pinfo->grabbedDirty) return;
+        pinfo->grabbedDirty = false;
+        _Check(cc_body_release_grabbed(_scene, pinfo->id, -1));
+        std::vector<KinBodyPtr> vgrabbed;
+        pbody->GetGrabbed(vgrabbed);
+        for (size_t g = 0; g < vgrabbed.size(); ++g) {
+            KinBodyPtr pgrabbed = vgrabbed[g];
+            KinBody::LinkPtr plink = pbody->IsGrabbing(*pgrabbed);
+            if (!plink) continue;
+            BodyInfoPtr ginfo = _InitKinBody(pgrabbed);
+            const Transform tinv = plink->GetTransform().inverse();
+            std::vector<double> rel(8 * pgrabbed->GetLinks().size());
+            for (size_t k = 0; k < pgrabbed->GetLinks().size(); ++k) PackTransform(tinv * pgrabbed->GetLinks()[k]->GetTransform(), &rel[8 * k]);
+            std::vector<KinBody::LinkPtr> vrigid;
+            plink->GetRigidlyAttachedLinks(vrigid);
+            std::list<KinBody::LinkConstPtr> listignored;
+            pbody->GetIgnoredLinksOfGrabbed(pgrabbed, listignored);
+            std::vector<int32_t> noncolliding;
+            std::vector<std::pair<KinBodyConstPtr, BodyInfoPtr> > vsources(1, std::make_pair(pbody, pinfo));
+            for (size_t o = 0; o < g; ++o) {
+                KinBody::LinkPtr potherlink = pbody->IsGrabbing(*vgrabbed[o]);
+                if (std::find(vrigid.begin(), vrigid.end(), potherlink) == vrigid.end()) vsources.push_back(std::make_pair(KinBodyConstPtr(vgrabbed[o]), _InitKinBody(vgrabbed[o])));
+            }
+            for (size_t isrc = 0; isrc < vsources.size(); ++isrc) {
+                FOREACHC(itlink, vsources[isrc].first->GetLinks()) {
+                    if (isrc == 0 && (std::find(vrigid.begin(), vrigid.end(), *itlink) != vrigid.end() ||
+                                      std::find(listignored.begin(), listignored.end(), KinBody::LinkConstPtr(*itlink)) != listignored.end())) continue;
+                    std::vector<int32_t> triples;
+                    for (size_t k = 0; k < pgrabbed->GetLinks().size(); ++k) { triples.push_back((*itlink)->GetIndex()); triples.push_back(ginfo->id); triples.push_back((int)k); }
+                    if (!_CheckPairs(vsources[isrc].first, triples, CollisionReportPtr(), true)) {
+                        noncolliding.push_back(vsources[isrc].second->id);
+                        noncolliding.push_back((*itlink)->GetIndex());
+                    }
+                }
+            }
+            _Check(cc_body_set_grabbed(_scene, pinfo->id, ginfo->id, plink->GetIndex(), rel.data(), noncolliding.data(), (int)noncolliding.size() / 2));
+            _SyncKinematics(pgrabbed, ginfo);      // grabbedBody.CheckSelfCollision needs its non-adjacent list
+        }
+    }
+
+    /// link poses in the row layout of a bound query: the body's links, then those of its grabbed bodies (cc_query_get_links)
+    std::vector<double> _QueryPoses(cc_query* query)
+    {
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        std::vector<int32_t> links(2 * (size_t)std::max(1, info.nlinks));
+        cc_query_get_links(query, links.data());
+        std::vector<double> T8(8 * (size_t)info.nlinks);
+        for (int l = 0; l < info.nlinks; ++l) {
+            KinBodyPtr p = _byid[links[2 * l]].lock();
+            PackTransform(p->GetLinks().at(links[2 * l + 1])->GetTransform(), &T8[8 * (size_t)l]);
+        }
+        return T8;
+    }
+
+    KinBody::LinkConstPtr _QueryLink(cc_query* query, int qindex)
+    {
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        std::vector<int32_t> links(2 * (size_t)std::max(1, info.nlinks));
+        cc_query_get_links(query, links.data());
+        KinBodyPtr p = _byid[links[2 * qindex]].lock();
+        return p->GetLinks().at(links[2 * qindex + 1]);
+    }
+
+    /// CO_Distance on a bound single-state query (collisionPQP.h:622-648): minDistance, the closest pair, one contact
+    void _FillDistance(cc_query* query, const std::vector<double>& T8, int flags, CollisionReportPtr report)
+    {
+        double dist = 0, pts[6];
+        int32_t pair = -1;
+        _Check(cc_distance_poses(query, T8.data(), 1, flags, 0.0, 0.0, 0.0, &dist, &pair, pts));
+        if (pair < 0 || dist >= report->minDistance) return;
+        std::vector<int32_t> quads = _Quads(query);
+        KinBody::LinkConstPtr plink1 = _QueryLink(query, quads[4 * pair]);
+        KinBody::LinkConstPtr plink2 = quads[4 * pair + 3] == 1 ? _QueryLink(query, quads[4 * pair + 2])
+                                                                : KinBody::LinkConstPtr(_byid[quads[4 * pair + 1]].lock()->GetLinks().at(quads[4 * pair + 2]));
+        report->minDistance = dist;
+        const int icollision = report->AddLinkCollision(*plink1, *plink2);
+        CollisionPairInfo& cpinfo = report->vCollisionInfos[icollision];
+        cpinfo.contacts.resize(1);
+        const Vector p1(pts[0], pts[1], pts[2]), p2(pts[3], pts[4], pts[5]);
+        const dReal depth = RaveSqrt((p2 - p1).lengthsqr3());
+        cpinfo.contacts[0].pos = p1;
+        cpinfo.contacts[0].depth = -depth;
+        cpinfo.contacts[0].norm = depth > 0 ? (p2 - p1) * (1 / depth) : Vector(0, 0, 0);
     }
 
     void _OnStructure(boost::weak_ptr<BodyInfo> winfo, bool kinematics)
@@ -522,6 +638,7 @@ private:
         _Synchronize();
         BodyInfoPtr pinfo = _Info(pbody);
         _SyncKinematics(pbody, pinfo);
+        _SyncGrabbed(pbody, pinfo);
         _Check(cc_scene_commit(_scene));
         QueryKey key;
         key.body = pinfo->id; key.options = _options;
@@ -552,11 +669,12 @@ private:
         cc_query* query = _Bind(pbody, active);
         cc_query_info info;
         cc_query_get_info(query, &info);
-        std::vector<double> T8 = _Poses(pbody);
+        std::vector<double> T8 = _QueryPoses(query);       // grabbed links included: the bound query covers them
         std::vector<uint32_t> mask(!report ? 0 : info.mask_words);
         uint32_t verdict = 0;
         _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | (!report ? 0 : CC_BATCH_ALL_PAIRS), &verdict, NULL, NULL, !report ? NULL : mask.data()));
         if ((verdict & CC_VERDICT_ENV) && !!report) _FillReport(pbody, query, mask, info.npairs_env, report);
+        if (!(verdict & CC_VERDICT_ENV) && !!report && (_options & CO_Distance)) _FillDistance(query, T8, CC_BATCH_ENV, report);
         return (verdict & CC_VERDICT_ENV) != 0;
     }
 
@@ -567,7 +685,7 @@ private:
             if (!((mask[p >> 5] >> (p & 31)) & 1u)) continue;
             KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
             if (!pother) continue;
-            report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));   // collisionPQP.h:586
+            report->AddLinkCollision(*_QueryLink(query, quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));   // collisionPQP.h:586
         }
         report->minDistance = 0;                                                                                       // :587
     }
