@@ -25,7 +25,9 @@
 namespace ccdev {
 
 constexpr int kDistStackCap = 1024;                 // items per warp
-constexpr size_t kDistWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 8 + (size_t)kDistStackCap * 8 + 32 * 4;
+constexpr int kDistTriQCap = 96;                    // pending leaf pairs (evaluated 32 at a time, so full warps run the triangle code)
+constexpr size_t kDistWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 8 + (size_t)kDistStackCap * 8 +
+                                      (size_t)kDistTriQCap * 8 + 32 * 4;
 
 struct DistOut {
     double* min_distance;       // [n] metres; dist_max when nothing is closer (1e30 when dist_max <= 0 and there is no pair)
@@ -162,7 +164,8 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
     int32_t* slot_pair = (int32_t*)(slot_rt + kNumSlots * 24);    // [kNumSlots] reference pair index
     int32_t* slot_la = slot_pair + kNumSlots;                     // [kNumSlots] plan slot of link a (to place the closest points)
     uint2* stack = (uint2*)(slot_la + kNumSlots);                 // [kDistStackCap] {nodeA | slot << 26, nodeB}
-    uint32_t* cbuf = (uint32_t*)(stack + kDistStackCap);          // [32] candidate device pair indices
+    uint2* triq = stack + kDistStackCap;                          // [kDistTriQCap] {triA | slot << 26, triB}
+    uint32_t* cbuf = (uint32_t*)(triq + kDistTriQCap);            // [32] candidate device pair indices
     const unsigned lt_mask = (1u << lane) - 1u;
     const int ndyn = P.ndyn;
     const float best_init = D.dist_max > 0.f ? D.dist_max * D.dist_max : 3.0e38f;
@@ -258,8 +261,47 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
             }
             __syncwarp();
 
-            // ---- drain
-            while (sp > 0) {
+            // ---- drain: box pairs 32 at a time; leaf pairs are queued and evaluated 32 at a time
+            int ntri = 0;
+            while (sp > 0 || ntri > 0) {
+                if (ntri >= 32 || (sp == 0 && ntri > 0)) {
+                    const int tn = ntri < 32 ? ntri : 32;
+                    float d2 = 3.0e38f;
+                    V3 cp = v3(0.f, 0.f, 0.f), cq = cp;
+                    uint32_t s = 0;
+                    if (lane < tn) {
+                        const uint2 e = triq[ntri - 1 - lane];
+                        s = e.x >> 26;
+                        const uint32_t ta_idx = e.x & 0x3ffffffu;
+                        const float4 v0 = __ldg(P.tris + 3 * (size_t)ta_idx);
+                        V3 p1, p2, q0, q1, q2;
+                        load_tri_pair(P.tris, slot_rt + 24 * s, ta_idx, e.y, p1, p2, q0, q1, q2);
+                        d2 = tri_tri_dist2(p1, p2, q0, q1, q2, cp, cq);
+                        const V3 org = v3(v0.x, v0.y, v0.z);
+                        cp = cp + org; cq = cq + org;
+                    }
+                    ntri -= tn;
+                    const unsigned key = __reduce_min_sync(kFull, __float_as_uint(d2));
+                    if (__uint_as_float(key) < best2) {
+                        const unsigned who = __ballot_sync(kFull, __float_as_uint(d2) == key);
+                        const int src = __ffs(who) - 1;
+                        best2 = __uint_as_float(key);
+                        thr2 = best2;
+                        if (approx && best2 < 1.0e37f) {
+                            const float b = sqrtf(best2);
+                            const float th = fmaxf(0.f, fminf(b - D.abs_err, b * inv_rel));
+                            thr2 = th * th;
+                        }
+                        const uint32_t bs = __shfl_sync(kFull, s, src);
+                        best_pair = slot_pair[bs];
+                        best_la = slot_la[bs];
+                        best_p = v3(__shfl_sync(kFull, cp.x, src), __shfl_sync(kFull, cp.y, src), __shfl_sync(kFull, cp.z, src));
+                        best_q = v3(__shfl_sync(kFull, cq.x, src), __shfl_sync(kFull, cq.y, src), __shfl_sync(kFull, cq.z, src));
+                    }
+                    __syncwarp();
+                    if (best2 == 0.f) { sp = 0; ntri = 0; }       // touching / penetrating: nothing can be smaller
+                    continue;
+                }
                 // near the capacity only one item is expanded per iteration (a single path cannot overflow the margin)
                 const int width = sp > kDistStackCap - 160 ? 1 : 32;
                 const int n = sp < width ? sp : width;
@@ -268,10 +310,8 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                 if (valid) it = stack[sp - 1 - lane];
                 sp -= n;
                 __syncwarp();
-                bool push = false;
+                bool push = false, leaf = false;
                 uint2 o0 = make_uint2(0u, 0u), o1 = o0;
-                float d2 = 3.0e38f;
-                V3 cp = v3(0.f, 0.f, 0.f), cq = cp;
                 const uint32_t s = it.x >> 26;
                 if (valid) {
                     const uint32_t x = it.x & 0x3ffffffu, y = it.y;
@@ -285,13 +325,8 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                     if (box_gap2(R, t, a0, a1, b0, b1) < thr2) {
                         const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
                         if (la < 0 && lb < 0) {
-                            const float4* ta = P.tris + 3 * (size_t)(~la);
-                            const float4 v0 = __ldg(ta);
-                            V3 p1, p2, q0, q1, q2;
-                            load_tri_pair(P.tris, rt, (uint32_t)(~la), (uint32_t)(~lb), p1, p2, q0, q1, q2);
-                            d2 = tri_tri_dist2(p1, p2, q0, q1, q2, cp, cq);
-                            const V3 org = v3(v0.x, v0.y, v0.z);
-                            cp = cp + org; cq = cq + org;
+                            leaf = true;
+                            o0 = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
                         } else {
                             push = true;
                             if (lb < 0 || (la >= 0 && a1.w > b1.w)) {
@@ -304,24 +339,9 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                         }
                     }
                 }
-                // new minimum?
-                const unsigned key = __reduce_min_sync(kFull, __float_as_uint(d2));
-                if (__uint_as_float(key) < best2) {
-                    const unsigned who = __ballot_sync(kFull, __float_as_uint(d2) == key);
-                    const int src = __ffs(who) - 1;
-                    best2 = __uint_as_float(key);
-                    thr2 = best2;
-                    if (approx && best2 < 1.0e37f) {
-                        const float b = sqrtf(best2);
-                        const float th = fmaxf(0.f, fminf(b - D.abs_err, b * inv_rel));
-                        thr2 = th * th;
-                    }
-                    const uint32_t bs = __shfl_sync(kFull, s, src);
-                    best_pair = slot_pair[bs];
-                    best_la = slot_la[bs];
-                    best_p = v3(__shfl_sync(kFull, cp.x, src), __shfl_sync(kFull, cp.y, src), __shfl_sync(kFull, cp.z, src));
-                    best_q = v3(__shfl_sync(kFull, cq.x, src), __shfl_sync(kFull, cq.y, src), __shfl_sync(kFull, cq.z, src));
-                }
+                const unsigned lm = __ballot_sync(kFull, leaf);
+                if (leaf) triq[ntri + __popc(lm & lt_mask)] = o0;
+                ntri += __popc(lm);
                 const unsigned pm = __ballot_sync(kFull, push);
                 if (push) {
                     const int at = sp + 2 * __popc(pm & lt_mask);
@@ -329,7 +349,6 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                 }
                 sp += 2 * __popc(pm);
                 __syncwarp();
-                if (best2 == 0.f) sp = 0;          // touching / penetrating: nothing can be smaller
             }
             if (best2 == 0.f) break;
         }

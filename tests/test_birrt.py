@@ -146,3 +146,30 @@ def test_gpu_plans_equal_oracle_serial_plans(wamtest1):
     assert all(r["status"] == pl.PLAN_SOLVED for r in gpu)
     for r in gpu:
         assert not orc.check_batch(robot, r["path"])["verdict"].any()
+
+
+@pytest.mark.gpu
+def test_gpu_plans_pr2_right_arm_with_circular_joints():
+    """PR2 right arm (two continuous joints, CO_ActiveDOFs): harder queries (tens of iterations), same plans as the serial loop."""
+    from openrave_b200.checker import CO_ActiveDOFs, CudaCollisionChecker
+    worlds = []
+    for factory in (lambda e: oracle.OracleChecker(e, "port"), lambda e: CudaCollisionChecker(e, 0)):
+        env = load_scene("pr2test1")
+        robot = env.GetRobots()[0]
+        arm = [m for m in robot.GetManipulators() if m.GetName() == "rightarm"][0].GetArmIndices()
+        robot.SetActiveDOFs(arm)
+        cc = factory(env)
+        env.SetCollisionChecker(cc)
+        cc.SetCollisionOptions(CO_ActiveDOFs)
+        worlds.append((env, robot, cc, arm))
+    (env, robot, orc, arm), (env2, robot2, cc, _) = worlds
+    q = sample_configs(robot, 200, seed=3, active=arm)
+    free = q[orc.check_batch(robot, q, active=arm)["verdict"] == 0]
+    starts, goals, seeds = free[0:16:2].copy(), free[1:16:2].copy(), np.arange(8)
+    cpu = pl.BirrtPlanner(robot, orc.group_checker(robot, arm)).PlanBatch(starts, goals, seeds)
+    gpu = pl.BirrtPlanner(robot2, cc).PlanBatch(starts, goals, seeds)
+    assert max(r["iterations"] for r in cpu) > 5
+    same = sum(1 for a, b in zip(cpu, gpu) if a["status"] == b["status"] and np.array_equal(a["path"], b["path"]))
+    assert same >= 7, same
+    for r in gpu:
+        assert r["status"] == pl.PLAN_SOLVED and not orc.check_batch(robot, r["path"], active=arm)["verdict"].any()
