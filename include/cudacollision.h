@@ -227,6 +227,17 @@ int cc_scene_synchronize(cc_scene* s);
  * separating-axis candidate count as touching.  0 (default) = the reference's strict test (pqp/PQP.cpp:366-367). */
 int cc_scene_set_tri_epsilon(cc_scene* s, double eps);
 
+/* Certified free space (on by default).  Once a bound query has seen 16k batched configurations the library looks at the
+ * link pairs whose relative pose depends on only one or two active DOFs (everything the torso carries against the
+ * environment, a shoulder next to a wall, an upper arm next to a forearm): the exact distance on a grid over those DOFs
+ * (cc_distance_kernel) minus the largest displacement any point can make inside a grid cell certifies cells
+ * collision-free.  A pair certified in every cell can never collide inside the joint limits and leaves the batched pair
+ * list (hoisting, generalised from pose-invariant pairs); a partly certified pair keeps a bit table that the batched entry
+ * consults after the broadphase instead of descending the trees.  Verdicts and reported pairs are unchanged (a skipped pair
+ * is at least 3e-4 m from contact).  cc_query_get_table_count reports the pairs with a table and the pairs removed. */
+int cc_scene_set_pair_tables(cc_scene* s, int enabled);
+int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped);
+
 /* Diagnostics: record, for every configuration of the following batches on this query, how many traversal
  * iterations (32 box-pair tests each) the device spent on it; read the last batch's trace back with
  * cc_query_get_work_trace (synchronises).  Used by the load-balance studies in profiles/. */

@@ -49,7 +49,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
-           "cc_distance_batch", "cc_distance_poses"]
+           "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count"]
 
 _lib = None
 
@@ -88,6 +88,8 @@ def load_library():
     lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
+    lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
+    lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
@@ -150,6 +152,13 @@ class BoundQuery(object):
         checker._ck(self.lib.cc_query_get_links(handle, _ptr(self.links)))
         self.links = self.links[:info.nlinks]
         self.nlinks_body = len(body.links)
+
+    def table_count(self):
+        """How many link pairs of this query are covered by a certified free-space table (0 until the tables are built)."""
+        n, d = ctypes.c_int(0), ctypes.c_int(0)
+        self.checker._ck(self.lib.cc_query_get_table_count(self.handle, ctypes.byref(n), ctypes.byref(d)))
+        self.dropped_pairs = d.value
+        return n.value + d.value
 
     def link_of(self, qindex):
         """Query link index -> Link object (a grabbed body's link when qindex >= the body's link count)."""
@@ -499,6 +508,10 @@ class CudaCollisionChecker(object):
 
     def SetCounters(self, enabled):
         self._ck(self.lib.cc_scene_set_counters(self.scene, 1 if enabled else 0))
+
+    def SetPairTables(self, enabled):
+        self._ck(self.lib.cc_scene_set_pair_tables(self.scene, 1 if enabled else 0))
+        self._invalidate()
 
     def SetTriangleEpsilon(self, eps):
         self._ck(self.lib.cc_scene_set_tri_epsilon(self.scene, float(eps)))

@@ -71,6 +71,8 @@ struct FkStep {                 // one joint of the chain program, 256 bytes
 };
 static_assert(sizeof(FkStep) == 256, "FkStep layout");
 
+struct PairTable;
+
 struct Params {
     // scene (device pointers)
     const float4* nodes;        // 2 x float4 per node: {cx cy cz | left} {ex ey ez | right}
@@ -116,6 +118,23 @@ struct Params {
     int32_t split;
     const int32_t* part_begin;  // [split + 1]
     const int32_t* part_nenv;   // [split]
+    // certified free-space tables (FK mode only): pair_table[k] >= 0 names a table over the 1 or 2 active DOFs the pair's
+    // relative pose depends on; a set bit = every configuration of that cell is at least the contact band away from contact
+    // (distance at the cell centre > the largest displacement any point can make inside the cell), so the pair is skipped
+    const int32_t* pair_table;  // [npairs_dev] (same order as `pairs`), or NULL
+    const struct PairTable* tables;
+    const uint32_t* table_bits;
+};
+
+struct PairTable {
+    int32_t col0, col1;         // columns of q (col1 = -1: one DOF)
+    int32_t n0, n1;             // cells per DOF (n1 = 1 for one DOF)
+    int32_t circ0, circ1;       // circular DOFs are not clamped by SetDOFValues: 1 = outside the range the table does not apply,
+                                // 2 = the range is the full circle, the value is wrapped into it
+    uint32_t bit_base;          // first bit of this table in table_bits
+    int32_t pad;
+    double lo0, hi0, inv0;      // cell = (int)((clamp(v) - lo) * inv), the last cell closed
+    double lo1, hi1, inv1;
 };
 
 // ------------------------------------------------------------------------------------------------ FP64 SE(3)
@@ -483,10 +502,41 @@ __device__ __forceinline__ int filter_queue(uint2* q, int count, uint32_t dead_s
     return w;
 }
 
+// Is configuration `qrow` inside a certified-free cell of table tb?  The DOF values are clamped like KinBody::SetDOFValues
+// clamps them (kinbody.cpp:2149-2224); a circular DOF outside its range is left to the narrowphase.
+__device__ __noinline__ bool table_cell_free(const Params& P, int tb, const double* __restrict__ qrow)
+{
+    const PairTable& T = P.tables[tb];
+    const double two_pi = 6.283185307179586476925286766559;
+    double v0 = qrow[T.col0];
+    if (v0 < T.lo0 || v0 > T.hi0) {
+        if (!(v0 == v0) || T.circ0 == 1) return false;
+        if (T.circ0 == 2) { v0 -= two_pi * floor((v0 - T.lo0) / two_pi); if (v0 < T.lo0 || v0 > T.hi0) return false; }
+        else v0 = v0 < T.lo0 ? T.lo0 : T.hi0;
+    }
+    int i0 = (int)((v0 - T.lo0) * T.inv0);
+    if (i0 >= T.n0) i0 = T.n0 - 1;
+    uint32_t bit = (uint32_t)i0;
+    if (T.col1 >= 0) {
+        double v1 = qrow[T.col1];
+        if (v1 < T.lo1 || v1 > T.hi1) {
+            if (!(v1 == v1) || T.circ1 == 1) return false;
+            if (T.circ1 == 2) { v1 -= two_pi * floor((v1 - T.lo1) / two_pi); if (v1 < T.lo1 || v1 > T.hi1) return false; }
+            else v1 = v1 < T.lo1 ? T.lo1 : T.hi1;
+        }
+        int i1 = (int)((v1 - T.lo1) * T.inv1);
+        if (i1 >= T.n1) i1 = T.n1 - 1;
+        bit = (uint32_t)i0 * (uint32_t)T.n1 + (uint32_t)i1;
+    }
+    bit += T.bit_base;
+    return (__ldg(&P.table_bits[bit >> 5]) >> (bit & 31)) & 1u;
+}
+
 // kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,
 // each over its own share of the pair list, outputs merged with atomics (small batches: the latency of a batch is the
 // traversal of its slowest configuration, so that one is spread over several warps).
-template <bool kSplit>
+// kTables: the plan carries certified free-space tables (compiled out otherwise, so plans without tables run the plain code).
+template <bool kSplit, bool kTables>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -510,6 +560,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     int nenv_dev = P.nenv_dev, npairs_dev = P.npairs_dev;
     const uint32_t* pairs = P.pairs;
     const int32_t* pair_orig = P.pair_orig;
+    const int32_t* ptable = P.pair_table;
     const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
 
@@ -524,6 +575,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             const int part = w - c * P.split;
             const int pb = __ldg(&P.part_begin[part]);
             pairs = P.pairs + pb; pair_orig = P.pair_orig + pb;
+            if (kTables) ptable = P.pair_table + pb;
             npairs_dev = __ldg(&P.part_begin[part + 1]) - pb;
             nenv_dev = __ldg(&P.part_nenv[part]);
         }
@@ -575,6 +627,10 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const float4* pb = (const float4*)((sb < ndyn ? ab : st_ab) + 8 * sb);
                         const float4 ac = pa[0], ae = pa[1], bc = pb[0], be = pb[1];
                         ov[h] = fabsf(ac.x - bc.x) <= ae.x + be.x && fabsf(ac.y - bc.y) <= ae.y + be.y && fabsf(ac.z - bc.z) <= ae.z + be.z;
+                        if (kTables && ov[h]) {
+                            const int tb = __ldg(&ptable[k0 + 32 * h + lane]);
+                            if (tb >= 0 && table_cell_free(P, tb, P.q + (size_t)c * P.ncols)) ov[h] = false;
+                        }
                     }
                 }
 #pragma unroll

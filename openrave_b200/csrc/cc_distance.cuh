@@ -37,6 +37,8 @@ struct DistOut {
     // PQP_Distance's tolerances (pqp/PQP.cpp:717-721, 776): a box pair is skipped when its bound d satisfies
     // d + abs_err >= best or d * (1 + rel_err) >= best, so the result r obeys exact <= r <= max(exact + abs_err, exact * (1 + rel_err))
     float rel_err, abs_err;
+    // per-pair mode (table building): work item w = configuration w / npairs_dev, pair w % npairs_dev, outputs indexed by w
+    int32_t per_pair;
 };
 
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -176,12 +178,18 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
         int c = 0;
         if (lane == 0) c = atomicAdd(&P.counters[0], 1);
         c = __shfl_sync(kFull, c, 0);
-        if (c >= P.n) break;
+        const int w = c;
+        int k_begin = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+        int k_end = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+        if (D.per_pair) {
+            if (w >= P.n * P.npairs_dev) break;
+            c = w / P.npairs_dev;
+            k_begin = w - c * P.npairs_dev;
+            k_end = k_begin + 1;
+        } else if (c >= P.n) break;
         const float* xf = P.xf32 + (size_t)c * ndyn * 12;
         const float* ab = P.aabb + (size_t)c * ndyn * 8;
         const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;
-        const int k_begin = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
-        const int k_end = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
 
         float best2 = best_init;             // warp-uniform
         float thr2 = best_init;              // squared pruning threshold: best2 itself, or tightened by the tolerances
@@ -355,10 +363,10 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
 
         if (lane == 0) {
             double dist = best_pair >= 0 ? (double)sqrtf(best2) : (D.dist_max > 0.f ? (double)D.dist_max : 1e30);
-            D.min_distance[c] = dist;
-            if (D.min_pair) D.min_pair[c] = best_pair;
+            D.min_distance[w] = dist;
+            if (D.min_pair) D.min_pair[w] = best_pair;
             if (D.points) {
-                double* o = D.points + 6 * (size_t)c;
+                double* o = D.points + 6 * (size_t)w;
                 if (best_pair >= 0) {
                     const float* A = best_la < ndyn ? xf + 12 * best_la : P.st_xf + 12 * (size_t)(best_la - ndyn);
                     const V3 pts[2] = {best_p, best_q};

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <limits>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -119,6 +120,7 @@ struct cc_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
     float tri_eps = 0.0f;
+    bool pair_tables = true;                // certified free-space tables for pairs that depend on <= 2 active DOFs
     ~cc_scene()
     {
         for (HBody* b : bodies) delete b;
@@ -249,7 +251,7 @@ struct Plan {
     DevBuf<float> d_st_xf, d_st_aabb, d_link_box;
     DevBuf<ccdev::FkStep> d_steps;
     // split traversal tables for S = 2, 4, 8 (index log2(S) - 1), built with the plan
-    struct Split { DevBuf<uint32_t> d_pairs; DevBuf<int32_t> d_orig, d_part_begin, d_part_nenv; };
+    struct Split { DevBuf<uint32_t> d_pairs; DevBuf<int32_t> d_orig, d_part_begin, d_part_nenv; std::vector<int32_t> orig; };
     Split split[3];
 };
 
@@ -273,6 +275,18 @@ struct cc_query {
     std::vector<uint8_t> pair_live;          // [npairs] 0: can never collide (disabled / no mesh), kept for indexing only
     int nenv_total = 0, nself_total = 0;
     Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
+    // certified free-space tables of the batched FK-mode plan (built once enough configurations have gone through)
+    bool allow_tables = false, tables_done = false;
+    std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
+    uint64_t fk_configs_seen = 0;
+    int ntables = 0;
+    DevBuf<int32_t> d_pair_table;            // mainl order
+    DevBuf<int32_t> d_pair_table_split[3];   // split orders
+    DevBuf<ccdev::PairTable> d_tables;
+    DevBuf<uint32_t> d_table_bits;
+    int ndropped = 0;                        // pairs certified collision-free over the whole active range and removed
+    std::vector<int> p_main;                 // original indices of the pairs of the batched FK-mode plan
+    std::vector<uint8_t> moves;              // [nq] link is moved by some active DOF
     Plan dist;                               // distance queries in FK mode: every live pair, nothing hoisted (built on first use)
     bool dist_ready = false;
     std::vector<int> p_full;                 // indices of the live pairs
@@ -399,18 +413,18 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
-        int per_sm = 0, per_sm_split = 0;
-        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccdev::cc_traverse_kernel<false>, ccdev::kWarpsPerBlock * 32, tr_smem));
-        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_split, ccdev::cc_traverse_kernel<true>, ccdev::kWarpsPerBlock * 32, tr_smem));
-        if (per_sm < 1 || per_sm_split < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
-        per_sm = std::min(per_sm, per_sm_split);
-        if (getenv("CC_TUNE_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(getenv("CC_TUNE_BLOCKS_PER_SM"))));
-        if (getenv("CC_TUNE_CARVEOUT")) {
-            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
-            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_traverse_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
+        const void* variants[4] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>};
+        int per_sm = 1 << 30;
+        for (const void* kfn : variants) {
+            CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
+            int v = 0;
+            CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kfn, ccdev::kWarpsPerBlock * 32, tr_smem));
+            if (v < 1) return fail(CC_ERR_CUDA, "traversal kernel does not fit on an SM");
+            per_sm = std::min(per_sm, v);
+            if (getenv("CC_TUNE_CARVEOUT")) CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CC_TUNE_CARVEOUT"))));
         }
+        if (getenv("CC_TUNE_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(getenv("CC_TUNE_BLOCKS_PER_SM"))));
         S->trav_blocks_per_sm = per_sm;
     }
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
@@ -426,7 +440,10 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         int want = forced > 0 ? forced : std::min(by_load, by_pairs);
         while (split * 2 <= want && split < 8) split *= 2;
     }
+    const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only && S->tri_eps <= 1e-4f;
+    if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
+    if (sp && use_tables) P.pair_table = Q->d_pair_table_split[split == 2 ? 0 : (split == 4 ? 1 : 2)].p;
     if (sp) {
         P.pairs = sp->d_pairs.p; P.pair_orig = sp->d_orig.p; P.part_begin = sp->d_part_begin.p; P.part_nenv = sp->d_part_nenv.p;
         P.split = split;
@@ -490,8 +507,13 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        if (split > 1) ccdev::cc_traverse_kernel<true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
-        else ccdev::cc_traverse_kernel<false><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        if (use_tables) {
+            if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+            else ccdev::cc_traverse_kernel<false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        } else {
+            if (split > 1) ccdev::cc_traverse_kernel<true, false><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+            else ccdev::cc_traverse_kernel<false, false><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        }
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
         if (hio) {
@@ -515,7 +537,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
 // Minimum separation of n configurations (host buffers in and out, one stream, synchronous): FK kernel, then the
 // branch-and-bound distance kernel of cc_distance.cuh, chunk by chunk.
 int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h_in, int n, int flags, double max_distance,
-                    double rel_err, double abs_err, double* h_dist, int32_t* h_pair, double* h_pts)
+                    double rel_err, double abs_err, double* h_dist, int32_t* h_pair, double* h_pts, bool per_pair = false)
 {
     cc_scene* S = Q->scene;
     if (n <= 0) return CC_OK;
@@ -525,12 +547,15 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     const int row_doubles = pose_mode ? Q->nq * 8 : Q->ncols;
     const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
     int chunk = (int)std::min<size_t>(65536, std::max<size_t>(1024, ((size_t)1 << 29) / per_cfg));
+    const int outs_per_cfg = per_pair ? std::max(1, (int)pl.pairs.size()) : 1;       // per-pair mode: one result per (configuration, pair)
+    if (per_pair) chunk = std::max(1, std::min(chunk, (1 << 22) / outs_per_cfg));
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     int rc = ensure_scratch(Q, pl, chunk, 1);
     if (rc != CC_OK) return rc;
     P.cap = chunk;
     CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, (size_t)chunk * row_doubles)));
-    CC_CUDA(Q->d_dist.reserve(chunk)); CC_CUDA(Q->d_dpair.reserve(chunk)); CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
+    CC_CUDA(Q->d_dist.reserve((size_t)chunk * outs_per_cfg)); CC_CUDA(Q->d_dpair.reserve((size_t)chunk * outs_per_cfg));
+    CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
     const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
     if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
     if (fk_smem > 48 * 1024)
@@ -547,6 +572,8 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     D.dist_max = max_distance > 0 ? (float)max_distance : 0.f;
     D.rel_err = rel_err > 0 ? (float)rel_err : 0.f;
     D.abs_err = abs_err > 0 ? (float)abs_err : 0.f;
+    D.per_pair = per_pair ? 1 : 0;
+    if (per_pair) { D.min_pair = nullptr; D.points = nullptr; }
     cudaStream_t st = 0;
     for (int off = 0; off < n; off += chunk) {
         const int m = std::min(chunk, n - off);
@@ -559,14 +586,14 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
         ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
         CC_CUDA(cudaGetLastError());
         int grid = dist_blocks_per_sm * S->num_sms;
-        const int need = (m + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
-        if (grid > need) grid = need;
+        const long long need = ((long long)m * outs_per_cfg + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
+        if (grid > need) grid = (int)need;
         ccdev::cc_distance_kernel<<<grid, ccdev::kWarpsPerBlock * 32, d_smem, st>>>(P, D);
         CC_CUDA(cudaGetLastError());
         S->stats.launches += 2;
-        CC_CUDA(cudaMemcpyAsync(h_dist + off, Q->d_dist.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (h_pair) CC_CUDA(cudaMemcpyAsync(h_pair + off, Q->d_dpair.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        if (h_pts) CC_CUDA(cudaMemcpyAsync(h_pts + (size_t)off * 6, Q->d_dpts.p, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CC_CUDA(cudaMemcpyAsync(h_dist + (size_t)off * outs_per_cfg, Q->d_dist.p, (size_t)m * outs_per_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h_pair && !per_pair) CC_CUDA(cudaMemcpyAsync(h_pair + off, Q->d_dpair.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (h_pts && !per_pair) CC_CUDA(cudaMemcpyAsync(h_pts + (size_t)off * 6, Q->d_dpts.p, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CC_CUDA(cudaStreamSynchronize(st));
     }
     return CC_OK;
@@ -590,6 +617,318 @@ HBody* get_body(cc_scene* s, int body)
 }
 
 }  // namespace
+
+
+// ================================================================================================ certified free-space tables
+// Near-miss pairs — a shoulder next to a wall, an upper arm next to a forearm — pass the AABB test in every configuration and
+// cost a full descent each time just to prove separation.  When the relative pose of such a pair depends on only one or two
+// active DOFs, that proof can be made once: the exact distance at the centre of every cell of a grid over those DOFs
+// (cc_distance_kernel), minus the largest displacement any point of one link can make relative to the other inside the cell
+// (sum over the DOFs of half cell width x K_d, K_d = 1 for a prismatic joint, the largest possible distance of a point of the
+// link from the joint anchor for a revolute one, bounded by chain segment lengths so that it holds for every value of the
+// other joints), certifies the whole cell collision-free.  The traversal kernel skips a certified pair after its AABB test;
+// everything else runs the normal narrowphase, so verdicts are unchanged.  Which pairs get a table is decided by a short
+// calibration run that counts how often each pair passes the AABB test.
+namespace {
+
+double norm3(const double* t) { return sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]); }
+
+struct ChainInfo {
+    std::vector<int> parent_joint;   // [links] joint whose child is the link, -1 for the root
+};
+
+// joints from link l up to the root (child-to-parent order)
+std::vector<int> path_to_root(const HBody& B, const ChainInfo& ci, int l)
+{
+    std::vector<int> out;
+    for (int guard = 0; l >= 0 && ci.parent_joint[l] >= 0 && guard < 1 << 16; ++guard) { out.push_back(ci.parent_joint[l]); l = B.joints[ci.parent_joint[l]].parent_link; }
+    return out;
+}
+
+double joint_span(const cc_joint& j)     // largest change of |child origin - parent origin| contribution of one joint
+{
+    double s = norm3(j.left + 4) + norm3(j.right + 4);
+    if (!j.is_static && j.type == CC_JOINT_PRISMATIC) s += norm3(j.axis) * std::max(fabs(j.lower), fabs(j.upper));
+    return s;
+}
+
+double link_radius(const HLink& L)
+{
+    double r2 = 0;
+    for (size_t i = 0; i + 2 < L.verts.size(); i += 3) r2 = std::max(r2, L.verts[i] * L.verts[i] + L.verts[i + 1] * L.verts[i + 1] + L.verts[i + 2] * L.verts[i + 2]);
+    return sqrt(r2);
+}
+
+// K_d for every active DOF on the tree path between query links a and b (b == -1: the other link is static in the world, the
+// path is root -> a).  Returns false when the pair cannot be tabulated (a mimic joint on the path, a joint with a DOF that
+// is active but not 1:1, more than two varying DOFs).  `moving_radius_b`: radius of the link whose points are followed.
+bool pair_rates(const HBody& B, const ChainInfo& ci, const std::vector<int>& col_of_dof, int a, int b, double radius_a, double radius_b,
+                std::vector<int>& dofs, std::vector<double>& K)
+{
+    std::vector<int> pa = path_to_root(B, ci, a), pb;
+    if (b >= 0) {
+        pb = path_to_root(B, ci, b);
+        while (!pa.empty() && !pb.empty() && pa.back() == pb.back()) { pa.pop_back(); pb.pop_back(); }
+    }
+    // varying joints
+    dofs.clear(); K.clear();
+    std::vector<std::pair<int, bool>> varying;      // (joint, on a's branch)
+    for (int side = 0; side < 2; ++side)
+        for (int j : (side == 0 ? pa : pb)) {
+            const cc_joint& J = B.joints[j];
+            if (J.mimic_dof >= 0) { if (col_of_dof[J.mimic_dof] >= 0) return false; continue; }
+            if (J.is_static || J.dof_index < 0) continue;
+            if (col_of_dof[J.dof_index] >= 0) varying.push_back(std::make_pair(j, side == 0));
+        }
+    if (varying.empty() || varying.size() > 2) return false;
+    // followed link = b seen from a's frame (or a seen from the world when b is static); the swapped roles give another valid
+    // bound, the smaller sum is kept by the caller through two calls
+    for (auto& v : varying) {
+        const cc_joint& J = B.joints[v.first];
+        double k;
+        if (J.type == CC_JOINT_PRISMATIC) k = norm3(J.axis);
+        else {
+            // distance from the joint anchor (origin of parent * left) to any point of the followed link
+            double len = 0;
+            if (b < 0) {
+                // world-static other link: follow a; the joint is on a's branch: segments below the joint towards a
+                len = norm3(J.right + 4);
+                for (int j : pa) { if (j == v.first) break; len += joint_span(B.joints[j]); }
+                k = len + radius_a;
+            } else if (!v.second) {
+                // joint on b's branch, follow b: segments below the joint towards b
+                len = norm3(J.right + 4);
+                for (int j : pb) { if (j == v.first) break; len += joint_span(B.joints[j]); }
+                k = len + radius_b;
+            } else {
+                // joint on a's branch, follow b as seen from a: up from the joint to the common ancestor, then down to b
+                len = norm3(J.left + 4);
+                bool above = false;
+                for (int j : pa) { if (above) len += joint_span(B.joints[j]); if (j == v.first) above = true; }
+                for (int j : pb) len += joint_span(B.joints[j]);
+                k = len + radius_b;
+            }
+        }
+        dofs.push_back(J.dof_index);
+        K.push_back(k);
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, const std::vector<uint8_t>& dynamic, bool with_fk);
+}
+
+static int build_pair_tables(cc_query* Q)
+{
+    cc_scene* S = Q->scene;
+    HBody* B = S->bodies[Q->body];
+    Q->tables_done = true;
+    if (!Q->allow_tables || !S->pair_tables || getenv("CC_TUNE_NO_TABLES") || Q->p_main.empty() || Q->ncols == 0) return CC_OK;
+    const int nlb = (int)B->links.size();
+    const std::vector<int>& col_of_dof = Q->col_of_dof;
+    if ((int)col_of_dof.size() != B->ndof) return CC_OK;
+    std::vector<const cc_joint*> joint_of_dof(B->ndof, nullptr);
+    for (const cc_joint& j : B->joints) if (j.dof_index >= 0 && j.mimic_dof < 0) joint_of_dof[j.dof_index] = &j;
+    for (int d = 0; d < B->ndof; ++d) if (col_of_dof[d] >= 0 && !joint_of_dof[d]) return CC_OK;     // an active DOF without its own joint
+    ChainInfo ci;
+    ci.parent_joint.assign(nlb, -1);
+    for (size_t k = 0; k < B->joints.size(); ++k) ci.parent_joint[B->joints[k].child_link] = (int)k;
+    std::vector<double> radius_cache(nlb, -1.0);
+    auto rad = [&](int l) { if (radius_cache[l] < 0) radius_cache[l] = link_radius(B->links[l]); return radius_cache[l]; };
+
+    // ---- pairs of the batched plan whose relative pose depends on one or two active DOFs, grouped by that DOF set
+    struct Cand { int p; int a, ob, j, cls; std::vector<int> dofs; std::vector<double> K; };
+    std::vector<Cand> cands;
+    for (int p : Q->p_main) {
+        Cand c;
+        c.p = p; c.a = Q->quads[4 * p]; c.ob = Q->quads[4 * p + 1]; c.j = Q->quads[4 * p + 2]; c.cls = Q->quads[4 * p + 3];
+        if (c.a >= nlb || (c.cls == 1 && c.j >= nlb)) continue;
+        const double rb = c.cls == 1 ? rad(c.j) : link_radius(S->bodies[c.ob]->links[c.j]);
+        if (!pair_rates(*B, ci, col_of_dof, c.a, c.cls == 1 ? c.j : -1, rad(c.a), rb, c.dofs, c.K)) continue;
+        if (c.cls == 1) {
+            // the same pair with the roles swapped (a followed from b's frame) is an equally valid bound: keep the tighter one
+            std::vector<int> d2; std::vector<double> K2;
+            if (pair_rates(*B, ci, col_of_dof, c.j, c.a, rb, rad(c.a), d2, K2) && d2.size() == c.dofs.size()) {
+                double s1 = 0, s2 = 0;
+                for (double k : c.K) s1 += k;
+                for (double k : K2) s2 += k;
+                if (s2 < s1) { c.dofs = d2; c.K = K2; }
+            }
+        }
+        // canonical DOF order inside the pair
+        if (c.dofs.size() == 2 && c.dofs[0] > c.dofs[1]) { std::swap(c.dofs[0], c.dofs[1]); std::swap(c.K[0], c.K[1]); }
+        cands.push_back(c);
+    }
+    if (cands.empty()) return CC_OK;
+    std::sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.dofs < y.dofs; });
+
+    std::vector<ccdev::PairTable> tables;
+    std::vector<uint32_t> bits;
+    std::vector<int32_t> table_of_orig(Q->quads.size() / 4, -1);
+    std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
+    const double margin = 3e-4;
+    const size_t max_bits_words = (size_t)1 << 20;                  // 4 MB of tables at most
+    // One pass over a set of candidates that share their DOF set, on an n0 x n1 grid.  Pairs certified in every cell are
+    // marked dropped; with `final` the partly certified ones get their bit table, otherwise they are returned for a finer pass.
+    auto grid_pass = [&](const std::vector<size_t>& members, int n0, int n1, bool final, std::vector<size_t>& undecided) -> int {
+        const std::vector<int>& dofs = cands[members[0]].dofs;
+        const int nd = (int)dofs.size();
+        const cc_joint& j0 = *joint_of_dof[dofs[0]];
+        const cc_joint* j1 = nd == 2 ? joint_of_dof[dofs[1]] : nullptr;
+        const double w0 = (j0.upper - j0.lower) / n0, w1 = j1 ? (j1->upper - j1->lower) / n1 : 0.0;
+        if (!(w0 > 0) || (j1 && !(w1 > 0))) return CC_OK;
+        // one pairs-query for the whole set: env-class triples keep their order, then the self-class ones
+        std::vector<int32_t> triples;
+        std::vector<size_t> order;                                  // candidate index of every pair of the group query
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t i : members)
+                if ((cands[i].cls == 1) == (pass == 1)) {
+                    triples.push_back(cands[i].a); triples.push_back(cands[i].cls == 1 ? Q->body : cands[i].ob); triples.push_back(cands[i].j);
+                    order.push_back(i);
+                }
+        double cap = 0;
+        std::vector<double> delta(order.size());
+        for (size_t k = 0; k < order.size(); ++k) {
+            const Cand& c = cands[order[k]];
+            delta[k] = 0.5 * w0 * c.K[0] + (j1 ? 0.5 * w1 * c.K[1] : 0.0);
+            cap = std::max(cap, delta[k] + margin);
+        }
+        cc_query* PQ = nullptr;
+        int rc = cc_query_create_pairs(S, Q->body, triples.data(), (int)order.size(), &PQ);
+        if (rc != CC_OK) return rc;
+        const int ncell = n0 * n1;
+        std::vector<double> rows((size_t)ncell * B->ndof);
+        for (int i0 = 0; i0 < n0; ++i0)
+            for (int i1 = 0; i1 < n1; ++i1) {
+                double* r = &rows[((size_t)i0 * n1 + i1) * B->ndof];
+                for (int d = 0; d < B->ndof; ++d) r[d] = B->dofvals[d];
+                r[dofs[0]] = j0.lower + (i0 + 0.5) * w0;
+                if (j1) r[dofs[1]] = j1->lower + (i1 + 0.5) * w1;
+            }
+        if (!PQ->dist_ready) {
+            std::vector<uint8_t> all_dynamic(PQ->nq, 1);
+            rc = build_plan(PQ, PQ->dist, PQ->p_full, all_dynamic, true);
+            if (rc != CC_OK) { cc_query_destroy(PQ); return rc; }
+            CC_CUDA(cudaDeviceSynchronize());
+            PQ->dist_ready = true;
+        }
+        const int npd = (int)PQ->dist.pairs.size();
+        std::vector<double> dist((size_t)ncell * std::max(1, npd));
+        if (npd > 0)
+            rc = launch_distance(PQ, PQ->dist, false, rows.data(), ncell, CC_BATCH_ENV | CC_BATCH_SELF, cap * 1.01 + 1e-3, 0.0, 0.0,
+                                 dist.data(), nullptr, nullptr, true);
+        if (rc != CC_OK) { cc_query_destroy(PQ); return rc; }
+        const double two_pi = 6.283185307179586476925286766559;
+        auto partial_circle = [&](const cc_joint* j) { return j && j->is_circular && (j->upper - j->lower) < two_pi - 1e-6; };
+        for (int dp = 0; dp < npd; ++dp) {
+            const size_t k = (size_t)PQ->dist.orig[dp];             // index into `order`
+            const Cand& c = cands[order[k]];
+            size_t nfree = 0;
+            std::vector<uint32_t> tb((ncell + 31) / 32, 0u);
+            double dmin = 1e30;
+            for (int i = 0; i < ncell; ++i) {
+                const double d = dist[(size_t)i * npd + dp];
+                dmin = std::min(dmin, d);
+                if (d > delta[k] + margin) { tb[i >> 5] |= 1u << (i & 31); ++nfree; }
+            }
+            if (getenv("CC_DEBUG_TABLES"))
+                fprintf(stderr, "[tables] %s x %s/%s: %d DOF, grid %d x %d, K = %.3f %.3f, delta = %.4f m, min dist = %.4f m, certified cells %.1f%%\n",
+                        B->links[c.a].name.c_str(), c.cls == 1 ? B->name.c_str() : S->bodies[c.ob]->name.c_str(),
+                        (c.cls == 1 ? B->links[c.j] : S->bodies[c.ob]->links[c.j]).name.c_str(), nd, n0, n1, c.K[0], nd == 2 ? c.K[1] : 0.0,
+                        delta[k], dmin, 100.0 * nfree / ncell);
+            // never in contact inside the joint limits: the pair can leave the plan — unless a circular DOF covers only part of
+            // the circle (SetDOFValues does not clamp those, so values outside the grid exist): then it keeps a table
+            if (nfree == (size_t)ncell && !partial_circle(&j0) && !partial_circle(j1)) { dropped[c.p] = 1; continue; }
+            if (!final) { undecided.push_back(order[k]); continue; }
+            if (nfree * 10 < (size_t)ncell || bits.size() + tb.size() > max_bits_words) continue;
+            ccdev::PairTable T;
+            memset(&T, 0, sizeof(T));
+            T.col0 = col_of_dof[dofs[0]]; T.col1 = j1 ? col_of_dof[dofs[1]] : -1;
+            T.n0 = n0; T.n1 = n1;
+            T.circ0 = !j0.is_circular ? 0 : (partial_circle(&j0) ? 1 : 2);
+            T.circ1 = !j1 || !j1->is_circular ? 0 : (partial_circle(j1) ? 1 : 2);
+            T.lo0 = j0.lower; T.hi0 = j0.upper; T.inv0 = 1.0 / w0;
+            T.lo1 = j1 ? j1->lower : 0.0; T.hi1 = j1 ? j1->upper : 0.0; T.inv1 = j1 ? 1.0 / w1 : 0.0;
+            T.bit_base = (uint32_t)bits.size() * 32u;
+            bits.insert(bits.end(), tb.begin(), tb.end());
+            table_of_orig[c.p] = (int32_t)tables.size();
+            tables.push_back(T);
+        }
+        cc_query_destroy(PQ);
+        return CC_OK;
+    };
+    // coarse grid first (far-apart pairs certify there for a hundredth of the cost), the fine grid only for what is left
+    for (size_t g0 = 0; g0 < cands.size();) {
+        size_t g1 = g0;
+        while (g1 < cands.size() && cands[g1].dofs == cands[g0].dofs) ++g1;
+        std::vector<size_t> members, undecided, none;
+        for (size_t i = g0; i < g1; ++i) members.push_back(i);
+        const bool one = cands[g0].dofs.size() == 1;
+        int rc = grid_pass(members, one ? 64 : 32, one ? 1 : 32, false, undecided);
+        if (rc != CC_OK) return rc;
+        if (!undecided.empty()) {
+            std::sort(undecided.begin(), undecided.end());
+            rc = grid_pass(undecided, one ? 1024 : 256, one ? 1 : 256, true, none);
+            if (rc != CC_OK) return rc;
+        }
+        g0 = g1;
+    }
+
+    // ---- certified-free pairs leave the batched plan
+    CC_CUDA(cudaSetDevice(S->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    std::vector<int> p_keep;
+    for (int p : Q->p_main) {
+        if (dropped[p]) { Q->ndropped++; continue; }
+        p_keep.push_back(p);
+    }
+    if (getenv("CC_DEBUG_TABLES"))
+        fprintf(stderr, "[tables] plan before: %zu pairs, %d dynamic slots, %d static, %zu fk steps; dropping %d\n", Q->mainl.pairs.size(), Q->mainl.ndyn,
+                Q->mainl.nstatic, Q->mainl.steps.size(), Q->ndropped);
+    if (Q->ndropped > 0) {
+        std::vector<uint8_t> main_dynamic(Q->nq, 0);
+        for (int p : p_keep) {
+            const int a = Q->quads[4 * p];
+            if (Q->moves[a]) main_dynamic[a] = 1;
+            if (Q->quads[4 * p + 3] == 1) { const int b2 = Q->quads[4 * p + 2]; if (Q->moves[b2]) main_dynamic[b2] = 1; }
+        }
+        int rc = build_plan(Q, Q->mainl, p_keep, main_dynamic, true);
+        if (rc != CC_OK) return rc;
+        Q->p_main = p_keep;
+    }
+    if (getenv("CC_DEBUG_TABLES"))
+        fprintf(stderr, "[tables] plan after: %zu pairs, %d dynamic slots, %d static, %zu fk steps, %zu tables\n", Q->mainl.pairs.size(), Q->mainl.ndyn,
+                Q->mainl.nstatic, Q->mainl.steps.size(), tables.size());
+    const Plan& pl = Q->mainl;
+    if (!tables.empty()) {
+        std::vector<int32_t> t(pl.orig.size(), -1);
+        for (size_t i = 0; i < t.size(); ++i) t[i] = table_of_orig[pl.orig[i]];
+        CC_CUDA(Q->d_tables.upload(tables));
+        CC_CUDA(Q->d_table_bits.upload(bits));
+        CC_CUDA(Q->d_pair_table.upload(t));
+        for (int si = 0; si < 3; ++si) {
+            std::vector<int32_t> ts(pl.split[si].orig.size(), -1);
+            for (size_t i = 0; i < ts.size(); ++i) ts[i] = table_of_orig[pl.split[si].orig[i]];
+            CC_CUDA(Q->d_pair_table_split[si].upload(ts));
+        }
+    }
+    CC_CUDA(cudaDeviceSynchronize());
+    Q->ntables = (int)tables.size();
+    return CC_OK;
+}
+
+// Tables cost a few hundred milliseconds to build: they are built once a query has seen enough batched configurations.
+static int maybe_build_tables(cc_query* q, int n)
+{
+    if (q->tables_done) return CC_OK;
+    static const long long after = getenv("CC_TUNE_TABLES_AFTER") ? atoll(getenv("CC_TUNE_TABLES_AFTER")) : 16384;
+    q->fk_configs_seen += (uint64_t)n;
+    if ((long long)q->fk_configs_seen < after) return CC_OK;
+    return build_pair_tables(q);
+}
 
 // ================================================================================================ C ABI
 extern "C" {
@@ -930,6 +1269,7 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
             pn.push_back(ne);
             pb.push_back((int32_t)sp.size());
         }
+        pl.split[si].orig = so;
         CC_CUDA(pl.split[si].d_pairs.upload(sp)); CC_CUDA(pl.split[si].d_orig.upload(so));
         CC_CUDA(pl.split[si].d_part_begin.upload(pb)); CC_CUDA(pl.split[si].d_part_nenv.upload(pn));
     }
@@ -965,6 +1305,7 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
         col_of_dof[act[c]] = (int)c;
     }
     Q->ncols = (int)act.size();
+    Q->col_of_dof = col_of_dof;
     Q->cur_active.resize(act.size());
     for (size_t c = 0; c < act.size(); ++c) Q->cur_active[c] = B->dofvals[act[c]];
     auto affects = [&](int d, int l) { return B->affects[(size_t)d * nlb + Q->ql_host[l]] != 0; };
@@ -1064,7 +1405,10 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
         if (Q->quads[4 * p + 3] == 1) { const int b = Q->quads[4 * p + 2]; if (moves[b]) main_dynamic[b] = 1; }
     }
     CC_CUDA(cudaSetDevice(S->device));
+    Q->p_main = p_main;
+    Q->moves = moves;
     Q->p_full = p_full;
+    Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size();     // not with grabbed links (their chain is not walked below)
     int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
     if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
@@ -1327,6 +1671,7 @@ int cc_check_batch_device(cc_query* q, const double* d_q, int n, int flags, uint
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     CC_CUDA(cudaSetDevice(q->scene->device));
     const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    { int rc = maybe_build_tables(q, n); if (rc != CC_OK) return rc; }
     return launch(q, q->mainl, true, d_q, n, f, d_verdict, d_fe, d_fs, d_mask, nullptr, (cudaStream_t)stream);
 }
 
@@ -1359,6 +1704,7 @@ int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags, uint
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    { int rc = maybe_build_tables(q, n); if (rc != CC_OK) return rc; }
     return run_host(q, dof_values, (size_t)n * q->ncols, n, f, false, verdict, first_env, first_self, pair_mask, nullptr);
 }
 
@@ -1429,6 +1775,21 @@ int cc_scene_set_counters(cc_scene* s, int enabled)
 {
     if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
     s->counters = enabled != 0;
+    return CC_OK;
+}
+
+int cc_scene_set_pair_tables(cc_scene* s, int enabled)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    s->pair_tables = enabled != 0;
+    return CC_OK;
+}
+
+int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped)
+{
+    if (!q) return fail(CC_ERR_INVALID, "bad arguments");
+    if (out_tables) *out_tables = q->ntables > 0 ? q->ntables : 0;
+    if (out_dropped) *out_dropped = q->ndropped;
     return CC_OK;
 }
 
