@@ -648,7 +648,8 @@ std::vector<int> path_to_root(const HBody& B, const ChainInfo& ci, int l)
 double joint_span(const cc_joint& j)     // largest change of |child origin - parent origin| contribution of one joint
 {
     double s = norm3(j.left + 4) + norm3(j.right + 4);
-    if (!j.is_static && j.type == CC_JOINT_PRISMATIC) s += norm3(j.axis) * std::max(fabs(j.lower), fabs(j.upper));
+    // (a mimic joint's value may sit up to 5e-4 outside its limits, kinbody.cpp:2326-2386: 1e-3 covers that)
+    if (!j.is_static && j.type == CC_JOINT_PRISMATIC) s += norm3(j.axis) * (std::max(fabs(j.lower), fabs(j.upper)) + (j.mimic_dof >= 0 ? 1e-3 : 0.0));
     return s;
 }
 
@@ -739,10 +740,74 @@ static int build_pair_tables(cc_query* Q)
     std::vector<double> radius_cache(nlb, -1.0);
     auto rad = [&](int l) { if (radius_cache[l] < 0) radius_cache[l] = link_radius(B->links[l]); return radius_cache[l]; };
 
+    std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
+    const double margin = 3e-4;
+    // ---- reach certificate (any number of DOFs): every point of a link stays inside a ball around the anchor of the first
+    // varying joint on its path from the base (a fixed point of the world: everything above that joint is fixed), of radius
+    // chain length below the anchor + the link's radius.  An environment link whose world AABB is farther from the centre than
+    // that radius can never touch the link.
+    {
+        std::vector<double> ball(4 * (size_t)nlb, -1.0);            // per link: centre xyz, radius (radius < 0: none)
+        for (int l = 0; l < nlb; ++l) {
+            std::vector<int> path = path_to_root(*B, ci, l);        // child-to-parent order
+            int first = -1;                                         // the varying joint closest to the root
+            bool ok = true;
+            for (int idx = (int)path.size() - 1; idx >= 0 && ok; --idx) {
+                const cc_joint& J = B->joints[path[idx]];
+                if (J.mimic_dof >= 0) { if (col_of_dof[J.mimic_dof] >= 0) { if (first < 0) ok = false; } continue; }
+                if (!J.is_static && J.dof_index >= 0 && col_of_dof[J.dof_index] >= 0 && first < 0) first = idx;
+            }
+            if (!ok || first < 0) continue;
+            const cc_joint& JF = B->joints[path[first]];
+            double radius = norm3(JF.right + 4) + rad(l);
+            if (JF.type == CC_JOINT_PRISMATIC) radius += norm3(JF.axis) * std::max(fabs(JF.lower), fabs(JF.upper));
+            for (int idx = first - 1; idx >= 0; --idx) radius += joint_span(B->joints[path[idx]]);
+            // anchor = origin of (parent link pose * left); the parent link does not move with the active DOFs
+            const double* x = B->links[JF.parent_link].xf;
+            const double il = 2.0 / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+            const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+            const double Rm[9] = {1 - il * (q2 * q2 + q3 * q3), il * (q1 * q2 - q0 * q3), il * (q1 * q3 + q0 * q2),
+                                  il * (q1 * q2 + q0 * q3), 1 - il * (q1 * q1 + q3 * q3), il * (q2 * q3 - q0 * q1),
+                                  il * (q1 * q3 - q0 * q2), il * (q2 * q3 + q0 * q1), 1 - il * (q1 * q1 + q2 * q2)};
+            const double* tl = JF.left + 4;
+            for (int r = 0; r < 3; ++r) ball[4 * l + r] = x[4 + r] + Rm[3 * r] * tl[0] + Rm[3 * r + 1] * tl[1] + Rm[3 * r + 2] * tl[2];
+            ball[4 * l + 3] = radius;
+        }
+        for (int p : Q->p_main) {
+            if (Q->quads[4 * p + 3] != 0) continue;
+            const int a = Q->quads[4 * p];
+            if (a >= nlb || ball[4 * a + 3] < 0) continue;
+            const HLink& E = S->bodies[Q->quads[4 * p + 1]]->links[Q->quads[4 * p + 2]];
+            if (E.nodes.empty()) continue;
+            // world AABB of the environment link's (already inflated) root box, in double
+            const double* x = E.xf;
+            const double il = 2.0 / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+            const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+            const double Rm[9] = {1 - il * (q2 * q2 + q3 * q3), il * (q1 * q2 - q0 * q3), il * (q1 * q3 + q0 * q2),
+                                  il * (q1 * q2 + q0 * q3), 1 - il * (q1 * q1 + q3 * q3), il * (q2 * q3 - q0 * q1),
+                                  il * (q1 * q3 - q0 * q2), il * (q2 * q3 + q0 * q1), 1 - il * (q1 * q1 + q2 * q2)};
+            double d2 = 0;
+            for (int r = 0; r < 3; ++r) {
+                double c = x[4 + r], e = 0;
+                for (int k = 0; k < 3; ++k) { c += Rm[3 * r + k] * (double)E.nodes[0].c[k]; e += fabs(Rm[3 * r + k]) * (double)E.nodes[0].e[k]; }
+                const double g = fabs(ball[4 * a + r] - c) - e;
+                if (g > 0) d2 += g * g;
+            }
+            const double reach = ball[4 * a + 3] + margin;
+            if (d2 > reach * reach) dropped[p] = 1;
+        }
+        if (getenv("CC_DEBUG_TABLES")) {
+            size_t nd = 0;
+            for (uint8_t d : dropped) nd += d;
+            fprintf(stderr, "[tables] reach certificate: %zu environment pairs can never be reached\n", nd);
+        }
+    }
+
     // ---- pairs of the batched plan whose relative pose depends on one or two active DOFs, grouped by that DOF set
     struct Cand { int p; int a, ob, j, cls; std::vector<int> dofs; std::vector<double> K; };
     std::vector<Cand> cands;
     for (int p : Q->p_main) {
+        if (dropped[p]) continue;
         Cand c;
         c.p = p; c.a = Q->quads[4 * p]; c.ob = Q->quads[4 * p + 1]; c.j = Q->quads[4 * p + 2]; c.cls = Q->quads[4 * p + 3];
         if (c.a >= nlb || (c.cls == 1 && c.j >= nlb)) continue;
@@ -762,14 +827,11 @@ static int build_pair_tables(cc_query* Q)
         if (c.dofs.size() == 2 && c.dofs[0] > c.dofs[1]) { std::swap(c.dofs[0], c.dofs[1]); std::swap(c.K[0], c.K[1]); }
         cands.push_back(c);
     }
-    if (cands.empty()) return CC_OK;
     std::sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.dofs < y.dofs; });
 
     std::vector<ccdev::PairTable> tables;
     std::vector<uint32_t> bits;
     std::vector<int32_t> table_of_orig(Q->quads.size() / 4, -1);
-    std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
-    const double margin = 3e-4;
     const size_t max_bits_words = (size_t)1 << 20;                  // 4 MB of tables at most
     // One pass over a set of candidates that share their DOF set, on an n0 x n1 grid.  Pairs certified in every cell are
     // marked dropped; with `final` the partly certified ones get their bit table, otherwise they are returned for a finer pass.
