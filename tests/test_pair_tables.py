@@ -43,6 +43,26 @@ def test_tables_do_not_change_results(scene, manip, expect_tables):
         a2 = on.CheckCollisionBatch(robot, q[:n], active=active)
         assert np.array_equal(a2["verdict"], b["verdict"][:n]) and np.array_equal(a2["first_env_index"], b["first_env_index"][:n])
         assert np.array_equal(a2["first_self_index"], b["first_self_index"][:n])
+    # adversarial inputs for the cell lookup: values exactly on / beyond the joint limits (SetDOFValues clamps them), circular
+    # DOFs several turns away (not clamped: the lookup wraps them), values on cell boundaries
+    idx = list(range(robot.GetDOF())) if active is None else list(active)
+    lo = np.array([robot.joints[d].lower for d in idx]); hi = np.array([robot.joints[d].upper for d in idx])
+    circ = np.array([bool(robot.joints[d].circular) for d in idx])
+    rng = np.random.default_rng(5)
+    qa = q[:60000].copy()
+    pick = rng.random(qa.shape)
+    qa = np.where(pick < 0.05, lo, qa)
+    qa = np.where((pick >= 0.05) & (pick < 0.10), hi, qa)
+    qa = np.where((pick >= 0.10) & (pick < 0.15) & ~circ, hi + 0.3, qa)
+    qa = np.where((pick >= 0.15) & (pick < 0.20) & ~circ, lo - 0.3, qa)
+    cells = lo + np.round((qa - lo) / (hi - lo) * 256) * (hi - lo) / 256            # on 256-cell boundaries
+    qa = np.where((pick >= 0.20) & (pick < 0.30), cells, qa)
+    turns = rng.integers(-2, 3, size=qa.shape) * (2 * np.pi)
+    qa = np.where(circ, qa + turns, qa)
+    a3 = on.CheckCollisionBatch(robot, qa, active=active)
+    b3 = off.CheckCollisionBatch(robot2, qa, active=active)
+    assert np.array_equal(a3["verdict"], b3["verdict"]) and np.array_equal(a3["first_env_index"], b3["first_env_index"])
+    assert np.array_equal(a3["first_self_index"], b3["first_self_index"])
     # complete pair masks too
     m1 = on.CheckCollisionBatch(robot, q[:3000], active=active, all_pairs=True)["mask"]
     m2 = off.CheckCollisionBatch(robot2, q[:3000], active=active, all_pairs=True)["mask"]
