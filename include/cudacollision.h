@@ -212,6 +212,13 @@ int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, d
 int cc_distance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double max_distance, double rel_err,
                       double abs_err, double* min_distance, int32_t* min_pair, double* closest_points);
 
+/* ---- CO_UseTolerance (collisionPQP.h:650-657: PQP_Tolerance per visited pair, report->numWithinTol).  within_mask
+ * [n][mask_words]: bit p set <=> pair p (cc_query_get_pairs) is no farther apart than `tolerance` metres (distance <=
+ * tolerance, pqp/PQP.cpp:1056; colliding pairs included).  The plugin turns the bits into numWithinTol the way
+ * CheckCollisionP does: the number of other bodies with at least one pair within tolerance (collisionPQP.h:443-497). */
+int cc_tolerance_batch(cc_query* q, const double* dof_values, int n, int flags, double tolerance, uint32_t* within_mask);
+int cc_tolerance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double tolerance, uint32_t* within_mask);
+
 /* Page-locked host buffers for the host-buffer entry points (cc_check_batch, cc_check_poses, cc_fk_batch).  Those calls
  * cut a big batch into chunks and copy each chunk's inputs / results on the chunk's own stream; with buffers from
  * cc_host_alloc the copies overlap the kernels of the neighbouring chunk.  Ordinary (pageable) memory stays valid

@@ -49,7 +49,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_query_get_pairs", "cc_check_batch", "cc_check_batch_device", "cc_check_poses", "cc_fk_batch",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
-           "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count"]
+           "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
+           "cc_tolerance_batch", "cc_tolerance_poses"]
 
 _lib = None
 
@@ -88,6 +89,8 @@ def load_library():
     lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
+    lib.cc_tolerance_batch.argtypes = [vp, vp, ci, ci, cd, vp]
+    lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
     lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
@@ -233,6 +236,20 @@ class BoundQuery(object):
                             _ptr(pair), _ptr(pts)))
         return dist, pair, pts
 
+    def within_tolerance(self, tolerance, q=None, flags=BATCH_ENV | BATCH_SELF, poses=None):
+        """CO_UseTolerance: [n, npairs] bool, pair p no farther apart than `tolerance` (PQP_Tolerance semantics)."""
+        if poses is not None:
+            a = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
+            fn = self.lib.cc_tolerance_poses
+        else:
+            a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+            fn = self.lib.cc_tolerance_batch
+        n = a.shape[0]
+        mask = np.zeros((n, self.info.mask_words), dtype=np.uint32)
+        self.checker._ck(fn(self.handle, _ptr(a), n, flags, float(tolerance), _ptr(mask)))
+        bits = (mask[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
+        return bits.reshape(n, -1)[:, :self.npairs].astype(bool)
+
     def decode_pair(self, idx):
         """pair indices -> [n, 3] {query link, other body id, other link} (oracle layout), -1 rows where idx < 0."""
         out = np.full((len(idx), 3), -1, dtype=np.int32)
@@ -299,8 +316,8 @@ class CudaCollisionChecker(object):
 
     # ---- CollisionCheckerBase surface (collisionchecker.h:200-237)
     def SetCollisionOptions(self, options):
-        if options & (CO_UseTolerance | CO_Contacts):
-            return False   # tolerance counts / contact points of colliding pairs are not provided by this checker
+        if options & CO_Contacts:
+            return False   # contact points of colliding pairs are not provided by this checker
         if options != self._options:
             self._options = int(options)
             self._invalidate()
@@ -310,7 +327,10 @@ class CudaCollisionChecker(object):
         return self._options
 
     def SetTolerance(self, tol):
-        return False
+        """collisionPQP.h:426-428: enables the tolerance count and sets its threshold."""
+        self._tolerance = float(tol)
+        self.SetCollisionOptions(self._options | CO_UseTolerance)
+        return True
 
     def InitEnvironment(self):
         self._drop_queries()
@@ -534,6 +554,10 @@ class CudaCollisionChecker(object):
                 report.minDistance = 0
             if report is not None and (self._options & CO_Distance) and not hit:
                 self._fill_distance(bq, a, BATCH_ENV, report)
+            if report is not None and (self._options & CO_UseTolerance):
+                # numWithinTol = other bodies with at least one link pair within tolerance (collisionPQP.h:443-497)
+                w = bq.within_tolerance(getattr(self, "_tolerance", 0.0), flags=BATCH_ENV, poses=T)[0]
+                report.numWithinTol = len(set(int(bq.pairs[p, 1]) for p in np.nonzero(w[:bq.info.npairs_env])[0]))
             return hit
         if isinstance(a, KinBody) and isinstance(b, KinBody):
             triples = [(l1.index, self.body_id(b), l2.index) for l1 in a.links for l2 in b.links]

@@ -1811,6 +1811,54 @@ int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double ma
     return launch_distance(q, q->full, true, T8, n, flags, max_distance, rel_err, abs_err, min_distance, min_pair, closest_points);
 }
 
+// CO_UseTolerance: which pairs are within `tolerance` of each other (PQP_Tolerance: distance <= tolerance, pqp/PQP.cpp:1056).
+// Per-pair mode of the distance kernel with the search radius just above the tolerance; one bit per pair of the query.
+static int tolerance_common(cc_query* q, const Plan& pl, bool pose_mode, const double* in, int n, int flags, double tolerance,
+                            uint32_t* within_mask)
+{
+    if (n == 0) return CC_OK;
+    const int npd = (int)pl.pairs.size();
+    memset(within_mask, 0, (size_t)n * q->mask_words * sizeof(uint32_t));
+    if (npd == 0) return CC_OK;
+    std::vector<double> dist((size_t)n * npd);
+    int rc = launch_distance(q, pl, pose_mode, in, n, flags, tolerance * 1.001 + 1e-6, 0.0, 0.0, dist.data(), nullptr, nullptr, true);
+    if (rc != CC_OK) return rc;
+    const bool env = (flags & CC_BATCH_ENV) != 0, self = (flags & CC_BATCH_SELF) != 0;
+    for (int c = 0; c < n; ++c)
+        for (int k = 0; k < npd; ++k) {
+            const bool is_env = k < pl.nenv;
+            if ((is_env && !env) || (!is_env && !self)) continue;
+            if (dist[(size_t)c * npd + k] <= tolerance) {
+                const int p = pl.orig[k];
+                within_mask[(size_t)c * q->mask_words + (p >> 5)] |= 1u << (p & 31);
+            }
+        }
+    return CC_OK;
+}
+
+int cc_tolerance_batch(cc_query* q, const double* dof_values, int n, int flags, double tolerance, uint32_t* within_mask)
+{
+    if (!q || n < 0 || !within_mask || !(tolerance >= 0) || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_tolerance_poses");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    if (!q->dist_ready) {
+        CC_CUDA(cudaSetDevice(q->scene->device));
+        std::vector<uint8_t> all_dynamic(q->nq, 1);
+        int rc = build_plan(q, q->dist, q->p_full, all_dynamic, true);
+        if (rc != CC_OK) return rc;
+        CC_CUDA(cudaDeviceSynchronize());
+        q->dist_ready = true;
+    }
+    return tolerance_common(q, q->dist, false, dof_values, n, flags, tolerance, within_mask);
+}
+
+int cc_tolerance_poses(cc_query* q, const double* T8, int n, int flags, double tolerance, uint32_t* within_mask)
+{
+    if (!q || n < 0 || !within_mask || !(tolerance >= 0) || (n > 0 && !T8)) return fail(CC_ERR_INVALID, "bad arguments");
+    if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    return tolerance_common(q, q->full, true, T8, n, flags, tolerance, within_mask);
+}
+
 int cc_host_alloc(size_t bytes, void** out)
 {
     if (!out) return fail(CC_ERR_INVALID, "out is NULL");

@@ -77,6 +77,7 @@ def _load(kind):
     lib.orc_check_link_pairs.argtypes = [vp, ci, vp, vp, ci, vp]
     lib.orc_check_batch.argtypes = [vp, ci, vp, ci, ctypes.POINTER(OrcOptions), vp, ci, vp, vp, vp, vp, vp, vp, vp,
                                     ctypes.c_int64, vp, vp]
+    lib.orc_pair_queries.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, cd, cd, vp, vp]
     lib.orc_distance_batch.argtypes = [vp, ci, vp, ci, vp, vp, ci, cd, vp, vp]
     lib.orc_time_batch.restype = cd
     lib.orc_time_batch.argtypes = [vp, ci, vp, ci, ci, ci, vp, ci, vp]
@@ -263,6 +264,23 @@ class OracleChecker(object):
         self.lib.orc_distance_batch(self.scene, bid, _ptr(act), len(active), ctypes.byref(opt), _ptr(q), n,
                                     float(max_distance), _ptr(dist), _ptr(pair))
         return dict(distance=dist, pair=pair)
+
+    def pair_queries(self, body, q, triples, active=None, cap=0.0, tolerance=0.0):
+        """Per configuration and (query link, other body id, other link) triple: exact distance clipped at `cap`, and
+        PQP_Tolerance's verdict at `tolerance`.  Returns (dist [n, m], within [n, m] bool)."""
+        self._sync()
+        bid = self._sync_kinematics(body)
+        if active is None:
+            active = body.GetActiveDOFIndices() if body.is_robot else list(range(body.GetDOF()))
+        act = np.array(active, dtype=np.int32)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active))
+        tr = np.ascontiguousarray(np.array(triples, dtype=np.int32).reshape(-1, 3))
+        n, m = q.shape[0], tr.shape[0]
+        dist = np.zeros((n, m), dtype=np.float64)
+        within = np.zeros((n, m), dtype=np.uint8)
+        self.lib.orc_pair_queries(self.scene, bid, _ptr(act), len(act), _ptr(q), n, _ptr(tr), m, float(cap), float(tolerance),
+                                  _ptr(dist), _ptr(within))
+        return dist, within.astype(bool)
 
     def time_batch(self, body, q, active=None, flags=BATCH_ENV | BATCH_SELF):
         self._sync()

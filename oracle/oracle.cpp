@@ -1437,6 +1437,38 @@ int orc_distance_batch(void* sp, int body, const int32_t* active, int nactive, c
     return 0;
 }
 
+// Per-pair queries on a batch (parity of CO_UseTolerance and of the per-pair mode of the product's distance kernel): for
+// every configuration and every listed (query link, other body, other link) triple, the exact distance clipped at `cap`
+// (cap <= 0: unbounded) and PQP_Tolerance's verdict at `tolerance` (the reference's own routine in the _ref build,
+// pqp/PQP.cpp:1000-1180; the restated inflated descent otherwise).  Query links follow the robot-only layout.
+int orc_pair_queries(void* sp, int body, const int32_t* active, int nactive, const double* q, int n, const int32_t* triples,
+                     int ntriples, double cap, double tolerance, double* dist_out, uint8_t* within_out)
+{
+    Scene* s = (Scene*)sp;
+    Body* b = s->bodies[body];
+    std::vector<double> vals(b->dofvals);
+    std::vector<Xf> xf;
+    for (int c = 0; c < n; ++c) {
+        for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * nactive + a];
+        forward_kinematics(*b, &vals[0], b->xf[0], xf);
+        for (int k = 0; k < ntriples; ++k) {
+            const int la = triples[3 * k], ob = triples[3 * k + 1], lb = triples[3 * k + 2];
+            const LinkModel& A = *b->links[la];
+            const LinkModel& Bm = *s->bodies[ob]->links[lb];
+            const Xf& xb = ob == body ? xf[lb] : s->bodies[ob]->xf[lb];
+            double d = cap > 0 ? cap : 1e30;
+            bool w = false;
+            if (A.valid && Bm.valid) {
+                if (dist_out) d = links_distance(xf[la], A, xb, Bm, d);
+                if (within_out) w = links_within(xf[la], A, xb, Bm, tolerance);
+            }
+            if (dist_out) dist_out[(size_t)c * ntriples + k] = d;
+            if (within_out) within_out[(size_t)c * ntriples + k] = w ? 1 : 0;
+        }
+    }
+    return 0;
+}
+
 // Single-thread timing helper for the CPU baseline: runs orc_check_batch semantics (no band, no outputs
 // except verdicts) and returns elapsed seconds.
 double orc_time_batch(void* sp, int body, const int32_t* active, int nactive, int options, int flags,

@@ -134,3 +134,47 @@ def test_gpu_distance_pr2_and_report_path():
             pos, norm, depth = rep.contacts[0]
             assert abs(-depth - rep.minDistance) < TOL and abs(np.linalg.norm(norm) - 1) < 1e-6
             assert rep.plink1.name == robot.links[want["pair"][0][0]].name
+
+
+@pytest.mark.skipif(not have_ref_oracle(), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_tolerance_restatement_equals_reference_pqp():
+    """PQP_Tolerance of the unmodified library == (exact distance <= tolerance) of the restatement, pair by pair."""
+    _, robot, port, active = _lab1("port", True)
+    _, robot2, ref, _ = _lab1("reference", True)
+    by = port._bodies_by_id()
+    triples = [(l.index, bid, ol.index) for l in robot.links[1:9] for bid, b in by.items() if b is not robot for ol in b.links][:60]
+    q = sample_configs(robot, 25, seed=43, active=active)
+    tol = 0.05
+    d, _ = port.pair_queries(robot, q, triples, active=active, cap=1.0, tolerance=tol)
+    _, w = ref.pair_queries(robot2, q, triples, active=active, cap=0.0, tolerance=tol)
+    clear = np.abs(d - tol) > 1e-9
+    assert np.array_equal((d <= tol)[clear], w[clear]) and w.any() and not w.all()
+
+
+@pytest.mark.gpu
+def test_gpu_tolerance_mask_equals_oracle():
+    from openrave_b200.checker import CO_ActiveDOFs, CO_UseTolerance, CudaCollisionChecker
+    from openrave_b200.environment import CollisionReport
+    _, robot, orc, active = _lab1("port", True)
+    env2, robot2, cc, _ = _lab1(lambda e: CudaCollisionChecker(e, 0), True)
+    q = sample_configs(robot, 300, seed=47, active=active)
+    tol = 0.03
+    bq = cc.bind(robot2, active)
+    w = bq.within_tolerance(tol, q)
+    # the query's pairs as (query link, other body, other link) triples on the oracle's body ids (same order of bodies)
+    triples = [(int(a), int(ob), int(j)) for a, ob, j, _ in bq.pairs]
+    d, _ = orc.pair_queries(robot, q, triples, active=active, cap=tol * 2, tolerance=tol)
+    clear = np.abs(d - tol) > TOL
+    assert np.array_equal(w[clear], (d <= tol)[clear])
+    assert w.any(axis=1).mean() > 0.2 and not w.all()
+    # the report path: numWithinTol = other bodies with a pair within tolerance (collisionPQP.h:443-497)
+    cc.SetCollisionOptions(CO_ActiveDOFs)
+    cc.SetTolerance(tol)
+    assert cc.GetCollisionOptions() & CO_UseTolerance
+    bq = cc.bind(robot2, active)
+    for row, wrow in zip(q[:6], (d <= tol)[:6]):
+        robot2.SetDOFValues(row.tolist(), active)
+        rep = CollisionReport()
+        env2.CheckCollision(robot2, report=rep)
+        want = len(set(t[1] for t, inside, cls in zip(triples, wrow, bq.pairs[:, 3]) if inside and cls == 0))
+        assert rep.numWithinTol == want
