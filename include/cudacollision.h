@@ -165,6 +165,13 @@ int cc_scene_commit(cc_scene* s);
  *   initial-pose probe (kinbody.cpp:5563-5577). */
 int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out);
 int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out);
+/* A bound query captures, at creation, the poses of every link it does not move itself (other bodies' links, links of the
+ * query body no active DOF moves, the base link) and the values of the inactive DOFs.  After cc_body_set_link_transforms /
+ * cc_body_set_dof_values on ANY body, cc_query_refresh re-reads them (a few small uploads and the re-evaluation of the
+ * pose-invariant pairs; certificates are rebuilt later) — the pair lists, hence link enable flags, attachments, grabs and
+ * meshes, must be unchanged, otherwise create a new query.  This is what lets the single-state overloads follow moving
+ * bodies the way pqprave does (it reads every transform per call, collisionPQP.h:438-463) without re-binding. */
+int cc_query_refresh(cc_query* q);
 int cc_query_destroy(cc_query* q);
 int cc_query_get_info(const cc_query* q, cc_query_info* info);
 /* pair index -> {query link, other body, other link, 0=env|1=self}, [npairs][4] */
@@ -250,6 +257,10 @@ int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_droppe
  * cc_query_get_work_trace (synchronises).  Used by the load-balance studies in profiles/. */
 int cc_query_trace_work(cc_query* q, int enabled);
 int cc_query_get_work_trace(cc_query* q, uint32_t* out_iterations, int n);
+
+/* Measured FP32 FMA throughput of a device in TFLOP/s (a short FMA-chain kernel): the denominator of the compute-side
+ * roofline figure bench.py reports next to the memory-side one. */
+int cc_device_fp32_peak(int cuda_device, double* out_tflops);
 
 /* ---- statistics (PQP_CollideResult::NumBVTests/NumTriTests analogue, pqp/PQP.cpp:489,500) */
 int cc_scene_set_counters(cc_scene* s, int enabled);

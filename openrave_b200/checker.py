@@ -50,7 +50,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
-           "cc_tolerance_batch", "cc_tolerance_poses"]
+           "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh"]
 
 _lib = None
 
@@ -83,12 +83,14 @@ def load_library():
     lib.cc_query_create.argtypes = [vp, ci, vp, ci, ci, ctypes.POINTER(vp)]
     lib.cc_query_create_pairs.argtypes = [vp, ci, vp, ci, ctypes.POINTER(vp)]
     lib.cc_query_destroy.argtypes = [vp]
+    lib.cc_query_refresh.argtypes = [vp]
     lib.cc_query_get_info.argtypes = [vp, ctypes.POINTER(cc_query_info)]
     lib.cc_query_get_pairs.argtypes = [vp, vp]
     lib.cc_check_batch.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_check_batch_device.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
+    lib.cc_device_fp32_peak.argtypes = [ci, ctypes.POINTER(cd)]
     lib.cc_tolerance_batch.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
@@ -109,6 +111,15 @@ def load_library():
 
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def device_fp32_peak(device=0):
+    """Measured FP32 FMA TFLOP/s of a CUDA device (cc_device_fp32_peak)."""
+    lib = load_library()
+    v = ctypes.c_double(0.0)
+    if lib.cc_device_fp32_peak(device, ctypes.byref(v)) != 0:
+        raise CudaCollisionError((lib.cc_last_error() or b"").decode())
+    return v.value
 
 
 class PinnedArray(object):
@@ -155,6 +166,16 @@ class BoundQuery(object):
         checker._ck(self.lib.cc_query_get_links(handle, _ptr(self.links)))
         self.links = self.links[:info.nlinks]
         self.nlinks_body = len(body.links)
+        self.stale_own = False      # the query body itself moved since the last refresh (matters to the FK-mode entries only)
+
+    def refresh(self):
+        """cc_query_refresh: re-read captured poses / inactive DOF values after bodies moved."""
+        self.checker._ck(self.lib.cc_query_refresh(self.handle))
+        self.stale_own = False
+
+    def _fresh_for_fk(self):
+        if self.stale_own:
+            self.refresh()
 
     def table_count(self):
         """How many link pairs of this query are covered by a certified free-space table (0 until the tables are built)."""
@@ -195,6 +216,7 @@ class BoundQuery(object):
 
     def check(self, q, flags=BATCH_ENV | BATCH_SELF, want_mask=False, out=None):
         """`out` = (verdict u32[n], first_env i32[n], first_self i32[n]) lets a caller reuse (pinned) result buffers."""
+        self._fresh_for_fk()
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
         n = q.shape[0]
         if out is not None:
@@ -226,6 +248,7 @@ class BoundQuery(object):
             a = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
             fn = self.lib.cc_distance_poses
         else:
+            self._fresh_for_fk()
             a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
             fn = self.lib.cc_distance_batch
         n = a.shape[0]
@@ -242,6 +265,7 @@ class BoundQuery(object):
             a = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, self.info.nlinks, 8)
             fn = self.lib.cc_tolerance_poses
         else:
+            self._fresh_for_fk()
             a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
             fn = self.lib.cc_tolerance_batch
         n = a.shape[0]
@@ -258,6 +282,7 @@ class BoundQuery(object):
         return out
 
     def fk(self, q):
+        self._fresh_for_fk()
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
         n = q.shape[0]
         out = np.zeros((n, self.info.nlinks, 8), dtype=np.float64)
@@ -274,6 +299,7 @@ class BoundQuery(object):
 
     def check_device(self, d_q_ptr, n, flags, d_verdict_ptr, d_fe_ptr, d_fs_ptr, d_mask_ptr=0, stream=0):
         """Raw device-pointer entry (torch tensors' data_ptr()); asynchronous on `stream`."""
+        self._fresh_for_fk()
         self.checker._ck(self.lib.cc_check_batch_device(self.handle, d_q_ptr, n, flags, d_verdict_ptr, d_fe_ptr, d_fs_ptr,
                                                         d_mask_ptr or None, stream or None))
 
@@ -375,9 +401,12 @@ class CudaCollisionChecker(object):
             self._ck(self.lib.cc_scene_remove_body(self.scene, bid))
             self._invalidate()
 
-    def _on_body_changed(self, body):
+    def _on_body_changed(self, body, kind="structure"):
+        """Pose changes are pushed at the next query and the cached bound queries refreshed (cc_query_refresh); anything that
+        can change a pair list (enable flags, grabs, active DOFs, geometry) drops them."""
         self._dirty.add(id(body))
-        self._invalidate()
+        if kind != "pose":
+            self._invalidate()
 
     def _invalidate(self):
         self._epoch += 1
@@ -394,8 +423,10 @@ class CudaCollisionChecker(object):
         for b in self.env.GetBodies():
             if id(b) not in self._ids:
                 self.InitKinBody(b)
+        moved = set()
         for b in self.env.GetBodies():
             if id(b) in self._dirty:
+                moved.add(id(b))
                 bid = self._ids[id(b)]
                 T = flatten.transforms8(b.GetLinkTransformations())
                 self._ck(self.lib.cc_body_set_link_transforms(self.scene, bid, _ptr(T)))
@@ -414,6 +445,14 @@ class CudaCollisionChecker(object):
                     self._ck(self.lib.cc_body_set_grabbed(self.scene, bid, gid, link, _ptr(rel), _ptr(nc) if len(nc) else None, len(nc)))
                 self._grab_epochs[id(b)] = ep
         self._ck(self.lib.cc_scene_commit(self.scene))
+        # bound queries captured poses: other bodies moving needs a refresh now, the query body's own motion only matters to
+        # the FK-mode entries (base pose, inactive DOF values) and is refreshed lazily there
+        for bq in self._queries.values():
+            own = {id(bq.body)} | {id(g.body) for g in getattr(bq.body, "grabbed", [])}
+            if moved - own:
+                bq.refresh()
+            elif moved & own:
+                bq.stale_own = True
 
     def _sync_kinematics(self, body, need_pairs=True):
         bid = self._ids[id(body)]

@@ -244,6 +244,7 @@ struct Plan {
     std::vector<uint32_t> pairs;     // slot_a | slot_b << 16
     std::vector<int32_t> orig;
     int nenv = 0, ndyn = 0, nstatic = 0, nsave = 0;
+    std::vector<std::pair<int, int>> statics;   // (body, link) of every static slot (poses refreshed by cc_query_refresh)
     std::vector<int32_t> emit;       // [nq] link -> dynamic slot or -1
     std::vector<ccdev::FkStep> steps;
     DevBuf<uint32_t> d_pairs;
@@ -286,6 +287,8 @@ struct cc_query {
     DevBuf<uint32_t> d_table_bits;
     int ndropped = 0;                        // pairs certified collision-free over the whole active range and removed
     std::vector<int> p_main;                 // original indices of the pairs of the batched FK-mode plan
+    std::vector<int> p_main_all;             // the same before any certificate removed pairs
+    std::vector<int> p_hoist;                // pose-invariant pairs
     std::vector<uint8_t> moves;              // [nq] link is moved by some active DOF
     Plan dist;                               // distance queries in FK mode: every live pair, nothing hoisted (built on first use)
     bool dist_ready = false;
@@ -1266,6 +1269,7 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         if (cls == 0) pl.nenv++;
     }
     pl.nstatic = (int)statics.size();
+    pl.statics = statics;
     if (pl.ndyn + pl.nstatic > 0xffff) return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots");
     for (size_t i = 0; i < sa_v.size(); ++i) {
         const uint32_t sa = sa_v[i] >= 0 ? (uint32_t)sa_v[i] : (uint32_t)(pl.ndyn + (-1 - sa_v[i]));
@@ -1334,6 +1338,39 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         pl.split[si].orig = so;
         CC_CUDA(pl.split[si].d_pairs.upload(sp)); CC_CUDA(pl.split[si].d_orig.upload(so));
         CC_CUDA(pl.split[si].d_part_begin.upload(pb)); CC_CUDA(pl.split[si].d_part_nenv.upload(pn));
+    }
+    return CC_OK;
+}
+
+// Evaluate the pose-invariant pairs once, with the traversal kernel, at the current DOF values; the result is merged into
+// every batched verdict as a constant mask.
+static int evaluate_hoisted(cc_query* Q)
+{
+    cc_scene* S = Q->scene;
+    const int np = (int)Q->quads.size() / 4;
+    int rc = CC_OK;
+    Q->hoisted_first_env = 0x7fffffff; Q->hoisted_first_self = 0x7fffffff;
+    Q->hoisted_mask.assign(Q->mask_words, 0u);
+    CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
+    if (!Q->hoisted.pairs.empty()) {
+        CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, Q->cur_active.size())));
+        if (!Q->cur_active.empty())
+            CC_CUDA(cudaMemcpy(Q->d_q.p, Q->cur_active.data(), Q->cur_active.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CC_CUDA(Q->d_mask.reserve(Q->mask_words));
+        rc = launch(Q, Q->hoisted, false, Q->d_q.p, 1, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS, nullptr, nullptr,
+                        nullptr, Q->d_mask.p, nullptr, 0);
+        if (rc != CC_OK) return rc;
+        CC_CUDA(cudaMemcpy(Q->hoisted_mask.data(), Q->d_mask.p, Q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        rc = check_err_flag(S);
+        if (rc != CC_OK) return rc;
+        S->stats.configs -= 1;
+        for (int p = 0; p < np; ++p)
+            if (Q->hoisted_mask[p >> 5] & (1u << (p & 31))) {
+                if (p < Q->nenv_total) { if (p < Q->hoisted_first_env) Q->hoisted_first_env = p; }
+                else if (p < Q->hoisted_first_self) Q->hoisted_first_self = p;
+            }
+        CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
+        CC_CUDA(cudaDeviceSynchronize());
     }
     return CC_OK;
 }
@@ -1468,6 +1505,8 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     }
     CC_CUDA(cudaSetDevice(S->device));
     Q->p_main = p_main;
+    Q->p_main_all = p_main;
+    Q->p_hoist = p_hoist;
     Q->moves = moves;
     Q->p_full = p_full;
     Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size();     // not with grabbed links (their chain is not walked below)
@@ -1475,30 +1514,8 @@ static int finish_query(cc_query* Q, const std::vector<int>& slot_body, const st
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
     if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
     if (rc != CC_OK) return rc;
-    Q->hoisted_mask.assign(Q->mask_words, 0u);
-    CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
-
-    // ---- evaluate the hoisted pairs once, with the same kernel, at the current DOF values
-    if (!Q->hoisted.pairs.empty()) {
-        CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, Q->cur_active.size())));
-        if (!Q->cur_active.empty())
-            CC_CUDA(cudaMemcpy(Q->d_q.p, Q->cur_active.data(), Q->cur_active.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CC_CUDA(Q->d_mask.reserve(Q->mask_words));
-        rc = launch(Q, Q->hoisted, false, Q->d_q.p, 1, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS, nullptr, nullptr,
-                        nullptr, Q->d_mask.p, nullptr, 0);
-        if (rc != CC_OK) return rc;
-        CC_CUDA(cudaMemcpy(Q->hoisted_mask.data(), Q->d_mask.p, Q->mask_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        rc = check_err_flag(S);
-        if (rc != CC_OK) return rc;
-        S->stats.configs -= 1;
-        for (int p = 0; p < np; ++p)
-            if (Q->hoisted_mask[p >> 5] & (1u << (p & 31))) {
-                if (p < Q->nenv_total) { if (p < Q->hoisted_first_env) Q->hoisted_first_env = p; }
-                else if (p < Q->hoisted_first_self) Q->hoisted_first_self = p;
-            }
-        CC_CUDA(Q->d_hoisted_mask.upload(Q->hoisted_mask));
-        CC_CUDA(cudaDeviceSynchronize());
-    }
+    rc = evaluate_hoisted(Q);
+    if (rc != CC_OK) return rc;
     return CC_OK;
 }
 
@@ -1670,6 +1687,66 @@ int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntr
     if (rc != CC_OK) { delete Q; return rc; }
     *out = Q;
     return CC_OK;
+}
+
+// Re-read what a bound query captured from the scene — the poses of every static slot (other bodies' links, query links no
+// active DOF moves), the query body's base pose, the values of its inactive DOFs — without rebuilding the pair lists.
+int cc_query_refresh(cc_query* q)
+{
+    if (!q) return fail(CC_ERR_INVALID, "query is NULL");
+    cc_scene* S = q->scene;
+    HBody* B = get_body(S, q->body);
+    if (!B) return fail(CC_ERR_STATE, "the query's body was removed");
+    if (!S->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
+    CC_CUDA(cudaSetDevice(S->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    memcpy(q->base, B->links[0].xf, sizeof(q->base));
+    q->center[0] = q->base[4]; q->center[1] = q->base[5]; q->center[2] = q->base[6];
+    for (int d = 0; d < B->ndof && d < (int)q->col_of_dof.size(); ++d) if (q->col_of_dof[d] >= 0) q->cur_active[q->col_of_dof[d]] = B->dofvals[d];
+    // certificates depend on the captured poses: back to the full pair list, to be rebuilt after the next 16k configurations
+    const bool had_certificates = q->ntables > 0 || q->ndropped > 0;
+    q->ntables = 0; q->ndropped = 0; q->tables_done = false; q->fk_configs_seen = 0;
+    Plan* plans[4] = {&q->full, &q->mainl, &q->hoisted, q->dist_ready ? &q->dist : nullptr};
+    if (had_certificates && q->p_main.size() != q->p_main_all.size()) {
+        std::vector<uint8_t> main_dynamic(q->nq, 0);
+        for (int p : q->p_main_all) {
+            const int a = q->quads[4 * p];
+            if (q->moves[a]) main_dynamic[a] = 1;
+            if (q->quads[4 * p + 3] == 1) { const int b2 = q->quads[4 * p + 2]; if (q->moves[b2]) main_dynamic[b2] = 1; }
+        }
+        q->p_main = q->p_main_all;
+        int rc = build_plan(q, q->mainl, q->p_main, main_dynamic, true);
+        if (rc != CC_OK) return rc;
+    }
+    for (Plan* pl : plans) {
+        if (!pl || pl->nstatic == 0) continue;
+        std::vector<float> stxf((size_t)pl->nstatic * 12, 0.f), staabb((size_t)pl->nstatic * 8, 0.f);
+        for (int i = 0; i < pl->nstatic; ++i) {
+            const HLink& L = S->bodies[pl->statics[i].first]->links[pl->statics[i].second];
+            pose_to_rt32(L.xf, q->center, &stxf[(size_t)i * 12]);
+            static_aabb(L, q->center, &staabb[(size_t)i * 8]);
+        }
+        CC_CUDA(pl->d_st_xf.upload(stxf)); CC_CUDA(pl->d_st_aabb.upload(staabb));
+    }
+    // inactive DOF values live in the chain programs
+    for (Plan* pl : plans) {
+        if (!pl || pl->steps.empty()) continue;
+        bool changed = false;
+        for (ccdev::FkStep& st : pl->steps) {
+            if (st.src_col >= 0) continue;
+            // find the joint of this step to re-read its source DOF
+            for (const cc_joint& j : B->joints)
+                if (j.parent_link == st.parent && j.child_link == st.child) {
+                    const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+                    const double v = srcdof >= 0 ? B->dofvals[srcdof] : 0.0;
+                    if (v != st.src_const) { st.src_const = v; changed = true; }
+                    break;
+                }
+        }
+        if (changed) CC_CUDA(pl->d_steps.upload(pl->steps));
+    }
+    CC_CUDA(cudaDeviceSynchronize());
+    return evaluate_hoisted(q);
 }
 
 int cc_query_destroy(cc_query* q)
@@ -1885,6 +1962,34 @@ int cc_scene_set_counters(cc_scene* s, int enabled)
 {
     if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
     s->counters = enabled != 0;
+    return CC_OK;
+}
+
+int cc_device_fp32_peak(int cuda_device, double* out_tflops)
+{
+    if (!out_tflops) return fail(CC_ERR_INVALID, "out is NULL");
+    CC_CUDA(cudaSetDevice(cuda_device));
+    cudaDeviceProp prop;
+    CC_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    float* d = nullptr;
+    CC_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CC_CUDA(cudaEventCreate(&e0)); CC_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CC_CUDA(cudaEventRecord(e0, 0));
+        ccdev::cc_fma_peak_kernel<<<blocks, threads>>>(d, 0.999f, 1e-3f);
+        CC_CUDA(cudaEventRecord(e1, 0));
+        CC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 4096 * (double)blocks * threads;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *out_tflops = best;
     return CC_OK;
 }
 

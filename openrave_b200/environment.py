@@ -143,9 +143,10 @@ class Environment(object):
             return cc.CheckCollision(a, report=report)
         return cc.CheckCollision(a, b, report=report)
 
-    def _body_changed(self, body):
+    def _body_changed(self, body, kind="structure"):
+        """kind 'pose': only link transforms / DOF values moved; 'structure': enable flags, grabs, active DOFs, geometry."""
         if self.checker is not None:
-            self.checker._on_body_changed(body)
+            self.checker._on_body_changed(body, kind)
 
     def __enter__(self):
         return self

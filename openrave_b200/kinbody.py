@@ -445,7 +445,7 @@ class KinBody(object):
     def _notify_transform_changed(self):
         self._update_grabbed_bodies()
         if self.env is not None:
-            self.env._body_changed(self)
+            self.env._body_changed(self, "pose")
 
     # --- grabbing (src/libopenrave/kinbodygrab.cpp) -------------------------------------------------
     def rigidly_attached_links(self, link):
@@ -549,7 +549,7 @@ class KinBody(object):
                 l.t = rm.t_mul(g.link.t, rel)
             g.body._update_grabbed_bodies()
             if g.body.env is not None:
-                g.body.env._body_changed(g.body)
+                g.body.env._body_changed(g.body, "pose")
 
     def GetQueryLinkTransformations(self):
         """The body's link transforms followed by those of its grabbed bodies in grab order: the row layout of the

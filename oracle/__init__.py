@@ -151,7 +151,7 @@ class OracleChecker(object):
         if bid is not None:
             self.lib.orc_body_set_removed(self.scene, bid, 1)
 
-    def _on_body_changed(self, body):
+    def _on_body_changed(self, body, kind="structure"):
         self._dirty.add(id(body))
 
     def _sync_body(self, body):

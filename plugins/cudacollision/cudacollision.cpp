@@ -200,6 +200,7 @@ public:
         if (probot->GetAffineDOF() != 0) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: affine active DOFs are not batched yet", ORE_NotImplemented);
         if (ndof != (int)probot->GetActiveDOFIndices().size()) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ndof != active DOF count", ORE_InvalidArguments);
         cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices());
+        if (_stale.erase(query)) _Check(cc_query_refresh(query));      // base pose / inactive DOF values of the robot moved
         std::vector<int32_t> fe(firstpairs ? n : 0), fs(firstpairs ? n : 0);
         _Check(cc_check_batch(query, q, n, flags, verdict, firstpairs ? fe.data() : NULL, firstpairs ? fs.data() : NULL, NULL));
         if (firstpairs) {
@@ -530,6 +531,7 @@ private:
     {
         for (std::map<QueryKey, cc_query*>::iterator it = _queries.begin(); it != _queries.end(); ++it) cc_query_destroy(it->second);
         _queries.clear();
+        _stale.clear();
     }
 
     /// push poses / enable flags / attachments of every body whose update stamp moved, then commit (idempotent)
@@ -538,11 +540,13 @@ private:
         std::vector<KinBodyPtr> vbodies;
         GetEnv()->GetBodies(vbodies);
         bool changed = false;
+        std::set<int> moved;                 // cc ids of the bodies whose poses were pushed in this pass
         std::vector<double> T8;
         std::vector<uint8_t> enabled;
         FOREACHC(itbody, vbodies) {
             BodyInfoPtr pinfo = _InitKinBody(*itbody);
             if (pinfo->transformStamp == (*itbody)->GetUpdateStamp()) continue;
+            moved.insert(pinfo->id);
             T8 = _Poses(*itbody);
             _Check(cc_body_set_link_transforms(_scene, pinfo->id, T8.data()));
             enabled.resize((*itbody)->GetLinks().size());
@@ -561,9 +565,27 @@ private:
             for (size_t i = 0; i < vbodies.size(); ++i)
                 for (size_t j = i + 1; j < vbodies.size(); ++j)
                     _Check(cc_body_set_attached(_scene, _Info(vbodies[i])->id, _Info(vbodies[j])->id, vbodies[i]->IsAttached(*vbodies[j]) ? 1 : 0));
-            _DropQueries();       // bound queries capture static poses and hoisted verdicts
         }
         _Check(cc_scene_commit(_scene));
+        // Bound queries captured poses (static slots, base, inactive DOF values, hoisted verdicts).  Pose changes do not change
+        // a pair list, so the queries are refreshed, not re-created: at once when another body moved, lazily (before the next
+        // FK-mode call) when only the query's own body or what it grabs moved — the single-state overloads pass that body's
+        // transforms in anyway.  Structural changes (enable flags, attachments, grabs, joints, geometry, active DOFs) arrive
+        // through the change callbacks and drop the queries.
+        for (std::map<QueryKey, cc_query*>::iterator it = _queries.begin(); it != _queries.end() && !moved.empty(); ++it) {
+            std::set<int> own;
+            own.insert(it->first.body);
+            KinBodyPtr pown = _byid[it->first.body].lock();
+            if (!!pown) {
+                std::vector<KinBodyPtr> vgrabbed;
+                pown->GetGrabbed(vgrabbed);
+                FOREACHC(itg, vgrabbed) { own.insert(_Info(*itg)->id); }
+            }
+            bool others = false;
+            FOREACHC(itm, moved) { if (own.find(*itm) == own.end()) { others = true; break; } }
+            if (others) { _Check(cc_query_refresh(it->second)); _stale.erase(it->second); }
+            else _stale.insert(it->second);
+        }
     }
 
     std::vector<double> _Poses(KinBodyConstPtr pbody) const
@@ -776,6 +798,7 @@ private:
     std::string _userdatakey;
     std::map<int, KinBodyWeakPtr> _byid;
     std::map<QueryKey, cc_query*> _queries;
+    std::set<cc_query*> _stale;            // queries whose own body moved since their last refresh (matters to the FK-mode entry only)
 };
 
 // ---------------------------------------------------------------------------------------------- plugin entry (plugin.h:30-157)
