@@ -278,6 +278,7 @@ struct cc_query {
     Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
     // certified free-space tables of the batched FK-mode plan (built once enough configurations have gone through)
     bool allow_tables = false, tables_done = false;
+    float cert_tri_eps = 0.0f;               // cc_scene_set_tri_epsilon value the certificates were built with
     std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
     uint64_t fk_configs_seen = 0;
     int ntables = 0;
@@ -443,7 +444,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         int want = forced > 0 ? forced : std::min(by_load, by_pairs);
         while (split * 2 <= want && split < 8) split *= 2;
     }
-    const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only && S->tri_eps <= 1e-4f;
+    const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
     if (sp && use_tables) P.pair_table = Q->d_pair_table_split[split == 2 ? 0 : (split == 4 ? 1 : 2)].p;
@@ -744,7 +745,10 @@ static int build_pair_tables(cc_query* Q)
     auto rad = [&](int l) { if (radius_cache[l] < 0) radius_cache[l] = link_radius(B->links[l]); return radius_cache[l]; };
 
     std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
-    const double margin = 3e-4;
+    // safety margin of every certificate: FP32 error of the distance kernel (~1e-5 m) + the 1e-4 m contact band, plus the
+    // conservative margin of the triangle test when the caller has set one (pairs closer than it count as touching)
+    Q->cert_tri_eps = S->tri_eps;
+    const double margin = 3e-4 + (double)S->tri_eps;
     // ---- reach certificate (any number of DOFs): every point of a link stays inside a ball around the anchor of the first
     // varying joint on its path from the base (a fixed point of the world: everything above that joint is fixed), of radius
     // chain length below the anchor + the link's radius.  An environment link whose world AABB is farther from the centre than
@@ -986,8 +990,15 @@ static int build_pair_tables(cc_query* Q)
 }
 
 // Tables cost a few hundred milliseconds to build: they are built once a query has seen enough batched configurations.
+extern "C" { static int reset_certificates(cc_query* q); }
+
 static int maybe_build_tables(cc_query* q, int n)
 {
+    // the certificates were proven with a margin that includes the triangle-test epsilon in force at the time
+    if (q->tables_done && q->cert_tri_eps != q->scene->tri_eps && (q->ntables > 0 || q->ndropped > 0)) {
+        int rc = reset_certificates(q);
+        if (rc != CC_OK) return rc;
+    }
     if (q->tables_done) return CC_OK;
     static const long long after = getenv("CC_TUNE_TABLES_AFTER") ? atoll(getenv("CC_TUNE_TABLES_AFTER")) : 16384;
     q->fk_configs_seen += (uint64_t)n;
@@ -1689,6 +1700,28 @@ int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntr
     return CC_OK;
 }
 
+// Forget the free-space certificates of a query: the batched plan gets its full pair list back, the certificates are rebuilt
+// once the query has seen another 16k configurations.
+static int reset_certificates(cc_query* q)
+{
+    const bool dropped = q->p_main.size() != q->p_main_all.size();
+    q->ntables = 0; q->ndropped = 0; q->tables_done = false; q->fk_configs_seen = 0;
+    if (dropped) {
+        CC_CUDA(cudaSetDevice(q->scene->device));
+        CC_CUDA(cudaDeviceSynchronize());
+        std::vector<uint8_t> main_dynamic(q->nq, 0);
+        for (int p : q->p_main_all) {
+            const int a = q->quads[4 * p];
+            if (q->moves[a]) main_dynamic[a] = 1;
+            if (q->quads[4 * p + 3] == 1) { const int b2 = q->quads[4 * p + 2]; if (q->moves[b2]) main_dynamic[b2] = 1; }
+        }
+        q->p_main = q->p_main_all;
+        int rc = build_plan(q, q->mainl, q->p_main, main_dynamic, true);
+        if (rc != CC_OK) return rc;
+    }
+    return CC_OK;
+}
+
 // Re-read what a bound query captured from the scene — the poses of every static slot (other bodies' links, query links no
 // active DOF moves), the query body's base pose, the values of its inactive DOFs — without rebuilding the pair lists.
 int cc_query_refresh(cc_query* q)
@@ -1704,20 +1737,8 @@ int cc_query_refresh(cc_query* q)
     q->center[0] = q->base[4]; q->center[1] = q->base[5]; q->center[2] = q->base[6];
     for (int d = 0; d < B->ndof && d < (int)q->col_of_dof.size(); ++d) if (q->col_of_dof[d] >= 0) q->cur_active[q->col_of_dof[d]] = B->dofvals[d];
     // certificates depend on the captured poses: back to the full pair list, to be rebuilt after the next 16k configurations
-    const bool had_certificates = q->ntables > 0 || q->ndropped > 0;
-    q->ntables = 0; q->ndropped = 0; q->tables_done = false; q->fk_configs_seen = 0;
+    { int rc = reset_certificates(q); if (rc != CC_OK) return rc; }
     Plan* plans[4] = {&q->full, &q->mainl, &q->hoisted, q->dist_ready ? &q->dist : nullptr};
-    if (had_certificates && q->p_main.size() != q->p_main_all.size()) {
-        std::vector<uint8_t> main_dynamic(q->nq, 0);
-        for (int p : q->p_main_all) {
-            const int a = q->quads[4 * p];
-            if (q->moves[a]) main_dynamic[a] = 1;
-            if (q->quads[4 * p + 3] == 1) { const int b2 = q->quads[4 * p + 2]; if (q->moves[b2]) main_dynamic[b2] = 1; }
-        }
-        q->p_main = q->p_main_all;
-        int rc = build_plan(q, q->mainl, q->p_main, main_dynamic, true);
-        if (rc != CC_OK) return rc;
-    }
     for (Plan* pl : plans) {
         if (!pl || pl->nstatic == 0) continue;
         std::vector<float> stxf((size_t)pl->nstatic * 12, 0.f), staabb((size_t)pl->nstatic * 8, 0.f);
