@@ -19,7 +19,10 @@
 // The nearest-neighbour structure is an exact linear scan (the reference's cover tree, rplanners.h:170-860, returns the
 // same node up to ties); insertion refuses a node closer than 0.001 * step to its nearest neighbour like _InsertRecursive.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <coroutine>
 #include <cstdint>
 #include <cstring>
@@ -121,7 +124,8 @@ int edge_samples(const CSpace& cs, const double* q0, const double* q1, int inter
     int count = 0;
     auto push = [&](const double* q, double t) { out.insert(out.end(), q, q + n); if (times) times->push_back(t); ++count; };
     if (check_end) push(q1, 1.0);
-    std::vector<double> dQ(q1, q1 + n);
+    static thread_local std::vector<double> dQ, cur, d;     // scratch (this runs a hundred times per Extend ray)
+    dQ.assign(q1, q1 + n);
     cs.diff(dQ.data(), q0);
     int nsteps = 0, total = 0;
     for (int i = 0; i < n; ++i) {
@@ -134,7 +138,8 @@ int edge_samples(const CSpace& cs, const double* q0, const double* q1, int inter
     if (nsteps == 0) return count;
     const double fisteps = 1.0 / nsteps;
     for (int i = 0; i < n; ++i) dQ[i] *= fisteps;
-    std::vector<double> cur(q0, q0 + n), d(n);
+    cur.assign(q0, q0 + n);
+    d.resize(n);
     if (cs.neigh(cur.data(), dQ.data())) return -1;
     for (int f = start; f < nsteps; ++f) {
         push(cur.data(), f * fisteps);
@@ -218,14 +223,32 @@ struct Tree {
         if (dist_out) *dist_out = bd;
         return best;
     }
+    // is some node within `r` of c?  (weighted distance; a node is rejected as soon as its partial sum exceeds r^2, which for
+    // r = 0.001 * step happens at the first coordinate for all but coincident nodes)
+    bool any_within(const CSpace& cs, const double* c, double r) const
+    {
+        const double r2 = r * r;
+        for (int i = 0; i < size(); ++i) {
+            const double* n = cfg(i);
+            double s = 0;
+            int k = 0;
+            for (; k < dof; ++k) {
+                double d = n[k] - c[k];
+                if (cs.any_circular && cs.circ[k]) {
+                    if (d < -kPi) d += 2 * kPi * std::ceil((-kPi - d) / (2 * kPi));
+                    else if (d >= kPi) d -= 2 * kPi * std::floor((d + kPi) / (2 * kPi));
+                }
+                s += cs.w2[k] * d * d;
+                if (s > r2) break;
+            }
+            if (k == dof) return true;
+        }
+        return false;
+    }
     // _InsertNode (rplanners.h:710-738): -1 when a node within _mindistance already exists
     int insert(const CSpace& cs, int par, const double* c, uint32_t ud)
     {
-        if (size() > 0) {
-            double d;
-            nearest(cs, c, &d);
-            if (d <= mindist) return -1;
-        }
+        if (size() > 0 && any_within(cs, c, mindist)) return -1;
         q.insert(q.end(), c, c + dof);
         parent.push_back(par);
         userdata.push_back(ud);
@@ -788,7 +811,11 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
     std::vector<int32_t> group_begin, seg_begin, ffs, fv, ffc;
     std::vector<int> owner;
     std::vector<uint32_t> verdict;
+    double t_check = 0, t_gather = 0, t_resume = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     for (;;) {
+        const auto t0 = now();
         q.clear();
         group_begin.assign(1, 0);
         seg_begin.assign(1, 0);
@@ -807,6 +834,8 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
         ffs.assign(ngroups, -1);
         fv.assign(ngroups, 0);
         ffc.assign(ngroups, -1);
+        const auto t1 = now();
+        t_gather += secs(t0, t1);
         int rc;
         if (p->query) rc = gpu_group_check(p->query, q.data(), nconfigs, group_begin.data(), ngroups, seg_begin.data(), ffs.data(), fv.data(), ffc.data(), verdict);
         else rc = p->fn(p->user, q.data(), nconfigs, n, group_begin.data(), ngroups, seg_begin.data(), (int)seg_begin.size() - 1, ffs.data(), fv.data(), ffc.data());
@@ -815,6 +844,8 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
             p->problems.clear();
             return rc;
         }
+        const auto t2 = now();
+        t_check += secs(t1, t2);
         p->totals[0] += 1;
         p->totals[1] += 1;
         p->totals[2] += (uint64_t)nconfigs;
@@ -840,7 +871,11 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
             h.resume();
             if (tasks[owner[g]].h.done()) pr.done = true;
         }
+        t_resume += secs(t2, now());
     }
+    if (getenv("CC_DEBUG_PLANNER"))
+        fprintf(stderr, "[planner] %llu rounds: gather %.2f ms, checker %.2f ms, planner host (resume) %.2f ms\n",
+                (unsigned long long)p->totals[0], 1e3 * t_gather, 1e3 * t_check, 1e3 * t_resume);
     for (int k = 0; k < nproblems; ++k) results[k] = p->problems[k]->res;
     return CC_OK;
 }
