@@ -573,6 +573,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
+    # the report == NULL flavour the planners use (CC_BATCH_FIRST_HIT): same kernels, stops at the first contact
+    from openrave_b200.checker import BATCH_FIRST_HIT
+    evf = []
+    for _ in range(max(3, args.steps // 2)):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        bq.check_device(d_q.data_ptr(), n, flags | BATCH_FIRST_HIT, d_verdict.data_ptr(), 0, 0, 0, stream.cuda_stream)
+        e1.record(stream)
+        evf.append((e0, e1))
+    torch.cuda.synchronize()
+    first_hit_ms = sum(a.elapsed_time(b) for a, b in evf) / len(evf)
+    step_device()                           # leave the full outputs in the result buffers for the consistency check below
+    torch.cuda.synchronize()
+
     # end to end through the host-buffer entry
     for _ in range(2):
         step_e2e()
@@ -604,7 +619,8 @@ def main():
                            "bvh_nodes": bq.info.total_nodes, "tris": bq.info.total_tris,
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
                            "parallelism": "configs sharded, scene replicated (dp%d)" % world,
-                           "colliding_fraction": float((v_last != 0).mean())},
+                           "colliding_fraction": float((v_last != 0).mean()),
+                           "first_hit_mode_configs_per_s": world * n / (first_hit_ms / 1000.0)},
                 "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * ndof * 8),
                         "d2h_bytes_per_step": int(n * 12)},
                 "gpu_launches": int(launches_timed),

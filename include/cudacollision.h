@@ -84,7 +84,12 @@ typedef struct cc_joint {
 enum cc_batch_flags {
     CC_BATCH_ENV = 1,        /* Environment::CheckCollision(robot) */
     CC_BATCH_SELF = 2,       /* KinBody::CheckSelfCollision(robot) */
-    CC_BATCH_ALL_PAIRS = 4   /* no early exit: fill the complete per-pair bitmask (report != NULL path) */
+    CC_BATCH_ALL_PAIRS = 4,  /* no early exit: fill the complete per-pair bitmask (report != NULL path) */
+    CC_BATCH_FIRST_HIT = 8   /* verdict only, the report == NULL path of the reference: CheckCollision(robot) returns at its first
+                              * colliding pair (collisionPQP.h:288-290) and the planners' _CheckState skips the self check once the
+                              * environment check failed (planningutils.cpp:2523-2548).  CC_VERDICT_ENV is exact; CC_VERDICT_SELF is
+                              * exact when CC_VERDICT_ENV is clear and otherwise only set if a self contact happened to be found;
+                              * first_env / first_self come back as -1.  Ignored together with CC_BATCH_ALL_PAIRS. */
 };
 
 /* Verdict bits written per configuration. */

@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("CUDACOLLISION_LIB") or os.path.join(_HERE, "libcudaco
 CO_Distance, CO_UseTolerance, CO_Contacts, CO_RayAnyHit = 1, 2, 4, 8
 CO_ActiveDOFs, CO_AllLinkCollisions, CO_AllGeometryCollisions, CO_AllGeometryContacts, CO_IgnoreCallbacks = \
     0x10, 0x20, 0x40, 0x80, 0x100
-BATCH_ENV, BATCH_SELF, BATCH_ALL_PAIRS = 1, 2, 4
+BATCH_ENV, BATCH_SELF, BATCH_ALL_PAIRS, BATCH_FIRST_HIT = 1, 2, 4, 8
 
 
 class CudaCollisionError(RuntimeError):

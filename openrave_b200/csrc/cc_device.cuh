@@ -50,6 +50,7 @@ constexpr int kNone = 0x7fffffff;
 
 // flags (low bits mirror cc_batch_flags)
 constexpr int kFlagEnv = 1, kFlagSelf = 2, kFlagAllPairs = 4, kFlagPoseMode = 8, kFlagFkOnly = 16, kFlagCounters = 32;
+constexpr int kFlagFirstHit = 128;     // verdict only: an env hit ends the configuration, a self hit ends the self pairs
 constexpr int kFlagInitOutputs = 64;   // split traversal: the FK kernel initialises the outputs the traversal combines into
 
 struct FkStep {                 // one joint of the chain program, 256 bytes
@@ -553,6 +554,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     uint2* spill = P.spill + (size_t)(blockIdx.x * kWarpsPerBlock + wib) * P.spill_cap;
 
     const bool all_pairs = (P.flags & kFlagAllPairs) != 0;
+    const bool first_hit = (P.flags & kFlagFirstHit) != 0 && !all_pairs;
     const bool counters = (P.flags & kFlagCounters) != 0;
     const float eps2 = P.tri_eps * P.tri_eps;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -592,11 +594,16 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         // warp-uniform state, all in registers
         int sp = 0, spill_count = 0, ntri = 0, ntri2 = 0, ncb = 0;
         int best_env = P.hoisted_first_env, best_self = P.hoisted_first_self;
+        if (first_hit) {
+            // "a hit precedes everything": -1 makes every remaining pair of the class irrelevant
+            if (best_env != kNone) { best_env = -1; best_self = -1; }
+            else if (best_self != kNone) best_self = -1;
+        }
         uint32_t slot_hit = 0;     // slots of the current batch of root pairs with a contact
         uint32_t slot_dead = 0;    // slots whose items are no longer wanted (contact found, or preceded by a contact); non-zero
                                    // also means refills from the spill area have to be filtered
         bool failed = false;
-        uint32_t iters = 0;
+        uint32_t iters = P.hoisted_first_self != kNone ? 0x80000000u : 0u;     // bit 31: a self contact was really found (first-hit mode)
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
         int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
         const int kend = (P.flags & kFlagSelf) ? npairs_dev : nenv_dev;
@@ -775,6 +782,11 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                             const int ps = __reduce_min_sync(kFull, (pass && pidx >= nenv_total) ? pidx : kNone);
                             if (pe < best_env) { best_env = pe; recheck = true; }
                             if (ps < best_self) { best_self = ps; recheck = true; }
+                            if (ps != kNone) iters |= 0x80000000u;
+                            if (first_hit) {
+                                if (best_env != kNone) { best_env = -1; best_self = -1; }
+                                else if (best_self != kNone) best_self = -1;
+                            }
                             slot_dead |= slot_hit;
                             if (!all_pairs) {
                                 bool d = false;
@@ -912,18 +924,19 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             }
             uint32_t v = 0;
             if ((P.flags & kFlagEnv) && be != kNone) v |= 1u;
-            if ((P.flags & kFlagSelf) && bs != kNone) v |= 2u;
+            if ((P.flags & kFlagSelf) && (first_hit ? (iters >> 31) != 0u : bs != kNone)) v |= 2u;
+            if (first_hit) { be = -1; bs = -1; }      // no first pairs in this mode
             if (kSplit) {
                 // merge with the other work items of this configuration (-1 reads as the largest unsigned value)
                 if (v && P.verdict) atomicOr(&P.verdict[c], v);
                 if ((v & 1u) && P.first_env) atomicMin((unsigned int*)&P.first_env[c], (unsigned int)be);
                 if ((v & 2u) && P.first_self) atomicMin((unsigned int*)&P.first_self[c], (unsigned int)bs);
-                if (P.work_out) atomicAdd(&P.work_out[c], iters);
+                if (P.work_out) atomicAdd(&P.work_out[c], iters & 0x7fffffffu);
             } else {
                 if (P.verdict) P.verdict[c] = v;
                 if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
                 if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
-                if (P.work_out) P.work_out[c] = iters;
+                if (P.work_out) P.work_out[c] = iters & 0x7fffffffu;
             }
         }
         __syncwarp();

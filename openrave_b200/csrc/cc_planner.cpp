@@ -703,7 +703,7 @@ int gpu_group_check(cc_query* q, const double* cfg, int nconfigs, const int32_t*
 {
     verdict.resize((size_t)std::max(nconfigs, 1));
     if (nconfigs > 0) {
-        const int rc = cc_check_batch(q, cfg, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF, verdict.data(), nullptr, nullptr, nullptr);
+        const int rc = cc_check_batch(q, cfg, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_FIRST_HIT, verdict.data(), nullptr, nullptr, nullptr);
         if (rc != CC_OK) return rc;
     }
     for (int g = 0; g < ngroups; ++g) {

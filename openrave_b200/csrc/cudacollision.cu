@@ -1830,7 +1830,7 @@ int cc_check_batch_device(cc_query* q, const double* d_q, int n, int flags, uint
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     CC_CUDA(cudaSetDevice(q->scene->device));
-    const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ((flags & CC_BATCH_FIRST_HIT) ? ccdev::kFlagFirstHit : 0);
     { int rc = maybe_build_tables(q, n); if (rc != CC_OK) return rc; }
     return launch(q, q->mainl, true, d_q, n, f, d_verdict, d_fe, d_fs, d_mask, nullptr, (cudaStream_t)stream);
 }
@@ -1863,7 +1863,7 @@ int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags, uint
     if (!q || n < 0 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
-    const int f = flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS);
+    const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ((flags & CC_BATCH_FIRST_HIT) ? ccdev::kFlagFirstHit : 0);
     { int rc = maybe_build_tables(q, n); if (rc != CC_OK) return rc; }
     return run_host(q, dof_values, (size_t)n * q->ncols, n, f, false, verdict, first_env, first_self, pair_mask, nullptr);
 }
@@ -1873,7 +1873,7 @@ int cc_check_poses(cc_query* q, const double* T8, int n, int flags, uint32_t* ve
 {
     if (!q || n < 0 || (n > 0 && !T8)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
-    const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ccdev::kFlagPoseMode;
+    const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ccdev::kFlagPoseMode | ((flags & CC_BATCH_FIRST_HIT) ? ccdev::kFlagFirstHit : 0);
     return run_host(q, T8, (size_t)n * q->nq * 8, n, f, true, verdict, first_env, first_self, pair_mask, nullptr);
 }
 

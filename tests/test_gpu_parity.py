@@ -177,3 +177,23 @@ def test_determinism(world):
     assert (a["verdict"] == b["verdict"]).all()
     assert (a["first_env_index"] == b["first_env_index"]).all()
     assert (a["first_self_index"] == b["first_self_index"]).all()
+
+
+@pytest.mark.gpu
+def test_first_hit_mode_keeps_the_planner_return_code(world):
+    """CC_BATCH_FIRST_HIT = the report == NULL path: the env bit is exact, the self bit is exact whenever the env bit is clear,
+    i.e. the code DynamicsCollisionConstraint::_CheckState returns (env first, then self, planningutils.cpp:2523-2548)."""
+    from openrave_b200.checker import BATCH_ENV, BATCH_SELF, BATCH_FIRST_HIT
+    env, robot, cc, orc = world[:4]
+    q = sample_configs(robot, 30000, seed=71)
+    full = cc.CheckCollisionBatch(robot, q)["verdict"]
+    fast = cc.CheckCollisionBatch(robot, q, flags=BATCH_ENV | BATCH_SELF | BATCH_FIRST_HIT)["verdict"]
+    assert np.array_equal(fast & 1, full & 1)
+    free_env = (full & 1) == 0
+    assert np.array_equal(fast[free_env], full[free_env])
+    assert ((fast & 2) <= (full & 2)).all()                 # a reported self contact is a real one
+    code = lambda v: np.where(v & 1, 1, np.where(v & 2, 2, 0))
+    assert np.array_equal(code(fast), code(full))
+    for n in (1, 50, 700):                                  # split kernel
+        f2 = cc.CheckCollisionBatch(robot, q[:n], flags=BATCH_ENV | BATCH_SELF | BATCH_FIRST_HIT)["verdict"]
+        assert np.array_equal(code(f2), code(full[:n]))
