@@ -38,10 +38,16 @@ namespace ccdev {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMinBlocksPerSM = 8;   // 32 warps / SM: registers capped at 64 per thread
 constexpr int kFkThreads = 128;
-constexpr int kStackCap = 320;       // items of shared-memory LIFO per warp
+#ifndef CC_STACK_CAP
+#define CC_STACK_CAP 320
+#endif
+#ifndef CC_TRIQ_CAP
+#define CC_TRIQ_CAP 96
+#endif
+constexpr int kStackCap = CC_STACK_CAP;   // items of shared-memory LIFO per warp
 constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
 constexpr int kNumSlots = 32;        // root pairs traversed together
-constexpr int kTriQCap = 96;         // pending leaf x leaf tests (drained 32 at a time)
+constexpr int kTriQCap = CC_TRIQ_CAP;         // pending leaf x leaf tests (drained 32 at a time)
 constexpr int kTriQ2Cap = 64;        // leaf x leaf tests that survived the two face-normal axes (15 axes left, drained 32 at a time)
 constexpr int kBroadPerLane = 4;     // broadphase pairs per lane per step (independent loads in flight)
 constexpr int kCandCap = 32 * kBroadPerLane + 32;   // pending candidate pair indices (a step only runs with < 32 pending)
