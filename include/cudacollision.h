@@ -308,7 +308,8 @@ typedef struct cc_birrt_params {
     int32_t path_optimize_iterations;/* _ExtractPath calls _SimpleOptimizePath(path, 10) (rrt.h:647) */
     int32_t smoother_iterations;     /* linearsmoother _nMaxIterations, reference default 100; 0 = no post-processing */
     int32_t max_extend_steps;        /* Extend's "avoid infinite loops" bound, 100 (rplanners.h:324) */
-    int32_t speculate_steps;         /* steps of a ray sent per round (<= 0: the whole ray) */
+    int32_t speculate_steps;         /* steps of a ray sent per round: 0 the whole ray, n > 0 fixed chunks, n < 0 adaptive (|n| first,
+                                      * doubling while the chunks pass); the plans are the same for every value */
     int32_t reserved;
 } cc_birrt_params;
 

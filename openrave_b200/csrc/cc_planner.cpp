@@ -339,10 +339,15 @@ struct Problem {
         bool added = false;
         std::vector<double> cur(tree.cfg(nn), tree.cfg(nn) + n), nxt(n), delta(n);
         const int maxsteps = prm.max_extend_steps > 0 ? prm.max_extend_steps : 100;
-        const int chunk = prm.speculate_steps > 0 ? prm.speculate_steps : maxsteps;
+        // steps submitted per round: the whole ray (0), a fixed number (> 0), or adaptive (< 0): -speculate_steps steps first,
+        // doubling every time a chunk passes — rays that die at an obstacle cost little, free rays finish in a few rounds
+        int chunk = prm.speculate_steps > 0 ? prm.speculate_steps : (prm.speculate_steps < 0 ? -prm.speculate_steps : maxsteps);
         int iter = 0;
         int terminal = -1;                      // set when the ray ends without needing a check
+        bool first_chunk = true;
         while (iter < maxsteps && terminal < 0) {
+            if (!first_chunk && prm.speculate_steps < 0) chunk *= 2;
+            first_chunk = false;
             // ---- generate up to `chunk` steps
             group.clear();
             std::vector<double> ray;            // the new configuration of every generated step

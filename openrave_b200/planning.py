@@ -270,7 +270,7 @@ class BirrtPlanner(object):
     (start, goal) problems in lockstep; `PlanPath` is the single-problem call of the reference API."""
 
     def __init__(self, robot, checker, step_length=0.04, max_iterations=10000, goal_bias=0.01, smoother_iterations=100,
-                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=0):
+                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8):
         self.lib = _planner_lib()
         self.robot = robot
         self.active = list(robot.GetActiveDOFIndices())

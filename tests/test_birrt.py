@@ -91,12 +91,13 @@ def test_lockstep_and_ray_chunking_do_not_change_plans(wamtest1):
     for k in range(6):
         r = solo.PlanPath(starts[k], goals[k], int(seeds[k]))
         assert np.array_equal(r["path"], ref[k]["path"]) and r["configs_serial"] == ref[k]["configs_serial"]
-    chunked = pl.BirrtPlanner(robot, orc.group_checker(robot), speculate_steps=7)
-    got = chunked.PlanBatch(starts, goals, seeds)
-    for a, b in zip(got, ref):
-        assert np.array_equal(a["path"], b["path"]) and np.array_equal(a["path_raw"], b["path_raw"])
-        assert a["configs_serial"] == b["configs_serial"] and a["configs_submitted"] <= b["configs_submitted"]
-        assert a["rounds"] >= b["rounds"]
+    for spec in (7, -4):                                                # fixed chunks, adaptive chunks
+        chunked = pl.BirrtPlanner(robot, orc.group_checker(robot), speculate_steps=spec)
+        got = chunked.PlanBatch(starts, goals, seeds)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a["path"], b["path"]) and np.array_equal(a["path_raw"], b["path_raw"])
+            assert a["configs_serial"] == b["configs_serial"] and a["configs_submitted"] <= b["configs_submitted"]
+            assert a["rounds"] >= b["rounds"]
 
 
 def test_colliding_endpoints_are_refused(wamtest1):
