@@ -272,6 +272,10 @@ struct cc_planner {
     void* user = nullptr;
     std::vector<std::unique_ptr<Problem>> problems;
     uint64_t totals[4] = {0, 0, 0, 0};
+    // page-locked staging for the GPU checker (cc_host_alloc): configurations in, verdicts out
+    double* pin_q = nullptr; size_t pin_q_cap = 0;
+    uint32_t* pin_v = nullptr; size_t pin_v_cap = 0;
+    ~cc_planner() { if (pin_q) cc_host_free(pin_q); if (pin_v) cc_host_free(pin_v); }
 };
 
 namespace {
@@ -702,13 +706,31 @@ struct Problem {
 // ------------------------------------------------------------------------------------------------ the GPU checker
 // All configurations of all groups in one cc_check_batch call (speculative: nothing stops early), then the first failing
 // segment of every group in the reference's order.
-int gpu_group_check(cc_query* q, const double* cfg, int nconfigs, const int32_t* group_begin, int ngroups,
-                    const int32_t* segment_begin, int32_t* first_fail_segment, int32_t* fail_verdict, int32_t* first_fail_config,
-                    std::vector<uint32_t>& verdict)
+int gpu_group_check(cc_planner* p, const double* cfg, int nconfigs, int ndof, const int32_t* group_begin, int ngroups,
+                    const int32_t* segment_begin, int32_t* first_fail_segment, int32_t* fail_verdict, int32_t* first_fail_config)
 {
-    verdict.resize((size_t)std::max(nconfigs, 1));
+    // stage through page-locked buffers: the copies of small batches then cost a few microseconds instead of tens
+    const size_t need_q = (size_t)std::max(nconfigs, 1) * ndof, need_v = (size_t)std::max(nconfigs, 1);
+    if (need_q > p->pin_q_cap) {
+        if (p->pin_q) cc_host_free(p->pin_q);
+        p->pin_q = nullptr; p->pin_q_cap = 0;
+        void* m = nullptr;
+        const int rc = cc_host_alloc(need_q * 2 * sizeof(double), &m);
+        if (rc != CC_OK) return rc;
+        p->pin_q = (double*)m; p->pin_q_cap = need_q * 2;
+    }
+    if (need_v > p->pin_v_cap) {
+        if (p->pin_v) cc_host_free(p->pin_v);
+        p->pin_v = nullptr; p->pin_v_cap = 0;
+        void* m = nullptr;
+        const int rc = cc_host_alloc(need_v * 2 * sizeof(uint32_t), &m);
+        if (rc != CC_OK) return rc;
+        p->pin_v = (uint32_t*)m; p->pin_v_cap = need_v * 2;
+    }
+    uint32_t* verdict = p->pin_v;
     if (nconfigs > 0) {
-        const int rc = cc_check_batch(q, cfg, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_FIRST_HIT, verdict.data(), nullptr, nullptr, nullptr);
+        std::memcpy(p->pin_q, cfg, (size_t)nconfigs * ndof * sizeof(double));
+        const int rc = cc_check_batch(p->query, p->pin_q, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_FIRST_HIT, verdict, nullptr, nullptr, nullptr);
         if (rc != CC_OK) return rc;
     }
     for (int g = 0; g < ngroups; ++g) {
@@ -815,7 +837,6 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
     std::vector<double> q;
     std::vector<int32_t> group_begin, seg_begin, ffs, fv, ffc;
     std::vector<int> owner;
-    std::vector<uint32_t> verdict;
     double t_check = 0, t_gather = 0, t_resume = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -842,7 +863,7 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
         const auto t1 = now();
         t_gather += secs(t0, t1);
         int rc;
-        if (p->query) rc = gpu_group_check(p->query, q.data(), nconfigs, group_begin.data(), ngroups, seg_begin.data(), ffs.data(), fv.data(), ffc.data(), verdict);
+        if (p->query) rc = gpu_group_check(p, q.data(), nconfigs, n, group_begin.data(), ngroups, seg_begin.data(), ffs.data(), fv.data(), ffc.data());
         else rc = p->fn(p->user, q.data(), nconfigs, n, group_begin.data(), ngroups, seg_begin.data(), (int)seg_begin.size() - 1, ffs.data(), fv.data(), ffc.data());
         if (rc != CC_OK) {
             if (!p->query) cc_internal_set_error("cc_birrt_plan_batch: the checker callback failed");

@@ -112,7 +112,8 @@ struct cc_scene {
     int spill_warps = 0;
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    DevBuf<int32_t> d_err;                  // [0] error flag (a traversal overflowed its spill area)
+    int32_t* h_err = nullptr;               // error flag (a traversal overflowed its spill area): page-locked, mapped into the
+    int32_t* d_err = nullptr;               //   device address space, so the host reads it after a sync without a copy
     int trav_blocks_per_sm = 0;             // occupancy of cc_traverse_kernel (queried once)
     DevBuf<unsigned long long> d_stats;     // [0] bv, [1] tri
     bool counters = false;
@@ -127,6 +128,7 @@ struct cc_scene {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (h_err) cudaFreeHost(h_err);
         for (int i = 0; i < 2; ++i) { if (ev_join[i]) cudaEventDestroy(ev_join[i]); if (lane_stream[i]) cudaStreamDestroy(lane_stream[i]); }
     }
 };
@@ -371,7 +373,7 @@ void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev
     memcpy(P.base, Q->base, sizeof(P.base));
     memcpy(P.center, Q->center, sizeof(P.center));
     P.tri_eps = S->tri_eps;
-    P.err_flag = S->d_err.p;
+    P.err_flag = S->d_err;
     P.stats = S->d_stats.p;
     P.spill_cap = 2048;
     P.split = 1;
@@ -605,10 +607,10 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
 
 int check_err_flag(cc_scene* S)
 {
-    int32_t h = 0;
-    CC_CUDA(cudaMemcpy(&h, S->d_err.p, sizeof(h), cudaMemcpyDeviceToHost));
+    // callers have synchronised the stream(s) that could have set it
+    const int32_t h = *(volatile int32_t*)S->h_err;
     if (h) {
-        cudaMemset(S->d_err.p, 0, sizeof(int32_t));
+        *(volatile int32_t*)S->h_err = 0;
         return fail(CC_ERR_NOMEM, "device traversal stack overflowed its spill area");
     }
     return CC_OK;
@@ -648,8 +650,9 @@ int cc_scene_create(int cuda_device, cc_scene** out)
     cudaDeviceProp prop;
     CC_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
     s->num_sms = prop.multiProcessorCount;
-    CC_CUDA(s->d_err.reserve(1));
-    CC_CUDA(cudaMemset(s->d_err.p, 0, sizeof(int32_t)));
+    CC_CUDA(cudaHostAlloc((void**)&s->h_err, sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    *s->h_err = 0;
+    CC_CUDA(cudaHostGetDevicePointer((void**)&s->d_err, s->h_err, 0));
     CC_CUDA(s->d_stats.reserve(2));
     CC_CUDA(cudaMemset(s->d_stats.p, 0, 2 * sizeof(unsigned long long)));
     CC_CUDA(cudaEventCreate(&s->ev0));
