@@ -18,12 +18,15 @@
 // (:331-356); single-state queries read the bodies' CURRENT link transforms and never run FK (:438-447).
 #include <openrave/openrave.h>
 #include <openrave/plugin.h>
+#include <openrave/plannerparameters.h>      // RRTParameters (cudabirrt)
 
 #include <boost/bind/bind.hpp>
 #include <boost/lexical_cast.hpp>
 #include <boost/make_shared.hpp>
 
+#include <cstring>
 #include <map>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -216,6 +219,15 @@ public:
             }
         }
         return 0;
+    }
+
+    /// the bound query behind CheckCollisionBatch for (robot, its active DOFs, current options): what cc_planner_set_query takes
+    cc_query* BindQuery(RobotBaseConstPtr probot)
+    {
+        if (probot->GetAffineDOF() != 0) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: affine active DOFs are not batched yet", ORE_NotImplemented);
+        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices());
+        if (_stale.erase(query)) _Check(cc_query_refresh(query));
+        return query;
     }
 
     // ------------------------------------------------------------------------------------------ single-state overloads
@@ -801,15 +813,118 @@ private:
     std::set<cc_query*> _stale;            // queries whose own body moved since their last refresh (matters to the FK-mode entry only)
 };
 
+// ---------------------------------------------------------------------------------------------- planner: "cudabirrt"
+// RaveCreatePlanner(env, "cudabirrt"): BirrtPlanner's interface (plugins/rplanners/rrt.h:279-659) on cc_birrt_plan_batch.  InitPlan reads
+// the same RRTParameters (goal bias is BirrtPlanner's constant 0.01, rrt.h:315), PlanPath plans vinitialconfig -> vgoalconfig and
+// appends the smoothed waypoints to the trajectory; PlanPathBatch is the new entry for callers that hold many queries.  Needs the
+// environment's collision checker to be "cudacollision".  Multiple initial / goal configurations, goal / initial samplers and
+// planner callbacks are not carried over (single start, single goal per problem).
+class CudaBirrtPlanner : public PlannerBase
+{
+public:
+    CudaBirrtPlanner(EnvironmentBasePtr penv) : PlannerBase(penv), _planner(NULL)
+    {
+        __description = ":Interface Author: cudacollision\n\nBi-directional RRT (RRT-Connect) + linear shortcutting with every edge check batched on the GPU; "
+                        "many planning problems advance in lockstep.";
+    }
+    virtual ~CudaBirrtPlanner() { if (_planner) cc_planner_destroy(_planner); }
+
+    virtual PlannerStatus InitPlan(RobotBasePtr probot, PlannerParametersConstPtr pparams)
+    {
+        EnvironmentLock lock(GetEnv()->GetMutex());
+        _parameters.reset(new RRTParameters());
+        _parameters->copy(pparams);
+        _robot = probot;
+        const int ndof = _parameters->GetDOF();
+        if ((int)probot->GetActiveDOFIndices().size() != ndof) return PlannerStatus("cudabirrt plans over the robot's active joint DOFs", PS_Failed);
+        // PlannerParameters::SetRobotActiveJoints' configuration space (planner.cpp:650-697)
+        std::vector<dReal> weights;
+        probot->GetActiveDOFWeights(weights);
+        std::vector<uint8_t> circular(ndof, 0);
+        for (int i = 0; i < ndof; ++i) {
+            KinBody::JointPtr pjoint = probot->GetJointFromDOFIndex(probot->GetActiveDOFIndices()[i]);
+            circular[i] = pjoint->IsCircular(probot->GetActiveDOFIndices()[i] - pjoint->GetDOFIndex()) ? 1 : 0;
+        }
+        cc_cspace space = {ndof, 0, _parameters->_vConfigLowerLimit.data(), _parameters->_vConfigUpperLimit.data(),
+                           _parameters->_vConfigResolution.data(), weights.data(), circular.data()};
+        if (_planner) { cc_planner_destroy(_planner); _planner = NULL; }
+        if (cc_planner_create(&space, &_planner) != CC_OK) return PlannerStatus(cc_last_error(), PS_Failed);
+        boost::shared_ptr<CudaCollisionChecker> pchecker = boost::dynamic_pointer_cast<CudaCollisionChecker>(GetEnv()->GetCollisionChecker());
+        if (!pchecker) return PlannerStatus("cudabirrt needs the cudacollision checker (env->SetCollisionChecker)", PS_Failed);
+        // the planners run with CO_ActiveDOFs (rrt.h:61, 387)
+        CollisionOptionsStateSaver optionstate(pchecker, pchecker->GetCollisionOptions() | CO_ActiveDOFs, false);
+        if (cc_planner_set_query(_planner, pchecker->BindQuery(probot)) != CC_OK) return PlannerStatus(cc_last_error(), PS_Failed);
+        memset(&_birrt, 0, sizeof(_birrt));
+        _birrt.step_length = _parameters->_fStepLength > 0 ? _parameters->_fStepLength : 0.04;
+        _birrt.goal_bias = 0.01;
+        _birrt.point_tolerance = 0.2;
+        _birrt.max_iterations = _parameters->_nMaxIterations > 0 ? _parameters->_nMaxIterations : 10000;
+        _birrt.path_optimize_iterations = 10;
+        _birrt.smoother_iterations = _parameters->_sPostProcessingPlanner.size() > 0 ? 100 : 0;     // linearsmoother's default budget
+        _birrt.max_extend_steps = 100;
+        _birrt.speculate_steps = -8;
+        return PlannerStatus(PS_HasSolution);
+    }
+
+    virtual PlannerStatus PlanPath(TrajectoryBasePtr ptraj, int planningoptions = 0)
+    {
+        if (!_planner || !_parameters) return PlannerStatus("cudabirrt: not initialized", PS_Failed);
+        const int ndof = _parameters->GetDOF();
+        if ((int)_parameters->vinitialconfig.size() != ndof || (int)_parameters->vgoalconfig.size() != ndof)
+            return PlannerStatus("cudabirrt: one initial and one goal configuration per problem", PS_Failed);
+        std::vector<TrajectoryBasePtr> vtraj(1, ptraj);
+        std::vector<uint32_t> seeds(1, _parameters->_nRandomGeneratorSeed);
+        std::vector<int> vstatus;
+        PlanPathBatch(_parameters->vinitialconfig, _parameters->vgoalconfig, seeds, vtraj, vstatus);
+        if (vstatus[0] == CC_PLAN_SOLVED) return PlannerStatus(PS_HasSolution);
+        return PlannerStatus("cudabirrt: no path", vstatus[0] == CC_PLAN_BAD_INITIAL ? (PS_Failed | PS_FailedDueToInitial)
+                                                   : vstatus[0] == CC_PLAN_BAD_GOAL ? (PS_Failed | PS_FailedDueToGoal) : PS_Failed);
+    }
+
+    /// starts / goals: [n][ndof]; every solved problem appends its waypoints to vtraj[k] (positions only; retiming is left to the
+    /// caller's post-processor, as after linearsmoother with a retimer-less configuration)
+    void PlanPathBatch(const std::vector<dReal>& starts, const std::vector<dReal>& goals, const std::vector<uint32_t>& seeds,
+                       std::vector<TrajectoryBasePtr>& vtraj, std::vector<int>& vstatus)
+    {
+        EnvironmentLock lock(GetEnv()->GetMutex());
+        const int ndof = _parameters->GetDOF();
+        const int n = (int)starts.size() / ndof;
+        std::vector<cc_plan_result> results(std::max(n, 1));
+        if (cc_birrt_plan_batch(_planner, &_birrt, n, starts.data(), goals.data(), seeds.data(), results.data()) != CC_OK)
+            throw OPENRAVE_EXCEPTION_FORMAT("cudabirrt: %s", cc_last_error(), ORE_Failed);
+        vstatus.resize(n);
+        std::vector<dReal> waypoints;
+        for (int k = 0; k < n; ++k) {
+            vstatus[k] = results[k].status;
+            if (results[k].status != CC_PLAN_SOLVED || k >= (int)vtraj.size() || !vtraj[k]) continue;
+            int nw = 0;
+            cc_planner_get_path(_planner, k, 0, NULL, 0, &nw);
+            waypoints.resize((size_t)nw * ndof);
+            cc_planner_get_path(_planner, k, 0, waypoints.data(), nw, &nw);
+            if (vtraj[k]->GetConfigurationSpecification().GetDOF() == 0) vtraj[k]->Init(_parameters->_configurationspecification);
+            vtraj[k]->Insert(vtraj[k]->GetNumWaypoints(), waypoints, _parameters->_configurationspecification);
+        }
+    }
+
+    virtual PlannerParametersConstPtr GetParameters() const { return _parameters; }
+
+private:
+    RobotBasePtr _robot;
+    RRTParametersPtr _parameters;
+    cc_planner* _planner;
+    cc_birrt_params _birrt;
+};
+
 // ---------------------------------------------------------------------------------------------- plugin entry (plugin.h:30-157)
 class CudaCollisionPlugin : public RavePlugin
 {
 public:
-    CudaCollisionPlugin() { _interfaces[PT_CollisionChecker].push_back("cudacollision"); }
+    CudaCollisionPlugin() { _interfaces[PT_CollisionChecker].push_back("cudacollision"); _interfaces[PT_Planner].push_back("cudabirrt"); }
     virtual ~CudaCollisionPlugin() {}
     virtual InterfaceBasePtr CreateInterface(InterfaceType type, const std::string& interfacename, std::istream& sinput, EnvironmentBasePtr penv)
     {
         if (type == PT_CollisionChecker && interfacename == "cudacollision") return boost::make_shared<CudaCollisionChecker>(penv, boost::ref(sinput));
+        if (type == PT_Planner && interfacename == "cudabirrt") return boost::make_shared<CudaBirrtPlanner>(penv);
         return InterfaceBasePtr();
     }
     virtual const InterfaceMap& GetInterfaces() const { return _interfaces; }
