@@ -84,3 +84,31 @@ def test_activedofs_option(world):
 def test_nonadjacent_list_through_gpu(world):
     scene, env, robot, cc, orc, active, seed = world
     assert robot.GetNonAdjacentLinks(0, checker=cc) == robot.GetNonAdjacentLinks(0, checker=orc)
+
+
+def test_full_size_batch_properties(world):
+    """BASELINE.json's full sizes (1M configurations): size-independent properties — a permuted batch gives the permuted
+    results, two halves give the whole (chunk boundaries, two-stream pipeline, certificates built mid-way do not matter), a
+    random sample agrees with the oracle."""
+    scene, env, robot, cc, orc, active, seed = world
+    n = 1000000
+    q = sample_configs(robot, n, seed=seed, active=active)
+    a = cc.CheckCollisionBatch(robot, q, active=active)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(n)
+    b = cc.CheckCollisionBatch(robot, q[perm], active=active)
+    assert np.array_equal(b["verdict"], a["verdict"][perm])
+    assert np.array_equal(b["first_env_index"], a["first_env_index"][perm])
+    assert np.array_equal(b["first_self_index"], a["first_self_index"][perm])
+    h1 = cc.CheckCollisionBatch(robot, q[:n // 2 + 7], active=active)
+    h2 = cc.CheckCollisionBatch(robot, q[n // 2 + 7:], active=active)
+    assert np.array_equal(np.concatenate([h1["verdict"], h2["verdict"]]), a["verdict"])
+    assert np.array_equal(np.concatenate([h1["first_self_index"], h2["first_self_index"]]), a["first_self_index"])
+    pick = np.sort(rng.choice(n, 1500, replace=False))
+    ref = orc.check_batch(robot, q[pick], active=active, want_band=True)
+    band = classify(ref)
+    assert not ((a["verdict"][pick] != ref["verdict"]) & ~band).any()
+    ok = ~band & (ref["verdict"] == a["verdict"][pick])
+    e = ok & ((ref["verdict"] & 1) != 0)
+    assert np.array_equal(a["first_env"][pick][e], ref["first_env"][e])
+    assert 0.3 < (a["verdict"] != 0).mean() < 0.9
