@@ -253,9 +253,10 @@ int cc_scene_set_tri_epsilon(cc_scene* s, double eps);
  * collision-free.  A pair certified in every cell can never collide inside the joint limits and leaves the batched pair
  * list (hoisting, generalised from pose-invariant pairs); a partly certified pair keeps a bit table that the batched entry
  * consults after the broadphase instead of descending the trees.  Verdicts and reported pairs are unchanged (a skipped pair
- * is at least 3e-4 m from contact).  cc_query_get_table_count reports the pairs with a table and the pairs removed. */
+ * is at least 3e-4 m from contact).  cc_query_get_table_count reports the pairs with a table, the pairs removed and the
+ * wall time the last build took (any pointer may be NULL). */
 int cc_scene_set_pair_tables(cc_scene* s, int enabled);
-int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped);
+int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped, double* out_build_ms);
 
 /* Diagnostics: record, for every configuration of the following batches on this query, how many traversal
  * iterations (32 box-pair tests each) the device spent on it; read the last batch's trace back with

@@ -94,7 +94,7 @@ def load_library():
     lib.cc_tolerance_batch.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
-    lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(cd)]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
@@ -179,9 +179,10 @@ class BoundQuery(object):
 
     def table_count(self):
         """How many link pairs of this query are covered by a certified free-space table (0 until the tables are built)."""
-        n, d = ctypes.c_int(0), ctypes.c_int(0)
-        self.checker._ck(self.lib.cc_query_get_table_count(self.handle, ctypes.byref(n), ctypes.byref(d)))
+        n, d, ms = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+        self.checker._ck(self.lib.cc_query_get_table_count(self.handle, ctypes.byref(n), ctypes.byref(d), ctypes.byref(ms)))
         self.dropped_pairs = d.value
+        self.certificate_build_ms = ms.value
         return n.value + d.value
 
     def link_of(self, qindex):

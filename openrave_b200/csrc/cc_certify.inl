@@ -381,6 +381,9 @@ static int maybe_build_tables(cc_query* q, int n)
     static const long long after = getenv("CC_TUNE_TABLES_AFTER") ? atoll(getenv("CC_TUNE_TABLES_AFTER")) : 16384;
     q->fk_configs_seen += (uint64_t)n;
     if ((long long)q->fk_configs_seen < after) return CC_OK;
-    return build_pair_tables(q);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = build_pair_tables(q);
+    q->cert_build_ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <limits>
 #include <random>
 #include <string>
@@ -280,6 +281,7 @@ struct cc_query {
     Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
     // certified free-space tables of the batched FK-mode plan (built once enough configurations have gone through)
     bool allow_tables = false, tables_done = false;
+    double cert_build_ms = 0.0;              // wall time of the last certificate build
     float cert_tri_eps = 0.0f;               // cc_scene_set_tri_epsilon value the certificates were built with
     std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
     uint64_t fk_configs_seen = 0;
@@ -1641,11 +1643,12 @@ int cc_scene_set_pair_tables(cc_scene* s, int enabled)
     return CC_OK;
 }
 
-int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped)
+int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped, double* out_build_ms)
 {
     if (!q) return fail(CC_ERR_INVALID, "bad arguments");
     if (out_tables) *out_tables = q->ntables > 0 ? q->ntables : 0;
     if (out_dropped) *out_dropped = q->ndropped;
+    if (out_build_ms) *out_build_ms = q->cert_build_ms;
     return CC_OK;
 }
 
