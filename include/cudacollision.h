@@ -231,6 +231,19 @@ int cc_distance_poses(cc_query* q, const double* link_transforms8, int n, int fl
 int cc_tolerance_batch(cc_query* q, const double* dof_values, int n, int flags, double tolerance, uint32_t* within_mask);
 int cc_tolerance_poses(cc_query* q, const double* link_transforms8, int n, int flags, double tolerance, uint32_t* within_mask);
 
+/* ---- CO_Contacts (collisionPQP.h:578-603: PQP_ALL_CONTACTS per link pair, one CONTACT per intersecting triangle pair through
+ * OpenRAVE::geometry::TriTriCollision, geometry.h:1817-1912) for ONE set of link transforms [nlinks][8].  Up to max_contacts
+ * records, sorted by (pair, triangle a, triangle b):
+ *   out_pair[i]           pair index (cc_query_get_pairs)
+ *   out_triangles[i][2]   triangle index inside the query link's mesh / the other link's mesh (the ids PQP reports)
+ *   out_has_contact[i]    TriTriCollision's return value for that triangle pair (0: it yields no CONTACT, as in the reference)
+ *   out_pos_norm[i][6]    contact position and normal (world), valid where out_has_contact[i]; depth is 0 (collisionPQP.h:602)
+ * *out_count = number of intersecting triangle pairs found (if it exceeds max_contacts the list was cut).  The last two
+ * outputs may be NULL.  cc_tri_tri_contact is the contact routine itself (3 x xyz per triangle), returns 0 / 1. */
+int cc_contacts_poses(cc_query* q, const double* link_transforms8, int flags, int max_contacts, int* out_count, int32_t* out_pair,
+                      int32_t* out_triangles, uint8_t* out_has_contact, double* out_pos_norm);
+int cc_tri_tri_contact(const double* u9, const double* v9, double* pos3, double* norm3);
+
 /* Page-locked host buffers for the host-buffer entry points (cc_check_batch, cc_check_poses, cc_fk_batch).  Those calls
  * cut a big batch into chunks and copy each chunk's inputs / results on the chunk's own stream; with buffers from
  * cc_host_alloc the copies overlap the kernels of the neighbouring chunk.  Ordinary (pageable) memory stays valid

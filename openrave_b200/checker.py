@@ -50,7 +50,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_scene_synchronize", "cc_query_trace_work", "cc_query_get_work_trace", "cc_scene_set_tri_epsilon", "cc_scene_set_counters", "cc_scene_get_stats",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
-           "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh"]
+           "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
+           "cc_contacts_poses", "cc_tri_tri_contact"]
 
 _lib = None
 
@@ -91,6 +92,8 @@ def load_library():
     lib.cc_check_poses.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cc_fk_batch.argtypes = [vp, vp, ci, vp]
     lib.cc_device_fp32_peak.argtypes = [ci, ctypes.POINTER(cd)]
+    lib.cc_contacts_poses.argtypes = [vp, vp, ci, ci, ctypes.POINTER(ci), vp, vp, vp, vp]
+    lib.cc_tri_tri_contact.argtypes = [vp, vp, vp, vp]
     lib.cc_tolerance_batch.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
@@ -275,6 +278,20 @@ class BoundQuery(object):
         bits = (mask[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
         return bits.reshape(n, -1)[:, :self.npairs].astype(bool)
 
+    def contacts(self, poses, flags=BATCH_ENV | BATCH_SELF, max_contacts=65536):
+        """CO_Contacts for one set of link transforms: (pair index [m], triangles [m,2], has_contact [m] bool, pos [m,3],
+        norm [m,3], total) — one row per intersecting triangle pair, sorted by (pair, triangle a, triangle b)."""
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(self.info.nlinks, 8)
+        cnt = ctypes.c_int(0)
+        pair = np.zeros(max_contacts, dtype=np.int32)
+        tris = np.zeros((max_contacts, 2), dtype=np.int32)
+        has = np.zeros(max_contacts, dtype=np.uint8)
+        pn = np.zeros((max_contacts, 6), dtype=np.float64)
+        self.checker._ck(self.lib.cc_contacts_poses(self.handle, _ptr(T), flags, max_contacts, ctypes.byref(cnt), _ptr(pair), _ptr(tris),
+                                                    _ptr(has), _ptr(pn)))
+        m = min(cnt.value, max_contacts)
+        return pair[:m], tris[:m], has[:m].astype(bool), pn[:m, 0:3], pn[:m, 3:6], cnt.value
+
     def decode_pair(self, idx):
         """pair indices -> [n, 3] {query link, other body id, other link} (oracle layout), -1 rows where idx < 0."""
         out = np.full((len(idx), 3), -1, dtype=np.int32)
@@ -343,8 +360,6 @@ class CudaCollisionChecker(object):
 
     # ---- CollisionCheckerBase surface (collisionchecker.h:200-237)
     def SetCollisionOptions(self, options):
-        if options & CO_Contacts:
-            return False   # contact points of colliding pairs are not provided by this checker
         if options != self._options:
             self._options = int(options)
             self._invalidate()
@@ -592,6 +607,14 @@ class CudaCollisionChecker(object):
                         l1, ob, l2, _ = bq.pairs[p]
                         report.AddLinkCollision(bq.link_of(l1), self._bodies[ob].links[l2])
                 report.minDistance = 0
+            if hit and report is not None and (self._options & CO_Contacts):
+                # one CONTACT per intersecting triangle pair that TriTriCollision accepts (collisionPQP.h:591-603), depth 0
+                pidx, _, has, pos, norm, _ = bq.contacts(T, BATCH_ENV)
+                for p, ok, x, nrm in zip(pidx, has, pos, norm):
+                    if ok:
+                        l1, ob, l2, _ = bq.pairs[p]
+                        key = (bq.link_of(l1), self._bodies[ob].links[l2])
+                        report.contacts_by_pair.setdefault(key, []).append((x.copy(), nrm.copy(), 0.0))
             if report is not None and (self._options & CO_Distance) and not hit:
                 self._fill_distance(bq, a, BATCH_ENV, report)
             if report is not None and (self._options & CO_UseTolerance):

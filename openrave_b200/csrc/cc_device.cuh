@@ -128,6 +128,11 @@ struct Params {
     // certified free-space tables (FK mode only): pair_table[k] >= 0 names a table over the 1 or 2 active DOFs the pair's
     // relative pose depends on; a set bit = every configuration of that cell is at least the contact band away from contact
     // (distance at the cell centre > the largest displacement any point can make inside the cell), so the pair is skipped
+    // all-contacts flavour (CO_Contacts on the report path): every intersecting triangle pair is appended as
+    // {configuration, reference pair index, triangle of slot a, triangle of slot b} (global triangle indices)
+    uint4* contact_out;
+    uint32_t* contact_count;    // [0] number of records produced (may exceed contact_cap: the rest is dropped)
+    int32_t contact_cap;
     const int32_t* pair_table;  // [npairs_dev] (same order as `pairs`), or NULL
     const struct PairTable* tables;
     const uint32_t* table_bits;
@@ -543,7 +548,9 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // each over its own share of the pair list, outputs merged with atomics (small batches: the latency of a batch is the
 // traversal of its slowest configuration, so that one is spread over several warps).
 // kTables: the plan carries certified free-space tables (compiled out otherwise, so plans without tables run the plain code).
-template <bool kSplit, bool kTables>
+// kContacts: all contacts of every pair are enumerated and recorded (PQP_ALL_CONTACTS, collisionPQP.h:578): no pair is
+// abandoned at its first contact; used with kFlagAllPairs for single configurations.
+template <bool kSplit, bool kTables, bool kContacts = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -783,6 +790,10 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                             // contacts: record them, then purge everything that no longer matters from the queues
                             const uint32_t s = e.x >> 26;
                             const int pidx = pass ? slot_pair[s] : kNone;
+                            if (kContacts && pass) {
+                                const uint32_t at = atomicAdd(P.contact_count, 1u);
+                                if ((int)at < P.contact_cap) P.contact_out[at] = make_uint4((uint32_t)c, (uint32_t)pidx, e.x & 0x3ffffffu, e.y);
+                            }
                             slot_hit |= __reduce_or_sync(kFull, pass ? (1u << s) : 0u);
                             const int pe = __reduce_min_sync(kFull, (pass && pidx < nenv_total) ? pidx : kNone);
                             const int ps = __reduce_min_sync(kFull, (pass && pidx >= nenv_total) ? pidx : kNone);
@@ -793,7 +804,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                                 if (best_env != kNone) { best_env = -1; best_self = -1; }
                                 else if (best_self != kNone) best_self = -1;
                             }
-                            slot_dead |= slot_hit;
+                            if (!kContacts) slot_dead |= slot_hit;
                             if (!all_pairs) {
                                 bool d = false;
                                 if (lane < nsl) { const int p = slot_pair[lane]; d = (p < nenv_total) ? (p > best_env) : (p > best_self); }

@@ -281,6 +281,9 @@ struct cc_query {
     Plan full, mainl, hoisted;               // pose mode | batched FK mode | pose-invariant pairs (evaluated once at bind)
     // certified free-space tables of the batched FK-mode plan (built once enough configurations have gone through)
     bool allow_tables = false, tables_done = false;
+    uint4* contact_out = nullptr;            // set around a cc_contacts_poses launch
+    uint32_t* contact_count = nullptr;
+    int contact_cap = 0;
     double cert_build_ms = 0.0;              // wall time of the last certificate build
     float cert_tri_eps = 0.0f;               // cc_scene_set_tri_epsilon value the certificates were built with
     std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
@@ -421,8 +424,9 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        const void* variants[4] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>};
+        const void* variants[5] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>};
         int per_sm = 1 << 30;
         for (const void* kfn : variants) {
             CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -448,6 +452,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         int want = forced > 0 ? forced : std::min(by_load, by_pairs);
         while (split * 2 <= want && split < 8) split *= 2;
     }
+    const bool contacts = Q->contact_out != nullptr && (flags & CC_BATCH_ALL_PAIRS);
+    if (contacts) { split = 1; P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
@@ -515,7 +521,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        if (use_tables) {
+        if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
             else ccdev::cc_traverse_kernel<false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         } else {
@@ -1530,6 +1537,10 @@ int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double ma
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     return launch_distance(q, q->full, true, T8, n, flags, max_distance, rel_err, abs_err, min_distance, min_pair, closest_points);
 }
+
+}  // extern "C" (reopened below)
+#include "cc_contacts.inl"
+extern "C" {
 
 // CO_UseTolerance: which pairs are within `tolerance` of each other (PQP_Tolerance: distance <= tolerance, pqp/PQP.cpp:1056).
 // Per-pair mode of the distance kernel with the search radius just above the tolerance; one bit per pair of the query.

@@ -27,6 +27,7 @@ class CollisionReport(object):
         self.minDistance = 1e20
         self.numCols = 0
         self.nNumValidCollisions = 0
+        self.contacts_by_pair = {}    # CO_Contacts: (link1, link2) -> [(pos, norm, depth)] (CollisionPairInfo::contacts)
         self.numWithinTol = 0         # CO_UseTolerance: bodies with a link pair within the tolerance
         self.contacts = []            # CO_Distance: [(pos, norm, depth)] of the closest pair (collisionPQP.h:633-647)
 

@@ -77,6 +77,7 @@ def _load(kind):
     lib.orc_check_link_pairs.argtypes = [vp, ci, vp, vp, ci, vp]
     lib.orc_check_batch.argtypes = [vp, ci, vp, ci, ctypes.POINTER(OrcOptions), vp, ci, vp, vp, vp, vp, vp, vp, vp,
                                     ctypes.c_int64, vp, vp]
+    lib.orc_tri_tri_collision.argtypes = [vp, vp, vp, vp]
     lib.orc_pair_queries.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, cd, cd, vp, vp]
     lib.orc_distance_batch.argtypes = [vp, ci, vp, ci, vp, vp, ci, cd, vp, vp]
     lib.orc_time_batch.restype = cd
@@ -264,6 +265,15 @@ class OracleChecker(object):
         self.lib.orc_distance_batch(self.scene, bid, _ptr(act), len(active), ctypes.byref(opt), _ptr(q), n,
                                     float(max_distance), _ptr(dist), _ptr(pair))
         return dict(distance=dist, pair=pair)
+
+    def tri_tri_collision(self, u, v):
+        """The reference's TriTriCollision on world-space triangles u, v [3,3] (reference build only): (hit, pos, norm)."""
+        u = np.ascontiguousarray(u, dtype=np.float64); v = np.ascontiguousarray(v, dtype=np.float64)
+        pos, norm = np.zeros(3), np.zeros(3)
+        rc = self.lib.orc_tri_tri_collision(_ptr(u), _ptr(v), _ptr(pos), _ptr(norm))
+        if rc < 0:
+            raise RuntimeError("TriTriCollision is only available in the reference-linked oracle build")
+        return bool(rc), pos, norm
 
     def pair_queries(self, body, q, triples, active=None, cap=0.0, tolerance=0.0):
         """Per configuration and (query link, other body id, other link) triple: exact distance clipped at `cap`, and

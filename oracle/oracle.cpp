@@ -42,6 +42,8 @@
 #include "../include/cudacollision.h"   // POD cc_joint + option bits only
 
 #ifdef ORACLE_USE_REF_PQP
+#include <array>                    // (geometry.h uses std::array without including it)
+#include <openrave/geometry.h>      // the reference's own TriTriCollision (header-only, include/openrave/geometry.h:1817-1912)
 #include "PQP.h"
 #endif
 
@@ -1467,6 +1469,24 @@ int orc_pair_queries(void* sp, int body, const int32_t* active, int nactive, con
         }
     }
     return 0;
+}
+
+// The reference's contact routine for one intersecting triangle pair (collisionPQP.h:591-603 calls it per PQP contact):
+// the UNMODIFIED OpenRAVE::geometry::TriTriCollision in the _ref build; -1 in the restated build (contacts are pinned on the
+// reference routine only).  u, v: 3 x xyz world coordinates.
+int orc_tri_tri_collision(const double* u, const double* v, double* pos, double* norm)
+{
+#ifdef ORACLE_USE_REF_PQP
+    using OpenRAVE::geometry::RaveVector;
+    RaveVector<double> u1(u[0], u[1], u[2]), u2(u[3], u[4], u[5]), u3(u[6], u[7], u[8]);
+    RaveVector<double> v1(v[0], v[1], v[2]), v2(v[3], v[4], v[5]), v3(v[6], v[7], v[8]), p, n;
+    if (!OpenRAVE::geometry::TriTriCollision(u1, u2, u3, v1, v2, v3, p, n)) return 0;
+    pos[0] = p.x; pos[1] = p.y; pos[2] = p.z; norm[0] = n.x; norm[1] = n.y; norm[2] = n.z;
+    return 1;
+#else
+    (void)u; (void)v; (void)pos; (void)norm;
+    return -1;
+#endif
 }
 
 // Single-thread timing helper for the CPU baseline: runs orc_check_batch semantics (no band, no outputs

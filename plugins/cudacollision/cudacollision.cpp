@@ -146,12 +146,12 @@ public:
     // ------------------------------------------------------------------------------------------ options
     virtual bool SetCollisionOptions(int options)
     {
-        if (options & (CO_UseTolerance | CO_Contacts | CO_RayAnyHit)) return false;   // not provided (cf. fclcollision.cpp:171-180)
+        if (options & CO_RayAnyHit) return false;   // rays are not provided (cf. fclcollision.cpp:171-180)
         if (options != _options) { _options = options; _DropQueries(); }
         return true;
     }
     virtual int GetCollisionOptions() const { return _options; }
-    virtual void SetTolerance(dReal) {}
+    virtual void SetTolerance(dReal tolerance) { _tolerance = tolerance; _options |= CO_UseTolerance; }   // collisionPQP.h:426-428
 
     // ------------------------------------------------------------------------------------------ bodies
     virtual bool InitEnvironment()
@@ -507,6 +507,39 @@ private:
         return p->GetLinks().at(links[2 * qindex + 1]);
     }
 
+    /// CO_Contacts: one CONTACT per intersecting triangle pair TriTriCollision accepts, depth 0 (collisionPQP.h:591-603)
+    void _FillContacts(cc_query* query, const std::vector<double>& T8, int flags, CollisionReportPtr report)
+    {
+        const int maxcontacts = 1 << 16;
+        std::vector<int32_t> pairs(maxcontacts), tris(2 * (size_t)maxcontacts);
+        std::vector<uint8_t> has(maxcontacts);
+        std::vector<double> posnorm(6 * (size_t)maxcontacts);
+        int count = 0;
+        _Check(cc_contacts_poses(query, T8.data(), flags, maxcontacts, &count, pairs.data(), tris.data(), has.data(), posnorm.data()));
+        std::vector<int32_t> quads = _Quads(query);
+        for (int i = 0; i < std::min(count, maxcontacts); ++i) {
+            if (!has[i]) continue;
+            const int p = pairs[i];
+            KinBody::LinkConstPtr plink1 = _QueryLink(query, quads[4 * p]);
+            KinBody::LinkConstPtr plink2 = quads[4 * p + 3] == 1 ? _QueryLink(query, quads[4 * p + 2])
+                                                                    : KinBody::LinkConstPtr(_byid[quads[4 * p + 1]].lock()->GetLinks().at(quads[4 * p + 2]));
+            const int icollision = report->AddLinkCollision(*plink1, *plink2);
+            const double* o = &posnorm[6 * (size_t)i];
+            report->vCollisionInfos[icollision].contacts.push_back(CONTACT(Vector(o[0], o[1], o[2]), Vector(o[3], o[4], o[5]), 0));
+        }
+    }
+
+    /// CO_UseTolerance: numWithinTol = other bodies with at least one link pair within the tolerance (collisionPQP.h:443-497)
+    void _FillTolerance(cc_query* query, const std::vector<double>& T8, const cc_query_info& info, CollisionReportPtr report)
+    {
+        std::vector<uint32_t> within(info.mask_words);
+        _Check(cc_tolerance_poses(query, T8.data(), 1, CC_BATCH_ENV, _tolerance, within.data()));
+        std::vector<int32_t> quads = _Quads(query);
+        std::set<int> bodies;
+        for (int p = 0; p < info.npairs_env; ++p) if ((within[p >> 5] >> (p & 31)) & 1u) bodies.insert(quads[4 * p + 1]);
+        report->numWithinTol = (int)bodies.size();
+    }
+
     /// CO_Distance on a bound single-state query (collisionPQP.h:622-648): minDistance, the closest pair, one contact
     void _FillDistance(cc_query* query, const std::vector<double>& T8, int flags, CollisionReportPtr report)
     {
@@ -708,7 +741,9 @@ private:
         uint32_t verdict = 0;
         _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | (!report ? 0 : CC_BATCH_ALL_PAIRS), &verdict, NULL, NULL, !report ? NULL : mask.data()));
         if ((verdict & CC_VERDICT_ENV) && !!report) _FillReport(pbody, query, mask, info.npairs_env, report);
+        if ((verdict & CC_VERDICT_ENV) && !!report && (_options & CO_Contacts)) _FillContacts(query, T8, CC_BATCH_ENV, report);
         if (!(verdict & CC_VERDICT_ENV) && !!report && (_options & CO_Distance)) _FillDistance(query, T8, CC_BATCH_ENV, report);
+        if (!!report && (_options & CO_UseTolerance)) _FillTolerance(query, T8, info, report);
         return (verdict & CC_VERDICT_ENV) != 0;
     }
 
@@ -807,6 +842,7 @@ private:
 
     cc_scene* _scene;
     int _options, _device;
+    dReal _tolerance = 0;
     std::string _userdatakey;
     std::map<int, KinBodyWeakPtr> _byid;
     std::map<QueryKey, cc_query*> _queries;
