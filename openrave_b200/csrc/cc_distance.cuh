@@ -12,10 +12,12 @@
 //   1. every pair's world-AABB gap (from the FK kernel's boxes) gives a lower bound; the pair with the smallest bound is
 //      descended first so that the running minimum `best2` is tight before the other pairs are looked at;
 //   2. pairs whose bound is below best2 are descended 32 at a time (one relative pose per slot in shared memory);
-//   3. an iteration pops up to 32 (nodeA, nodeB) items, each lane bounds its box pair from below (sum of squared gaps along
-//      A's three axes and along B's three axes, the larger of the two), drops it when the bound reaches best2, runs the exact
-//      triangle-triangle distance on leaf pairs (9 edge-edge + 6 vertex-face candidates, 0 when the 17-axis test reports
-//      contact) and otherwise pushes the two children of the larger box;
+//   3. an iteration pops up to 32 items — the two children of one node against a node of the other tree — and each lane bounds
+//      both box pairs from below (sum of squared gaps along A's three axes and along B's three axes, the larger of the two);
+//      a child whose bound reaches best2 is dropped, a leaf pair goes to the triangle queue, otherwise the larger box of the
+//      pair is split into the next item (the nearer child is stored last, so it is expanded first); queued leaf pairs run 32
+//      at a time through the exact triangle-triangle distance (9 edge-edge + 6 vertex-face candidates, 0 when the 17-axis
+//      test reports contact);
 //   4. a warp min-reduction keeps best2, the pair and the closest points.
 // Boxes are inflated by 1e-5 m at build time, so a lower bound can only be too small: nothing that could hold the minimum
 // is pruned by rounding.
@@ -232,7 +234,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                 if (ncb == 0) break;
             }
             __syncwarp();
-            int sp = 0;
+            int sp = 0, ntri = 0;
             {
                 bool cand = false;
                 uint32_t ra = 0, rb = 0;
@@ -263,14 +265,29 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                     ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
                     cand = true;
                 }
-                const unsigned cm = __ballot_sync(kFull, cand);
-                if (cand) stack[__popc(cm & lt_mask)] = make_uint2(ra | ((uint32_t)lane << 26), rb);
-                sp = __popc(cm);
+                // first items: two leaves go straight to the triangle queue, otherwise the larger root box is split
+                // (item = the two children of the split node x the other node; bit 31 of y: the children live in tree B)
+                bool leafpair = false;
+                uint2 it0 = make_uint2(0u, 0u);
+                if (cand) {
+                    const float4 a0 = __ldg(&P.nodes[2 * ra]), a1 = __ldg(&P.nodes[2 * ra + 1]);
+                    const float4 b0 = __ldg(&P.nodes[2 * rb]), b1 = __ldg(&P.nodes[2 * rb + 1]);
+                    const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+                    const uint32_t sb = (uint32_t)lane << 26;
+                    if (la < 0 && lb < 0) { leafpair = true; it0 = make_uint2((uint32_t)(~la) | sb, (uint32_t)(~lb)); }
+                    else if (lb < 0 || (la >= 0 && a1.w > b1.w)) it0 = make_uint2((uint32_t)la | sb, rb);
+                    else it0 = make_uint2((uint32_t)lb | sb, ra | 0x80000000u);
+                }
+                const unsigned tm0 = __ballot_sync(kFull, leafpair);
+                const unsigned pm0 = __ballot_sync(kFull, cand && !leafpair);
+                if (leafpair) triq[__popc(tm0 & lt_mask)] = it0;
+                if (cand && !leafpair) stack[__popc(pm0 & lt_mask)] = it0;
+                ntri = __popc(tm0);
+                sp = __popc(pm0);
             }
             __syncwarp();
 
-            // ---- drain: box pairs 32 at a time; leaf pairs are queued and evaluated 32 at a time
-            int ntri = 0;
+            // ---- drain: 32 items at a time (two box bounds each); leaf pairs are queued and evaluated 32 at a time
             while (sp > 0 || ntri > 0) {
                 if (ntri >= 32 || (sp == 0 && ntri > 0)) {
                     const int tn = ntri < 32 ? ntri : 32;
@@ -318,44 +335,52 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                 if (valid) it = stack[sp - 1 - lane];
                 sp -= n;
                 __syncwarp();
-                bool push = false, leaf = false;
+                // each item: children x, x+1 of one tree against node y of the other; a child whose bound reaches the running
+                // minimum is dropped here and never stored
+                bool lf0 = false, lf1 = false, ps0 = false, ps1 = false;
                 uint2 o0 = make_uint2(0u, 0u), o1 = o0;
-                const uint32_t s = it.x >> 26;
+                float g0 = 3.0e38f, g1 = 3.0e38f;
                 if (valid) {
-                    const uint32_t x = it.x & 0x3ffffffu, y = it.y;
-                    const float4 a0 = __ldg(&P.nodes[2 * x]), a1 = __ldg(&P.nodes[2 * x + 1]);
-                    const float4 b0 = __ldg(&P.nodes[2 * y]), b1 = __ldg(&P.nodes[2 * y + 1]);
-                    const float* rt = slot_rt + 24 * s;
+                    const uint32_t sbits = it.x & 0xfc000000u;
+                    const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x7fffffffu;
+                    const bool side = (it.y >> 31) != 0u;               // false: the children are in tree A, true: in tree B
+                    const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
+                    const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
+                    const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
+                    const float* rt = slot_rt + 24 * (it.x >> 26);
                     float R[9], t[3];
 #pragma unroll
                     for (int k = 0; k < 9; ++k) R[k] = rt[k];
                     t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-                    if (box_gap2(R, t, a0, a1, b0, b1) < thr2) {
-                        const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
-                        if (la < 0 && lb < 0) {
-                            leaf = true;
-                            o0 = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
-                        } else {
-                            push = true;
-                            if (lb < 0 || (la >= 0 && a1.w > b1.w)) {
-                                o0 = make_uint2((uint32_t)la | (s << 26), y);
-                                o1 = make_uint2((uint32_t)(la + 1) | (s << 26), y);
-                            } else {
-                                o0 = make_uint2(x | (s << 26), (uint32_t)lb);
-                                o1 = make_uint2(x | (s << 26), (uint32_t)(lb + 1));
-                            }
+                    g0 = side ? box_gap2(R, t, oa, ob, c0a, c0b) : box_gap2(R, t, c0a, c0b, oa, ob);
+                    g1 = side ? box_gap2(R, t, oa, ob, c1a, c1b) : box_gap2(R, t, c1a, c1b, oa, ob);
+                    const int lo = __float_as_int(oa.w);
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if ((ch ? g1 : g0) < thr2) {
+                            const int lc = __float_as_int(ch ? c1a.w : c0a.w);
+                            const float sc = ch ? c1b.w : c0b.w;
+                            uint2 out;
+                            const bool tq = lc < 0 && lo < 0;
+                            if (tq) out = side ? make_uint2((uint32_t)(~lo) | sbits, (uint32_t)(~lc)) : make_uint2((uint32_t)(~lc) | sbits, (uint32_t)(~lo));
+                            else if (lo < 0 || (lc >= 0 && sc > ob.w)) out = make_uint2((uint32_t)lc | sbits, it.y);                          // split the child
+                            else out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));                                // split the other
+                            if (ch) { o1 = out; lf1 = tq; ps1 = !tq; } else { o0 = out; lf0 = tq; ps0 = !tq; }
                         }
                     }
+                    // the nearer child is stored last, so that it is expanded first
+                    if (ps0 && ps1 && g0 < g1) { const uint2 tmp = o0; o0 = o1; o1 = tmp; }
                 }
-                const unsigned lm = __ballot_sync(kFull, leaf);
-                if (leaf) triq[ntri + __popc(lm & lt_mask)] = o0;
-                ntri += __popc(lm);
-                const unsigned pm = __ballot_sync(kFull, push);
-                if (push) {
-                    const int at = sp + 2 * __popc(pm & lt_mask);
-                    stack[at] = o0; stack[at + 1] = o1;
+                {
+                    const unsigned l0 = __ballot_sync(kFull, lf0), l1 = __ballot_sync(kFull, lf1);
+                    if (lf0) triq[ntri + __popc(l0 & lt_mask)] = o0;
+                    if (lf1) triq[ntri + __popc(l0) + __popc(l1 & lt_mask)] = o1;
+                    ntri += __popc(l0) + __popc(l1);
+                    const unsigned p0 = __ballot_sync(kFull, ps0), p1 = __ballot_sync(kFull, ps1);
+                    if (ps0) stack[sp + __popc(p0 & lt_mask)] = o0;
+                    if (ps1) stack[sp + __popc(p0) + __popc(p1 & lt_mask)] = o1;
+                    sp += __popc(p0) + __popc(p1);
                 }
-                sp += 2 * __popc(pm);
                 __syncwarp();
             }
             if (best2 == 0.f) break;
