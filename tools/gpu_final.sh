@@ -18,7 +18,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cc_traverse -s 10 -c 1 -f -o gpurun_out/prof_trav_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_trav_$TAG.log 2>&1; echo "ncu trav rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:cc_fk -s 10 -c 1 -f -o gpurun_out/prof_fk_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cc_fk -s 40 -c 1 -f -o gpurun_out/prof_fk_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_fk_$TAG.log 2>&1; echo "ncu fk rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cc_traverse -s 10 -c 1 -f -o gpurun_out/prof_trav_clutter_$TAG \
     python bench.py --workload wam_clutter200_1250k --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_trav_clutter_$TAG.log 2>&1; echo "ncu trav clutter rc=$?"
