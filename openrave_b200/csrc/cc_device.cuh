@@ -36,7 +36,10 @@
 namespace ccdev {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMinBlocksPerSM = 8;   // 32 warps / SM: registers capped at 64 per thread
+#ifndef CC_MIN_BLOCKS
+#define CC_MIN_BLOCKS 7
+#endif
+constexpr int kMinBlocksPerSM = CC_MIN_BLOCKS;   // shared memory allows 7 blocks (28 warps) per SM: the register cap follows that (73), not 8 blocks (64)
 constexpr int kFkThreads = 128;
 #ifndef CC_STACK_CAP
 #define CC_STACK_CAP 320
