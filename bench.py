@@ -634,6 +634,10 @@ def main():
             tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
             if os.path.isfile(tp):   # dram bytes of one step's kernels, from the committed `ncu --set full` capture
                 traffic = json.load(open(tp)).get("dram_bytes_per_step")
+            physical = None
+            pp = os.path.join(ROOT, "profiles", "physical_%s.json" % args.workload)
+            if os.path.isfile(pp):   # utilisation counters of the dominant kernel from the committed ncu capture of this command
+                physical = json.load(open(pp))
             # compute side: the reference's box / triangle test counts priced at 263 / 745 flops + FK
             from openrave_b200.checker import device_fp32_peak
             fp32_peak = device_fp32_peak(local_rank)
@@ -644,6 +648,7 @@ def main():
                                 "fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
                                          "algorithmic_flops_per_config": flops_per_config,
                                          "peak_source": "measured in this run (cc_device_fp32_peak: FMA chains on every SM)"},
+                                "physical": physical,
                                 "algorithmic_bytes_per_config": bytes_per_config,
                                 "ref_bv_tests_per_config": cnt[0], "ref_tri_tests_per_config": cnt[1],
                                 "note": "algorithmic bytes follow the reference's counters (no broadphase, all contacts); frac > 1 "
