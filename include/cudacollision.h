@@ -324,8 +324,14 @@ typedef struct cc_birrt_params {
     int32_t max_extend_steps;        /* Extend's "avoid infinite loops" bound, 100 (rplanners.h:324) */
     int32_t speculate_steps;         /* steps of a ray sent per round: 0 the whole ray, n > 0 fixed chunks, n < 0 adaptive (|n| first,
                                       * doubling while the chunks pass); the plans are the same for every value */
-    int32_t reserved;
+    int32_t post_processor;          /* cc_post_processor: PlannerParameters::_sPostProcessingPlanner */
 } cc_birrt_params;
+
+/* The path optimiser that runs on the raw plan (`_sPostProcessingPlanner`): the default "linearsmoother"
+ * (planner.cpp:28, 315; plugins/rplanners/linearsmoother.cpp) or "shortcut_linear" (ShortcutLinearPlanner,
+ * plugins/rplanners/linearshortcutadvanced.cpp:76-569: _SubsampleTrajectory, _OptimizePath, _OptimizePathOneDOF — the one
+ * rmanipulation/basemanipulation.cpp:788 selects).  Both run `smoother_iterations` iterations per pass. */
+enum cc_post_processor { CC_POST_LINEARSMOOTHER = 0, CC_POST_SHORTCUT_LINEAR = 1 };
 
 enum cc_plan_status { CC_PLAN_FAILED = 0, CC_PLAN_SOLVED = 1, CC_PLAN_BAD_INITIAL = 2, CC_PLAN_BAD_GOAL = 3 };
 
@@ -336,7 +342,7 @@ typedef struct cc_plan_result {
     int32_t waypoints_raw;           /* after _ExtractPath (incl. _SimpleOptimizePath) */
     int32_t waypoints;               /* after the linear smoother */
     int32_t rounds;                  /* lockstep rounds this problem took part in */
-    int32_t reserved;
+    int32_t shortcuts;               /* successful shortcuts of the shortcut_linear post-processor (its return values) */
     double length_raw, length;       /* sum of SimpleDistanceMetric over consecutive waypoints */
     uint64_t configs_submitted;      /* configurations sent to the checker for this problem */
     uint64_t configs_serial;         /* configurations the serial per-sample loop would have checked (up to each first failure) */

@@ -628,6 +628,193 @@ struct Problem {
         co_return 0;
     }
 
+    // ---------------------------------------------------------------------------------------- shortcut_linear post-processor
+    // ShortcutLinearPlanner (plugins/rplanners/linearshortcutadvanced.cpp): the planner basemanipulation selects
+    // (rmanipulation/basemanipulation.cpp:788).  Every CheckPathAllConstraints call carries CFO_FillCheckedConfiguration, and
+    // the configurations it returns on success are the samples it visited (planningutils.cpp:2801-2813, 3410-3413, 3524-3533,
+    // 3611-3623): q0 first when the interval is closed at the start, the interior samples, q1 LAST when it is closed at the end
+    // — i.e. edge_samples' checking order with the leading q1 rotated to the back.  They do not depend on any verdict, so a
+    // whole shortcut (all segments of a single-DOF shortcut) is generated first and sent to the checker as one group.
+    void filled_configurations(size_t cfg_begin, size_t cfg_end, int interval, std::vector<double>& out) const
+    {
+        const int n = ndof();
+        out.clear();
+        if (cfg_end <= cfg_begin) return;
+        const bool check_end = (interval == IT_OpenStart || interval == IT_Closed);
+        const double* q = group.q.data();
+        if (check_end) {
+            out.insert(out.end(), q + (cfg_begin + 1) * n, q + cfg_end * n);
+            out.insert(out.end(), q + cfg_begin * n, q + (cfg_begin + 1) * n);
+        } else out.insert(out.end(), q + cfg_begin * n, q + cfg_end * n);
+    }
+
+    // ShortcutLinearPlanner::_SubsampleTrajectory (linearshortcutadvanced.cpp:578-652)
+    void subsample_trajectory(const std::vector<double>& in, PathList& lp) const
+    {
+        const int n = ndof();
+        const size_t nw = in.size() / n;
+        std::vector<double> q0(in.begin(), in.begin() + n), q1(n), dq(n), dq2(n), qcur;
+        lp.nodes.push_back(PathList::Node{q0, 0});
+        qcur = q0;
+        for (size_t ip = 1; ip < nw; ++ip) {
+            q1.assign(in.begin() + ip * n, in.begin() + (ip + 1) * n);
+            dq = q1;
+            cs->diff(dq.data(), q0.data());
+            int nsteps = 1;
+            for (int i = 0; i < n; ++i) {
+                const int s = cs->res[i] != 0 ? (int)(std::fabs(dq[i]) / cs->res[i]) : (int)(std::fabs(dq[i]) * 100);
+                nsteps = std::max(nsteps, s);
+            }
+            const double fisteps = 1.0 / nsteps;
+            for (int i = 0; i < n; ++i) dq[i] *= fisteps;
+            // q + dq repeatedly; the default neighbour function never fails, so the `mult` retry of the reference stays at 1;
+            // a clamped step (NSS_SuccessfulWithDeviation) ends the subsampling of this segment
+            for (int f = 1; f < nsteps; ++f) {
+                if (cs->neigh(qcur.data(), dq.data())) { qcur = lp.nodes.back().q; break; }
+                const double d = cs->dist(lp.nodes.back().q.data(), qcur.data());
+                lp.nodes.push_back(PathList::Node{qcur, d});
+            }
+            const double d = cs->dist(lp.nodes.back().q.data(), q1.data());
+            lp.nodes.push_back(PathList::Node{q1, d});
+            qcur = q1;
+            q0.swap(q1);
+        }
+        // the reference appends the last waypoint once more (:648-650), at distance 0 from its twin
+        q1.assign(in.end() - n, in.end());
+        lp.nodes.push_back(PathList::Node{q1, cs->dist(lp.nodes.back().q.data(), q1.data())});
+    }
+
+    // ShortcutLinearPlanner::_OptimizePath (linearshortcutadvanced.cpp:188-339)
+    Task<int> shortcut_linear_path(PathList& lp, int maxiter, Sampler& rs)
+    {
+        const int n = ndof();
+        int numshortcuts = 0;
+        std::vector<double> cfgs, dists;
+        for (int iiter = maxiter; iiter > 0 && lp.nodes.size() > 2;) {
+            --iiter;
+            const uint32_t endIndex = 2 + rs.u32() % ((uint32_t)lp.nodes.size() - 2);
+            const uint32_t startIndex = rs.u32() % (endIndex - 1);
+            auto itstart = std::next(lp.nodes.begin(), startIndex);
+            auto itend = itstart;
+            double total = 0;
+            for (uint32_t j = 0; j < endIndex - startIndex; ++j) { ++itend; total += itend->d; }
+            if (cs->dist(itstart->q.data(), itend->q.data()) > total - 0.1 * prm.step_length) continue;
+            group.clear();
+            add_edge(itstart->q.data(), itend->q.data(), IT_Open);
+            if (group.state_error) continue;
+            filled_configurations(0, group.q.size() / n, IT_Open, cfgs);
+            if (cfgs.empty()) continue;                        // nothing between the end points: the reference rejects (:265-270)
+            CheckReply r = co_await check();
+            if (r.first_fail_segment >= 0) continue;
+            const size_t nc = cfgs.size() / n;
+            dists.assign(nc + 1, 0.0);
+            double newtotal = dists[0] = cs->dist(itstart->q.data(), &cfgs[0]);
+            for (size_t k = 1; k < nc; ++k) { dists[k] = cs->dist(&cfgs[(k - 1) * n], &cfgs[k * n]); newtotal += dists[k]; }
+            dists[nc] = cs->dist(&cfgs[(nc - 1) * n], itend->q.data());
+            newtotal += dists[nc];
+            if (newtotal > total - 0.1 * prm.step_length) continue;
+            ++itstart;
+            for (size_t k = 0; k < nc; ++k)
+                lp.nodes.insert(itstart, PathList::Node{std::vector<double>(cfgs.begin() + k * n, cfgs.begin() + (k + 1) * n), dists[k]});
+            itend->d = dists[nc];
+            lp.nodes.erase(itstart, itend);
+            ++numshortcuts;
+        }
+        co_return numshortcuts;
+    }
+
+    // ShortcutLinearPlanner::_OptimizePathOneDOF (linearshortcutadvanced.cpp:344-569): one DOF is interpolated linearly in
+    // path length over a random sub-path, the other DOFs keep their values
+    Task<int> shortcut_linear_one_dof(PathList& lp, int maxiter, Sampler& rs)
+    {
+        const int n = ndof();
+        int numshortcuts = 0;
+        std::vector<double> vcur(n), vnext(n), vdelta(n), cfgs;
+        std::list<PathList::Node> sp;
+        for (int iiter = 0; iiter < maxiter; ++iiter) {
+            if (lp.nodes.size() <= 2) break;
+            uint32_t idof = rs.u32() % (uint32_t)(n + 1);       // the last DOF gets twice the chance (:374-377)
+            if (idof > (uint32_t)(n - 1)) idof = n - 1;
+            const uint32_t endIndex = 2 + rs.u32() % ((uint32_t)lp.nodes.size() - 2);
+            const uint32_t startIndex = rs.u32() % (endIndex - 1);
+            if (endIndex == startIndex + 1) continue;
+            auto itstart = std::next(lp.nodes.begin(), startIndex);
+            auto itend = itstart;
+            double totaldof = 0, total = 0, curv = itstart->q[idof];
+            for (uint32_t j = 0; j < endIndex - startIndex; ++j) {
+                ++itend;
+                totaldof += std::fabs(itend->q[idof] - curv);
+                total += itend->d;
+                curv = itend->q[idof];
+            }
+            const double expected = itend->q[idof] - itstart->q[idof];
+            if (std::fabs(expected) > totaldof - 0.1 * cs->res[idof]) continue;
+            sp.clear();
+            group.clear();
+            bool ok = true;
+            const double fdelta = expected / total, fstart = itstart->q[idof];
+            double fcurdist = 0, newdof = 0, newtotal = 0;
+            auto itnode = itstart;
+            vcur = itnode->q;
+            do {
+                ++itnode;
+                fcurdist += itnode->d;
+                vnext = itnode->q;
+                if (itnode != itend) vnext[idof] = fstart + fcurdist * fdelta;
+                // through _neighstatefn from the last accepted configuration (:436-474)
+                const std::vector<double>& from = sp.empty() ? vcur : sp.back().q;
+                for (int k = 0; k < n; ++k) { vdelta[k] = vnext[k] - from[k]; vnext[k] = from[k]; }
+                const bool deviated = cs->neigh(vnext.data(), vdelta.data());
+                if (itnode == itend && deviated) { ok = false; break; }
+                const size_t c0 = group.q.size() / n;
+                add_edge(vcur.data(), vnext.data(), IT_OpenStart);
+                if (group.state_error) { ok = false; break; }
+                filled_configurations(c0, group.q.size() / n, IT_OpenStart, cfgs);
+                if (cfgs.empty()) { ok = false; break; }
+                // NB the reference measures the first configuration of EVERY segment from the shortcut's start node (:506-508)
+                sp.push_back(PathList::Node{std::vector<double>(cfgs.begin(), cfgs.begin() + n), cs->dist(itstart->q.data(), &cfgs[0])});
+                newdof += std::fabs(cfgs[idof] - itstart->q[idof]);
+                newtotal += sp.back().d;
+                for (size_t k = 1; k < cfgs.size() / n && ok; ++k) {
+                    const double* c = &cfgs[k * n];
+                    newdof += std::fabs(c[idof] - sp.back().q[idof]);
+                    if (newdof > totaldof - 0.1 * cs->res[idof]) { ok = false; break; }
+                    const double d = cs->dist(sp.back().q.data(), c);
+                    sp.push_back(PathList::Node{std::vector<double>(c, c + n), d});
+                    newtotal += d;
+                    if (newtotal > 1.1 * total) { ok = false; break; }
+                }
+                if (!ok) break;
+                vcur.swap(vnext);
+            } while (itnode != itend);
+            if (!ok || sp.empty()) continue;                    // rejected on lengths alone: no verdict can change that
+            CheckReply r = co_await check();
+            if (r.first_fail_segment >= 0) continue;
+            ++numshortcuts;
+            ++itstart;
+            ++itend;
+            lp.nodes.insert(itstart, sp.begin(), sp.end());
+            lp.nodes.erase(itstart, itend);
+        }
+        co_return numshortcuts;
+    }
+
+    // ShortcutLinearPlanner::PlanPath (linearshortcutadvanced.cpp:76-184) without the retimer that follows it
+    Task<int> shortcut_linear(const std::vector<double>& in, std::vector<double>& out)
+    {
+        const int n = ndof();
+        if ((int)in.size() < 2 * n) { out = in; co_return 0; }
+        Sampler rs(seed);                                       // _puniformsampler->SetSeed(_nRandomGeneratorSeed) (:62)
+        PathList lp;
+        subsample_trajectory(in, lp);
+        const int iters = prm.smoother_iterations > 0 ? prm.smoother_iterations : 100;   // _InitPlan (:54-56)
+        res.shortcuts = co_await shortcut_linear_path(lp, iters, rs);
+        res.shortcuts += co_await shortcut_linear_one_dof(lp, iters, rs);
+        out.clear();
+        for (auto& nd : lp.nodes) out.insert(out.end(), nd.q.begin(), nd.q.end());
+        co_return 0;
+    }
+
     // BirrtPlanner::InitPlan + PlanPath for one start and one goal
     Task<int> plan()
     {
@@ -694,7 +881,8 @@ struct Problem {
         co_await simple_optimize(path_raw, prm.path_optimize_iterations);
         res.waypoints_raw = (int)path_raw.size() / n;
         res.length_raw = path_length(path_raw);
-        if (prm.smoother_iterations > 0) co_await smooth(path_raw, path);
+        if (prm.smoother_iterations > 0 && prm.post_processor == CC_POST_SHORTCUT_LINEAR) co_await shortcut_linear(path_raw, path);
+        else if (prm.smoother_iterations > 0) co_await smooth(path_raw, path);
         else path = path_raw;
         res.waypoints = (int)path.size() / n;
         res.length = path_length(path);

@@ -215,6 +215,175 @@ def CheckPathAllConstraints(constraint, q0, q1, interval=IT_Closed, options=0xff
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class ShortcutLinearPlanner(object):
+    """RaveCreatePlanner(env, 'shortcut_linear') (plugins/rplanners/linearshortcutadvanced.cpp), literally: one
+    CheckPathAllConstraints call per candidate segment, in the reference's order, over a DynamicsCollisionConstraint.  The
+    library runs the same optimiser with whole shortcuts per checker call (csrc/cc_planner.cpp, CC_POST_SHORTCUT_LINEAR);
+    this class is the per-call form the tests compare it with.  Retiming (the `_linearretimer` that follows) is not part of
+    the collision path."""
+
+    def __init__(self, constraint, weights=None, step_length=0.04, max_iterations=100, seed=0):
+        self.c = constraint
+        n = len(constraint.active)
+        self.w2 = np.ones(n) if weights is None else np.asarray(weights, dtype=np.float64) ** 2
+        self.step_length = step_length if step_length > 0 else 0.04          # _InitPlan (:52-59)
+        self.max_iterations = max_iterations if max_iterations > 0 else 100
+        bg = np.random.MT19937()
+        bg._legacy_seeding(int(seed))                                        # mt19937ar.h init_genrand(seed)
+        self._bg = bg
+        self.calls = 0                                                       # CheckPathAllConstraints calls made
+
+    def _u32(self):
+        return int(self._bg.random_raw())
+
+    def _dist(self, a, b):
+        """SimpleDistanceMetric::Eval (planningutils.cpp:4714-4723), summed in DOF order."""
+        d = self.c.diffstate(a, b)
+        s = 0.0
+        for i in range(len(d)):
+            s += float(self.w2[i]) * float(d[i]) * float(d[i])
+        return math.sqrt(s)
+
+    def _check(self, q0, q1, interval):
+        fr = ConstraintFilterReturn()
+        self.calls += 1
+        try:
+            ret = self.c.Check(q0, q1, interval, 0xffff | CFO_FillCheckedConfiguration, fr)
+        except NotImplementedError:
+            return CFO_StateSettingError, []
+        return ret, [np.array(c, dtype=np.float64) for c in fr._configurations]
+
+    def _subsample(self, waypoints):
+        """_SubsampleTrajectory (:578-652)."""
+        c = self.c
+        q0 = np.array(waypoints[0], dtype=np.float64)
+        path = [[q0.copy(), 0.0]]
+        qcur = q0.copy()
+        for ip in range(1, len(waypoints)):
+            q1 = np.array(waypoints[ip], dtype=np.float64)
+            dq = c.diffstate(q1, q0)
+            nsteps = 1
+            for i in range(len(dq)):
+                steps = int(abs(dq[i]) / c.resolution[i]) if c.resolution[i] != 0 else int(abs(dq[i]) * 100)
+                nsteps = max(nsteps, steps)
+            dq = dq * (1.0 / nsteps)
+            for f in range(1, nsteps):
+                qn, dev = c.neighstate(qcur, dq)
+                if dev:                                                      # NSS_SuccessfulWithDeviation: stop subsampling
+                    qcur = path[-1][0].copy()
+                    break
+                qcur = qn
+                path.append([qcur.copy(), self._dist(path[-1][0], qcur)])
+            path.append([q1.copy(), self._dist(path[-1][0], q1)])
+            qcur = q1.copy()
+            q0 = q1
+        qlast = np.array(waypoints[-1], dtype=np.float64)
+        path.append([qlast, self._dist(path[-1][0], qlast)])                 # the reference adds the last point twice (:648-650)
+        return path
+
+    def _optimize_path(self, path):
+        """_OptimizePath (:188-339)."""
+        num = 0
+        iiter = self.max_iterations
+        while iiter > 0 and len(path) > 2:
+            iiter -= 1
+            end = 2 + self._u32() % (len(path) - 2)
+            start = self._u32() % (end - 1)
+            total = 0.0
+            for j in range(start + 1, end + 1):                              # plain left-to-right sum like the reference
+                total += path[j][1]
+            if self._dist(path[start][0], path[end][0]) > total - 0.1 * self.step_length:
+                continue
+            ret, cfgs = self._check(path[start][0], path[end][0], IT_Open)
+            if ret != 0 or len(cfgs) == 0:
+                continue
+            dists = [self._dist(path[start][0], cfgs[0])]
+            for k in range(1, len(cfgs)):
+                dists.append(self._dist(cfgs[k - 1], cfgs[k]))
+            dists.append(self._dist(cfgs[-1], path[end][0]))
+            newtotal = 0.0
+            for d in dists:
+                newtotal += d
+            if newtotal > total - 0.1 * self.step_length:
+                continue
+            path[end][1] = dists[-1]
+            path[start + 1:end] = [[cfgs[k], dists[k]] for k in range(len(cfgs))]
+            num += 1
+        return num
+
+    def _optimize_path_one_dof(self, path):
+        """_OptimizePathOneDOF (:344-569)."""
+        c = self.c
+        n = len(c.active)
+        num = 0
+        for _ in range(self.max_iterations):
+            if len(path) <= 2:
+                break
+            idof = min(self._u32() % (n + 1), n - 1)
+            end = 2 + self._u32() % (len(path) - 2)
+            start = self._u32() % (end - 1)
+            if end == start + 1:
+                continue
+            totaldof, total, curv = 0.0, 0.0, path[start][0][idof]
+            for j in range(start + 1, end + 1):
+                totaldof += abs(path[j][0][idof] - curv)
+                total += path[j][1]
+                curv = path[j][0][idof]
+            expected = path[end][0][idof] - path[start][0][idof]
+            if abs(expected) > totaldof - 0.1 * c.resolution[idof]:
+                continue
+            sp, ok = [], True
+            fdelta, fstart, fcur = expected / total, path[start][0][idof], 0.0
+            newdof = newtotal = 0.0
+            vcur = path[start][0].copy()
+            for j in range(start + 1, end + 1):
+                fcur += path[j][1]
+                vnext = path[j][0].copy()
+                if j != end:
+                    vnext[idof] = fstart + fcur * fdelta
+                base = sp[-1][0] if sp else vcur
+                vnext, dev = c.neighstate(base.copy(), vnext - base)
+                if j == end and dev:
+                    ok = False
+                    break
+                ret, cfgs = self._check(vcur, vnext, IT_OpenStart)
+                if ret != 0 or len(cfgs) == 0:
+                    ok = False
+                    break
+                sp.append([cfgs[0], self._dist(path[start][0], cfgs[0])])   # sic: from the start node for every segment (:506-508)
+                newdof += abs(cfgs[0][idof] - path[start][0][idof])
+                newtotal += sp[-1][1]
+                for k in range(1, len(cfgs)):
+                    newdof += abs(cfgs[k][idof] - sp[-1][0][idof])
+                    if newdof > totaldof - 0.1 * c.resolution[idof]:
+                        ok = False
+                        break
+                    sp.append([cfgs[k], self._dist(sp[-1][0], cfgs[k])])
+                    newtotal += sp[-1][1]
+                    if newtotal > 1.1 * total:
+                        ok = False
+                        break
+                if not ok:
+                    break
+                vcur = vnext
+            if not ok or not sp:
+                continue
+            num += 1
+            path[start + 1:end + 1] = sp
+        return num
+
+    def PlanPath(self, waypoints):
+        """Returns (new waypoints [m, ndof], shortcuts of pass 1, shortcuts of pass 2)."""
+        waypoints = np.asarray(waypoints, dtype=np.float64)
+        if len(waypoints) < 2:
+            return waypoints.copy(), 0, 0
+        path = self._subsample(waypoints)
+        a = self._optimize_path(path)
+        b = self._optimize_path_one_dof(path)
+        return np.array([p[0] for p in path]), a, b
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # BiRRT + linear shortcutting in lockstep over the batched entry (libcudacollision.so: csrc/cc_planner.cpp)
 
 import ctypes
@@ -229,17 +398,18 @@ class cc_birrt_params(ctypes.Structure):
     _fields_ = [("step_length", ctypes.c_double), ("goal_bias", ctypes.c_double), ("point_tolerance", ctypes.c_double),
                 ("max_iterations", ctypes.c_int32), ("path_optimize_iterations", ctypes.c_int32),
                 ("smoother_iterations", ctypes.c_int32), ("max_extend_steps", ctypes.c_int32), ("speculate_steps", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("post_processor", ctypes.c_int32)]
 
 
 class cc_plan_result(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("iterations", ctypes.c_int32), ("nodes_forward", ctypes.c_int32),
                 ("nodes_backward", ctypes.c_int32), ("waypoints_raw", ctypes.c_int32), ("waypoints", ctypes.c_int32),
-                ("rounds", ctypes.c_int32), ("reserved", ctypes.c_int32), ("length_raw", ctypes.c_double),
+                ("rounds", ctypes.c_int32), ("shortcuts", ctypes.c_int32), ("length_raw", ctypes.c_double),
                 ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64)]
 
 
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
+POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
                    "cc_planner_edge_samples", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
@@ -270,7 +440,7 @@ class BirrtPlanner(object):
     (start, goal) problems in lockstep; `PlanPath` is the single-problem call of the reference API."""
 
     def __init__(self, robot, checker, step_length=0.04, max_iterations=10000, goal_bias=0.01, smoother_iterations=100,
-                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8):
+                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8, post_processor="linearsmoother"):
         self.lib = _planner_lib()
         self.robot = robot
         self.active = list(robot.GetActiveDOFIndices())
@@ -287,7 +457,7 @@ class BirrtPlanner(object):
         self._ck(self.lib.cc_planner_create(ctypes.byref(sp), ctypes.byref(h)))
         self.handle = h
         self.params = cc_birrt_params(step_length, goal_bias, point_tolerance, max_iterations, path_optimize_iterations,
-                                      smoother_iterations, 100, speculate_steps, 0)
+                                      smoother_iterations, 100, speculate_steps, POST_PROCESSORS[post_processor])
         self._keep = None
         if isinstance(checker, tuple):
             fn, blk = checker

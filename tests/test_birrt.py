@@ -100,6 +100,32 @@ def test_lockstep_and_ray_chunking_do_not_change_plans(wamtest1):
             assert a["rounds"] >= b["rounds"]
 
 
+def test_shortcut_linear_equals_the_per_call_restatement(wamtest1):
+    """`shortcut_linear` (ShortcutLinearPlanner, linearshortcutadvanced.cpp:76-569) as the post-processor: the library sends a whole
+    shortcut (every segment of a single-DOF shortcut) to the checker at once; the Python class makes one CheckPathAllConstraints
+    call per segment like the reference.  Same random stream, same raw path => the same waypoints, bit for bit."""
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 8, seed=3)
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot), post_processor="shortcut_linear")
+    res = P.PlanBatch(starts, goals, seeds=np.arange(8))
+    base = pl.BirrtPlanner(robot, orc.group_checker(robot)).PlanBatch(starts, goals, seeds=np.arange(8))
+    cons = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    shortcuts = 0
+    for k, (r, b) in enumerate(zip(res, base)):
+        assert r["status"] == pl.PLAN_SOLVED and np.array_equal(r["path_raw"], b["path_raw"])    # only the post-processor differs
+        S = pl.ShortcutLinearPlanner(cons, weights=P._w, step_length=0.04, max_iterations=100, seed=k)
+        p, n1, n2 = S.PlanPath(r["path_raw"])
+        assert np.array_equal(p, r["path"]) and n1 + n2 == r["shortcuts"]
+        shortcuts += r["shortcuts"]
+        assert np.array_equal(r["path"][0], starts[k]) and np.array_equal(r["path"][-1], goals[k])
+        assert r["length"] <= r["length_raw"] + 1e-9
+        assert not orc.check_batch(robot, r["path"])["verdict"].any()
+    assert shortcuts >= 5                                             # the optimiser did fire (and one-DOF shortcuts among them)
+    solo = pl.BirrtPlanner(robot, orc.group_checker(robot), post_processor="shortcut_linear", speculate_steps=0)
+    for k in (4, 5):                                                  # lockstep width does not matter
+        assert np.array_equal(solo.PlanPath(starts[k], goals[k], k)["path"], res[k]["path"])
+
+
 def test_colliding_endpoints_are_refused(wamtest1):
     env, robot, orc = wamtest1
     act = robot.GetActiveDOFIndices()
@@ -147,6 +173,27 @@ def test_gpu_plans_equal_oracle_serial_plans(wamtest1):
     assert all(r["status"] == pl.PLAN_SOLVED for r in gpu)
     for r in gpu:
         assert not orc.check_batch(robot, r["path"])["verdict"].any()
+
+
+@pytest.mark.gpu
+def test_gpu_shortcut_linear_plans_equal_oracle_serial_plans(wamtest1):
+    from openrave_b200.checker import CudaCollisionChecker
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 16, seed=3)
+    seeds = np.arange(16)
+    cpu = pl.BirrtPlanner(robot, orc.group_checker(robot), post_processor="shortcut_linear").PlanBatch(starts, goals, seeds)
+    env2 = load_scene("wamtest1")
+    robot2 = env2.GetRobots()[0]
+    robot2.SetActiveDOFs(robot2.GetActiveManipulator().GetArmIndices())
+    cc = CudaCollisionChecker(env2, 0)
+    env2.SetCollisionChecker(cc)
+    gpu = pl.BirrtPlanner(robot2, cc, post_processor="shortcut_linear").PlanBatch(starts, goals, seeds)
+    same = sum(1 for a, b in zip(cpu, gpu) if a["status"] == b["status"] and np.array_equal(a["path"], b["path"])
+               and a["shortcuts"] == b["shortcuts"])
+    assert same >= 15, same                                          # a difference needs a sample inside the 1e-4 m contact band
+    assert sum(r["shortcuts"] for r in gpu) >= 5
+    for r in gpu:
+        assert r["status"] == pl.PLAN_SOLVED and not orc.check_batch(robot, r["path"])["verdict"].any()
 
 
 @pytest.mark.gpu
