@@ -133,7 +133,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_baseline(env, robot, q, budget_s=12.0, kind=None):
+def cpu_baseline(env, robot, q, budget_s=12.0, kind=None, gpu=None):
     """Single-thread pqprave-equivalent configs/s on a bounded prefix of the same batch."""
     import oracle
     if kind is None:
@@ -146,8 +146,26 @@ def cpu_baseline(env, robot, q, budget_s=12.0, kind=None):
     secs, _ = orc.time_batch(robot, q[:m])
     ref = orc.check_batch(robot, q[:min(m, 2000)])
     cnt = ref["counters"].astype(np.float64)
+    parity = None
+    if gpu is not None:
+        # SURVEY.md 8d parity stats on the same prefix: verdict bits + first colliding pairs of the CUDA path against the CPU arm;
+        # a differing configuration is classified with the oracle's contact band (separation / penetration <= 1e-4 m)
+        k = len(ref["verdict"])
+        bad = gpu["verdict"][:k] != ref["verdict"]
+        fe = gpu["first_env"][:k].copy()
+        hit = fe[:, 0] >= 0
+        fe[hit, 1] = [orc._ids[id(gpu["checker"].body_from_id(b))] for b in fe[hit, 1]]       # body ids of the two harnesses differ
+        pair_bad = ~bad & ((fe != ref["first_env"]).any(axis=1) | (gpu["first_self"][:k] != ref["first_self"]).any(axis=1))
+        idx = np.nonzero(bad | pair_bad)[0]
+        in_band = 0
+        if len(idx):
+            b = orc.check_batch(robot, q[idx], want_band=True)
+            in_band = int(((b["near"] != 0) | ((b["verdict"] != 0) & (b["penetration"] <= 1e-4))).sum())
+        parity = {"compared": int(k), "verdict_and_pairs_identical": int(k - len(idx)), "verdict_differs": int(bad.sum()),
+                  "first_pair_differs": int(pair_bad.sum()), "differing_inside_1e-4m_band": in_band,
+                  "differing_outside_band": int(len(idx) - in_band), "against": "oracle (%s)" % kind}
     return {"value": m / secs, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs)}, cnt.mean(axis=0)
+            "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs)}, cnt.mean(axis=0), parity
 
 
 def run_reference_arm(args):
@@ -625,8 +643,11 @@ def main():
         base = None
         cnt = None
         if not args.no_cpu_baseline and world == 1:
-            base, cnt = cpu_baseline(env, robot, q_host)
+            got = cc.CheckCollisionBatch(robot, q_host[:2000])     # the product's answers for the prefix the CPU arm also checks
+            got["checker"] = cc
+            base, cnt, parity = cpu_baseline(env, robot, q_host, gpu=got)
             line["cpu_baseline"] = base
+            line["parity"] = parity
         if cnt is not None:
             bytes_per_config = cnt[0] * 2 * 64 + cnt[1] * 2 * 36 + 8 * ndof + 16
             achieved = n * bytes_per_config / (kernel_ms / 1000.0) / 1e9

@@ -369,6 +369,17 @@ int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user);
  * joint limits (state-setting error). */
 int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, int interval,
                             double* out_configs, int max_configs, int* out_count);
+/* The same for a parabolic ramp: DynamicsCollisionConstraint::Check's quadratic branch (planningutils.cpp:2660-2681, 2726-2766,
+ * 2844-3319), taken when the caller passes end-point velocities and timeelapsed > 0 — the parabolic smoothers' feasibility
+ * checks (plugins/rplanners/parabolicsmoother.cpp, CheckPathAllConstraints(a, b, da, db, timeelapsed, ...)).  The sampled
+ * positions follow q0 + dq0 t + (dq1 - dq0) t^2 / (2 timeelapsed); out_times[i] is the ramp time of sample i (NaN for the
+ * linear sub-steps the reference inserts where a step still exceeds 1.01 x a resolution) and out_kind[i] is its
+ * cc_ramp_sample_kind: only CC_RAMP_REPORTED samples appear in ConstraintFilterReturn::_configurations.  All samples are in
+ * checking order; the tail sub-steps (between the last ramp sample and q1) are checked BEFORE that last ramp sample (:3207-3296).  *out_count = -1: CFO_StateSettingError (no root, the ramp needs steps 100x finer than the resolutions, ...). */
+int cc_planner_ramp_samples(cc_planner* p, const double* q0, const double* q1, const double* dq0, const double* dq1,
+                            double timeelapsed, int interval, double* out_configs, double* out_times, uint8_t* out_kind,
+                            int max_configs, int* out_count);
+enum cc_ramp_sample_kind { CC_RAMP_SUBSTEP = 0, CC_RAMP_REPORTED = 1, CC_RAMP_TAIL_SUBSTEP = 2, CC_RAMP_END_UNREPORTED = 3 };
 /* BiRRT + path shortcutting for nproblems (start, goal) pairs in lockstep.  starts/goals: [nproblems][ndof];
  * seeds[nproblems] = PlannerParameters::_nRandomGeneratorSeed per problem.  results[nproblems] is filled; the paths stay in
  * the planner until the next call and are read with cc_planner_get_path. */

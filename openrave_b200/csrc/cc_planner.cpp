@@ -158,6 +158,197 @@ int edge_samples(const CSpace& cs, const double* q0, const double* q1, int inter
     return count;
 }
 
+// mathextra::solvequad (include/openrave/mathextra.h:214-256): roots of a x^2 + b x + c, the small-root forms kept
+int solvequad(double a, double b, double c, double& r1, double& r2)
+{
+    if (a == 0) {
+        if (b == 0) return 0;
+        r1 = r2 = -c / b;
+        return 1;
+    }
+    if (c == 0) { r1 = 0; r2 = -b / a; return 2; }
+    double d = b * b - 4.0 * c * a;
+    if (d < 0) {
+        if (d < -1e-16) return 0;
+        d = 0;
+    }
+    d = std::sqrt(d);
+    if (std::fabs(-b - d) < std::fabs(a)) r1 = 0.5 * (-b + d) / a; else r1 = 2.0 * c / (-b - d);
+    if (std::fabs(-b + d) < std::fabs(a)) r2 = 0.5 * (-b - d) / a; else r2 = 2.0 * c / (-b + d);
+    return 2;
+}
+
+// DynamicsCollisionConstraint::Check, quadratic branch (planningutils.cpp:2726-2766, 2844-3319): the edge is the ramp
+// q(t) = q0 + dq0 t + a t^2 / 2 with a = (dq1 - dq0) / timeelapsed.  The DOF that needs the most steps (counting both sides of
+// its turning point) is advanced by equal increments of its own travelled distance; the time of every increment comes from
+// the ramp's quadratic, and a step in which another DOF would move farther than 1.01 x its resolution is cut short in time.
+// Same order as the linear branch: q1 first when the interval is closed at the end, q0 when closed at the start, then the
+// walk.  `filled` holds the cc_ramp_sample_kind of every configuration: only kind 1 is reported by CFO_FillCheckedConfiguration
+// (linear sub-steps after a step that still exceeds 1.01 x a resolution are checked but not reported, :3163-3196, 3207-3258).  Returns the number of appended configurations or -1 = CFO_StateSettingError.
+int edge_samples_quadratic(const CSpace& cs, const double* q0, const double* q1, const double* dq0, const double* dq1, double T,
+                           int interval, std::vector<double>& out, std::vector<double>* times, std::vector<uint8_t>* filled)
+{
+    const int n = cs.n;
+    int start = (interval == IT_Open || interval == IT_OpenStart) ? 1 : 0;
+    const bool check_end = (interval == IT_OpenStart || interval == IT_Closed);
+    int count = 0;
+    auto push = [&](const double* q, double t, int f) {
+        out.insert(out.end(), q, q + n);
+        if (times) times->push_back(t);
+        if (filled) filled->push_back((uint8_t)f);
+        ++count;
+    };
+    if (check_end) push(q1, T, 1);
+    std::vector<double> dQ(q1, q1 + n), acc(n), cur(q0, q0 + n), vel(dq0, dq0 + n), prev(n), prevvel(n);
+    cs.diff(dQ.data(), q0);
+    const double iT = 1.0 / T;
+    for (int i = 0; i < n; ++i) acc[i] = (dq1[i] - dq0[i]) * iT;
+    int nsteps = 0, largest = -1, total = 0;
+    for (int i = 0; i < n; ++i) {
+        double travel = std::fabs(dQ[i]);
+        if (std::fabs(acc[i]) > kEpsilonLinear) {
+            const double tin = -dq0[i] / acc[i];
+            if (tin >= 0 && tin < T) {                       // the DOF turns around inside the ramp: count both legs
+                const double pin = 0.5 * dq0[i] * tin;
+                travel = std::fabs(pin) + std::fabs(dQ[i] - pin);
+            }
+        }
+        const int s = cs.res[i] != 0 ? (int)(travel / cs.res[i] + 0.99) : (int)(travel * 100);
+        total += s;
+        if (s > nsteps) { nsteps = s; largest = i; }
+    }
+    if (total == 0 && start > 0) return count;
+    if (start == 0) { push(q0, 0.0, 1); start = 1; }
+    if (nsteps == 0) return count;
+
+    const double aL = acc[largest], vL = dq0[largest], fLargestStep = dQ[largest];
+    double tInflection = T, fInflection = dQ[largest], fTravel = fInflection, fDelta;
+    if (std::fabs(aL) > kEpsilonLinear) {
+        const double tin = -vL / aL;
+        if (tin >= 0 && tin < T) {
+            tInflection = tin;
+            fInflection = 0.5 * vL * tInflection;
+            fTravel = std::fabs(fInflection) + std::fabs(dQ[largest] - fInflection);
+            fDelta = fTravel / nsteps;
+            if (fInflection < 0 || (std::fabs(fInflection) <= kEpsilonLinear && dQ[largest] > 0)) fDelta = -fDelta;
+        } else fDelta = fTravel / (double)nsteps;
+    } else fDelta = fTravel / (double)nsteps;
+
+    double roots[2], timestep = 0, fStep = 0, prevtime = 0, fBest = 0;
+    int istep = 0, repeating = 0;
+    bool compute_new = true, pending = false;
+    while (istep < nsteps && prevtime < T) {
+        if (pending) { push(cur.data(), timestep, 1); pending = false; }
+        double tmin = prevtime;
+        if (compute_new) {
+            if (prevtime >= tInflection) fBest = fStep - fDelta;
+            else if ((fDelta > 0 && fStep + fDelta > fInflection) || (fDelta < 0 && fStep + fDelta < fInflection)) {
+                fBest = fInflection - (fStep + fDelta - fInflection);       // straddles the turning point: reflect
+                tmin = tInflection - 1e-7;
+            } else fBest = fStep + fDelta;
+        }
+        if (std::fabs(aL) <= kEpsilonLinear) {
+            if (!(std::fabs(vL) > kEpsilon)) return -1;                      // "axis does not move?" (the reference asserts)
+            timestep = fBest / vL;
+        } else {
+            double fNew = fBest;
+            bool found = false;
+            int nr = solvequad(aL * 0.5, vL, -fNew, roots[0], roots[1]);
+            if (nr == 0 && std::fabs(fNew - fLargestStep) < 1e-7) { timestep = T; found = true; }
+            if (!found) {
+                for (int r = 0; r < nr; ++r)
+                    if (roots[r] > tmin && (!found || timestep > roots[r])) { timestep = roots[r]; found = true; }
+                if (!found && tmin < tInflection) {
+                    fNew = fStep;
+                    nr = solvequad(aL * 0.5, vL, -fNew, roots[0], roots[1]);
+                    for (int r = 0; r < nr; ++r)
+                        if (roots[r] > tmin && (!found || timestep > roots[r])) { timestep = roots[r]; fBest = fNew; found = true; }
+                }
+            }
+            if (!found) return -1;
+        }
+        prev = cur;
+        prevvel = vel;
+        double dqscale = 1.0;
+        for (int i = 0; i < n; ++i) {
+            dQ[i] = q0[i] + timestep * (dq0[i] + timestep * 0.5 * acc[i]) - cur[i];
+            if (std::fabs(dQ[i]) > cs.res[i] * 1.01) {
+                const int nr = solvequad(acc[i] * 0.5, dq0[i], q0[i] - cur[i] - cs.res[i], roots[0], roots[1]);
+                double tscaled = 0;
+                bool fs = false;
+                for (int r = 0; r < nr; ++r)
+                    if (roots[r] >= tmin && roots[r] <= timestep) {
+                        if (!fs || roots[r] < tscaled) tscaled = roots[r];
+                        fs = true;
+                    }
+                const double sc = (fs && timestep > prevtime) ? (tscaled - prevtime) / (timestep - prevtime) : std::fabs(cs.res[i] / dQ[i]);
+                if (sc < dqscale) dqscale = sc;
+            }
+        }
+        if (dqscale < 1) {
+            ++repeating;
+            if (dqscale <= 0.01 || repeating > nsteps * 2) return -1;
+            timestep = prevtime + (timestep - prevtime) * dqscale;
+            for (int i = 0; i < n; ++i) {
+                dQ[i] = q0[i] + timestep * (dq0[i] + timestep * 0.5 * acc[i]) - cur[i];
+                vel[i] = dq0[i] + timestep * acc[i];
+            }
+        } else {
+            for (int i = 0; i < n; ++i) vel[i] = dq0[i] + timestep * acc[i];
+            repeating = 0;
+            if (timestep > T + 1e-7) {
+                if (istep + 1 >= nsteps) break;                              // expected at the very end
+                return -1;
+            } else if (timestep > T) timestep = T;
+        }
+        cs.neigh(cur.data(), dQ.data());                                     // a clamp only sets bHasRampDeviatedFromInterpolation
+        pending = true;
+        bool moved = false;
+        int npost = 1;
+        for (int i = 0; i < n; ++i) {
+            const double f = std::fabs(cur[i] - prev[i]);
+            if (f > cs.res[i] * 1.01) npost = std::max(npost, (int)(f / cs.res[i] + 0.9999));
+            if (f > 0.0001) moved = true;
+        }
+        if (npost > 1) {
+            const double inp = 1 / (double)npost;
+            std::vector<double> step(n);
+            for (int i = 0; i < n; ++i) step[i] = (cur[i] - prev[i]) * inp;
+            for (int k = 0; k + 1 < npost; ++k) {
+                for (int i = 0; i < n; ++i) prev[i] += step[i];
+                push(prev.data(), NAN, 0);
+            }
+        }
+        if (!moved || (istep + 1 < nsteps && repeating > 2) || dqscale >= 1) { fStep = fBest; compute_new = true; ++istep; }
+        else compute_new = false;
+        prevtime = timestep;
+    }
+    if (std::fabs(fStep - fLargestStep) > std::fabs(fDelta)) return -1;      // "fStep did not reach fLargestStep"
+    {
+        int npost = 1;
+        for (int i = 0; i < n; ++i) {
+            const double f = std::fabs(q1[i] - cur[i]);
+            if (f > cs.res[i] * 1.01) npost = std::max(npost, (int)(f / cs.res[i] + 0.9999));
+        }
+        if (npost > 1) {
+            const double inp = 1 / (double)npost;
+            std::vector<double> step(n);
+            for (int i = 0; i < n; ++i) step[i] = (q1[i] - cur[i]) * inp;
+            prev = cur;
+            for (int k = 0; k + 1 < npost; ++k) {
+                for (int i = 0; i < n; ++i) prev[i] += step[i];
+                push(prev.data(), NAN, 2);
+            }
+        }
+    }
+    if (pending && cs.dist(cur.data(), q1) > 1e-7) {
+        push(cur.data(), timestep, 1);
+        // the walk stopped short of q1: the reference then leaves q1 out of the reported configurations (:3280)
+        if (check_end && filled) (*filled)[filled->size() - count] = 3;
+    }
+    return count;
+}
+
 // ------------------------------------------------------------------------------------------------ request / coroutine glue
 struct Group {                       // one request of one problem: ordered segments of ordered configurations
     std::vector<double> q;
@@ -990,6 +1181,22 @@ int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, i
     const int c = edge_samples(p->cs, q0, q1, interval, buf);
     *out_count = c;
     if (c > 0 && out_configs) std::memcpy(out_configs, buf.data(), sizeof(double) * p->cs.n * (size_t)std::min(c, std::max(max_configs, 0)));
+    return CC_OK;
+}
+
+int cc_planner_ramp_samples(cc_planner* p, const double* q0, const double* q1, const double* dq0, const double* dq1, double timeelapsed,
+                            int interval, double* out_configs, double* out_times, uint8_t* out_filled, int max_configs, int* out_count)
+{
+    if (!p || !q0 || !q1 || !dq0 || !dq1 || !out_count || interval < 0 || interval > 3 || !(timeelapsed > 0))
+        return fail(CC_ERR_INVALID, "cc_planner_ramp_samples: bad arguments");
+    std::vector<double> buf, times;
+    std::vector<uint8_t> filled;
+    const int c = edge_samples_quadratic(p->cs, q0, q1, dq0, dq1, timeelapsed, interval, buf, &times, &filled);
+    *out_count = c;
+    const size_t m = c > 0 ? (size_t)std::min(c, std::max(max_configs, 0)) : 0;
+    if (m && out_configs) std::memcpy(out_configs, buf.data(), sizeof(double) * p->cs.n * m);
+    if (m && out_times) std::memcpy(out_times, times.data(), sizeof(double) * m);
+    if (m && out_filled) std::memcpy(out_filled, filled.data(), m);
     return CC_OK;
 }
 

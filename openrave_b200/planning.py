@@ -24,6 +24,24 @@ CFO_CheckWithPerturbation = 0x00010000                                    # plan
 CFO_FillCheckedConfiguration = 0x00020000                                 # planner.h:38
 CFO_StateSettingError = 0x80000000                                        # planner.h:44
 G_EPSILON_JOINT_LIMIT = 1e-7                                               # g_fEpsilonJointLimit
+G_EPSILON_LINEAR = 1e-15 ** 0.9                                            # g_fEpsilonLinear (libopenrave.h:140)
+
+
+def _solvequad(a, b, c):
+    """mathextra::solvequad (include/openrave/mathextra.h:214-256); returns the list of roots."""
+    if a == 0:
+        return [] if b == 0 else [-c / b]
+    if c == 0:
+        return [0.0, -b / a]
+    d = b * b - 4.0 * c * a
+    if d < 0:
+        if d < -1e-16:
+            return []
+        d = 0.0
+    d = math.sqrt(d)
+    r1 = 0.5 * (-b + d) / a if abs(-b - d) < abs(a) else 2.0 * c / (-b - d)
+    r2 = 0.5 * (-b - d) / a if abs(-b + d) < abs(a) else 2.0 * c / (-b + d)
+    return [r1, r2]
 
 
 class ConstraintFilterReturn(object):
@@ -56,6 +74,7 @@ class DynamicsCollisionConstraint(object):
         self.upper = np.array([j.upper for j in joints])
         self.resolution = np.array([j.resolution for j in joints])
         self.circular = np.array([bool(j.circular) for j in joints])
+        self.weights = np.array([j.weight for j in joints])
 
     # ---- parameter functions
     def diffstate(self, q1, q0):
@@ -115,6 +134,216 @@ class DynamicsCollisionConstraint(object):
             out.append(cur.copy()); times.append(1.0); kinds.append('step')
         return np.array(out).reshape(-1, len(q0)), times, kinds
 
+    # ---- the sample sequence of a parabolic ramp (quadratic branch), in the order the reference checks it
+    def ramp_samples(self, q0, q1, dq0, dq1, timeelapsed, interval=IT_Closed):
+        """DynamicsCollisionConstraint::Check with end-point velocities and timeelapsed > 0 (planningutils.cpp:2660-2681,
+        2726-2766, 2844-3319).  Returns (samples [m, ndof], times [m] (NaN = linear sub-step), kinds [m]: 1 reported, 0 sub-step, 2 tail sub-step,
+        3 unreported end point) or None for
+        CFO_StateSettingError.  Scalar arithmetic in the reference's order (csrc/cc_planner.cpp holds the C++ twin)."""
+        n = len(self.active)
+        q0 = [float(x) for x in q0]; q1 = [float(x) for x in q1]
+        dq0 = [float(x) for x in dq0]; dq1 = [float(x) for x in dq1]
+        T = float(timeelapsed)
+        res = [float(x) for x in self.resolution]
+        eps_lin = G_EPSILON_LINEAR
+        start = 1 if interval in (IT_Open, IT_OpenStart) else 0
+        check_end = interval in (IT_OpenStart, IT_Closed)
+        out, times, filled = [], [], []
+
+        def push(q, t, f):
+            out.append(list(q)); times.append(t); filled.append(int(f))
+
+        def pack():
+            return np.array(out, dtype=np.float64).reshape(-1, n), times, filled
+
+        if check_end:
+            push(q1, T, 1)
+        dQ = [float(x) for x in self.diffstate(q1, q0)]
+        iT = 1.0 / T
+        acc = [(dq1[i] - dq0[i]) * iT for i in range(n)]
+        nsteps, largest, total = 0, -1, 0
+        for i in range(n):
+            travel = abs(dQ[i])
+            if abs(acc[i]) > eps_lin:
+                tin = -dq0[i] / acc[i]
+                if 0 <= tin < T:
+                    pin = 0.5 * dq0[i] * tin
+                    travel = abs(pin) + abs(dQ[i] - pin)
+            st = int(travel / res[i] + 0.99) if res[i] != 0 else int(travel * 100)
+            total += st
+            if st > nsteps:
+                nsteps, largest = st, i
+        if total == 0 and start > 0:
+            return pack()
+        if start == 0:
+            push(q0, 0.0, 1)
+            start = 1
+        if nsteps == 0:
+            return pack()
+        aL, vL, largest_step = acc[largest], dq0[largest], dQ[largest]
+        t_infl, f_infl = T, dQ[largest]
+        travel = f_infl
+        if abs(aL) > eps_lin:
+            tin = -vL / aL
+            if 0 <= tin < T:
+                t_infl = tin
+                f_infl = 0.5 * vL * t_infl
+                travel = abs(f_infl) + abs(dQ[largest] - f_infl)
+                fdelta = travel / nsteps
+                if f_infl < 0 or (abs(f_infl) <= eps_lin and dQ[largest] > 0):
+                    fdelta = -fdelta
+            else:
+                fdelta = travel / float(nsteps)
+        else:
+            fdelta = travel / float(nsteps)
+        cur, vel = list(q0), list(dq0)
+        lower, upper = [float(x) for x in self.lower], [float(x) for x in self.upper]
+        timestep = fstep = prevtime = fbest = 0.0
+        istep = repeating = 0
+        compute_new, pending = True, False
+        while istep < nsteps and prevtime < T:
+            if pending:
+                push(cur, timestep, 1)
+                pending = False
+            tmin = prevtime
+            if compute_new:
+                if prevtime >= t_infl:
+                    fbest = fstep - fdelta
+                elif (fdelta > 0 and fstep + fdelta > f_infl) or (fdelta < 0 and fstep + fdelta < f_infl):
+                    fbest = f_infl - (fstep + fdelta - f_infl)
+                    tmin = t_infl - 1e-7
+                else:
+                    fbest = fstep + fdelta
+            if abs(aL) <= eps_lin:
+                if not abs(vL) > 1e-15:
+                    return None
+                timestep = fbest / vL
+            else:
+                fnew, found = fbest, False
+                roots = _solvequad(aL * 0.5, vL, -fnew)
+                if len(roots) == 0 and abs(fnew - largest_step) < 1e-7:
+                    timestep, found = T, True
+                if not found:
+                    for r in roots:
+                        if r > tmin and (not found or timestep > r):
+                            timestep, found = r, True
+                    if not found and tmin < t_infl:
+                        fnew = fstep
+                        for r in _solvequad(aL * 0.5, vL, -fnew):
+                            if r > tmin and (not found or timestep > r):
+                                timestep, fbest, found = r, fnew, True
+                if not found:
+                    return None
+            prev = list(cur)
+            dqscale = 1.0
+            for i in range(n):
+                dQ[i] = q0[i] + timestep * (dq0[i] + timestep * 0.5 * acc[i]) - cur[i]
+                if abs(dQ[i]) > res[i] * 1.01:
+                    tscaled, fs = 0.0, False
+                    for r in _solvequad(acc[i] * 0.5, dq0[i], q0[i] - cur[i] - res[i]):
+                        if tmin <= r <= timestep:
+                            if not fs or r < tscaled:
+                                tscaled = r
+                            fs = True
+                    sc = (tscaled - prevtime) / (timestep - prevtime) if (fs and timestep > prevtime) else abs(res[i] / dQ[i])
+                    if sc < dqscale:
+                        dqscale = sc
+            if dqscale < 1:
+                repeating += 1
+                if dqscale <= 0.01 or repeating > nsteps * 2:
+                    return None
+                timestep = prevtime + (timestep - prevtime) * dqscale
+                for i in range(n):
+                    dQ[i] = q0[i] + timestep * (dq0[i] + timestep * 0.5 * acc[i]) - cur[i]
+                    vel[i] = dq0[i] + timestep * acc[i]
+            else:
+                for i in range(n):
+                    vel[i] = dq0[i] + timestep * acc[i]
+                repeating = 0
+                if timestep > T + 1e-7:
+                    if istep + 1 >= nsteps:
+                        break
+                    return None
+                elif timestep > T:
+                    timestep = T
+            for i in range(n):                                              # AddStatesWithLimitCheck
+                cur[i] = min(max(cur[i] + dQ[i], lower[i]), upper[i])
+            pending = True
+            moved, npost = False, 1
+            for i in range(n):
+                f = abs(cur[i] - prev[i])
+                if f > res[i] * 1.01:
+                    npost = max(npost, int(f / res[i] + 0.9999))
+                if f > 0.0001:
+                    moved = True
+            if npost > 1:
+                inp = 1 / float(npost)
+                step = [(cur[i] - prev[i]) * inp for i in range(n)]
+                for _ in range(npost - 1):
+                    for i in range(n):
+                        prev[i] += step[i]
+                    push(prev, float("nan"), 0)
+            if (not moved) or (istep + 1 < nsteps and repeating > 2) or dqscale >= 1:
+                fstep, compute_new = fbest, True
+                istep += 1
+            else:
+                compute_new = False
+            prevtime = timestep
+        if abs(fstep - largest_step) > abs(fdelta):
+            return None
+        npost = 1
+        for i in range(n):
+            f = abs(q1[i] - cur[i])
+            if f > res[i] * 1.01:
+                npost = max(npost, int(f / res[i] + 0.9999))
+        if npost > 1:
+            inp = 1 / float(npost)
+            step = [(q1[i] - cur[i]) * inp for i in range(n)]
+            prev = list(cur)
+            for _ in range(npost - 1):
+                for i in range(n):
+                    prev[i] += step[i]
+                push(prev, float("nan"), 2)
+        if pending and self._metric(cur, q1) > 1e-7:
+            push(cur, timestep, 1)
+            if check_end:
+                filled[0] = 3                                               # q1 was checked but the walk stopped short of it (:3280)
+        return pack()
+
+    def _metric(self, a, b):
+        """params->_distmetricfn (SimpleDistanceMetric, planningutils.cpp:4714-4723) with the robot's DOF weights."""
+        d = self.diffstate(a, b)
+        s = 0.0
+        for i in range(len(d)):
+            s += float(self.weights[i]) ** 2 * float(d[i]) * float(d[i])
+        return math.sqrt(s)
+
+    def CheckRamp(self, q0, q1, dq0, dq1, timeelapsed, interval=IT_Closed,
+                  options=0xffff | CFO_CheckWithPerturbation | CFO_FillCheckedConfiguration, filterreturn=None):
+        """Check(q0, q1, dq0, dq1, timeelapsed, ...) with valid velocities: every sample of the ramp in ONE CheckCollisionBatch."""
+        from .checker import BATCH_ENV, BATCH_SELF
+        opts = options & self.filtermask
+        flags = (BATCH_ENV if opts & CFO_CheckEnvCollisions else 0) | (BATCH_SELF if opts & CFO_CheckSelfCollisions else 0)
+        r = self.ramp_samples(q0, q1, dq0, dq1, timeelapsed, interval)
+        if r is None:
+            if filterreturn is not None:
+                filterreturn.Clear()
+                filterreturn._returncode = CFO_StateSettingError
+            return CFO_StateSettingError
+        s, t, filled = r
+        mult = 3 if (opts & CFO_CheckWithPerturbation) and self.perturbation > 0 else 1
+        codes = np.zeros(len(s), dtype=np.int64)
+        if len(s):
+            allq = self._perturbed(s) if mult == 3 else s
+            v = self.checker.CheckCollisionBatch(self.robot, allq, flags=flags, active=self.active)["verdict"].reshape(len(s), mult)
+            for i in range(len(s)):
+                for c in range(mult):
+                    code = self._code(int(v[i, c]))
+                    if code:
+                        codes[i] = code
+                        break
+        return self._finish(s, t, codes, options, filterreturn, filled=filled, end_first=(interval in (IT_OpenStart, IT_Closed)))
+
     def _perturbed(self, samples):
         """CFO_CheckWithPerturbation (:2344-2366): every state is also checked at +/- perturbation*resolution, clamped."""
         up = np.minimum(np.maximum(samples + self.perturbation * self.resolution, self.lower), self.upper)
@@ -125,7 +354,7 @@ class DynamicsCollisionConstraint(object):
     def _code(v):
         return CFO_CheckEnvCollisions if (v & 1) else (CFO_CheckSelfCollisions if (v & 2) else 0)
 
-    def _finish(self, samples, times, codes, options, filterreturn):
+    def _finish(self, samples, times, codes, options, filterreturn, filled=None, end_first=None):
         """First failing sample in reference order -> return code + ConstraintFilterReturn."""
         bad = np.nonzero(codes)[0]
         first = int(bad[0]) if len(bad) else -1
@@ -139,8 +368,11 @@ class DynamicsCollisionConstraint(object):
                 upto = len(samples) if first < 0 else first + 1
                 order = list(range(upto))
                 # time order: the end sample (checked first) is reported last when the whole edge is free (:3613-3624)
-                if first < 0 and len(order) and times[0] == 1.0 and len(order) > 1:
+                lead = (times[0] == 1.0) if end_first is None else end_first
+                if first < 0 and len(order) and lead and len(order) > 1:
                     order = order[1:] + [0]
+                if filled is not None:
+                    order = [i for i in order if filled[i] == 1]
                 filterreturn._configurations = [samples[i].tolist() for i in order]
                 filterreturn._configurationtimes = [float(times[i]) for i in order]
         return int(codes[first]) if first >= 0 else 0
@@ -411,7 +643,7 @@ class cc_plan_result(ctypes.Structure):
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
-                   "cc_planner_edge_samples", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
 def _planner_lib():
@@ -425,6 +657,7 @@ def _planner_lib():
     lib.cc_planner_set_query.argtypes = [vp, vp]
     lib.cc_planner_set_checker.argtypes = [vp, vp, vp]
     lib.cc_planner_edge_samples.argtypes = [vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_planner_ramp_samples.argtypes = [vp, vp, vp, vp, vp, ctypes.c_double, ci, vp, vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
@@ -491,6 +724,19 @@ class BirrtPlanner(object):
         self._ck(self.lib.cc_planner_edge_samples(self.handle, q0.ctypes.data, q1.ctypes.data, interval, out.ctypes.data,
                                                   cnt.value, ctypes.byref(cnt)))
         return out[:cnt.value]
+
+    def RampSamples(self, q0, q1, dq0, dq1, timeelapsed, interval=IT_Closed):
+        """(samples, times, filled) of cc_planner_ramp_samples, or None for CFO_StateSettingError."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (q0, q1, dq0, dq1)]
+        cnt = ctypes.c_int(0)
+        args = [self.handle] + [x.ctypes.data for x in a] + [float(timeelapsed), interval]
+        self._ck(self.lib.cc_planner_ramp_samples(*(args + [None, None, None, 0, ctypes.byref(cnt)])))
+        if cnt.value < 0:
+            return None
+        m = max(cnt.value, 1)
+        out, t, f = np.zeros((m, self.ndof)), np.zeros(m), np.zeros(m, dtype=np.uint8)
+        self._ck(self.lib.cc_planner_ramp_samples(*(args + [out.ctypes.data, t.ctypes.data, f.ctypes.data, cnt.value, ctypes.byref(cnt)])))
+        return out[:cnt.value], t[:cnt.value], f[:cnt.value].astype(np.int64)
 
     def PlanBatch(self, starts, goals, seeds=None):
         """Returns a list of dicts (status, iterations, path [w, ndof], path_raw, lengths, config counts) + totals."""
