@@ -598,15 +598,25 @@ class CudaCollisionChecker(object):
         if isinstance(a, KinBody) and b is None:
             bq = self.bind(a)
             T = flatten.transforms8(a.GetQueryLinkTransformations())[None]
-            want_all = report is not None
+            # collision callbacks may veto a colliding pair (collisionPQP.h:569-617): then every colliding pair is needed
+            use_cb = not (self._options & CO_IgnoreCallbacks) and self.env is not None and self.env.HasRegisteredCollisionCallbacks()
+            want_all = report is not None or use_cb
             verdict, fe, _, mask = bq.check_poses(T, BATCH_ENV | (BATCH_ALL_PAIRS if want_all else 0), want_mask=want_all)
             hit = bool(verdict[0] & 1)
-            if hit and report is not None:
+            vetoed = set()
+            if hit and want_all:
+                found = []
                 for p in range(bq.info.npairs_env):
                     if (mask[0, p >> 5] >> (p & 31)) & 1:
                         l1, ob, l2, _ = bq.pairs[p]
-                        report.AddLinkCollision(bq.link_of(l1), self._bodies[ob].links[l2])
-                report.minDistance = 0
+                        found.append((bq.link_of(l1), self._bodies[ob].links[l2]))
+                kept = self.env.filter_collisions_through_callbacks(self._options, found) if use_cb else found
+                vetoed = set((id(a_), id(b_)) for a_, b_ in found) - set((id(a_), id(b_)) for a_, b_ in kept)
+                hit = len(kept) > 0
+                if hit and report is not None:
+                    for l1, l2 in kept:
+                        report.AddLinkCollision(l1, l2)
+                    report.minDistance = 0
             if hit and report is not None and (self._options & CO_Contacts):
                 # one CONTACT per intersecting triangle pair that TriTriCollision accepts (collisionPQP.h:591-603), depth 0
                 pidx, _, has, pos, norm, _ = bq.contacts(T, BATCH_ENV)
@@ -614,6 +624,8 @@ class CudaCollisionChecker(object):
                     if ok:
                         l1, ob, l2, _ = bq.pairs[p]
                         key = (bq.link_of(l1), self._bodies[ob].links[l2])
+                        if (id(key[0]), id(key[1])) in vetoed:
+                            continue
                         report.contacts_by_pair.setdefault(key, []).append((x.copy(), nrm.copy(), 0.0))
             if report is not None and (self._options & CO_Distance) and not hit:
                 self._fill_distance(bq, a, BATCH_ENV, report)
@@ -654,12 +666,18 @@ class CudaCollisionChecker(object):
             T = flatten.transforms8(body.GetLinkTransformations())[None]
             verdict, _, _, mask = q.check_poses(T, BATCH_ENV | BATCH_SELF | BATCH_ALL_PAIRS, want_mask=True)
             hit = bool(verdict[0])
-            if hit and report is not None:
+            if hit:
+                found = []
                 for p in range(q.npairs):
                     if (mask[0, p >> 5] >> (p & 31)) & 1:
                         l1, ob, l2, _ = q.pairs[p]
-                        report.AddLinkCollision(body.links[l1], self._bodies[ob].links[l2])
-                report.minDistance = 0
+                        found.append((body.links[l1], self._bodies[ob].links[l2]))
+                kept = self.env.filter_collisions_through_callbacks(self._options, found) if self.env is not None else found
+                hit = len(kept) > 0
+                if hit and report is not None:
+                    for l1, l2 in kept:
+                        report.AddLinkCollision(l1, l2)
+                    report.minDistance = 0
         finally:
             q.close()
         return hit

@@ -58,8 +58,27 @@ class CollisionPairInfo(object):
         return (self.link2.body.name, self.link2.name, '')
 
 
+class CollisionAction(object):
+    """include/openrave/collisionchecker.h:40-44."""
+    DefaultAction = 0
+    Ignore = 1
+
+
+class _CallbackHandle(object):
+    """UserDataPtr returned by RegisterCollisionCallback: Close() (or losing the last reference) unregisters."""
+
+    def __init__(self, env, fn):
+        self._env, self._fn = env, fn
+
+    def Close(self):
+        if self._env is not None and self in self._env._collision_callbacks:
+            self._env._collision_callbacks.remove(self)
+        self._env = None
+
+
 class Environment(object):
     def __init__(self, data_dirs=None):
+        self._collision_callbacks = []
         self.bodies = []
         self.checker = None
         self._next_id = 1
@@ -143,6 +162,36 @@ class Environment(object):
         if b is None:
             return cc.CheckCollision(a, report=report)
         return cc.CheckCollision(a, b, report=report)
+
+    # ---- collision callbacks (environment-core.h RegisterCollisionCallback / GetRegisteredCollisionCallbacks)
+    def RegisterCollisionCallback(self, fn):
+        h = _CallbackHandle(self, fn)
+        self._collision_callbacks.append(h)
+        return h
+
+    def HasRegisteredCollisionCallbacks(self):
+        return len(self._collision_callbacks) > 0
+
+    def GetRegisteredCollisionCallbacks(self):
+        return [h._fn for h in self._collision_callbacks]
+
+    def filter_collisions_through_callbacks(self, options, pairs):
+        """What a checker does with a colliding link pair when callbacks are registered and CO_IgnoreCallbacks is off
+        (plugins/pqprave/collisionPQP.h:569-617, plugins/fclrave/fclcollision.cpp:1002-1011): every callback sees a report
+        holding that one pair; any answer other than DefaultAction drops the pair as if the links did not collide.
+        `pairs` is an iterable of (link1, link2) in the checker's order; returns the pairs that stand."""
+        CO_IgnoreCallbacks = 0x100                                  # collisionchecker.h CollisionOptions
+        if (options & CO_IgnoreCallbacks) or not self._collision_callbacks:
+            return list(pairs)
+        kept = []
+        for l1, l2 in pairs:
+            rep = CollisionReport()
+            rep.Reset(options)
+            rep.AddLinkCollision(l1, l2)
+            rep.minDistance = 0
+            if all(fn(rep, False) == CollisionAction.DefaultAction for fn in self.GetRegisteredCollisionCallbacks()):
+                kept.append((l1, l2))
+        return kept
 
     def _body_changed(self, body, kind="structure"):
         """kind 'pose': only link transforms / DOF values moved; 'structure': enable flags, grabs, active DOFs, geometry."""

@@ -364,6 +364,33 @@ class Manipulator(object):
     def GetTransform(self):
         return rm.t_mul(self.effector.t, self.t_local)
 
+    def CheckEndEffectorCollision(self, report=None):
+        """RobotBase::Manipulator::CheckEndEffectorCollision(report) (robotmanipulator.cpp:915-960): every link that all arm
+        joints affect is checked against the environment; with CO_AllLinkCollisions the report aggregates over the links."""
+        robot = self.robot
+        env = robot.env
+        cc = env.GetCollisionChecker()
+        all_links = bool(cc.GetCollisionOptions() & 0x20)                    # CO_AllLinkCollisions
+        arm = self.GetArmIndices()
+        found, hit = [], False
+        sub = type(report)() if report is not None else None
+        for link in robot.links:
+            if not all(robot.DoesAffect(robot.joints[d].jointindex, link.index) for d in arm):
+                continue
+            if env.CheckCollision(link, report=sub):
+                hit = True
+                if sub is not None:
+                    found += list(sub.vLinkColliding)
+                if not all_links:
+                    break
+        if report is not None:
+            report.Reset(cc.GetCollisionOptions())
+            for a, b in found:
+                report.AddLinkCollision(a, b)
+            if hit:
+                report.minDistance = 0
+        return hit
+
 
 # ----------------------------------------------------------------------------- body
 class KinBody(object):

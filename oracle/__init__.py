@@ -326,15 +326,20 @@ class OracleChecker(object):
         if report is not None:
             report.Reset(self._options)
         if isinstance(a, KinBody) and b is None:
-            res = self.check_batch(a, None, flags=BATCH_ENV, report=report is not None,
+            use_cb = not (self._options & 0x100) and self.env is not None and self.env.HasRegisteredCollisionCallbacks()
+            res = self.check_batch(a, None, flags=BATCH_ENV, report=(report is not None or use_cb),
                                    poses=flatten.transforms8(a.GetQueryLinkTransformations())[None])
             hit = bool(res["verdict"][0] & 1)
-            if report is not None and hit:
+            if (report is not None or use_cb) and hit:
                 bodies = self._bodies_by_id()
                 qlinks = list(a.links) + [l for g in a.grabbed for l in g.body.links]
-                for _, l1, ob, l2 in res["env_pairs"]:
-                    report.AddLinkCollision(qlinks[l1], bodies[ob].links[l2])
-                report.minDistance = 0
+                found = [(qlinks[l1], bodies[ob].links[l2]) for _, l1, ob, l2 in res["env_pairs"]]
+                kept = self.env.filter_collisions_through_callbacks(self._options, found) if use_cb else found   # collisionPQP.h:606-617
+                hit = len(kept) > 0
+                if report is not None and hit:
+                    for l1, l2 in kept:
+                        report.AddLinkCollision(l1, l2)
+                    report.minDistance = 0
             return hit
         if isinstance(a, Link) and isinstance(b, Link):
             if a.body is b.body:

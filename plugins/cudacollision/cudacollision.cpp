@@ -737,26 +737,54 @@ private:
         cc_query_info info;
         cc_query_get_info(query, &info);
         std::vector<double> T8 = _QueryPoses(query);       // grabbed links included: the bound query covers them
-        std::vector<uint32_t> mask(!report ? 0 : info.mask_words);
+        const bool wantall = !!report || _UseCallbacks();       // a callback may veto pairs: then every colliding pair is needed
+        std::vector<uint32_t> mask(!wantall ? 0 : info.mask_words);
         uint32_t verdict = 0;
-        _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | (!report ? 0 : CC_BATCH_ALL_PAIRS), &verdict, NULL, NULL, !report ? NULL : mask.data()));
-        if ((verdict & CC_VERDICT_ENV) && !!report) _FillReport(pbody, query, mask, info.npairs_env, report);
+        _Check(cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | (!wantall ? 0 : CC_BATCH_ALL_PAIRS), &verdict, NULL, NULL, !wantall ? NULL : mask.data()));
+        if ((verdict & CC_VERDICT_ENV) && wantall && _FillReport(pbody, query, mask, info.npairs_env, report) == 0) verdict &= ~(uint32_t)CC_VERDICT_ENV;
         if ((verdict & CC_VERDICT_ENV) && !!report && (_options & CO_Contacts)) _FillContacts(query, T8, CC_BATCH_ENV, report);
         if (!(verdict & CC_VERDICT_ENV) && !!report && (_options & CO_Distance)) _FillDistance(query, T8, CC_BATCH_ENV, report);
         if (!!report && (_options & CO_UseTolerance)) _FillTolerance(query, T8, info, report);
         return (verdict & CC_VERDICT_ENV) != 0;
     }
 
-    void _FillReport(KinBodyConstPtr pbody, cc_query* query, const std::vector<uint32_t>& mask, int npairs, CollisionReportPtr report)
+    /// collision callbacks are consulted unless CO_IgnoreCallbacks is set (collisionPQP.h:569)
+    bool _UseCallbacks() const { return !(_options & CO_IgnoreCallbacks) && GetEnv()->HasRegisteredCollisionCallbacks(); }
+
+    /// a colliding link pair stands unless a registered callback answers anything but CA_DefaultAction for a report that holds
+    /// just this pair (collisionPQP.h:606-617; fclcollision.cpp:1002-1011)
+    bool _PairStands(const KinBody::Link& link1, const KinBody::Link& link2)
+    {
+        if (!_UseCallbacks()) return true;
+        CollisionReportPtr preport(new CollisionReport());
+        preport->Reset(_options);
+        preport->AddLinkCollision(link1, link2);
+        preport->minDistance = 0;
+        std::list<EnvironmentBase::CollisionCallbackFn> listcallbacks;
+        GetEnv()->GetRegisteredCollisionCallbacks(listcallbacks);
+        FOREACHC(itfn, listcallbacks) {
+            if ((*itfn)(preport, false) != CA_DefaultAction) return false;
+        }
+        return true;
+    }
+
+    /// every colliding pair of the mask that the callbacks let stand goes into the report (may be null); returns how many stood
+    int _FillReport(KinBodyConstPtr pbody, cc_query* query, const std::vector<uint32_t>& mask, int npairs, CollisionReportPtr report)
     {
         std::vector<int32_t> quads = _Quads(query);
+        int nstanding = 0;
         for (int p = 0; p < npairs; ++p) {
             if (!((mask[p >> 5] >> (p & 31)) & 1u)) continue;
             KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
             if (!pother) continue;
-            report->AddLinkCollision(*_QueryLink(query, quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));   // collisionPQP.h:586
+            KinBody::LinkConstPtr plink1 = _QueryLink(query, quads[4 * p]);
+            KinBody::LinkConstPtr plink2 = pother->GetLinks().at(quads[4 * p + 2]);
+            if (!_PairStands(*plink1, *plink2)) continue;
+            ++nstanding;
+            if (!!report) report->AddLinkCollision(*plink1, *plink2);                                                 // collisionPQP.h:586
         }
-        report->minDistance = 0;                                                                                       // :587
+        if (!!report && nstanding > 0) report->minDistance = 0;                                                       // :587
+        return nstanding;
     }
 
     /// (link, other body, other link) triples of pbody against the environment in pqprave's order (collisionPQP.h:448-487)
@@ -804,16 +832,14 @@ private:
         std::vector<uint32_t> mask(info.mask_words);
         uint32_t verdict = 0; int32_t fe = -1, fs = -1;
         int rc = cc_check_poses(query, T8.data(), 1, CC_BATCH_ENV | CC_BATCH_SELF | (firstonly ? 0 : CC_BATCH_ALL_PAIRS), &verdict, &fe, &fs, firstonly ? NULL : mask.data());
-        if (rc == CC_OK && verdict && !!report) {
-            if (firstonly) {
-                std::vector<int32_t> quads = _Quads(query);
-                const int p = fs >= 0 ? fs : fe;
-                KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
-                if (!!pother) report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));
-                report->minDistance = 0;
-            } else {
-                _FillReport(pbody, query, mask, info.npairs_env + info.npairs_self, report);
-            }
+        if (rc == CC_OK && verdict && firstonly) {
+            std::vector<int32_t> quads = _Quads(query);
+            const int p = fs >= 0 ? fs : fe;
+            KinBodyPtr pother = _byid[quads[4 * p + 1]].lock();
+            if (!!pother && !!report) report->AddLinkCollision(*pbody->GetLinks().at(quads[4 * p]), *pother->GetLinks().at(quads[4 * p + 2]));
+            if (!!report) report->minDistance = 0;
+        } else if (rc == CC_OK && verdict && (!!report || _UseCallbacks())) {
+            if (_FillReport(pbody, query, mask, info.npairs_env + info.npairs_self, report) == 0) verdict = 0;        // every pair vetoed
         }
         cc_query_destroy(query);
         _Check(rc);

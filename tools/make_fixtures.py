@@ -47,6 +47,23 @@ def main():
             scene, len(env.GetBodies()), sum(l.idx.shape[0] for b in env.GetBodies() for l in b.links), path,
             os.path.getsize(path) / 1024.0))
 
+    # the robot test/test_collision.py:94-181 builds from an XML string (segway box model joined to the WAM by a dummy joint):
+    # the string is read from the reference's test file here, parsed by our loader, and only the flattened result is stored
+    src = open(os.path.join(REF, "test", "test_collision.py")).read()
+    a = src.index('testrobot_xml="""') + len('testrobot_xml="""')
+    xml = src[a:src.index('"""', a)]
+    f = tempfile.NamedTemporaryFile("w", suffix=".robot.xml", delete=False)
+    f.write(xml)
+    f.close()
+    env = Environment(data_dirs=[os.path.join(REF, "src"), tmp])
+    robot = env.ReadRobotURI(f.name)
+    os.unlink(f.name)
+    env.Add(robot)
+    path = os.path.join(OUT, "joinxml_segwaywam.npz")
+    save_environment(env, path)
+    print("joinxml_segwaywam: %d links, %d tris -> %s (%.1f KB)" % (
+        len(robot.links), sum(l.idx.shape[0] for l in robot.links), path, os.path.getsize(path) / 1024.0))
+
 
 if __name__ == "__main__":
     main()
