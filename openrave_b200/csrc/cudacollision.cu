@@ -178,7 +178,9 @@ struct Builder {
             nodes[node].left = ~order[first];
             return;
         }
-        // split the centroid bounds at the midpoint of the longest axis; fall back to the median
+        // split: binned surface-area heuristic over the three axes (the verdict does not depend on the tree's shape, only the
+        // number of box tests does); CC_TUNE_BVH=mid keeps the plain midpoint of the longest centroid axis; the median is the
+        // fallback of both
         double cmn[3] = {1e300, 1e300, 1e300}, cmx[3] = {-1e300, -1e300, -1e300};
         for (int i = first; i < first + count; ++i)
             for (int k = 0; k < 3; ++k) { double c = cen[3 * (size_t)order[i] + k]; if (c < cmn[k]) cmn[k] = c; if (c > cmx[k]) cmx[k] = c; }
@@ -186,6 +188,53 @@ struct Builder {
         if (cmx[1] - cmn[1] > cmx[ax] - cmn[ax]) ax = 1;
         if (cmx[2] - cmn[2] > cmx[ax] - cmn[ax]) ax = 2;
         double mid = 0.5 * (cmn[ax] + cmx[ax]);
+        static const bool use_sah = !(getenv("CC_TUNE_BVH") && !strcmp(getenv("CC_TUNE_BVH"), "mid"));
+        if (use_sah && count > 2) {
+            constexpr int NB = 16;
+            double best_cost = 1e300;
+            for (int a = 0; a < 3; ++a) {
+                const double w = cmx[a] - cmn[a];
+                if (!(w > 0)) continue;
+                double bmn[NB][3], bmx[NB][3];
+                int bcnt[NB];
+                for (int j = 0; j < NB; ++j) { bcnt[j] = 0; for (int k = 0; k < 3; ++k) { bmn[j][k] = 1e300; bmx[j][k] = -1e300; } }
+                const double sc = NB / w;
+                for (int i = first; i < first + count; ++i) {
+                    const int t = order[i];
+                    int j = (int)((cen[3 * (size_t)t + a] - cmn[a]) * sc);
+                    if (j >= NB) j = NB - 1;
+                    bcnt[j]++;
+                    for (int v = 0; v < 3; ++v) {
+                        const double* p = &L.verts[3 * (size_t)L.tris[3 * t + v]];
+                        for (int k = 0; k < 3; ++k) { if (p[k] < bmn[j][k]) bmn[j][k] = p[k]; if (p[k] > bmx[j][k]) bmx[j][k] = p[k]; }
+                    }
+                }
+                // suffix areas, then a prefix sweep
+                double rarea[NB];
+                int rcnt[NB];
+                {
+                    double amn[3] = {1e300, 1e300, 1e300}, amx[3] = {-1e300, -1e300, -1e300};
+                    int cacc = 0;
+                    for (int j = NB - 1; j >= 1; --j) {
+                        cacc += bcnt[j];
+                        for (int k = 0; k < 3; ++k) { amn[k] = std::min(amn[k], bmn[j][k]); amx[k] = std::max(amx[k], bmx[j][k]); }
+                        const double dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
+                        rarea[j] = cacc ? dx * dy + dy * dz + dz * dx : 0.0;
+                        rcnt[j] = cacc;
+                    }
+                }
+                double amn[3] = {1e300, 1e300, 1e300}, amx[3] = {-1e300, -1e300, -1e300};
+                int cacc = 0;
+                for (int j = 0; j + 1 < NB; ++j) {
+                    cacc += bcnt[j];
+                    for (int k = 0; k < 3; ++k) { amn[k] = std::min(amn[k], bmn[j][k]); amx[k] = std::max(amx[k], bmx[j][k]); }
+                    if (cacc == 0 || rcnt[j + 1] == 0) continue;
+                    const double dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
+                    const double cost = (dx * dy + dy * dz + dz * dx) * cacc + rarea[j + 1] * rcnt[j + 1];
+                    if (cost < best_cost) { best_cost = cost; ax = a; mid = cmn[a] + (j + 1) * (w / NB); }
+                }
+            }
+        }
         int* b = &order[first];
         int nleft = (int)(std::partition(b, b + count, [&](int t) { return cen[3 * (size_t)t + ax] < mid; }) - b);
         if (nleft == 0 || nleft == count) {
