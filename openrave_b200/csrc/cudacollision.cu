@@ -166,7 +166,13 @@ struct Builder {
             if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
             n.c[k] = cf; n.e[k] = ef;
         }
-        n.size2 = n.e[0] * n.e[0] + n.e[1] * n.e[1] + n.e[2] * n.e[2];
+        // what "the larger box" means when the descent picks the node to split: the volume (default; +1.3 .. 2.3 % over |e|^2 on the
+        // three robot workloads, profiles/r01C_ab_bvh_knobs.log); CC_TUNE_BVH_SIZE = 0 |e|^2, 1 area, 3 longest extent
+        static const int size_kind = getenv("CC_TUNE_BVH_SIZE") ? atoi(getenv("CC_TUNE_BVH_SIZE")) : 2;
+        n.size2 = size_kind == 1 ? n.e[0] * n.e[1] + n.e[1] * n.e[2] + n.e[2] * n.e[0]
+                : size_kind == 2 ? n.e[0] * n.e[1] * n.e[2]
+                : size_kind == 3 ? std::max(n.e[0], std::max(n.e[1], n.e[2]))
+                : n.e[0] * n.e[0] + n.e[1] * n.e[1] + n.e[2] * n.e[2];
     }
 
     void build(int node, int first, int count)
@@ -190,13 +196,23 @@ struct Builder {
         double mid = 0.5 * (cmn[ax] + cmx[ax]);
         static const bool use_sah = !(getenv("CC_TUNE_BVH") && !strcmp(getenv("CC_TUNE_BVH"), "mid"));
         if (use_sah && count > 2) {
-            constexpr int NB = 16;
+            constexpr int NBMAX = 64;
+            static const int NB = getenv("CC_TUNE_BVH_BINS") ? std::min(NBMAX, std::max(2, atoi(getenv("CC_TUNE_BVH_BINS")))) : 16;
+            static const int cost_kind = getenv("CC_TUNE_BVH_COST") ? atoi(getenv("CC_TUNE_BVH_COST")) : 0;    // 0 area, 1 volume, 2 |e|^2, 3 sum of extents
+            auto measure = [](double dx, double dy, double dz) {
+                switch (cost_kind) {
+                    case 1: return dx * dy * dz;
+                    case 2: return dx * dx + dy * dy + dz * dz;
+                    case 3: return dx + dy + dz;
+                    default: return dx * dy + dy * dz + dz * dx;
+                }
+            };
             double best_cost = 1e300;
             for (int a = 0; a < 3; ++a) {
                 const double w = cmx[a] - cmn[a];
                 if (!(w > 0)) continue;
-                double bmn[NB][3], bmx[NB][3];
-                int bcnt[NB];
+                double bmn[NBMAX][3], bmx[NBMAX][3];
+                int bcnt[NBMAX];
                 for (int j = 0; j < NB; ++j) { bcnt[j] = 0; for (int k = 0; k < 3; ++k) { bmn[j][k] = 1e300; bmx[j][k] = -1e300; } }
                 const double sc = NB / w;
                 for (int i = first; i < first + count; ++i) {
@@ -210,8 +226,8 @@ struct Builder {
                     }
                 }
                 // suffix areas, then a prefix sweep
-                double rarea[NB];
-                int rcnt[NB];
+                double rarea[NBMAX];
+                int rcnt[NBMAX];
                 {
                     double amn[3] = {1e300, 1e300, 1e300}, amx[3] = {-1e300, -1e300, -1e300};
                     int cacc = 0;
@@ -219,7 +235,7 @@ struct Builder {
                         cacc += bcnt[j];
                         for (int k = 0; k < 3; ++k) { amn[k] = std::min(amn[k], bmn[j][k]); amx[k] = std::max(amx[k], bmx[j][k]); }
                         const double dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
-                        rarea[j] = cacc ? dx * dy + dy * dz + dz * dx : 0.0;
+                        rarea[j] = cacc ? measure(dx, dy, dz) : 0.0;
                         rcnt[j] = cacc;
                     }
                 }
@@ -230,7 +246,7 @@ struct Builder {
                     for (int k = 0; k < 3; ++k) { amn[k] = std::min(amn[k], bmn[j][k]); amx[k] = std::max(amx[k], bmx[j][k]); }
                     if (cacc == 0 || rcnt[j + 1] == 0) continue;
                     const double dx = amx[0] - amn[0], dy = amx[1] - amn[1], dz = amx[2] - amn[2];
-                    const double cost = (dx * dy + dy * dz + dz * dx) * cacc + rarea[j + 1] * rcnt[j + 1];
+                    const double cost = measure(dx, dy, dz) * cacc + rarea[j + 1] * rcnt[j + 1];
                     if (cost < best_cost) { best_cost = cost; ax = a; mid = cmn[a] + (j + 1) * (w / NB); }
                 }
             }
