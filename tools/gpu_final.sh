@@ -2,7 +2,7 @@
 # Closing visit at HEAD: GPU parity tests, smoke, every bench workload (+ reference arms), ncu launch list and full captures.
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r01s}
+TAG=${1:-r01D}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.csv 2>&1
 nproc > gpurun_out/nproc_$TAG.txt; grep -m1 'model name' /proc/cpuinfo >> gpurun_out/nproc_$TAG.txt
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$TAG.log
