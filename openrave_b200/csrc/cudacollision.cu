@@ -263,8 +263,26 @@ struct Builder {
         int l = (int)nodes.size();
         nodes.push_back(HNode()); nodes.push_back(HNode());
         nodes[node].left = l;
-        build(l, first, nleft);
-        build(l + 1, first + nleft, count - nleft);
+        // the descent pops child 0 first: CC_TUNE_BVH_ORDER picks which half that is (0 = as partitioned, 1 = larger volume,
+        // 2 = smaller volume, 3 = more triangles)
+        static const int order_kind = getenv("CC_TUNE_BVH_ORDER") ? atoi(getenv("CC_TUNE_BVH_ORDER")) : 0;
+        bool swap_halves = false;
+        if (order_kind == 3) swap_halves = count - nleft > nleft;
+        else if (order_kind == 1 || order_kind == 2) {
+            double amn[3], amx[3], bmn[3], bmx[3];
+            bounds(first, nleft, amn, amx);
+            bounds(first + nleft, count - nleft, bmn, bmx);
+            const double va = (amx[0] - amn[0] + 2e-5) * (amx[1] - amn[1] + 2e-5) * (amx[2] - amn[2] + 2e-5);
+            const double vb = (bmx[0] - bmn[0] + 2e-5) * (bmx[1] - bmn[1] + 2e-5) * (bmx[2] - bmn[2] + 2e-5);
+            swap_halves = order_kind == 1 ? vb > va : vb < va;
+        }
+        if (swap_halves) {
+            build(l, first + nleft, count - nleft);
+            build(l + 1, first, nleft);
+        } else {
+            build(l, first, nleft);
+            build(l + 1, first + nleft, count - nleft);
+        }
     }
 };
 
