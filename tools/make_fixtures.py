@@ -64,6 +64,22 @@ def main():
     print("joinxml_segwaywam: %d links, %d tris -> %s (%.1f KB)" % (
         len(robot.links), sum(l.idx.shape[0] for l in robot.links), path, os.path.getsize(path) / 1024.0))
 
+    # the scene of test/test_robot.py:625-660 (test_distancechecking): the WAM alone, one mug at the manipulator's transform,
+    # a second mug named 'collision' at (0.5, 0, 0.5)
+    env = Environment(data_dirs=[os.path.join(REF, "src"), tmp])
+    robot = env.ReadRobotURI("robots/barrettwam.robot.xml")
+    env.Add(robot)
+    target = env.ReadKinBodyURI("data/mug1.kinbody.xml")
+    env.Add(target)
+    target.SetTransform(robot.GetActiveManipulator().GetTransform())
+    coltarget = env.ReadKinBodyURI("data/mug1.kinbody.xml")
+    coltarget.name = "collision"
+    env.Add(coltarget)
+    coltarget.SetTransform(((1.0, 0.0, 0.0, 0.0), (0.5, 0.0, 0.5)))
+    path = os.path.join(OUT, "wam_two_mugs.npz")
+    save_environment(env, path)
+    print("wam_two_mugs: %d bodies -> %s (%.1f KB)" % (len(env.GetBodies()), path, os.path.getsize(path) / 1024.0))
+
 
 if __name__ == "__main__":
     main()
