@@ -380,6 +380,24 @@ int cc_planner_ramp_samples(cc_planner* p, const double* q0, const double* q1, c
                             double timeelapsed, int interval, double* out_configs, double* out_times, uint8_t* out_kind,
                             int max_configs, int* out_count);
 enum cc_ramp_sample_kind { CC_RAMP_SUBSTEP = 0, CC_RAMP_REPORTED = 1, CC_RAMP_TAIL_SUBSTEP = 2, CC_RAMP_END_UNREPORTED = 3 };
+/* PlannerParameters::CheckPathAllConstraints (planner.h:373-379) for `nedges` edges in ONE checker call — the entry a caller of
+ * DynamicsCollisionConstraint::Check (planningutils.cpp:2586-3629) switches to.  q0, q1: [nedges][ndof].  dq0, dq1 ([nedges][ndof])
+ * and timeelapsed ([nedges]) may be NULL: positions-only linear edges; an edge with timeelapsed > 0 is sampled as a parabolic
+ * ramp (cc_planner_ramp_samples).  options: CFO_CheckEnvCollisions (1) | CFO_CheckSelfCollisions (2) are required,
+ * CFO_CheckWithPerturbation (0x10000) also checks every sample at +/- perturbation x resolution (planningutils.cpp:2344-2366,
+ * default perturbation 0.1).  Per edge: the reference's return code (0, 1 environment, 2 self, 0x80000000 state setting error),
+ * the index of the failing sample in checking order, ConstraintFilterReturn::_fTimeWhenInvalid, and (invalid_values, may be
+ * NULL, [nedges][ndof]) _invalidvalues. */
+typedef struct cc_edge_result {
+    int32_t return_code;
+    int32_t first_invalid;       /* -1: every sample passed */
+    int32_t nsamples;            /* samples the edge was discretised into (0 after a state setting error) */
+    int32_t perturbed;           /* which state of the failing sample collided: 0 itself, 1 +perturbation, 2 -perturbation */
+    double time_when_invalid;
+} cc_edge_result;
+int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const double* q1, const double* dq0, const double* dq1,
+                           const double* timeelapsed, int interval, int options, double perturbation, cc_edge_result* results,
+                           double* invalid_values);
 /* BiRRT + path shortcutting for nproblems (start, goal) pairs in lockstep.  starts/goals: [nproblems][ndof];
  * seeds[nproblems] = PlannerParameters::_nRandomGeneratorSeed per problem.  results[nproblems] is filled; the paths stay in
  * the planner until the next call and are read with cc_planner_get_path. */

@@ -1200,6 +1200,83 @@ int cc_planner_ramp_samples(cc_planner* p, const double* q0, const double* q1, c
     return CC_OK;
 }
 
+// PlannerParameters::CheckPathAllConstraints for many edges at once (planner.h:373-379 -> DynamicsCollisionConstraint::Check,
+// planningutils.cpp:2586-3629).  Every edge becomes one group; every sample one segment of 1 configuration, or of 3 with
+// CFO_CheckWithPerturbation (the state, then +perturbation x resolution, then -perturbation x resolution, clamped to the
+// limits, planningutils.cpp:2344-2366); the checker reports the first failing segment of each group, which is the sample the
+// serial loop would have returned at.
+int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const double* q1, const double* dq0, const double* dq1,
+                           const double* timeelapsed, int interval, int options, double perturbation, cc_edge_result* results,
+                           double* invalid_values)
+{
+    if (!p || nedges < 0 || (nedges > 0 && (!q0 || !q1 || !results)) || interval < 0 || interval > 3)
+        return fail(CC_ERR_INVALID, "cc_planner_check_edges: bad arguments");
+    if (!p->query && !p->fn) return fail(CC_ERR_STATE, "cc_planner_check_edges: no checker bound (cc_planner_set_query)");
+    if ((options & 3) != 3) return fail(CC_ERR_INVALID, "cc_planner_check_edges: CFO_CheckEnvCollisions | CFO_CheckSelfCollisions are checked together");
+    const bool ramps = dq0 && dq1 && timeelapsed;
+    const bool perturb = (options & 0x00010000) != 0 && perturbation > 0;      // CFO_CheckWithPerturbation (planner.h:37)
+    const int n = p->cs.n, mult = perturb ? 3 : 1;
+    const CSpace& cs = p->cs;
+    std::vector<double> samples, times, q;
+    std::vector<uint8_t> kinds;
+    std::vector<int32_t> group_begin(1, 0), seg_begin(1, 0), sample_begin(1, 0);
+    std::vector<double> all_samples, all_times;
+    for (int e = 0; e < nedges; ++e) {
+        samples.clear(); times.clear(); kinds.clear();
+        const double* a = q0 + (size_t)e * n;
+        const double* b = q1 + (size_t)e * n;
+        int c;
+        if (ramps && timeelapsed[e] > 0)
+            c = edge_samples_quadratic(cs, a, b, dq0 + (size_t)e * n, dq1 + (size_t)e * n, timeelapsed[e], interval, samples, &times, &kinds);
+        else c = edge_samples(cs, a, b, interval, samples, &times);
+        cc_edge_result& r = results[e];
+        std::memset(&r, 0, sizeof(r));
+        r.first_invalid = -1;
+        r.nsamples = c;
+        if (c < 0) {                       // the walk itself failed: CFO_StateSettingError, nothing to check
+            r.return_code = (int32_t)0x80000000u;
+            r.nsamples = 0;
+            c = 0;
+            samples.clear(); times.clear();
+        }
+        for (int i = 0; i < c; ++i) {
+            const double* sq = &samples[(size_t)i * n];
+            q.insert(q.end(), sq, sq + n);
+            if (perturb)
+                for (double f : {perturbation, -perturbation})
+                    for (int k = 0; k < n; ++k) q.push_back(std::min(std::max(sq[k] + f * cs.res[k], cs.lo[k]), cs.hi[k]));
+            seg_begin.push_back((int32_t)(q.size() / n));
+        }
+        group_begin.push_back((int32_t)seg_begin.size() - 1);
+        all_samples.insert(all_samples.end(), samples.begin(), samples.end());
+        all_times.insert(all_times.end(), times.begin(), times.end());
+        sample_begin.push_back((int32_t)all_times.size());
+    }
+    const int nconfigs = (int)(q.size() / n);
+    std::vector<int32_t> ffs(std::max(nedges, 1), -1), fv(std::max(nedges, 1), 0), ffc(std::max(nedges, 1), -1);
+    if (nconfigs > 0) {
+        int rc;
+        if (p->query) rc = gpu_group_check(p, q.data(), nconfigs, n, group_begin.data(), nedges, seg_begin.data(), ffs.data(), fv.data(), ffc.data());
+        else rc = p->fn(p->user, q.data(), nconfigs, n, group_begin.data(), nedges, seg_begin.data(), (int)seg_begin.size() - 1, ffs.data(), fv.data(), ffc.data());
+        if (rc != CC_OK) {
+            if (!p->query) cc_internal_set_error("cc_planner_check_edges: the checker callback failed");
+            return rc;
+        }
+    }
+    for (int e = 0; e < nedges; ++e) {
+        cc_edge_result& r = results[e];
+        if (r.return_code != 0 || ffs[e] < 0) continue;
+        const int i = ffs[e];
+        r.first_invalid = i;
+        r.return_code = (fv[e] & 1) ? 1 : 2;                                   // _CheckState: environment first, then self
+        r.perturbed = perturb ? (ffc[e] - seg_begin[group_begin[e] + i]) : 0;  // 0 the state itself, 1 / 2 its +/- perturbation
+        r.time_when_invalid = all_times[sample_begin[e] + i];
+        if (invalid_values) std::memcpy(invalid_values + (size_t)e * n, &all_samples[((size_t)sample_begin[e] + i) * n], sizeof(double) * n);
+    }
+    (void)mult;
+    return CC_OK;
+}
+
 int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts, const double* goals,
                         const uint32_t* seeds, cc_plan_result* results)
 {

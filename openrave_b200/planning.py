@@ -640,10 +640,15 @@ class cc_plan_result(ctypes.Structure):
                 ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64)]
 
 
+class cc_edge_result(ctypes.Structure):
+    _fields_ = [("return_code", ctypes.c_int32), ("first_invalid", ctypes.c_int32), ("nsamples", ctypes.c_int32),
+                ("perturbed", ctypes.c_int32), ("time_when_invalid", ctypes.c_double)]
+
+
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
-                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
 def _planner_lib():
@@ -658,6 +663,7 @@ def _planner_lib():
     lib.cc_planner_set_checker.argtypes = [vp, vp, vp]
     lib.cc_planner_edge_samples.argtypes = [vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_ramp_samples.argtypes = [vp, vp, vp, vp, vp, ctypes.c_double, ci, vp, vp, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_planner_check_edges.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, ci, ctypes.c_double, vp, vp]
     lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
@@ -737,6 +743,29 @@ class BirrtPlanner(object):
         out, t, f = np.zeros((m, self.ndof)), np.zeros(m), np.zeros(m, dtype=np.uint8)
         self._ck(self.lib.cc_planner_ramp_samples(*(args + [out.ctypes.data, t.ctypes.data, f.ctypes.data, cnt.value, ctypes.byref(cnt)])))
         return out[:cnt.value], t[:cnt.value], f[:cnt.value].astype(np.int64)
+
+    def CheckEdges(self, q0, q1, interval=IT_Closed, options=0xffff, perturbation=0.1, dq0=None, dq1=None, timeelapsed=None):
+        """cc_planner_check_edges: CheckPathAllConstraints for many edges in one checker call.  Returns a list of dicts
+        (return_code, first_invalid, nsamples, perturbed, time_when_invalid, invalid_values)."""
+        q0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(-1, self.ndof)
+        q1 = np.ascontiguousarray(q1, dtype=np.float64).reshape(-1, self.ndof)
+        k = q0.shape[0]
+        ptr = lambda a: None if a is None else a.ctypes.data
+        if dq0 is not None:
+            dq0 = np.ascontiguousarray(dq0, dtype=np.float64).reshape(-1, self.ndof)
+            dq1 = np.ascontiguousarray(dq1, dtype=np.float64).reshape(-1, self.ndof)
+            timeelapsed = np.ascontiguousarray(timeelapsed, dtype=np.float64).reshape(-1)
+        res = (cc_edge_result * max(k, 1))()
+        inv = np.zeros((max(k, 1), self.ndof))
+        self._ck(self.lib.cc_planner_check_edges(self.handle, k, q0.ctypes.data, q1.ctypes.data, ptr(dq0), ptr(dq1), ptr(timeelapsed),
+                                                 interval, options & 0xffffffff, float(perturbation), ctypes.addressof(res), inv.ctypes.data))
+        out = []
+        for i in range(k):
+            d = dict((f, getattr(res[i], f)) for f, _ in cc_edge_result._fields_)
+            d["return_code"] &= 0xffffffff
+            d["invalid_values"] = inv[i].copy() if d["first_invalid"] >= 0 else None
+            out.append(d)
+        return out
 
     def PlanBatch(self, starts, goals, seeds=None):
         """Returns a list of dicts (status, iterations, path [w, ndof], path_raw, lengths, config counts) + totals."""

@@ -95,3 +95,56 @@ def test_gpu_edges_equal_oracle_serial(wam):
     # identical except where the first failing sample sits inside the 1e-4 m contact band
     assert diff <= 2, diff
     assert 0 < sum(1 for g in got if g) < len(got)
+
+
+def test_check_edges_entry_equals_python_check(wam):
+    """cc_planner_check_edges (the C entry a CheckPathAllConstraints caller switches to) against the Python restatement of
+    DynamicsCollisionConstraint::Check over the same checker: return codes, failing sample, _fTimeWhenInvalid, _invalidvalues —
+    linear edges with and without CFO_CheckWithPerturbation, all four intervals, and parabolic ramps."""
+    env, robot, orc = wam
+    act = robot.GetActiveDOFIndices()
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    c = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    q = sample_configs(robot, 80, seed=17, active=act)
+    q0 = q[0::2]
+    q1 = q0 + 0.35 * (q[1::2] - q0)
+    nfail = 0
+    for interval in (pl.IT_Open, pl.IT_OpenStart, pl.IT_OpenEnd, pl.IT_Closed):
+        for options in (0xffff, 0xffff | pl.CFO_CheckWithPerturbation):
+            got = P.CheckEdges(q0, q1, interval, options, perturbation=0.1)
+            for k in range(len(q0)):
+                fr = pl.ConstraintFilterReturn()
+                ret = c.Check(q0[k], q1[k], interval, options, fr)
+                g = got[k]
+                assert g["return_code"] == ret
+                s, t, _ = c.edge_samples(q0[k], q1[k], interval)
+                assert g["nsamples"] == len(s)
+                if ret:
+                    nfail += 1
+                    assert np.array_equal(g["invalid_values"], np.array(fr._invalidvalues)) and g["time_when_invalid"] == fr._fTimeWhenInvalid
+                    assert np.array_equal(s[g["first_invalid"]], g["invalid_values"])
+                else:
+                    assert g["first_invalid"] == -1
+    assert nfail > 20
+    # parabolic ramps (quadratic branch)
+    rng = np.random.default_rng(5)
+    ramps = []
+    while len(ramps) < 40:
+        T = rng.uniform(0.1, 1.2)
+        a = c.lower + (0.2 + 0.6 * rng.random(len(act))) * (c.upper - c.lower)
+        v0, v1 = rng.uniform(-2, 2, len(act)), rng.uniform(-2, 2, len(act))
+        b = a + T * 0.5 * (v0 + v1)
+        if (b >= c.lower).all() and (b <= c.upper).all():
+            ramps.append((a, b, v0, v1, T))
+    A, B, V0, V1, TT = (np.array([r[i] for r in ramps]) for i in range(5))
+    got = P.CheckEdges(A, B, pl.IT_Closed, 0xffff, dq0=V0, dq1=V1, timeelapsed=TT)
+    codes = set()
+    for k, g in enumerate(got):
+        fr = pl.ConstraintFilterReturn()
+        ret = c.CheckRamp(A[k], B[k], V0[k], V1[k], TT[k], pl.IT_Closed, options=0xffff, filterreturn=fr)
+        assert g["return_code"] == ret
+        codes.add(ret)
+        if ret and ret != pl.CFO_StateSettingError:
+            assert np.array_equal(g["invalid_values"], np.array(fr._invalidvalues))
+    assert len(codes) >= 2
+    assert P.CheckEdges(np.zeros((0, len(act))), np.zeros((0, len(act)))) == []
