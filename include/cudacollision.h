@@ -403,6 +403,12 @@ int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const do
  * the planner until the next call and are read with cc_planner_get_path. */
 int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts,
                         const double* goals, const uint32_t* seeds, cc_plan_result* results);
+/* The same for BasicRrtPlanner (plugins/rplanners/rrt.h:693-938; RaveCreatePlanner(env, "basicrrt")): one forward tree, the goal
+ * sampled at the first iteration and then with probability goal_bias (0.05 in the reference), SpatialTree::Extend rays checked
+ * in one batch each, success when a ray connects within 2 x step_length of the goal; extent_type = BasicRRTParameters::
+ * _nRRTExtentType (1: a ray stops at its first new node).  The path ends at the connecting node like the reference's. */
+int cc_basicrrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int extent_type, int nproblems, const double* starts,
+                           const double* goals, const uint32_t* seeds, cc_plan_result* results);
 /* which: 0 = smoothed path, 1 = raw path.  Copies up to max_waypoints rows; *out_waypoints = the path's length. */
 int cc_planner_get_path(const cc_planner* p, int problem, int which, double* out, int max_waypoints, int* out_waypoints);
 /* Totals of the last cc_birrt_plan_batch: rounds, checker calls, configurations submitted, serial-equivalent configurations. */

@@ -524,7 +524,7 @@ struct Problem {
     // SpatialTree::Extend.  The ray c0 -> c1 -> ... is generated up front (it depends on the target only); chunks of
     // `speculate_steps` steps are submitted, one segment per step, and nodes are inserted for the steps before the first
     // failing one.
-    Task<int> extend(Tree& tree, const std::vector<double>& target, int& lastnode)
+    Task<int> extend(Tree& tree, const std::vector<double>& target, int& lastnode, bool one_step = false)
     {
         const int n = ndof();
         const int nn = tree.nearest(*cs, target.data());
@@ -537,11 +537,12 @@ struct Problem {
         // steps submitted per round: the whole ray (0), a fixed number (> 0), or adaptive (< 0): -speculate_steps steps first,
         // doubling every time a chunk passes — rays that die at an obstacle cost little, free rays finish in a few rounds
         int chunk = prm.speculate_steps > 0 ? prm.speculate_steps : (prm.speculate_steps < 0 ? -prm.speculate_steps : maxsteps);
+        if (one_step) chunk = 1;          // bOneStep (rplanners.h:442-444): the ray ends at its first inserted node
         int iter = 0;
         int terminal = -1;                      // set when the ray ends without needing a check
         bool first_chunk = true;
         while (iter < maxsteps && terminal < 0) {
-            if (!first_chunk && prm.speculate_steps < 0) chunk *= 2;
+            if (!first_chunk && prm.speculate_steps < 0 && !one_step) chunk *= 2;
             first_chunk = false;
             // ---- generate up to `chunk` steps
             group.clear();
@@ -576,6 +577,7 @@ struct Problem {
                 if (id >= 0) { pnode = id; lastnode = id; added = true; }
             }
             if (passed < gen) { terminal = added ? ET_Sucess : ET_Failed; break; }
+            if (one_step && added) { terminal = ET_Connected; break; }    // "BasicRRT relies on ET_Connected" (rplanners.h:443)
             iter += gen;
             cur = c;
             if (end_code == ET_Connected) { terminal = ET_Connected; break; }
@@ -1006,6 +1008,62 @@ struct Problem {
         co_return 0;
     }
 
+    // BasicRrtPlanner::InitPlan + PlanPath (plugins/rplanners/rrt.h:693-938) for one start and one goal: a single forward tree,
+    // the goal sampled at the first iteration and then with probability goal_bias (0.05 there), ET_Connected within
+    // 2 x step of the goal ends the search (_nMinIterations = 0), the path is the chain from the root to that node (it ends
+    // at the node, not at the goal, like the reference's), then _SimpleOptimizePath(10) and the post-processor.  The
+    // reference draws from RaveRandomFloat / RaveRandomInt here (global generator): the stream is this problem's sampler.
+    Task<int> plan_basic(bool one_step)
+    {
+        const int n = ndof();
+        uniform = Sampler(seed);
+        config = Sampler(seed);
+        fwd.dof = n;
+        fwd.step = prm.step_length;
+        fwd.mindist = 0.001 * prm.step_length;
+        fwd.fromgoal = false;
+        group.clear();
+        add_edge(start.data(), start.data(), IT_OpenStart);
+        CheckReply r = co_await check();
+        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_INITIAL; co_return 0; }
+        fwd.insert(*cs, -1, start.data(), 0);
+        group.clear();
+        add_edge(goal.data(), goal.data(), IT_OpenStart);                     // goals in collision are dropped (:738-743)
+        r = co_await check();
+        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }
+        const int maxiter = prm.max_iterations > 0 ? prm.max_iterations : 10000;
+        int iter = 0, best = -1, last = -1;
+        std::vector<double> target;
+        while (iter < maxiter) {
+            ++iter;
+            res.iterations++;
+            if (best >= 0) break;
+            if (iter == 1 || uniform.real(IT_Closed) < prm.goal_bias) {
+                (void)uniform.u32();                                          // RaveRandomInt() % _vecGoals.size(), one goal
+                target = goal;
+            } else sample_config(target);
+            const int et = co_await extend(fwd, target, last, one_step);
+            if (et == ET_Connected && cs->dist(goal.data(), fwd.cfg(last)) < 2 * prm.step_length) best = last;
+        }
+        res.nodes_forward = fwd.size();
+        res.nodes_backward = 0;
+        if (best < 0) { res.status = CC_PLAN_FAILED; co_return 0; }
+        std::vector<int> chain;
+        for (int i = best; i >= 0; i = fwd.parent[i]) chain.push_back(i);
+        path_raw.clear();
+        for (auto it = chain.rbegin(); it != chain.rend(); ++it) path_raw.insert(path_raw.end(), fwd.cfg(*it), fwd.cfg(*it) + n);
+        co_await simple_optimize(path_raw, prm.path_optimize_iterations);
+        res.waypoints_raw = (int)path_raw.size() / n;
+        res.length_raw = path_length(path_raw);
+        if (prm.smoother_iterations > 0 && prm.post_processor == CC_POST_SHORTCUT_LINEAR) co_await shortcut_linear(path_raw, path);
+        else if (prm.smoother_iterations > 0) co_await smooth(path_raw, path);
+        else path = path_raw;
+        res.waypoints = (int)path.size() / n;
+        res.length = path_length(path);
+        res.status = CC_PLAN_SOLVED;
+        co_return 0;
+    }
+
     // BirrtPlanner::InitPlan + PlanPath for one start and one goal
     Task<int> plan()
     {
@@ -1277,8 +1335,11 @@ int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const do
     return CC_OK;
 }
 
-int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts, const double* goals,
-                        const uint32_t* seeds, cc_plan_result* results)
+}  // extern "C"
+
+// kind 0: BiRRT; 1: BasicRRT; 2: BasicRRT with one-step extension (_nRRTExtentType == 1)
+static int plan_batch(cc_planner* p, const cc_birrt_params* params, int kind, int nproblems, const double* starts, const double* goals,
+                      const uint32_t* seeds, cc_plan_result* results)
 {
     if (!p || !params || nproblems < 0 || (nproblems > 0 && (!starts || !goals || !results)))
         return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: bad arguments");
@@ -1298,7 +1359,7 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
         std::memset(&pr->res, 0, sizeof(pr->res));
         p->problems.push_back(std::move(pr));
     }
-    for (int k = 0; k < nproblems; ++k) tasks.push_back(p->problems[k]->plan());
+    for (int k = 0; k < nproblems; ++k) tasks.push_back(kind == 0 ? p->problems[k]->plan() : p->problems[k]->plan_basic(kind == 2));
     std::memset(p->totals, 0, sizeof(p->totals));
 
     // start every coroutine: each runs until its first request (or to completion)
@@ -1376,6 +1437,20 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
                 (unsigned long long)p->totals[0], 1e3 * t_gather, 1e3 * t_check, 1e3 * t_resume);
     for (int k = 0; k < nproblems; ++k) results[k] = p->problems[k]->res;
     return CC_OK;
+}
+
+extern "C" {
+
+int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts, const double* goals,
+                        const uint32_t* seeds, cc_plan_result* results)
+{
+    return plan_batch(p, params, 0, nproblems, starts, goals, seeds, results);
+}
+
+int cc_basicrrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int extent_type, int nproblems, const double* starts,
+                           const double* goals, const uint32_t* seeds, cc_plan_result* results)
+{
+    return plan_batch(p, params, extent_type == 1 ? 2 : 1, nproblems, starts, goals, seeds, results);
 }
 
 int cc_planner_get_path(const cc_planner* p, int problem, int which, double* out, int max_waypoints, int* out_waypoints)

@@ -648,7 +648,7 @@ class cc_edge_result(ctypes.Structure):
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
-                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
 def _planner_lib():
@@ -665,6 +665,7 @@ def _planner_lib():
     lib.cc_planner_ramp_samples.argtypes = [vp, vp, vp, vp, vp, ctypes.c_double, ci, vp, vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_check_edges.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, ci, ctypes.c_double, vp, vp]
     lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
+    lib.cc_basicrrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, ci, vp, vp, vp, vp]
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
     lib._planner_ready = True
@@ -767,15 +768,20 @@ class BirrtPlanner(object):
             out.append(d)
         return out
 
-    def PlanBatch(self, starts, goals, seeds=None):
-        """Returns a list of dicts (status, iterations, path [w, ndof], path_raw, lengths, config counts) + totals."""
+    def PlanBatch(self, starts, goals, seeds=None, planner="birrt", extent_type=0):
+        """Returns a list of dicts (status, iterations, path [w, ndof], path_raw, lengths, config counts) + totals.
+        planner: "birrt" (BirrtPlanner) or "basicrrt" (BasicRrtPlanner, extent_type = _nRRTExtentType)."""
         starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, self.ndof)
         goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, self.ndof)
         k = starts.shape[0]
         seeds = np.zeros(k, dtype=np.uint32) if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
         res = (cc_plan_result * max(k, 1))()
-        self._ck(self.lib.cc_birrt_plan_batch(self.handle, ctypes.byref(self.params), k, starts.ctypes.data, goals.ctypes.data,
-                                              seeds.ctypes.data, ctypes.addressof(res)))
+        if planner == "basicrrt":
+            self._ck(self.lib.cc_basicrrt_plan_batch(self.handle, ctypes.byref(self.params), extent_type, k, starts.ctypes.data,
+                                                     goals.ctypes.data, seeds.ctypes.data, ctypes.addressof(res)))
+        else:
+            self._ck(self.lib.cc_birrt_plan_batch(self.handle, ctypes.byref(self.params), k, starts.ctypes.data, goals.ctypes.data,
+                                                  seeds.ctypes.data, ctypes.addressof(res)))
         out = []
         for i in range(k):
             r = res[i]

@@ -221,3 +221,40 @@ def test_gpu_plans_pr2_right_arm_with_circular_joints():
     assert same >= 7, same
     for r in gpu:
         assert r["status"] == pl.PLAN_SOLVED and not orc.check_batch(robot, r["path"], active=arm)["verdict"].any()
+
+
+def test_basicrrt_plans_are_valid_and_batching_invariant(wamtest1):
+    """BasicRrtPlanner (rrt.h:693-938) on the batched entry: a single tree with goal bias; the raw path runs from the start to a
+    node within 2 x step of the goal; every edge is collision free under the oracle; lockstep width, ray chunking and the
+    one-step extension (_nRRTExtentType = 1) behave as specified."""
+    env, robot, orc = wamtest1
+    starts, goals = _free_pairs(robot, orc, 6, seed=3)
+    seeds = np.arange(6) + 7
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot), goal_bias=0.05, max_iterations=4000)
+    res = P.PlanBatch(starts, goals, seeds, planner="basicrrt")
+    cons = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    w = np.sqrt(P._w ** 2)
+    for r, s, g in zip(res, starts, goals):
+        assert r["status"] == pl.PLAN_SOLVED and r["nodes_backward"] == 0
+        for key in ("path", "path_raw"):
+            p = r[key]
+            assert np.array_equal(p[0], s)
+            assert np.sqrt(((w * (p[-1] - g)) ** 2).sum()) < 2 * 0.04                 # ends at the connecting node (rrt.h:820-823)
+            assert not orc.check_batch(robot, p)["verdict"].any()
+        p = r["path_raw"]
+        assert not any(cons.CheckMany([(p[i], p[i + 1]) for i in range(len(p) - 1)], pl.IT_Open, options=0xffff))
+        assert r["length"] <= r["length_raw"] + 1e-9
+    solo = pl.BirrtPlanner(robot, orc.group_checker(robot), goal_bias=0.05, max_iterations=4000, speculate_steps=0)
+    for k in (0, 3):
+        a = solo.PlanBatch([starts[k]], [goals[k]], [seeds[k]], planner="basicrrt")[0]
+        assert np.array_equal(a["path"], res[k]["path"]) and a["iterations"] == res[k]["iterations"]
+    one = P.PlanBatch(starts[:3], goals[:3], seeds[:3], planner="basicrrt", extent_type=1)
+    for r, full in zip(one, res):
+        assert r["status"] in (pl.PLAN_SOLVED, pl.PLAN_FAILED)
+        if r["status"] == pl.PLAN_SOLVED:
+            assert r["iterations"] >= full["iterations"]                            # one node per iteration instead of a whole ray
+            assert not orc.check_batch(robot, r["path"])["verdict"].any()
+    bad = sample_configs(robot, 200, seed=9, active=robot.GetActiveDOFIndices())
+    v = orc.check_batch(robot, bad, active=robot.GetActiveDOFIndices())["verdict"]
+    r = P.PlanBatch([bad[v != 0][0]], [goals[0]], [1], planner="basicrrt")[0]
+    assert r["status"] == pl.PLAN_BAD_INITIAL
