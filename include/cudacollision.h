@@ -346,6 +346,8 @@ typedef struct cc_plan_result {
     double length_raw, length;       /* sum of SimpleDistanceMetric over consecutive waypoints */
     uint64_t configs_submitted;      /* configurations sent to the checker for this problem */
     uint64_t configs_serial;         /* configurations the serial per-sample loop would have checked (up to each first failure) */
+    int32_t start_index, goal_index; /* GOALPATH::startindex / goalindex (rrt.h:296-302): which initial configuration (rank among the
+                                      * valid ones) and which goal (index as given) the plan connects; -1 when there is no plan */
 } cc_plan_result;
 
 /* A checker for groups of ordered segments.  Configurations q[nconfigs][ndof]; segment s owns configurations
@@ -403,6 +405,14 @@ int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const do
  * the planner until the next call and are read with cc_planner_get_path. */
 int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nproblems, const double* starts,
                         const double* goals, const uint32_t* seeds, cc_plan_result* results);
+/* BiRRT with several initial and several goal configurations per problem (RRTParameters::vinitialconfig / vgoalconfig holding
+ * more than one configuration, rrt.h:72-88, 327-343 — e.g. one goal per IK solution): problem k owns the initial configurations
+ * [start_begin[k], start_begin[k+1]) of `starts` and the goals [goal_begin[k], goal_begin[k+1]) of `goals`.  Configurations that
+ * fail the constraints are skipped (a goal keeps its index); the goal to extend toward is drawn like rrt.h:443-466; the search
+ * ends at the first connection (_minimumgoalpaths = 1) and reports which start / goal it joined. */
+int cc_birrt_plan_batch_multi(cc_planner* p, const cc_birrt_params* params, int nproblems, const int32_t* start_begin,
+                              const double* starts, const int32_t* goal_begin, const double* goals, const uint32_t* seeds,
+                              cc_plan_result* results);
 /* The same for BasicRrtPlanner (plugins/rplanners/rrt.h:693-938; RaveCreatePlanner(env, "basicrrt")): one forward tree, the goal
  * sampled at the first iteration and then with probability goal_bias (0.05 in the reference), SpatialTree::Extend rays checked
  * in one batch each, success when a ray connects within 2 x step_length of the goal; extent_type = BasicRRTParameters::

@@ -474,7 +474,8 @@ namespace {
 struct Problem {
     const CSpace* cs = nullptr;
     cc_birrt_params prm{};
-    std::vector<double> start, goal;
+    std::vector<double> start, goal;          // first initial / goal configuration (BasicRRT plans with these)
+    std::vector<double> starts_all, goals_all; // every initial / goal configuration of the problem, flat (BiRRT)
     uint32_t seed = 0;
     cc_plan_result res{};
     std::vector<double> path_raw, path;       // flat [waypoints][dof]
@@ -1077,17 +1078,32 @@ struct Problem {
         }
         fwd.fromgoal = false;
         bwd.fromgoal = true;
-        // initial and goal configurations: CheckPathAllConstraints(v, v, IT_OpenStart) (rrt.h:78, 325)
-        group.clear();
-        add_edge(start.data(), start.data(), IT_OpenStart);
-        CheckReply r = co_await check();
-        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_INITIAL; co_return 0; }
-        fwd.insert(*cs, -1, start.data(), 0);
-        group.clear();
-        add_edge(goal.data(), goal.data(), IT_OpenStart);
-        r = co_await check();
-        if (r.first_fail_segment >= 0) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }
-        bwd.insert(*cs, -1, goal.data(), 0);
+        // initial and goal configurations: CheckPathAllConstraints(v, v, IT_OpenStart) each (rrt.h:76-88, 327-343).  Valid initial
+        // configurations become roots of the forward tree (userdata = their rank among the valid ones), goals roots of the
+        // backward tree (userdata = their index in vgoalconfig; a goal that fails keeps its slot as a dummy)
+        CheckReply r;
+        const int nstarts = (int)starts_all.size() / n, ngoals = (int)goals_all.size() / n;
+        for (int k = 0; k < nstarts; ++k) {
+            const double* v = &starts_all[(size_t)k * n];
+            group.clear();
+            add_edge(v, v, IT_OpenStart);
+            r = co_await check();
+            if (r.first_fail_segment >= 0) continue;
+            fwd.insert(*cs, -1, v, (uint32_t)fwd.size());
+        }
+        if (fwd.size() == 0) { res.status = CC_PLAN_BAD_INITIAL; co_return 0; }
+        std::vector<int> goal_nodes(ngoals, -1);
+        int nvalidgoals = 0;
+        for (int k = 0; k < ngoals; ++k) {
+            const double* v = &goals_all[(size_t)k * n];
+            group.clear();
+            add_edge(v, v, IT_OpenStart);
+            r = co_await check();
+            if (r.first_fail_segment >= 0) continue;
+            goal_nodes[k] = bwd.insert(*cs, -1, v, (uint32_t)k);
+            if (goal_nodes[k] >= 0) ++nvalidgoals;
+        }
+        if (bwd.size() == 0) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }
 
         const int maxiter = prm.max_iterations > 0 ? prm.max_iterations : 10000;
         Tree* A = &fwd;
@@ -1099,10 +1115,16 @@ struct Problem {
             ++iter;
             res.iterations++;
             target.clear();
-            if (sample_goal || uniform.real(IT_Closed) < prm.goal_bias) {
+            if ((sample_goal || uniform.real(IT_Closed) < prm.goal_bias) && nvalidgoals > 0) {
                 sample_goal = false;
-                (void)uniform.u32();              // one goal: its index draw is still consumed (rrt.h:441-444)
-                target.assign(goal.begin(), goal.end());
+                // up to 3 x #goals draws until one names a goal that stands (rrt.h:443-466; with _minimumgoalpaths = 1 no goal
+                // has been reached yet while the loop runs)
+                for (int testiter = 0; testiter < ngoals * 3; ++testiter) {
+                    const uint32_t gi = uniform.u32() % (uint32_t)ngoals;
+                    if (goal_nodes[gi] < 0) continue;
+                    target.assign(bwd.cfg(goal_nodes[gi]), bwd.cfg(goal_nodes[gi]) + n);
+                    break;
+                }
             }
             if (target.empty()) sample_config(target);
             int et = co_await extend(*A, target, ia);
@@ -1126,7 +1148,11 @@ struct Problem {
         for (int i = cf; i >= 0; i = fwd.parent[i]) chain.push_back(i);
         path_raw.clear();
         for (auto it = chain.rbegin(); it != chain.rend(); ++it) path_raw.insert(path_raw.end(), fwd.cfg(*it), fwd.cfg(*it) + n);
-        for (int i = cb; i >= 0; i = bwd.parent[i]) path_raw.insert(path_raw.end(), bwd.cfg(i), bwd.cfg(i) + n);
+        for (int i = cb; i >= 0; i = bwd.parent[i]) {
+            path_raw.insert(path_raw.end(), bwd.cfg(i), bwd.cfg(i) + n);
+            if (bwd.parent[i] < 0) res.goal_index = (int32_t)bwd.userdata[i];         // GOALPATH::goalindex (rrt.h:633-644)
+        }
+        res.start_index = (int32_t)fwd.userdata[chain.back()];                          // GOALPATH::startindex (:622-631)
         co_await simple_optimize(path_raw, prm.path_optimize_iterations);
         res.waypoints_raw = (int)path_raw.size() / n;
         res.length_raw = path_length(path_raw);
@@ -1339,7 +1365,7 @@ int cc_planner_check_edges(cc_planner* p, int nedges, const double* q0, const do
 
 // kind 0: BiRRT; 1: BasicRRT; 2: BasicRRT with one-step extension (_nRRTExtentType == 1)
 static int plan_batch(cc_planner* p, const cc_birrt_params* params, int kind, int nproblems, const double* starts, const double* goals,
-                      const uint32_t* seeds, cc_plan_result* results)
+                      const uint32_t* seeds, cc_plan_result* results, const int32_t* start_begin = nullptr, const int32_t* goal_begin = nullptr)
 {
     if (!p || !params || nproblems < 0 || (nproblems > 0 && (!starts || !goals || !results)))
         return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: bad arguments");
@@ -1353,10 +1379,16 @@ static int plan_batch(cc_planner* p, const cc_birrt_params* params, int kind, in
         auto pr = std::make_unique<Problem>();
         pr->cs = &p->cs;
         pr->prm = *params;
-        pr->start.assign(starts + (size_t)k * n, starts + (size_t)(k + 1) * n);
-        pr->goal.assign(goals + (size_t)k * n, goals + (size_t)(k + 1) * n);
+        const int s0 = start_begin ? start_begin[k] : k, s1 = start_begin ? start_begin[k + 1] : k + 1;
+        const int g0 = goal_begin ? goal_begin[k] : k, g1 = goal_begin ? goal_begin[k + 1] : k + 1;
+        if (s1 <= s0 || g1 <= g0) { p->problems.clear(); return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: a problem needs at least one initial and one goal configuration"); }
+        pr->starts_all.assign(starts + (size_t)s0 * n, starts + (size_t)s1 * n);
+        pr->goals_all.assign(goals + (size_t)g0 * n, goals + (size_t)g1 * n);
+        pr->start.assign(pr->starts_all.begin(), pr->starts_all.begin() + n);
+        pr->goal.assign(pr->goals_all.begin(), pr->goals_all.begin() + n);
         pr->seed = seeds ? seeds[k] : 0;
         std::memset(&pr->res, 0, sizeof(pr->res));
+        pr->res.start_index = pr->res.goal_index = -1;
         p->problems.push_back(std::move(pr));
     }
     for (int k = 0; k < nproblems; ++k) tasks.push_back(kind == 0 ? p->problems[k]->plan() : p->problems[k]->plan_basic(kind == 2));
@@ -1445,6 +1477,13 @@ int cc_birrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int nprobl
                         const uint32_t* seeds, cc_plan_result* results)
 {
     return plan_batch(p, params, 0, nproblems, starts, goals, seeds, results);
+}
+
+int cc_birrt_plan_batch_multi(cc_planner* p, const cc_birrt_params* params, int nproblems, const int32_t* start_begin, const double* starts,
+                              const int32_t* goal_begin, const double* goals, const uint32_t* seeds, cc_plan_result* results)
+{
+    if (nproblems > 0 && (!start_begin || !goal_begin)) return fail(CC_ERR_INVALID, "cc_birrt_plan_batch_multi: bad arguments");
+    return plan_batch(p, params, 0, nproblems, starts, goals, seeds, results, start_begin, goal_begin);
 }
 
 int cc_basicrrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int extent_type, int nproblems, const double* starts,

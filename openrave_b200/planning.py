@@ -637,7 +637,8 @@ class cc_plan_result(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("iterations", ctypes.c_int32), ("nodes_forward", ctypes.c_int32),
                 ("nodes_backward", ctypes.c_int32), ("waypoints_raw", ctypes.c_int32), ("waypoints", ctypes.c_int32),
                 ("rounds", ctypes.c_int32), ("shortcuts", ctypes.c_int32), ("length_raw", ctypes.c_double),
-                ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64)]
+                ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64),
+                ("start_index", ctypes.c_int32), ("goal_index", ctypes.c_int32)]
 
 
 class cc_edge_result(ctypes.Structure):
@@ -648,7 +649,7 @@ class cc_edge_result(ctypes.Structure):
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
-                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_birrt_plan_batch_multi", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
 def _planner_lib():
@@ -666,6 +667,7 @@ def _planner_lib():
     lib.cc_planner_check_edges.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, ci, ctypes.c_double, vp, vp]
     lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
     lib.cc_basicrrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, ci, vp, vp, vp, vp]
+    lib.cc_birrt_plan_batch_multi.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp, vp, vp]
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
     lib._planner_ready = True
@@ -782,6 +784,9 @@ class BirrtPlanner(object):
         else:
             self._ck(self.lib.cc_birrt_plan_batch(self.handle, ctypes.byref(self.params), k, starts.ctypes.data, goals.ctypes.data,
                                                   seeds.ctypes.data, ctypes.addressof(res)))
+        return self._collect(res, k)
+
+    def _collect(self, res, k):
         out = []
         for i in range(k):
             r = res[i]
@@ -800,3 +805,19 @@ class BirrtPlanner(object):
 
     def PlanPath(self, start, goal, seed=0):
         return self.PlanBatch([start], [goal], [seed])[0]
+
+    def PlanBatchMulti(self, starts_per_problem, goals_per_problem, seeds=None):
+        """BiRRT with several initial / goal configurations per problem (lists of [k_i, ndof] arrays): cc_birrt_plan_batch_multi.
+        The result dicts carry start_index / goal_index (GOALPATH::startindex / goalindex)."""
+        k = len(starts_per_problem)
+        S = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.ndof) for a in starts_per_problem]
+        G = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.ndof) for a in goals_per_problem]
+        sb = np.concatenate([[0], np.cumsum([len(a) for a in S])]).astype(np.int32)
+        gb = np.concatenate([[0], np.cumsum([len(a) for a in G])]).astype(np.int32)
+        sa = np.ascontiguousarray(np.concatenate(S)) if k else np.zeros((0, self.ndof))
+        ga = np.ascontiguousarray(np.concatenate(G)) if k else np.zeros((0, self.ndof))
+        seeds = np.zeros(k, dtype=np.uint32) if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        res = (cc_plan_result * max(k, 1))()
+        self._ck(self.lib.cc_birrt_plan_batch_multi(self.handle, ctypes.byref(self.params), k, sb.ctypes.data, sa.ctypes.data,
+                                                    gb.ctypes.data, ga.ctypes.data, seeds.ctypes.data, ctypes.addressof(res)))
+        return self._collect(res, k)

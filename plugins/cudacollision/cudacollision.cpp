@@ -933,15 +933,27 @@ public:
     {
         if (!_planner || !_parameters) return PlannerStatus("cudabirrt: not initialized", PS_Failed);
         const int ndof = _parameters->GetDOF();
-        if ((int)_parameters->vinitialconfig.size() != ndof || (int)_parameters->vgoalconfig.size() != ndof)
-            return PlannerStatus("cudabirrt: one initial and one goal configuration per problem", PS_Failed);
-        std::vector<TrajectoryBasePtr> vtraj(1, ptraj);
-        std::vector<uint32_t> seeds(1, _parameters->_nRandomGeneratorSeed);
-        std::vector<int> vstatus;
-        PlanPathBatch(_parameters->vinitialconfig, _parameters->vgoalconfig, seeds, vtraj, vstatus);
-        if (vstatus[0] == CC_PLAN_SOLVED) return PlannerStatus(PS_HasSolution);
-        return PlannerStatus("cudabirrt: no path", vstatus[0] == CC_PLAN_BAD_INITIAL ? (PS_Failed | PS_FailedDueToInitial)
-                                                   : vstatus[0] == CC_PLAN_BAD_GOAL ? (PS_Failed | PS_FailedDueToGoal) : PS_Failed);
+        const int ninitial = (int)_parameters->vinitialconfig.size() / ndof, ngoals = (int)_parameters->vgoalconfig.size() / ndof;
+        if (ninitial < 1 || ngoals < 1 || (int)_parameters->vinitialconfig.size() % ndof || (int)_parameters->vgoalconfig.size() % ndof)
+            return PlannerStatus("cudabirrt: initial / goal configurations are improperly specified", PS_Failed);      // rrt.h:65-69, 322-328
+        // several initial configurations and several goals (one per IK solution, say) are one problem (rrt.h:72-88, 327-343)
+        EnvironmentLock lock(GetEnv()->GetMutex());
+        const int32_t start_begin[2] = {0, ninitial}, goal_begin[2] = {0, ngoals};
+        const uint32_t seed = _parameters->_nRandomGeneratorSeed;
+        cc_plan_result result;
+        if (cc_birrt_plan_batch_multi(_planner, &_birrt, 1, start_begin, _parameters->vinitialconfig.data(), goal_begin,
+                                      _parameters->vgoalconfig.data(), &seed, &result) != CC_OK)
+            throw OPENRAVE_EXCEPTION_FORMAT("cudabirrt: %s", cc_last_error(), ORE_Failed);
+        if (result.status != CC_PLAN_SOLVED)
+            return PlannerStatus("cudabirrt: no path", result.status == CC_PLAN_BAD_INITIAL ? (PS_Failed | PS_FailedDueToInitial)
+                                                       : result.status == CC_PLAN_BAD_GOAL ? (PS_Failed | PS_FailedDueToGoal) : PS_Failed);
+        int nw = 0;
+        cc_planner_get_path(_planner, 0, 0, NULL, 0, &nw);
+        std::vector<dReal> waypoints((size_t)nw * ndof);
+        cc_planner_get_path(_planner, 0, 0, waypoints.data(), nw, &nw);
+        if (ptraj->GetConfigurationSpecification().GetDOF() == 0) ptraj->Init(_parameters->_configurationspecification);
+        ptraj->Insert(ptraj->GetNumWaypoints(), waypoints, _parameters->_configurationspecification);
+        return PlannerStatus(PS_HasSolution);
     }
 
     /// starts / goals: [n][ndof]; every solved problem appends its waypoints to vtraj[k] (positions only; retiming is left to the

@@ -258,3 +258,32 @@ def test_basicrrt_plans_are_valid_and_batching_invariant(wamtest1):
     v = orc.check_batch(robot, bad, active=robot.GetActiveDOFIndices())["verdict"]
     r = P.PlanBatch([bad[v != 0][0]], [goals[0]], [1], planner="basicrrt")[0]
     assert r["status"] == pl.PLAN_BAD_INITIAL
+
+
+def test_birrt_with_several_initial_and_goal_configurations(wamtest1):
+    """RRTParameters::vinitialconfig / vgoalconfig with more than one configuration (rrt.h:72-88, 327-343, 443-466): one start
+    and one goal per problem through the multi entry is the single entry; colliding goals / starts are skipped and keep their
+    index; the plan joins one valid start to one valid goal and says which."""
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    starts, goals = _free_pairs(robot, orc, 6, seed=3)
+    seeds = np.arange(6)
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    single = P.PlanBatch(starts, goals, seeds)
+    multi = P.PlanBatchMulti([s[None] for s in starts], [g[None] for g in goals], seeds)
+    for a, b in zip(single, multi):
+        assert np.array_equal(a["path"], b["path"]) and a["iterations"] == b["iterations"]
+        assert (b["start_index"], b["goal_index"]) == (0, 0) and (a["start_index"], a["goal_index"]) == (0, 0)
+    q = sample_configs(robot, 300, seed=9, active=act)
+    v = orc.check_batch(robot, q, active=act)["verdict"]
+    bad, good = q[v != 0], q[v == 0]
+    S = [np.array([bad[0], good[0], good[1]]), np.array([good[2]])]
+    G = [np.array([bad[1], good[3], bad[2], good[4]]), np.array([bad[3], bad[4]])]
+    res = P.PlanBatchMulti(S, G, [11, 12])
+    r = res[0]
+    assert r["status"] == pl.PLAN_SOLVED
+    assert r["goal_index"] in (1, 3) and r["start_index"] in (0, 1)            # goals keep their index, starts are ranked among the valid
+    assert np.array_equal(r["path"][0], S[0][1 + r["start_index"]]) and np.array_equal(r["path"][-1], G[0][r["goal_index"]])
+    assert not orc.check_batch(robot, r["path"])["verdict"].any()
+    assert res[1]["status"] == pl.PLAN_BAD_GOAL and res[1]["goal_index"] == -1
+    assert P.PlanBatchMulti([np.array([bad[0]])], [np.array([good[0]])], [1])[0]["status"] == pl.PLAN_BAD_INITIAL
