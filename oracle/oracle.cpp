@@ -7,7 +7,9 @@
 // Parity pin: this restatement is checked (tests/test_oracle_vs_ref.py) against the UNMODIFIED vendored PQP
 // compiled from /root/reference/plugins/pqprave/pqp by oracle/Makefile into oracle/_ref/ (identical contact
 // lists and identical NumBVTests/NumTriTests on random poses), and against the reference's own known-answer
-// tests for lab1 (tests/test_oracle_golden.py <- test/test_collision.py:183-251).
+// tests: lab1 verdicts and pqp distances (tests/test_oracle_golden.py <- test/test_collision.py:183-251), the four pqp
+// minDistance values of test/test_robot.py:625-660 (first one to 17 digits), and test/test_collision.py's selfcollision /
+// attachedbodies / joinxml / callbacks / multiplecontacts cases (tests/test_reference_collision_tests.py).
 //
 // What is restated, with the reference lines it follows:
 //   Transform algebra            include/openrave/geometry.h:255-262 (normalize4), :430-446 (rotate),
