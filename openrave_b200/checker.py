@@ -658,6 +658,28 @@ class CudaCollisionChecker(object):
             return self._single_pairs(a.body, triples, report)
         raise CudaCollisionError("CheckCollision overload not supported (rays throw in pqprave as well)")
 
+    def CheckCollisionExcluding(self, a, bodyexcluded, linkexcluded, report=None):
+        """CheckCollision(body | link, vbodyexcluded, vlinkexcluded, report) (collisionchecker.h:249-263; pqprave
+        collisionPQP.h:314-329, 432-498): the surviving link pairs go through one explicit-pair query per attached body."""
+        from .environment import excluding_pairs
+        if report is not None:
+            report.Reset(self._options)
+        self._sync()
+        hit = False
+        sub = type(report)() if report is not None else None
+        for qb, pairs in excluding_pairs(self.env, a, bodyexcluded, linkexcluded):
+            triples = [(l1.index, self.body_id(l2.body), l2.index) for l1, l2 in pairs]
+            if self._single_pairs(qb, triples, sub):
+                hit = True
+                if report is None:
+                    return True
+                for l1, l2 in sub.vLinkColliding:
+                    report.AddLinkCollision(l1, l2)
+                report.minDistance = 0
+            if sub is not None:
+                sub.Reset(self._options)
+        return hit
+
     def _single_pairs(self, body, triples, report):
         if not triples:
             return False

@@ -155,10 +155,14 @@ class Environment(object):
     def GetCollisionChecker(self):
         return self.checker
 
-    def CheckCollision(self, a, b=None, report=None):
+    def CheckCollision(self, a, b=None, report=None, bodyexcluded=None, linkexcluded=None):
+        """The CheckCollision overloads of EnvironmentBase (environment-core.h:1491-1572); `bodyexcluded` / `linkexcluded` select
+        the (body | link, vbodyexcluded, vlinkexcluded) overloads (collisionchecker.h:249-263)."""
         cc = self.checker
         if cc is None:
             raise RuntimeError("no collision checker set")
+        if bodyexcluded is not None or linkexcluded is not None:
+            return cc.CheckCollisionExcluding(a, list(bodyexcluded or ()), list(linkexcluded or ()), report=report)
         if b is None:
             return cc.CheckCollision(a, report=report)
         return cc.CheckCollision(a, b, report=report)
@@ -203,6 +207,38 @@ class Environment(object):
 
     def __exit__(self, *a):
         return False
+
+
+def excluding_pairs(env, a, bodyexcluded, linkexcluded):
+    """Link pairs of CheckCollisionP with exclusion lists (plugins/pqprave/collisionPQP.h:432-498, 314-329) in the reference's order:
+    for a body, each attached body (itself, what it grabs) against every other body that is not attached to it and not
+    excluded; links named in `linkexcluded` are skipped on either side.  For a link, only that link (attached bodies are not
+    walked, collisionchecker.h:250).  Returns [(query body, [(link1, link2), ...]), ...]."""
+    from .kinbody import Link
+    excl_b = set(id(b) for b in bodyexcluded)
+    excl_l = set(id(l) for l in linkexcluded)
+    if isinstance(a, Link):
+        groups = [(a.body, [a])]
+        attached = set([id(a.body)])
+    else:
+        bodies = [a] + [g.body for g in getattr(a, "grabbed", [])]
+        attached = set(id(b) for b in bodies)
+        groups = [(b, list(b.links)) for b in bodies]
+    out = []
+    for qb, links in groups:
+        pairs = []
+        for ob in env.GetBodies():
+            if id(ob) in attached or id(ob) in excl_b:
+                continue
+            for l1 in links:
+                if id(l1) in excl_l:
+                    continue
+                for l2 in ob.links:
+                    if id(l2) in excl_l:
+                        continue
+                    pairs.append((l1, l2))
+        out.append((qb, pairs))
+    return out
 
 
 def default_data_dirs():

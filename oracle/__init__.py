@@ -379,6 +379,24 @@ class OracleChecker(object):
             return hit
         raise NotImplementedError("CheckCollision overload")
 
+    def CheckCollisionExcluding(self, a, bodyexcluded, linkexcluded, report=None):
+        """CheckCollisionP with exclusion lists, literally (collisionPQP.h:432-498): one DoPQP per surviving link pair, in order."""
+        from openrave_b200.environment import excluding_pairs
+        if report is not None:
+            report.Reset(self._options)
+        hit = False
+        for _, pairs in excluding_pairs(self.env, a, bodyexcluded, linkexcluded):
+            found = [(l1, l2) for l1, l2 in pairs if self._link_vs_links(l1, [l2])]
+            kept = self.env.filter_collisions_through_callbacks(self._options, found)
+            if kept:
+                hit = True
+                if report is None:
+                    return True
+                for l1, l2 in kept:
+                    report.AddLinkCollision(l1, l2)
+                report.minDistance = 0
+        return hit
+
     def _bodies_by_id(self):
         return {self._ids[id(b)]: b for b in self.env.GetBodies() if id(b) in self._ids}
 

@@ -118,3 +118,28 @@ def test_selfcollision_joinxml(make):
     report = CollisionReport()
     assert robot.CheckSelfCollision(report)
     assert report.plink1.body is robot and report.plink2.body is robot
+
+
+def test_excluded_bodies_and_links_oracle():
+    """The (body | link, vbodyexcluded, vlinkexcluded) overloads (collisionchecker.h:249-263; pqprave collisionPQP.h:432-498):
+    excluding what a body collides with frees it, excluding something else does not, and excluded links are skipped on
+    either side.  (CPU, oracle; the CUDA checker shares `excluding_pairs` and its explicit-pair query.)"""
+    env = _oracle_env("lab1")
+    mug1, mug2, table = env.GetKinBody("mug1"), env.GetKinBody("mug2"), env.GetKinBody("table")
+    robot = env.GetRobots()[0]
+    report = CollisionReport()
+    assert env.CheckCollision(mug1, report=report)                            # mug1 rests on the table
+    others = set(b.body for _, b in report.vLinkColliding)
+    assert table in others or len(others) >= 1
+    assert not env.CheckCollision(mug1, bodyexcluded=list(others), linkexcluded=[])
+    assert env.CheckCollision(mug1, bodyexcluded=[robot], linkexcluded=[])
+    assert not env.CheckCollision(mug1, bodyexcluded=[], linkexcluded=[l for b in others for l in b.links])
+    assert not env.CheckCollision(mug1, bodyexcluded=[], linkexcluded=list(mug1.links))     # its own link excluded: nothing left
+    # the link overload, with a report: only the colliding, non-excluded bodies are named
+    mug2.SetTransform(mug1.GetTransform())
+    rep = CollisionReport()
+    assert env.CheckCollision(mug1.links[0], bodyexcluded=list(others), linkexcluded=[], report=rep)
+    assert set(b.body for _, b in rep.vLinkColliding) == {mug2}
+    assert not env.CheckCollision(mug1.links[0], bodyexcluded=list(others) + [mug2], linkexcluded=[])
+    # same answers as the plain overloads when nothing is excluded
+    assert env.CheckCollision(robot, bodyexcluded=[], linkexcluded=[]) == env.CheckCollision(robot)
