@@ -165,7 +165,8 @@ def cpu_baseline(env, robot, q, budget_s=12.0, kind=None, gpu=None):
                   "first_pair_differs": int(pair_bad.sum()), "differing_inside_1e-4m_band": in_band,
                   "differing_outside_band": int(len(idx) - in_band), "against": "oracle (%s)" % kind}
     return {"value": m / secs, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs)}, cnt.mean(axis=0), parity
+            "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs),
+            "fclrave": "not runnable here: FCL is not part of the reference tree or of this image (SURVEY.md 8d)"}, cnt.mean(axis=0), parity
 
 
 def run_reference_arm(args):
