@@ -22,6 +22,9 @@
 // Boxes are inflated by 1e-5 m at build time, so a lower bound can only be too small: nothing that could hold the minimum
 // is pruned by rounding.
 #pragma once
+#ifndef CC_DIST_PUSH_REVERSED
+#define CC_DIST_PUSH_REVERSED 0
+#endif
 #include "cc_device.cuh"
 
 namespace ccdev {
@@ -377,8 +380,15 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                     if (lf1) triq[ntri + __popc(l0) + __popc(l1 & lt_mask)] = o1;
                     ntri += __popc(l0) + __popc(l1);
                     const unsigned p0 = __ballot_sync(kFull, ps0), p1 = __ballot_sync(kFull, ps1);
+#if CC_DIST_PUSH_REVERSED
+                    // experimental (untested on the GPU so far, off by default): lane 0 popped the top item, so its outputs go
+                    // back on top — the order that paid off in the collision kernel (profiles/r01I_ab_push_order.log)
+                    if (ps0) stack[sp + __popc(p0) - 1 - __popc(p0 & lt_mask)] = o0;
+                    if (ps1) stack[sp + __popc(p0) + __popc(p1) - 1 - __popc(p1 & lt_mask)] = o1;
+#else
                     if (ps0) stack[sp + __popc(p0 & lt_mask)] = o0;
                     if (ps1) stack[sp + __popc(p0) + __popc(p1 & lt_mask)] = o1;
+#endif
                     sp += __popc(p0) + __popc(p1);
                 }
                 __syncwarp();
