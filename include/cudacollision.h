@@ -331,7 +331,8 @@ typedef struct cc_birrt_params {
  * (planner.cpp:28, 315; plugins/rplanners/linearsmoother.cpp) or "shortcut_linear" (ShortcutLinearPlanner,
  * plugins/rplanners/linearshortcutadvanced.cpp:76-569: _SubsampleTrajectory, _OptimizePath, _OptimizePathOneDOF — the one
  * rmanipulation/basemanipulation.cpp:788 selects).  Both run `smoother_iterations` iterations per pass. */
-enum cc_post_processor { CC_POST_LINEARSMOOTHER = 0, CC_POST_SHORTCUT_LINEAR = 1 };
+enum cc_post_processor { CC_POST_LINEARSMOOTHER = 0, CC_POST_SHORTCUT_LINEAR = 1,
+                         CC_POST_LINEARSMOOTHER_SHORTCUTS = 2 /* "linearsmoother 0": _nUseSingleDOFSmoothing = 0, shortcuts only (linearsmoother.cpp:25-26, 241-244) */ };
 
 enum cc_plan_status { CC_PLAN_FAILED = 0, CC_PLAN_SOLVED = 1, CC_PLAN_BAD_INITIAL = 2, CC_PLAN_BAD_GOAL = 3 };
 

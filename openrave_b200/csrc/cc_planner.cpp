@@ -813,8 +813,12 @@ struct Problem {
         }
         const int iters = prm.smoother_iterations;
         if (lp.nodes.size() > 1) {
-            const double d1 = co_await smooth_shortcut(lp, total, iters * 8 / 10, rs);
-            co_await smooth_single_dof(lp, d1, iters * 2 / 10, rs);
+            if (prm.post_processor == CC_POST_LINEARSMOOTHER_SHORTCUTS) {
+                co_await smooth_shortcut(lp, total, iters, rs);               // "linearsmoother 0": every iteration is a shortcut (:241-244)
+            } else {
+                const double d1 = co_await smooth_shortcut(lp, total, iters * 8 / 10, rs);
+                co_await smooth_single_dof(lp, d1, iters * 2 / 10, rs);
+            }
         }
         out.clear();
         for (auto& nd : lp.nodes) out.insert(out.end(), nd.q.begin(), nd.q.end());

@@ -124,6 +124,11 @@ def test_shortcut_linear_equals_the_per_call_restatement(wamtest1):
     solo = pl.BirrtPlanner(robot, orc.group_checker(robot), post_processor="shortcut_linear", speculate_steps=0)
     for k in (4, 5):                                                  # lockstep width does not matter
         assert np.array_equal(solo.PlanPath(starts[k], goals[k], k)["path"], res[k]["path"])
+    # "linearsmoother 0" (_nUseSingleDOFSmoothing = 0): shortcuts only — same raw paths, valid results, never longer than raw
+    only = pl.BirrtPlanner(robot, orc.group_checker(robot), post_processor="linearsmoother 0").PlanBatch(starts, goals, seeds=np.arange(8))
+    for r, b in zip(only, base):
+        assert np.array_equal(r["path_raw"], b["path_raw"]) and r["length"] <= r["length_raw"] + 1e-9
+        assert not orc.check_batch(robot, r["path"])["verdict"].any()
 
 
 def test_colliding_endpoints_are_refused(wamtest1):
