@@ -925,7 +925,9 @@ public:
         _birrt.smoother_iterations = _parameters->_sPostProcessingPlanner.size() > 0 ? 100 : 0;     // linearsmoother's default budget
         _birrt.max_extend_steps = 100;
         _birrt.speculate_steps = -8;
-        _birrt.post_processor = _parameters->_sPostProcessingPlanner == "shortcut_linear" ? CC_POST_SHORTCUT_LINEAR : CC_POST_LINEARSMOOTHER;
+        _birrt.post_processor = _parameters->_sPostProcessingPlanner == "shortcut_linear" ? CC_POST_SHORTCUT_LINEAR
+                                : _parameters->_sPostProcessingPlanner == "linearsmoother 0" ? CC_POST_LINEARSMOOTHER_SHORTCUTS   // creation args (linearsmoother.cpp:25-26)
+                                : CC_POST_LINEARSMOOTHER;
         return PlannerStatus(PS_HasSolution);
     }
 
