@@ -286,6 +286,14 @@ int cc_scene_set_counters(cc_scene* s, int enabled);
 int cc_scene_get_stats(const cc_scene* s, cc_stats* out);
 
 
+/* Diagnostic (no device needed): the bounding-volume hierarchy cc_scene_commit builds for one triangle mesh — what replaces
+ * PQP_Model::EndModel / build_model (pqp/PQP.cpp:169-241, pqp/Build.cpp:344-551) on the device side.  vertices: [nvertices][3],
+ * triangles: [ntriangles][3] vertex indices.  out_nodes (may be NULL): 8 x 32-bit words per node {cx, cy, cz, left (int32),
+ * ex, ey, ez, size}: link-frame AABB centre and half extents; left >= 0: index of the first child (the second is left + 1),
+ * left < 0: leaf holding triangle ~left; node 0 is the root; *out_count = 2 ntriangles - 1. */
+int cc_debug_build_bvh(const double* vertices, int nvertices, const int32_t* triangles, int ntriangles, float* out_nodes,
+                       int max_nodes, int* out_count);
+
 /* ==== planners on the batched entry (BASELINE.json configs[2]) =========================================
  * The reference's RRT family spends its time in PlannerParameters::CheckPathAllConstraints (planner.h:373-379) ->
  * DynamicsCollisionConstraint::Check (planningutils.cpp:2586-3629), one sample at a time.  These entry points run the same

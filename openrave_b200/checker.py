@@ -51,7 +51,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
-           "cc_contacts_poses", "cc_tri_tri_contact"]
+           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh"]
 
 _lib = None
 

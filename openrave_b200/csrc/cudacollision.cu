@@ -1773,3 +1773,22 @@ int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
 }
 
 }  // extern "C"
+
+// Diagnostic, no device needed: the BVH of one triangle mesh exactly as cc_scene_commit builds it (binned surface-area
+// splits, one triangle per leaf, children adjacent).  The CPU tests check its invariants; the GPU never sees this call.
+extern "C" int cc_debug_build_bvh(const double* vertices, int nvertices, const int32_t* triangles, int ntriangles, float* out_nodes,
+                                  int max_nodes, int* out_count)
+{
+    if (!vertices || !triangles || nvertices <= 0 || ntriangles <= 0 || !out_count) return fail(CC_ERR_INVALID, "cc_debug_build_bvh: bad arguments");
+    for (int i = 0; i < 3 * ntriangles; ++i)
+        if (triangles[i] < 0 || triangles[i] >= nvertices) return fail(CC_ERR_INVALID, "cc_debug_build_bvh: vertex index out of range");
+    HLink L;
+    L.verts.assign(vertices, vertices + 3 * (size_t)nvertices);
+    L.tris.assign(triangles, triangles + 3 * (size_t)ntriangles);
+    build_link_bvh(L);
+    *out_count = (int)L.nodes.size();
+    if (out_nodes && max_nodes > 0)
+        memcpy(out_nodes, L.nodes.data(), sizeof(HNode) * (size_t)std::min<int>(max_nodes, (int)L.nodes.size()));
+    return CC_OK;
+}
+
