@@ -44,19 +44,11 @@ constexpr int kFkThreads = 128;
 #ifndef CC_STACK_CAP
 #define CC_STACK_CAP 320
 #endif
-// CC_DUAL_RATIO > 0: when both nodes of a surviving box pair are internal and their sizes (volumes) are within this factor
-// of each other, the next item splits BOTH (4 child-pair box tests in one iteration) instead of the larger one only.  The
-// descent of a colliding pair is a dependent chain of iterations from the roots to a leaf pair; splitting both trees at
-// once halves its length where the trees are balanced against each other, and never tests more boxes than two one-sided
-// steps would when both children of the first step survive.  0 = one-sided items only.
-#ifndef CC_DUAL_RATIO
-#define CC_DUAL_RATIO 0
-#endif
 #ifndef CC_PUSH_REVERSED
 #define CC_PUSH_REVERSED 1     // 1: the outputs of the lane that popped the top item go back on top (strict pair-order priority: +18 .. 37 %, profiles/r01I_ab_push_order.log)
 #endif
 #ifndef CC_TRIQ_CAP
-#define CC_TRIQ_CAP (CC_DUAL_RATIO > 0 ? 144 : 96)
+#define CC_TRIQ_CAP 96
 #endif
 constexpr int kStackCap = CC_STACK_CAP;   // items of shared-memory LIFO per warp
 constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
@@ -849,82 +841,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     if (valid) it = stack[sp - 1 - lane];
                     sp -= n;
                     __syncwarp();
-#if CC_DUAL_RATIO > 0
-                    // ---- items with the dual flag (bit 30 of y) hold the children x, x+1 of a node of tree A and the children
-                    // y, y+1 of a node of tree B: four box pairs; the others are the one-sided items described above
-                    bool tq[4] = {false, false, false, false}, ps[4] = {false, false, false, false};
-                    uint2 o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = make_uint2(0u, 0u);
-                    if (valid) {
-                        const uint32_t sbits = it.x & 0xfc000000u;
-                        const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x3fffffffu;
-                        const bool side = (it.y >> 31) != 0u;                  // false: x is in tree A, true: x is in tree B
-                        const bool dual = ((it.y >> 30) & 1u) != 0u;           // dual items always have side == false
-                        const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
-                        const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
-                        const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
-                        float4 pa = oa, pb = ob;
-                        if (dual) { pa = __ldg(&P.nodes[2 * y + 2]); pb = __ldg(&P.nodes[2 * y + 3]); }
-                        const float* rt = slot_rt + 24 * (it.x >> 26) + (side ? 12 : 0);
-                        float R[9], t[3];
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) R[k] = rt[k];
-                        t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-                        if (counters) n_bv += dual ? 4 : 2;
-                        bool ov[4] = {false, false, false, false};            // [other k][child ch] -> 2 k + ch
-                        box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
-                                         oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov[0], ov[1]);
-                        if (dual)
-                            box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
-                                             pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ov[2], ov[3]);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int lo = __float_as_int(k ? pa.w : oa.w);
-                            const float so = k ? pb.w : ob.w;
-#pragma unroll
-                            for (int ch = 0; ch < 2; ++ch) {
-                                if (ov[2 * k + ch]) {
-                                    const int lc = __float_as_int(ch ? c1a.w : c0a.w);
-                                    const float sc = ch ? c1b.w : c0b.w;
-                                    uint2 out;
-                                    const bool leafpair = lc < 0 && lo < 0;
-                                    if (leafpair) {
-                                        out = side ? make_uint2((uint32_t)(~lo) | sbits, (uint32_t)(~lc))
-                                                   : make_uint2((uint32_t)(~lc) | sbits, (uint32_t)(~lo));
-                                    } else if (lc >= 0 && lo >= 0 && sc <= (float)(CC_DUAL_RATIO) * so && so <= (float)(CC_DUAL_RATIO) * sc) {
-                                        out = side ? make_uint2((uint32_t)lo | sbits, (uint32_t)lc | 0x40000000u)             // split both
-                                                   : make_uint2((uint32_t)lc | sbits, (uint32_t)lo | 0x40000000u);
-                                    } else if (lo < 0 || (lc >= 0 && sc > so)) {
-                                        out = make_uint2((uint32_t)lc | sbits, (y + k) | (side ? 0x80000000u : 0u));           // split the child
-                                    } else {
-                                        out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));          // split the other
-                                    }
-                                    o[2 * k + ch] = out; tq[2 * k + ch] = leafpair; ps[2 * k + ch] = !leafpair;
-                                }
-                            }
-                        }
-                    }
-                    {
-                        unsigned tmk[4], pmk[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { tmk[k] = __ballot_sync(kFull, tq[k]); pmk[k] = __ballot_sync(kFull, ps[k]); }
-                        if (tmk[0] | tmk[1] | tmk[2] | tmk[3]) {
-                            int off = ntri + __popc(tmk[0] & lt_mask) + __popc(tmk[1] & lt_mask) + __popc(tmk[2] & lt_mask) + __popc(tmk[3] & lt_mask);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) if (tq[k]) triq[off++] = o[k];
-                            ntri += __popc(tmk[0]) + __popc(tmk[1]) + __popc(tmk[2]) + __popc(tmk[3]);
-                        }
-                        if (pmk[0] | pmk[1] | pmk[2] | pmk[3]) {
-                            int off = sp + __popc(pmk[0] & lt_mask) + __popc(pmk[1] & lt_mask) + __popc(pmk[2] & lt_mask) + __popc(pmk[3] & lt_mask);
-#pragma unroll
-                            for (int k = 3; k >= 0; --k) if (ps[k]) stack[off++] = o[k];
-                            sp += __popc(pmk[0]) + __popc(pmk[1]) + __popc(pmk[2]) + __popc(pmk[3]);
-                        }
-                    }
-                    __syncwarp();
-                    constexpr int kPushMax = 128;
-#else
                     bool tq0 = false, tq1 = false, ps0 = false, ps1 = false;
                     uint2 o0 = make_uint2(0u, 0u), o1 = make_uint2(0u, 0u);     // outputs for child 0 / child 1 (tri entry or item)
                     if (valid) {
@@ -1000,7 +916,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
 #endif
                     __syncwarp();
                     constexpr int kPushMax = 64;
-#endif
                     if (sp > kStackCap - kPushMax) {
                         // move the oldest kSpillChunk items to global memory and slide the rest down
                         if (spill_count + kSpillChunk > P.spill_cap) {
