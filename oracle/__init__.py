@@ -79,6 +79,7 @@ def _load(kind):
                                     ctypes.c_int64, vp, vp]
     lib.orc_tri_tri_collision.argtypes = [vp, vp, vp, vp]
     lib.orc_pair_queries.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, cd, cd, vp, vp]
+    lib.orc_pair_band.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, cd, vp]
     lib.orc_distance_batch.argtypes = [vp, ci, vp, ci, vp, vp, ci, cd, vp, vp]
     lib.orc_time_batch.restype = cd
     lib.orc_time_batch.argtypes = [vp, ci, vp, ci, ci, ci, vp, ci, vp]
@@ -291,6 +292,20 @@ class OracleChecker(object):
         self.lib.orc_pair_queries(self.scene, bid, _ptr(act), len(act), _ptr(q), n, _ptr(tr), m, float(cap), float(tolerance),
                                   _ptr(dist), _ptr(within))
         return dist, within.astype(bool)
+
+    def pair_band(self, body, q, triples, active=None, band=1e-4):
+        """Contact-band class of every (query link, other body id, other link) triple in every configuration, [n, m] uint8:
+        0 free beyond the band, 1 free within it, 2 colliding with penetration measure <= band, 3 colliding deeper."""
+        self._sync()
+        bid = self._sync_kinematics(body)
+        if active is None:
+            active = body.GetActiveDOFIndices() if body.is_robot else list(range(body.GetDOF()))
+        act = np.array(active, dtype=np.int32)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active))
+        tr = np.ascontiguousarray(np.array(triples, dtype=np.int32).reshape(-1, 3))
+        out = np.zeros((q.shape[0], tr.shape[0]), dtype=np.uint8)
+        self.lib.orc_pair_band(self.scene, bid, _ptr(act), len(act), _ptr(q), q.shape[0], _ptr(tr), tr.shape[0], float(band), _ptr(out))
+        return out
 
     def time_batch(self, body, q, active=None, flags=BATCH_ENV | BATCH_SELF):
         self._sync()

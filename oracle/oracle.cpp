@@ -1473,6 +1473,36 @@ int orc_pair_queries(void* sp, int body, const int32_t* active, int nactive, con
     return 0;
 }
 
+// Contact-band class of single link pairs (the per-pair form of orc_check_batch's want_band, for the CO_AllLinkCollisions
+// parity test): out[c][k] = 0 free and farther apart than `band`, 1 free but within `band`, 2 colliding with a penetration
+// measure <= `band`, 3 colliding deeper than that.
+int orc_pair_band(void* sp, int body, const int32_t* active, int nactive, const double* q, int n, const int32_t* triples,
+                  int ntriples, double band, uint8_t* out)
+{
+    Scene* s = (Scene*)sp;
+    Body* b = s->bodies[body];
+    std::vector<double> vals(b->dofvals);
+    std::vector<Xf> xf;
+    for (int c = 0; c < n; ++c) {
+        for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * nactive + a];
+        forward_kinematics(*b, &vals[0], b->xf[0], xf);
+        for (int k = 0; k < ntriples; ++k) {
+            const int la = triples[3 * k], ob = triples[3 * k + 1], lb = triples[3 * k + 2];
+            const LinkModel& A = *b->links[la];
+            const LinkModel& Bm = *s->bodies[ob]->links[lb];
+            const Xf& xb = ob == body ? xf[lb] : s->bodies[ob]->xf[lb];
+            uint8_t cls = 0;
+            if (A.valid && Bm.valid) {
+                PairResult r = collide_links(xf[la], A, xb, Bm, false, true);
+                if (r.contacts > 0) cls = r.max_penetration <= band ? 2 : 3;
+                else cls = links_within(xf[la], A, xb, Bm, band) ? 1 : 0;
+            }
+            out[(size_t)c * ntriples + k] = cls;
+        }
+    }
+    return 0;
+}
+
 // The reference's contact routine for one intersecting triangle pair (collisionPQP.h:591-603 calls it per PQP contact):
 // the UNMODIFIED OpenRAVE::geometry::TriTriCollision in the _ref build; -1 in the restated build (contacts are pinned on the
 // reference routine only).  u, v: 3 x xyz world coordinates.

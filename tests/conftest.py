@@ -15,6 +15,39 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_present():
+    """Does cc_scene_create find a device?  (The library has no CPU path: without one every query entry point fails.)"""
+    import ctypes
+    try:
+        from openrave_b200 import checker
+        lib = checker.load_library()
+    except Exception:
+        return False
+    h = ctypes.c_void_p()
+    if lib.cc_scene_create(0, ctypes.byref(h)) != 0:
+        return False
+    lib.cc_scene_destroy(h)
+    return True
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a machine without a CUDA device skips the gpu-marked tests instead of failing them; tests
+    that are ABOUT the missing device (test_no_device_fails_loudly) are not gpu-marked and still run."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not _cuda_device_present():
+        skip = pytest.mark.skip(reason="no CUDA device (the product has no CPU path)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
+def _oracle_kind():
+    import oracle
+    return "reference" if oracle.available("reference") else "port"
+
+
+ORACLE_KIND = _oracle_kind()      # GPU parity tests check against the unmodified PQP whenever oracle/_ref exists
+
+
 def load_scene(name):
     from openrave_b200.environment import Environment
     env = Environment()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import sample_configs
+from conftest import ORACLE_KIND, sample_configs
 from openrave_b200 import clutter
 from openrave_b200.checker import BATCH_ENV, BATCH_SELF, CudaCollisionChecker
 
@@ -19,7 +19,7 @@ def make(nob, freq):
     env, robot = clutter.make_clutter_environment(clutter.default_fixture(), nobstacles=nob, freq=freq, seed=5)
     cc = CudaCollisionChecker(env, 0)
     env.SetCollisionChecker(cc)
-    orc = oracle.OracleChecker(env, "port")
+    orc = oracle.OracleChecker(env, ORACLE_KIND)
     orc.InitEnvironment()
     return env, robot, cc, orc, robot.GetActiveDOFIndices()
 

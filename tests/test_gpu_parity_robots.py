@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import load_scene, sample_configs
+from conftest import ORACLE_KIND, load_scene, sample_configs
 from openrave_b200.checker import BATCH_ENV, BATCH_SELF, CO_ActiveDOFs, CudaCollisionChecker
 
 pytestmark = pytest.mark.gpu
@@ -18,7 +18,7 @@ def world(request):
     env = load_scene(scene)
     cc = CudaCollisionChecker(env, 0)
     env.SetCollisionChecker(cc)
-    orc = oracle.OracleChecker(env, "port")
+    orc = oracle.OracleChecker(env, ORACLE_KIND)
     orc.InitEnvironment()
     robot = env.GetRobots()[0]
     manip, seed = CASES[scene]

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import load_scene, sample_configs
+from conftest import ORACLE_KIND, load_scene, sample_configs
 
 
 def _world(scene, manip, tables):
@@ -84,7 +84,7 @@ def test_tables_do_not_change_results(scene, manip, expect_tables):
     robot3 = env3.GetRobots()[0]
     if active is not None:
         robot3.SetActiveDOFs(active)
-    orc = oracle.OracleChecker(env3, "port")
+    orc = oracle.OracleChecker(env3, ORACLE_KIND)
     env3.SetCollisionChecker(orc)
     ref = orc.check_batch(robot3, q[:2500], active=active, want_band=True)
     band = (ref["near"] != 0) | ((ref["verdict"] != 0) & (ref["penetration"] <= 1e-4))
