@@ -195,7 +195,11 @@ int cc_query_get_links(const cc_query* q, int32_t* out_pairs);
 int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags,
                    uint32_t* verdict, int32_t* first_env, int32_t* first_self, uint32_t* pair_mask);
 /* Device-buffer variant: all pointers are device memory on the scene's device, work is enqueued on
- * `cuda_stream` (a cudaStream_t, NULL = legacy default stream) and NOT synchronised. */
+ * `cuda_stream` (a cudaStream_t, NULL = legacy default stream) and NOT synchronised.
+ * ONE call in flight per scene: the traversal's spill areas, work counters and per-chunk pose scratch belong to the scene and
+ * its queries, not to the stream.  Enqueue the next call on the SAME stream (stream order is enough), or synchronise first;
+ * two calls on different streams of one scene would share that state.  (The call that first crosses 16k configurations
+ * also builds the free-space certificates synchronously, see cc_scene_set_pair_tables.) */
 int cc_check_batch_device(cc_query* q, const double* d_dof_values, int n, int flags,
                           uint32_t* d_verdict, int32_t* d_first_env, int32_t* d_first_self,
                           uint32_t* d_pair_mask, void* cuda_stream);
@@ -266,10 +270,31 @@ int cc_scene_set_tri_epsilon(cc_scene* s, double eps);
  * collision-free.  A pair certified in every cell can never collide inside the joint limits and leaves the batched pair
  * list (hoisting, generalised from pose-invariant pairs); a partly certified pair keeps a bit table that the batched entry
  * consults after the broadphase instead of descending the trees.  Verdicts and reported pairs are unchanged (a skipped pair
- * is at least 3e-4 m from contact).  cc_query_get_table_count reports the pairs with a table, the pairs removed and the
+ * is at least 3e-4 m from contact).  Certificates are proven on the snapshot the query captured (cc_query_create /
+ * cc_query_refresh): if any body was moved since (cc_body_set_link_transforms, cc_body_set_dof_values) the build waits for the
+ * caller's cc_query_refresh.  cc_query_get_table_count reports the pairs with a table, the pairs removed and the
  * wall time the last build took (any pointer may be NULL). */
 int cc_scene_set_pair_tables(cc_scene* s, int enabled);
 int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped, double* out_build_ms);
+/* What the last certificate build proved, one record per pair that got a grid certificate (the reach certificates, which need
+ * no grid, are not listed).  Cell (i0, i1) of the grid covers q[col0] in [lo0 + i0 width0, lo0 + (i0+1) width0] (and the same
+ * for col1); it is certified when the exact distance at its centre exceeds delta + margin, delta = (k0 width0 + k1 width1) / 2
+ * being the farthest any point of one link can move relative to the other inside the cell.  min_slack = the smallest
+ * distance - delta - margin over the certified cells, attained in cell `tightest_cell` (= i0 n1 + i1): where a soundness
+ * test should aim (tests/test_pair_tables.py). */
+typedef struct cc_certificate {
+    int32_t pair;                  /* pair index (cc_query_get_pairs) */
+    int32_t col0, col1;            /* columns of q; col1 = -1: one DOF */
+    int32_t n0, n1;                /* grid size */
+    int32_t certified_cells;       /* of n0 n1 */
+    int32_t tightest_cell;
+    int32_t dropped;               /* 1: certified in every cell, the pair left the batched pair list; 0: it keeps a bit table */
+    double lo0, width0, lo1, width1;
+    double k0, k1;                 /* metres per unit of q[col0], q[col1] */
+    double delta, margin;
+    double min_slack, min_distance;
+} cc_certificate;
+int cc_query_get_certificates(const cc_query* q, cc_certificate* out, int max_records, int* out_count);
 
 /* Diagnostics: record, for every configuration of the following batches on this query, how many traversal
  * iterations (32 box-pair tests each) the device spent on it; read the last batch's trace back with
@@ -432,6 +457,13 @@ int cc_basicrrt_plan_batch(cc_planner* p, const cc_birrt_params* params, int ext
 int cc_planner_get_path(const cc_planner* p, int problem, int which, double* out, int max_waypoints, int* out_waypoints);
 /* Totals of the last cc_birrt_plan_batch: rounds, checker calls, configurations submitted, serial-equivalent configurations. */
 int cc_planner_get_totals(const cc_planner* p, uint64_t* out4);
+
+/* Diagnostic (no device needed): the per-DOF displacement rates K the free-space certificates rest on, for the pair (link_a,
+ * link_b) of one joint tree (link_b = -1: the other link is static in the world).  K_d bounds, for EVERY value of every joint,
+ * how far any point of one link moves in the other's frame per unit of DOF d.  *out_n = number of varying active DOFs between
+ * the two links (1 or 2; out_dofs / out_k filled), 0 when such a pair gets no certificate. */
+int cc_debug_pair_rates(const cc_joint* joints, int njoints, int nlinks, const int32_t* col_of_dof, int ndof, int link_a, int link_b,
+                        double radius_a, double radius_b, int32_t* out_dofs, double* out_k, int* out_n);
 
 #ifdef __cplusplus
 }

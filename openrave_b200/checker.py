@@ -37,6 +37,12 @@ class cc_query_info(ctypes.Structure):
                                               "mask_words", "total_nodes", "total_tris")]
 
 
+class cc_certificate(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("pair", "col0", "col1", "n0", "n1", "certified_cells", "tightest_cell", "dropped")] + \
+               [(n, ctypes.c_double) for n in ("lo0", "width0", "lo1", "width1", "k0", "k1", "delta", "margin", "min_slack",
+                                               "min_distance")]
+
+
 class cc_stats(ctypes.Structure):
     _fields_ = [("configs", ctypes.c_uint64), ("bv_tests", ctypes.c_uint64), ("tri_tests", ctypes.c_uint64),
                 ("launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double)]
@@ -51,7 +57,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
-           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh"]
+           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates"]
 
 _lib = None
 
@@ -98,6 +104,8 @@ def load_library():
     lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
     lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(cd)]
+    lib.cc_query_get_certificates.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_debug_pair_rates.argtypes = [vp, ci, ci, vp, ci, ci, ci, cd, cd, vp, vp, ctypes.POINTER(ci)]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_scene_synchronize.argtypes = [vp]
@@ -187,6 +195,14 @@ class BoundQuery(object):
         self.dropped_pairs = d.value
         self.certificate_build_ms = ms.value
         return n.value + d.value
+
+    def certificates(self):
+        """cc_query_get_certificates: what the last certificate build proved (a list of cc_certificate records)."""
+        n = ctypes.c_int(0)
+        self.checker._ck(self.lib.cc_query_get_certificates(self.handle, None, 0, ctypes.byref(n)))
+        arr = (cc_certificate * max(1, n.value))()
+        self.checker._ck(self.lib.cc_query_get_certificates(self.handle, ctypes.addressof(arr), n.value, ctypes.byref(n)))
+        return [arr[i] for i in range(n.value)]
 
     def link_of(self, qindex):
         """Query link index -> Link object (a grabbed body's link when qindex >= the body's link count)."""

@@ -30,8 +30,8 @@ std::vector<int> path_to_root(const HBody& B, const ChainInfo& ci, int l)
 double joint_span(const cc_joint& j)     // largest change of |child origin - parent origin| contribution of one joint
 {
     double s = norm3(j.left + 4) + norm3(j.right + 4);
-    // (a mimic joint's value may sit up to 5e-4 outside its limits, kinbody.cpp:2326-2386: 1e-3 covers that)
-    if (!j.is_static && j.type == CC_JOINT_PRISMATIC) s += norm3(j.axis) * (std::max(fabs(j.lower), fabs(j.upper)) + (j.mimic_dof >= 0 ? 1e-3 : 0.0));
+    // (a mimic joint's value may sit up to g_fEpsilonEvalJointLimit = 1.8e-10 outside its limits, kinbody.cpp:2326-2386)
+    if (!j.is_static && j.type == CC_JOINT_PRISMATIC) s += norm3(j.axis) * (std::max(fabs(j.lower), fabs(j.upper)) + (j.mimic_dof >= 0 ? 1e-9 : 0.0));
     return s;
 }
 
@@ -102,6 +102,35 @@ bool pair_rates(const HBody& B, const ChainInfo& ci, const std::vector<int>& col
 
 extern "C" {
 static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, const std::vector<uint8_t>& dynamic, bool with_fk);
+
+// Diagnostic, no device needed: the displacement rates the certificates rest on, for one link pair of a joint tree given the way
+// cc_body_set_kinematics takes it.  *out_n = number of varying DOFs (1 or 2) with out_dofs / out_k filled, 0 when the pair
+// cannot be tabulated.  The CPU tests check K against finite differences of the FK restatement (tests/test_pair_tables.py).
+int cc_debug_pair_rates(const cc_joint* joints, int njoints, int nlinks, const int32_t* col_of_dof, int ndof, int link_a, int link_b,
+                        double radius_a, double radius_b, int32_t* out_dofs, double* out_k, int* out_n)
+{
+    if (!joints || njoints <= 0 || nlinks <= 0 || !col_of_dof || !out_dofs || !out_k || !out_n || link_a < 0 || link_a >= nlinks ||
+        link_b >= nlinks)
+        return fail(CC_ERR_INVALID, "cc_debug_pair_rates: bad arguments");
+    HBody B;
+    B.links.resize(nlinks);
+    B.ndof = ndof;
+    B.joints.assign(joints, joints + njoints);
+    ChainInfo ci;
+    ci.parent_joint.assign(nlinks, -1);
+    for (int k = 0; k < njoints; ++k) {
+        if (joints[k].child_link < 0 || joints[k].child_link >= nlinks || joints[k].parent_link < 0 || joints[k].parent_link >= nlinks)
+            return fail(CC_ERR_INVALID, "cc_debug_pair_rates: joint link out of range");
+        ci.parent_joint[joints[k].child_link] = k;
+    }
+    std::vector<int> cols(col_of_dof, col_of_dof + ndof), dofs;
+    std::vector<double> K;
+    *out_n = 0;
+    if (!pair_rates(B, ci, cols, link_a, link_b, radius_a, radius_b, dofs, K)) return CC_OK;
+    *out_n = (int)dofs.size();
+    for (size_t i = 0; i < dofs.size(); ++i) { out_dofs[i] = dofs[i]; out_k[i] = K[i]; }
+    return CC_OK;
+}
 }
 
 static int build_pair_tables(cc_query* Q)
@@ -123,6 +152,7 @@ static int build_pair_tables(cc_query* Q)
     auto rad = [&](int l) { if (radius_cache[l] < 0) radius_cache[l] = link_radius(B->links[l]); return radius_cache[l]; };
 
     std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
+    Q->certs.clear();
     // safety margin of every certificate: FP32 error of the distance kernel (~1e-5 m) + the 1e-4 m contact band, plus the
     // conservative margin of the triangle test when the caller has set one (pairs closer than it count as touching)
     Q->cert_tri_eps = S->tri_eps;
@@ -275,12 +305,24 @@ static int build_pair_tables(cc_query* Q)
             const Cand& c = cands[order[k]];
             size_t nfree = 0;
             std::vector<uint32_t> tb((ncell + 31) / 32, 0u);
-            double dmin = 1e30;
+            double dmin = 1e30, slack = 1e30;
+            int tight = -1;
             for (int i = 0; i < ncell; ++i) {
                 const double d = dist[(size_t)i * npd + dp];
                 dmin = std::min(dmin, d);
-                if (d > delta[k] + margin) { tb[i >> 5] |= 1u << (i & 31); ++nfree; }
+                if (d > delta[k] + margin) {
+                    tb[i >> 5] |= 1u << (i & 31); ++nfree;
+                    if (d - delta[k] - margin < slack) { slack = d - delta[k] - margin; tight = i; }
+                }
             }
+            // what was proven, for cc_query_get_certificates (the adversarial tests aim at the tightest cells)
+            cc_certificate rec;
+            memset(&rec, 0, sizeof(rec));
+            rec.pair = c.p; rec.col0 = col_of_dof[dofs[0]]; rec.col1 = j1 ? col_of_dof[dofs[1]] : -1;
+            rec.n0 = n0; rec.n1 = n1; rec.certified_cells = (int32_t)nfree; rec.tightest_cell = tight;
+            rec.lo0 = j0.lower; rec.width0 = w0; rec.lo1 = j1 ? j1->lower : 0.0; rec.width1 = w1;
+            rec.k0 = c.K[0]; rec.k1 = nd == 2 ? c.K[1] : 0.0; rec.delta = delta[k]; rec.margin = margin;
+            rec.min_slack = slack; rec.min_distance = dmin;
             if (getenv("CC_DEBUG_TABLES"))
                 fprintf(stderr, "[tables] %s x %s/%s: %d DOF, grid %d x %d, K = %.3f %.3f, delta = %.4f m, min dist = %.4f m, certified cells %.1f%%\n",
                         B->links[c.a].name.c_str(), c.cls == 1 ? B->name.c_str() : S->bodies[c.ob]->name.c_str(),
@@ -288,9 +330,10 @@ static int build_pair_tables(cc_query* Q)
                         delta[k], dmin, 100.0 * nfree / ncell);
             // never in contact inside the joint limits: the pair can leave the plan — unless a circular DOF covers only part of
             // the circle (SetDOFValues does not clamp those, so values outside the grid exist): then it keeps a table
-            if (nfree == (size_t)ncell && !partial_circle(&j0) && !partial_circle(j1)) { dropped[c.p] = 1; continue; }
+            if (nfree == (size_t)ncell && !partial_circle(&j0) && !partial_circle(j1)) { dropped[c.p] = 1; rec.dropped = 1; Q->certs.push_back(rec); continue; }
             if (!final) { undecided.push_back(order[k]); continue; }
             if (nfree * 10 < (size_t)ncell || bits.size() + tb.size() > max_bits_words) continue;
+            Q->certs.push_back(rec);
             ccdev::PairTable T;
             memset(&T, 0, sizeof(T));
             T.col0 = col_of_dof[dofs[0]]; T.col1 = j1 ? col_of_dof[dofs[1]] : -1;
@@ -381,6 +424,11 @@ static int maybe_build_tables(cc_query* q, int n)
     static const long long after = getenv("CC_TUNE_TABLES_AFTER") ? atoll(getenv("CC_TUNE_TABLES_AFTER")) : 16384;
     q->fk_configs_seen += (uint64_t)n;
     if ((long long)q->fk_configs_seen < after) return CC_OK;
+    // build_pair_tables proves separation from the LIVE scene state (link poses, inactive DOF values, a nested pairs query);
+    // the batched kernels check against the snapshot the query captured at cc_query_create / cc_query_refresh.  The two are the
+    // same only while no body has been moved since: otherwise wait for the caller's cc_query_refresh (certificates already in
+    // force stay valid: they were proven on the snapshot the query still uses, and a refresh drops them).
+    if (q->pose_epoch != q->scene->pose_epoch) return CC_OK;
     const auto t0 = std::chrono::steady_clock::now();
     const int rc = build_pair_tables(q);
     q->cert_build_ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

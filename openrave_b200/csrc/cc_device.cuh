@@ -32,6 +32,7 @@
 #define CC_TRI_T2 8      // survivors that trigger an edge-axes pass
 #endif
 #include <stdint.h>
+#include "cc_epsilons.h"
 
 namespace ccdev {
 
@@ -421,8 +422,10 @@ __device__ __forceinline__ Xf joint_transform(const FkStep& st, const double* __
         const double ev = st.a * v + st.b;
         v = ev;
         if (!(st.flags & 4)) {
-            if (ev < st.lower) { if (ev >= st.lower - 1e-7) v = st.lower; else if (ev < st.lower - 5e-4) v = st.lower; }
-            else if (ev > st.upper) { if (ev <= st.upper + 1e-7) v = st.upper; else if (ev > st.upper + 5e-4) v = st.upper; }
+            // kinbody.cpp:2326-2375: within g_fEpsilonJointLimit of a limit -> the limit; farther out than g_fEpsilonEvalJointLimit
+            // -> clamped (CLA_CheckLimits); the sliver in between keeps the evaluated value, as in the reference
+            if (ev < st.lower) { if (ev >= st.lower - CC_EPSILON_JOINT_LIMIT) v = st.lower; else if (ev < st.lower - CC_EPSILON_EVAL_JOINT_LIMIT) v = st.lower; }
+            else if (ev > st.upper) { if (ev <= st.upper + CC_EPSILON_JOINT_LIMIT) v = st.upper; else if (ev > st.upper + CC_EPSILON_EVAL_JOINT_LIMIT) v = st.upper; }
         }
     }
     Xf J; J.q0 = 1; J.q1 = J.q2 = J.q3 = 0; J.tx = J.ty = J.tz = 0;

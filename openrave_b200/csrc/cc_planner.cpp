@@ -18,6 +18,7 @@
 // smoother candidate never depend on a collision result inside the same request, so the outcome equals the serial loop's.
 // The nearest-neighbour structure is an exact linear scan (the reference's cover tree, rplanners.h:170-860, returns the
 // same node up to ties); insertion refuses a node closer than 0.001 * step to its nearest neighbour like _InsertRecursive.
+#include "cc_epsilons.h"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -42,10 +43,10 @@ namespace {
 int fail(int code, const char* msg) { cc_internal_set_error(msg); return code; }
 
 constexpr double kPi = 3.14159265358979323846;
-constexpr double kEpsilon = 1e-15;                               // g_fEpsilon for dReal = double (openrave.h:130)
-const double kEpsilonLinear = std::pow(kEpsilon, 0.9);           // libopenrave.h:140
-const double kEpsilonJointLimit = std::pow(kEpsilon, 0.8);       // libopenrave.h:141
-const double kEpsilonDotProduct = std::pow(kEpsilon, 0.8);       // rrt.h:22
+constexpr double kEpsilon = CC_EPSILON;                          // g_fEpsilon for dReal = double (openrave.h:130)
+constexpr double kEpsilonLinear = CC_EPSILON_LINEAR;             // libopenrave.h:140
+constexpr double kEpsilonJointLimit = CC_EPSILON_JOINT_LIMIT;    // libopenrave.h:141
+constexpr double kEpsilonDotProduct = CC_EPSILON_JOINT_LIMIT;    // RavePow(g_fEpsilon, 0.8), rrt.h:22
 enum Interval { IT_Open = 0, IT_OpenStart = 1, IT_OpenEnd = 2, IT_Closed = 3 };
 
 // ------------------------------------------------------------------------------------------------ configuration space

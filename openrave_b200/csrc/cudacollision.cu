@@ -123,6 +123,8 @@ struct cc_scene {
     bool ev_pending = false;
     float tri_eps = 0.0f;
     bool pair_tables = true;                // certified free-space tables for pairs that depend on <= 2 active DOFs
+    uint64_t pose_epoch = 0;                // bumped by cc_body_set_link_transforms / cc_body_set_dof_values: a bound query whose
+                                            // snapshot is older than this must not prove anything from the live scene state
     ~cc_scene()
     {
         for (HBody* b : bodies) delete b;
@@ -371,6 +373,8 @@ struct cc_query {
     float cert_tri_eps = 0.0f;               // cc_scene_set_tri_epsilon value the certificates were built with
     std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
     uint64_t fk_configs_seen = 0;
+    uint64_t pose_epoch = 0;                 // cc_scene::pose_epoch when the query captured its snapshot (create / refresh)
+    std::vector<cc_certificate> certs;       // what the last certificate build proved, pair by pair (grid certificates only)
     int ntables = 0;
     DevBuf<int32_t> d_pair_table;            // mainl order
     DevBuf<int32_t> d_pair_table_split[3];   // split orders
@@ -816,6 +820,7 @@ int cc_body_set_link_transforms(cc_scene* s, int body, const double* T8)
     HBody* b = get_body(s, body);
     if (!b || !T8) return fail(CC_ERR_INVALID, "bad arguments");
     for (size_t i = 0; i < b->links.size(); ++i) memcpy(b->links[i].xf, T8 + 8 * i, 8 * sizeof(double));
+    s->pose_epoch++;
     return CC_OK;
 }
 
@@ -888,6 +893,7 @@ int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof
     HBody* b = get_body(s, body);
     if (!b || ndof != b->ndof || (ndof > 0 && !values)) return fail(CC_ERR_INVALID, "bad arguments");
     b->dofvals.assign(values, values + ndof);
+    s->pose_epoch++;
     return CC_OK;
 }
 
@@ -1234,6 +1240,7 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     Q->moves = moves;
     Q->p_full = p_full;
     Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size();     // not with grabbed links (their chain is not walked below)
+    Q->pose_epoch = S->pose_epoch;           // everything below reads the live scene state: that IS the query's snapshot
     int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
     if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
@@ -1418,6 +1425,7 @@ static int reset_certificates(cc_query* q)
 {
     const bool dropped = q->p_main.size() != q->p_main_all.size();
     q->ntables = 0; q->ndropped = 0; q->tables_done = false; q->fk_configs_seen = 0;
+    q->certs.clear();
     if (dropped) {
         CC_CUDA(cudaSetDevice(q->scene->device));
         CC_CUDA(cudaDeviceSynchronize());
@@ -1446,6 +1454,7 @@ int cc_query_refresh(cc_query* q)
     CC_CUDA(cudaSetDevice(S->device));
     CC_CUDA(cudaDeviceSynchronize());
     memcpy(q->base, B->links[0].xf, sizeof(q->base));
+    q->pose_epoch = S->pose_epoch;
     q->center[0] = q->base[4]; q->center[1] = q->base[5]; q->center[2] = q->base[6];
     for (int d = 0; d < B->ndof && d < (int)q->col_of_dof.size(); ++d) if (q->col_of_dof[d] >= 0) q->cur_active[q->col_of_dof[d]] = B->dofvals[d];
     // certificates depend on the captured poses: back to the full pair list, to be rebuilt after the next 16k configurations
@@ -1743,6 +1752,14 @@ int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_droppe
     if (out_tables) *out_tables = q->ntables > 0 ? q->ntables : 0;
     if (out_dropped) *out_dropped = q->ndropped;
     if (out_build_ms) *out_build_ms = q->cert_build_ms;
+    return CC_OK;
+}
+
+int cc_query_get_certificates(const cc_query* q, cc_certificate* out, int max_records, int* out_count)
+{
+    if (!q || !out_count || max_records < 0 || (max_records > 0 && !out)) return fail(CC_ERR_INVALID, "bad arguments");
+    *out_count = (int)q->certs.size();
+    for (int i = 0; i < max_records && i < (int)q->certs.size(); ++i) out[i] = q->certs[i];
     return CC_OK;
 }
 

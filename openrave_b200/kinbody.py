@@ -25,9 +25,12 @@ import numpy as np
 
 from . import ravemath as rm
 
-G_EPSILON_LINEAR = 1e-7              # g_fEpsilonLinear (double build)
-G_EPSILON_JOINT_LIMIT = 1e-7        # g_fEpsilonJointLimit
-G_EPSILON_EVAL_JOINT_LIMIT = 5e-4   # g_fEpsilonEvalJointLimit
+# dReal = double: g_fEpsilon = 1e-15 (include/openrave/openrave.h:130), the derived tolerances are RavePow(g_fEpsilon, x)
+# (src/libopenrave/libopenrave.h:140-142); the same values live in csrc/cc_epsilons.h for the device and the planner host
+G_EPSILON = 1e-15
+G_EPSILON_LINEAR = G_EPSILON ** 0.9              # g_fEpsilonLinear          3.16e-14
+G_EPSILON_JOINT_LIMIT = G_EPSILON ** 0.8         # g_fEpsilonJointLimit      1e-12
+G_EPSILON_EVAL_JOINT_LIMIT = G_EPSILON ** 0.65   # g_fEpsilonEvalJointLimit  1.78e-10
 
 AO_Enabled = 1       # include/openrave/kinbody.h:3298
 AO_ActiveDOFs = 2    # kinbody.h:3299

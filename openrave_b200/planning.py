@@ -23,7 +23,7 @@ CFO_CheckEnvCollisions, CFO_CheckSelfCollisions = 1, 2                    # plan
 CFO_CheckWithPerturbation = 0x00010000                                    # planner.h:37
 CFO_FillCheckedConfiguration = 0x00020000                                 # planner.h:38
 CFO_StateSettingError = 0x80000000                                        # planner.h:44
-G_EPSILON_JOINT_LIMIT = 1e-7                                               # g_fEpsilonJointLimit
+G_EPSILON_JOINT_LIMIT = 1e-15 ** 0.8                                       # g_fEpsilonJointLimit (libopenrave.h:141)
 G_EPSILON_LINEAR = 1e-15 ** 0.9                                            # g_fEpsilonLinear (libopenrave.h:140)
 
 

@@ -997,8 +997,11 @@ static void forward_kinematics(const Body& b, const double* vals_in, const Xf& b
             double ev = j.mimic_a * vals[j.mimic_dof] + j.mimic_b;
             v = ev;
             if (!j.is_circular) {
-                if (ev < j.lower) { if (ev >= j.lower - 1e-7) v = j.lower; else if (ev < j.lower - 5e-4) v = j.lower; }
-                else if (ev > j.upper) { if (ev <= j.upper + 1e-7) v = j.upper; else if (ev > j.upper + 5e-4) v = j.upper; }
+                // g_fEpsilon = 1e-15 for dReal = double (openrave.h:130); g_fEpsilonJointLimit = RavePow(g_fEpsilon, 0.8),
+                // g_fEpsilonEvalJointLimit = RavePow(g_fEpsilon, 0.65) (libopenrave.h:141-142); rules of kinbody.cpp:2326-2375
+                static const double eps_jl = pow(1e-15, 0.8), eps_eval = pow(1e-15, 0.65);
+                if (ev < j.lower) { if (ev >= j.lower - eps_jl) v = j.lower; else if (ev < j.lower - eps_eval) v = j.lower; }
+                else if (ev > j.upper) { if (ev <= j.upper + eps_jl) v = j.upper; else if (ev > j.upper + eps_eval) v = j.upper; }
             }
         } else if (j.dof_index >= 0) {
             v = vals[j.dof_index];

@@ -83,3 +83,34 @@ def test_moving_obstacle_and_inactive_dofs():
     fk = cc.ForwardKinematicsBatch(robot2, q[:16], active=active)
     ref_fk = orc.check_batch(robot, q[:16], active=active, want_fk=True)["fk"]
     assert np.abs(fk[..., :7] - ref_fk[..., :7]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_certificates_are_never_proven_on_poses_the_query_does_not_use():
+    """A raw C-ABI caller moves a body after binding and does NOT call cc_query_refresh: the bound query keeps checking its
+    snapshot (include/cudacollision.h), so the free-space certificates — which are proven from the live scene state — must not
+    be built until the refresh (they would drop pairs on poses the query does not use)."""
+    import ctypes
+    from openrave_b200 import flatten
+    (env, robot, orc, active), (env2, robot2, cc, _) = _pair(True)
+    q = sample_configs(robot, 40000, seed=67, active=active)
+    bq = cc.bind(robot2, active)
+    small = bq.check(q[:2000])                                              # < 16k configurations: no certificates yet
+    assert bq.table_count() == 0
+    # behind the harness's back: park mug1 next to wam4 in the scene only
+    mug = [b for b in env2.GetBodies() if b.name == "mug1"][0]
+    moved = rm.t_mul(robot2.GetLink("wam4").t, (rm.IDENT_Q, (0.0, 0.0, 0.25)))
+    T = flatten.transforms8([moved for _ in mug.links])
+    assert cc.lib.cc_body_set_link_transforms(cc.scene, cc.body_id(mug), T.ctypes.data_as(ctypes.c_void_p)) == 0
+    stale = bq.check(q)                                                     # crosses 16k: would build certificates
+    assert bq.table_count() == 0                                            # ... but the snapshot is stale: not built
+    assert np.array_equal(stale[0][:2000], small[0])                        # and the answers are still the snapshot's
+    bq.refresh()
+    fresh = bq.check(q)
+    assert bq.table_count() > 0
+    assert (fresh[0] != stale[0]).any()                                     # the moved mug now matters
+    mug1 = [b for b in env.GetBodies() if b.name == "mug1"][0]
+    mug1.SetTransform(rm.t_mul(robot.GetLink("wam4").t, (rm.IDENT_Q, (0.0, 0.0, 0.25))))
+    ref = orc.check_batch(robot, q[:3000], active=active, want_band=True)
+    band = (ref["near"] != 0) | ((ref["verdict"] != 0) & (ref["penetration"] <= 1e-4))
+    assert not ((fresh[0][:3000] != ref["verdict"]) & ~band).any()
