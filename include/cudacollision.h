@@ -302,6 +302,16 @@ int cc_query_get_certificates(const cc_query* q, cc_certificate* out, int max_re
 int cc_query_trace_work(cc_query* q, int enabled);
 int cc_query_get_work_trace(cc_query* q, uint32_t* out_iterations, int n);
 
+/* Diagnostics: the per-chunk timeline of the NEXT batched calls.  A big batch is cut into chunks that alternate between two
+ * internal streams ("lanes") so that the tail of one chunk's persistent traversal kernel overlaps the next chunk's kernels;
+ * with tracing on, three timed events per chunk are recorded on the chunk's lane.  cc_scene_get_timeline (synchronises)
+ * returns, for every chunk of the last traced call, milliseconds since the call's start event: {the lane became free for this
+ * chunk, its FK kernel ended, its traversal kernel ended} and the chunk's lane.  Overlapping [FK end, traversal end] intervals
+ * of consecutive chunks are the two-stream overlap bench.py's roofline accounting relies on (profiles/ holds the records). */
+int cc_scene_trace_timeline(cc_scene* s, int enabled);
+int cc_scene_get_timeline(cc_scene* s, double* out_ms /* [chunks][3] */, int32_t* out_lane /* [chunks], may be NULL */,
+                          int max_chunks, int* out_chunks);
+
 /* Measured FP32 FMA throughput of a device in TFLOP/s (a short FMA-chain kernel): the denominator of the compute-side
  * roofline figure bench.py reports next to the memory-side one. */
 int cc_device_fp32_peak(int cuda_device, double* out_tflops);

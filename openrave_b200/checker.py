@@ -57,7 +57,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
-           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates"]
+           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates",
+           "cc_scene_trace_timeline", "cc_scene_get_timeline"]
 
 _lib = None
 
@@ -104,6 +105,8 @@ def load_library():
     lib.cc_tolerance_poses.argtypes = [vp, vp, ci, ci, cd, vp]
     lib.cc_scene_set_pair_tables.argtypes = [vp, ci]
     lib.cc_query_get_table_count.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(cd)]
+    lib.cc_scene_trace_timeline.argtypes = [vp, ci]
+    lib.cc_scene_get_timeline.argtypes = [vp, vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_query_get_certificates.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_debug_pair_rates.argtypes = [vp, ci, ci, vp, ci, ci, ci, cd, cd, vp, vp, ctypes.POINTER(ci)]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
@@ -596,6 +599,18 @@ class CudaCollisionChecker(object):
         self._ck(self.lib.cc_scene_get_stats(self.scene, ctypes.byref(st)))
         return dict(configs=st.configs, bv_tests=st.bv_tests, tri_tests=st.tri_tests, launches=st.launches,
                     last_kernel_ms=st.last_kernel_ms)
+
+    def TraceTimeline(self, enabled=True):
+        self._ck(self.lib.cc_scene_trace_timeline(self.scene, 1 if enabled else 0))
+
+    def GetTimeline(self):
+        """Per-chunk timeline of the last traced batched call: (ms [chunks, 3] {lane free, FK end, traversal end}, lane [chunks])."""
+        n = ctypes.c_int(0)
+        self._ck(self.lib.cc_scene_get_timeline(self.scene, None, None, 0, ctypes.byref(n)))
+        ms = np.zeros((max(n.value, 1), 3), dtype=np.float64)
+        lane = np.zeros(max(n.value, 1), dtype=np.int32)
+        self._ck(self.lib.cc_scene_get_timeline(self.scene, _ptr(ms), _ptr(lane), n.value, ctypes.byref(n)))
+        return ms[:n.value], lane[:n.value]
 
     def SetCounters(self, enabled):
         self._ck(self.lib.cc_scene_set_counters(self.scene, 1 if enabled else 0))

@@ -123,11 +123,16 @@ struct cc_scene {
     bool ev_pending = false;
     float tri_eps = 0.0f;
     bool pair_tables = true;                // certified free-space tables for pairs that depend on <= 2 active DOFs
+    // per-chunk timeline of the last batched call (cc_scene_trace_timeline): 3 timed events per chunk on the chunk's lane stream
+    bool trace_timeline = false;
+    std::vector<cudaEvent_t> tl_events;
+    std::vector<int> tl_lane;               // lane of every chunk of the last traced call
     uint64_t pose_epoch = 0;                // bumped by cc_body_set_link_transforms / cc_body_set_dof_values: a bound query whose
                                             // snapshot is older than this must not prove anything from the live scene state
     ~cc_scene()
     {
         for (HBody* b : bodies) delete b;
+        for (cudaEvent_t e : tl_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -487,9 +492,18 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
     int chunk = (int)std::min<size_t>(131072, std::max<size_t>(1024, ((size_t)1 << 29) / per_cfg));
     if (n >= 262144) chunk = std::min(chunk, std::max(65536, ((n + 3) / 4 + 127) / 128 * 128));   // smaller chunks only multiply tails
+    static const int tune_chunk = getenv("CC_TUNE_CHUNK") ? atoi(getenv("CC_TUNE_CHUNK")) : 0;      // profiling knob: configurations per chunk
+    if (tune_chunk > 0) chunk = (tune_chunk + 127) / 128 * 128;
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     const int nchunks = (n + chunk - 1) / chunk;
     const bool overlap = nchunks >= 2;
+    static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
+                                                                                                     // chunk of each lane (timing without FK)
+    const bool timeline = S->trace_timeline && !fk_only;
+    if (timeline) {
+        while ((int)S->tl_events.size() < 3 * nchunks) { cudaEvent_t e; CC_CUDA(cudaEventCreate(&e)); S->tl_events.push_back(e); }
+        S->tl_lane.assign(nchunks, 0);
+    }
     {
         int rc = ensure_scratch(Q, pl, chunk, overlap ? 2 : 1);
         if (rc != CC_OK) return rc;
@@ -596,9 +610,13 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.xf32 = Q->d_xf32[k].p; P.aabb = Q->d_aabb[k].p; P.fksave = Q->d_fksave[k].p;
         P.counters = Q->d_counters[k].p;
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
-        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
-        CC_CUDA(cudaGetLastError());
-        S->stats.launches++;
+        if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
+        if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
+            ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
+            CC_CUDA(cudaGetLastError());
+            S->stats.launches++;
+        }
+        if (timeline) CC_CUDA(cudaEventRecord(S->tl_events[3 * ci + 1], cs));
         if (fk_only) {
             if (hio) CC_CUDA(copy_out(off, m, cs));
             continue;
@@ -618,6 +636,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         }
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
+        if (timeline) CC_CUDA(cudaEventRecord(S->tl_events[3 * ci + 2], cs));
         if (hio) {
             if (pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
             pend_off = off; pend_m = m; pend_cs = cs;
@@ -1702,6 +1721,32 @@ int cc_scene_synchronize(cc_scene* s)
     CC_CUDA(cudaSetDevice(s->device));
     CC_CUDA(cudaDeviceSynchronize());
     return check_err_flag(s);
+}
+
+int cc_scene_trace_timeline(cc_scene* s, int enabled)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    s->trace_timeline = enabled != 0;
+    if (!enabled) s->tl_lane.clear();
+    return CC_OK;
+}
+
+int cc_scene_get_timeline(cc_scene* s, double* out_ms, int32_t* out_lane, int max_chunks, int* out_chunks)
+{
+    if (!s || !out_chunks || max_chunks < 0 || (max_chunks > 0 && !out_ms)) return fail(CC_ERR_INVALID, "bad arguments");
+    CC_CUDA(cudaSetDevice(s->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    const int nc = (int)s->tl_lane.size();
+    *out_chunks = nc;
+    for (int c = 0; c < nc && c < max_chunks; ++c) {
+        for (int e = 0; e < 3; ++e) {
+            float ms = 0.f;
+            CC_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->tl_events[3 * c + e]));
+            out_ms[3 * c + e] = (double)ms;
+        }
+        if (out_lane) out_lane[c] = s->tl_lane[c];
+    }
+    return CC_OK;
 }
 
 int cc_scene_set_counters(cc_scene* s, int enabled)
