@@ -133,8 +133,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_baseline(env, robot, q, budget_s=12.0, kind=None, gpu=None):
-    """Single-thread pqprave-equivalent configs/s on a bounded prefix of the same batch."""
+def cpu_baseline(env, robot, q, budget_s=12.0, kind=None):
+    """Single-thread pqprave-equivalent configs/s on a bounded prefix of the same batch, and the reference's own work counters
+    (NumBVTests / NumTriTests per configuration) the algorithmic roofline figure is defined from."""
     import oracle
     if kind is None:
         kind = "reference" if oracle.available("reference") else "port"
@@ -146,27 +147,30 @@ def cpu_baseline(env, robot, q, budget_s=12.0, kind=None, gpu=None):
     secs, _ = orc.time_batch(robot, q[:m])
     ref = orc.check_batch(robot, q[:min(m, 2000)])
     cnt = ref["counters"].astype(np.float64)
-    parity = None
-    if gpu is not None:
-        # SURVEY.md 8d parity stats on the same prefix: verdict bits + first colliding pairs of the CUDA path against the CPU arm;
-        # a differing configuration is classified with the oracle's contact band (separation / penetration <= 1e-4 m)
-        k = len(ref["verdict"])
-        bad = gpu["verdict"][:k] != ref["verdict"]
-        fe = gpu["first_env"][:k].copy()
-        hit = fe[:, 0] >= 0
-        fe[hit, 1] = [orc._ids[id(gpu["checker"].body_from_id(b))] for b in fe[hit, 1]]       # body ids of the two harnesses differ
-        pair_bad = ~bad & ((fe != ref["first_env"]).any(axis=1) | (gpu["first_self"][:k] != ref["first_self"]).any(axis=1))
-        idx = np.nonzero(bad | pair_bad)[0]
-        in_band = 0
-        if len(idx):
-            b = orc.check_batch(robot, q[idx], want_band=True)
-            in_band = int(((b["near"] != 0) | ((b["verdict"] != 0) & (b["penetration"] <= 1e-4))).sum())
-        parity = {"compared": int(k), "verdict_and_pairs_identical": int(k - len(idx)), "verdict_differs": int(bad.sum()),
-                  "first_pair_differs": int(pair_bad.sum()), "differing_inside_1e-4m_band": in_band,
-                  "differing_outside_band": int(len(idx) - in_band), "against": "oracle (%s)" % kind}
     return {"value": m / secs, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": "first %d of the %d seeded configs, 1 thread, %.1f s" % (m, len(q), secs),
-            "fclrave": "not runnable here: FCL is not part of the reference tree or of this image (SURVEY.md 8d)"}, cnt.mean(axis=0), parity
+            "fclrave": "not runnable here: FCL is not part of the reference tree or of this image (SURVEY.md 8d)"}, cnt.mean(axis=0)
+
+
+def parity_record(workload, cc, robot, q, rate_1core, budget_s=25.0):
+    """SURVEY.md 8d parity stats, live: the CUDA path against the CPU oracle on a prefix of the timed batch sized to ~budget_s of
+    wall clock on ALL host cores (contact-band classifier on for every configuration), plus the committed full-size sweep of
+    this workload (tests/parity_sweep.py -> profiles/r02_parity_<workload>.json) when there is one."""
+    from oracle import parity
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    m = int(min(len(q), max(2000, 0.4 * rate_1core * workers * budget_s)))      # the band classifier roughly doubles the cost
+    got = cc.CheckCollisionBatch(robot, q[:m])
+    ref = parity.oracle_pass(workload, q[:m], workers=workers, want_band=True)
+    rec = parity.compare(got, ref, lambda b: cc.body_from_id(b).name)
+    rec["sample"] = "first %d of the %d seeded configs of the timed batch" % (m, len(q))
+    fp = os.path.join(ROOT, "profiles", "r02_parity_%s.json" % workload)
+    if os.path.isfile(fp):
+        full = json.load(open(fp))
+        rec["full_size_sweep"] = {k: full.get(k) for k in ("compared", "identical", "colliding", "near_contact", "verdict_differs",
+                                                           "first_pair_differs", "mismatch_inside_band", "mismatch_outside_band",
+                                                           "first_pair_mismatch", "against", "oracle_workers")}
+        rec["full_size_sweep"]["source"] = "profiles/r02_parity_%s.json (tests/parity_sweep.py on the GPU box)" % workload
+    return rec
 
 
 def run_reference_arm(args):
@@ -644,11 +648,9 @@ def main():
         base = None
         cnt = None
         if not args.no_cpu_baseline and world == 1:
-            got = cc.CheckCollisionBatch(robot, q_host[:2000])     # the product's answers for the prefix the CPU arm also checks
-            got["checker"] = cc
-            base, cnt, parity = cpu_baseline(env, robot, q_host, gpu=got)
+            base, cnt = cpu_baseline(env, robot, q_host)
+            base["parity"] = parity_record(args.workload, cc, robot, q_host, base["value"])
             line["cpu_baseline"] = base
-            line["parity"] = parity
         if cnt is not None:
             bytes_per_config = cnt[0] * 2 * 64 + cnt[1] * 2 * 36 + 8 * ndof + 16
             achieved = n * bytes_per_config / (kernel_ms / 1000.0) / 1e9
