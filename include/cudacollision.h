@@ -119,6 +119,18 @@ int cc_version(void);
 
 /* ---- scene lifecycle: CollisionCheckerBase ctor / InitEnvironment / DestroyEnvironment (collisionchecker.h:228-229) */
 int cc_scene_create(int cuda_device, cc_scene** out);
+/* One scene replicated on several devices of the box (north_star: "batches shard across the 8 GPUs of one box with the scene
+ * replicated per GPU"; the reference's idiom is one cloned environment per host thread, src/cppexamples/
+ * ormultithreadedplanning.cpp:27-33, src/libopenrave-core/environment-core.h:3657-3662).  The returned handle is used like
+ * any other scene: every scene / body / query call is mirrored onto the replicas (the BVHs are built once and handed over),
+ * and the host-buffer batch entries — cc_check_batch, cc_fk_batch, cc_distance_batch — cut a batch of >= 2 x 16384
+ * configurations into contiguous ranges, one per device, each device copying ITS slice of the caller's buffers in and its
+ * results out (no collective: the consumer is the host; page-locked buffers from cc_host_alloc are portable across the
+ * devices).  Results are bit-identical to the single-device scene's.  Smaller batches, the single-state entries
+ * (cc_check_poses, cc_contacts_poses, ...) and cc_check_batch_device run on cuda_devices[0] only.  A device may be listed
+ * more than once (the replicas then share it: that is how a one-GPU box tests the sharding). */
+int cc_scene_create_multi(const int* cuda_devices, int ndevices, cc_scene** out);
+int cc_scene_get_devices(const cc_scene* s, int* out_devices, int max_devices, int* out_count);
 int cc_scene_destroy(cc_scene* s);
 
 /* ---- InitKinBody / RemoveKinBody (collisionchecker.h:233-237; pqprave: collisionPQP.h:89-122) */

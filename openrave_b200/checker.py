@@ -58,7 +58,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
            "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates",
-           "cc_scene_trace_timeline", "cc_scene_get_timeline"]
+           "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices"]
 
 _lib = None
 
@@ -74,6 +74,8 @@ def load_library():
     vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
     lib.cc_last_error.restype = ctypes.c_char_p
     lib.cc_scene_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.cc_scene_create_multi.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    lib.cc_scene_get_devices.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_scene_destroy.argtypes = [vp]
     lib.cc_scene_add_body.argtypes = [vp, ctypes.c_char_p, ci, ci, ctypes.POINTER(ci)]
     lib.cc_scene_remove_body.argtypes = [vp, ci]
@@ -368,7 +370,11 @@ class CudaCollisionChecker(object):
 
     def _create_scene(self):
         h = ctypes.c_void_p()
-        self._ck(self.lib.cc_scene_create(self.device, ctypes.byref(h)))
+        if isinstance(self.device, (list, tuple)):      # "cudacollision 0,1,2,3": one scene replicated on several devices
+            devs = (ctypes.c_int * len(self.device))(*[int(d) for d in self.device])
+            self._ck(self.lib.cc_scene_create_multi(devs, len(self.device), ctypes.byref(h)))
+        else:
+            self._ck(self.lib.cc_scene_create(self.device, ctypes.byref(h)))
         self.scene = h
 
     def __del__(self):
@@ -762,6 +768,8 @@ def RaveCreateCollisionChecker(env, name):
     """Name-based factory like RaveCreateCollisionChecker(env, name): 'cudacollision [device]'."""
     parts = name.split()
     if parts and parts[0].lower() == "cudacollision":
+        if len(parts) > 1 and "," in parts[1]:
+            return CudaCollisionChecker(env, [int(x) for x in parts[1].split(",") if x != ""])
         dev = int(parts[1]) if len(parts) > 1 else 0
         return CudaCollisionChecker(env, dev)
     return None

@@ -18,6 +18,7 @@
 #include <limits>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cudacollision.h"
@@ -123,6 +124,9 @@ struct cc_scene {
     bool ev_pending = false;
     float tri_eps = 0.0f;
     bool pair_tables = true;                // certified free-space tables for pairs that depend on <= 2 active DOFs
+    // multi-device scene (cc_scene_create_multi): this is the replica on devices[0]; `peers` are full replicas on the other
+    // devices.  Every mutating entry point is mirrored onto them in the same order, so body / link / pair indices agree.
+    std::vector<cc_scene*> peers;
     // per-chunk timeline of the last batched call (cc_scene_trace_timeline): 3 timed events per chunk on the chunk's lane stream
     bool trace_timeline = false;
     std::vector<cudaEvent_t> tl_events;
@@ -131,6 +135,8 @@ struct cc_scene {
                                             // snapshot is older than this must not prove anything from the live scene state
     ~cc_scene()
     {
+        for (cc_scene* p : peers) { cudaSetDevice(p->device); cudaDeviceSynchronize(); delete p; }
+        cudaSetDevice(device);
         for (HBody* b : bodies) delete b;
         for (cudaEvent_t e : tl_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
@@ -411,6 +417,7 @@ struct cc_query {
     DevBuf<uint32_t> d_work;                 // optional per-configuration work trace (cc_query_get_work_trace)
     bool trace_work = false;
     int work_n = 0;
+    std::vector<cc_query*> peers;            // the same query bound on every peer replica of a multi-device scene
     // staging for the host-buffer API
     DevBuf<double> d_q, d_fk;
     DevBuf<uint32_t> d_verdict, d_mask;
@@ -737,6 +744,14 @@ HBody* get_body(cc_scene* s, int body)
     return s->bodies[body];
 }
 
+// mirror a mutating call onto the peer replicas of a multi-device scene
+template <typename F>
+int forward_peers(cc_scene* s, F f)
+{
+    for (cc_scene* p : s->peers) { const int rc = f(p); if (rc != CC_OK) return rc; }
+    return CC_OK;
+}
+
 }  // namespace
 
 
@@ -776,12 +791,37 @@ int cc_scene_create(int cuda_device, cc_scene** out)
     return CC_OK;
 }
 
+int cc_scene_create_multi(const int* cuda_devices, int ndevices, cc_scene** out)
+{
+    if (!out || !cuda_devices || ndevices < 1) return fail(CC_ERR_INVALID, "bad arguments");
+    cc_scene* head = nullptr;
+    int rc = cc_scene_create(cuda_devices[0], &head);
+    if (rc != CC_OK) return rc;
+    for (int i = 1; i < ndevices; ++i) {
+        cc_scene* p = nullptr;
+        rc = cc_scene_create(cuda_devices[i], &p);
+        if (rc != CC_OK) { const std::string keep = g_err; cc_scene_destroy(head); g_err = keep; return rc; }
+        head->peers.push_back(p);
+    }
+    cudaSetDevice(head->device);
+    *out = head;
+    return CC_OK;
+}
+
+int cc_scene_get_devices(const cc_scene* s, int* out_devices, int max_devices, int* out_count)
+{
+    if (!s || !out_count || max_devices < 0 || (max_devices > 0 && !out_devices)) return fail(CC_ERR_INVALID, "bad arguments");
+    *out_count = 1 + (int)s->peers.size();
+    for (int i = 0; i < *out_count && i < max_devices; ++i) out_devices[i] = i == 0 ? s->device : s->peers[i - 1]->device;
+    return CC_OK;
+}
+
 int cc_scene_destroy(cc_scene* s)
 {
     if (!s) return CC_OK;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    delete s;
+    delete s;               // also tears the peer replicas of a multi-device scene down
     return CC_OK;
 }
 
@@ -796,7 +836,7 @@ int cc_scene_add_body(cc_scene* s, const char* name, int nlinks, int is_robot, i
     int id = (int)s->bodies.size() - 1;
     b->attached.push_back(id);
     if (out_body) *out_body = id;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_add_body(p, name, nlinks, is_robot, nullptr); });
 }
 
 int cc_scene_remove_body(cc_scene* s, int body)
@@ -806,7 +846,7 @@ int cc_scene_remove_body(cc_scene* s, int body)
     b->removed = true;
     for (HLink& l : b->links) { l.verts.clear(); l.tris.clear(); l.nodes.clear(); l.tridata.clear(); }
     s->committed = false;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_remove_body(p, body); });
 }
 
 int cc_body_set_link_mesh(cc_scene* s, int body, int link, const char* link_name, const double* v, int nv,
@@ -823,7 +863,7 @@ int cc_body_set_link_mesh(cc_scene* s, int body, int link, const char* link_name
     L.tris.assign(tris, tris + 3 * (size_t)ntris);
     L.dirty = true;
     s->committed = false;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_link_mesh(p, body, link, link_name, v, nv, tris, ntris); });
 }
 
 int cc_body_set_link_enabled(cc_scene* s, int body, const uint8_t* enabled)
@@ -831,7 +871,7 @@ int cc_body_set_link_enabled(cc_scene* s, int body, const uint8_t* enabled)
     HBody* b = get_body(s, body);
     if (!b || !enabled) return fail(CC_ERR_INVALID, "bad arguments");
     for (size_t i = 0; i < b->links.size(); ++i) b->links[i].enabled = enabled[i] != 0;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_link_enabled(p, body, enabled); });
 }
 
 int cc_body_set_link_transforms(cc_scene* s, int body, const double* T8)
@@ -840,10 +880,19 @@ int cc_body_set_link_transforms(cc_scene* s, int body, const double* T8)
     if (!b || !T8) return fail(CC_ERR_INVALID, "bad arguments");
     for (size_t i = 0; i < b->links.size(); ++i) memcpy(b->links[i].xf, T8 + 8 * i, 8 * sizeof(double));
     s->pose_epoch++;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_link_transforms(p, body, T8); });
 }
 
+static int set_attached_one(cc_scene* s, int a, int bb, int attached);
 int cc_body_set_attached(cc_scene* s, int a, int bb, int attached)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    const int rc = set_attached_one(s, a, bb, attached);
+    if (rc != CC_OK) return rc;
+    return forward_peers(s, [&](cc_scene* p) { return set_attached_one(p, a, bb, attached); });
+}
+
+static int set_attached_one(cc_scene* s, int a, int bb, int attached)
 {
     HBody* A = get_body(s, a); HBody* B = get_body(s, bb);
     if (!A || !B) return fail(CC_ERR_INVALID, "bad body");
@@ -873,7 +922,9 @@ int cc_body_set_grabbed(cc_scene* s, int body, int grabbed_body, int link, const
     g->body = grabbed_body; g->link = link;
     g->rel.assign(rel8, rel8 + 8 * G->links.size());
     g->noncolliding.assign(noncolliding, noncolliding + 2 * (size_t)n_noncolliding);
-    return cc_body_set_attached(s, body, grabbed_body, 1);
+    const int rc = set_attached_one(s, body, grabbed_body, 1);
+    if (rc != CC_OK) return rc;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_grabbed(p, body, grabbed_body, link, rel8, noncolliding, n_noncolliding); });
 }
 
 int cc_body_release_grabbed(cc_scene* s, int body, int grabbed_body)
@@ -882,11 +933,11 @@ int cc_body_release_grabbed(cc_scene* s, int body, int grabbed_body)
     if (!B) return fail(CC_ERR_INVALID, "bad body");
     for (size_t i = 0; i < B->grabs.size();) {
         if (grabbed_body < 0 || B->grabs[i].body == grabbed_body) {
-            if (get_body(s, B->grabs[i].body)) cc_body_set_attached(s, body, B->grabs[i].body, 0);
+            if (get_body(s, B->grabs[i].body)) set_attached_one(s, body, B->grabs[i].body, 0);
             B->grabs.erase(B->grabs.begin() + i);
         } else ++i;
     }
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_release_grabbed(p, body, grabbed_body); });
 }
 
 int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints, const uint8_t* affects)
@@ -904,7 +955,7 @@ int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const c
     b->joints.assign(joints, joints + njoints);
     b->affects.assign(affects, affects + (size_t)ndof * nl);
     if ((int)b->dofvals.size() != ndof) b->dofvals.assign(ndof, 0.0);
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_kinematics(p, body, ndof, njoints, joints, affects); });
 }
 
 int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof)
@@ -913,7 +964,7 @@ int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof
     if (!b || ndof != b->ndof || (ndof > 0 && !values)) return fail(CC_ERR_INVALID, "bad arguments");
     b->dofvals.assign(values, values + ndof);
     s->pose_epoch++;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_dof_values(p, body, values, ndof); });
 }
 
 int cc_body_set_nonadjacent_pairs(cc_scene* s, int body, const int32_t* packed, int n)
@@ -926,7 +977,7 @@ int cc_body_set_nonadjacent_pairs(cc_scene* s, int body, const int32_t* packed, 
         if (l0 >= nl || l1 >= nl) return fail(CC_ERR_INVALID, "pair link out of range");
     }
     b->nonadjacent.assign(packed, packed + n);
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_nonadjacent_pairs(p, body, packed, n); });
 }
 
 int cc_scene_commit(cc_scene* s)
@@ -963,6 +1014,22 @@ int cc_scene_commit(cc_scene* s)
     if (!nodes.empty()) CC_CUDA(cudaMemcpy(s->d_nodes.p, nodes.data(), nodes.size() * sizeof(HNode), cudaMemcpyHostToDevice));
     if (!tris.empty()) CC_CUDA(cudaMemcpy(s->d_tris.p, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice));
     s->committed = true;
+    // peer replicas: the trees were just built here, hand them over instead of building them again per device
+    for (cc_scene* p : s->peers) {
+        if (p->bodies.size() != s->bodies.size()) return fail(CC_ERR_STATE, "replicas of a multi-device scene diverged");
+        for (size_t b = 0; b < s->bodies.size(); ++b) {
+            if (p->bodies[b]->links.size() != s->bodies[b]->links.size()) return fail(CC_ERR_STATE, "replicas of a multi-device scene diverged");
+            for (size_t l = 0; l < s->bodies[b]->links.size(); ++l) {
+                HLink& dst = p->bodies[b]->links[l];
+                if (!dst.dirty) continue;
+                dst.nodes = s->bodies[b]->links[l].nodes; dst.tridata = s->bodies[b]->links[l].tridata;
+                dst.dirty = false;
+            }
+        }
+        const int rc = cc_scene_commit(p);
+        if (rc != CC_OK) return rc;
+    }
+    if (!s->peers.empty()) CC_CUDA(cudaSetDevice(s->device));
     return CC_OK;
 }
 
@@ -1269,7 +1336,49 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     return CC_OK;
 }
 
+static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out);
+static int query_create_pairs_one(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out);
+
+}  // extern "C"
+// bind the same query on every peer replica of a multi-device scene
+template <typename F>
+static int bind_on_peers(cc_scene* s, cc_query* Q, F create)
+{
+    for (cc_scene* p : s->peers) {
+        cc_query* pq = nullptr;
+        const int rc = create(p, &pq);
+        if (rc != CC_OK) { const std::string keep = g_err; cc_query_destroy(Q); g_err = keep; return rc; }
+        Q->peers.push_back(pq);
+    }
+    if (!s->peers.empty()) CC_CUDA(cudaSetDevice(s->device));
+    return CC_OK;
+}
+extern "C" {
+
 int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out)
+{
+    if (!s || !out) return fail(CC_ERR_INVALID, "bad arguments");
+    cc_query* Q = nullptr;
+    int rc = query_create_one(s, body, active_dofs, nactive, options, &Q);
+    if (rc != CC_OK) return rc;
+    rc = bind_on_peers(s, Q, [&](cc_scene* p, cc_query** o) { return query_create_one(p, body, active_dofs, nactive, options, o); });
+    if (rc != CC_OK) return rc;
+    *out = Q;
+    return CC_OK;
+}
+
+int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out)
+{
+    if (!s || !out) return fail(CC_ERR_INVALID, "bad arguments");
+    cc_query* Q = nullptr;
+    int rc = query_create_pairs_one(s, body, triples, ntriples, &Q);
+    if (rc != CC_OK) return rc;
+    // explicit pair lists serve the single-state overloads and the certificate builder: one configuration, one device
+    *out = Q;
+    return CC_OK;
+}
+
+static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out)
 {
     HBody* B = get_body(s, body);
     if (!B || !out || nactive < 0 || (nactive > 0 && !active_dofs)) return fail(CC_ERR_INVALID, "bad arguments");
@@ -1395,7 +1504,7 @@ int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nacti
     return CC_OK;
 }
 
-int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out)
+static int query_create_pairs_one(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out)
 {
     HBody* B = get_body(s, body);
     if (!B || !out || ntriples < 0 || (ntriples > 0 && !triples)) return fail(CC_ERR_INVALID, "bad arguments");
@@ -1507,12 +1616,19 @@ int cc_query_refresh(cc_query* q)
         if (changed) CC_CUDA(pl->d_steps.upload(pl->steps));
     }
     CC_CUDA(cudaDeviceSynchronize());
-    return evaluate_hoisted(q);
+    {
+        const int rc = evaluate_hoisted(q);
+        if (rc != CC_OK) return rc;
+    }
+    for (cc_query* pq : q->peers) { const int rc = cc_query_refresh(pq); if (rc != CC_OK) return rc; }
+    if (!q->peers.empty()) CC_CUDA(cudaSetDevice(S->device));
+    return CC_OK;
 }
 
 int cc_query_destroy(cc_query* q)
 {
     if (!q) return CC_OK;
+    for (cc_query* pq : q->peers) cc_query_destroy(pq);
     cudaSetDevice(q->scene->device);
     cudaDeviceSynchronize();
     delete q;
@@ -1597,6 +1713,41 @@ static int run_host(cc_query* q, const double* in, size_t in_doubles, int n, int
     return check_err_flag(S);
 }
 
+// ---- multi-device scenes: a host-buffer batch is range-sharded over the replicas, one host thread per extra device, every
+// replica copying its slice in and its results out of the caller's buffers itself (host consumer, no collective)
+static int shard_count(const cc_query* q, int n)
+{
+    const int G = 1 + (int)q->peers.size();
+    if (G == 1) return 1;
+    static const int min_per = getenv("CC_TUNE_SHARD_MIN") ? std::max(1, atoi(getenv("CC_TUNE_SHARD_MIN"))) : 16384;
+    return std::max(1, std::min(G, n / min_per));        // small batches stay on the first device: a launch costs more than the work
+}
+
+}  // extern "C"
+// f(replica query, first row, rows) -> cc_status; shard 0 runs on the calling thread
+template <typename F>
+static int run_sharded(cc_query* q, int n, F f)
+{
+    const int G = shard_count(q, n);
+    if (G <= 1) return f(q, 0, n);
+    std::vector<int> rcs(G, CC_OK);
+    std::vector<std::string> errs(G);
+    auto begin = [&](int g) { return (int)((long long)n * g / G); };
+    std::vector<std::thread> workers;
+    for (int g = 1; g < G; ++g)
+        workers.emplace_back([&, g]() {
+            rcs[g] = f(q->peers[g - 1], begin(g), begin(g + 1) - begin(g));
+            if (rcs[g] != CC_OK) errs[g] = g_err;
+        });
+    rcs[0] = f(q, 0, begin(1));
+    if (rcs[0] != CC_OK) errs[0] = g_err;
+    for (std::thread& t : workers) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != CC_OK) { g_err = "device " + std::to_string(g == 0 ? q->scene->device : q->peers[g - 1]->scene->device) + ": " + errs[g]; return rcs[g]; }
+    return CC_OK;
+}
+extern "C" {
+
 int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags, uint32_t* verdict, int32_t* first_env,
                    int32_t* first_self, uint32_t* pair_mask)
 {
@@ -1604,8 +1755,12 @@ int cc_check_batch(cc_query* q, const double* dof_values, int n, int flags, uint
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_check_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     const int f = (flags & (CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_ALL_PAIRS)) | ((flags & CC_BATCH_FIRST_HIT) ? ccdev::kFlagFirstHit : 0);
-    { int rc = maybe_build_tables(q, n); if (rc != CC_OK) return rc; }
-    return run_host(q, dof_values, (size_t)n * q->ncols, n, f, false, verdict, first_env, first_self, pair_mask, nullptr);
+    return run_sharded(q, n, [&](cc_query* r, int off, int m) -> int {
+        { int rc = maybe_build_tables(r, m); if (rc != CC_OK) return rc; }
+        return run_host(r, dof_values ? dof_values + (size_t)off * r->ncols : nullptr, (size_t)m * r->ncols, m, f, false,
+                        verdict ? verdict + off : nullptr, first_env ? first_env + off : nullptr, first_self ? first_self + off : nullptr,
+                        pair_mask ? pair_mask + (size_t)off * r->mask_words : nullptr, nullptr);
+    });
 }
 
 int cc_check_poses(cc_query* q, const double* T8, int n, int flags, uint32_t* verdict, int32_t* first_env,
@@ -1621,7 +1776,10 @@ int cc_fk_batch(cc_query* q, const double* dof_values, int n, double* out_T8)
 {
     if (!q || n < 0 || !out_T8 || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics");
-    return run_host(q, dof_values, (size_t)n * q->ncols, n, ccdev::kFlagFkOnly, false, nullptr, nullptr, nullptr, nullptr, out_T8);
+    return run_sharded(q, n, [&](cc_query* r, int off, int m) -> int {
+        return run_host(r, dof_values ? dof_values + (size_t)off * r->ncols : nullptr, (size_t)m * r->ncols, m, ccdev::kFlagFkOnly, false,
+                        nullptr, nullptr, nullptr, nullptr, out_T8 + (size_t)off * r->nq * 8);
+    });
 }
 
 int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, double max_distance, double rel_err,
@@ -1630,15 +1788,19 @@ int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, d
     if (!q || n < 0 || !min_distance || (n > 0 && q->ncols > 0 && !dof_values)) return fail(CC_ERR_INVALID, "bad arguments");
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_distance_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
-    if (!q->dist_ready) {
-        CC_CUDA(cudaSetDevice(q->scene->device));
-        std::vector<uint8_t> all_dynamic(q->nq, 1);
-        int rc = build_plan(q, q->dist, q->p_full, all_dynamic, true);
-        if (rc != CC_OK) return rc;
-        CC_CUDA(cudaDeviceSynchronize());
-        q->dist_ready = true;
-    }
-    return launch_distance(q, q->dist, false, dof_values, n, flags, max_distance, rel_err, abs_err, min_distance, min_pair, closest_points);
+    return run_sharded(q, n, [&](cc_query* r, int off, int m) -> int {
+        if (!r->dist_ready) {
+            CC_CUDA(cudaSetDevice(r->scene->device));
+            std::vector<uint8_t> all_dynamic(r->nq, 1);
+            int rc = build_plan(r, r->dist, r->p_full, all_dynamic, true);
+            if (rc != CC_OK) return rc;
+            CC_CUDA(cudaDeviceSynchronize());
+            r->dist_ready = true;
+        }
+        return launch_distance(r, r->dist, false, dof_values ? dof_values + (size_t)off * r->ncols : nullptr, m, flags, max_distance, rel_err,
+                               abs_err, min_distance + off, min_pair ? min_pair + off : nullptr,
+                               closest_points ? closest_points + (size_t)off * 6 : nullptr);
+    });
 }
 
 int cc_distance_poses(cc_query* q, const double* T8, int n, int flags, double max_distance, double rel_err, double abs_err,
@@ -1718,6 +1880,7 @@ int cc_host_free(void* p)
 int cc_scene_synchronize(cc_scene* s)
 {
     if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    for (cc_scene* p : s->peers) { const int rc = cc_scene_synchronize(p); if (rc != CC_OK) return rc; }
     CC_CUDA(cudaSetDevice(s->device));
     CC_CUDA(cudaDeviceSynchronize());
     return check_err_flag(s);
@@ -1753,7 +1916,7 @@ int cc_scene_set_counters(cc_scene* s, int enabled)
 {
     if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
     s->counters = enabled != 0;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_set_counters(p, enabled); });
 }
 
 int cc_device_fp32_peak(int cuda_device, double* out_tflops)
@@ -1788,7 +1951,7 @@ int cc_scene_set_pair_tables(cc_scene* s, int enabled)
 {
     if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
     s->pair_tables = enabled != 0;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_set_pair_tables(p, enabled); });
 }
 
 int cc_query_get_table_count(const cc_query* q, int* out_tables, int* out_dropped, double* out_build_ms)
@@ -1812,7 +1975,7 @@ int cc_scene_set_tri_epsilon(cc_scene* s, double eps)
 {
     if (!s || eps < 0) return fail(CC_ERR_INVALID, "bad arguments");
     s->tri_eps = (float)eps;
-    return CC_OK;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_set_tri_epsilon(p, eps); });
 }
 
 int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
@@ -1831,6 +1994,14 @@ int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
     CC_CUDA(cudaMemcpy(h, s->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
     s->stats.bv_tests = h[0]; s->stats.tri_tests = h[1];
     *out = s->stats;
+    for (cc_scene* p : s->peers) {       // a multi-device scene reports the sum over its replicas
+        cc_stats ps;
+        const int rc = cc_scene_get_stats(p, &ps);
+        if (rc != CC_OK) return rc;
+        out->configs += ps.configs; out->bv_tests += ps.bv_tests; out->tri_tests += ps.tri_tests; out->launches += ps.launches;
+        out->last_kernel_ms = std::max(out->last_kernel_ms, ps.last_kernel_ms);
+    }
+    if (!s->peers.empty()) CC_CUDA(cudaSetDevice(s->device));
     return CC_OK;
 }
 
