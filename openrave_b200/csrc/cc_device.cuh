@@ -123,6 +123,7 @@ struct Params {
     int32_t* counters;          // [0] traversal work counter
     int32_t* err_flag;          // set when a traversal overflows its spill area
     int32_t cap;
+    int32_t nsave;              // parked poses of the chain program (fused kernel: size of a warp's save area)
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
@@ -378,9 +379,19 @@ __host__ __device__ inline size_t fk_smem_bytes(int nq, int nsteps, int ndyn)
     return (size_t)nsteps * sizeof(FkStep) + (size_t)ndyn * 32 + (size_t)nq * 4;
 }
 
+// Where the FK of ONE configuration puts its results.  cc_fk_kernel: row `c` of the per-chunk scratch (slots contiguous per
+// configuration).  Fused kernel: the warp's private area, slot-major with the 32 configurations of a batch side by side, so the
+// 32 lanes of an FK batch write 1536 / 1024 contiguous bytes per slot.
+struct FkDst {
+    float* xf;  int xf_stride;       // FP32 R|t of slot d at xf + d * xf_stride (12 floats)
+    float* ab;  int ab_stride;       // world AABB of slot d at ab + d * ab_stride (8 floats)
+    double* save;                    // parked pose i, component k at save[i * save_pose_stride + k * save_comp_stride]
+    size_t save_pose_stride, save_comp_stride;
+};
+
 // Emit one link pose: optional FP64 copy-out, FP32 R|t (matrixFromQuat, geometry.h:779-800) and the world AABB
 // of the link's root box, both into the dynamic slot `d` of configuration `c` (d < 0: only the copy-out).
-__device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbox, int c, int l, int d, const Xf& T)
+__device__ __forceinline__ void emit_link(const Params& P, const float* linkbox, const FkDst& D, int c, int l, int d, const Xf& T)
 {
     if (P.fk_out) {
         double* dst = P.fk_out + ((size_t)c * P.nq + l) * 8;
@@ -394,14 +405,14 @@ __device__ __forceinline__ void emit_link(const Params& P, const float* s_linkbo
     R[3] = (float)(il * (T.q1 * T.q2 + T.q0 * T.q3));   R[4] = (float)(1 - qq1 - qq3);                    R[5] = (float)(il * (T.q2 * T.q3 - T.q0 * T.q1));
     R[6] = (float)(il * (T.q1 * T.q3 - T.q0 * T.q2));   R[7] = (float)(il * (T.q2 * T.q3 + T.q0 * T.q1)); R[8] = (float)(1 - qq1 - qq2);
     t[0] = (float)(T.tx - P.center[0]); t[1] = (float)(T.ty - P.center[1]); t[2] = (float)(T.tz - P.center[2]);
-    float4* dst = (float4*)(P.xf32 + ((size_t)c * P.ndyn + d) * 12);
+    float4* dst = (float4*)(D.xf + (size_t)d * D.xf_stride);
     dst[0] = make_float4(R[0], R[1], R[2], R[3]);
     dst[1] = make_float4(R[4], R[5], R[6], R[7]);
     dst[2] = make_float4(R[8], t[0], t[1], t[2]);
-    const float* lb = s_linkbox + 8 * d;
+    const float* lb = linkbox + 8 * d;
     const float reps = 1e-6f;
     const float cx = lb[0], cy = lb[1], cz = lb[2], ex = lb[3], ey = lb[4], ez = lb[5];
-    float4* ab = (float4*)(P.aabb + ((size_t)c * P.ndyn + d) * 8);
+    float4* ab = (float4*)(D.ab + (size_t)d * D.ab_stride);
     ab[0] = make_float4(fmaf(R[0], cx, fmaf(R[1], cy, fmaf(R[2], cz, t[0]))), fmaf(R[3], cx, fmaf(R[4], cy, fmaf(R[5], cz, t[1]))),
                         fmaf(R[6], cx, fmaf(R[7], cy, fmaf(R[8], cz, t[2]))), 0.f);
     ab[1] = make_float4((fabsf(R[0]) + reps) * ex + (fabsf(R[1]) + reps) * ey + (fabsf(R[2]) + reps) * ez,
@@ -443,6 +454,46 @@ __device__ __forceinline__ Xf joint_transform(const FkStep& st, const double* __
     return xf_mul(xf_mul(L, J), xf_load(st.R));       // (L * J) * R, kinbody.cpp:2478
 }
 
+// KinBody::SetDOFValues' joint loop for configuration c (kinbody.cpp:2286-2481): the chain program is walked depth-first with
+// the running transform in registers; poses later branches start from are parked through D.save.
+__device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, const float* linkbox, const int32_t* emit, const FkDst& D, int c)
+{
+    const Xf base = xf_load(P.base);
+    emit_link(P, linkbox, D, c, 0, emit[0], base);                // link 0 keeps its pose (kinbody.cpp:2281)
+    const double* qrow = P.q + (size_t)c * P.ncols;
+    Xf cur = base;
+    const size_t ps = D.save_pose_stride, cs = D.save_comp_stride;
+    for (int s = 0; s < P.nsteps; ++s) {
+        const FkStep& st = steps[s];
+        if (st.load_parent == -1) cur = base;
+        else if (st.load_parent >= 0) {
+            const double* sv = D.save + (size_t)st.load_parent * ps;
+            cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
+            cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
+        }
+        cur = xf_mul(cur, joint_transform(st, qrow));
+        if (st.save >= 0) {
+            double* sv = D.save + (size_t)st.save * ps;
+            sv[0] = cur.q0; sv[cs] = cur.q1; sv[2 * cs] = cur.q2; sv[3 * cs] = cur.q3;
+            sv[4 * cs] = cur.tx; sv[5 * cs] = cur.ty; sv[6 * cs] = cur.tz;
+        }
+        emit_link(P, linkbox, D, c, st.child, emit[st.child], cur);
+    }
+}
+
+// The same for the fused kernel: called by a whole warp, lane i doing configuration first + i of a batch of `count` <= 32, into
+// the warp's private slot-major area.  Not inlined: its FP64 register needs stay out of the traversal loop's allocation.
+__device__ __noinline__ void fk_batch_warp(const Params& P, int first, int count, float* wxf, float* wab, double* wsave)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane >= count) return;
+    FkDst D;
+    D.xf = wxf + lane * 12; D.xf_stride = 32 * 12;
+    D.ab = wab + lane * 8; D.ab_stride = 32 * 8;
+    D.save = wsave + lane; D.save_pose_stride = 7 * 32; D.save_comp_stride = 32;
+    fk_chain(P, P.steps, P.link_box, P.emit_index, D, first + lane);
+}
+
 __global__ void __launch_bounds__(kFkThreads)
 cc_fk_kernel(const __grid_constant__ Params P)
 {
@@ -473,30 +524,20 @@ cc_fk_kernel(const __grid_constant__ Params P)
     if (P.flags & kFlagPoseMode) {
         const double* src = P.q + (size_t)c * P.nq * 8;
         for (int l = 0; l < P.nq; ++l)
-            if (s_emit[l] >= 0) emit_link(P, s_linkbox, c, l, s_emit[l], xf_load(src + 8 * l));
+            if (s_emit[l] >= 0) {
+                FkDst D;
+                D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
+                D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
+                D.save = nullptr; D.save_pose_stride = D.save_comp_stride = 0;
+                emit_link(P, s_linkbox, D, c, l, s_emit[l], xf_load(src + 8 * l));
+            }
         return;
     }
-    const Xf base = xf_load(P.base);
-    emit_link(P, s_linkbox, c, 0, s_emit[0], base);               // link 0 keeps its pose (kinbody.cpp:2281)
-    const double* qrow = P.q + (size_t)c * P.ncols;
-    Xf cur = base;
-    const size_t cs = (size_t)P.cap;
-    for (int s = 0; s < P.nsteps; ++s) {
-        const FkStep& st = s_steps[s];
-        if (st.load_parent == -1) cur = base;
-        else if (st.load_parent >= 0) {
-            const double* sv = P.fksave + (size_t)st.load_parent * 7 * cs + c;
-            cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
-            cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
-        }
-        cur = xf_mul(cur, joint_transform(st, qrow));
-        if (st.save >= 0) {
-            double* sv = P.fksave + (size_t)st.save * 7 * cs + c;
-            sv[0] = cur.q0; sv[cs] = cur.q1; sv[2 * cs] = cur.q2; sv[3 * cs] = cur.q3;
-            sv[4 * cs] = cur.tx; sv[5 * cs] = cur.ty; sv[6 * cs] = cur.tz;
-        }
-        emit_link(P, s_linkbox, c, st.child, s_emit[st.child], cur);
-    }
+    FkDst D;
+    D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
+    D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
+    D.save = P.fksave + c; D.save_pose_stride = 7 * (size_t)P.cap; D.save_comp_stride = (size_t)P.cap;
+    fk_chain(P, s_steps, s_linkbox, s_emit, D, c);
 }
 
 // ================================================================================================ kernel 2: traversal
@@ -559,7 +600,12 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // kTables: the plan carries certified free-space tables (compiled out otherwise, so plans without tables run the plain code).
 // kContacts: all contacts of every pair are enumerated and recorded (PQP_ALL_CONTACTS, collisionPQP.h:578): no pair is
 // abandoned at its first contact; used with kFlagAllPairs for single configurations.
-template <bool kSplit, bool kTables, bool kContacts = false>
+// kFused: FK runs inside this kernel.  A warp takes a BATCH of up to 32 configurations off the work counter, computes their FK
+// one configuration per lane (fk_batch_warp: the FK kernel's code, FP64) into its private slot-major area in global memory,
+// then traverses them one by one.  No separate FK launch, no chunk-sized pose scratch, and the FK of one warp overlaps the
+// traversals of the others.  Batches shrink towards the end of the work (guided self-scheduling) so that the last warps
+// finish together.  Big FK-mode batches only (the host picks it), never with kSplit / kContacts.
+template <bool kSplit, bool kTables, bool kContacts = false, bool kFused = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -587,12 +633,40 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const int32_t* ptable = P.pair_table;
     const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
+    // fused FK: the warp's private pose area and its current batch
+    const size_t wid = (size_t)blockIdx.x * kWarpsPerBlock + wib;
+    float* const wxf = kFused ? P.xf32 + wid * (size_t)ndyn * 32 * 12 : nullptr;
+    float* const wab = kFused ? P.aabb + wid * (size_t)ndyn * 32 * 8 : nullptr;
+    double* const wsave = kFused ? P.fksave + wid * (size_t)P.nsave * 7 * 32 : nullptr;
+    int batch_first = 0, batch_count = 0, batch_pos = 0;
+    const int xs = kFused ? 32 * 12 : 12, as = kFused ? 32 * 8 : 8;      // floats between consecutive slots
 
     for (;;) {
         int c = 0;
-        if (lane == 0) c = atomicAdd(&P.counters[0], 1);
-        c = __shfl_sync(kFull, c, 0);
-        if (c >= nwork) break;
+        if (kFused) {
+            if (batch_pos == batch_count) {
+                int first = 0, take = 0;
+                if (lane == 0) {
+                    // guided self-scheduling: full batches while plenty of work is left, smaller ones near the end
+                    const int left = nwork - *(volatile int32_t*)&P.counters[0];
+                    const int per_warp = left / (2 * (int)(gridDim.x * kWarpsPerBlock));
+                    take = per_warp >= 32 ? 32 : (per_warp >= 16 ? 16 : (per_warp >= 8 ? 8 : 4));
+                    first = atomicAdd(&P.counters[0], take);
+                }
+                first = __shfl_sync(kFull, first, 0);
+                take = __shfl_sync(kFull, take, 0);
+                if (first >= nwork) break;
+                batch_first = first; batch_count = nwork - first < take ? nwork - first : take; batch_pos = 0;
+                __syncwarp();
+                fk_batch_warp(P, batch_first, batch_count, wxf, wab, wsave);
+                __syncwarp();           // the lanes' stores are visible to the whole warp from here on
+            }
+            c = batch_first + batch_pos;
+        } else {
+            if (lane == 0) c = atomicAdd(&P.counters[0], 1);
+            c = __shfl_sync(kFull, c, 0);
+            if (c >= nwork) break;
+        }
         if (kSplit) {
             const int w = c;
             c = w / P.split;
@@ -603,9 +677,9 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             npairs_dev = __ldg(&P.part_begin[part + 1]) - pb;
             nenv_dev = __ldg(&P.part_nenv[part]);
         }
-        const float* xf = P.xf32 + (size_t)c * ndyn * 12;
-        const float* ab = P.aabb + (size_t)c * ndyn * 8;
-        const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;       // static slot s lives at st_ab + 8 s
+        const float* xf = kFused ? wxf + batch_pos * 12 : P.xf32 + (size_t)c * ndyn * 12;       // slot d at xf + d * xs
+        const float* ab = kFused ? wab + batch_pos * 8 : P.aabb + (size_t)c * ndyn * 8;          // slot d at ab + d * as
+        if (kFused) ++batch_pos;
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
         if (!kSplit && P.pair_mask) {
             uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
@@ -652,8 +726,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     ov[h] = false;
                     if (pr[h] != 0xffffffffu) {
                         const int sa = pr[h] & 0xffff, sb = pr[h] >> 16;
-                        const float4* pa = (const float4*)((sa < ndyn ? ab : st_ab) + 8 * sa);
-                        const float4* pb = (const float4*)((sb < ndyn ? ab : st_ab) + 8 * sb);
+                        const float4* pa = (const float4*)(sa < ndyn ? ab + as * sa : P.st_aabb + 8 * (size_t)(sa - ndyn));
+                        const float4* pb = (const float4*)(sb < ndyn ? ab + as * sb : P.st_aabb + 8 * (size_t)(sb - ndyn));
                         const float4 ac = pa[0], ae = pa[1], bc = pb[0], be = pb[1];
                         ov[h] = fabsf(ac.x - bc.x) <= ae.x + be.x && fabsf(ac.y - bc.y) <= ae.y + be.y && fabsf(ac.z - bc.z) <= ae.z + be.z;
                         if (kTables && ov[h]) {
@@ -693,13 +767,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const int la = pr & 0xffff, lb = pr >> 16;
                         float A[12], Bx[12];
                         {
-                            const float4* e = la < ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
+                            const float4* e = la < ndyn ? (const float4*)(xf + xs * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
                             A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
                         }
                         {
-                            const float4* e = lb < ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
+                            const float4* e = lb < ndyn ? (const float4*)(xf + xs * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
                             const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                             Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
                             Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;

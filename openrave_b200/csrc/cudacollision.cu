@@ -493,48 +493,15 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     const bool fk_only = (flags & ccdev::kFlagFkOnly) != 0;
     const int row_doubles = (flags & ccdev::kFlagPoseMode) ? Q->nq * 8 : Q->ncols;
 
-    // ---- chunking.  Big batches are cut into >= 4 chunks that alternate between two internal streams: while the
-    // persistent traversal kernel of chunk i drains its last (long) configurations, the FK kernel and the traversal
-    // blocks of chunk i+1 fill the SMs it has already left.  Scratch per set stays around half a GB at most.
-    const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
-    int chunk = (int)std::min<size_t>(131072, std::max<size_t>(1024, ((size_t)1 << 29) / per_cfg));
-    if (n >= 262144) chunk = std::min(chunk, std::max(65536, ((n + 3) / 4 + 127) / 128 * 128));   // smaller chunks only multiply tails
-    static const int tune_chunk = getenv("CC_TUNE_CHUNK") ? atoi(getenv("CC_TUNE_CHUNK")) : 0;      // profiling knob: configurations per chunk
-    if (tune_chunk > 0) chunk = (tune_chunk + 127) / 128 * 128;
-    chunk = std::min(chunk, (n + 127) / 128 * 128);
-    const int nchunks = (n + chunk - 1) / chunk;
-    const bool overlap = nchunks >= 2;
-    static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
-                                                                                                     // chunk of each lane (timing without FK)
-    const bool timeline = S->trace_timeline && !fk_only;
-    if (timeline) {
-        while ((int)S->tl_events.size() < 3 * nchunks) { cudaEvent_t e; CC_CUDA(cudaEventCreate(&e)); S->tl_events.push_back(e); }
-        S->tl_lane.assign(nchunks, 0);
-    }
-    {
-        int rc = ensure_scratch(Q, pl, chunk, overlap ? 2 : 1);
-        if (rc != CC_OK) return rc;
-    }
-    P.cap = chunk;
-    if (overlap && !S->lane_stream[0]) {
-        for (int i = 0; i < 2; ++i) {
-            CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
-            CC_CUDA(cudaEventCreateWithFlags(&S->ev_join[i], cudaEventDisableTiming));
-        }
-        CC_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
-    }
-
-    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
-    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
-    if (fk_smem > 48 * 1024)
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
     // CC_TUNE_EXTRA_SMEM (bytes per block) is a profiling knob: it trades resident traversal blocks for L1 capacity
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        const void* variants[5] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
+        const void* variants[7] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
                                    (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>};
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, false, true>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, true, false, true>};
         int per_sm = 1 << 30;
         for (const void* kfn : variants) {
             CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -547,7 +514,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         if (getenv("CC_TUNE_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(getenv("CC_TUNE_BLOCKS_PER_SM"))));
         S->trav_blocks_per_sm = per_sm;
     }
-    if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     // spill areas: one per pipeline lane, sized for a full persistent grid
     const int full_warps = S->trav_blocks_per_sm * S->num_sms * ccdev::kWarpsPerBlock;
     // small batches: spread every configuration over 2, 4 or 8 warps (as many as keep the work items within ~2 waves and
@@ -561,7 +527,53 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         while (split * 2 <= want && split < 8) split *= 2;
     }
     const bool contacts = Q->contact_out != nullptr && (flags & CC_BATCH_ALL_PAIRS);
-    if (contacts) { split = 1; P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
+    if (contacts) split = 1;
+    // big FK-mode batches: FK inside the traversal kernel (cc_traverse_kernel<.., kFused>): a warp needs dozens of 32-configuration
+    // batches for its lanes to stay busy, so the separate FK kernel keeps the smaller ones.  CC_TUNE_FUSED: 0 never, 2 whenever legal.
+    static const int tune_fused = getenv("CC_TUNE_FUSED") ? atoi(getenv("CC_TUNE_FUSED")) : 1;
+    const bool fused = tune_fused > 0 && !fk_only && !(flags & ccdev::kFlagPoseMode) && split == 1 && !contacts && d_fk == nullptr &&
+                       (tune_fused > 1 || (long long)n >= 64LL * full_warps);
+
+    // ---- chunking.  Big batches are cut into chunks that alternate between two internal streams: while the persistent
+    // traversal kernel of chunk i drains its last (long) configurations, the kernels of chunk i+1 fill the SMs it has already
+    // left, and (host-buffer entry) the copies of one chunk overlap the kernels of the other lane.  Chunks of 256k: with 128k
+    // the per-chunk tails cost 10 % on the PR2 workload (profiles/r02a_knobs.log).  Scratch per set stays below 1 GB.
+    const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
+    int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
+    if (fused && !hio) chunk = std::max(chunk, (n + 127) / 128 * 128);      // device-resident input: nothing to overlap, one launch
+    static const int tune_chunk = getenv("CC_TUNE_CHUNK") ? atoi(getenv("CC_TUNE_CHUNK")) : 0;      // profiling knob: configurations per chunk
+    if (tune_chunk > 0) chunk = (tune_chunk + 127) / 128 * 128;
+    chunk = std::min(chunk, (n + 127) / 128 * 128);
+    const int nchunks = (n + chunk - 1) / chunk;
+    const bool overlap = nchunks >= 2;
+    static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
+                                                                                                     // chunk of each lane (timing without FK)
+    const bool timeline = S->trace_timeline && !fk_only;
+    if (timeline) {
+        while ((int)S->tl_events.size() < 3 * nchunks) { cudaEvent_t e; CC_CUDA(cudaEventCreate(&e)); S->tl_events.push_back(e); }
+        S->tl_lane.assign(nchunks, 0);
+    }
+    {
+        // fused: the pose scratch is per WARP (32 configurations each), not per configuration of the chunk
+        int rc = ensure_scratch(Q, pl, fused ? full_warps * 32 : chunk, overlap ? 2 : 1);
+        if (rc != CC_OK) return rc;
+    }
+    P.cap = chunk;
+    P.nsave = pl.nsave;
+    if (overlap && !S->lane_stream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
+            CC_CUDA(cudaEventCreateWithFlags(&S->ev_join[i], cudaEventDisableTiming));
+        }
+        CC_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+    }
+
+    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
+    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
+    if (fk_smem > 48 * 1024)
+        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+    if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
+    if (contacts) { P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
@@ -618,7 +630,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.counters = Q->d_counters[k].p;
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
         if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
-        if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
+        if (!fused && !(tune_skip_fk && ci >= 2 && !fk_only)) {
             ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
@@ -633,7 +645,10 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        if (fused) {
+            if (use_tables) ccdev::cc_traverse_kernel<false, true, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+            else ccdev::cc_traverse_kernel<false, false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        } else if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
             else ccdev::cc_traverse_kernel<false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 visit b: the fused FK + traversal kernel.  Parity with the fused path forced everywhere it is legal, then the default
+# configuration, then A/B timings (fused off / on, chunk sizes) and the other workloads.
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r02b}
+CC_TUNE_FUSED=2 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu_fused_forced.log 2>&1; echo "pytest (fused forced) rc=$?"; tail -4 gpurun_out/${TAG}_pytest_gpu_fused_forced.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest_gpu.log
+for knobs in "CC_TUNE_FUSED=0" "CC_TUNE_FUSED=1" "CC_TUNE_FUSED=2" "CC_TUNE_FUSED=1 CC_TUNE_CHUNK=250112" "CC_TUNE_FUSED=1 CC_TUNE_NO_TABLES=1"; do
+  echo "=== $knobs"
+  for w in pr2_pr2test1_1m wam_lab1_100k hironx_table_1m wam_clutter200_1250k; do
+    env $knobs timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/err_$TAG.txt | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('$w', round(d['value']/1e6, 2), 'M/s', round(d['ms_per_step'], 3), 'ms  e2e', round(d['e2e']['value']/1e6, 2), 'first-hit', round(d['config']['first_hit_mode_configs_per_s']/1e6, 2), 'launches', d['gpu_launches'])
+"; tail -2 gpurun_out/err_$TAG.txt
+  done
+done 2>&1 | tee gpurun_out/${TAG}_ab_fused.log
+timeout 300 python tools/gpu_timeline.py pr2_pr2test1_1m > gpurun_out/${TAG}_timeline_pr2.json 2> gpurun_out/err_tl.txt; tail -2 gpurun_out/err_tl.txt
