@@ -535,17 +535,18 @@ def main():
     q_host = sample(robot, n, seed + 1000 * rank)
     q_pinned = torch.from_numpy(q_host).pin_memory()
     d_q = q_pinned.cuda(non_blocking=True)
-    d_verdict = torch.zeros(n, dtype=torch.int32, device="cuda")
-    d_fe = torch.zeros(n, dtype=torch.int32, device="cuda")
-    d_fs = torch.zeros(n, dtype=torch.int32, device="cuda")
-    gathered = [torch.zeros(3 * n, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+    # verdict | first env pair | first self pair of this rank's shard in ONE buffer, so that what crosses NVLink is a single
+    # ncclAllGather into a preallocated tensor (no torch.cat, no per-rank copy-out inside the timed region)
+    d_res = torch.zeros(3 * n, dtype=torch.int32, device="cuda")
+    d_verdict, d_fe, d_fs = d_res[0:n], d_res[n:2 * n], d_res[2 * n:3 * n]
+    gathered = torch.empty(world * 3 * n, dtype=torch.int32, device="cuda") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
 
     def step_device():
         bq.check_device(d_q.data_ptr(), n, flags, d_verdict.data_ptr(), d_fe.data_ptr(), d_fs.data_ptr(), 0, stream.cuda_stream)
-        if world > 1:   # only the per-config verdicts and first-contact pairs cross NVLink
-            dist.all_gather(gathered, torch.cat([d_verdict, d_fe, d_fs]))
+        if world > 1:   # only the per-config verdicts and first-contact pairs cross NVLink (device consumer)
+            dist.all_gather_into_tensor(gathered, d_res)
 
     # the caller-side buffers of the host entry: page-locked (cc_host_alloc), reused every step
     from openrave_b200.checker import PinnedArray
@@ -606,18 +607,46 @@ def main():
     step_device()                           # leave the full outputs in the result buffers for the consistency check below
     torch.cuda.synchronize()
 
-    # end to end through the host-buffer entry
-    for _ in range(2):
-        step_e2e()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v_last = step_e2e()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    # end to end through the host-buffer entry.  One GPU: this process's own checker.  N GPUs: ONE process (rank 0) drives all N
+    # devices through a multi-device scene (cc_scene_create_multi): one cc_check_batch call over the N x n configurations of all
+    # ranks in one page-locked buffer, range-sharded inside the library, every device copying its slice in and its results out
+    # (host consumer: no collective).  The other ranks idle at the barrier meanwhile — this is the call an OpenRAVE process makes.
+    multi = None
+    if world == 1:
+        for _ in range(2):
+            step_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v_last = step_e2e()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+    else:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_s = 0.0
+        if rank == 0:
+            env_m, robot_m, _, _ = load_world(args.workload)
+            cc_m = CudaCollisionChecker(env_m, list(range(world)))
+            env_m.SetCollisionChecker(cc_m)
+            bq_m = cc_m.bind(robot_m)
+            q_all = PinnedArray((world * n, ndof), np.float64)
+            for r in range(world):
+                q_all.array[r * n:(r + 1) * n] = sample(robot, n, seed + 1000 * r)
+            pv, pe, ps = PinnedArray(world * n, np.uint32), PinnedArray(world * n, np.int32), PinnedArray(world * n, np.int32)
+            for _ in range(3):
+                bq_m.check(q_all.array, flags, out=(pv.array, pe.array, ps.array))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                bq_m.check(q_all.array, flags, out=(pv.array, pe.array, ps.array))
+            e2e_s = (time.perf_counter() - t0) / args.steps
+            v_last = pv.array[:n].copy()
+            multi = {"devices": list(range(world)), "configs_per_call": world * n,
+                     "kernel_launches_per_call": int((cc_m.GetStatistics()["launches"]) // (args.steps + 3))}
+            bq_m.close()
+            cc_m.DestroyEnvironment()
+        dist.barrier()
+        if rank != 0:
+            v_last = d_verdict.cpu().numpy().astype(np.uint32)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -636,11 +665,13 @@ def main():
                            "pairs_with_table": ntab_only, "certificate_build_ms": cert_ms,
                            "bvh_nodes": bq.info.total_nodes, "tris": bq.info.total_tris,
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
-                           "parallelism": "configs sharded, scene replicated (dp%d)" % world,
+                           "parallelism": "configs sharded, scene replicated (dp%d)" % world, "multi_device_e2e": multi,
                            "colliding_fraction": float((v_last != 0).mean()),
                            "first_hit_mode_configs_per_s": world * n / (first_hit_ms / 1000.0)},
-                "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * ndof * 8),
-                        "d2h_bytes_per_step": int(n * 12)},
+                "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * n * ndof * 8),
+                        "d2h_bytes_per_step": int(world * n * 12),
+                        "path": "cc_check_batch, pinned host buffers" + ("" if world == 1 else
+                                " — ONE process, one call over all %d devices (cc_scene_create_multi)" % world)},
                 "gpu_launches": int(launches_timed),
                 "clocks": sampler.summary(),
                 "wall_s_timed_region": t_wall}

@@ -33,6 +33,11 @@
 
 #include "cudacollision.h"
 
+// the reference's plugins each carry this in their plugindefs.h (plugins/pqprave/plugindefs.h:30-47)
+#ifndef FOREACHC
+#define FOREACHC(it, v) for (auto it = (v).begin(); it != (v).end(); ++it)
+#endif
+
 using namespace OpenRAVE;
 
 namespace {

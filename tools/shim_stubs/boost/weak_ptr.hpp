@@ -1,0 +1,2 @@
+#pragma once
+#include <boost/shared_ptr.hpp>
