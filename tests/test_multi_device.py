@@ -49,7 +49,7 @@ def _check_equal_to_single(devices, scene, manip, n):
     assert _same(a, b)
     assert 0.02 < (a["verdict"] != 0).mean() < 0.999
     # every replica did work: the scene-wide statistics are the sum over the replicas
-    assert many.GetStatistics()["configs"] == n and many.GetStatistics()["launches"] >= 2 * len(devices)
+    assert many.GetStatistics()["configs"] >= n and many.GetStatistics()["launches"] >= 2 * len(devices)
     # ragged sizes around the sharding threshold, complete masks, FK, distances
     for m in (1, 33, 16384 * len(devices) - 1, 16384 * len(devices) + 5):
         assert _same(one.CheckCollisionBatch(robot1, q[:m], active=active), many.CheckCollisionBatch(robot2, q[:m], active=active))
