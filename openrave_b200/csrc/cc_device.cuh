@@ -66,11 +66,17 @@ constexpr int kFlagEnv = 1, kFlagSelf = 2, kFlagAllPairs = 4, kFlagPoseMode = 8,
 constexpr int kFlagFirstHit = 128;     // verdict only: an env hit ends the configuration, a self hit ends the self pairs
 constexpr int kFlagInitOutputs = 64;   // split traversal: the FK kernel initialises the outputs the traversal combines into
 
-struct FkStep {                 // one joint of the chain program, 256 bytes
+// The chain program (compiled per plan by compile_fk_program, cudacollision.cu).  Only joints whose value depends on an ACTIVE DOF
+// are walked ("varying" steps: T_child = T_parent * L * J(q) * R, kinbody.cpp:2478); everything rigidly attached to such a joint's
+// child link — static joints, joints of inactive DOFs, grabbed links — is folded on the host into one constant per link and
+// becomes a "constant" step right after it: T_link = T_anchor * L, which leaves the running transform alone.  The left
+// transform of a varying step likewise absorbs the constant path from the previous varying joint's child to its own parent.
+struct FkStep {                 // 256 bytes
     int32_t type;               // 1 revolute, 2 prismatic
-    int32_t parent, child;
+    int32_t parent, child;      // links (parent: the link whose pose the step starts from)
     int32_t src_col;            // column of q feeding this joint (own DOF or the mimic source); -1: constant
-    int32_t flags;              // bit0 static, bit1 mimic, bit2 own-circular, bit3 source-circular
+    int32_t flags;              // bit0 static / constant joint (only L is used), bit1 mimic, bit2 own-circular, bit3 source-circular,
+                                // bit4 constant step: the child's pose is emitted as running * L, the running transform is kept
     int32_t load_parent;        // -2: parent pose is the running transform, -1: link 0's pose, >=0: parked pose index
     int32_t save;               // >=0: park this child's pose (a later step branches off it)
     int32_t pad;
@@ -123,7 +129,10 @@ struct Params {
     int32_t* counters;          // [0] traversal work counter
     int32_t* err_flag;          // set when a traversal overflows its spill area
     int32_t cap;
-    int32_t nsave;              // parked poses of the chain program (fused kernel: size of a warp's save area)
+    // layout of the per-chunk pose scratch, in floats: slot d of configuration c lives at xf32 + c * xf_cfg_stride + d * xf_slot_stride.
+    // Slot-major (the default): xf_cfg_stride = 12, xf_slot_stride = 12 * cap, so that the FK kernel's threads (one configuration
+    // each) write a slot with fully coalesced stores; configuration-major: xf_cfg_stride = 12 * ndyn, xf_slot_stride = 12.
+    int32_t xf_slot_stride, xf_cfg_stride, ab_slot_stride, ab_cfg_stride;
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
@@ -379,9 +388,7 @@ __host__ __device__ inline size_t fk_smem_bytes(int nq, int nsteps, int ndyn)
     return (size_t)nsteps * sizeof(FkStep) + (size_t)ndyn * 32 + (size_t)nq * 4;
 }
 
-// Where the FK of ONE configuration puts its results.  cc_fk_kernel: row `c` of the per-chunk scratch (slots contiguous per
-// configuration).  Fused kernel: the warp's private area, slot-major with the 32 configurations of a batch side by side, so the
-// 32 lanes of an FK batch write 1536 / 1024 contiguous bytes per slot.
+// Where the FK of ONE configuration puts its results: the per-chunk pose scratch in either layout (Params::xf_slot_stride).
 struct FkDst {
     float* xf;  int xf_stride;       // FP32 R|t of slot d at xf + d * xf_stride (12 floats)
     float* ab;  int ab_stride;       // world AABB of slot d at ab + d * ab_stride (8 floats)
@@ -471,6 +478,10 @@ __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, c
             cur.q0 = sv[0]; cur.q1 = sv[cs]; cur.q2 = sv[2 * cs]; cur.q3 = sv[3 * cs];
             cur.tx = sv[4 * cs]; cur.ty = sv[5 * cs]; cur.tz = sv[6 * cs];
         }
+        if (st.flags & 16) {                                     // rigidly attached to the running link: pose out, nothing else
+            emit_link(P, linkbox, D, c, st.child, emit[st.child], xf_mul(cur, xf_load(st.L)));
+            continue;
+        }
         cur = xf_mul(cur, joint_transform(st, qrow));
         if (st.save >= 0) {
             double* sv = D.save + (size_t)st.save * ps;
@@ -479,19 +490,6 @@ __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, c
         }
         emit_link(P, linkbox, D, c, st.child, emit[st.child], cur);
     }
-}
-
-// The same for the fused kernel: called by a whole warp, lane i doing configuration first + i of a batch of `count` <= 32, into
-// the warp's private slot-major area.  Not inlined: its FP64 register needs stay out of the traversal loop's allocation.
-__device__ __noinline__ void fk_batch_warp(const Params& P, int first, int count, float* wxf, float* wab, double* wsave)
-{
-    const int lane = threadIdx.x & 31;
-    if (lane >= count) return;
-    FkDst D;
-    D.xf = wxf + lane * 12; D.xf_stride = 32 * 12;
-    D.ab = wab + lane * 8; D.ab_stride = 32 * 8;
-    D.save = wsave + lane; D.save_pose_stride = 7 * 32; D.save_comp_stride = 32;
-    fk_chain(P, P.steps, P.link_box, P.emit_index, D, first + lane);
 }
 
 __global__ void __launch_bounds__(kFkThreads)
@@ -526,16 +524,16 @@ cc_fk_kernel(const __grid_constant__ Params P)
         for (int l = 0; l < P.nq; ++l)
             if (s_emit[l] >= 0) {
                 FkDst D;
-                D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
-                D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
+                D.xf = P.xf32 + (size_t)c * P.xf_cfg_stride; D.xf_stride = P.xf_slot_stride;
+                D.ab = P.aabb + (size_t)c * P.ab_cfg_stride; D.ab_stride = P.ab_slot_stride;
                 D.save = nullptr; D.save_pose_stride = D.save_comp_stride = 0;
                 emit_link(P, s_linkbox, D, c, l, s_emit[l], xf_load(src + 8 * l));
             }
         return;
     }
     FkDst D;
-    D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
-    D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
+    D.xf = P.xf32 + (size_t)c * P.xf_cfg_stride; D.xf_stride = P.xf_slot_stride;
+    D.ab = P.aabb + (size_t)c * P.ab_cfg_stride; D.ab_stride = P.ab_slot_stride;
     D.save = P.fksave + c; D.save_pose_stride = 7 * (size_t)P.cap; D.save_comp_stride = (size_t)P.cap;
     fk_chain(P, s_steps, s_linkbox, s_emit, D, c);
 }
@@ -600,12 +598,7 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // kTables: the plan carries certified free-space tables (compiled out otherwise, so plans without tables run the plain code).
 // kContacts: all contacts of every pair are enumerated and recorded (PQP_ALL_CONTACTS, collisionPQP.h:578): no pair is
 // abandoned at its first contact; used with kFlagAllPairs for single configurations.
-// kFused: FK runs inside this kernel.  A warp takes a BATCH of up to 32 configurations off the work counter, computes their FK
-// one configuration per lane (fk_batch_warp: the FK kernel's code, FP64) into its private slot-major area in global memory,
-// then traverses them one by one.  No separate FK launch, no chunk-sized pose scratch, and the FK of one warp overlaps the
-// traversals of the others.  Batches shrink towards the end of the work (guided self-scheduling) so that the last warps
-// finish together.  Big FK-mode batches only (the host picks it), never with kSplit / kContacts.
-template <bool kSplit, bool kTables, bool kContacts = false, bool kFused = false>
+template <bool kSplit, bool kTables, bool kContacts = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -633,40 +626,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const int32_t* ptable = P.pair_table;
     const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
-    // fused FK: the warp's private pose area and its current batch
-    const size_t wid = (size_t)blockIdx.x * kWarpsPerBlock + wib;
-    float* const wxf = kFused ? P.xf32 + wid * (size_t)ndyn * 32 * 12 : nullptr;
-    float* const wab = kFused ? P.aabb + wid * (size_t)ndyn * 32 * 8 : nullptr;
-    double* const wsave = kFused ? P.fksave + wid * (size_t)P.nsave * 7 * 32 : nullptr;
-    int batch_first = 0, batch_count = 0, batch_pos = 0;
-    const int xs = kFused ? 32 * 12 : 12, as = kFused ? 32 * 8 : 8;      // floats between consecutive slots
+    const size_t xs = (size_t)P.xf_slot_stride, as = (size_t)P.ab_slot_stride;      // floats between consecutive slots of one configuration
 
     for (;;) {
         int c = 0;
-        if (kFused) {
-            if (batch_pos == batch_count) {
-                int first = 0, take = 0;
-                if (lane == 0) {
-                    // guided self-scheduling: full batches while plenty of work is left, smaller ones near the end
-                    const int left = nwork - *(volatile int32_t*)&P.counters[0];
-                    const int per_warp = left / (2 * (int)(gridDim.x * kWarpsPerBlock));
-                    take = per_warp >= 32 ? 32 : (per_warp >= 16 ? 16 : (per_warp >= 8 ? 8 : 4));
-                    first = atomicAdd(&P.counters[0], take);
-                }
-                first = __shfl_sync(kFull, first, 0);
-                take = __shfl_sync(kFull, take, 0);
-                if (first >= nwork) break;
-                batch_first = first; batch_count = nwork - first < take ? nwork - first : take; batch_pos = 0;
-                __syncwarp();
-                fk_batch_warp(P, batch_first, batch_count, wxf, wab, wsave);
-                __syncwarp();           // the lanes' stores are visible to the whole warp from here on
-            }
-            c = batch_first + batch_pos;
-        } else {
-            if (lane == 0) c = atomicAdd(&P.counters[0], 1);
-            c = __shfl_sync(kFull, c, 0);
-            if (c >= nwork) break;
-        }
+        if (lane == 0) c = atomicAdd(&P.counters[0], 1);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= nwork) break;
         if (kSplit) {
             const int w = c;
             c = w / P.split;
@@ -677,9 +643,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             npairs_dev = __ldg(&P.part_begin[part + 1]) - pb;
             nenv_dev = __ldg(&P.part_nenv[part]);
         }
-        const float* xf = kFused ? wxf + batch_pos * 12 : P.xf32 + (size_t)c * ndyn * 12;       // slot d at xf + d * xs
-        const float* ab = kFused ? wab + batch_pos * 8 : P.aabb + (size_t)c * ndyn * 8;          // slot d at ab + d * as
-        if (kFused) ++batch_pos;
+        const float* xf = P.xf32 + (size_t)c * P.xf_cfg_stride;       // slot d at xf + d * xs
+        const float* ab = P.aabb + (size_t)c * P.ab_cfg_stride;       // slot d at ab + d * as
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
         if (!kSplit && P.pair_mask) {
             uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;

@@ -192,9 +192,9 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
             k_begin = w - c * P.npairs_dev;
             k_end = k_begin + 1;
         } else if (c >= P.n) break;
-        const float* xf = P.xf32 + (size_t)c * ndyn * 12;
-        const float* ab = P.aabb + (size_t)c * ndyn * 8;
-        const float* st_ab = P.st_aabb - 8 * (size_t)ndyn;
+        const float* xf = P.xf32 + (size_t)c * P.xf_cfg_stride;        // slot d at xf + d * xs (Params::xf_slot_stride)
+        const float* ab = P.aabb + (size_t)c * P.ab_cfg_stride;
+        const size_t xs = (size_t)P.xf_slot_stride, as = (size_t)P.ab_slot_stride;
 
         float best2 = best_init;             // warp-uniform
         float thr2 = best_init;              // squared pruning threshold: best2 itself, or tightened by the tolerances
@@ -204,8 +204,8 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
         auto pair_bound = [&](int k) -> float {
             const uint32_t pr = __ldg(&P.pairs[k]);
             const int sa = pr & 0xffff, sb = pr >> 16;
-            const float4* pa = (const float4*)((sa < ndyn ? ab : st_ab) + 8 * sa);
-            const float4* pb = (const float4*)((sb < ndyn ? ab : st_ab) + 8 * sb);
+            const float4* pa = (const float4*)(sa < ndyn ? ab + as * sa : P.st_aabb + 8 * (size_t)(sa - ndyn));
+            const float4* pb = (const float4*)(sb < ndyn ? ab + as * sb : P.st_aabb + 8 * (size_t)(sb - ndyn));
             return aabb_gap2(pa[0], pa[1], pb[0], pb[1]);
         };
 
@@ -247,13 +247,13 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
                     const int la = pr & 0xffff, lb = pr >> 16;
                     float A[12], Bx[12], R[9], t[3];
                     {
-                        const float4* e = la < ndyn ? (const float4*)(xf + 12 * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
+                        const float4* e = la < ndyn ? (const float4*)(xf + xs * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
                         const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                         A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
                         A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
                     }
                     {
-                        const float4* e = lb < ndyn ? (const float4*)(xf + 12 * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
+                        const float4* e = lb < ndyn ? (const float4*)(xf + xs * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
                         const float4 e0 = e[0], e1 = e[1], e2 = e[2];
                         Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
                         Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
@@ -403,7 +403,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
             if (D.points) {
                 double* o = D.points + 6 * (size_t)w;
                 if (best_pair >= 0) {
-                    const float* A = best_la < ndyn ? xf + 12 * best_la : P.st_xf + 12 * (size_t)(best_la - ndyn);
+                    const float* A = best_la < ndyn ? xf + xs * best_la : P.st_xf + 12 * (size_t)(best_la - ndyn);
                     const V3 pts[2] = {best_p, best_q};
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {

@@ -445,6 +445,15 @@ int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
     return CC_OK;
 }
 
+// Layout of the per-chunk pose scratch (ccdev::Params::xf_slot_stride): slot-major by default — the FK kernel's threads, one
+// configuration each, then write every slot with fully coalesced stores; CC_TUNE_SLOT_MAJOR=0 keeps configurations contiguous.
+void set_scratch_layout(ccdev::Params& P, const Plan& pl, int cap)
+{
+    static const bool slot_major = !(getenv("CC_TUNE_SLOT_MAJOR") && atoi(getenv("CC_TUNE_SLOT_MAJOR")) == 0);
+    if (slot_major) { P.xf_cfg_stride = 12; P.xf_slot_stride = 12 * cap; P.ab_cfg_stride = 8; P.ab_slot_stride = 8 * cap; }
+    else { P.xf_cfg_stride = 12 * pl.ndyn; P.xf_slot_stride = 12; P.ab_cfg_stride = 8 * pl.ndyn; P.ab_slot_stride = 8; }
+}
+
 // Host buffers of the host-buffer entry points: when given, every chunk copies its own slice in before its FK kernel and
 // its results out after its traversal kernel, on the chunk's lane stream, so the transfers of one chunk overlap the kernels
 // of the other lane (pinned buffers from cc_host_alloc make the copies truly asynchronous; pageable ones still work).
@@ -497,11 +506,9 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        const void* variants[7] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
+        const void* variants[5] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
                                    (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, false, false, true>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, true, false, true>};
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>};
         int per_sm = 1 << 30;
         for (const void* kfn : variants) {
             CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -528,19 +535,12 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     }
     const bool contacts = Q->contact_out != nullptr && (flags & CC_BATCH_ALL_PAIRS);
     if (contacts) split = 1;
-    // big FK-mode batches: FK inside the traversal kernel (cc_traverse_kernel<.., kFused>): a warp needs dozens of 32-configuration
-    // batches for its lanes to stay busy, so the separate FK kernel keeps the smaller ones.  CC_TUNE_FUSED: 0 never, 2 whenever legal.
-    static const int tune_fused = getenv("CC_TUNE_FUSED") ? atoi(getenv("CC_TUNE_FUSED")) : 1;
-    const bool fused = tune_fused > 0 && !fk_only && !(flags & ccdev::kFlagPoseMode) && split == 1 && !contacts && d_fk == nullptr &&
-                       (tune_fused > 1 || (long long)n >= 64LL * full_warps);
-
     // ---- chunking.  Big batches are cut into chunks that alternate between two internal streams: while the persistent
     // traversal kernel of chunk i drains its last (long) configurations, the kernels of chunk i+1 fill the SMs it has already
     // left, and (host-buffer entry) the copies of one chunk overlap the kernels of the other lane.  Chunks of 256k: with 128k
     // the per-chunk tails cost 10 % on the PR2 workload (profiles/r02a_knobs.log).  Scratch per set stays below 1 GB.
     const size_t per_cfg = std::max<size_t>(64, scratch_bytes_per_config(pl));
     int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
-    if (fused && !hio) chunk = std::max(chunk, (n + 127) / 128 * 128);      // device-resident input: nothing to overlap, one launch
     static const int tune_chunk = getenv("CC_TUNE_CHUNK") ? atoi(getenv("CC_TUNE_CHUNK")) : 0;      // profiling knob: configurations per chunk
     if (tune_chunk > 0) chunk = (tune_chunk + 127) / 128 * 128;
     chunk = std::min(chunk, (n + 127) / 128 * 128);
@@ -554,12 +554,11 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         S->tl_lane.assign(nchunks, 0);
     }
     {
-        // fused: the pose scratch is per WARP (32 configurations each), not per configuration of the chunk
-        int rc = ensure_scratch(Q, pl, fused ? full_warps * 32 : chunk, overlap ? 2 : 1);
+        int rc = ensure_scratch(Q, pl, chunk, overlap ? 2 : 1);
         if (rc != CC_OK) return rc;
     }
     P.cap = chunk;
-    P.nsave = pl.nsave;
+    set_scratch_layout(P, pl, chunk);
     if (overlap && !S->lane_stream[0]) {
         for (int i = 0; i < 2; ++i) {
             CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
@@ -630,7 +629,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.counters = Q->d_counters[k].p;
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
         if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
-        if (!fused && !(tune_skip_fk && ci >= 2 && !fk_only)) {
+        if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
             ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
@@ -645,10 +644,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        if (fused) {
-            if (use_tables) ccdev::cc_traverse_kernel<false, true, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
-            else ccdev::cc_traverse_kernel<false, false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
-        } else if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
             else ccdev::cc_traverse_kernel<false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
@@ -696,6 +692,7 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     int rc = ensure_scratch(Q, pl, chunk, 1);
     if (rc != CC_OK) return rc;
     P.cap = chunk;
+    set_scratch_layout(P, pl, chunk);
     CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, (size_t)chunk * row_doubles)));
     CC_CUDA(Q->d_dist.reserve((size_t)chunk * outs_per_cfg)); CC_CUDA(Q->d_dpair.reserve((size_t)chunk * outs_per_cfg));
     CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
@@ -1071,6 +1068,134 @@ static void static_aabb(const HLink& L, const double center[3], float* o)
     }
 }
 
+// ---- host mirror of the device's FP64 pose algebra (cc_device.cuh: same operation order, geometry.h:255-262, 430-480)
+struct HXf { double q[4]; double t[3]; };
+
+static void hxf_normalize(double* q)
+{
+    double f = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double eps = 2.220446049250313e-16;
+    if (f < 1.0 - eps || f > 1.0 + eps) { f = sqrt(f); q[0] /= f; q[1] /= f; q[2] /= f; q[3] /= f; }
+}
+
+static HXf hxf_mul(const HXf& a, const HXf& b)
+{
+    HXf r;
+    const double* q = a.q;
+    const double xx = 2 * q[1] * q[1], xy = 2 * q[1] * q[2], xz = 2 * q[1] * q[3], xw = 2 * q[1] * q[0];
+    const double yy = 2 * q[2] * q[2], yz = 2 * q[2] * q[3], yw = 2 * q[2] * q[0];
+    const double zz = 2 * q[3] * q[3], zw = 2 * q[3] * q[0];
+    r.t[0] = a.t[0] + ((1 - yy - zz) * b.t[0] + (xy - zw) * b.t[1] + (xz + yw) * b.t[2]);
+    r.t[1] = a.t[1] + ((xy + zw) * b.t[0] + (1 - xx - zz) * b.t[1] + (yz - xw) * b.t[2]);
+    r.t[2] = a.t[2] + ((xz - yw) * b.t[0] + (yz + xw) * b.t[1] + (1 - xx - yy) * b.t[2]);
+    r.q[0] = a.q[0] * b.q[0] - a.q[1] * b.q[1] - a.q[2] * b.q[2] - a.q[3] * b.q[3];
+    r.q[1] = a.q[0] * b.q[1] + a.q[1] * b.q[0] + a.q[2] * b.q[3] - a.q[3] * b.q[2];
+    r.q[2] = a.q[0] * b.q[2] + a.q[2] * b.q[0] + a.q[3] * b.q[1] - a.q[1] * b.q[3];
+    r.q[3] = a.q[0] * b.q[3] + a.q[3] * b.q[0] + a.q[1] * b.q[2] - a.q[2] * b.q[1];
+    hxf_normalize(r.q);
+    return r;
+}
+
+static HXf hxf_load(const double* p) { HXf r; for (int i = 0; i < 4; ++i) r.q[i] = p[i]; for (int i = 0; i < 3; ++i) r.t[i] = p[4 + i]; return r; }
+static void hxf_store(const HXf& x, double* p) { for (int i = 0; i < 4; ++i) p[i] = x.q[i]; for (int i = 0; i < 3; ++i) p[4 + i] = x.t[i]; p[7] = 0.0; }
+
+// L * J(value) * R of a joint whose value does not depend on an active DOF (ccdev::joint_transform with src_col < 0)
+static HXf host_constant_joint(const ccdev::FkStep& st)
+{
+    const HXf L = hxf_load(st.L);
+    if (st.flags & 1) return L;
+    double v = st.src_const;
+    if (!(st.flags & 8)) { if (v < st.src_lower) v = st.src_lower; else if (v > st.src_upper) v = st.src_upper; }
+    if (st.flags & 2) {
+        const double ev = st.a * v + st.b;
+        v = ev;
+        if (!(st.flags & 4)) {
+            if (ev < st.lower) { if (ev >= st.lower - CC_EPSILON_JOINT_LIMIT) v = st.lower; else if (ev < st.lower - CC_EPSILON_EVAL_JOINT_LIMIT) v = st.lower; }
+            else if (ev > st.upper) { if (ev <= st.upper + CC_EPSILON_JOINT_LIMIT) v = st.upper; else if (ev > st.upper + CC_EPSILON_EVAL_JOINT_LIMIT) v = st.upper; }
+        }
+    }
+    HXf J; J.q[0] = 1; J.q[1] = J.q[2] = J.q[3] = 0; J.t[0] = J.t[1] = J.t[2] = 0;
+    if (st.type == 1) {
+        const double len = sqrt(st.axis[0] * st.axis[0] + st.axis[1] * st.axis[1] + st.axis[2] * st.axis[2]);
+        if (len != 0) { const double sn = sin(v * 0.5) / len, cs = cos(v * 0.5); J.q[0] = cs; J.q[1] = st.axis[0] * sn; J.q[2] = st.axis[1] * sn; J.q[3] = st.axis[2] * sn; }
+    } else { J.t[0] = st.axis[0] * v; J.t[1] = st.axis[1] * v; J.t[2] = st.axis[2] * v; }
+    return hxf_mul(hxf_mul(L, J), hxf_load(st.R));
+}
+
+// Compile the chain program of a plan from the query's joint list (Q->steps: every joint, depth-first, with its current
+// constant value): varying joints are walked on the device, everything rigidly attached to a varying joint's child (or to the
+// base link) is folded into one constant per emitted link (ccdev::FkStep).  Re-run by cc_query_refresh when the values of
+// inactive DOFs change.
+static void compile_fk_program(const cc_query* Q, Plan& pl)
+{
+    const int nl = Q->nq;
+    pl.steps.clear();
+    pl.nsave = 0;
+    if (!Q->has_fk || Q->steps.empty()) return;
+    static const bool fold = !(getenv("CC_TUNE_FK_FOLD") && atoi(getenv("CC_TUNE_FK_FOLD")) == 0);    // 0: walk every joint (A/B)
+    std::vector<uint8_t> need(nl, 0);
+    for (int i = (int)Q->steps.size() - 1; i >= 0; --i) {
+        const ccdev::FkStep& st = Q->steps[i];
+        if (pl.emit[st.child] >= 0) need[st.child] = 1;
+        if (need[st.child]) need[st.parent] = 1;         // depth-first order: children come after their parent
+    }
+    // per link: the link whose pose it is rigidly attached to ("anchor": link 0 or the child of a varying joint), its pose in
+    // that link's frame, and the constant steps waiting to be placed after the anchor's varying step
+    std::vector<int> anchor(nl, 0);
+    std::vector<HXf> rel(nl);
+    std::vector<uint8_t> rel_identity(nl, 1);
+    std::vector<std::vector<ccdev::FkStep>> consts(nl);      // indexed by anchor link
+    std::vector<ccdev::FkStep> varying;                        // in depth-first order
+    for (const ccdev::FkStep& st0 : Q->steps) {
+        if (!need[st0.child]) continue;
+        const bool is_varying = !fold || (!(st0.flags & 1) && st0.src_col >= 0);
+        const int p = st0.parent, c = st0.child;
+        if (!is_varying) {
+            const HXf M = host_constant_joint(st0);
+            rel[c] = rel_identity[p] ? M : hxf_mul(rel[p], M);
+            rel_identity[c] = 0;
+            anchor[c] = anchor[p];
+            if (pl.emit[c] >= 0) {
+                ccdev::FkStep e;
+                memset(&e, 0, sizeof(e));
+                e.type = 1; e.parent = anchor[c]; e.child = c; e.src_col = -1; e.flags = 1 | 16; e.load_parent = -2; e.save = -1;
+                hxf_store(rel[c], e.L);
+                e.R[0] = 1.0;
+                consts[anchor[c]].push_back(e);
+            }
+        } else {
+            ccdev::FkStep v = st0;
+            v.parent = fold ? anchor[p] : p;
+            if (fold && !rel_identity[p]) { const HXf L2 = hxf_mul(rel[p], hxf_load(st0.L)); hxf_store(L2, v.L); }
+            varying.push_back(v);
+            anchor[c] = c; rel_identity[c] = 1;
+        }
+    }
+    for (const ccdev::FkStep& e : consts[0]) pl.steps.push_back(e);          // rigidly attached to the base link
+    for (const ccdev::FkStep& v : varying) {
+        pl.steps.push_back(v);
+        for (const ccdev::FkStep& e : consts[v.child]) pl.steps.push_back(e);
+    }
+    // where each varying step finds its starting pose: the running transform, the base, or a parked pose
+    std::vector<int> save_of_link(nl, -1);
+    int last_varying = -1;
+    for (size_t i = 0; i < pl.steps.size(); ++i) {
+        ccdev::FkStep& st = pl.steps[i];
+        if (st.flags & 16) continue;
+        st.save = -1;
+        if (last_varying >= 0 && pl.steps[last_varying].child == st.parent) st.load_parent = -2;
+        else if (st.parent == 0) st.load_parent = -1;
+        else {
+            if (save_of_link[st.parent] < 0) {
+                save_of_link[st.parent] = pl.nsave++;
+                for (size_t j = 0; j < i; ++j) if (!(pl.steps[j].flags & 16) && pl.steps[j].child == st.parent) pl.steps[j].save = save_of_link[st.parent];
+            }
+            st.load_parent = save_of_link[st.parent];
+        }
+        last_varying = (int)i;
+    }
+}
+
 // Lay one pair list out for the device.  `dynamic[l]`: query link l gets a per-configuration pose (scratch slot); every
 // other link a pair names (environment links, query links no active DOF moves) becomes a static slot at its current pose.
 static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, const std::vector<uint8_t>& dynamic, bool with_fk)
@@ -1125,32 +1250,9 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         pose_to_rt32(L.xf, Q->center, &stxf[(size_t)i * 12]);
         static_aabb(L, Q->center, &staabb[(size_t)i * 8]);
     }
-    // FK program pruned to the ancestors of the dynamic slots
     pl.steps.clear();
     pl.nsave = 0;
-    if (with_fk && Q->has_fk) {
-        std::vector<uint8_t> need(nl, 0);
-        for (int i = (int)Q->steps.size() - 1; i >= 0; --i) {
-            const ccdev::FkStep& st = Q->steps[i];
-            if (pl.emit[st.child] >= 0) need[st.child] = 1;
-            if (need[st.child]) need[st.parent] = 1;         // depth-first order: children come after their parent
-        }
-        for (const ccdev::FkStep& st : Q->steps) if (need[st.child]) pl.steps.push_back(st);
-        std::vector<int> save_of_link(nl, -1);
-        for (size_t i = 0; i < pl.steps.size(); ++i) {
-            ccdev::FkStep& st = pl.steps[i];
-            st.save = -1;
-            if (i > 0 && pl.steps[i - 1].child == st.parent) st.load_parent = -2;
-            else if (st.parent == 0) st.load_parent = -1;
-            else {
-                if (save_of_link[st.parent] < 0) {
-                    save_of_link[st.parent] = pl.nsave++;
-                    for (size_t j = 0; j < i; ++j) if (pl.steps[j].child == st.parent) pl.steps[j].save = save_of_link[st.parent];
-                }
-                st.load_parent = save_of_link[st.parent];
-            }
-        }
-    }
+    if (with_fk) compile_fk_program(Q, pl);
     CC_CUDA(pl.d_pairs.upload(pl.pairs)); CC_CUDA(pl.d_orig.upload(pl.orig)); CC_CUDA(pl.d_emit.upload(pl.emit));
     CC_CUDA(pl.d_slot_root.upload(roots)); CC_CUDA(pl.d_link_box.upload(linkbox));
     CC_CUDA(pl.d_st_xf.upload(stxf)); CC_CUDA(pl.d_st_aabb.upload(staabb));
@@ -1613,13 +1715,11 @@ int cc_query_refresh(cc_query* q)
         }
         CC_CUDA(pl->d_st_xf.upload(stxf)); CC_CUDA(pl->d_st_aabb.upload(staabb));
     }
-    // inactive DOF values live in the chain programs
-    for (Plan* pl : plans) {
-        if (!pl || pl->steps.empty()) continue;
+    // inactive DOF values are folded into the chain programs' constants: re-read them and recompile
+    {
         bool changed = false;
-        for (ccdev::FkStep& st : pl->steps) {
-            if (st.src_col >= 0) continue;
-            // find the joint of this step to re-read its source DOF
+        for (ccdev::FkStep& st : q->steps) {
+            if (st.src_col >= 0 || (st.flags & 1)) continue;
             for (const cc_joint& j : B->joints)
                 if (j.parent_link == st.parent && j.child_link == st.child) {
                     const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
@@ -1628,7 +1728,12 @@ int cc_query_refresh(cc_query* q)
                     break;
                 }
         }
-        if (changed) CC_CUDA(pl->d_steps.upload(pl->steps));
+        if (changed)
+            for (Plan* pl : plans) {
+                if (!pl || pl->steps.empty()) continue;
+                compile_fk_program(q, *pl);
+                CC_CUDA(pl->d_steps.upload(pl->steps));
+            }
     }
     CC_CUDA(cudaDeviceSynchronize());
     {
