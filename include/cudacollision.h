@@ -427,6 +427,10 @@ int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user);
  * joint limits (state-setting error). */
 int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, int interval,
                             double* out_configs, int max_configs, int* out_count);
+/* ConstraintFilterReturn::_configurationtimes of the same samples (planningutils.cpp:2801-2808, 3410-3413): the interpolation
+ * coefficient in [0, 1] of every sample of cc_planner_edge_samples, in the same (checking) order. */
+int cc_planner_edge_sample_times(cc_planner* p, const double* q0, const double* q1, int interval, double* out_times, int max_configs,
+                                 int* out_count);
 /* The same for a parabolic ramp: DynamicsCollisionConstraint::Check's quadratic branch (planningutils.cpp:2660-2681, 2726-2766,
  * 2844-3319), taken when the caller passes end-point velocities and timeelapsed > 0 — the parabolic smoothers' feasibility
  * checks (plugins/rplanners/parabolicsmoother.cpp, CheckPathAllConstraints(a, b, da, db, timeelapsed, ...)).  The sampled

@@ -192,9 +192,9 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
             k_begin = w - c * P.npairs_dev;
             k_end = k_begin + 1;
         } else if (c >= P.n) break;
-        const float* xf = P.xf32 + (size_t)c * P.xf_cfg_stride;        // slot d at xf + d * xs (Params::xf_slot_stride)
-        const float* ab = P.aabb + (size_t)c * P.ab_cfg_stride;
-        const size_t xs = (size_t)P.xf_slot_stride, as = (size_t)P.ab_slot_stride;
+        const float* xf = P.xf32 + (size_t)c * ndyn * 12;
+        const float* ab = P.aabb + (size_t)c * ndyn * 8;
+        constexpr int xs = 12, as = 8;
 
         float best2 = best_init;             // warp-uniform
         float thr2 = best_init;              // squared pruning threshold: best2 itself, or tightened by the tolerances

@@ -1262,6 +1262,17 @@ int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user)
     return CC_OK;
 }
 
+int cc_planner_edge_sample_times(cc_planner* p, const double* q0, const double* q1, int interval, double* out_times, int max_configs,
+                                 int* out_count)
+{
+    if (!p || !q0 || !q1 || !out_count || interval < 0 || interval > 3) return fail(CC_ERR_INVALID, "cc_planner_edge_sample_times: bad arguments");
+    std::vector<double> buf, times;
+    const int c = edge_samples(p->cs, q0, q1, interval, buf, &times);
+    *out_count = c;
+    if (c > 0 && out_times) std::memcpy(out_times, times.data(), sizeof(double) * (size_t)std::min(c, std::max(max_configs, 0)));
+    return CC_OK;
+}
+
 int cc_planner_edge_samples(cc_planner* p, const double* q0, const double* q1, int interval, double* out_configs, int max_configs,
                             int* out_count)
 {

@@ -445,15 +445,6 @@ int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
     return CC_OK;
 }
 
-// Layout of the per-chunk pose scratch (ccdev::Params::xf_slot_stride): slot-major by default — the FK kernel's threads, one
-// configuration each, then write every slot with fully coalesced stores; CC_TUNE_SLOT_MAJOR=0 keeps configurations contiguous.
-void set_scratch_layout(ccdev::Params& P, const Plan& pl, int cap)
-{
-    static const bool slot_major = !(getenv("CC_TUNE_SLOT_MAJOR") && atoi(getenv("CC_TUNE_SLOT_MAJOR")) == 0);
-    if (slot_major) { P.xf_cfg_stride = 12; P.xf_slot_stride = 12 * cap; P.ab_cfg_stride = 8; P.ab_slot_stride = 8 * cap; }
-    else { P.xf_cfg_stride = 12 * pl.ndyn; P.xf_slot_stride = 12; P.ab_cfg_stride = 8 * pl.ndyn; P.ab_slot_stride = 8; }
-}
-
 // Host buffers of the host-buffer entry points: when given, every chunk copies its own slice in before its FK kernel and
 // its results out after its traversal kernel, on the chunk's lane stream, so the transfers of one chunk overlap the kernels
 // of the other lane (pinned buffers from cc_host_alloc make the copies truly asynchronous; pageable ones still work).
@@ -558,7 +549,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         if (rc != CC_OK) return rc;
     }
     P.cap = chunk;
-    set_scratch_layout(P, pl, chunk);
     if (overlap && !S->lane_stream[0]) {
         for (int i = 0; i < 2; ++i) {
             CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
@@ -692,7 +682,6 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     int rc = ensure_scratch(Q, pl, chunk, 1);
     if (rc != CC_OK) return rc;
     P.cap = chunk;
-    set_scratch_layout(P, pl, chunk);
     CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, (size_t)chunk * row_doubles)));
     CC_CUDA(Q->d_dist.reserve((size_t)chunk * outs_per_cfg)); CC_CUDA(Q->d_dpair.reserve((size_t)chunk * outs_per_cfg));
     CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));

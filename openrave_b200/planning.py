@@ -649,7 +649,7 @@ class cc_edge_result(ctypes.Structure):
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1, "linearsmoother 0": 2}          # PlannerParameters::_sPostProcessingPlanner
 PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
-                   "cc_planner_edge_samples", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_birrt_plan_batch_multi", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
+                   "cc_planner_edge_samples", "cc_planner_edge_sample_times", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_birrt_plan_batch_multi", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
 def _planner_lib():

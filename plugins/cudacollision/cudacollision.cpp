@@ -6,10 +6,10 @@
 //   checker->SendCommand(sout, sinput)  with  "CheckBatch <robot> <n> <flags> <ptr q> <ptr verdict> <ptr firstpairs>"
 //
 // Built against the reference headers (include/openrave/*.h) inside an OpenRAVE source tree or against an installed
-// OpenRAVE (CMakeLists.txt next to this file).  It cannot be compiled in the B200 build container of this repository:
-// libopenrave needs Boost >= 1.67, libxml2 and rapidjson, none of which are present there; the same
-// object model is exercised there through the Python twin openrave_b200/checker.py, which makes the identical
-// sequence of C-ABI calls.
+// OpenRAVE (CMakeLists.txt next to this file).  It cannot be LINKED or run in the B200 build container of this repository
+// (libopenrave needs Boost >= 1.67, libxml2 and rapidjson), but it is type-checked there against the
+// unmodified reference headers by tools/shim_syntax_check.sh (g++ -fsyntax-only with Boost stand-ins); the same object model
+// is exercised through the Python twin openrave_b200/checker.py, which makes the identical sequence of C-ABI calls.
 //
 // Semantics kept (plugins/pqprave/collisionPQP.h): true = collision; report->Reset(options) first (:174-176); every
 // colliding (link1,link2) appended in env-body / link / link order with minDistance = 0 (:476-485, :586-587); first
@@ -113,6 +113,7 @@ class CudaCollisionChecker : public CollisionCheckerBase
         int transformStamp;              // KinBody::GetUpdateStamp at the last pose upload
         bool kinematicsDirty, pairsDirty, grabbedDirty;
         UserDataPtr cbGeometry, cbEnable, cbAttached, cbJoints, cbActive, cbGrabbed;
+        std::map<int, std::vector<int32_t> > grabLists;   // grabbed body's cc id -> its (body, link) non-colliding list, computed when it was grabbed
         BodyInfo() : id(-1), transformStamp(-1), kinematicsDirty(true), pairsDirty(true), grabbedDirty(true) {}
     };
     typedef boost::shared_ptr<BodyInfo> BodyInfoPtr;
@@ -131,9 +132,21 @@ public:
     {
         __description = ":Interface Author: cudacollision\n\nBatched collision checker for NVIDIA B200 (sm_100a): forward kinematics, "
                         "broadphase, BVH traversal and triangle tests run on the GPU for N configurations per call.";
-        sinput >> _device;
+        // creation arguments: "cudacollision [device | d0,d1,...]" — a device list replicates the scene on every listed GPU and
+        // range-shards the batched entries over them inside the library (cc_scene_create_multi)
+        std::string sdevices;
+        sinput >> sdevices;
+        std::vector<int> vdevices;
+        {
+            std::stringstream ss(sdevices);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) vdevices.push_back(boost::lexical_cast<int>(tok));
+        }
+        if (vdevices.empty()) vdevices.push_back(0);
+        _device = vdevices[0];
         _userdatakey = std::string("cudacollision") + boost::lexical_cast<std::string>(this);
-        _Check(cc_scene_create(_device, &_scene));
+        if (vdevices.size() > 1) _Check(cc_scene_create_multi(vdevices.data(), (int)vdevices.size(), &_scene));
+        else _Check(cc_scene_create(_device, &_scene));
         RegisterCommand("CheckBatch", boost::bind(&CudaCollisionChecker::_CheckBatchCommand, this, boost::placeholders::_1, boost::placeholders::_2),
                         "CheckBatch robotname n flags qptr verdictptr firstpairsptr : batched FK + env + self check of n active-DOF "
                         "vectors (row-major doubles at qptr); writes uint32 verdicts (bit0 env, bit1 self) and int32[n][4] "
@@ -432,19 +445,73 @@ private:
         if (!!pbody) { _UploadMeshes(pbody, pinfo); pinfo->pairsDirty = true; _DropQueries(); }
     }
 
+    /// Prop_RobotGrabbed fires inside Grab / Release: the non-colliding list of a NEWLY grabbed body is computed right here, at
+    /// the poses of the grab — the state Grabbed::_listNonCollidingLinksWhenGrabbed refers to (the reference saves that state and
+    /// evaluates lazily, kinbodygrab.cpp:63-200).  Lists of bodies grabbed earlier are kept, those of released bodies dropped.
     void _OnGrabbed(boost::weak_ptr<BodyInfo> winfo)
     {
         BodyInfoPtr pinfo = winfo.lock();
         if (!pinfo) return;
         pinfo->grabbedDirty = true;
         _DropQueries();
+        KinBodyPtr pbody = pinfo->body.lock();
+        if (!pbody) return;
+        std::vector<KinBodyPtr> vgrabbed;
+        pbody->GetGrabbed(vgrabbed);
+        std::map<int, std::vector<int32_t> > kept;
+        for (size_t g = 0; g < vgrabbed.size(); ++g) {
+            BodyInfoPtr ginfo = _InitKinBody(vgrabbed[g]);
+            std::map<int, std::vector<int32_t> >::iterator it = pinfo->grabLists.find(ginfo->id);
+            if (it != pinfo->grabLists.end()) kept[ginfo->id] = it->second;
+        }
+        pinfo->grabLists.swap(kept);
+        try {
+            _Synchronize();
+            for (size_t g = 0; g < vgrabbed.size(); ++g) {
+                const int gid = _Info(vgrabbed[g])->id;
+                if (pinfo->grabLists.find(gid) == pinfo->grabLists.end()) pinfo->grabLists[gid] = _NonCollidingList(pbody, pinfo, vgrabbed, g);
+            }
+        } catch (const std::exception& ex) {
+            RAVELOG_WARN_FORMAT("cudacollision: non-colliding list of a grabbed body deferred to the next query (%s)", ex.what());
+        }
     }
 
-    /// KinBody::_vGrabbedBodies -> cc_body_set_grabbed.  The reference evaluates Grabbed::_listNonCollidingLinksWhenGrabbed
-    /// lazily at the state saved when Grab was called (kinbodygrab.cpp:63-200); that list is private, so it is recomputed
-    /// here with this checker at the first query after the grab (the same state in the usual Grab -> plan sequence): links
-    /// of the grabber that are not rigidly attached to the grabbing link, not in the ignore set and not touching the
-    /// grabbed body, plus the non-touching links of the other grabbed bodies.
+    /// Grabbed::_listNonCollidingLinksWhenGrabbed of vgrabbed[g] at the CURRENT poses: links of the grabber that are not rigidly
+    /// attached to the grabbing link, not in the ignore set and not touching the grabbed body, plus the non-touching links of the
+    /// bodies grabbed before it (kinbodygrab.cpp:63-200), as (cc body id, link index) pairs
+    std::vector<int32_t> _NonCollidingList(KinBodyConstPtr pbody, BodyInfoPtr pinfo, const std::vector<KinBodyPtr>& vgrabbed, size_t g)
+    {
+        std::vector<int32_t> noncolliding;
+        KinBodyPtr pgrabbed = vgrabbed[g];
+        KinBody::LinkPtr plink = pbody->IsGrabbing(*pgrabbed);
+        if (!plink) return noncolliding;
+        BodyInfoPtr ginfo = _InitKinBody(pgrabbed);
+        std::vector<KinBody::LinkPtr> vrigid;
+        plink->GetRigidlyAttachedLinks(vrigid);
+        std::list<KinBody::LinkConstPtr> listignored;
+        pbody->GetIgnoredLinksOfGrabbed(pgrabbed, listignored);
+        std::vector<std::pair<KinBodyConstPtr, BodyInfoPtr> > vsources(1, std::make_pair(pbody, pinfo));
+        for (size_t o = 0; o < g; ++o) {
+            KinBody::LinkPtr potherlink = pbody->IsGrabbing(*vgrabbed[o]);
+            if (std::find(vrigid.begin(), vrigid.end(), potherlink) == vrigid.end()) vsources.push_back(std::make_pair(KinBodyConstPtr(vgrabbed[o]), _InitKinBody(vgrabbed[o])));
+        }
+        for (size_t isrc = 0; isrc < vsources.size(); ++isrc) {
+            FOREACHC(itlink, vsources[isrc].first->GetLinks()) {
+                if (isrc == 0 && (std::find(vrigid.begin(), vrigid.end(), *itlink) != vrigid.end() ||
+                                  std::find(listignored.begin(), listignored.end(), KinBody::LinkConstPtr(*itlink)) != listignored.end())) continue;
+                std::vector<int32_t> triples;
+                for (size_t k = 0; k < pgrabbed->GetLinks().size(); ++k) { triples.push_back((*itlink)->GetIndex()); triples.push_back(ginfo->id); triples.push_back((int)k); }
+                if (!_CheckPairs(vsources[isrc].first, triples, CollisionReportPtr(), true)) {
+                    noncolliding.push_back(vsources[isrc].second->id);
+                    noncolliding.push_back((*itlink)->GetIndex());
+                }
+            }
+        }
+        return noncolliding;
+    }
+
+    /// KinBody::_vGrabbedBodies -> cc_body_set_grabbed, with the lists _OnGrabbed computed at grab time (a list that could not
+    /// be computed then — the checker was attached to the environment after the grab — is computed now)
     void _SyncGrabbed(KinBodyConstPtr pbody, BodyInfoPtr pinfo)
     {
         if (!pinfo->grabbedDirty) return;
@@ -460,28 +527,8 @@ private:
             const Transform tinv = plink->GetTransform().inverse();
             std::vector<double> rel(8 * pgrabbed->GetLinks().size());
             for (size_t k = 0; k < pgrabbed->GetLinks().size(); ++k) PackTransform(tinv * pgrabbed->GetLinks()[k]->GetTransform(), &rel[8 * k]);
-            std::vector<KinBody::LinkPtr> vrigid;
-            plink->GetRigidlyAttachedLinks(vrigid);
-            std::list<KinBody::LinkConstPtr> listignored;
-            pbody->GetIgnoredLinksOfGrabbed(pgrabbed, listignored);
-            std::vector<int32_t> noncolliding;
-            std::vector<std::pair<KinBodyConstPtr, BodyInfoPtr> > vsources(1, std::make_pair(pbody, pinfo));
-            for (size_t o = 0; o < g; ++o) {
-                KinBody::LinkPtr potherlink = pbody->IsGrabbing(*vgrabbed[o]);
-                if (std::find(vrigid.begin(), vrigid.end(), potherlink) == vrigid.end()) vsources.push_back(std::make_pair(KinBodyConstPtr(vgrabbed[o]), _InitKinBody(vgrabbed[o])));
-            }
-            for (size_t isrc = 0; isrc < vsources.size(); ++isrc) {
-                FOREACHC(itlink, vsources[isrc].first->GetLinks()) {
-                    if (isrc == 0 && (std::find(vrigid.begin(), vrigid.end(), *itlink) != vrigid.end() ||
-                                      std::find(listignored.begin(), listignored.end(), KinBody::LinkConstPtr(*itlink)) != listignored.end())) continue;
-                    std::vector<int32_t> triples;
-                    for (size_t k = 0; k < pgrabbed->GetLinks().size(); ++k) { triples.push_back((*itlink)->GetIndex()); triples.push_back(ginfo->id); triples.push_back((int)k); }
-                    if (!_CheckPairs(vsources[isrc].first, triples, CollisionReportPtr(), true)) {
-                        noncolliding.push_back(vsources[isrc].second->id);
-                        noncolliding.push_back((*itlink)->GetIndex());
-                    }
-                }
-            }
+            if (pinfo->grabLists.find(ginfo->id) == pinfo->grabLists.end()) pinfo->grabLists[ginfo->id] = _NonCollidingList(pbody, pinfo, vgrabbed, g);
+            const std::vector<int32_t>& noncolliding = pinfo->grabLists[ginfo->id];
             _Check(cc_body_set_grabbed(_scene, pinfo->id, ginfo->id, plink->GetIndex(), rel.data(), noncolliding.data(), (int)noncolliding.size() / 2));
             _SyncKinematics(pgrabbed, ginfo);      // grabbedBody.CheckSelfCollision needs its non-adjacent list
         }
@@ -880,6 +927,8 @@ private:
     std::set<cc_query*> _stale;            // queries whose own body moved since their last refresh (matters to the FK-mode entry only)
 };
 
+#include "cudabatched.h"
+
 // ---------------------------------------------------------------------------------------------- planner: "cudabirrt"
 // RaveCreatePlanner(env, "cudabirrt"): BirrtPlanner's interface (plugins/rplanners/rrt.h:279-659) on cc_birrt_plan_batch.  InitPlan reads
 // the same RRTParameters (goal bias is BirrtPlanner's constant 0.01, rrt.h:315), PlanPath plans vinitialconfig -> vgoalconfig and
@@ -1001,12 +1050,18 @@ private:
 class CudaCollisionPlugin : public RavePlugin
 {
 public:
-    CudaCollisionPlugin() { _interfaces[PT_CollisionChecker].push_back("cudacollision"); _interfaces[PT_Planner].push_back("cudabirrt"); }
+    CudaCollisionPlugin()
+    {
+        _interfaces[PT_CollisionChecker].push_back("cudacollision"); _interfaces[PT_CollisionChecker].push_back("cudacachechecker");
+        _interfaces[PT_Planner].push_back("cudabirrt"); _interfaces[PT_Planner].push_back("cudabatched");
+    }
     virtual ~CudaCollisionPlugin() {}
     virtual InterfaceBasePtr CreateInterface(InterfaceType type, const std::string& interfacename, std::istream& sinput, EnvironmentBasePtr penv)
     {
         if (type == PT_CollisionChecker && interfacename == "cudacollision") return boost::make_shared<CudaCollisionChecker>(penv, boost::ref(sinput));
+        if (type == PT_CollisionChecker && interfacename == "cudacachechecker") return boost::make_shared<CudaCacheChecker>(penv, boost::ref(sinput));
         if (type == PT_Planner && interfacename == "cudabirrt") return boost::make_shared<CudaBirrtPlanner>(penv);
+        if (type == PT_Planner && interfacename == "cudabatched") return boost::make_shared<CudaBatchedPlanner>(penv, boost::ref(sinput));
         return InterfaceBasePtr();
     }
     virtual const InterfaceMap& GetInterfaces() const { return _interfaces; }
