@@ -132,6 +132,14 @@ struct Params {
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
+    // heavy configurations (a few need 50x the mean work and would make the whole persistent grid wait for one warp): a
+    // full-batch launch gives up on a configuration after `defer_budget` descent iterations and appends it to `heavy_out`
+    // (count in heavy_out_count); a second, split launch (`heavy_in` / `heavy_in_count`) then spreads each of them over `split` warps
+    int32_t defer_budget;       // 0: never give up
+    int32_t* heavy_out;
+    int32_t* heavy_out_count;
+    const int32_t* heavy_in;    // split launch over the deferred configurations instead of [0, n)
+    const int32_t* heavy_in_count;
     // split traversal (small batches): every configuration becomes `split` work items, item `part` owning the pairs
     // [part_begin[part], part_begin[part + 1]) of `pairs` / `pair_orig` (round-robin blocks of the reference order, env pairs
     // first: part_nenv[part] of them); results are combined with atomics into outputs the FK kernel initialised
@@ -620,7 +628,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const uint32_t* pairs = P.pairs;
     const int32_t* pair_orig = P.pair_orig;
     const int32_t* ptable = P.pair_table;
-    const int nwork = kSplit ? P.n * P.split : P.n;
+    const int nwork = kSplit ? (P.heavy_in ? __ldg(P.heavy_in_count) : P.n) * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
     // pose scratch: the slots of one configuration are contiguous ([cap][ndyn][12] / [cap][ndyn][8]).  The slot-major alternative
     // (coalesced FK stores, scattered traversal reads) measured 5 % slower on PR2 and 30 % slower on the clutter scene
@@ -636,6 +644,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             const int w = c;
             c = w / P.split;
             const int part = w - c * P.split;
+            if (P.heavy_in) c = __ldg(&P.heavy_in[c]);
             const int pb = __ldg(&P.part_begin[part]);
             pairs = P.pairs + pb; pair_orig = P.pair_orig + pb;
             if (kTables) ptable = P.pair_table + pb;
@@ -663,6 +672,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         uint32_t slot_dead = 0;    // slots whose items are no longer wanted (contact found, or preceded by a contact); non-zero
                                    // also means refills from the spill area have to be filtered
         bool failed = false;
+        bool deferred = false;     // gave up on this configuration: the split launch that follows redoes it on several warps
         uint32_t iters = P.hoisted_first_self != kNone ? 0x80000000u : 0u;     // bit 31: a self contact was really found (first-hit mode)
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
         int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
@@ -877,6 +887,10 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
                     const int n = sp < 32 ? sp : 32;
                     ++iters;
+                    if (!kSplit && !kContacts && P.defer_budget > 0 && (int)(iters & 0x7fffffffu) > P.defer_budget) {
+                        deferred = true; failed = true; sp = 0; ntri = 0; ntri2 = 0; spill_count = 0;
+                        break;
+                    }
                     const bool valid = lane < n;
                     uint2 it = make_uint2(0u, 0u);
                     if (valid) it = stack[sp - 1 - lane];
@@ -994,6 +1008,18 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         }
 
         // ---------------------------------------------------------------- verdict
+        if (deferred) {
+            // hand the configuration over with neutral outputs: the split launch merges its parts into them with atomics
+            if (lane == 0) {
+                if (P.verdict) P.verdict[c] = 0u;
+                if (P.first_env) P.first_env[c] = -1;
+                if (P.first_self) P.first_self[c] = -1;
+                if (P.work_out) P.work_out[c] = iters & 0x7fffffffu;
+                P.heavy_out[atomicAdd(P.heavy_out_count, 1)] = c;
+            }
+            __syncwarp();
+            continue;
+        }
         if (lane == 0) {
             int be = best_env, bs = best_self;
             if (mask_row) {

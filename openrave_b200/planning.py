@@ -441,6 +441,53 @@ class DynamicsCollisionConstraint(object):
         return self._finish(s, t, codes, options, filterreturn)
 
 
+class BatchedPathConstraint(DynamicsCollisionConstraint):
+    """Twin of plugins/cudacollision/cudabatched.h::BatchedPathConstraint — what PlannerParameters::_checkpathvelocityconstraintsfn
+    is rebound to so that UNMODIFIED stock planners batch every edge: same call signature and ConstraintFilterReturn as
+    DynamicsCollisionConstraint.Check, but the edge goes to the GPU in one cc_planner_check_edges call (sample generation,
+    +/- perturbation copies, first failing sample, return code all inside the library)."""
+
+    def __init__(self, robot, checker, perturbation=0.1):
+        DynamicsCollisionConstraint.__init__(self, robot, checker, perturbation=perturbation)
+        self._planner = BirrtPlanner(robot, checker)
+        self.edges = 0
+        self.samples = 0
+
+    def Check(self, q0, q1, interval=IT_Closed, options=0xffff | CFO_CheckWithPerturbation | CFO_FillCheckedConfiguration,
+              filterreturn=None, dq0=None, dq1=None, timeelapsed=0.0):
+        P = self._planner
+        ramp = timeelapsed > 0 and dq0 is not None and dq1 is not None
+        opts = options & (CFO_CheckEnvCollisions | CFO_CheckSelfCollisions | CFO_CheckWithPerturbation)
+        r = P.CheckEdges(q0, q1, interval, opts, self.perturbation, dq0 if ramp else None, dq1 if ramp else None,
+                         [timeelapsed] if ramp else None)[0]
+        self.edges += 1
+        self.samples += max(r["nsamples"], 0)
+        code = r["return_code"]
+        if filterreturn is not None:
+            filterreturn.Clear()
+            filterreturn._returncode = code
+            first = r["first_invalid"]
+            if code and first >= 0:
+                filterreturn._invalidvalues = r["invalid_values"].tolist()
+                filterreturn._fTimeWhenInvalid = r["time_when_invalid"]
+            if (options & CFO_FillCheckedConfiguration) and code != CFO_StateSettingError:
+                if ramp:
+                    s, t, kinds = P.RampSamples(q0, q1, dq0, dq1, timeelapsed, interval)
+                    endfirst = interval in (IT_OpenStart, IT_Closed)
+                else:
+                    s, t = P.EdgeSamples(q0, q1, interval), P.EdgeSampleTimes(q0, q1, interval)
+                    kinds = np.ones(len(s), dtype=np.int64)
+                    endfirst = len(t) > 0 and t[0] == 1.0
+                upto = len(s) if first < 0 else min(len(s), first + 1)
+                order = list(range(upto))
+                if first < 0 and endfirst and len(order) > 1:
+                    order = order[1:] + [0]
+                order = [i for i in order if kinds[i] == 1]
+                filterreturn._configurations = [s[i].tolist() for i in order]
+                filterreturn._configurationtimes = [float(t[i]) for i in order]
+        return code
+
+
 def CheckPathAllConstraints(constraint, q0, q1, interval=IT_Closed, options=0xffff, filterreturn=None):
     """PlannerParameters::CheckPathAllConstraints (planner.h:373-379) for positions-only edges."""
     return constraint.Check(q0, q1, interval, options, filterreturn)
@@ -663,6 +710,7 @@ def _planner_lib():
     lib.cc_planner_set_query.argtypes = [vp, vp]
     lib.cc_planner_set_checker.argtypes = [vp, vp, vp]
     lib.cc_planner_edge_samples.argtypes = [vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
+    lib.cc_planner_edge_sample_times.argtypes = [vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_ramp_samples.argtypes = [vp, vp, vp, vp, vp, ctypes.c_double, ci, vp, vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_check_edges.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, ci, ctypes.c_double, vp, vp]
     lib.cc_birrt_plan_batch.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp]
@@ -732,6 +780,19 @@ class BirrtPlanner(object):
         out = np.zeros((max(cnt.value, 1), self.ndof))
         self._ck(self.lib.cc_planner_edge_samples(self.handle, q0.ctypes.data, q1.ctypes.data, interval, out.ctypes.data,
                                                   cnt.value, ctypes.byref(cnt)))
+        return out[:cnt.value]
+
+    def EdgeSampleTimes(self, q0, q1, interval=IT_Closed):
+        """ConstraintFilterReturn::_configurationtimes of EdgeSamples' rows (cc_planner_edge_sample_times)."""
+        q0 = np.ascontiguousarray(q0, dtype=np.float64)
+        q1 = np.ascontiguousarray(q1, dtype=np.float64)
+        cnt = ctypes.c_int(0)
+        self._ck(self.lib.cc_planner_edge_sample_times(self.handle, q0.ctypes.data, q1.ctypes.data, interval, None, 0, ctypes.byref(cnt)))
+        if cnt.value < 0:
+            return None
+        out = np.zeros(max(cnt.value, 1))
+        self._ck(self.lib.cc_planner_edge_sample_times(self.handle, q0.ctypes.data, q1.ctypes.data, interval, out.ctypes.data,
+                                                       cnt.value, ctypes.byref(cnt)))
         return out[:cnt.value]
 
     def RampSamples(self, q0, q1, dq0, dq1, timeelapsed, interval=IT_Closed):

@@ -96,8 +96,8 @@ public:
     uint64_t GetNumSamples() const { return _nsamples; }
 
 private:
-    /// ConstraintFilterReturn::_configurations / _configurationtimes: the samples the check visited, in time order, up to the
-    /// failing one (planningutils.cpp:2801-2813, 3410-3413; ramps: 3611-3623 report only the ramp samples)
+    /// ConstraintFilterReturn::_configurations / _configurationtimes: the samples the check visited, up to the failing one
+    /// (planningutils.cpp:2801-2813, 3410-3413)
     void _FillConfigurations(const std::vector<dReal>& q0, const std::vector<dReal>& q1, const std::vector<dReal>& dq0, const std::vector<dReal>& dq1,
                              bool ramp, double T, IntervalType interval, const cc_edge_result& result, ConstraintFilterReturn& ret)
     {
@@ -110,14 +110,15 @@ private:
             cc_planner_edge_sample_times(_planner, q0.data(), q1.data(), (int)interval, _times.data(), cap, &count);
         }
         count = std::min(count, cap);
+        // checking order up to the failing sample; the end point — checked first — is reported last when the whole edge passed
+        // (planningutils.cpp:3613-3624); ramps report only their ramp samples (:3611-3623)
+        const int upto = result.first_invalid < 0 ? count : std::min(count, result.first_invalid + 1);
         std::vector<int> order;
-        for (int i = 0; i < count; ++i) {
-            if (_kinds[i] != CC_RAMP_REPORTED) continue;
-            if (result.first_invalid >= 0 && _times[i] > result.time_when_invalid) continue;
-            order.push_back(i);
-        }
-        std::stable_sort(order.begin(), order.end(), [this](int a, int b) { return _times[a] < _times[b]; });
+        for (int i = 0; i < upto; ++i) order.push_back(i);
+        const bool endfirst = ramp ? (interval == IT_OpenStart || interval == IT_Closed) : (count > 0 && _times[0] == 1.0);
+        if (result.first_invalid < 0 && endfirst && order.size() > 1) std::rotate(order.begin(), order.begin() + 1, order.end());
         FOREACHC(it, order) {
+            if (_kinds[*it] != CC_RAMP_REPORTED) continue;
             ret._configurations.insert(ret._configurations.end(), _samples.begin() + (size_t)*it * _ndof, _samples.begin() + (size_t)(*it + 1) * _ndof);
             ret._configurationtimes.push_back(_times[*it]);
         }
