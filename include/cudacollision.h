@@ -182,6 +182,16 @@ int cc_scene_commit(cc_scene* s);
  *   initial-pose probe (kinbody.cpp:5563-5577). */
 int cc_query_create(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out);
 int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out);
+/* cc_query_create with AFFINE active DOFs (RobotBase::SetActiveDOFs(dofindices, affine, rotationaxis); robot.cpp:1193-1225,
+ * planner.cpp:658-667 — base planning).  affine_dofs: OpenRAVE::DOFAffine bits (same values).  A row of q then holds the nactive
+ * joint values followed by X | Y | Z (those that are set) and ONE rotation: RotationAxis (angle about rotation_axis3),
+ * Rotation3D (axis * angle, 3 values) or RotationQuat (4 values; normalised and left-multiplied by quat_limit_start4 =
+ * RobotBase::_vRotationQuatLimitStart, NULL = identity): RaveGetTransformFromAffineDOFValues (libopenrave.cpp:1868-1924)
+ * applied to the body's pose at bind time (the components that are not active keep their bound values).  Every link moves
+ * with the base, so no environment pair is hoisted; self pairs are hoisted as usual.  No free-space certificates. */
+enum cc_affine_dofs { CC_DOF_X = 1, CC_DOF_Y = 2, CC_DOF_Z = 4, CC_DOF_RotationAxis = 8, CC_DOF_Rotation3D = 16, CC_DOF_RotationQuat = 32 };
+int cc_query_create_affine(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int affine_dofs, const double* rotation_axis3,
+                           const double* quat_limit_start4, int options, cc_query** out);
 /* A bound query captures, at creation, the poses of every link it does not move itself (other bodies' links, links of the
  * query body no active DOF moves, the base link) and the values of the inactive DOFs.  After cc_body_set_link_transforms /
  * cc_body_set_dof_values on ANY body, cc_query_refresh re-reads them (a few small uploads and the re-evaluation of the

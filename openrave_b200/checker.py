@@ -58,7 +58,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
            "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates",
-           "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices"]
+           "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices", "cc_query_create_affine"]
 
 _lib = None
 
@@ -92,6 +92,7 @@ def load_library():
     lib.cc_scene_commit.argtypes = [vp]
     lib.cc_query_create.argtypes = [vp, ci, vp, ci, ci, ctypes.POINTER(vp)]
     lib.cc_query_create_pairs.argtypes = [vp, ci, vp, ci, ctypes.POINTER(vp)]
+    lib.cc_query_create_affine.argtypes = [vp, ci, vp, ci, ci, vp, vp, ci, ctypes.POINTER(vp)]
     lib.cc_query_destroy.argtypes = [vp]
     lib.cc_query_refresh.argtypes = [vp]
     lib.cc_query_get_info.argtypes = [vp, ctypes.POINTER(cc_query_info)]
@@ -522,11 +523,19 @@ class CudaCollisionChecker(object):
         opts = self._options if options is None else options
         if active is None and body.is_robot and body.active_dofs is not None:
             active = body.GetActiveDOFIndices()
-        key = (bid, tuple(active) if active is not None else None, opts)
+        affine = int(getattr(body, "affine_dofs", 0)) if body.is_robot else 0
+        key = (bid, tuple(active) if active is not None else None, opts, affine, tuple(getattr(body, "affine_axis", ())) if affine else ())
         q = self._queries.get(key)
         if q is None:
             h = ctypes.c_void_p()
-            if active is None:
+            if affine:
+                # RobotBase::SetActiveDOFs(indices, affine, axis): the affine values follow the joint values in every row
+                act = np.array(list(active) if active is not None else list(range(body.GetDOF())), dtype=np.int32)
+                axis = np.array(body.affine_axis, dtype=np.float64)
+                qs = np.array(body.affine_quat_start, dtype=np.float64)
+                self._ck(self.lib.cc_query_create_affine(self.scene, bid, _ptr(act) if len(act) else None, len(act), affine, _ptr(axis), _ptr(qs),
+                                                         opts, ctypes.byref(h)))
+            elif active is None:
                 self._ck(self.lib.cc_query_create(self.scene, bid, None, 0, opts, ctypes.byref(h)))
             else:
                 act = np.array(active, dtype=np.int32)

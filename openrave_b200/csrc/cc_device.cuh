@@ -111,6 +111,12 @@ struct Params {
     int32_t nq, ndyn, nstatic, npairs_dev, nenv_dev, nenv_total, nsteps, ncols;
     int32_t hoisted_first_env, hoisted_first_self, mask_words, flags;
     double base[8];             // pose of link 0 (kept, kinbody.cpp:2281)
+    // affine active DOFs (RobotBase::SetActiveDOFValues, robot.cpp:1193-1225): the columns [affine_col, ..) of q hold X | Y | Z and one
+    // of RotationAxis (angle) | Rotation3D (axis * angle) | RotationQuat (4, normalised, left-multiplied by affine_qstart) and
+    // overwrite those components of link 0's pose per configuration (RaveGetTransformFromAffineDOFValues, libopenrave.cpp:1868-1924)
+    int32_t affine_mask, affine_col;
+    double affine_axis[4];
+    double affine_qstart[4];
     double center[3];           // subtracted from every translation before the FP32 conversion
     float tri_eps;              // conservative margin of the triangle test (metres), 0 = reference's strict test
     // io (already offset to this chunk)
@@ -465,13 +471,44 @@ __device__ __forceinline__ Xf joint_transform(const FkStep& st, const double* __
     return xf_mul(xf_mul(L, J), xf_load(st.R));       // (L * J) * R, kinbody.cpp:2478
 }
 
+// Link 0's pose of one configuration when the active DOFs include affine ones.  Same bit values as OpenRAVE::DOFAffine.
+__device__ __forceinline__ Xf affine_base(const Params& P, Xf t, const double* __restrict__ a)
+{
+    const int m = P.affine_mask;
+    if (m & 1) t.tx = *a++;
+    if (m & 2) t.ty = *a++;
+    if (m & 4) t.tz = *a++;
+    if (m & 8) {                                   // DOF_RotationAxis
+        double sn, cs; sincos(*a * 0.5, &sn, &cs);
+        t.q0 = cs; t.q1 = P.affine_axis[0] * sn; t.q2 = P.affine_axis[1] * sn; t.q3 = P.affine_axis[2] * sn;
+    } else if (m & 16) {                           // DOF_Rotation3D: axis * angle
+        const double x = a[0], y = a[1], z = a[2];
+        const double ang = sqrt(x * x + y * y + z * z);
+        if (ang > 0) {
+            double sn, cs; sincos(0.5 * ang, &sn, &cs);
+            const double f = sn / ang;
+            t.q0 = cs; t.q1 = f * x; t.q2 = f * y; t.q3 = f * z;
+        } else { t.q0 = 1; t.q1 = t.q2 = t.q3 = 0; }
+    } else if (m & 32) {                           // DOF_RotationQuat: normalize4, then _vRotationQuatLimitStart * q (robot.cpp:1205-1207)
+        double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3];
+        quat_normalize(r0, r1, r2, r3);
+        const double* s = P.affine_qstart;
+        t.q0 = s[0] * r0 - s[1] * r1 - s[2] * r2 - s[3] * r3;
+        t.q1 = s[0] * r1 + s[1] * r0 + s[2] * r3 - s[3] * r2;
+        t.q2 = s[0] * r2 + s[2] * r0 + s[3] * r1 - s[1] * r3;
+        t.q3 = s[0] * r3 + s[3] * r0 + s[1] * r2 - s[2] * r1;
+    }
+    return t;
+}
+
 // KinBody::SetDOFValues' joint loop for configuration c (kinbody.cpp:2286-2481): the chain program is walked depth-first with
 // the running transform in registers; poses later branches start from are parked through D.save.
 __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, const float* linkbox, const int32_t* emit, const FkDst& D, int c)
 {
-    const Xf base = xf_load(P.base);
-    emit_link(P, linkbox, D, c, 0, emit[0], base);                // link 0 keeps its pose (kinbody.cpp:2281)
     const double* qrow = P.q + (size_t)c * P.ncols;
+    Xf base = xf_load(P.base);                                    // link 0 keeps its pose (kinbody.cpp:2281) ...
+    if (P.affine_mask) base = affine_base(P, base, qrow + P.affine_col);      // ... unless affine DOFs are active
+    emit_link(P, linkbox, D, c, 0, emit[0], base);
     Xf cur = base;
     const size_t ps = D.save_pose_stride, cs = D.save_comp_stride;
     for (int s = 0; s < P.nsteps; ++s) {

@@ -419,6 +419,8 @@ struct cc_query {
     bool trace_work = false;
     int work_n = 0;
     std::vector<cc_query*> peers;            // the same query bound on every peer replica of a multi-device scene
+    int affine_mask = 0, naffine = 0;        // affine active DOFs: their columns follow the joint columns of q
+    double affine_axis[4] = {0, 0, 1, 0}, affine_qstart[4] = {1, 0, 0, 0};
     // staging for the host-buffer API
     DevBuf<double> d_q, d_fk;
     DevBuf<uint32_t> d_verdict, d_mask;
@@ -478,6 +480,8 @@ void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev
     P.flags = flags | (S->counters ? ccdev::kFlagCounters : 0);
     memcpy(P.base, Q->base, sizeof(P.base));
     memcpy(P.center, Q->center, sizeof(P.center));
+    P.affine_mask = Q->affine_mask; P.affine_col = Q->ncols - Q->naffine;
+    memcpy(P.affine_axis, Q->affine_axis, sizeof(P.affine_axis)); memcpy(P.affine_qstart, Q->affine_qstart, sizeof(P.affine_qstart));
     P.tri_eps = S->tri_eps;
     P.err_flag = S->d_err;
     P.stats = S->d_stats.p;
@@ -1351,14 +1355,22 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         if (act[c] < 0 || act[c] >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
         col_of_dof[act[c]] = (int)c;
     }
-    Q->ncols = (int)act.size();
+    Q->ncols = (int)act.size() + Q->naffine;
     Q->col_of_dof = col_of_dof;
-    Q->cur_active.resize(act.size());
+    Q->cur_active.assign((size_t)Q->ncols, 0.0);
     for (size_t c = 0; c < act.size(); ++c) Q->cur_active[c] = B->dofvals[act[c]];
+    if (Q->naffine) {
+        // the bound pose in affine coordinates — only the translation matters: the pairs evaluated at the bound values are the
+        // pose-invariant (self) ones, and a base rotation does not change them
+        size_t c = act.size();
+        for (int k = 0; k < 3; ++k) if (Q->affine_mask & (1 << k)) Q->cur_active[c++] = B->links.empty() ? 0.0 : B->links[0].xf[4 + k];
+        if (Q->affine_mask & CC_DOF_RotationQuat) Q->cur_active[c] = 1.0;
+    }
     auto affects = [&](int d, int l) { return B->affects[(size_t)d * nlb + Q->ql_host[l]] != 0; };
     std::vector<uint8_t> moves(nl, 0);
     for (int l = 0; l < nl; ++l)
         for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
+    if (Q->naffine) std::fill(moves.begin(), moves.end(), (uint8_t)1);        // the base moves: so does every link
 
     // ---- FK chain program
     Q->has_fk = true;
@@ -1457,7 +1469,7 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     Q->p_hoist = p_hoist;
     Q->moves = moves;
     Q->p_full = p_full;
-    Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size();     // not with grabbed links (their chain is not walked below)
+    Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size() && !Q->naffine;     // not with grabbed links (their chain is not walked below), not with a moving base
     Q->pose_epoch = S->pose_epoch;           // everything below reads the live scene state: that IS the query's snapshot
     int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
@@ -1468,7 +1480,8 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     return CC_OK;
 }
 
-static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out);
+struct AffineSpec { int mask = 0; double axis[3] = {0, 0, 1}; double qstart[4] = {1, 0, 0, 0}; };
+static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out, const AffineSpec* affine = nullptr);
 static int query_create_pairs_one(cc_scene* s, int body, const int32_t* triples, int ntriples, cc_query** out);
 
 }  // extern "C"
@@ -1510,7 +1523,37 @@ int cc_query_create_pairs(cc_scene* s, int body, const int32_t* triples, int ntr
     return CC_OK;
 }
 
-static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out)
+int cc_query_create_affine(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int affine_dofs, const double* rotation_axis3,
+                           const double* quat_limit_start4, int options, cc_query** out)
+{
+    if (!s || !out || affine_dofs < 0 || affine_dofs > 63) return fail(CC_ERR_INVALID, "bad arguments");
+    const int nrot = ((affine_dofs & CC_DOF_RotationAxis) ? 1 : 0) + ((affine_dofs & CC_DOF_Rotation3D) ? 1 : 0) + ((affine_dofs & CC_DOF_RotationQuat) ? 1 : 0);
+    if (nrot > 1) return fail(CC_ERR_INVALID, "only one rotation parameterisation may be active");
+    if ((affine_dofs & CC_DOF_RotationAxis) && !rotation_axis3) return fail(CC_ERR_INVALID, "DOF_RotationAxis needs its axis");
+    if (affine_dofs == 0) return cc_query_create(s, body, active_dofs, nactive, options, out);
+    if (active_dofs == nullptr && nactive == 0) {
+        // (an empty joint list with affine DOFs is legitimate: pure base motion; NULL means "all joints" for cc_query_create only)
+        static const int32_t none = 0;
+        active_dofs = &none;
+    }
+    AffineSpec A;
+    A.mask = affine_dofs;
+    if (rotation_axis3) {
+        const double len = sqrt(rotation_axis3[0] * rotation_axis3[0] + rotation_axis3[1] * rotation_axis3[1] + rotation_axis3[2] * rotation_axis3[2]);
+        if (!(len > 0)) return fail(CC_ERR_INVALID, "zero rotation axis");
+        for (int k = 0; k < 3; ++k) A.axis[k] = rotation_axis3[k];
+    }
+    if (quat_limit_start4) for (int k = 0; k < 4; ++k) A.qstart[k] = quat_limit_start4[k];
+    cc_query* Q = nullptr;
+    int rc = query_create_one(s, body, active_dofs, nactive, options, &Q, &A);
+    if (rc != CC_OK) return rc;
+    rc = bind_on_peers(s, Q, [&](cc_scene* p, cc_query** o) { return query_create_one(p, body, active_dofs, nactive, options, o, &A); });
+    if (rc != CC_OK) return rc;
+    *out = Q;
+    return CC_OK;
+}
+
+static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, int nactive, int options, cc_query** out, const AffineSpec* affine)
 {
     HBody* B = get_body(s, body);
     if (!B || !out || nactive < 0 || (nactive > 0 && !active_dofs)) return fail(CC_ERR_INVALID, "bad arguments");
@@ -1523,6 +1566,13 @@ static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, i
     for (int d : act) if (d < 0 || d >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
     cc_query* Q = new cc_query();
     Q->scene = s; Q->body = body;
+    if (affine && affine->mask) {
+        Q->affine_mask = affine->mask;
+        Q->naffine = ((affine->mask & 1) ? 1 : 0) + ((affine->mask & 2) ? 1 : 0) + ((affine->mask & 4) ? 1 : 0) + ((affine->mask & CC_DOF_RotationAxis) ? 1 : 0) +
+                     ((affine->mask & CC_DOF_Rotation3D) ? 3 : 0) + ((affine->mask & CC_DOF_RotationQuat) ? 4 : 0);
+        for (int k = 0; k < 3; ++k) Q->affine_axis[k] = affine->axis[k];
+        for (int k = 0; k < 4; ++k) Q->affine_qstart[k] = affine->qstart[k];
+    }
     // query links: the body's own, then every grabbed body's in grab order
     for (int l = 0; l < nlb; ++l) { Q->ql_body.push_back(body); Q->ql_link.push_back(l); Q->ql_host.push_back(l); Q->ql_grab.push_back(-1); }
     std::vector<int> grab_base(B->grabs.size(), 0);
@@ -1546,7 +1596,7 @@ static int query_create_one(cc_scene* s, int body, const int32_t* active_dofs, i
     // _IsActiveLink (collisionPQP.h:710-735): only links of the active robot itself are filtered, grabbed links never
     std::vector<uint8_t> active_link(nl, 1);
     const bool filter = (options & CC_CO_ActiveDOFs) && B->is_robot;
-    if (filter) {
+    if (filter && !(affine && affine->mask)) {           // with affine DOFs every link is active (collisionPQP.h:716-719)
         for (int l = 0; l < nlb; ++l) {
             active_link[l] = 0;
             for (int d : act) if (B->affects[(size_t)d * nlb + l]) { active_link[l] = 1; break; }

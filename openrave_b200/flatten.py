@@ -97,3 +97,12 @@ def grab_tables(body, body_id):
         nc = np.array([(body_id(l.body), l.index) for l in g.noncolliding], dtype=np.int32).reshape(-1, 2)
         out.append((body_id(g.body), g.link.index, rel, nc))
     return out
+
+
+DOF_X, DOF_Y, DOF_Z, DOF_RotationAxis, DOF_Rotation3D, DOF_RotationQuat = 1, 2, 4, 8, 16, 32      # OpenRAVE::DOFAffine (openrave.h:2540-2551)
+
+
+def affine_count(mask):
+    """RaveGetAffineDOF: how many values the affine DOFs of `mask` add to an active-DOF vector."""
+    return sum(1 for b in (DOF_X, DOF_Y, DOF_Z, DOF_RotationAxis) if mask & b) + (3 if mask & DOF_Rotation3D else 0) + \
+        (4 if mask & DOF_RotationQuat else 0)

@@ -962,8 +962,13 @@ class Robot(KinBody):
     def GetActiveManipulator(self):
         return self.manipulators[self.active_manip] if self.manipulators else None
 
-    def SetActiveDOFs(self, indices):
+    def SetActiveDOFs(self, indices, affine=0, rotationaxis=(0.0, 0.0, 1.0)):
+        """RobotBase::SetActiveDOFs(dofindices, affine, rotationaxis) (robot.cpp:1130-1190): joint DOFs plus OpenRAVE::DOFAffine
+        bits; an active-DOF vector is the joint values followed by X | Y | Z and one rotation parameterisation."""
         self.active_dofs = [int(i) for i in indices]
+        self.affine_dofs = int(affine)
+        self.affine_axis = tuple(float(x) for x in rotationaxis)
+        self.affine_quat_start = (1.0, 0.0, 0.0, 0.0)                      # _vRotationQuatLimitStart (robot.cpp:826)
         self._nonadjacent_cache = {k: v for k, v in self._nonadjacent_cache.items() if not (k[1] & AO_ActiveDOFs)}
         if self.env is not None:
             self.env._body_changed(self)
@@ -971,11 +976,46 @@ class Robot(KinBody):
     def GetActiveDOFIndices(self):
         return list(range(self.GetDOF())) if self.active_dofs is None else list(self.active_dofs)
 
+    def GetAffineDOF(self):
+        return int(getattr(self, "affine_dofs", 0))
+
     def GetActiveDOF(self):
-        return len(self.GetActiveDOFIndices())
+        from .flatten import affine_count
+        return len(self.GetActiveDOFIndices()) + affine_count(self.GetAffineDOF())
 
     def SetActiveDOFValues(self, values):
-        self.SetDOFValues(values, self.GetActiveDOFIndices())
+        """RobotBase::SetActiveDOFValues (robot.cpp:1193-1225): the affine values overwrite components of the base pose
+        (RaveGetTransformFromAffineDOFValues, libopenrave.cpp:1868-1924), then SetDOFValues(joints, transform)."""
+        idx = self.GetActiveDOFIndices()
+        m = self.GetAffineDOF()
+        if not m:
+            self.SetDOFValues(values, idx)
+            return
+        a = [float(v) for v in values[len(idx):]]
+        q, t = self.links[0].t
+        q, t = list(q), list(t)
+        k = 0
+        for bit, comp in ((1, 0), (2, 1), (4, 2)):
+            if m & bit:
+                t[comp] = a[k]
+                k += 1
+        if m & 8:
+            s = math.sin(a[k] * 0.5)
+            q = [math.cos(a[k] * 0.5), self.affine_axis[0] * s, self.affine_axis[1] * s, self.affine_axis[2] * s]
+        elif m & 16:
+            x, y, z = a[k:k + 3]
+            ang = math.sqrt(x * x + y * y + z * z)
+            if ang > 0:
+                f = math.sin(0.5 * ang) / ang
+                q = [math.cos(0.5 * ang), f * x, f * y, f * z]
+            else:
+                q = [1.0, 0.0, 0.0, 0.0]
+        elif m & 32:
+            r = rm.normalize4(tuple(a[k:k + 4]))
+            q = list(rm.quat_mul_raw(self.affine_quat_start, r))
+        self.SetTransform((tuple(q), tuple(t)))
+        if idx:
+            self.SetDOFValues(list(values[:len(idx)]), idx)
 
     def GetActiveDOFLimits(self):
         lo, hi = self.GetDOFLimits()

@@ -74,6 +74,7 @@ def _load(kind):
     lib.orc_body_set_removed.argtypes = [vp, ci, ci]
     lib.orc_body_set_kinematics.argtypes = [vp, ci, ci, ci, vp, vp, vp]
     lib.orc_body_set_nonadjacent_pairs.argtypes = [vp, ci, vp, ci]
+    lib.orc_body_set_affine.argtypes = [vp, ci, ci, vp, vp]
     lib.orc_check_link_pairs.argtypes = [vp, ci, vp, vp, ci, vp]
     lib.orc_check_batch.argtypes = [vp, ci, vp, ci, ctypes.POINTER(OrcOptions), vp, ci, vp, vp, vp, vp, vp, vp, vp,
                                     ctypes.c_int64, vp, vp]
@@ -197,6 +198,10 @@ class OracleChecker(object):
         else:
             na = np.zeros(0, dtype=np.int32)
         self.lib.orc_body_set_nonadjacent_pairs(self.scene, bid, _ptr(na), int(na.size))
+        mask = int(getattr(body, "affine_dofs", 0))
+        axis = np.array(getattr(body, "affine_axis", (0.0, 0.0, 1.0)), dtype=np.float64)
+        qstart = np.array(getattr(body, "affine_quat_start", (1.0, 0.0, 0.0, 0.0)), dtype=np.float64)
+        self.lib.orc_body_set_affine(self.scene, bid, mask, _ptr(axis), _ptr(qstart))
         return bid
 
     def _check_link_pairs_at(self, body, transforms, pairs):
@@ -226,7 +231,7 @@ class OracleChecker(object):
             n = q.shape[0]
             opt.pose_mode = 1
         else:
-            q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active))
+            q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active) + flatten.affine_count(getattr(body, "affine_dofs", 0)))
             n = q.shape[0]
         nl = len(body.links) + sum(len(g.body.links) for g in getattr(body, "grabbed", []))   # grabbed links follow the body's own
         verdict = np.zeros(n, dtype=np.uint32)

@@ -956,7 +956,12 @@ struct Body {
         std::vector<int32_t> noncolliding;   // (body, link) pairs: _listNonCollidingLinksWhenGrabbed
     };
     std::vector<Grab> grabs;
-    Body() : is_robot(false), removed(false), ndof(0) {}
+    // affine active DOFs (RobotBase::SetActiveDOFs(indices, affine, axis)): bits of OpenRAVE::DOFAffine, the rotation axis of
+    // DOF_RotationAxis and _vRotationQuatLimitStart; their values follow the joint values in every row of a batch
+    int affine_mask;
+    double affine_axis[3];
+    double affine_qstart[4];
+    Body() : is_robot(false), removed(false), ndof(0), affine_mask(0) { affine_axis[0] = affine_axis[1] = 0; affine_axis[2] = 1; affine_qstart[0] = 1; affine_qstart[1] = affine_qstart[2] = affine_qstart[3] = 0; }
     ~Body() { for (size_t i = 0; i < links.size(); ++i) delete links[i]; }
 };
 
@@ -964,6 +969,36 @@ struct Scene {
     std::vector<Body*> bodies;
     ~Scene() { for (size_t i = 0; i < bodies.size(); ++i) delete bodies[i]; }
 };
+
+static int affine_count(int m) { return ((m & 1) ? 1 : 0) + ((m & 2) ? 1 : 0) + ((m & 4) ? 1 : 0) + ((m & 8) ? 1 : 0) + ((m & 16) ? 3 : 0) + ((m & 32) ? 4 : 0); }
+
+// RaveGetTransformFromAffineDOFValues (libopenrave.cpp:1868-1924) + the _vRotationQuatLimitStart product of
+// RobotBase::SetActiveDOFValues (robot.cpp:1203-1207), applied to the body's current pose t
+static Xf affine_transform(const Body& b, Xf t, const double* a)
+{
+    const int m = b.affine_mask;
+    if (m & 1) t.t[0] = *a++;
+    if (m & 2) t.t[1] = *a++;
+    if (m & 4) t.t[2] = *a++;
+    if (m & 8) {
+        const double angle = *a++, fsin = sin(angle * 0.5);
+        t.q[0] = cos(angle * 0.5); t.q[1] = b.affine_axis[0] * fsin; t.q[2] = b.affine_axis[1] * fsin; t.q[3] = b.affine_axis[2] * fsin;
+    } else if (m & 16) {
+        const double x = a[0], y = a[1], z = a[2], fang = sqrt(x * x + y * y + z * z);
+        if (fang > 0) { const double f = sin(0.5 * fang) / fang; t.q[0] = cos(0.5 * fang); t.q[1] = f * x; t.q[2] = f * y; t.q[3] = f * z; }
+        else { t.q[0] = 1; t.q[1] = t.q[2] = t.q[3] = 0; }
+    } else if (m & 32) {
+        double r[4] = {a[0], a[1], a[2], a[3]};
+        double f = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+        if (f < 1 - 2.220446049250313e-16 || f > 1 + 2.220446049250313e-16) { f = sqrt(f); for (int k = 0; k < 4; ++k) r[k] /= f; }      // normalize4
+        const double* s = b.affine_qstart;                                                                                                 // quatMultiply(start, r)
+        t.q[0] = s[0] * r[0] - s[1] * r[1] - s[2] * r[2] - s[3] * r[3];
+        t.q[1] = s[0] * r[1] + s[1] * r[0] + s[2] * r[3] - s[3] * r[2];
+        t.q[2] = s[0] * r[2] + s[2] * r[0] + s[3] * r[1] - s[1] * r[3];
+        t.q[3] = s[0] * r[3] + s[3] * r[0] + s[1] * r[2] - s[2] * r[1];
+    }
+    return t;
+}
 
 // KinBody::SetDOFValues' joint loop.  `vals` holds ALL DOF values; they are clamped here like
 // kinbody.cpp:2149-2224 does (non-circular DOFs only).
@@ -1030,6 +1065,7 @@ static void active_links(const Body& b, const int32_t* active, int nactive, int 
 {
     out.assign(b.links.size(), 1);
     if (!(options & CC_CO_ActiveDOFs) || !b.is_robot) return;
+    if (b.affine_mask) return;                   // "enable everything" (collisionPQP.h:716-719)
     out.assign(b.links.size(), 0);
     for (size_t l = 0; l < b.links.size(); ++l)
         for (int a = 0; a < nactive; ++a)
@@ -1166,6 +1202,15 @@ int orc_body_set_kinematics(void* sp, int body, int ndof, int njoints, const cc_
     return 0;
 }
 
+int orc_body_set_affine(void* sp, int body, int mask, const double* axis3, const double* qstart4)
+{
+    Body* b = ((Scene*)sp)->bodies[body];
+    b->affine_mask = mask;
+    if (axis3) for (int k = 0; k < 3; ++k) b->affine_axis[k] = axis3[k];
+    if (qstart4) for (int k = 0; k < 4; ++k) b->affine_qstart[k] = qstart4[k];
+    return 0;
+}
+
 int orc_body_set_nonadjacent_pairs(void* sp, int body, const int32_t* packed, int n)
 {
     Body* b = ((Scene*)sp)->bodies[body];
@@ -1240,8 +1285,9 @@ int orc_check_batch(void* sp, int body, const int32_t* active, int nactive, cons
             const double* T8 = q + (size_t)c * nle * 8;
             for (size_t i = 0; i < nle; ++i) { memcpy(xf[i].q, T8 + 8 * i, 32); memcpy(xf[i].t, T8 + 8 * i + 4, 24); }
         } else {
-            for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * nactive + a];
-            forward_kinematics(*b, &vals[0], b->xf[0], xf);
+            const size_t ncols = (size_t)nactive + affine_count(b->affine_mask);
+            for (int a = 0; a < nactive; ++a) vals[active[a]] = q[(size_t)c * ncols + a];
+            forward_kinematics(*b, &vals[0], b->affine_mask ? affine_transform(*b, b->xf[0], q + (size_t)c * ncols + nactive) : b->xf[0], xf);
             // KinBody::_UpdateGrabbedBodies: grabbed links follow their grabbing link
             xf.resize(nle);
             for (size_t g = 0; g < b->grabs.size(); ++g)

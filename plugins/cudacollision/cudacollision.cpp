@@ -120,9 +120,14 @@ class CudaCollisionChecker : public CollisionCheckerBase
 
     struct QueryKey {
         int body; std::vector<int> active; int options;
+        int affine;                      // RobotBase::GetAffineDOF() of a batched query over the robot's active DOFs, else 0
+        double axis[3];
+        QueryKey() : body(-1), options(0), affine(0) { axis[0] = axis[1] = 0; axis[2] = 1; }
         bool operator<(const QueryKey& r) const {
             if (body != r.body) return body < r.body;
             if (options != r.options) return options < r.options;
+            if (affine != r.affine) return affine < r.affine;
+            if (affine) for (int k = 0; k < 3; ++k) if (axis[k] != r.axis[k]) return axis[k] < r.axis[k];
             return active < r.active;
         }
     };
@@ -218,9 +223,8 @@ public:
     /// DynamicsCollisionConstraint::Check (planningutils.cpp:3405-3526).
     int CheckCollisionBatch(RobotBaseConstPtr probot, const dReal* q, int n, int ndof, uint32_t* verdict, int32_t* firstpairs, int flags)
     {
-        if (probot->GetAffineDOF() != 0) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: affine active DOFs are not batched yet", ORE_NotImplemented);
-        if (ndof != (int)probot->GetActiveDOFIndices().size()) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ndof != active DOF count", ORE_InvalidArguments);
-        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices());
+        if (ndof != probot->GetActiveDOF()) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: ndof != active DOF count (joint values, then the affine values)", ORE_InvalidArguments);
+        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices(), probot);
         if (_stale.erase(query)) _Check(cc_query_refresh(query));      // base pose / inactive DOF values of the robot moved
         std::vector<int32_t> fe(firstpairs ? n : 0), fs(firstpairs ? n : 0);
         _Check(cc_check_batch(query, q, n, flags, verdict, firstpairs ? fe.data() : NULL, firstpairs ? fs.data() : NULL, NULL));
@@ -242,8 +246,7 @@ public:
     /// the bound query behind CheckCollisionBatch for (robot, its active DOFs, current options): what cc_planner_set_query takes
     cc_query* BindQuery(RobotBaseConstPtr probot)
     {
-        if (probot->GetAffineDOF() != 0) throw OPENRAVE_EXCEPTION_FORMAT0("cudacollision: affine active DOFs are not batched yet", ORE_NotImplemented);
-        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices());
+        cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices(), probot);
         if (_stale.erase(query)) _Check(cc_query_refresh(query));
         return query;
     }
@@ -752,7 +755,8 @@ private:
         }
     }
 
-    cc_query* _Bind(KinBodyConstPtr pbody, const std::vector<int>* active)
+    /// paffinerobot: bind over the robot's affine active DOFs too (RobotBase::SetActiveDOFs(indices, affine, axis), robot.cpp:1193-1225)
+    cc_query* _Bind(KinBodyConstPtr pbody, const std::vector<int>* active, RobotBaseConstPtr paffinerobot = RobotBaseConstPtr())
     {
         _Synchronize();
         BodyInfoPtr pinfo = _Info(pbody);
@@ -762,10 +766,24 @@ private:
         QueryKey key;
         key.body = pinfo->id; key.options = _options;
         if (active) key.active = *active;
+        if (!!paffinerobot && paffinerobot->GetAffineDOF() != 0) {
+            key.affine = paffinerobot->GetAffineDOF();
+            const Vector& ax = paffinerobot->GetAffineRotationAxis();
+            key.axis[0] = ax.x; key.axis[1] = ax.y; key.axis[2] = ax.z;
+        }
         std::map<QueryKey, cc_query*>::iterator it = _queries.find(key);
         if (it != _queries.end()) return it->second;
         cc_query* query = NULL;
         std::vector<int32_t> act(key.active.begin(), key.active.end());
+        if (key.affine) {
+            // _vRotationQuatLimitStart = GetAffineRotationQuatLimits() / its norm (robot.h:1097-1099, robot.cpp:1031)
+            Vector qs = paffinerobot->GetAffineRotationQuatLimits();
+            const dReal len = RaveSqrt(qs.lengthsqr4());
+            double qstart[4] = {1, 0, 0, 0};
+            if (len > 0) { qstart[0] = qs.x / len; qstart[1] = qs.y / len; qstart[2] = qs.z / len; qstart[3] = qs.w / len; }
+            int32_t none = 0;
+            _Check(cc_query_create_affine(_scene, pinfo->id, act.empty() ? &none : act.data(), (int)act.size(), key.affine, key.axis, qstart, _options, &query));
+        } else
         _Check(cc_query_create(_scene, pinfo->id, active ? act.data() : NULL, (int)act.size(), _options, &query));
         _queries[key] = query;
         return query;

