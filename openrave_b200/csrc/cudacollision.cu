@@ -569,10 +569,11 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     if (contacts) { P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
-    // configurations that need far more descent iterations than the rest are cut short and redone on 8 warps each by a second
-    // launch (CC_TUNE_DEFER: the iteration budget, 0 = off): without this a 100k-configuration PR2 batch spends half its time
-    // waiting for a handful of warps (profiles/r02d_scale_n.log)
-    static const int defer_budget = getenv("CC_TUNE_DEFER") ? atoi(getenv("CC_TUNE_DEFER")) : 64;
+    // configurations that need far more descent iterations than the rest can be cut short and redone on 8 warps each by a second
+    // launch (CC_TUNE_DEFER = the iteration budget).  Off by default: splitting by PAIRS does not parallelise them (their work sits
+    // in one or two deep descents) and the restart is wasted work — PR2 gains only between 12k and 200k configurations per
+    // call (1.15 -> 0.77 ms at 12.5k) and loses 6 % at 1M, WAM/lab1 loses at every size (profiles/r02e_ab_defer.log)
+    static const int defer_budget = getenv("CC_TUNE_DEFER") ? atoi(getenv("CC_TUNE_DEFER")) : 0;
     const Plan::Split* sp8 = (int)pl.pairs.size() > 32 ? &pl.split[2] : nullptr;
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
