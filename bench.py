@@ -604,6 +604,26 @@ def main():
         evf.append((e0, e1))
     torch.cuda.synchronize()
     first_hit_ms = sum(a.elapsed_time(b) for a, b in evf) / len(evf)
+    # a scene whose obstacles keep moving never gets to use the free-space certificates (cc_query_refresh drops the ones a moved
+    # body touches): the same batch with them switched off is the floor of the dynamic-scene throughput
+    cc.SetPairTables(False)
+    bq_dyn = cc.bind(robot)
+    evd = []
+    for k in range(2 + max(3, args.steps // 2)):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        bq_dyn.check_device(d_q.data_ptr(), n, flags, d_verdict.data_ptr(), d_fe.data_ptr(), d_fs.data_ptr(), 0, stream.cuda_stream)
+        e1.record(stream)
+        if k >= 2:
+            evd.append((e0, e1))
+    torch.cuda.synchronize()
+    dynamic_ms = sum(a.elapsed_time(b) for a, b in evd) / len(evd)
+    cc.SetPairTables(True)
+    bq = cc.bind(robot)
+    for _ in range(2):                      # certificates are rebuilt on the re-bound query before the e2e timing below
+        step_device()
+    torch.cuda.synchronize()
     step_device()                           # leave the full outputs in the result buffers for the consistency check below
     torch.cuda.synchronize()
 
@@ -667,7 +687,10 @@ def main():
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
                            "parallelism": "configs sharded, scene replicated (dp%d)" % world, "multi_device_e2e": multi,
                            "colliding_fraction": float((v_last != 0).mean()),
-                           "first_hit_mode_configs_per_s": world * n / (first_hit_ms / 1000.0)},
+                           "first_hit_mode_configs_per_s": world * n / (first_hit_ms / 1000.0),
+                           "dynamic_scene_configs_per_s": world * n / (dynamic_ms / 1000.0),
+                           "dynamic_scene_note": "the same batch with cc_scene_set_pair_tables(0): what a caller gets while obstacles move "
+                                                 "every few batches (a refresh drops the certificates a moved body touches)"},
                 "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * n * ndof * 8),
                         "d2h_bytes_per_step": int(world * n * 12),
                         "path": "cc_check_batch, pinned host buffers" + ("" if world == 1 else
@@ -691,8 +714,24 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_step")
             physical = None
             pp = os.path.join(ROOT, "profiles", "physical_%s.json" % args.workload)
-            if os.path.isfile(pp):   # utilisation counters of the dominant kernel from the committed ncu capture of this command
+            if os.path.isfile(pp):   # counters of the step's kernels from the committed ncu capture of this command (tools/harvest_r02.py)
                 physical = json.load(open(pp))
+                # the PHYSICAL utilisation of this run, recomputable from profiles/ alone + this line's own value and clocks:
+                #   issue_frac  = warp instructions per configuration (ncu inst_executed of the FK + traversal launches / their
+                #                 configurations) x configs/s / (SMs x 4 schedulers x SM clock): the binding resource
+                #   lane_efficiency = active threads per executed warp instruction / 32
+                #   dram_frac   = DRAM bytes per step (ncu dram__bytes_read + write of the same launches) / step time / measured copy peak
+                props = torch.cuda.get_device_properties(local_rank)
+                clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+                w = physical.get("warp_instructions_per_configuration")
+                if w:
+                    physical["issue_frac"] = w * (n / (kernel_ms / 1000.0)) / (props.multi_processor_count * 4 * clk)
+                    physical["issue_frac_inputs"] = {"sm_count": props.multi_processor_count, "schedulers_per_sm": 4, "sm_clock_hz": clk,
+                                                     "configs_per_s_per_gpu": n / (kernel_ms / 1000.0)}
+                if physical.get("threads_per_instruction"):
+                    physical["lane_efficiency"] = physical["threads_per_instruction"] / 32.0
+                if traffic:
+                    physical["dram_frac"] = traffic / (kernel_ms / 1000.0) / (peak * 1e9)
             # compute side: the reference's box / triangle test counts priced at 263 / 745 flops + FK
             from openrave_b200.checker import device_fp32_peak
             fp32_peak = device_fp32_peak(local_rank)

@@ -51,6 +51,9 @@ constexpr int kFkThreads = 128;
 #ifndef CC_TRIQ_CAP
 #define CC_TRIQ_CAP 96
 #endif
+#ifndef CC_BROAD_SMEM
+#define CC_BROAD_SMEM 1        // 1: the broadphase reads the configuration's link boxes from shared memory (staged into the idle LIFO area)
+#endif
 constexpr int kStackCap = CC_STACK_CAP;   // items of shared-memory LIFO per warp
 constexpr int kSpillChunk = 128;     // items moved to / from the global spill area at a time
 constexpr int kNumSlots = 32;        // root pairs traversed together
@@ -138,14 +141,6 @@ struct Params {
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
-    // heavy configurations (a few need 50x the mean work and would make the whole persistent grid wait for one warp): a
-    // full-batch launch gives up on a configuration after `defer_budget` descent iterations and appends it to `heavy_out`
-    // (count in heavy_out_count); a second, split launch (`heavy_in` / `heavy_in_count`) then spreads each of them over `split` warps
-    int32_t defer_budget;       // 0: never give up
-    int32_t* heavy_out;
-    int32_t* heavy_out_count;
-    const int32_t* heavy_in;    // split launch over the deferred configurations instead of [0, n)
-    const int32_t* heavy_in_count;
     // split traversal (small batches): every configuration becomes `split` work items, item `part` owning the pairs
     // [part_begin[part], part_begin[part + 1]) of `pairs` / `pair_orig` (round-robin blocks of the reference order, env pairs
     // first: part_nenv[part] of them); results are combined with atomics into outputs the FK kernel initialised
@@ -665,7 +660,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const uint32_t* pairs = P.pairs;
     const int32_t* pair_orig = P.pair_orig;
     const int32_t* ptable = P.pair_table;
-    const int nwork = kSplit ? (P.heavy_in ? __ldg(P.heavy_in_count) : P.n) * P.split : P.n;
+    const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
     // pose scratch: the slots of one configuration are contiguous ([cap][ndyn][12] / [cap][ndyn][8]).  The slot-major alternative
     // (coalesced FK stores, scattered traversal reads) measured 5 % slower on PR2 and 30 % slower on the clutter scene
@@ -681,7 +676,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             const int w = c;
             c = w / P.split;
             const int part = w - c * P.split;
-            if (P.heavy_in) c = __ldg(&P.heavy_in[c]);
             const int pb = __ldg(&P.part_begin[part]);
             pairs = P.pairs + pb; pair_orig = P.pair_orig + pb;
             if (kTables) ptable = P.pair_table + pb;
@@ -709,9 +703,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         uint32_t slot_dead = 0;    // slots whose items are no longer wanted (contact found, or preceded by a contact); non-zero
                                    // also means refills from the spill area have to be filtered
         bool failed = false;
-        bool deferred = false;     // gave up on this configuration: the split launch that follows redoes it on several warps
         uint32_t iters = P.hoisted_first_self != kNone ? 0x80000000u : 0u;     // bit 31: a self contact was really found (first-hit mode)
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
+        // The broadphase tests ~500 link pairs per configuration, each against two world boxes of this configuration — scattered
+        // 32-byte reads of pose scratch that comes from DRAM.  Between two drains the LIFO area is empty, so the configuration's
+        // boxes (32 B per dynamic slot) are staged there with a few coalesced loads and the pair tests read shared memory.
+        const bool ab_fits = CC_BROAD_SMEM && ndyn * 8 * (int)sizeof(float) <= kStackCap * (int)sizeof(uint2);
+        bool ab_staged = false;
         int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
         const int kend = (P.flags & kFlagSelf) ? npairs_dev : nenv_dev;
 
@@ -724,6 +722,14 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     else if (best_self < __ldg(&pair_orig[k0])) { k0 = kend; continue; }
                 }
                 // ------------------------------------------------------------ broadphase: 32 x kBroadPerLane pairs, world AABBs
+                if (ab_fits && !ab_staged) {
+                    float4* dst = (float4*)stack;
+                    const float4* src = (const float4*)ab;
+                    for (int i = lane; i < 2 * ndyn; i += 32) dst[i] = src[i];
+                    ab_staged = true;
+                    __syncwarp();
+                }
+                const float* abs_ = ab_fits ? (const float*)stack : ab;                 // generic pointer: shared or global
                 const int lim = (k0 < nenv_dev && nenv_dev < kend) ? nenv_dev : kend;     // do not straddle env | self
                 uint32_t pr[kBroadPerLane];
 #pragma unroll
@@ -737,8 +743,8 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     ov[h] = false;
                     if (pr[h] != 0xffffffffu) {
                         const int sa = pr[h] & 0xffff, sb = pr[h] >> 16;
-                        const float4* pa = (const float4*)(sa < ndyn ? ab + as * sa : P.st_aabb + 8 * (size_t)(sa - ndyn));
-                        const float4* pb = (const float4*)(sb < ndyn ? ab + as * sb : P.st_aabb + 8 * (size_t)(sb - ndyn));
+                        const float4* pa = (const float4*)(sa < ndyn ? abs_ + as * sa : P.st_aabb + 8 * (size_t)(sa - ndyn));
+                        const float4* pb = (const float4*)(sb < ndyn ? abs_ + as * sb : P.st_aabb + 8 * (size_t)(sb - ndyn));
                         const float4 ac = pa[0], ae = pa[1], bc = pb[0], be = pb[1];
                         ov[h] = fabsf(ac.x - bc.x) <= ae.x + be.x && fabsf(ac.y - bc.y) <= ae.y + be.y && fabsf(ac.z - bc.z) <= ae.z + be.z;
                         if (kTables && ov[h]) {
@@ -761,6 +767,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             }
             {
                 // ---------------------------------------------------------------- a batch of <= 32 root pairs
+                ab_staged = false;         // the LIFO area is about to be used
                 const int cnt = ncb < 32 ? ncb : 32;
                 bool cand = false;
                 float R[9], t[3];
@@ -924,10 +931,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
                     const int n = sp < 32 ? sp : 32;
                     ++iters;
-                    if (!kSplit && !kContacts && P.defer_budget > 0 && (int)(iters & 0x7fffffffu) > P.defer_budget) {
-                        deferred = true; failed = true; sp = 0; ntri = 0; ntri2 = 0; spill_count = 0;
-                        break;
-                    }
                     const bool valid = lane < n;
                     uint2 it = make_uint2(0u, 0u);
                     if (valid) it = stack[sp - 1 - lane];
@@ -1045,18 +1048,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         }
 
         // ---------------------------------------------------------------- verdict
-        if (deferred) {
-            // hand the configuration over with neutral outputs: the split launch merges its parts into them with atomics
-            if (lane == 0) {
-                if (P.verdict) P.verdict[c] = 0u;
-                if (P.first_env) P.first_env[c] = -1;
-                if (P.first_self) P.first_self[c] = -1;
-                if (P.work_out) P.work_out[c] = iters & 0x7fffffffu;
-                P.heavy_out[atomicAdd(P.heavy_out_count, 1)] = c;
-            }
-            __syncwarp();
-            continue;
-        }
         if (lane == 0) {
             int be = best_env, bs = best_self;
             if (mask_row) {

@@ -406,8 +406,7 @@ struct cc_query {
     // per-chunk scratch (grown on demand, shared by the plans)
     DevBuf<float> d_xf32[2], d_aabb[2];      // two sets: consecutive chunks overlap on two streams
     DevBuf<double> d_fksave[2];
-    DevBuf<int32_t> d_counters[2];           // per lane: [0] work counter, [1] deferred configurations, [2] work counter of their split launch
-    DevBuf<int32_t> d_heavy[2];              // per lane: the deferred configurations of the chunk in flight
+    DevBuf<int32_t> d_counters[2];
     DevBuf<uint32_t> d_hoisted_mask;
     std::vector<uint32_t> hoisted_mask;
     int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
@@ -443,8 +442,7 @@ int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
         CC_CUDA(Q->d_xf32[k].reserve((size_t)cap * std::max(1, pl.ndyn) * 12));
         CC_CUDA(Q->d_aabb[k].reserve((size_t)cap * std::max(1, pl.ndyn) * 8));
         CC_CUDA(Q->d_fksave[k].reserve((size_t)cap * std::max(1, pl.nsave) * 7));
-        CC_CUDA(Q->d_counters[k].reserve(4));
-        CC_CUDA(Q->d_heavy[k].reserve((size_t)std::max(cap, 1)));
+        CC_CUDA(Q->d_counters[k].reserve(2));
     }
     return CC_OK;
 }
@@ -569,12 +567,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     if (contacts) { P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
-    // configurations that need far more descent iterations than the rest can be cut short and redone on 8 warps each by a second
-    // launch (CC_TUNE_DEFER = the iteration budget).  Off by default: splitting by PAIRS does not parallelise them (their work sits
-    // in one or two deep descents) and the restart is wasted work — PR2 gains only between 12k and 200k configurations per
-    // call (1.15 -> 0.77 ms at 12.5k) and loses 6 % at 1M, WAM/lab1 loses at every size (profiles/r02e_ab_defer.log)
-    static const int defer_budget = getenv("CC_TUNE_DEFER") ? atoi(getenv("CC_TUNE_DEFER")) : 0;
-    const Plan::Split* sp8 = (int)pl.pairs.size() > 32 ? &pl.split[2] : nullptr;
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
@@ -629,7 +621,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.work_out = (Q->trace_work && !fk_only) ? Q->d_work.p + off : nullptr;
         P.xf32 = Q->d_xf32[k].p; P.aabb = Q->d_aabb[k].p; P.fksave = Q->d_fksave[k].p;
         P.counters = Q->d_counters[k].p;
-        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, 4 * sizeof(int32_t), cs));
+        if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
         if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
         if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
             ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
@@ -646,10 +638,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        const bool defer = defer_budget > 0 && split == 1 && !contacts && sp8 != nullptr;
-        P.defer_budget = defer ? defer_budget : 0;
-        P.heavy_out = Q->d_heavy[k].p; P.heavy_out_count = Q->d_counters[k].p + 1;
-        P.heavy_in = nullptr; P.heavy_in_count = nullptr;
         if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
@@ -660,21 +648,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         }
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
-        if (defer) {
-            // second launch: the configurations the first one gave up on, each spread over 8 warps (outputs merged with atomics)
-            ccdev::Params P2 = P;
-            P2.defer_budget = 0;
-            P2.heavy_in = Q->d_heavy[k].p; P2.heavy_in_count = Q->d_counters[k].p + 1;
-            P2.counters = Q->d_counters[k].p + 2;
-            P2.pairs = sp8->d_pairs.p; P2.pair_orig = sp8->d_orig.p; P2.part_begin = sp8->d_part_begin.p; P2.part_nenv = sp8->d_part_nenv.p;
-            P2.split = 8;
-            if (use_tables) P2.pair_table = Q->d_pair_table_split[2].p;
-            const int grid2 = std::min(S->trav_blocks_per_sm * S->num_sms, (int)(((long long)m * 8 + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock));
-            if (use_tables) ccdev::cc_traverse_kernel<true, true><<<grid2, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P2);
-            else ccdev::cc_traverse_kernel<true, false><<<grid2, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P2);
-            CC_CUDA(cudaGetLastError());
-            S->stats.launches++;
-        }
         if (timeline) CC_CUDA(cudaEventRecord(S->tl_events[3 * ci + 2], cs));
         if (hio) {
             if (pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
