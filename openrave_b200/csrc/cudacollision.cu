@@ -111,6 +111,10 @@ struct cc_scene {
     DevBuf<float4> d_nodes, d_tris;
     int total_nodes = 0, total_tris = 0;
     DevBuf<uint2> d_spill[2];               // one per pipeline lane (two chunks are in flight at a time)
+    // work sharing between the warps of a full-batch traversal (ccdev::kShareAfter): per lane, control words + record states
+    // (one array, zeroed before every launch) and the records themselves
+    DevBuf<uint32_t> d_share_ctl[2];
+    DevBuf<unsigned char> d_share_rec[2];
     int spill_warps = 0;
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -581,6 +585,14 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         for (int k = 0; k < (overlap ? 2 : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
         S->spill_warps = full_warps;
     }
+    // heavy configurations are shared between warps (CC_TUNE_SHARE=0 turns it off): 256 records per lane
+    static const int share_cap = getenv("CC_TUNE_SHARE") ? atoi(getenv("CC_TUNE_SHARE")) : 256;
+    const bool share = share_cap > 0 && !fk_only && split == 1 && !contacts && !(flags & CC_BATCH_ALL_PAIRS);
+    if (share)
+        for (int k = 0; k < (overlap ? 2 : 1); ++k) {
+            CC_CUDA(S->d_share_ctl[k].reserve(4 + (size_t)share_cap));
+            CC_CUDA(S->d_share_rec[k].reserve((size_t)share_cap * ccdev::kShareRecBytes));
+        }
     CC_CUDA(cudaEventRecord(S->ev0, st));
     if (overlap) {
         CC_CUDA(cudaEventRecord(S->ev_fork, st));
@@ -638,6 +650,12 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
+        P.share_cap = 0;
+        if (share) {
+            CC_CUDA(cudaMemsetAsync(S->d_share_ctl[k].p, 0, (4 + (size_t)share_cap) * sizeof(uint32_t), cs));
+            P.share_ctl = (int32_t*)S->d_share_ctl[k].p; P.share_state = S->d_share_ctl[k].p + 4; P.share_rec = S->d_share_rec[k].p;
+            P.share_cap = share_cap;
+        }
         if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);

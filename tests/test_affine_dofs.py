@@ -28,13 +28,13 @@ def _sample(robot, arm, affine, n, seed, spread=0.6):
     base = np.array(robot.links[0].t[1])
     for bit, k in ((DOF_X, 0), (DOF_Y, 1), (DOF_Z, 2)):
         if affine & bit:
-            cols.append(base[k] + (rng.random((n, 1)) - 0.5) * 2 * (0.05 if bit == DOF_Z else spread))
+            cols.append(base[k] + ((rng.random((n, 1)) * 0.08 + 0.03) if bit == DOF_Z else (rng.random((n, 1)) - 0.5) * 2 * spread))
     if affine & DOF_RotationAxis:
         cols.append((rng.random((n, 1)) - 0.5) * 2 * np.pi)
     elif affine & DOF_Rotation3D:
-        cols.append((rng.random((n, 3)) - 0.5) * 2.0)
+        cols.append((rng.random((n, 3)) - 0.5) * np.array([0.06, 0.06, 4.0]))       # small tilts, any yaw (axis * angle)
     elif affine & DOF_RotationQuat:
-        cols.append(rng.normal(size=(n, 4)))                      # not normalised on purpose: the reference normalises
+        cols.append(rng.normal(size=(n, 4)) * np.array([1.0, 0.02, 0.02, 1.0]))     # mostly yaw; not normalised on purpose: the reference normalises
     return np.hstack(cols)
 
 
@@ -89,7 +89,7 @@ def test_gpu_base_planning_batch_equals_oracle(affine):
         hit = fe[:, 0] >= 0
         fe[hit, 1] = [orc._ids[id([b for b in env2.GetBodies() if b.name == cc.body_from_id(int(x)).name][0])] for x in fe[hit, 1]]
         assert (fe[ok] == ref["first_env"][ok]).all() and (got["first_self"][:m][ok] == ref["first_self"][ok]).all()
-        assert 0.05 < (ref["verdict"] != 0).mean() < 0.99
+        assert 0.05 < (ref["verdict"] != 0).mean() < 0.995
         # every env pair depends on the base pose: nothing involving the environment may be hoisted; self pairs still are
         info = got["query"].info
         if opts == 0:                       # (with CO_ActiveDOFs only self pairs an active joint can change are listed at all)
