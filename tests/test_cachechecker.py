@@ -104,3 +104,42 @@ def test_single_state_calls_follow_the_reference_flow():
     # other bodies bypass the cache (cachechecker.cpp:199-204)
     mug = [b for b in env.GetBodies() if b is not robot][0]
     assert cc.CheckCollision(mug) == orc.CheckCollision(mug)
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_cache_misses_of_a_batch_reach_the_cuda_checker_in_one_call():
+    """f3: the cache in front of the CUDA checker — every miss of a batch goes to the GPU in ONE cc_check_batch call,
+    repeated batches are answered by the cache, and with tight thresholds the answers are the oracle's exact ones.  The C++ form
+    of the same wrapper is plugins/cudacollision/cudabatched.h::CudaCacheChecker (type-checked by tools/shim_syntax_check.sh)."""
+    from openrave_b200.checker import CudaCollisionChecker
+    env, robot, orc = _world()
+    env2 = load_scene("wamtest1")
+    robot2 = env2.GetRobots()[0]
+    robot2.SetActiveDOFs(robot2.GetActiveManipulator().GetArmIndices())
+    gpu = CudaCollisionChecker(env2, 0)
+    env2.SetCollisionChecker(gpu)
+    act = robot2.GetActiveDOFIndices()
+    cc = CacheCollisionChecker(gpu, robot2, collisionthresh=0.05, freespacethresh=0.05)
+    q = sample_configs(robot, 20000, seed=4, active=act)
+    launches0 = gpu.GetStatistics()["launches"]
+    configs0 = gpu.GetStatistics()["configs"]
+    r1 = cc.CheckCollisionBatch(robot2, q)
+    st = gpu.GetStatistics()
+    assert st["configs"] - configs0 == len(q) and 1 <= st["launches"] - launches0 <= 4          # one batched call (FK + traversal kernels)
+    assert not r1["from_cache"].any()
+    ref = orc.check_batch(robot, q[:1500], active=act, want_band=True)
+    band = (ref["near"] != 0) | ((ref["verdict"] != 0) & (ref["penetration"] <= 1e-4))
+    assert not ((r1["verdict"][:1500] != ref["verdict"]) & ~band).any()
+    r2 = cc.CheckCollisionBatch(robot2, q)                                                      # all from the cache now
+    assert gpu.GetStatistics()["configs"] == st["configs"] and (r2["from_cache"] == 3).all()
+    assert np.array_equal(r2["verdict"], r1["verdict"])
+    # single-state calls: a miss reaches the GPU's single-state overloads, a repeat does not
+    qn = sample_configs(robot, 30, seed=9, active=act)
+    for rounds in range(2):
+        for k in range(30):
+            robot2.SetDOFValues(qn[k].tolist(), act)
+            cc.CheckCollision(robot2)
+    assert cc.stats["inner_configs"] <= len(q) + 30
