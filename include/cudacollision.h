@@ -139,6 +139,24 @@ int cc_scene_remove_body(cc_scene* s, int body);
 /* Link::GetCollisionData(): link-frame vertices (xyz doubles) + triangle indices (TriMesh, openrave.h:2501-2505) */
 int cc_body_set_link_mesh(cc_scene* s, int body, int link, const char* link_name,
                           const double* vertices_xyz, int nvertices, const int32_t* triangles, int ntriangles);
+/* ---- analytic primitives (fclrave semantics, off by default).  fclrave gives every box / sphere / cylinder / capsule geometry its
+ * exact convex shape (plugins/fclrave/fclspace.cpp:475-602) where pqprave, the primary reference, sees the tessellated triangle
+ * soup of the whole link (Link::GetCollisionData).  cc_body_set_link_primitives hands a link's primitive geometries over
+ * (KinBody::GeometryInfo: type, pose in the link frame, _vGeomData: box half extents; sphere radius; cylinder / capsule radius
+ * and height along the geometry's z axis); the link's tessellated mesh is still set with cc_body_set_link_mesh.  After
+ * cc_scene_set_analytic_primitives(scene, 1) every link pair with such a link is decided on the exact shapes — primitive x
+ * primitive by boolean GJK, primitive x mesh by GJK against the triangles its bounding box reaches — in queries bound
+ * afterwards.  FCL itself is an external, un-vendored fork: "parity unpinned"; the exact shapes contain their tessellation, so
+ * this mode reports a superset of the tessellated contacts, the difference being pairs closer than the tessellation's sagitta. */
+enum cc_geom_type { CC_GEOM_BOX = 1, CC_GEOM_SPHERE = 2, CC_GEOM_CYLINDER = 3, CC_GEOM_CAPSULE = 4 };
+typedef struct cc_geom {
+    int32_t type;          /* cc_geom_type */
+    int32_t reserved;
+    double pose[8];        /* geometry pose in the link frame, {qw qx qy qz tx ty tz 0} */
+    double dims[4];        /* box: half extents x y z; sphere: radius; cylinder, capsule: radius, height */
+} cc_geom;
+int cc_body_set_link_primitives(cc_scene* s, int body, int link, const cc_geom* geoms, int ngeoms);
+int cc_scene_set_analytic_primitives(cc_scene* s, int enabled);
 /* Link::IsEnabled() for every link */
 int cc_body_set_link_enabled(cc_scene* s, int body, const uint8_t* enabled);
 /* KinBody::GetLinkTransformations(): [nlinks][8] */

@@ -60,20 +60,6 @@ constexpr int kBroadPerLane = 4;     // broadphase pairs per lane per step (inde
 constexpr int kCandCap = 32 * kBroadPerLane + 32;   // pending candidate pair indices (a step only runs with < 32 pending)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNone = 0x7fffffff;
-// ---- work sharing (heavy configurations).  A few configurations need 50x the mean number of descent iterations (two links
-// pressed against each other: thousands of overlapping box pairs before the first contact) and a persistent grid would wait for
-// the single warp that owns one.  A warp whose configuration has passed kShareAfter iterations counts as HEAVY; warps that run
-// out of configurations stay around while heavy work exists and wait for records; a heavy warp with a deep LIFO and waiting
-// helpers hands the OLDEST kShareItems items of its LIFO (later pairs / far subtrees), together with the relative poses of its
-// current root pairs, to one of them through a record in global memory.  Results meet in the outputs through atomics.
-#ifndef CC_SHARE_AFTER
-#define CC_SHARE_AFTER 24
-#endif
-constexpr int kShareAfter = CC_SHARE_AFTER;     // descent iterations after which a configuration counts as heavy
-constexpr int kShareItems = 64;                 // items per record
-constexpr int kShareMinDepth = 2 * kShareItems; // LIFO depth from which the owner gives items away
-constexpr int kShareRecBytes = 64 + kNumSlots * 4 + kNumSlots * 96 + kShareItems * 8;      // header | slot_pair | slot_rt | items
-static_assert(kShareRecBytes % 16 == 0, "record alignment");
 
 // flags (low bits mirror cc_batch_flags)
 constexpr int kFlagEnv = 1, kFlagSelf = 2, kFlagAllPairs = 4, kFlagPoseMode = 8, kFlagFkOnly = 16, kFlagCounters = 32;
@@ -152,11 +138,6 @@ struct Params {
     unsigned long long* stats;  // [0] bv tests, [1] tri tests
     uint2* spill;               // [num_warps][spill_cap]
     int32_t spill_cap;
-    // work sharing between the warps of a full-batch launch (see kShareAfter); share_cap = 0: off
-    int32_t* share_ctl;         // [0] records posted and not finished, [1] heavy owners + helpers at work, [2] records waiting to be claimed, [3] warps waiting
-    uint32_t* share_state;      // [share_cap] 0 free, 1 being written, 2 waiting, 3 being processed
-    unsigned char* share_rec;   // [share_cap][kShareRecBytes]
-    int32_t share_cap;
     // split traversal (small batches): every configuration becomes `split` work items, item `part` owning the pairs
     // [part_begin[part], part_begin[part + 1]) of `pairs` / `pair_orig` (round-robin blocks of the reference order, env pairs
     // first: part_nenv[part] of them); results are combined with atomics into outputs the FK kernel initialised
@@ -544,7 +525,7 @@ __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, c
     }
 }
 
-__global__ void __launch_bounds__(kFkThreads)
+__global__ void __launch_bounds__(kFkThreads, 6)     // latency-bound kernel: keep 24 warps per SM resident (<= 85 registers; the affine base adds a few)
 cc_fk_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -678,57 +659,20 @@ cc_traverse_kernel(const __grid_constant__ Params P)
     const int32_t* ptable = P.pair_table;
     const int nwork = kSplit ? P.n * P.split : P.n;
     unsigned long long n_bv = 0, n_tri = 0;
-    // pose scratch: the slots of one configuration are contiguous ([cap][ndyn][12] / [cap][ndyn][8]).  The slot-major alternative
-    // (coalesced FK stores, scattered traversal reads) measured 5 % slower on PR2 and 30 % slower on the clutter scene
-    // (profiles/r02c_ab_fk.log)
+    // pose scratch: the slots of one configuration are contiguous ([cap][ndyn][12] / [cap][ndyn][8]).  Measured and left out in
+    // round 2 (A/B logs under profiles/): slot-major scratch (coalesced FK stores, scattered traversal reads: -5 % PR2, -30 % clutter,
+    // r02c_ab_fk.log); FK inside this kernel, one warp per 32 configurations (46 vs 81 M configs/s: the latency-bound FK occupies
+    // warp residency, r02b_ab_fused_fk.log); staging the configuration's link boxes in shared memory for the broadphase (-4 .. 10 %,
+    // r02g_ab_broad_smem.log); giving up on heavy configurations and redoing them split 8 ways (r02e_ab_defer.log); handing LIFO items
+    // of heavy configurations to idle warps through global records (the extra state spills at the 72-register cap: 59 / 45 vs
+    // 81 M configs/s, r02h_ab_share.log).
     constexpr int xs = 12, as = 8;
 
-    // work sharing: only the plain full-batch flavour, never with complete pair masks (their first pairs are read back per warp)
-    const bool share = !kSplit && !kContacts && P.share_cap > 0 && !all_pairs;
-    // warp-uniform flags of the sharing machinery, packed into one register (the kernel sits at its register cap)
-    constexpr uint32_t kQueueDone = 1u, kSharedOut = 2u, kIsHeavy = 4u, kResume = 8u;
-    uint32_t wf = 0u;
     for (;;) {
         int c = 0;
-        int rec = -1;                // >= 0: this work item is a record another warp posted
-        if (!(wf & kQueueDone)) {
-            if (lane == 0) c = atomicAdd(&P.counters[0], 1);
-            c = __shfl_sync(kFull, c, 0);
-            if (c >= nwork) { if (!share) break; wf |= kQueueDone; }
-        }
-        if (wf & kQueueDone) {
-            // help while heavy work exists: claim a waiting record, or leave once nothing is heavy and nothing is posted
-            bool waiting = false;
-            for (;;) {
-                int nfull = 0;
-                if (lane == 0) nfull = *(volatile int32_t*)&P.share_ctl[2];
-                nfull = __shfl_sync(kFull, nfull, 0);
-                if (nfull > 0) {
-                    for (int base = 0; base < P.share_cap && rec < 0; base += 32) {
-                        const int i = base + lane;
-                        const bool full = i < P.share_cap && *(volatile uint32_t*)&P.share_state[i] == 2u;
-                        unsigned m = __ballot_sync(kFull, full);
-                        while (m && rec < 0) {
-                            const int src = __ffs(m) - 1; m &= m - 1;
-                            int got = 0;
-                            if (lane == src) got = atomicCAS(&P.share_state[i], 2u, 3u) == 2u ? 1 : 0;
-                            if (__shfl_sync(kFull, got, src)) rec = base + src;
-                        }
-                    }
-                }
-                if (rec >= 0) break;
-                int heavy = 0, posted = 0;
-                if (lane == 0) { heavy = *(volatile int32_t*)&P.share_ctl[1]; __threadfence(); posted = *(volatile int32_t*)&P.share_ctl[0]; }
-                heavy = __shfl_sync(kFull, heavy, 0); posted = __shfl_sync(kFull, posted, 0);
-                if (heavy == 0 && posted == 0) break;       // (a poster stays heavy until after its record is counted: read order matters)
-                if (!waiting) { waiting = true; if (lane == 0) atomicAdd(&P.share_ctl[3], 1); }
-                __nanosleep(400);
-            }
-            if (waiting && lane == 0) atomicSub(&P.share_ctl[3], 1);
-            if (rec < 0) break;
-            if (lane == 0) { atomicSub(&P.share_ctl[2], 1); atomicAdd(&P.share_ctl[1], 1); }      // claimed; this warp is at (heavy) work now
-        }
-        if (rec >= 0) c = __ldcg((const int32_t*)(P.share_rec + (size_t)rec * kShareRecBytes));      // (records are re-used: never through L1)
+        if (lane == 0) c = atomicAdd(&P.counters[0], 1);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= nwork) break;
         if (kSplit) {
             const int w = c;
             c = w / P.split;
@@ -742,7 +686,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
         const float* xf = P.xf32 + (size_t)c * ndyn * 12;
         const float* ab = P.aabb + (size_t)c * ndyn * 8;
         uint32_t* mask_row = (all_pairs && P.pair_mask) ? P.pair_mask + (size_t)c * P.mask_words : nullptr;
-        if (!kSplit && P.pair_mask && rec < 0) {
+        if (!kSplit && P.pair_mask) {
             uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
             for (int i = lane; i < P.mask_words; i += 32) mrow[i] = P.hoisted_mask ? P.hoisted_mask[i] : 0u;
             __syncwarp();
@@ -761,30 +705,12 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                                    // also means refills from the spill area have to be filtered
         bool failed = false;
         uint32_t iters = P.hoisted_first_self != kNone ? 0x80000000u : 0u;     // bit 31: a self contact was really found (first-hit mode)
-        // kSharedOut: the outputs of this configuration are merged with atomics (it was shared, or this is a record);
-        // kIsHeavy: counted in share_ctl[1]; kResume: enter the drain directly with the record's items
-        wf = (wf & kQueueDone) | (rec >= 0 ? (kSharedOut | kIsHeavy | kResume) : 0u);
-        int nsl_rec = 0;
-        if (rec >= 0) {
-            // a record: the relative poses of the owner's root pairs and kShareItems of its LIFO items; no broadphase, no root tests
-            const unsigned char* rec_ptr = P.share_rec + (size_t)rec * kShareRecBytes;
-            const int32_t* hdr = (const int32_t*)rec_ptr;
-            nsl_rec = __ldcg(hdr + 1); sp = __ldcg(hdr + 2); best_env = __ldcg(hdr + 3); best_self = __ldcg(hdr + 4);
-            const int32_t* rp = (const int32_t*)(rec_ptr + 64);
-            const float4* rr = (const float4*)(rec_ptr + 64 + kNumSlots * 4);
-            const uint2* ri = (const uint2*)(rec_ptr + 64 + kNumSlots * 4 + kNumSlots * 96);
-            if (lane < nsl_rec) slot_pair[lane] = __ldcg(rp + lane);
-            for (int i = lane; i < nsl_rec * 6; i += 32) ((float4*)slot_rt)[i] = __ldcg(rr + i);
-            for (int i = lane; i < sp; i += 32) stack[i] = __ldcg(ri + i);
-            iters = 0u;
-            __syncwarp();
-        }
         bool recheck = true;       // a new best may let the broadphase skip the rest of its class
+        int k0 = (P.flags & kFlagEnv) ? 0 : nenv_dev;
         const int kend = (P.flags & kFlagSelf) ? npairs_dev : nenv_dev;
-        int k0 = rec >= 0 ? kend : ((P.flags & kFlagEnv) ? 0 : nenv_dev);
 
-        while ((k0 < kend || ncb > 0 || (wf & kResume)) && !failed) {
-            if (!(wf & kResume) && k0 < kend && ncb < 32) {
+        while ((k0 < kend || ncb > 0) && !failed) {
+            if (k0 < kend && ncb < 32) {
                 if (!all_pairs && recheck) {
                     // pairs are in reference order inside each class: once a hit precedes everything left, skip the rest
                     recheck = false;
@@ -829,99 +755,95 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             }
             {
                 // ---------------------------------------------------------------- a batch of <= 32 root pairs
-                int nsl = nsl_rec;           // root pairs (slots) of this batch
-                if (!(wf & kResume)) {
-                    const int cnt = ncb < 32 ? ncb : 32;
-                    bool cand = false;
-                    float R[9], t[3];
-                    int orig = 0;
-                    uint32_t ra = 0, rb = 0;
-                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
-                    if (lane < cnt) {
-                        const uint32_t k = cbuf[lane];
-                        orig = __ldg(&pair_orig[k]);
-                        const bool is_env = (int)k < nenv_dev;
-                        bool skip = false;
-                        if (!all_pairs) skip = is_env ? (orig > best_env) : (orig > best_self);
-                        if (!skip) {
-                            const uint32_t pr = __ldg(&pairs[k]);
-                            const int la = pr & 0xffff, lb = pr >> 16;
-                            float A[12], Bx[12];
-                            {
-                                const float4* e = la < ndyn ? (const float4*)(xf + xs * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
-                                const float4 e0 = e[0], e1 = e[1], e2 = e[2];
-                                A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
-                                A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
-                            }
-                            {
-                                const float4* e = lb < ndyn ? (const float4*)(xf + xs * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
-                                const float4 e0 = e[0], e1 = e[1], e2 = e[2];
-                                Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
-                                Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
-                            }
-                            relative_pose(A, Bx, R, t);
-                            ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
-                            a0 = __ldg(&P.nodes[2 * ra]); a1 = __ldg(&P.nodes[2 * ra + 1]);
-                            b0 = __ldg(&P.nodes[2 * rb]); b1 = __ldg(&P.nodes[2 * rb + 1]);
-                            if (counters) n_bv++;
-                            cand = box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
+                const int cnt = ncb < 32 ? ncb : 32;
+                bool cand = false;
+                float R[9], t[3];
+                int orig = 0;
+                uint32_t ra = 0, rb = 0;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+                if (lane < cnt) {
+                    const uint32_t k = cbuf[lane];
+                    orig = __ldg(&pair_orig[k]);
+                    const bool is_env = (int)k < nenv_dev;
+                    bool skip = false;
+                    if (!all_pairs) skip = is_env ? (orig > best_env) : (orig > best_self);
+                    if (!skip) {
+                        const uint32_t pr = __ldg(&pairs[k]);
+                        const int la = pr & 0xffff, lb = pr >> 16;
+                        float A[12], Bx[12];
+                        {
+                            const float4* e = la < ndyn ? (const float4*)(xf + xs * la) : (const float4*)(P.st_xf + 12 * (size_t)(la - ndyn));
+                            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                            A[0] = e0.x; A[1] = e0.y; A[2] = e0.z; A[3] = e0.w; A[4] = e1.x; A[5] = e1.y; A[6] = e1.z; A[7] = e1.w;
+                            A[8] = e2.x; A[9] = e2.y; A[10] = e2.z; A[11] = e2.w;
                         }
-                    }
-                    // drop the consumed candidates
-                    {
-                        const int rest = ncb - cnt;
-                        uint32_t mv[kBroadPerLane];
-    #pragma unroll
-                        for (int h = 0; h < kBroadPerLane; ++h) mv[h] = (32 * h + lane < rest) ? cbuf[cnt + 32 * h + lane] : 0u;
-                        __syncwarp();
-    #pragma unroll
-                        for (int h = 0; h < kBroadPerLane; ++h) if (32 * h + lane < rest) cbuf[32 * h + lane] = mv[h];
-                        ncb = rest;
-                        __syncwarp();
-                    }
-                    const unsigned cm = __ballot_sync(kFull, cand);
-                    if (cm == 0u) continue;
-                    nsl = __popc(cm);
-                    if (cand) {
-                        const int s = __popc(cm & lt_mask);
-                        float* rt = slot_rt + 24 * s;
-    #pragma unroll
-                        for (int i = 0; i < 9; ++i) rt[i] = R[i];
-                        rt[9] = t[0]; rt[10] = t[1]; rt[11] = t[2];
-                        // inverse: x_B = R^T x_A - R^T t (items whose split node lives in tree B use it, so the two
-                        // children always play the un-transformed role and every lane runs the same code)
-    #pragma unroll
-                        for (int i = 0; i < 3; ++i)
-    #pragma unroll
-                            for (int j = 0; j < 3; ++j) rt[12 + 3 * i + j] = R[3 * j + i];
-                        rt[21] = -(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]);
-                        rt[22] = -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]);
-                        rt[23] = -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2]);
-                        slot_pair[s] = orig;
-                    }
-                    // first items: both leaves -> triangle queue; else split the larger box (PQP.cpp:539-544 compares BV
-                    // sizes; any rule is verdict-neutral).  Reversed so the lowest pair index is popped first.
-                    {
-                        const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
-                        const bool leafpair = cand && la < 0 && lb < 0;
-                        const bool push = cand && !leafpair;
-                        const unsigned tm = __ballot_sync(kFull, leafpair);
-                        const unsigned pm = __ballot_sync(kFull, push);
-                        const uint32_t s = (uint32_t)__popc(cm & lt_mask);
-                        if (leafpair) triq[ntri + __popc(tm & lt_mask)] = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
-                        if (push) {
-                            uint2 it;
-                            if (lb < 0 || (la >= 0 && a1.w > b1.w)) it = make_uint2((uint32_t)la | (s << 26), rb);
-                            else it = make_uint2((uint32_t)lb | (s << 26), ra | 0x80000000u);
-                            stack[sp + (__popc(pm) - 1 - __popc(pm & lt_mask))] = it;
+                        {
+                            const float4* e = lb < ndyn ? (const float4*)(xf + xs * lb) : (const float4*)(P.st_xf + 12 * (size_t)(lb - ndyn));
+                            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                            Bx[0] = e0.x; Bx[1] = e0.y; Bx[2] = e0.z; Bx[3] = e0.w; Bx[4] = e1.x; Bx[5] = e1.y; Bx[6] = e1.z; Bx[7] = e1.w;
+                            Bx[8] = e2.x; Bx[9] = e2.y; Bx[10] = e2.z; Bx[11] = e2.w;
                         }
-                        ntri += __popc(tm);
-                        sp += __popc(pm);
+                        relative_pose(A, Bx, R, t);
+                        ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
+                        a0 = __ldg(&P.nodes[2 * ra]); a1 = __ldg(&P.nodes[2 * ra + 1]);
+                        b0 = __ldg(&P.nodes[2 * rb]); b1 = __ldg(&P.nodes[2 * rb + 1]);
+                        if (counters) n_bv++;
+                        cand = box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
                     }
-                    __syncwarp();
-
                 }
-                wf &= ~kResume;
+                // drop the consumed candidates
+                {
+                    const int rest = ncb - cnt;
+                    uint32_t mv[kBroadPerLane];
+#pragma unroll
+                    for (int h = 0; h < kBroadPerLane; ++h) mv[h] = (32 * h + lane < rest) ? cbuf[cnt + 32 * h + lane] : 0u;
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < kBroadPerLane; ++h) if (32 * h + lane < rest) cbuf[32 * h + lane] = mv[h];
+                    ncb = rest;
+                    __syncwarp();
+                }
+                const unsigned cm = __ballot_sync(kFull, cand);
+                if (cm == 0u) continue;
+                const int nsl = __popc(cm);
+                if (cand) {
+                    const int s = __popc(cm & lt_mask);
+                    float* rt = slot_rt + 24 * s;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) rt[i] = R[i];
+                    rt[9] = t[0]; rt[10] = t[1]; rt[11] = t[2];
+                    // inverse: x_B = R^T x_A - R^T t (items whose split node lives in tree B use it, so the two
+                    // children always play the un-transformed role and every lane runs the same code)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) rt[12 + 3 * i + j] = R[3 * j + i];
+                    rt[21] = -(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]);
+                    rt[22] = -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]);
+                    rt[23] = -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2]);
+                    slot_pair[s] = orig;
+                }
+                // first items: both leaves -> triangle queue; else split the larger box (PQP.cpp:539-544 compares BV
+                // sizes; any rule is verdict-neutral).  Reversed so the lowest pair index is popped first.
+                {
+                    const int la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+                    const bool leafpair = cand && la < 0 && lb < 0;
+                    const bool push = cand && !leafpair;
+                    const unsigned tm = __ballot_sync(kFull, leafpair);
+                    const unsigned pm = __ballot_sync(kFull, push);
+                    const uint32_t s = (uint32_t)__popc(cm & lt_mask);
+                    if (leafpair) triq[ntri + __popc(tm & lt_mask)] = make_uint2((uint32_t)(~la) | (s << 26), (uint32_t)(~lb));
+                    if (push) {
+                        uint2 it;
+                        if (lb < 0 || (la >= 0 && a1.w > b1.w)) it = make_uint2((uint32_t)la | (s << 26), rb);
+                        else it = make_uint2((uint32_t)lb | (s << 26), ra | 0x80000000u);
+                        stack[sp + (__popc(pm) - 1 - __popc(pm & lt_mask))] = it;
+                    }
+                    ntri += __popc(tm);
+                    sp += __popc(pm);
+                }
+                __syncwarp();
+
                 // ---------------------------------------------------------------- drain: descent + triangle batches
                 for (;;) {
                     const bool stack_empty = sp == 0 && spill_count == 0;
@@ -1099,61 +1021,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         }
                         sp = rest;
                     }
-                    // ---- heavy configuration: count it, and give the oldest LIFO items away while helpers wait (see kShareAfter)
-                    if (share && (iters & 0x7fffffffu) >= (uint32_t)kShareAfter) {
-                        if (!(wf & kIsHeavy)) { wf |= kIsHeavy; if (lane == 0) atomicAdd(&P.share_ctl[1], 1); }
-                        if (sp >= kShareMinDepth && spill_count == 0 && (iters & 3u) == 0u) {
-                            int ri = -1;
-                            if (lane == 0 && *(volatile int32_t*)&P.share_ctl[3] > *(volatile int32_t*)&P.share_ctl[2]) {
-                                // more helpers waiting than records on offer: take a free record
-                                const unsigned h = (unsigned)(blockIdx.x * kWarpsPerBlock + wib) * 7u + iters;
-                                for (int probe = 0; probe < 8 && ri < 0; ++probe) {
-                                    const int i = (int)((h + (unsigned)probe) % (unsigned)P.share_cap);
-                                    if (atomicCAS(&P.share_state[i], 0u, 1u) == 0u) ri = i;
-                                }
-                            }
-                            ri = __shfl_sync(kFull, ri, 0);
-                            if (ri >= 0) {
-                                if (!(wf & kSharedOut)) {
-                                    // first hand-over of this configuration: neutral outputs, every participant merges into them
-                                    wf |= kSharedOut;
-                                    if (lane == 0) {
-                                        if (P.verdict) P.verdict[c] = 0u;
-                                        if (P.first_env) P.first_env[c] = -1;
-                                        if (P.first_self) P.first_self[c] = -1;
-                                        if (P.work_out) P.work_out[c] = 0u;
-                                    }
-                                }
-                                unsigned char* rp = P.share_rec + (size_t)ri * kShareRecBytes;
-                                if (lane == 0) {
-                                    int32_t* hdr = (int32_t*)rp;
-                                    hdr[0] = c; hdr[1] = nsl; hdr[2] = kShareItems; hdr[3] = best_env; hdr[4] = best_self;
-                                }
-                                if (lane < nsl) ((int32_t*)(rp + 64))[lane] = slot_pair[lane];
-                                for (int i = lane; i < nsl * 6; i += 32) ((float4*)(rp + 64 + kNumSlots * 4))[i] = ((const float4*)slot_rt)[i];
-                                for (int i = lane; i < kShareItems; i += 32) ((uint2*)(rp + 64 + kNumSlots * 4 + kNumSlots * 96))[i] = stack[i];
-                                const int rest = sp - kShareItems;
-                                __syncwarp();
-                                for (int b = 0; b < rest; b += 32) {
-                                    const int i = b + lane;
-                                    uint2 v = make_uint2(0u, 0u);
-                                    if (i < rest) v = stack[kShareItems + i];
-                                    __syncwarp();
-                                    if (i < rest) stack[i] = v;
-                                    __syncwarp();
-                                }
-                                sp = rest;
-                                __threadfence();
-                                __syncwarp();
-                                if (lane == 0) {
-                                    atomicAdd(&P.share_ctl[0], 1);          // posted (the poster is still counted as heavy)
-                                    atomicAdd(&P.share_ctl[2], 1);
-                                    __threadfence();
-                                    atomicExch(&P.share_state[ri], 2u);
-                                }
-                            }
-                        }
-                    }
                 }
                 // ---------------------------------------------------------------- publish this batch's hits
                 if (mask_row && slot_hit) {
@@ -1186,7 +1053,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
             if ((P.flags & kFlagEnv) && be != kNone) v |= 1u;
             if ((P.flags & kFlagSelf) && (first_hit ? (iters >> 31) != 0u : bs != kNone)) v |= 2u;
             if (first_hit) { be = -1; bs = -1; }      // no first pairs in this mode
-            if (kSplit || (wf & kSharedOut)) {
+            if (kSplit) {
                 // merge with the other work items of this configuration (-1 reads as the largest unsigned value)
                 if (v && P.verdict) atomicOr(&P.verdict[c], v);
                 if ((v & 1u) && P.first_env) atomicMin((unsigned int*)&P.first_env[c], (unsigned int)be);
@@ -1197,11 +1064,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 if (P.first_env) P.first_env[c] = (v & 1u) ? be : -1;
                 if (P.first_self) P.first_self[c] = (v & 2u) ? bs : -1;
                 if (P.work_out) P.work_out[c] = iters & 0x7fffffffu;
-            }
-            if (share) {
-                __threadfence();
-                if (rec >= 0) { atomicExch(&P.share_state[rec], 0u); atomicSub(&P.share_ctl[0], 1); }      // record done (after its results)
-                if (wf & kIsHeavy) atomicSub(&P.share_ctl[1], 1);
             }
         }
         __syncwarp();

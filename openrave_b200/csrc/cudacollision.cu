@@ -24,6 +24,7 @@
 #include "../../include/cudacollision.h"
 #include "cc_device.cuh"
 #include "cc_distance.cuh"
+#include "cc_analytic.cuh"
 
 namespace {
 
@@ -54,6 +55,7 @@ struct HLink {
     std::vector<HNode> nodes;      // local indices
     std::vector<float> tridata;    // 12 floats per triangle
     int node_base = -1, tri_base = -1;
+    std::vector<cc_geom> prims;    // analytic primitives of the link (cc_body_set_link_primitives); used in analytic mode only
     int ntris() const { return (int)tris.size() / 3; }
 };
 
@@ -111,10 +113,6 @@ struct cc_scene {
     DevBuf<float4> d_nodes, d_tris;
     int total_nodes = 0, total_tris = 0;
     DevBuf<uint2> d_spill[2];               // one per pipeline lane (two chunks are in flight at a time)
-    // work sharing between the warps of a full-batch traversal (ccdev::kShareAfter): per lane, control words + record states
-    // (one array, zeroed before every launch) and the records themselves
-    DevBuf<uint32_t> d_share_ctl[2];
-    DevBuf<unsigned char> d_share_rec[2];
     int spill_warps = 0;
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -127,6 +125,7 @@ struct cc_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
     float tri_eps = 0.0f;
+    bool analytic = false;                  // fclrave semantics: links with primitives collide as exact convex shapes (cc_analytic.cuh)
     bool pair_tables = true;                // certified free-space tables for pairs that depend on <= 2 active DOFs
     // multi-device scene (cc_scene_create_multi): this is the replica on devices[0]; `peers` are full replicas on the other
     // devices.  Every mutating entry point is mirrored onto them in the same order, so body / link / pair indices agree.
@@ -329,6 +328,53 @@ void build_link_bvh(HLink& L)
         }
 }
 
+// quaternion pose -> rotation matrix (row major), double
+void quat_to_matrix(const double* x, double* Rm)
+{
+    const double q0 = x[0], q1 = x[1], q2 = x[2], q3 = x[3];
+    const double il = 2.0 / (q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    Rm[0] = 1 - il * (q2 * q2 + q3 * q3); Rm[1] = il * (q1 * q2 - q0 * q3); Rm[2] = il * (q1 * q3 + q0 * q2);
+    Rm[3] = il * (q1 * q2 + q0 * q3); Rm[4] = 1 - il * (q1 * q1 + q3 * q3); Rm[5] = il * (q2 * q3 - q0 * q1);
+    Rm[6] = il * (q1 * q3 - q0 * q2); Rm[7] = il * (q2 * q3 + q0 * q1); Rm[8] = 1 - il * (q1 * q1 + q2 * q2);
+}
+
+// half extents of a primitive's bounding box in its own frame (box: itself; cylinder r, r, h/2; capsule r, r, h/2 + r)
+void prim_half_extents(const cc_geom& g, double e[3])
+{
+    if (g.type == CC_GEOM_BOX) { e[0] = g.dims[0]; e[1] = g.dims[1]; e[2] = g.dims[2]; }
+    else if (g.type == CC_GEOM_SPHERE) { e[0] = e[1] = e[2] = g.dims[0]; }
+    else if (g.type == CC_GEOM_CYLINDER) { e[0] = e[1] = g.dims[0]; e[2] = 0.5 * g.dims[1]; }
+    else { e[0] = e[1] = g.dims[0]; e[2] = 0.5 * g.dims[1] + g.dims[0]; }
+}
+
+// The root box of a link bounds its tessellated mesh; the exact primitives stick out of their tessellation by the sagitta, so
+// the root box (link boxes, static world boxes: all pruning starts there) is grown to hold them too.
+void expand_root_for_primitives(HLink& L)
+{
+    if (L.prims.empty() || L.nodes.empty()) return;
+    double mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) { mn[k] = (double)L.nodes[0].c[k] - (double)L.nodes[0].e[k]; mx[k] = (double)L.nodes[0].c[k] + (double)L.nodes[0].e[k]; }
+    for (const cc_geom& g : L.prims) {
+        double Rm[9], e[3];
+        quat_to_matrix(g.pose, Rm);
+        prim_half_extents(g, e);
+        for (int r = 0; r < 3; ++r) {
+            double ext = 0;
+            for (int k = 0; k < 3; ++k) ext += fabs(Rm[3 * r + k]) * e[k];
+            ext += 1e-5;
+            mn[r] = std::min(mn[r], g.pose[4 + r] - ext); mx[r] = std::max(mx[r], g.pose[4 + r] + ext);
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        const double c = 0.5 * (mn[k] + mx[k]);
+        const float cf = (float)c;
+        const double e = 0.5 * (mx[k] - mn[k]) + fabs(c - (double)cf);
+        float ef = (float)e;
+        if ((double)ef < e) ef = nextafterf(ef, std::numeric_limits<float>::infinity());
+        L.nodes[0].c[k] = cf; L.nodes[0].e[k] = ef;
+    }
+}
+
 // quaternion pose -> FP32 R|t relative to `center` (matrixFromQuat, geometry.h:779-800)
 void pose_to_rt32(const double* x, const double center[3], float* o)
 {
@@ -354,6 +400,13 @@ struct Plan {
     DevBuf<int32_t> d_orig, d_emit, d_slot_root;
     DevBuf<float> d_st_xf, d_st_aabb, d_link_box;
     DevBuf<ccdev::FkStep> d_steps;
+    // analytic link pairs of the plan (same slot space; never part of `pairs`): evaluated by cc_analytic_kernel after the traversal
+    std::vector<uint32_t> apairs;
+    std::vector<int32_t> aorig;
+    int anenv = 0;
+    DevBuf<uint32_t> d_apairs;
+    DevBuf<int32_t> d_aorig, d_slot_prim;
+    DevBuf<ccdev::Prim> d_prims;
     // split traversal tables for S = 2, 4, 8 (index log2(S) - 1), built with the plan
     struct Split { DevBuf<uint32_t> d_pairs; DevBuf<int32_t> d_orig, d_part_begin, d_part_nenv; std::vector<int32_t> orig; };
     Split split[3];
@@ -403,6 +456,7 @@ struct cc_query {
     Plan dist;                               // distance queries in FK mode: every live pair, nothing hoisted (built on first use)
     bool dist_ready = false;
     std::vector<int> p_full;                 // indices of the live pairs
+    std::vector<int> p_analytic;             // pairs with an analytic link (scene in analytic mode): out of every traversal plan
     DevBuf<double> d_dist, d_dpts;
     DevBuf<int32_t> d_dpair;
     bool has_fk = false;
@@ -585,14 +639,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         for (int k = 0; k < (overlap ? 2 : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
         S->spill_warps = full_warps;
     }
-    // heavy configurations are shared between warps (CC_TUNE_SHARE=0 turns it off): 256 records per lane
-    static const int share_cap = getenv("CC_TUNE_SHARE") ? atoi(getenv("CC_TUNE_SHARE")) : 256;
-    const bool share = share_cap > 0 && !fk_only && split == 1 && !contacts && !(flags & CC_BATCH_ALL_PAIRS);
-    if (share)
-        for (int k = 0; k < (overlap ? 2 : 1); ++k) {
-            CC_CUDA(S->d_share_ctl[k].reserve(4 + (size_t)share_cap));
-            CC_CUDA(S->d_share_rec[k].reserve((size_t)share_cap * ccdev::kShareRecBytes));
-        }
     CC_CUDA(cudaEventRecord(S->ev0, st));
     if (overlap) {
         CC_CUDA(cudaEventRecord(S->ev_fork, st));
@@ -650,12 +696,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         const int need = (int)(((long long)m * split + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock);
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
-        P.share_cap = 0;
-        if (share) {
-            CC_CUDA(cudaMemsetAsync(S->d_share_ctl[k].p, 0, (4 + (size_t)share_cap) * sizeof(uint32_t), cs));
-            P.share_ctl = (int32_t*)S->d_share_ctl[k].p; P.share_state = S->d_share_ctl[k].p + 4; P.share_rec = S->d_share_rec[k].p;
-            P.share_cap = share_cap;
-        }
         if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
@@ -666,6 +706,16 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         }
         CC_CUDA(cudaGetLastError());
         S->stats.launches++;
+        if (!pl.apairs.empty()) {
+            // analytic link pairs on the exact shapes, merged into what the traversal has just written
+            ccdev::AnalyticParams AP;
+            AP.pairs = pl.d_apairs.p; AP.orig = pl.d_aorig.p; AP.npairs = (int)pl.apairs.size(); AP.nenv = pl.anenv;
+            AP.slot_prim = pl.d_slot_prim.p; AP.prims = pl.d_prims.p;
+            const long long items = (long long)m * AP.npairs;
+            ccdev::cc_analytic_kernel<<<(unsigned)((items + 127) / 128), 128, 0, cs>>>(P, AP);
+            CC_CUDA(cudaGetLastError());
+            S->stats.launches++;
+        }
         if (timeline) CC_CUDA(cudaEventRecord(S->tl_events[3 * ci + 2], cs));
         if (hio) {
             if (pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
@@ -889,6 +939,28 @@ int cc_body_set_link_mesh(cc_scene* s, int body, int link, const char* link_name
     return forward_peers(s, [&](cc_scene* p) { return cc_body_set_link_mesh(p, body, link, link_name, v, nv, tris, ntris); });
 }
 
+int cc_body_set_link_primitives(cc_scene* s, int body, int link, const cc_geom* geoms, int ngeoms)
+{
+    HBody* b = get_body(s, body);
+    if (!b || link < 0 || link >= (int)b->links.size() || ngeoms < 0 || (ngeoms > 0 && !geoms)) return fail(CC_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < ngeoms; ++i) {
+        if (geoms[i].type < CC_GEOM_BOX || geoms[i].type > CC_GEOM_CAPSULE) return fail(CC_ERR_INVALID, "unknown primitive type");
+        if (!(geoms[i].dims[0] > 0)) return fail(CC_ERR_INVALID, "primitive with a non-positive size");
+    }
+    HLink& L = b->links[link];
+    L.prims.assign(geoms, geoms + ngeoms);
+    L.dirty = true;              // the root box has to hold the exact shapes
+    s->committed = false;
+    return forward_peers(s, [&](cc_scene* p) { return cc_body_set_link_primitives(p, body, link, geoms, ngeoms); });
+}
+
+int cc_scene_set_analytic_primitives(cc_scene* s, int enabled)
+{
+    if (!s) return fail(CC_ERR_INVALID, "scene is NULL");
+    s->analytic = enabled != 0;
+    return forward_peers(s, [&](cc_scene* p) { return cc_scene_set_analytic_primitives(p, enabled); });
+}
+
 int cc_body_set_link_enabled(cc_scene* s, int body, const uint8_t* enabled)
 {
     HBody* b = get_body(s, body);
@@ -1013,7 +1085,7 @@ int cc_scene_commit(cc_scene* s)
     for (HBody* b : s->bodies) {
         if (b->removed) continue;
         for (HLink& L : b->links) {
-            if (L.dirty) { build_link_bvh(L); L.dirty = false; }
+            if (L.dirty) { build_link_bvh(L); expand_root_for_primitives(L); L.dirty = false; }
             if (L.nodes.empty()) { L.node_base = L.tri_base = -1; continue; }
             if ((nodes.size() & 1) == 0) nodes.push_back(HNode());   // odd base: sibling pairs (odd local index first) are 64-byte aligned
             L.node_base = (int)nodes.size();
@@ -1216,7 +1288,14 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
     const int nl = Q->nq;
     pl.emit.assign(std::max(1, nl), -1);
     pl.ndyn = 0;
-    for (int l = 0; l < nl; ++l) if (dynamic[l]) pl.emit[l] = pl.ndyn++;
+    std::vector<uint8_t> dyn(dynamic);
+    if (&pl == &Q->mainl && with_fk && Q->has_fk)      // the links of the analytic pairs need their per-configuration poses too
+        for (int p : Q->p_analytic) {
+            const int a = Q->quads[4 * p];
+            if (Q->moves[a]) dyn[a] = 1;
+            if (Q->quads[4 * p + 3] == 1) { const int b2 = Q->quads[4 * p + 2]; if (Q->moves[b2]) dyn[b2] = 1; }
+        }
+    for (int l = 0; l < nl; ++l) if (dyn[l]) pl.emit[l] = pl.ndyn++;
     std::vector<std::pair<int, int>> statics;                // (body, link) in order of first use
     auto static_slot = [&](int body, int link) {
         for (size_t i = 0; i < statics.size(); ++i) if (statics[i].first == body && statics[i].second == link) return (int)i;
@@ -1236,6 +1315,21 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         pl.orig.push_back(p);
         if (cls == 0) pl.nenv++;
     }
+    // analytic pairs (cc_analytic_kernel) live in the same slot space
+    const bool with_analytic = (&pl == &Q->mainl || &pl == &Q->full) && !Q->p_analytic.empty();
+    std::vector<int> asa_v, asb_v;
+    pl.apairs.clear(); pl.aorig.clear(); pl.anenv = 0;
+    if (with_analytic)
+        for (int p : Q->p_analytic) {
+            const int a = Q->quads[4 * p], ob = Q->quads[4 * p + 1], j = Q->quads[4 * p + 2], cls = Q->quads[4 * p + 3];
+            const int sa = pl.emit[a] >= 0 ? pl.emit[a] : -1 - static_slot(Q->ql_body[a], Q->ql_link[a]);
+            int sb;
+            if (cls == 1) sb = pl.emit[j] >= 0 ? pl.emit[j] : -1 - static_slot(Q->ql_body[j], Q->ql_link[j]);
+            else sb = -1 - static_slot(ob, j);
+            asa_v.push_back(sa); asb_v.push_back(sb);
+            pl.aorig.push_back(p);
+            if (cls == 0) pl.anenv++;
+        }
     pl.nstatic = (int)statics.size();
     pl.statics = statics;
     if (pl.ndyn + pl.nstatic > 0xffff) return fail(CC_ERR_UNSUPPORTED, "more than 65535 link slots");
@@ -1243,6 +1337,11 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         const uint32_t sa = sa_v[i] >= 0 ? (uint32_t)sa_v[i] : (uint32_t)(pl.ndyn + (-1 - sa_v[i]));
         const uint32_t sb = sb_v[i] >= 0 ? (uint32_t)sb_v[i] : (uint32_t)(pl.ndyn + (-1 - sb_v[i]));
         pl.pairs.push_back(sa | (sb << 16));
+    }
+    for (size_t i = 0; i < asa_v.size(); ++i) {
+        const uint32_t sa = asa_v[i] >= 0 ? (uint32_t)asa_v[i] : (uint32_t)(pl.ndyn + (-1 - asa_v[i]));
+        const uint32_t sb = asb_v[i] >= 0 ? (uint32_t)asb_v[i] : (uint32_t)(pl.ndyn + (-1 - asb_v[i]));
+        pl.apairs.push_back(sa | (sb << 16));
     }
     std::vector<int32_t> roots((size_t)std::max(1, pl.ndyn + pl.nstatic), 0);
     std::vector<float> linkbox((size_t)std::max(1, pl.ndyn) * 8, 0.f), stxf((size_t)std::max(1, pl.nstatic) * 12, 0.f),
@@ -1260,6 +1359,31 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         roots[pl.ndyn + i] = L.node_base < 0 ? 0 : L.node_base;
         pose_to_rt32(L.xf, Q->center, &stxf[(size_t)i * 12]);
         static_aabb(L, Q->center, &staabb[(size_t)i * 8]);
+    }
+    if (with_analytic) {
+        // primitives of every slot (dynamic query links first, then the statics), FP32, pose in the link frame
+        std::vector<int32_t> slot_prim(1, 0);
+        std::vector<ccdev::Prim> prims;
+        auto add_link = [&](const HLink& L) {
+            for (const cc_geom& g : L.prims) {
+                ccdev::Prim d;
+                double Rm[9];
+                quat_to_matrix(g.pose, Rm);
+                for (int k = 0; k < 9; ++k) d.R[k] = (float)Rm[k];
+                for (int k = 0; k < 3; ++k) d.t[k] = (float)g.pose[4 + k];
+                d.dims[0] = (float)g.dims[0]; d.dims[1] = (float)g.dims[1]; d.dims[2] = (float)g.dims[2];
+                if (g.type == CC_GEOM_CYLINDER || g.type == CC_GEOM_CAPSULE) d.dims[1] = (float)(0.5 * g.dims[1]);     // half height
+                d.type = g.type;
+                prims.push_back(d);
+            }
+            slot_prim.push_back((int32_t)prims.size());
+        };
+        std::vector<int> link_of_slot(pl.ndyn, -1);
+        for (int l = 0; l < nl; ++l) if (pl.emit[l] >= 0) link_of_slot[pl.emit[l]] = l;
+        for (int d = 0; d < pl.ndyn; ++d) add_link(Q->qlink(link_of_slot[d]));
+        for (int i = 0; i < pl.nstatic; ++i) add_link(S->bodies[statics[i].first]->links[statics[i].second]);
+        CC_CUDA(pl.d_apairs.upload(pl.apairs)); CC_CUDA(pl.d_aorig.upload(pl.aorig));
+        CC_CUDA(pl.d_slot_prim.upload(slot_prim)); CC_CUDA(pl.d_prims.upload(prims));
     }
     pl.steps.clear();
     pl.nsave = 0;
@@ -1433,11 +1557,20 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     // ---- split the pair list and lay the three plans out
     const int np = (int)Q->quads.size() / 4;
     Q->mask_words = std::max(1, (np + 31) / 32);
-    std::vector<int> p_full, p_main, p_hoist;
+    std::vector<int> p_full, p_full_mesh, p_main, p_hoist;
+    Q->p_analytic.clear();
     for (int p = 0; p < np; ++p) {
         if (!Q->pair_live[p]) continue;
         const int a = Q->quads[4 * p], cls = Q->quads[4 * p + 3];
         p_full.push_back(p);
+        if (S->analytic) {
+            // fclrave semantics: a pair with a link made of primitives is decided on the exact shapes (cc_analytic.cuh), per
+            // configuration (never hoisted, never certified)
+            const HLink& La = Q->qlink(a);
+            const HLink& Lb = cls == 1 ? Q->qlink(Q->quads[4 * p + 2]) : S->bodies[Q->quads[4 * p + 1]]->links[Q->quads[4 * p + 2]];
+            if (!La.prims.empty() || !Lb.prims.empty()) { Q->p_analytic.push_back(p); continue; }
+        }
+        p_full_mesh.push_back(p);
         bool hoist = false;
         if (allow_hoist && Q->has_fk) {
             if (cls == 0) hoist = !moves[a];
@@ -1463,7 +1596,7 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     Q->p_full = p_full;
     Q->allow_tables = allow_hoist && Q->has_fk && Q->nq == (int)B->links.size() && !Q->naffine;     // not with grabbed links (their chain is not walked below), not with a moving base
     Q->pose_epoch = S->pose_epoch;           // everything below reads the live scene state: that IS the query's snapshot
-    int rc = build_plan(Q, Q->full, p_full, all_dynamic, false);
+    int rc = build_plan(Q, Q->full, p_full_mesh, all_dynamic, false);
     if (rc == CC_OK) rc = build_plan(Q, Q->hoisted, p_hoist, all_dynamic, true);
     if (rc == CC_OK) rc = build_plan(Q, Q->mainl, p_main, Q->has_fk ? main_dynamic : all_dynamic, true);
     if (rc != CC_OK) return rc;
