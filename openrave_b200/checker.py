@@ -43,6 +43,14 @@ class cc_certificate(ctypes.Structure):
                                                "min_distance")]
 
 
+class cc_geom(ctypes.Structure):
+    """Mirror of `struct cc_geom` (include/cudacollision.h): one analytic primitive of a link."""
+    _fields_ = [("type", ctypes.c_int32), ("reserved", ctypes.c_int32), ("pose", ctypes.c_double * 8), ("dims", ctypes.c_double * 4)]
+
+
+GEOM_TYPES = {"box": 1, "sphere": 2, "cylinder": 3, "capsule": 4}
+
+
 class cc_stats(ctypes.Structure):
     _fields_ = [("configs", ctypes.c_uint64), ("bv_tests", ctypes.c_uint64), ("tri_tests", ctypes.c_uint64),
                 ("launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double)]
@@ -58,7 +66,8 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
            "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_query_get_certificates", "cc_debug_pair_rates",
-           "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices", "cc_query_create_affine"]
+           "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices", "cc_query_create_affine",
+           "cc_body_set_link_primitives", "cc_scene_set_analytic_primitives"]
 
 _lib = None
 
@@ -81,6 +90,8 @@ def load_library():
     lib.cc_scene_remove_body.argtypes = [vp, ci]
     lib.cc_body_set_link_mesh.argtypes = [vp, ci, ci, ctypes.c_char_p, vp, ci, vp, ci]
     lib.cc_body_set_link_enabled.argtypes = [vp, ci, vp]
+    lib.cc_body_set_link_primitives.argtypes = [vp, ci, ci, vp, ci]
+    lib.cc_scene_set_analytic_primitives.argtypes = [vp, ci]
     lib.cc_body_set_link_transforms.argtypes = [vp, ci, vp]
     lib.cc_body_set_attached.argtypes = [vp, ci, ci, ci]
     lib.cc_body_set_kinematics.argtypes = [vp, ci, ci, ci, vp, vp]
@@ -406,6 +417,8 @@ class CudaCollisionChecker(object):
             self.lib.cc_scene_destroy(self.scene)
             self.scene = None
         self._create_scene()
+        if getattr(self, "_analytic", False):
+            self._ck(self.lib.cc_scene_set_analytic_primitives(self.scene, 1))
         self._ids, self._bodies, self._dirty, self._kin_dirty = {}, {}, set(), set()
         self._grab_epochs = {}
         for b in self.env.GetBodies():
@@ -431,6 +444,17 @@ class CudaCollisionChecker(object):
             v, i = flatten.link_mesh_arrays(l)
             self._ck(self.lib.cc_body_set_link_mesh(self.scene, bid.value, l.index, l.name.encode(), _ptr(v), v.shape[0],
                                                     _ptr(i), i.shape[0]))
+            prims = getattr(l, "prims", None)
+            if prims:       # KinBody::GeometryInfo of a link made of primitives only: used when the analytic mode is on
+                arr = (cc_geom * len(prims))()
+                for k, g in enumerate(prims):
+                    arr[k].type = GEOM_TYPES[g["type"]]
+                    for j, x in enumerate(list(g["t"][0]) + list(g["t"][1]) + [0.0]):
+                        arr[k].pose[j] = x
+                    d = list(g["data"]) + [0.0, 0.0, 0.0, 0.0]
+                    for j in range(4):
+                        arr[k].dims[j] = d[j]
+                self._ck(self.lib.cc_body_set_link_primitives(self.scene, bid.value, l.index, ctypes.addressof(arr), len(prims)))
         self._dirty.add(id(body))
         self._kin_dirty.add(id(body))
         self._invalidate()
@@ -632,6 +656,12 @@ class CudaCollisionChecker(object):
 
     def SetPairTables(self, enabled):
         self._ck(self.lib.cc_scene_set_pair_tables(self.scene, 1 if enabled else 0))
+        self._invalidate()
+
+    def SetAnalyticPrimitives(self, enabled):
+        """fclrave semantics: links made of box / sphere / cylinder primitives collide as the exact shapes (cc_analytic.cuh)."""
+        self._ck(self.lib.cc_scene_set_analytic_primitives(self.scene, 1 if enabled else 0))
+        self._analytic = bool(enabled)
         self._invalidate()
 
     def SetTriangleEpsilon(self, eps):

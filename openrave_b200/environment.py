@@ -89,6 +89,15 @@ class Environment(object):
         if filename.endswith(".npz"):
             from .serialize import load_environment_into
             load_environment_into(self, filename)
+            # side fixture of the analytic-geometry mode: the primitive geometries of the links that consist of primitives only
+            import json
+            import os
+            side = filename[:-4] + ".prims.json"
+            if os.path.isfile(side):
+                prims = json.load(open(side))
+                for b in self.bodies:
+                    for l in b.links:
+                        l.prims = prims.get(b.name, {}).get(l.name, [])
             return True
         from .xmlscene import SceneLoader
         SceneLoader(self.data_dirs).load_environment(self, filename)
