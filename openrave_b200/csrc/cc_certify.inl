@@ -133,6 +133,27 @@ int cc_debug_pair_rates(const cc_joint* joints, int njoints, int nlinks, const i
 }
 }
 
+// (Re)upload the tables and the per-pair table indices in the order of the batched plan and of its split variants.
+static int upload_pair_tables(cc_query* Q)
+{
+    const Plan& pl = Q->mainl;
+    int valid = 0;
+    for (int32_t t : Q->table_of_orig) valid += t >= 0 ? 1 : 0;
+    Q->ntables = valid;
+    if (Q->h_tables.empty()) return CC_OK;
+    std::vector<int32_t> t(pl.orig.size(), -1);
+    for (size_t i = 0; i < t.size(); ++i) t[i] = Q->table_of_orig[pl.orig[i]];
+    CC_CUDA(Q->d_tables.upload(Q->h_tables));
+    CC_CUDA(Q->d_table_bits.upload(Q->h_bits));
+    CC_CUDA(Q->d_pair_table.upload(t));
+    for (int si = 0; si < 3; ++si) {
+        std::vector<int32_t> ts(pl.split[si].orig.size(), -1);
+        for (size_t i = 0; i < ts.size(); ++i) ts[i] = Q->table_of_orig[pl.split[si].orig[i]];
+        CC_CUDA(Q->d_pair_table_split[si].upload(ts));
+    }
+    return CC_OK;
+}
+
 static int build_pair_tables(cc_query* Q)
 {
     cc_scene* S = Q->scene;
@@ -151,8 +172,12 @@ static int build_pair_tables(cc_query* Q)
     std::vector<double> radius_cache(nlb, -1.0);
     auto rad = [&](int l) { if (radius_cache[l] < 0) radius_cache[l] = link_radius(B->links[l]); return radius_cache[l]; };
 
-    std::vector<uint8_t> dropped(Q->quads.size() / 4, 0);
-    Q->certs.clear();
+    // certificates persist in the query (cc_query_refresh drops only the ones a moved body touches); a build examines the pairs
+    // that have none yet
+    const size_t npairs_all = Q->quads.size() / 4;
+    if (Q->cert_dropped.size() != npairs_all) { Q->cert_dropped.assign(npairs_all, 0); Q->table_of_orig.assign(npairs_all, -1); Q->h_tables.clear(); Q->h_bits.clear(); Q->certs.clear(); }
+    std::vector<uint8_t>& dropped = Q->cert_dropped;
+    const std::vector<uint8_t> dropped_before(dropped);
     // safety margin of every certificate: FP32 error of the distance kernel (~1e-5 m) + the 1e-4 m contact band, plus the
     // conservative margin of the triangle test when the caller has set one (pairs closer than it count as touching)
     Q->cert_tri_eps = S->tri_eps;
@@ -222,7 +247,7 @@ static int build_pair_tables(cc_query* Q)
     struct Cand { int p; int a, ob, j, cls; std::vector<int> dofs; std::vector<double> K; };
     std::vector<Cand> cands;
     for (int p : Q->p_main) {
-        if (dropped[p]) continue;
+        if (dropped[p] || Q->table_of_orig[p] >= 0) continue;      // already certified (everywhere / with a table)
         Cand c;
         c.p = p; c.a = Q->quads[4 * p]; c.ob = Q->quads[4 * p + 1]; c.j = Q->quads[4 * p + 2]; c.cls = Q->quads[4 * p + 3];
         if (c.a >= nlb || (c.cls == 1 && c.j >= nlb)) continue;
@@ -244,9 +269,9 @@ static int build_pair_tables(cc_query* Q)
     }
     std::sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.dofs < y.dofs; });
 
-    std::vector<ccdev::PairTable> tables;
-    std::vector<uint32_t> bits;
-    std::vector<int32_t> table_of_orig(Q->quads.size() / 4, -1);
+    std::vector<ccdev::PairTable>& tables = Q->h_tables;
+    std::vector<uint32_t>& bits = Q->h_bits;
+    std::vector<int32_t>& table_of_orig = Q->table_of_orig;
     const size_t max_bits_words = (size_t)1 << 20;                  // 4 MB of tables at most
     // One pass over a set of candidates that share their DOF set, on an n0 x n1 grid.  Pairs certified in every cell are
     // marked dropped; with `final` the partly certified ones get their bit table, otherwise they are returned for a finer pass.
@@ -371,14 +396,15 @@ static int build_pair_tables(cc_query* Q)
     CC_CUDA(cudaSetDevice(S->device));
     CC_CUDA(cudaDeviceSynchronize());
     std::vector<int> p_keep;
+    int newly_dropped = 0;
     for (int p : Q->p_main) {
-        if (dropped[p]) { Q->ndropped++; continue; }
+        if (dropped[p]) { Q->ndropped++; newly_dropped += dropped_before[p] ? 0 : 1; continue; }
         p_keep.push_back(p);
     }
     if (getenv("CC_DEBUG_TABLES"))
         fprintf(stderr, "[tables] plan before: %zu pairs, %d dynamic slots, %d static, %zu fk steps; dropping %d\n", Q->mainl.pairs.size(), Q->mainl.ndyn,
                 Q->mainl.nstatic, Q->mainl.steps.size(), Q->ndropped);
-    if (Q->ndropped > 0) {
+    if (p_keep.size() != Q->p_main.size()) {
         std::vector<uint8_t> main_dynamic(Q->nq, 0);
         for (int p : p_keep) {
             const int a = Q->quads[4 * p];
@@ -392,32 +418,23 @@ static int build_pair_tables(cc_query* Q)
     if (getenv("CC_DEBUG_TABLES"))
         fprintf(stderr, "[tables] plan after: %zu pairs, %d dynamic slots, %d static, %zu fk steps, %zu tables\n", Q->mainl.pairs.size(), Q->mainl.ndyn,
                 Q->mainl.nstatic, Q->mainl.steps.size(), tables.size());
-    const Plan& pl = Q->mainl;
-    if (!tables.empty()) {
-        std::vector<int32_t> t(pl.orig.size(), -1);
-        for (size_t i = 0; i < t.size(); ++i) t[i] = table_of_orig[pl.orig[i]];
-        CC_CUDA(Q->d_tables.upload(tables));
-        CC_CUDA(Q->d_table_bits.upload(bits));
-        CC_CUDA(Q->d_pair_table.upload(t));
-        for (int si = 0; si < 3; ++si) {
-            std::vector<int32_t> ts(pl.split[si].orig.size(), -1);
-            for (size_t i = 0; i < ts.size(); ++i) ts[i] = table_of_orig[pl.split[si].orig[i]];
-            CC_CUDA(Q->d_pair_table_split[si].upload(ts));
-        }
+    {
+        const int rc = upload_pair_tables(Q);
+        if (rc != CC_OK) return rc;
     }
     CC_CUDA(cudaDeviceSynchronize());
-    Q->ntables = (int)tables.size();
+    (void)newly_dropped;
     return CC_OK;
 }
 
 // Tables cost a few hundred milliseconds to build: they are built once a query has seen enough batched configurations.
-extern "C" { static int reset_certificates(cc_query* q); }
+extern "C" { static int invalidate_certificates(cc_query* q, const std::vector<uint8_t>* invalid); }
 
 static int maybe_build_tables(cc_query* q, int n)
 {
     // the certificates were proven with a margin that includes the triangle-test epsilon in force at the time
     if (q->tables_done && q->cert_tri_eps != q->scene->tri_eps && (q->ntables > 0 || q->ndropped > 0)) {
-        int rc = reset_certificates(q);
+        int rc = invalidate_certificates(q, nullptr);
         if (rc != CC_OK) return rc;
     }
     if (q->tables_done) return CC_OK;

@@ -394,6 +394,7 @@ struct Plan {
     std::vector<int32_t> orig;
     int nenv = 0, ndyn = 0, nstatic = 0, nsave = 0;
     std::vector<std::pair<int, int>> statics;   // (body, link) of every static slot (poses refreshed by cc_query_refresh)
+    std::vector<double> st_pose;                // [nstatic][8] the poses those slots were laid out with (what moved since? cc_query_refresh)
     std::vector<int32_t> emit;       // [nq] link -> dynamic slot or -1
     std::vector<ccdev::FkStep> steps;
     DevBuf<uint32_t> d_pairs;
@@ -442,7 +443,12 @@ struct cc_query {
     std::vector<int> col_of_dof;             // [ndof] column of q feeding a DOF, -1: not active
     uint64_t fk_configs_seen = 0;
     uint64_t pose_epoch = 0;                 // cc_scene::pose_epoch when the query captured its snapshot (create / refresh)
-    std::vector<cc_certificate> certs;       // what the last certificate build proved, pair by pair (grid certificates only)
+    std::vector<cc_certificate> certs;       // what the certificate builds proved, pair by pair (grid certificates only)
+    std::vector<uint8_t> cert_dropped;       // [npairs] certified collision-free over the whole active range: out of the batched plan
+    std::vector<int32_t> table_of_orig;      // [npairs] bit table of a partly certified pair, -1: none
+    std::vector<ccdev::PairTable> h_tables;  // host copies of the tables / their bits (new certificates are appended)
+    std::vector<uint32_t> h_bits;
+    std::vector<double> snap_static;         // poses (8 doubles per static slot of `mainl`) the certificates were proven on
     int ntables = 0;
     DevBuf<int32_t> d_pair_table;            // mainl order
     DevBuf<int32_t> d_pair_table_split[3];   // split orders
@@ -1354,11 +1360,13 @@ static int build_plan(cc_query* Q, Plan& pl, const std::vector<int>& plist, cons
         if (!L.nodes.empty()) { for (int k = 0; k < 3; ++k) { o[k] = L.nodes[0].c[k]; o[3 + k] = L.nodes[0].e[k]; } o[6] = 1.0f; }
         else { o[0] = o[1] = o[2] = 0.f; o[3] = o[4] = o[5] = -1e30f; }   // no geometry: an AABB that overlaps nothing
     }
+    pl.st_pose.assign((size_t)pl.nstatic * 8, 0.0);
     for (int i = 0; i < pl.nstatic; ++i) {
         const HLink& L = S->bodies[statics[i].first]->links[statics[i].second];
         roots[pl.ndyn + i] = L.node_base < 0 ? 0 : L.node_base;
         pose_to_rt32(L.xf, Q->center, &stxf[(size_t)i * 12]);
         static_aabb(L, Q->center, &staabb[(size_t)i * 8]);
+        memcpy(&pl.st_pose[(size_t)i * 8], L.xf, 8 * sizeof(double));
     }
     if (with_analytic) {
         // primitives of every slot (dynamic query links first, then the statics), FP32, pose in the link frame
@@ -1854,27 +1862,38 @@ static int query_create_pairs_one(cc_scene* s, int body, const int32_t* triples,
     return CC_OK;
 }
 
-// Forget the free-space certificates of a query: the batched plan gets its full pair list back, the certificates are rebuilt
-// once the query has seen another 16k configurations.
-static int reset_certificates(cc_query* q)
+// Forget free-space certificates of a query: those of the pairs flagged in `invalid` (all of them when it is NULL).  Pairs that
+// had left the batched plan come back into it; the next certificate build (after another 16k configurations) examines only the
+// pairs that have no certificate.
+static int invalidate_certificates(cc_query* q, const std::vector<uint8_t>* invalid)
 {
-    const bool dropped = q->p_main.size() != q->p_main_all.size();
-    q->ntables = 0; q->ndropped = 0; q->tables_done = false; q->fk_configs_seen = 0;
-    q->certs.clear();
-    if (dropped) {
-        CC_CUDA(cudaSetDevice(q->scene->device));
-        CC_CUDA(cudaDeviceSynchronize());
+    if (q->cert_dropped.empty()) { q->tables_done = false; q->fk_configs_seen = 0; return CC_OK; }
+    bool replan = false, any = false;
+    for (size_t p = 0; p < q->cert_dropped.size(); ++p) {
+        if (invalid && !(*invalid)[p]) continue;
+        if (q->cert_dropped[p]) { q->cert_dropped[p] = 0; q->ndropped--; replan = true; any = true; }
+        if (q->table_of_orig[p] >= 0) { q->table_of_orig[p] = -1; any = true; }
+    }
+    if (!any) return CC_OK;
+    q->certs.erase(std::remove_if(q->certs.begin(), q->certs.end(), [&](const cc_certificate& c) { return !invalid || (*invalid)[c.pair]; }), q->certs.end());
+    q->tables_done = false; q->fk_configs_seen = 0;
+    CC_CUDA(cudaSetDevice(q->scene->device));
+    CC_CUDA(cudaDeviceSynchronize());
+    if (replan) {
+        std::vector<int> keep;
         std::vector<uint8_t> main_dynamic(q->nq, 0);
         for (int p : q->p_main_all) {
+            if (q->cert_dropped[p]) continue;
+            keep.push_back(p);
             const int a = q->quads[4 * p];
             if (q->moves[a]) main_dynamic[a] = 1;
             if (q->quads[4 * p + 3] == 1) { const int b2 = q->quads[4 * p + 2]; if (q->moves[b2]) main_dynamic[b2] = 1; }
         }
-        q->p_main = q->p_main_all;
+        q->p_main = keep;
         int rc = build_plan(q, q->mainl, q->p_main, main_dynamic, true);
         if (rc != CC_OK) return rc;
     }
-    return CC_OK;
+    return upload_pair_tables(q);
 }
 
 // Re-read what a bound query captured from the scene — the poses of every static slot (other bodies' links, query links no
@@ -1888,12 +1907,42 @@ int cc_query_refresh(cc_query* q)
     if (!S->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     CC_CUDA(cudaSetDevice(S->device));
     CC_CUDA(cudaDeviceSynchronize());
+    // what moved since the snapshot: the query body's base, and which other bodies (the static slots of the plan that holds
+    // EVERY live pair — a body whose pairs are all certified no longer appears in the batched plan)
+    const bool base_moved = memcmp(q->base, B->links[0].xf, 7 * sizeof(double)) != 0;
+    std::vector<uint8_t> body_moved(S->bodies.size(), 0);
+    for (int i = 0; i < q->full.nstatic && (size_t)i * 8 < q->full.st_pose.size(); ++i) {
+        const std::pair<int, int>& sl = q->full.statics[i];
+        if (memcmp(&q->full.st_pose[(size_t)i * 8], S->bodies[sl.first]->links[sl.second].xf, 7 * sizeof(double)) != 0) body_moved[sl.first] = 1;
+    }
     memcpy(q->base, B->links[0].xf, sizeof(q->base));
     q->pose_epoch = S->pose_epoch;
     q->center[0] = q->base[4]; q->center[1] = q->base[5]; q->center[2] = q->base[6];
     for (int d = 0; d < B->ndof && d < (int)q->col_of_dof.size(); ++d) if (q->col_of_dof[d] >= 0) q->cur_active[q->col_of_dof[d]] = B->dofvals[d];
-    // certificates depend on the captured poses: back to the full pair list, to be rebuilt after the next 16k configurations
-    { int rc = reset_certificates(q); if (rc != CC_OK) return rc; }
+    // inactive DOF values are folded into the chain programs' constants: did any change?
+    bool inactive_changed = false;
+    for (ccdev::FkStep& st : q->steps) {
+        if (st.src_col >= 0 || (st.flags & 1)) continue;
+        for (const cc_joint& j : B->joints)
+            if (j.parent_link == st.parent && j.child_link == st.child) {
+                const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+                const double v = srcdof >= 0 ? B->dofvals[srcdof] : 0.0;
+                if (v != st.src_const) { st.src_const = v; inactive_changed = true; }
+                break;
+            }
+    }
+    // free-space certificates were proven on the old poses: drop the ones a moved body touches — every environment pair when
+    // the robot's base moved, everything when an inactive DOF changed (it may sit on the path between two links) — and keep
+    // the rest; the dropped ones are re-examined after the next 16k configurations
+    if (!q->cert_dropped.empty()) {
+        std::vector<uint8_t> invalid(q->cert_dropped.size(), 0);
+        for (size_t p = 0; p < invalid.size(); ++p) {
+            const int ob = q->quads[4 * p + 1], cls = q->quads[4 * p + 3];
+            invalid[p] = inactive_changed || (cls == 0 && (base_moved || body_moved[ob])) ? 1 : 0;
+        }
+        const int rc = invalidate_certificates(q, &invalid);
+        if (rc != CC_OK) return rc;
+    }
     Plan* plans[4] = {&q->full, &q->mainl, &q->hoisted, q->dist_ready ? &q->dist : nullptr};
     for (Plan* pl : plans) {
         if (!pl || pl->nstatic == 0) continue;
@@ -1902,29 +1951,16 @@ int cc_query_refresh(cc_query* q)
             const HLink& L = S->bodies[pl->statics[i].first]->links[pl->statics[i].second];
             pose_to_rt32(L.xf, q->center, &stxf[(size_t)i * 12]);
             static_aabb(L, q->center, &staabb[(size_t)i * 8]);
+            if ((size_t)i * 8 + 8 <= pl->st_pose.size()) memcpy(&pl->st_pose[(size_t)i * 8], L.xf, 8 * sizeof(double));
         }
         CC_CUDA(pl->d_st_xf.upload(stxf)); CC_CUDA(pl->d_st_aabb.upload(staabb));
     }
-    // inactive DOF values are folded into the chain programs' constants: re-read them and recompile
-    {
-        bool changed = false;
-        for (ccdev::FkStep& st : q->steps) {
-            if (st.src_col >= 0 || (st.flags & 1)) continue;
-            for (const cc_joint& j : B->joints)
-                if (j.parent_link == st.parent && j.child_link == st.child) {
-                    const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
-                    const double v = srcdof >= 0 ? B->dofvals[srcdof] : 0.0;
-                    if (v != st.src_const) { st.src_const = v; changed = true; }
-                    break;
-                }
+    if (inactive_changed)
+        for (Plan* pl : plans) {
+            if (!pl || pl->steps.empty()) continue;
+            compile_fk_program(q, *pl);
+            CC_CUDA(pl->d_steps.upload(pl->steps));
         }
-        if (changed)
-            for (Plan* pl : plans) {
-                if (!pl || pl->steps.empty()) continue;
-                compile_fk_program(q, *pl);
-                CC_CUDA(pl->d_steps.upload(pl->steps));
-            }
-    }
     CC_CUDA(cudaDeviceSynchronize());
     {
         const int rc = evaluate_hoisted(q);
