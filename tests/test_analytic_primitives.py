@@ -85,7 +85,7 @@ def _seg_seg_dist(p1, q1, p2, q2):
     return np.linalg.norm((p1 + d1 * s) - (p2 + d2 * t))
 
 
-def _check(ga, gb, exact_distance, n=6000, spread=0.6, band=2e-5):
+def _check(ga, gb, exact_distance, n=6000, spread=0.3, band=2e-5):
     env, mover, obstacle, cc = _two_prim_scene(ga, gb)
     T = _random_poses(n, 5, spread)
     bq = cc.bind(mover)
@@ -95,7 +95,7 @@ def _check(ga, gb, exact_distance, n=6000, spread=0.6, band=2e-5):
     d = np.array([exact_distance(_rot(T[i, 0, 0:4]), T[i, 0, 4:7]) for i in range(n)])
     clear = np.abs(d) > band
     assert (hit[clear] == (d[clear] < 0)).all(), int((hit[clear] != (d[clear] < 0)).sum())
-    assert 0.1 < hit.mean() < 0.9
+    assert 0.05 < hit.mean() < 0.95, hit.mean()
     assert (fe[hit] == 0).all() and (fe[~hit] == -1).all()
     return hit
 
@@ -133,7 +133,7 @@ def test_box_box_equals_the_tessellated_answer():
     from openrave_b200.checker import BATCH_ENV
     ha, hb = [0.2, 0.05, 0.3], [0.1, 0.25, 0.15]
     env, mover, obstacle, cc = _two_prim_scene(dict(type="box", data=ha), dict(type="box", data=hb))
-    T = _random_poses(8000, 7, 0.6)
+    T = _random_poses(8000, 7, 0.35)
     va = cc.bind(mover).check_poses(T)[0]
     cc.SetAnalyticPrimitives(False)
     bq = cc.bind(mover)
@@ -168,9 +168,12 @@ def test_scene_analytic_is_a_superset_within_the_sagitta(scene):
     sagitta = rmax * (1.0 - math.cos(math.pi / 51.0)) + 2e-5
     gained = ana["verdict"] != tess["verdict"]
     assert (dist[gained] <= sagitta).all(), (int(gained.sum()), float(dist[gained].max()) if gained.any() else 0.0, sagitta)
-    same = ~gained
-    assert np.array_equal(ana["first_env_index"][same], tess["first_env_index"][same])
-    assert np.array_equal(ana["first_self_index"][same], tess["first_self_index"][same])
+    # the first colliding pair in reference order can only move EARLIER (an exact shape touching where its tessellation did not)
+    for key in ("first_env_index", "first_self_index"):
+        a, t = ana[key], tess[key]
+        both = (a >= 0) & (t >= 0)
+        assert (a[both] <= t[both]).all() and ((t >= 0) <= (a >= 0)).all()
+        assert (a[both] == t[both]).mean() > 0.98
     # complete masks agree where the verdicts do; single-state overloads run through the same pass
     m1 = cc.CheckCollisionBatch(robot, q[:2000], all_pairs=True)["mask"]
     cc.SetAnalyticPrimitives(False)

@@ -128,13 +128,13 @@ def test_gpu_cache_misses_of_a_batch_reach_the_cuda_checker_in_one_call():
     configs0 = gpu.GetStatistics()["configs"]
     r1 = cc.CheckCollisionBatch(robot2, q)
     st = gpu.GetStatistics()
-    assert st["configs"] - configs0 == len(q) and 1 <= st["launches"] - launches0 <= 4          # one batched call (FK + traversal kernels)
+    assert len(q) <= st["configs"] - configs0 <= len(q) + 2 and 1 <= st["launches"] - launches0 <= 8      # one batched call (+ the bind-time probe)
     assert not r1["from_cache"].any()
     ref = orc.check_batch(robot, q[:1500], active=act, want_band=True)
     band = (ref["near"] != 0) | ((ref["verdict"] != 0) & (ref["penetration"] <= 1e-4))
     assert not ((r1["verdict"][:1500] != ref["verdict"]) & ~band).any()
     r2 = cc.CheckCollisionBatch(robot2, q)                                                      # all from the cache now
-    assert gpu.GetStatistics()["configs"] == st["configs"] and (r2["from_cache"] == 3).all()
+    assert gpu.GetStatistics()["configs"] == st["configs"] and (r2["from_cache"] == 3).all()                # nothing reached the GPU
     assert np.array_equal(r2["verdict"], r1["verdict"])
     # single-state calls: a miss reaches the GPU's single-state overloads, a repeat does not
     qn = sample_configs(robot, 30, seed=9, active=act)
