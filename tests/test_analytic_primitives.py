@@ -9,7 +9,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import load_scene, sample_configs
+from conftest import ORACLE_KIND, load_scene, sample_configs
 from openrave_b200 import kinbody as kb
 from openrave_b200 import ravemath as rm
 
@@ -172,8 +172,23 @@ def test_scene_analytic_is_a_superset_within_the_sagitta(scene):
     for key in ("first_env_index", "first_self_index"):
         a, t = ana[key], tess[key]
         both = (a >= 0) & (t >= 0)
-        assert (a[both] <= t[both]).all() and ((t >= 0) <= (a >= 0)).all()
+        assert ((t >= 0) <= (a >= 0)).all()
         assert (a[both] == t[both]).mean() > 0.98
+        # ... except where the tessellated contact of the earlier pair is a graze: the FP32 GJK of the exact shapes and the FP32
+        # triangle test may disagree inside the contact band of THAT pair (oracle: colliding with a penetration measure <= 1e-3 m)
+        later = np.flatnonzero(both & (a > t))
+        assert len(later) <= max(2, int(both.sum()) // 200), len(later)
+        if len(later):
+            import oracle
+            env_o = load_scene(scene)
+            orc = oracle.OracleChecker(env_o, ORACLE_KIND)
+            bq = tess["query"]
+            for c in later[:20]:
+                l1, ob, l2, _ = bq.pairs[int(t[c])]
+                name = cc.body_from_id(int(ob)).name
+                other = [b for b in env_o.GetBodies() if b.name == name][0]
+                cls = orc.pair_band(env_o.GetRobots()[0], q[c:c + 1], [(int(l1), orc._ids[id(other)], int(l2))], band=1e-3)[0, 0]
+                assert cls in (1, 2), "configuration %d: pair %d found by the triangle test, missed by the exact shapes, class %d" % (c, int(t[c]), cls)
     # complete masks agree where the verdicts do; single-state overloads run through the same pass
     m1 = cc.CheckCollisionBatch(robot, q[:2000], all_pairs=True)["mask"]
     cc.SetAnalyticPrimitives(False)

@@ -128,7 +128,7 @@ def test_gpu_cache_misses_of_a_batch_reach_the_cuda_checker_in_one_call():
     configs0 = gpu.GetStatistics()["configs"]
     r1 = cc.CheckCollisionBatch(robot2, q)
     st = gpu.GetStatistics()
-    assert len(q) <= st["configs"] - configs0 <= len(q) + 2 and 1 <= st["launches"] - launches0 <= 8      # one batched call (+ the bind-time probe)
+    assert len(q) <= st["configs"] - configs0 <= len(q) + 2 and 1 <= st["launches"] - launches0 <= 64     # one batched call (+ the bind-time probe and, past 16k configurations, the kernels that build the certificates)
     assert not r1["from_cache"].any()
     ref = orc.check_batch(robot, q[:1500], active=act, want_band=True)
     band = (ref["near"] != 0) | ((ref["verdict"] != 0) & (ref["penetration"] <= 1e-4))
