@@ -155,6 +155,10 @@ struct Params {
     const int32_t* pair_table;  // [npairs_dev] (same order as `pairs`), or NULL
     const struct PairTable* tables;
     const uint32_t* table_bits;
+    // broadphase candidates (full batches): bit k of row c = device pair k passed the world-AABB test (and no certificate covers
+    // the configuration's cell); written by cc_broad_kernel, one thread per configuration, read by the traversal's kCand flavour
+    uint32_t* cand;             // [cap][cand_words]
+    int32_t cand_words;
 };
 
 struct PairTable {
@@ -625,13 +629,74 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
     return (__ldg(&P.table_bits[bit >> 5]) >> (bit & 31)) & 1u;
 }
 
+// ================================================================================================ kernel 1b: broadphase
+// World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
+// one bit per pair, one row of cand_words words per configuration.  A warp owns 32 consecutive configurations; for each word
+// of 32 pairs every lane decodes ITS pair once (slots -> box addresses, row stride 0 for a static slot, table index) and the
+// warp then walks its 32 configurations: four box loads, the three-axis test, one ballot — lane i keeps configuration i's word.
+// In the traversal kernel the same test decodes the pair for every configuration again and compacts candidates step by step:
+// 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
+__global__ void __launch_bounds__(128)
+cc_broad_kernel(const __grid_constant__ Params P)
+{
+    const int lane = threadIdx.x & 31;
+    const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (c0 >= P.n) return;
+    const int nc = P.n - c0 < 32 ? P.n - c0 : 32;
+    const int ndyn = P.ndyn;
+    const size_t row = (size_t)ndyn * 2;                                       // float4 per configuration
+    const float4* __restrict__ ab0 = (const float4*)P.aabb + (size_t)c0 * row;
+    const float4* __restrict__ sab = (const float4*)P.st_aabb;
+    const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+    const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+    for (int w = kbeg >> 5; 32 * w < kend; ++w) {
+        const int k = 32 * w + lane;
+        const bool live = k < kend;
+        const float4* pa = ndyn > 0 ? ab0 : sab;                               // lanes past the list read something valid
+        const float4* pb = pa;
+        size_t step_a = 0, step_b = 0;
+        int tb = -1;
+        if (live) {
+            const uint32_t pr = __ldg(&P.pairs[k]);
+            const int sa = pr & 0xffff, sb = pr >> 16;
+            if (sa < ndyn) { pa = ab0 + 2 * sa; step_a = row; } else { pa = sab + 2 * (sa - ndyn); step_a = 0; }
+            if (sb < ndyn) { pb = ab0 + 2 * sb; step_b = row; } else { pb = sab + 2 * (sb - ndyn); step_b = 0; }
+            if (P.pair_table) tb = __ldg(&P.pair_table[k]);
+        }
+        uint32_t mine = 0u;
+        // branch-free box test on purpose (&, not &&): every lane loads whole boxes, no lazily evaluated scalar loads
+        if (__any_sync(kFull, tb >= 0)) {
+#pragma unroll 2
+            for (int i = 0; i < nc; ++i) {
+                const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
+                pa += step_a; pb += step_b;
+                bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
+                if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(c0 + i) * P.ncols)) ov = false;
+                const unsigned m = __ballot_sync(kFull, ov);
+                if (lane == i) mine = m;
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < nc; ++i) {
+                const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
+                pa += step_a; pb += step_b;
+                const bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
+                const unsigned m = __ballot_sync(kFull, ov);
+                if (lane == i) mine = m;
+            }
+        }
+        if (lane < nc) P.cand[(size_t)(c0 + lane) * P.cand_words + w] = mine;
+    }
+}
+
 // kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,
 // each over its own share of the pair list, outputs merged with atomics (small batches: the latency of a batch is the
 // traversal of its slowest configuration, so that one is spread over several warps).
 // kTables: the plan carries certified free-space tables (compiled out otherwise, so plans without tables run the plain code).
 // kContacts: all contacts of every pair are enumerated and recorded (PQP_ALL_CONTACTS, collisionPQP.h:578): no pair is
 // abandoned at its first contact; used with kFlagAllPairs for single configurations.
-template <bool kSplit, bool kTables, bool kContacts = false>
+// kCand: the broadphase has already run (cc_broad_kernel, certificates included): candidates come from P.cand, 32 pairs per lane.
+template <bool kSplit, bool kTables, bool kContacts = false, bool kCand = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocksPerSM)
 cc_traverse_kernel(const __grid_constant__ Params P)
 {
@@ -719,6 +784,33 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 }
                 // ------------------------------------------------------------ broadphase: 32 x kBroadPerLane pairs, world AABBs
                 const int lim = (k0 < nenv_dev && nenv_dev < kend) ? nenv_dev : kend;     // do not straddle env | self
+                if (kCand) {
+                    // one word of 32 precomputed pair bits per lane; as many whole words as the candidate buffer takes
+                    const int w0 = k0 >> 5, w = w0 + lane;
+                    uint32_t bits = 0u;
+                    if (32 * w < lim) {
+                        bits = P.cand[(size_t)c * P.cand_words + w];
+                        if (w == w0) bits &= 0xffffffffu << (k0 & 31);                   // pairs before k0 are done
+                        const int over = 32 * w + 32 - lim;                               // pairs from lim on: next class / none
+                        if (over > 0) bits &= 0xffffffffu >> over;
+                    }
+                    const int cntw = __popc(bits);
+                    int incl = cntw;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                    const bool take = ncb + incl <= kCandCap;                            // non-decreasing: a prefix of the lanes
+                    const int nw = __popc(__ballot_sync(kFull, take));                    // >= 1: ncb < 32 here, a word adds <= 32
+                    if (take) {
+                        int off = ncb + incl - cntw;
+                        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1u; cbuf[off++] = (uint32_t)(32 * w + b); }
+                    }
+                    ncb += __shfl_sync(kFull, incl, nw - 1);
+                    __syncwarp();
+                    k0 = 32 * (w0 + nw) < lim ? 32 * (w0 + nw) : lim;
+                    if (k0 == nenv_dev) recheck = true;
+                    if (ncb < 32 && k0 < kend) continue;
+                    if (ncb == 0) continue;
+                } else {
                 uint32_t pr[kBroadPerLane];
 #pragma unroll
                 for (int h = 0; h < kBroadPerLane; ++h) {
@@ -752,6 +844,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                 if (k0 == nenv_dev) recheck = true;
                 if (ncb < 32 && k0 < kend) continue;
                 if (ncb == 0) continue;
+                }
             }
             {
                 // ---------------------------------------------------------------- a batch of <= 32 root pairs

@@ -469,6 +469,7 @@ struct cc_query {
     std::vector<ccdev::FkStep> steps;       // every joint, depth-first order
     // per-chunk scratch (grown on demand, shared by the plans)
     DevBuf<float> d_xf32[2], d_aabb[2];      // two sets: consecutive chunks overlap on two streams
+    DevBuf<uint32_t> d_cand[2];              // broadphase candidate bits of a chunk (cc_broad_kernel -> traversal)
     DevBuf<double> d_fksave[2];
     DevBuf<int32_t> d_counters[2];
     DevBuf<uint32_t> d_hoisted_mask;
@@ -497,7 +498,7 @@ namespace {
 // Bytes of per-chunk scratch one configuration needs.
 size_t scratch_bytes_per_config(const Plan& pl)
 {
-    return (size_t)pl.ndyn * (48 + 32) + (size_t)pl.nsave * 56;
+    return (size_t)pl.ndyn * (48 + 32) + (size_t)pl.nsave * 56 + (pl.pairs.size() + 31) / 32 * 4;
 }
 
 int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
@@ -507,6 +508,7 @@ int ensure_scratch(cc_query* Q, const Plan& pl, int cap, int nsets)
         CC_CUDA(Q->d_aabb[k].reserve((size_t)cap * std::max(1, pl.ndyn) * 8));
         CC_CUDA(Q->d_fksave[k].reserve((size_t)cap * std::max(1, pl.nsave) * 7));
         CC_CUDA(Q->d_counters[k].reserve(2));
+        CC_CUDA(Q->d_cand[k].reserve((size_t)cap * std::max<size_t>(1, (pl.pairs.size() + 31) / 32)));
     }
     return CC_OK;
 }
@@ -565,9 +567,10 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     static const size_t extra_smem = getenv("CC_TUNE_EXTRA_SMEM") ? (size_t)atoi(getenv("CC_TUNE_EXTRA_SMEM")) : 0;
     const size_t tr_smem = ccdev::kWarpSmemBytes * ccdev::kWarpsPerBlock + extra_smem;
     if (S->trav_blocks_per_sm == 0) {
-        const void* variants[5] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
+        const void* variants[6] = {(const void*)ccdev::cc_traverse_kernel<false, false>, (const void*)ccdev::cc_traverse_kernel<true, false>,
                                    (const void*)ccdev::cc_traverse_kernel<false, true>, (const void*)ccdev::cc_traverse_kernel<true, true>,
-                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>};
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, true>,
+                                   (const void*)ccdev::cc_traverse_kernel<false, false, false, true>};
         int per_sm = 1 << 30;
         for (const void* kfn : variants) {
             CC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem));
@@ -633,6 +636,11 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     if (contacts) { P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
     if (use_tables) { P.pair_table = Q->d_pair_table.p; P.tables = Q->d_tables.p; P.table_bits = Q->d_table_bits.p; }
+    // full batches: the broadphase (and the certificate lookups) run one thread per configuration in cc_broad_kernel and hand the
+    // traversal one bit per pair; CC_TUNE_CAND=0 keeps the broadphase inside the traversal warp (A/B: profiles/r02k_ab_cand.log)
+    static const bool tune_cand = !(getenv("CC_TUNE_CAND") && atoi(getenv("CC_TUNE_CAND")) == 0);
+    const bool use_cand = tune_cand && split == 1 && !contacts && !fk_only && !pl.pairs.empty();
+    P.cand_words = (int)((pl.pairs.size() + 31) / 32);
     const Plan::Split* sp = split > 1 ? &pl.split[split == 2 ? 0 : (split == 4 ? 1 : 2)] : nullptr;
     if (sp && use_tables) P.pair_table = Q->d_pair_table_split[split == 2 ? 0 : (split == 4 ? 1 : 2)].p;
     if (sp) {
@@ -685,10 +693,16 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.work_out = (Q->trace_work && !fk_only) ? Q->d_work.p + off : nullptr;
         P.xf32 = Q->d_xf32[k].p; P.aabb = Q->d_aabb[k].p; P.fksave = Q->d_fksave[k].p;
         P.counters = Q->d_counters[k].p;
+        P.cand = Q->d_cand[k].p;
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
         if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
         if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
             ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
+            CC_CUDA(cudaGetLastError());
+            S->stats.launches++;
+        }
+        if (use_cand) {
+            ccdev::cc_broad_kernel<<<(m + 127) / 128, 128, 0, cs>>>(P);
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
         }
@@ -703,6 +717,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         if (grid > need) grid = need;
         P.spill = S->d_spill[k].p;
         if (contacts) ccdev::cc_traverse_kernel<false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
+        else if (use_cand) ccdev::cc_traverse_kernel<false, false, false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
         else if (use_tables) {
             if (split > 1) ccdev::cc_traverse_kernel<true, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
             else ccdev::cc_traverse_kernel<false, true><<<grid, ccdev::kWarpsPerBlock * 32, tr_smem, cs>>>(P);
