@@ -48,6 +48,9 @@ constexpr int kFkThreads = 128;
 #ifndef CC_PUSH_REVERSED
 #define CC_PUSH_REVERSED 1     // 1: the outputs of the lane that popped the top item go back on top (strict pair-order priority: +18 .. 37 %, profiles/r01I_ab_push_order.log)
 #endif
+#ifndef CC_OUT_SELECT
+#define CC_OUT_SELECT 0      // 1: the descent builds its outputs with selects instead of divergent branches (A/B)
+#endif
 #ifndef CC_TRIQ_CAP
 #define CC_TRIQ_CAP 96
 #endif
@@ -529,7 +532,10 @@ __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, c
     }
 }
 
-__global__ void __launch_bounds__(kFkThreads, 6)     // latency-bound kernel: keep 24 warps per SM resident (<= 85 registers; the affine base adds a few)
+#ifndef CC_FK_BLOCKS
+#define CC_FK_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kFkThreads, CC_FK_BLOCKS)     // latency-bound kernel: keep 24 warps per SM resident (<= 85 registers; the affine base adds a few)
 cc_fk_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -631,62 +637,59 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 
 // ================================================================================================ kernel 1b: broadphase
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
-// one bit per pair, one row of cand_words words per configuration.  A warp owns 32 consecutive configurations; for each word
-// of 32 pairs every lane decodes ITS pair once (slots -> box addresses, row stride 0 for a static slot, table index) and the
-// warp then walks its 32 configurations: four box loads, the three-axis test, one ballot — lane i keeps configuration i's word.
-// In the traversal kernel the same test decodes the pair for every configuration again and compacts candidates step by step:
-// 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
+// one bit per pair, one row of cand_words words per configuration.  A warp takes kBroadConfigs consecutive configurations, one
+// after the other; for each it walks the pair list 32 pairs at a time (lane = pair: four box loads, the three-axis test, one
+// ballot; lane j keeps word j and the row goes out as one coalesced store).  The configuration's boxes (1.3 KB on PR2) are
+// fetched from L2 once and then hit L1 for every word.  In the traversal kernel the same test also compacts candidates step by
+// step and holds a 72-register warp while it waits for the boxes: 1 450 of 7 430 warp instructions per PR2 configuration and
+// 28 % of its stall samples (profiles/r02i_trav_sass.txt).
+constexpr int kBroadConfigs = 8;
+
+template <bool kWithTables>
+__device__ __forceinline__ void broad_rows(const Params& P, int c_begin, int c_end, int lane)
+{
+    const int ndyn = P.ndyn;
+    const float4* __restrict__ sab = (const float4*)P.st_aabb;
+    const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+    const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+    const int w_beg = kbeg >> 5, w_end = (kend + 31) >> 5;
+    for (int c = c_begin; c < c_end; ++c) {
+        const float4* __restrict__ ab = (const float4*)P.aabb + (size_t)c * ndyn * 2;
+        uint32_t mine = 0u;
+#pragma unroll 2
+        for (int w = w_beg; w < w_end; ++w) {
+            const int k = 32 * w + lane;
+            const int kk = k < kend ? k : kend - 1;                          // lanes past the list repeat the last pair (branch-free)
+            const uint32_t pr = __ldg(&P.pairs[kk]);
+            const int sa = pr & 0xffff, sb = pr >> 16;
+            const float4* pa = sa < ndyn ? ab + 2 * sa : sab + 2 * (sa - ndyn);
+            const float4* pb = sb < ndyn ? ab + 2 * sb : sab + 2 * (sb - ndyn);
+            const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
+            // & on purpose (not &&): every lane loads whole boxes, no lazily evaluated scalar loads
+            bool ov = (k < kend) & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
+            if (kWithTables) {
+                if (ov) {
+                    const int tb = __ldg(&P.pair_table[kk]);
+                    if (tb >= 0 && table_cell_free(P, tb, P.q + (size_t)c * P.ncols)) ov = false;
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, ov);
+            const int j = (w - w_beg) & 31;
+            if (lane == j) mine = m;
+            if (j == 31 || w == w_end - 1) { if (lane <= j) P.cand[(size_t)c * P.cand_words + (w - j) + lane] = mine; }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 cc_broad_kernel(const __grid_constant__ Params P)
 {
     const int lane = threadIdx.x & 31;
-    const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kBroadConfigs;
     if (c0 >= P.n) return;
-    const int nc = P.n - c0 < 32 ? P.n - c0 : 32;
-    const int ndyn = P.ndyn;
-    const size_t row = (size_t)ndyn * 2;                                       // float4 per configuration
-    const float4* __restrict__ ab0 = (const float4*)P.aabb + (size_t)c0 * row;
-    const float4* __restrict__ sab = (const float4*)P.st_aabb;
-    const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
-    const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
-    for (int w = kbeg >> 5; 32 * w < kend; ++w) {
-        const int k = 32 * w + lane;
-        const bool live = k < kend;
-        const float4* pa = ndyn > 0 ? ab0 : sab;                               // lanes past the list read something valid
-        const float4* pb = pa;
-        size_t step_a = 0, step_b = 0;
-        int tb = -1;
-        if (live) {
-            const uint32_t pr = __ldg(&P.pairs[k]);
-            const int sa = pr & 0xffff, sb = pr >> 16;
-            if (sa < ndyn) { pa = ab0 + 2 * sa; step_a = row; } else { pa = sab + 2 * (sa - ndyn); step_a = 0; }
-            if (sb < ndyn) { pb = ab0 + 2 * sb; step_b = row; } else { pb = sab + 2 * (sb - ndyn); step_b = 0; }
-            if (P.pair_table) tb = __ldg(&P.pair_table[k]);
-        }
-        uint32_t mine = 0u;
-        // branch-free box test on purpose (&, not &&): every lane loads whole boxes, no lazily evaluated scalar loads
-        if (__any_sync(kFull, tb >= 0)) {
-#pragma unroll 2
-            for (int i = 0; i < nc; ++i) {
-                const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
-                pa += step_a; pb += step_b;
-                bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
-                if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(c0 + i) * P.ncols)) ov = false;
-                const unsigned m = __ballot_sync(kFull, ov);
-                if (lane == i) mine = m;
-            }
-        } else {
-#pragma unroll 4
-            for (int i = 0; i < nc; ++i) {
-                const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
-                pa += step_a; pb += step_b;
-                const bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
-                const unsigned m = __ballot_sync(kFull, ov);
-                if (lane == i) mine = m;
-            }
-        }
-        if (lane < nc) P.cand[(size_t)(c0 + lane) * P.cand_words + w] = mine;
-    }
+    const int c1 = c0 + kBroadConfigs < P.n ? c0 + kBroadConfigs : P.n;
+    if (P.pair_table) broad_rows<true>(P, c0, c1, lane);
+    else broad_rows<false>(P, c0, c1, lane);
 }
 
 // kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,
@@ -1016,7 +1019,7 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                     if (valid) it = stack[sp - 1 - lane];
                     sp -= n;
                     __syncwarp();
-                    bool tq0 = false, tq1 = false, ps0 = false, ps1 = false;
+                    uint32_t of = 0u;      // bit 0 / 1: child 0 / 1 goes to the triangle queue, bit 2 / 3: child 0 / 1 is pushed back as an item
                     uint2 o0 = make_uint2(0u, 0u), o1 = make_uint2(0u, 0u);     // outputs for child 0 / child 1 (tri entry or item)
                     if (valid) {
                         const uint32_t sbits = it.x & 0xfc000000u;
@@ -1035,6 +1038,28 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         bool ov0, ov1;
                         box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
                                          oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
+#if CC_OUT_SELECT
+                        // branch-free form of the loop below (selects instead of divergent paths)
+                        {
+                            const uint32_t flip = side ? 0u : 0x80000000u;
+                            const bool ol = lo < 0;
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) {
+                                const bool ov = ch ? ov1 : ov0;
+                                const int lc = __float_as_int(ch ? c1a.w : c0a.w);
+                                const float sc = ch ? c1b.w : c0b.w;
+                                const bool cl = lc < 0;
+                                const bool tq = ov & cl & ol;
+                                const bool splitc = ol | (!cl & (sc > ob.w));
+                                const uint32_t ta = side ? (uint32_t)(~lo) : (uint32_t)(~lc), tb = side ? (uint32_t)(~lc) : (uint32_t)(~lo);
+                                const uint32_t px = splitc ? (uint32_t)lc : (uint32_t)lo;
+                                const uint32_t py = splitc ? it.y : ((x + ch) | flip);
+                                const uint2 out = make_uint2((tq ? ta : px) | sbits, tq ? tb : py);
+                                if (ch) o1 = out; else o0 = out;
+                                of |= (tq ? 1u : (ov ? 4u : 0u)) << ch;
+                            }
+                        }
+#else
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
                             if (ch ? ov1 : ov0) {
@@ -1050,10 +1075,13 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                                 } else {
                                     out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));     // split the other
                                 }
-                                if (ch) { o1 = out; tq1 = tq; ps1 = !tq; } else { o0 = out; tq0 = tq; ps0 = !tq; }
+                                if (ch) o1 = out; else o0 = out;
+                                of |= (tq ? 1u : 4u) << ch;
                             }
                         }
+#endif
                     }
+                    const bool tq0 = (of & 1u) != 0u, tq1 = (of & 2u) != 0u, ps0 = (of & 4u) != 0u, ps1 = (of & 8u) != 0u;
                     const unsigned t0m = __ballot_sync(kFull, tq0), t1m = __ballot_sync(kFull, tq1);
                     const unsigned p0m = __ballot_sync(kFull, ps0), p1m = __ballot_sync(kFull, ps1);
 #if CC_PUSH_REVERSED

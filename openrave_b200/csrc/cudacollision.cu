@@ -702,7 +702,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
             S->stats.launches++;
         }
         if (use_cand) {
-            ccdev::cc_broad_kernel<<<(m + 127) / 128, 128, 0, cs>>>(P);
+            const int bwarps = (m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs;
+            ccdev::cc_broad_kernel<<<(bwarps + 3) / 4, 128, 0, cs>>>(P);
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
         }

@@ -182,6 +182,7 @@ def test_scene_analytic_is_a_superset_within_the_sagitta(scene):
             import oracle
             env_o = load_scene(scene)
             orc = oracle.OracleChecker(env_o, ORACLE_KIND)
+            orc._sync()          # registers the bodies (fills orc._ids)
             bq = tess["query"]
             for c in later[:20]:
                 l1, ob, l2, _ = bq.pairs[int(t[c])]
