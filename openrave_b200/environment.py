@@ -97,7 +97,7 @@ class Environment(object):
                 prims = json.load(open(side))
                 for b in self.bodies:
                     for l in b.links:
-                        l.prims = prims.get(b.name, {}).get(l.name, [])
+                        l.prims = prims.get(b.name, {}).get("%d:%s" % (l.index, l.name), [])
             return True
         from .xmlscene import SceneLoader
         SceneLoader(self.data_dirs).load_environment(self, filename)

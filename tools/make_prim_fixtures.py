@@ -33,7 +33,7 @@ def main():
                 gs = l.geometries
                 if not gs or any(g.type not in ("box", "cylinder", "sphere") for g in gs):
                     continue
-                out.setdefault(b.name, {})[l.name] = [dict(type=g.type, t=[list(g.t[0]), list(g.t[1])], data=[float(x) for x in g.data]) for g in gs]
+                out.setdefault(b.name, {})["%d:%s" % (l.index, l.name)] = [dict(type=g.type, t=[list(g.t[0]), list(g.t[1])], data=[float(x) for x in g.data]) for g in gs]
                 n += len(gs)
         path = os.path.join(OUT, scene + ".prims.json")
         json.dump(out, open(path, "w"), indent=1, sort_keys=True)
