@@ -533,9 +533,9 @@ __device__ __forceinline__ void fk_chain(const Params& P, const FkStep* steps, c
 }
 
 #ifndef CC_FK_BLOCKS
-#define CC_FK_BLOCKS 6
+#define CC_FK_BLOCKS 4      // 104 registers, no spilled loop counter: 4 > 5 > 6 blocks by 0.5 - 2 % (profiles/r02l_ab.log)
 #endif
-__global__ void __launch_bounds__(kFkThreads, CC_FK_BLOCKS)     // latency-bound kernel: keep 24 warps per SM resident (<= 85 registers; the affine base adds a few)
+__global__ void __launch_bounds__(kFkThreads, CC_FK_BLOCKS)
 cc_fk_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -637,47 +637,55 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 
 // ================================================================================================ kernel 1b: broadphase
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
-// one bit per pair, one row of cand_words words per configuration.  A warp takes kBroadConfigs consecutive configurations, one
-// after the other; for each it walks the pair list 32 pairs at a time (lane = pair: four box loads, the three-axis test, one
-// ballot; lane j keeps word j and the row goes out as one coalesced store).  The configuration's boxes (1.3 KB on PR2) are
-// fetched from L2 once and then hit L1 for every word.  In the traversal kernel the same test also compacts candidates step by
-// step and holds a 72-register warp while it waits for the boxes: 1 450 of 7 430 warp instructions per PR2 configuration and
-// 28 % of its stall samples (profiles/r02i_trav_sass.txt).
-constexpr int kBroadConfigs = 8;
+// one bit per pair, one row of cand_words words per configuration.  A warp owns ONE word of 32 pairs (lane = pair) and sweeps
+// kBroadConfigs consecutive configurations with it: the pair is decoded once, the box of a static slot is loaded once and stays
+// in registers, and per configuration only the boxes of dynamic slots are fetched — pairs are in the reference's order, link by
+// link, so the lanes of a word mostly ask for the same box and the load is a broadcast (2 - 4 L1 wavefronts per word and
+// configuration; gathering all four boxes per lane costs 16 - 32 and made the kernel L1-bound: profiles/r02l_ab.log).  Lane i keeps
+// configuration i's ballot; a group of 32 configurations goes out with one store.  In the traversal kernel the same test decodes
+// the pair for every configuration, compacts candidates step by step and holds a 72-register warp while it waits for the boxes:
+// 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
+constexpr int kBroadConfigs = 256;
 
-template <bool kWithTables>
-__device__ __forceinline__ void broad_rows(const Params& P, int c_begin, int c_end, int lane)
+// kEnvWord: every live lane's pair is (dynamic slot, static slot) — a moving link of the query body against the environment,
+// the bulk of every plan: only slot a's box is loaded per configuration, no per-lane predication
+template <bool kWithTables, bool kEnvWord>
+__device__ __forceinline__ void broad_word(const Params& P, int w, int c_begin, int c_end, int lane, int kend)
 {
     const int ndyn = P.ndyn;
+    const size_t row = (size_t)ndyn * 2;                                       // float4 per configuration
     const float4* __restrict__ sab = (const float4*)P.st_aabb;
-    const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
-    const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
-    const int w_beg = kbeg >> 5, w_end = (kend + 31) >> 5;
-    for (int c = c_begin; c < c_end; ++c) {
-        const float4* __restrict__ ab = (const float4*)P.aabb + (size_t)c * ndyn * 2;
+    const int k = 32 * w + lane;
+    const bool live = k < kend;
+    const int kk = live ? k : kend - 1;
+    const uint32_t pr = __ldg(&P.pairs[kk]);
+    const int sa = pr & 0xffff, sb = pr >> 16;
+    const bool a_dyn = sa < ndyn, b_dyn = sb < ndyn;
+    const float4* pa = (const float4*)P.aabb + (size_t)c_begin * row + 2 * (a_dyn ? sa : 0);
+    const float4* pb = (const float4*)P.aabb + (size_t)c_begin * row + 2 * (b_dyn ? sb : 0);
+    float4 ac = make_float4(0.f, 0.f, 0.f, 0.f), ae = ac, bc = ac, be = ac;
+    if (!a_dyn) { ac = __ldg(sab + 2 * (sa - ndyn)); ae = __ldg(sab + 2 * (sa - ndyn) + 1); }
+    if (!b_dyn) { bc = __ldg(sab + 2 * (sb - ndyn)); be = __ldg(sab + 2 * (sb - ndyn) + 1); }
+    int tb = -1;
+    if (kWithTables) { if (live) tb = __ldg(&P.pair_table[kk]); }
+    for (int g = c_begin; g < c_end; g += 32) {
+        const int nc = c_end - g < 32 ? c_end - g : 32;
         uint32_t mine = 0u;
-#pragma unroll 2
-        for (int w = w_beg; w < w_end; ++w) {
-            const int k = 32 * w + lane;
-            const int kk = k < kend ? k : kend - 1;                          // lanes past the list repeat the last pair (branch-free)
-            const uint32_t pr = __ldg(&P.pairs[kk]);
-            const int sa = pr & 0xffff, sb = pr >> 16;
-            const float4* pa = sa < ndyn ? ab + 2 * sa : sab + 2 * (sa - ndyn);
-            const float4* pb = sb < ndyn ? ab + 2 * sb : sab + 2 * (sb - ndyn);
-            const float4 ac = __ldg(pa), ae = __ldg(pa + 1), bc = __ldg(pb), be = __ldg(pb + 1);
-            // & on purpose (not &&): every lane loads whole boxes, no lazily evaluated scalar loads
-            bool ov = (k < kend) & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
-            if (kWithTables) {
-                if (ov) {
-                    const int tb = __ldg(&P.pair_table[kk]);
-                    if (tb >= 0 && table_cell_free(P, tb, P.q + (size_t)c * P.ncols)) ov = false;
-                }
+#pragma unroll 4
+        for (int i = 0; i < nc; ++i) {
+            if (kEnvWord) { ac = __ldg(pa); ae = __ldg(pa + 1); pa += row; }
+            else {
+                if (a_dyn) { ac = __ldg(pa); ae = __ldg(pa + 1); }
+                if (b_dyn) { bc = __ldg(pb); be = __ldg(pb + 1); }
+                pa += row; pb += row;
             }
+            // & on purpose (not &&): no lazily evaluated scalar loads, no divergent branches
+            bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
+            if (kWithTables) { if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(g + i) * P.ncols)) ov = false; }
             const unsigned m = __ballot_sync(kFull, ov);
-            const int j = (w - w_beg) & 31;
-            if (lane == j) mine = m;
-            if (j == 31 || w == w_end - 1) { if (lane <= j) P.cand[(size_t)c * P.cand_words + (w - j) + lane] = mine; }
+            if (lane == i) mine = m;
         }
+        if (lane < nc) P.cand[(size_t)(g + lane) * P.cand_words + w] = mine;
     }
 }
 
@@ -685,11 +693,25 @@ __global__ void __launch_bounds__(128)
 cc_broad_kernel(const __grid_constant__ Params P)
 {
     const int lane = threadIdx.x & 31;
-    const int c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kBroadConfigs;
+    const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
+    const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+    const int w_beg = kbeg >> 5, nwords = ((kend + 31) >> 5) - w_beg;
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // (configuration block, word): the warps of a thread
+    const int cb = item / nwords;                                            // block share their configurations' boxes in L1
+    const int w = w_beg + (item - cb * nwords);
+    const int c0 = cb * kBroadConfigs;
     if (c0 >= P.n) return;
     const int c1 = c0 + kBroadConfigs < P.n ? c0 + kBroadConfigs : P.n;
-    if (P.pair_table) broad_rows<true>(P, c0, c1, lane);
-    else broad_rows<false>(P, c0, c1, lane);
+    const int k = 32 * w + lane;
+    bool tables = false, env_word = true;
+    if (P.pair_table) tables = __any_sync(kFull, k < kend && __ldg(&P.pair_table[k]) >= 0);
+    {
+        const uint32_t pr = __ldg(&P.pairs[k < kend ? k : kend - 1]);
+        env_word = __all_sync(kFull, (int)(pr & 0xffff) < P.ndyn && (int)(pr >> 16) >= P.ndyn);
+    }
+    if (tables) broad_word<true, false>(P, w, c0, c1, lane, kend);
+    else if (env_word) broad_word<false, true>(P, w, c0, c1, lane, kend);
+    else broad_word<false, false>(P, w, c0, c1, lane, kend);
 }
 
 // kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,

@@ -36,6 +36,8 @@ struct DistOut {
     int32_t* min_pair;          // [n] reference-order pair index attaining it, -1 when none
     double* points;             // [n][6] closest points in world coordinates (on the query link, on the other link), or NULL
     float dist_max;             // search radius, <= 0: unbounded
+    float bound;                // > 0: a pair OUTSIDE this launch is known to be this close (the pose-invariant pairs of the query,
+                                // measured once): the search starts from it instead of from the radius; <= 0: none
     // PQP_Distance's tolerances (pqp/PQP.cpp:717-721, 776): a box pair is skipped when its bound d satisfies
     // d + abs_err >= best or d * (1 + rel_err) >= best, so the result r obeys exact <= r <= max(exact + abs_err, exact * (1 + rel_err))
     float rel_err, abs_err;
@@ -172,9 +174,15 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
     uint32_t* cbuf = (uint32_t*)(triq + kDistTriQCap);            // [32] candidate device pair indices
     const unsigned lt_mask = (1u << lane) - 1u;
     const int ndyn = P.ndyn;
-    const float best_init = D.dist_max > 0.f ? D.dist_max * D.dist_max : 3.0e38f;
     const bool approx = D.rel_err > 0.f || D.abs_err > 0.f;
     const float inv_rel = 1.f / (1.f + fmaxf(D.rel_err, 0.f));
+    float best_init = D.dist_max > 0.f ? D.dist_max * D.dist_max : 3.0e38f;
+    float thr_init = best_init;
+    if (D.bound > 0.f && D.bound * D.bound < best_init) {
+        best_init = D.bound * D.bound;
+        thr_init = best_init;
+        if (approx) { const float th = fmaxf(0.f, fminf(D.bound - D.abs_err, D.bound * inv_rel)); thr_init = th * th; }     // as if found here
+    }
 
     for (;;) {
         int c = 0;
@@ -194,7 +202,7 @@ cc_distance_kernel(const __grid_constant__ Params P, const __grid_constant__ Dis
         constexpr int xs = 12, as = 8;
 
         float best2 = best_init;             // warp-uniform
-        float thr2 = best_init;              // squared pruning threshold: best2 itself, or tightened by the tolerances
+        float thr2 = thr_init;               // squared pruning threshold: best2 itself, or tightened by the tolerances
         int best_pair = -1, best_la = 0;
         V3 best_p = v3(0.f, 0.f, 0.f), best_q = best_p;     // closest points in link a's frame (warp-uniform copies)
 

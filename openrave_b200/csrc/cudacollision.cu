@@ -459,7 +459,14 @@ struct cc_query {
     std::vector<int> p_main_all;             // the same before any certificate removed pairs
     std::vector<int> p_hoist;                // pose-invariant pairs
     std::vector<uint8_t> moves;              // [nq] link is moved by some active DOF
-    Plan dist;                               // distance queries in FK mode: every live pair, nothing hoisted (built on first use)
+    Plan dist;                               // tolerance queries in FK mode: every live pair, nothing hoisted (built on first use)
+    // minimum-distance queries in FK mode: the pairs between links no active DOF moves are measured ONCE (dist_static, at the
+    // current pose) and every configuration's search starts from that bound; dist_main holds the rest
+    Plan dist_main, dist_static;
+    std::vector<int> p_dist_main, p_dist_static;
+    std::vector<uint8_t> dist_dynamic;
+    bool dist_main_ready = false;
+    struct StaticMin { bool valid = false; double d = 0; int pair = -1; double pts[6] = {0, 0, 0, 0, 0, 0}; } dist_static_min[4];
     bool dist_ready = false;
     std::vector<int> p_full;                 // indices of the live pairs
     std::vector<int> p_analytic;             // pairs with an analytic link (scene in analytic mode): out of every traversal plan
@@ -702,8 +709,9 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
             S->stats.launches++;
         }
         if (use_cand) {
-            const int bwarps = (m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs;
-            ccdev::cc_broad_kernel<<<(bwarps + 3) / 4, 128, 0, cs>>>(P);
+            const int kb = (P.flags & ccdev::kFlagEnv) ? 0 : P.nenv_dev, ke = (P.flags & ccdev::kFlagSelf) ? P.npairs_dev : P.nenv_dev;
+            const long long bwarps = (long long)((m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs) * std::max(0, ((ke + 31) >> 5) - (kb >> 5));
+            if (bwarps > 0) ccdev::cc_broad_kernel<<<(unsigned)((bwarps + 3) / 4), 128, 0, cs>>>(P);
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
         }
@@ -760,7 +768,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
 // Minimum separation of n configurations (host buffers in and out, one stream, synchronous): FK kernel, then the
 // branch-and-bound distance kernel of cc_distance.cuh, chunk by chunk.
 int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h_in, int n, int flags, double max_distance,
-                    double rel_err, double abs_err, double* h_dist, int32_t* h_pair, double* h_pts, bool per_pair = false)
+                    double rel_err, double abs_err, double* h_dist, int32_t* h_pair, double* h_pts, bool per_pair = false, double bound = -1.0)
 {
     cc_scene* S = Q->scene;
     if (n <= 0) return CC_OK;
@@ -793,6 +801,7 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     ccdev::DistOut D;
     D.min_distance = Q->d_dist.p; D.min_pair = Q->d_dpair.p; D.points = h_pts ? Q->d_dpts.p : nullptr;
     D.dist_max = max_distance > 0 ? (float)max_distance : 0.f;
+    D.bound = bound > 0 ? nextafterf((float)bound, 3.0e38f) : 0.f;      // never below the double it came from
     D.rel_err = rel_err > 0 ? (float)rel_err : 0.f;
     D.abs_err = abs_err > 0 ? (float)abs_err : 0.f;
     D.per_pair = per_pair ? 1 : 0;
@@ -1606,6 +1615,21 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         }
         (hoist ? p_hoist : p_main).push_back(p);
     }
+    // minimum-distance queries: pairs between links that no active DOF moves keep their distance for the whole batch
+    Q->p_dist_main.clear(); Q->p_dist_static.clear(); Q->dist_dynamic.assign(nl, 1);
+    Q->dist_main_ready = false;
+    for (auto& sm : Q->dist_static_min) sm.valid = false;
+    {
+        const bool split_static = allow_hoist && Q->has_fk && !Q->naffine;
+        if (split_static) Q->dist_dynamic.assign(nl, 0);
+        for (int p : p_full) {
+            const int a = Q->quads[4 * p], cls = Q->quads[4 * p + 3];
+            const int b = cls == 1 ? Q->quads[4 * p + 2] : -1;
+            if (split_static && !moves[a] && (b < 0 || !moves[b])) { Q->p_dist_static.push_back(p); continue; }
+            Q->p_dist_main.push_back(p);
+            if (split_static) { if (moves[a]) Q->dist_dynamic[a] = 1; if (b >= 0 && moves[b]) Q->dist_dynamic[b] = 1; }
+        }
+    }
     std::vector<uint8_t> all_dynamic(nl, 1), main_dynamic(nl, 0);
     for (int p : p_main) {
         const int a = Q->quads[4 * p];
@@ -1959,7 +1983,9 @@ int cc_query_refresh(cc_query* q)
         const int rc = invalidate_certificates(q, &invalid);
         if (rc != CC_OK) return rc;
     }
-    Plan* plans[4] = {&q->full, &q->mainl, &q->hoisted, q->dist_ready ? &q->dist : nullptr};
+    Plan* plans[6] = {&q->full, &q->mainl, &q->hoisted, q->dist_ready ? &q->dist : nullptr, q->dist_main_ready ? &q->dist_main : nullptr,
+                      q->dist_main_ready ? &q->dist_static : nullptr};
+    for (auto& sm : q->dist_static_min) sm.valid = false;      // measured on the old poses
     for (Plan* pl : plans) {
         if (!pl || pl->nstatic == 0) continue;
         std::vector<float> stxf((size_t)pl->nstatic * 12, 0.f), staabb((size_t)pl->nstatic * 8, 0.f);
@@ -2151,17 +2177,46 @@ int cc_distance_batch(cc_query* q, const double* dof_values, int n, int flags, d
     if (!q->has_fk) return fail(CC_ERR_STATE, "body has no usable kinematics: use cc_distance_poses");
     if (!q->scene->committed) return fail(CC_ERR_STATE, "scene changed since the query was bound");
     return run_sharded(q, n, [&](cc_query* r, int off, int m) -> int {
-        if (!r->dist_ready) {
+        if (!r->dist_main_ready) {
             CC_CUDA(cudaSetDevice(r->scene->device));
             std::vector<uint8_t> all_dynamic(r->nq, 1);
-            int rc = build_plan(r, r->dist, r->p_full, all_dynamic, true);
+            int rc = build_plan(r, r->dist_main, r->p_dist_main, r->dist_dynamic, true);
+            if (rc == CC_OK) rc = build_plan(r, r->dist_static, r->p_dist_static, all_dynamic, true);
             if (rc != CC_OK) return rc;
             CC_CUDA(cudaDeviceSynchronize());
-            r->dist_ready = true;
+            r->dist_main_ready = true;
         }
-        return launch_distance(r, r->dist, false, dof_values ? dof_values + (size_t)off * r->ncols : nullptr, m, flags, max_distance, rel_err,
-                               abs_err, min_distance + off, min_pair ? min_pair + off : nullptr,
-                               closest_points ? closest_points + (size_t)off * 6 : nullptr);
+        // the pairs no active DOF can change: measured once per pose snapshot and class selection (exact, unbounded)
+        cc_query::StaticMin& sm = r->dist_static_min[flags & 3];
+        static const bool tune_no_static = getenv("CC_TUNE_DIST_STATIC") && atoi(getenv("CC_TUNE_DIST_STATIC")) == 0;      // A/B knob
+        if (!sm.valid) {
+            sm.d = 1e30; sm.pair = -1;
+            if (!r->dist_static.pairs.empty()) {
+                const int rc = launch_distance(r, r->dist_static, false, r->cur_active.data(), 1, flags, 0.0, 0.0, 0.0, &sm.d, &sm.pair, sm.pts);
+                if (rc != CC_OK) return rc;
+            }
+            sm.valid = true;
+        }
+        const bool have = sm.pair >= 0 && (max_distance <= 0 || sm.d < max_distance);
+        double* dist = min_distance + off;
+        int32_t* pair = min_pair ? min_pair + off : nullptr;
+        double* pts = closest_points ? closest_points + (size_t)off * 6 : nullptr;
+        std::vector<int32_t> pair_tmp;
+        if (have && !pair) { pair_tmp.resize(m); pair = pair_tmp.data(); }       // needed to tell "nothing closer" apart
+        if (r->dist_main.pairs.empty() || (have && sm.d <= 0.0)) {
+            for (int i = 0; i < m; ++i) { dist[i] = max_distance > 0 ? max_distance : 1e30; if (pair) pair[i] = -1; if (pts) for (int k = 0; k < 6; ++k) pts[6 * (size_t)i + k] = 0.0; }
+        } else {
+            const int rc = launch_distance(r, r->dist_main, false, dof_values ? dof_values + (size_t)off * r->ncols : nullptr, m, flags, max_distance,
+                                           rel_err, abs_err, dist, pair, pts, false, (have && !tune_no_static) ? sm.d : -1.0);
+            if (rc != CC_OK) return rc;
+        }
+        if (have)
+            for (int i = 0; i < m; ++i)
+                if (pair[i] < 0 || sm.d < dist[i]) {
+                    dist[i] = sm.d; pair[i] = sm.pair;
+                    if (pts) memcpy(pts + 6 * (size_t)i, sm.pts, sizeof(sm.pts));
+                }
+        return CC_OK;
     });
 }
 
