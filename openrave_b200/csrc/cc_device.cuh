@@ -48,6 +48,9 @@ constexpr int kFkThreads = 128;
 #ifndef CC_PUSH_REVERSED
 #define CC_PUSH_REVERSED 1     // 1: the outputs of the lane that popped the top item go back on top (strict pair-order priority: +18 .. 37 %, profiles/r01I_ab_push_order.log)
 #endif
+#ifndef CC_LD256
+#define CC_LD256 1           // 256-bit loads (LDG.E.256, sm_100) for the 32-byte BVH nodes and boxes (0: pairs of 128-bit loads, A/B)
+#endif
 #ifndef CC_OUT_SELECT
 #define CC_OUT_SELECT 0      // 1: the descent builds its outputs with selects instead of divergent branches (A/B)
 #endif
@@ -637,81 +640,94 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 
 // ================================================================================================ kernel 1b: broadphase
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
-// one bit per pair, one row of cand_words words per configuration.  A warp owns ONE word of 32 pairs (lane = pair) and sweeps
-// kBroadConfigs consecutive configurations with it: the pair is decoded once, the box of a static slot is loaded once and stays
-// in registers, and per configuration only the boxes of dynamic slots are fetched — pairs are in the reference's order, link by
-// link, so the lanes of a word mostly ask for the same box and the load is a broadcast (2 - 4 L1 wavefronts per word and
-// configuration; gathering all four boxes per lane costs 16 - 32 and made the kernel L1-bound: profiles/r02l_ab.log).  Lane i keeps
-// configuration i's ballot; a group of 32 configurations goes out with one store.  In the traversal kernel the same test decodes
-// the pair for every configuration, compacts candidates step by step and holds a 72-register warp while it waits for the boxes:
-// 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
-constexpr int kBroadConfigs = 256;
+// one bit per pair, one row of cand_words words per configuration.  A thread block takes kBroadConfigs consecutive configurations;
+// each of its warps owns one word of 32 pairs (lane = pair) and sweeps those configurations with it: the pair is decoded once, the
+// box of a static slot is loaded once and stays in registers, and per configuration only the boxes of dynamic slots are fetched,
+// one 256-bit load each.  Pairs are in the reference's order, link by link, so the lanes of a word mostly ask for the same box of
+// slot a (a broadcast), and the warps of the block walk the same rows at the same time, so a row comes from L2 once (per-lane
+// gathers of all four boxes cost 16 - 32 L1 wavefronts per word and configuration and made an earlier form L1-bound:
+// profiles/r02l_ab.log, r02m_ab_cand.log).  Lane i keeps configuration i's ballot; a group of 32 configurations goes out with
+// one store.  In the traversal kernel the same test decodes the pair for every configuration, compacts candidates step by step
+// and holds a 72-register warp while it waits for the boxes: 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of
+// its stall samples (profiles/r02i_trav_sass.txt).
+constexpr int kBroadConfigs = 64;
+constexpr int kBroadMaxWarps = 16;
 
-// kEnvWord: every live lane's pair is (dynamic slot, static slot) — a moving link of the query body against the environment,
-// the bulk of every plan: only slot a's box is loaded per configuration, no per-lane predication
-template <bool kWithTables, bool kEnvWord>
-__device__ __forceinline__ void broad_word(const Params& P, int w, int c_begin, int c_end, int lane, int kend)
+struct Box8 { float4 c, e; };
+// one 32-byte box {cx cy cz . | ex ey ez .} with a single 256-bit load (LDG.E.256, sm_100); p is 32-byte aligned
+__device__ __forceinline__ Box8 ld_box(const float4* p)
 {
+    Box8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.c.x), "=f"(r.c.y), "=f"(r.c.z), "=f"(r.c.w), "=f"(r.e.x), "=f"(r.e.y), "=f"(r.e.z), "=f"(r.e.w) : "l"(p));
+    return r;
+}
+
+// grid: one block per kBroadConfigs configurations; block: `blockDim.x / 32` warps, warp i takes the words i, i + warps, ...
+__global__ void __launch_bounds__(kBroadMaxWarps * 32)
+cc_broad_kernel(const __grid_constant__ Params P)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ndyn = P.ndyn;
     const size_t row = (size_t)ndyn * 2;                                       // float4 per configuration
     const float4* __restrict__ sab = (const float4*)P.st_aabb;
-    const int k = 32 * w + lane;
-    const bool live = k < kend;
-    const int kk = live ? k : kend - 1;
-    const uint32_t pr = __ldg(&P.pairs[kk]);
-    const int sa = pr & 0xffff, sb = pr >> 16;
-    const bool a_dyn = sa < ndyn, b_dyn = sb < ndyn;
-    const float4* pa = (const float4*)P.aabb + (size_t)c_begin * row + 2 * (a_dyn ? sa : 0);
-    const float4* pb = (const float4*)P.aabb + (size_t)c_begin * row + 2 * (b_dyn ? sb : 0);
-    float4 ac = make_float4(0.f, 0.f, 0.f, 0.f), ae = ac, bc = ac, be = ac;
-    if (!a_dyn) { ac = __ldg(sab + 2 * (sa - ndyn)); ae = __ldg(sab + 2 * (sa - ndyn) + 1); }
-    if (!b_dyn) { bc = __ldg(sab + 2 * (sb - ndyn)); be = __ldg(sab + 2 * (sb - ndyn) + 1); }
-    int tb = -1;
-    if (kWithTables) { if (live) tb = __ldg(&P.pair_table[kk]); }
-    for (int g = c_begin; g < c_end; g += 32) {
-        const int nc = c_end - g < 32 ? c_end - g : 32;
-        uint32_t mine = 0u;
-#pragma unroll 4
-        for (int i = 0; i < nc; ++i) {
-            if (kEnvWord) { ac = __ldg(pa); ae = __ldg(pa + 1); pa += row; }
-            else {
-                if (a_dyn) { ac = __ldg(pa); ae = __ldg(pa + 1); }
-                if (b_dyn) { bc = __ldg(pb); be = __ldg(pb + 1); }
-                pa += row; pb += row;
-            }
-            // & on purpose (not &&): no lazily evaluated scalar loads, no divergent branches
-            bool ov = live & (fabsf(ac.x - bc.x) <= ae.x + be.x) & (fabsf(ac.y - bc.y) <= ae.y + be.y) & (fabsf(ac.z - bc.z) <= ae.z + be.z);
-            if (kWithTables) { if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(g + i) * P.ncols)) ov = false; }
-            const unsigned m = __ballot_sync(kFull, ov);
-            if (lane == i) mine = m;
-        }
-        if (lane < nc) P.cand[(size_t)(g + lane) * P.cand_words + w] = mine;
-    }
-}
-
-__global__ void __launch_bounds__(128)
-cc_broad_kernel(const __grid_constant__ Params P)
-{
-    const int lane = threadIdx.x & 31;
     const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
     const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
-    const int w_beg = kbeg >> 5, nwords = ((kend + 31) >> 5) - w_beg;
-    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // (configuration block, word): the warps of a thread
-    const int cb = item / nwords;                                            // block share their configurations' boxes in L1
-    const int w = w_beg + (item - cb * nwords);
-    const int c0 = cb * kBroadConfigs;
-    if (c0 >= P.n) return;
+    const int w_beg = kbeg >> 5, w_end = (kend + 31) >> 5;
+    const int c0 = blockIdx.x * kBroadConfigs;
     const int c1 = c0 + kBroadConfigs < P.n ? c0 + kBroadConfigs : P.n;
-    const int k = 32 * w + lane;
-    bool tables = false, env_word = true;
-    if (P.pair_table) tables = __any_sync(kFull, k < kend && __ldg(&P.pair_table[k]) >= 0);
-    {
-        const uint32_t pr = __ldg(&P.pairs[k < kend ? k : kend - 1]);
-        env_word = __all_sync(kFull, (int)(pr & 0xffff) < P.ndyn && (int)(pr >> 16) >= P.ndyn);
+    const int rounds = (w_end - w_beg + nwarps - 1) / nwarps;
+    for (int r = 0; r < rounds; ++r) {
+        const int w = w_beg + r * nwarps + wib;
+        const bool have_word = w < w_end;                                      // (a warp without a word in the last round still meets the barriers)
+        const int k = 32 * w + lane;
+        const bool live = have_word && k < kend;
+        const int kk = live ? k : kend - 1;
+        const uint32_t pr = __ldg(&P.pairs[kk]);
+        const int sa = pr & 0xffff, sb = pr >> 16;
+        const bool a_dyn = sa < ndyn, b_dyn = sb < ndyn;
+        const float4* pa = (const float4*)P.aabb + (size_t)c0 * row + 2 * (a_dyn ? sa : 0);
+        const float4* pb = (const float4*)P.aabb + (size_t)c0 * row + 2 * (b_dyn ? sb : 0);
+        Box8 A, B;
+        A.c = make_float4(0.f, 0.f, 0.f, 0.f); A.e = A.c; B = A;
+        if (!a_dyn) A = ld_box(sab + 2 * (sa - ndyn));
+        if (!b_dyn) B = ld_box(sab + 2 * (sb - ndyn));
+        int tb = -1;
+        if (P.pair_table && live) tb = __ldg(&P.pair_table[kk]);
+        // warp-uniform flavours of the sweep: a word of (moving link, environment link) pairs — the bulk of every plan — loads only
+        // slot a's box per configuration; a word with a certificate table also looks the configuration's cell up
+        const bool env_word = __all_sync(kFull, a_dyn && !b_dyn);
+        const bool tables = __any_sync(kFull, tb >= 0);
+        for (int g = c0; g < c1; g += 32) {
+            const int nc = c1 - g < 32 ? c1 - g : 32;
+            uint32_t mine = 0u;
+            if (have_word) {
+                if (env_word && !tables) {
+#pragma unroll 4
+                    for (int i = 0; i < nc; ++i) {
+                        A = ld_box(pa); pa += row;
+                        // & on purpose (not &&): no lazily evaluated loads, no divergent branches
+                        const bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
+                        const unsigned m = __ballot_sync(kFull, ov);
+                        if (lane == i) mine = m;
+                    }
+                } else {
+#pragma unroll 2
+                    for (int i = 0; i < nc; ++i) {
+                        if (a_dyn) A = ld_box(pa);
+                        if (b_dyn) B = ld_box(pb);
+                        pa += row; pb += row;
+                        bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
+                        if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(g + i) * P.ncols)) ov = false;
+                        const unsigned m = __ballot_sync(kFull, ov);
+                        if (lane == i) mine = m;
+                    }
+                }
+                if (lane < nc) P.cand[(size_t)(g + lane) * P.cand_words + w] = mine;
+            }
+            __syncthreads();          // keep the block's warps on the same rows of boxes (one L2 fetch per row)
+        }
     }
-    if (tables) broad_word<true, false>(P, w, c0, c1, lane, kend);
-    else if (env_word) broad_word<false, true>(P, w, c0, c1, lane, kend);
-    else broad_word<false, false>(P, w, c0, c1, lane, kend);
 }
 
 // kSplit = false: one work item per configuration (full batches).  kSplit = true: P.split work items per configuration,
@@ -903,8 +919,12 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         }
                         relative_pose(A, Bx, R, t);
                         ra = (uint32_t)__ldg(&P.slot_root[la]); rb = (uint32_t)__ldg(&P.slot_root[lb]);
+#if CC_LD256
+                        { const Box8 na = ld_box(&P.nodes[2 * ra]), nb = ld_box(&P.nodes[2 * rb]); a0 = na.c; a1 = na.e; b0 = nb.c; b1 = nb.e; }
+#else
                         a0 = __ldg(&P.nodes[2 * ra]); a1 = __ldg(&P.nodes[2 * ra + 1]);
                         b0 = __ldg(&P.nodes[2 * rb]); b1 = __ldg(&P.nodes[2 * rb + 1]);
+#endif
                         if (counters) n_bv++;
                         cand = box_overlap(R, t, a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
                     }
@@ -1047,9 +1067,15 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const uint32_t sbits = it.x & 0xfc000000u;
                         const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x7fffffffu;
                         const bool side = (it.y >> 31) != 0u;                  // false: x is in tree A, true: x is in tree B
+#if CC_LD256
+                        // a node is 32 bytes: one 256-bit load each (3 instead of 6 loads per item, half the L1 tag lookups)
+                        const Box8 n0 = ld_box(&P.nodes[2 * x]), n1 = ld_box(&P.nodes[2 * x + 2]), no = ld_box(&P.nodes[2 * y]);
+                        const float4 c0a = n0.c, c0b = n0.e, c1a = n1.c, c1b = n1.e, oa = no.c, ob = no.e;
+#else
                         const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
                         const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
                         const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
+#endif
                         const float* rt = slot_rt + 24 * (it.x >> 26) + (side ? 12 : 0);      // maps the other node into the children's frame
                         float R[9], t[3];
 #pragma unroll

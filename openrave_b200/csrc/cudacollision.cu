@@ -105,6 +105,8 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int kMaxLanes = 4;      // pipeline lanes of a big batch (streams + scratch sets); two are used unless CC_TUNE_LANES says otherwise
+
 struct cc_scene {
     int device = 0;
     int num_sms = 0;
@@ -112,10 +114,10 @@ struct cc_scene {
     bool committed = false;
     DevBuf<float4> d_nodes, d_tris;
     int total_nodes = 0, total_tris = 0;
-    DevBuf<uint2> d_spill[2];               // one per pipeline lane (two chunks are in flight at a time)
+    DevBuf<uint2> d_spill[kMaxLanes];       // one per pipeline lane (one chunk per lane is in flight at a time)
     int spill_warps = 0;
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t lane_stream[kMaxLanes] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     int32_t* h_err = nullptr;               // error flag (a traversal overflowed its spill area): page-locked, mapped into the
     int32_t* d_err = nullptr;               //   device address space, so the host reads it after a sync without a copy
     int trav_blocks_per_sm = 0;             // occupancy of cc_traverse_kernel (queried once)
@@ -146,7 +148,7 @@ struct cc_scene {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (h_err) cudaFreeHost(h_err);
-        for (int i = 0; i < 2; ++i) { if (ev_join[i]) cudaEventDestroy(ev_join[i]); if (lane_stream[i]) cudaStreamDestroy(lane_stream[i]); }
+        for (int i = 0; i < kMaxLanes; ++i) { if (ev_join[i]) cudaEventDestroy(ev_join[i]); if (lane_stream[i]) cudaStreamDestroy(lane_stream[i]); }
     }
 };
 
@@ -475,10 +477,10 @@ struct cc_query {
     bool has_fk = false;
     std::vector<ccdev::FkStep> steps;       // every joint, depth-first order
     // per-chunk scratch (grown on demand, shared by the plans)
-    DevBuf<float> d_xf32[2], d_aabb[2];      // two sets: consecutive chunks overlap on two streams
-    DevBuf<uint32_t> d_cand[2];              // broadphase candidate bits of a chunk (cc_broad_kernel -> traversal)
-    DevBuf<double> d_fksave[2];
-    DevBuf<int32_t> d_counters[2];
+    DevBuf<float> d_xf32[kMaxLanes], d_aabb[kMaxLanes];      // one set per pipeline lane: consecutive chunks overlap on the lanes' streams
+    DevBuf<uint32_t> d_cand[kMaxLanes];              // broadphase candidate bits of a chunk (cc_broad_kernel -> traversal)
+    DevBuf<double> d_fksave[kMaxLanes];
+    DevBuf<int32_t> d_counters[kMaxLanes];
     DevBuf<uint32_t> d_hoisted_mask;
     std::vector<uint32_t> hoisted_mask;
     int hoisted_first_env = 0x7fffffff, hoisted_first_self = 0x7fffffff;
@@ -615,6 +617,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     const int nchunks = (n + chunk - 1) / chunk;
     const bool overlap = nchunks >= 2;
+    static const int nlanes = std::min(kMaxLanes, std::max(2, getenv("CC_TUNE_LANES") ? atoi(getenv("CC_TUNE_LANES")) : 2));     // pipeline lanes (A/B knob)
     static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
                                                                                                      // chunk of each lane (timing without FK)
     const bool timeline = S->trace_timeline && !fk_only;
@@ -623,12 +626,12 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         S->tl_lane.assign(nchunks, 0);
     }
     {
-        int rc = ensure_scratch(Q, pl, chunk, overlap ? 2 : 1);
+        int rc = ensure_scratch(Q, pl, chunk, overlap ? nlanes : 1);
         if (rc != CC_OK) return rc;
     }
     P.cap = chunk;
     if (overlap && !S->lane_stream[0]) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxLanes; ++i) {
             CC_CUDA(cudaStreamCreateWithFlags(&S->lane_stream[i], cudaStreamNonBlocking));
             CC_CUDA(cudaEventCreateWithFlags(&S->ev_join[i], cudaEventDisableTiming));
         }
@@ -655,15 +658,15 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         P.split = split;
         P.flags |= ccdev::kFlagInitOutputs;
     } else P.split = 1;
-    if (!fk_only && (S->spill_warps < full_warps || (overlap && !S->d_spill[1].p))) {
+    if (!fk_only && (S->spill_warps < full_warps || (overlap && !S->d_spill[nlanes - 1].p))) {
         CC_CUDA(cudaDeviceSynchronize());            // (first launches only) nobody may still be using the old areas
-        for (int k = 0; k < (overlap ? 2 : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
+        for (int k = 0; k < (overlap ? nlanes : 1); ++k) CC_CUDA(S->d_spill[k].reserve((size_t)full_warps * P.spill_cap));
         S->spill_warps = full_warps;
     }
     CC_CUDA(cudaEventRecord(S->ev0, st));
     if (overlap) {
         CC_CUDA(cudaEventRecord(S->ev_fork, st));
-        for (int i = 0; i < 2; ++i) CC_CUDA(cudaStreamWaitEvent(S->lane_stream[i], S->ev_fork, 0));
+        for (int i = 0; i < nlanes; ++i) CC_CUDA(cudaStreamWaitEvent(S->lane_stream[i], S->ev_fork, 0));
     }
     // results of chunk i go back to the host only after chunk i+1 has been enqueued: a copy into pageable memory blocks
     // the calling thread, and the device must already have the next chunk's work queued by then
@@ -685,7 +688,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     int ci = 0;
     for (int off = 0; off < n; off += chunk, ++ci) {
         const int m = std::min(chunk, n - off);
-        const int k = overlap ? (ci & 1) : 0;
+        const int k = overlap ? (ci % nlanes) : 0;
         cudaStream_t cs = overlap ? S->lane_stream[k] : st;
         if (hio && hio->in && row_doubles > 0)
             CC_CUDA(cudaMemcpyAsync(const_cast<double*>(d_q) + (size_t)off * row_doubles, hio->in + (size_t)off * row_doubles,
@@ -710,8 +713,12 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         }
         if (use_cand) {
             const int kb = (P.flags & ccdev::kFlagEnv) ? 0 : P.nenv_dev, ke = (P.flags & ccdev::kFlagSelf) ? P.npairs_dev : P.nenv_dev;
-            const long long bwarps = (long long)((m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs) * std::max(0, ((ke + 31) >> 5) - (kb >> 5));
-            if (bwarps > 0) ccdev::cc_broad_kernel<<<(unsigned)((bwarps + 3) / 4), 128, 0, cs>>>(P);
+            const int bwords = std::max(0, ((ke + 31) >> 5) - (kb >> 5));
+            if (bwords > 0) {
+                const int rounds = (bwords + ccdev::kBroadMaxWarps - 1) / ccdev::kBroadMaxWarps;
+                const int bw = (bwords + rounds - 1) / rounds;          // warps per block: the words spread evenly over the rounds
+                ccdev::cc_broad_kernel<<<(m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs, 32 * bw, 0, cs>>>(P);
+            }
             CC_CUDA(cudaGetLastError());
             S->stats.launches++;
         }
@@ -754,7 +761,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     }
     if (hio && pend_off >= 0) CC_CUDA(copy_out(pend_off, pend_m, pend_cs));
     if (overlap) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < nlanes; ++i) {
             CC_CUDA(cudaEventRecord(S->ev_join[i], S->lane_stream[i]));
             CC_CUDA(cudaStreamWaitEvent(st, S->ev_join[i], 0));
         }
