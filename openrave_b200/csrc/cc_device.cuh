@@ -640,17 +640,16 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 
 // ================================================================================================ kernel 1b: broadphase
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
-// one bit per pair, one row of cand_words words per configuration.  A thread block takes kBroadConfigs consecutive configurations;
-// each of its warps owns one word of 32 pairs (lane = pair) and sweeps those configurations with it: the pair is decoded once, the
-// box of a static slot is loaded once and stays in registers, and per configuration only the boxes of dynamic slots are fetched,
-// one 256-bit load each.  Pairs are in the reference's order, link by link, so the lanes of a word mostly ask for the same box of
-// slot a (a broadcast), and the warps of the block walk the same rows at the same time, so a row comes from L2 once (per-lane
-// gathers of all four boxes cost 16 - 32 L1 wavefronts per word and configuration and made an earlier form L1-bound:
-// profiles/r02l_ab.log, r02m_ab_cand.log).  Lane i keeps configuration i's ballot; a group of 32 configurations goes out with
-// one store.  In the traversal kernel the same test decodes the pair for every configuration, compacts candidates step by step
-// and holds a 72-register warp while it waits for the boxes: 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of
-// its stall samples (profiles/r02i_trav_sass.txt).
-constexpr int kBroadConfigs = 64;
+// one bit per pair, one row of cand_words words per configuration.  A thread block takes `group` (<= 32) consecutive
+// configurations: their boxes are one contiguous span of the FK kernel's output (1.3 KB per PR2 configuration), copied to shared
+// memory with coalesced loads — ONE trip to DRAM per block; sweeping configuration after configuration straight from global
+// memory costs a dependent DRAM round trip per step (682 us per 262 144-configuration PR2 chunk, issue-active 18 %, long-scoreboard
+// 23.8: profiles/r02n_broad_summary.md).  Each warp then owns words of 32 pairs (lane = pair): the pair is decoded once, the box
+// of a static slot is loaded once and stays in registers, the boxes of dynamic slots come from shared memory (pairs are in the
+// reference's order, link by link, so the lanes of a word mostly read the same box of slot a: a broadcast).  Lane i keeps
+// configuration i's ballot and the word goes out with one store.  In the traversal kernel the same test decodes the pair for
+// every configuration, compacts candidates step by step and holds a 72-register warp while it waits for the boxes: 1 450 of
+// 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
 constexpr int kBroadMaxWarps = 16;
 
 struct Box8 { float4 c, e; };
@@ -663,70 +662,69 @@ __device__ __forceinline__ Box8 ld_box(const float4* p)
     return r;
 }
 
-// grid: one block per kBroadConfigs configurations; block: `blockDim.x / 32` warps, warp i takes the words i, i + warps, ...
+// grid: one block per `group` configurations; block: blockDim.x / 32 warps, warp i takes the words i, i + warps, ...;
+// dynamic shared memory: group * ndyn * 32 bytes
 __global__ void __launch_bounds__(kBroadMaxWarps * 32)
-cc_broad_kernel(const __grid_constant__ Params P)
+cc_broad_kernel(const __grid_constant__ Params P, const int group)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_rows = (float4*)smem_raw;                                        // [group][ndyn][2]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ndyn = P.ndyn;
-    const size_t row = (size_t)ndyn * 2;                                       // float4 per configuration
+    const int row = ndyn * 2;                                                  // float4 per configuration
     const float4* __restrict__ sab = (const float4*)P.st_aabb;
     const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
     const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
     const int w_beg = kbeg >> 5, w_end = (kend + 31) >> 5;
-    const int c0 = blockIdx.x * kBroadConfigs;
-    const int c1 = c0 + kBroadConfigs < P.n ? c0 + kBroadConfigs : P.n;
-    const int rounds = (w_end - w_beg + nwarps - 1) / nwarps;
-    for (int r = 0; r < rounds; ++r) {
-        const int w = w_beg + r * nwarps + wib;
-        const bool have_word = w < w_end;                                      // (a warp without a word in the last round still meets the barriers)
+    const int c0 = blockIdx.x * group;
+    const int nc = P.n - c0 < group ? P.n - c0 : group;
+    {
+        const float4* __restrict__ src = (const float4*)P.aabb + (size_t)c0 * row;
+        for (int i = threadIdx.x; i < nc * row; i += blockDim.x) s_rows[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int w = w_beg + wib; w < w_end; w += nwarps) {
         const int k = 32 * w + lane;
-        const bool live = have_word && k < kend;
+        const bool live = k < kend;
         const int kk = live ? k : kend - 1;
         const uint32_t pr = __ldg(&P.pairs[kk]);
         const int sa = pr & 0xffff, sb = pr >> 16;
         const bool a_dyn = sa < ndyn, b_dyn = sb < ndyn;
-        const float4* pa = (const float4*)P.aabb + (size_t)c0 * row + 2 * (a_dyn ? sa : 0);
-        const float4* pb = (const float4*)P.aabb + (size_t)c0 * row + 2 * (b_dyn ? sb : 0);
+        const float4* pa = s_rows + 2 * (a_dyn ? sa : 0);
+        const float4* pb = s_rows + 2 * (b_dyn ? sb : 0);
         Box8 A, B;
         A.c = make_float4(0.f, 0.f, 0.f, 0.f); A.e = A.c; B = A;
         if (!a_dyn) A = ld_box(sab + 2 * (sa - ndyn));
         if (!b_dyn) B = ld_box(sab + 2 * (sb - ndyn));
         int tb = -1;
         if (P.pair_table && live) tb = __ldg(&P.pair_table[kk]);
-        // warp-uniform flavours of the sweep: a word of (moving link, environment link) pairs — the bulk of every plan — loads only
+        // warp-uniform flavours of the sweep: a word of (moving link, environment link) pairs — the bulk of most plans — reads only
         // slot a's box per configuration; a word with a certificate table also looks the configuration's cell up
         const bool env_word = __all_sync(kFull, a_dyn && !b_dyn);
         const bool tables = __any_sync(kFull, tb >= 0);
-        for (int g = c0; g < c1; g += 32) {
-            const int nc = c1 - g < 32 ? c1 - g : 32;
-            uint32_t mine = 0u;
-            if (have_word) {
-                if (env_word && !tables) {
+        uint32_t mine = 0u;
+        if (env_word && !tables) {
 #pragma unroll 4
-                    for (int i = 0; i < nc; ++i) {
-                        A = ld_box(pa); pa += row;
-                        // & on purpose (not &&): no lazily evaluated loads, no divergent branches
-                        const bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
-                        const unsigned m = __ballot_sync(kFull, ov);
-                        if (lane == i) mine = m;
-                    }
-                } else {
-#pragma unroll 2
-                    for (int i = 0; i < nc; ++i) {
-                        if (a_dyn) A = ld_box(pa);
-                        if (b_dyn) B = ld_box(pb);
-                        pa += row; pb += row;
-                        bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
-                        if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(g + i) * P.ncols)) ov = false;
-                        const unsigned m = __ballot_sync(kFull, ov);
-                        if (lane == i) mine = m;
-                    }
-                }
-                if (lane < nc) P.cand[(size_t)(g + lane) * P.cand_words + w] = mine;
+            for (int i = 0; i < nc; ++i) {
+                A.c = pa[0]; A.e = pa[1]; pa += row;
+                // & on purpose (not &&): no lazily evaluated loads, no divergent branches
+                const bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
+                const unsigned m = __ballot_sync(kFull, ov);
+                if (lane == i) mine = m;
             }
-            __syncthreads();          // keep the block's warps on the same rows of boxes (one L2 fetch per row)
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < nc; ++i) {
+                if (a_dyn) { A.c = pa[0]; A.e = pa[1]; }
+                if (b_dyn) { B.c = pb[0]; B.e = pb[1]; }
+                pa += row; pb += row;
+                bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
+                if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(c0 + i) * P.ncols)) ov = false;
+                const unsigned m = __ballot_sync(kFull, ov);
+                if (lane == i) mine = m;
+            }
         }
+        if (lane < nc) P.cand[(size_t)(c0 + lane) * P.cand_words + w] = mine;
     }
 }
 

@@ -48,53 +48,44 @@ struct DistOut {
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 
-// closest points of segments [p, p + d1] and [q, q + d2] (clamped quadratic minimisation)
+// closest points of segments [p, p + d1] and [q, q + d2] (clamped quadratic minimisation).  Branch-free: the 32 lanes of a
+// triangle batch take different clamping cases, and the divergent form ran every case one after the other with 8 - 11 lanes
+// each; its unrolled code also overflowed the instruction cache (no_instruction was the top stall, profiles/r02n_dist_summary.md)
 __device__ __forceinline__ float seg_seg(V3 p, V3 d1, V3 q, V3 d2, V3& c1, V3& c2)
 {
     const V3 r = p - q;
-    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
-    float s, t;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
     const float tiny = 1e-20f;
-    if (a <= tiny && e <= tiny) { s = t = 0.f; }
-    else if (a <= tiny) { s = 0.f; t = fminf(fmaxf(f / e, 0.f), 1.f); }
-    else {
-        const float c = dot(d1, r);
-        if (e <= tiny) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
-        else {
-            const float b = dot(d1, d2);
-            const float den = a * e - b * b;
-            s = den > tiny * a * e ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
-            t = (b * s + f) / e;
-            if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
-            else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
-        }
-    }
+    const float inv_a = a > tiny ? __fdividef(1.f, a) : 0.f;                 // a degenerate edge keeps its parameter at 0
+    const float inv_e = e > tiny ? __fdividef(1.f, e) : 0.f;
+    const float den = a * e - b * b;
+    float s = den > tiny * a * e ? __saturatef(__fdividef(b * f - c * e, den)) : 0.f;
+    const float tn = fmaf(b, s, f);                                          // t = tn / e before clamping
+    const float s_lo = __saturatef(-c * inv_a), s_hi = __saturatef((b - c) * inv_a);
+    s = (tn < 0.f || e <= tiny) ? s_lo : (tn > e ? s_hi : s);               // t clamped to 0 / 1: s re-solved for that end point
+    const float t = __saturatef(tn * inv_e);
     c1 = p + d1 * s;
     c2 = q + d2 * t;
     const V3 d = c1 - c2;
     return dot(d, d);
 }
 
-// closest point of triangle (a, b, c) to p (Voronoi-region walk)
+// closest point of triangle (a, b, c) to p: the Voronoi-region walk as selects, latest region first (same priority as the
+// early-return form: vertex a, vertex b, edge ab, vertex c, edge ac, edge bc, interior)
 __device__ __forceinline__ V3 closest_on_triangle(V3 p, V3 a, V3 b, V3 c)
 {
-    const V3 ab = b - a, ac = c - a, ap = p - a;
-    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
-    if (d1 <= 0.f && d2 <= 0.f) return a;
-    const V3 bp = p - b;
-    const float d3 = dot(ab, bp), d4 = dot(ac, bp);
-    if (d3 >= 0.f && d4 <= d3) return b;
-    const float vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) return a + ab * (d1 / (d1 - d3));
-    const V3 cp = p - c;
-    const float d5 = dot(ab, cp), d6 = dot(ac, cp);
-    if (d6 >= 0.f && d5 <= d6) return c;
-    const float vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) return a + ac * (d2 / (d2 - d6));
-    const float va = d3 * d6 - d5 * d4;
-    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) return b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6)));
-    const float den = 1.f / (va + vb + vc);
-    return a + ab * (vb * den) + ac * (vc * den);
+    const V3 ab = b - a, ac = c - a, ap = p - a, bp = p - b, cp = p - c;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap), d3 = dot(ab, bp), d4 = dot(ac, bp), d5 = dot(ab, cp), d6 = dot(ac, cp);
+    const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+    const float den = __fdividef(1.f, va + vb + vc);
+    float v = vb * den, w = vc * den;                                        // interior: a + ab v + ac w
+    { const bool k = va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f; const float ww = __fdividef(d4 - d3, (d4 - d3) + (d5 - d6)); v = k ? 1.f - ww : v; w = k ? ww : w; }
+    { const bool k = vb <= 0.f && d2 >= 0.f && d6 <= 0.f; const float ww = __fdividef(d2, d2 - d6); v = k ? 0.f : v; w = k ? ww : w; }
+    { const bool k = d6 >= 0.f && d5 <= d6; v = k ? 0.f : v; w = k ? 1.f : w; }
+    { const bool k = vc <= 0.f && d1 >= 0.f && d3 <= 0.f; const float vv = __fdividef(d1, d1 - d3); v = k ? vv : v; w = k ? 0.f : w; }
+    { const bool k = d3 >= 0.f && d4 <= d3; v = k ? 1.f : v; w = k ? 0.f : w; }
+    { const bool k = d1 <= 0.f && d2 <= 0.f; v = k ? 0.f : v; w = k ? 0.f : w; }
+    return a + ab * v + ac * w;
 }
 
 // Exact squared distance of triangles P = (0, p1, p2) and Q = (q0, q1, q2) with the closest points (same shifted frame).

@@ -105,7 +105,7 @@ struct DevBuf {
 
 }  // namespace
 
-constexpr int kMaxLanes = 4;      // pipeline lanes of a big batch (streams + scratch sets); two are used unless CC_TUNE_LANES says otherwise
+constexpr int kMaxLanes = 4;      // pipeline lanes of a big batch (streams + scratch sets); CC_TUNE_LANES = 2 .. 4 picks how many are used
 
 struct cc_scene {
     int device = 0;
@@ -116,6 +116,7 @@ struct cc_scene {
     int total_nodes = 0, total_tris = 0;
     DevBuf<uint2> d_spill[kMaxLanes];       // one per pipeline lane (one chunk per lane is in flight at a time)
     int spill_warps = 0;
+    size_t broad_smem_set = 0;              // dynamic shared memory cc_broad_kernel has been opted into
     cudaStream_t lane_stream[kMaxLanes] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     int32_t* h_err = nullptr;               // error flag (a traversal overflowed its spill area): page-locked, mapped into the
@@ -617,7 +618,7 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     const int nchunks = (n + chunk - 1) / chunk;
     const bool overlap = nchunks >= 2;
-    static const int nlanes = std::min(kMaxLanes, std::max(2, getenv("CC_TUNE_LANES") ? atoi(getenv("CC_TUNE_LANES")) : 2));     // pipeline lanes (A/B knob)
+    static const int nlanes = std::min(kMaxLanes, std::max(2, getenv("CC_TUNE_LANES") ? atoi(getenv("CC_TUNE_LANES")) : 4));     // pipeline lanes: 4 > 3 > 2 by about 1 % (profiles/r02n_ab.log)
     static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
                                                                                                      // chunk of each lane (timing without FK)
     const bool timeline = S->trace_timeline && !fk_only;
@@ -717,10 +718,16 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
             if (bwords > 0) {
                 const int rounds = (bwords + ccdev::kBroadMaxWarps - 1) / ccdev::kBroadMaxWarps;
                 const int bw = (bwords + rounds - 1) / rounds;          // warps per block: the words spread evenly over the rounds
-                ccdev::cc_broad_kernel<<<(m + ccdev::kBroadConfigs - 1) / ccdev::kBroadConfigs, 32 * bw, 0, cs>>>(P);
+                const int group = std::max(1, std::min(32, (96 * 1024) / std::max(1, P.ndyn * 32)));     // configurations per block
+                const size_t bsmem = (size_t)group * std::max(1, P.ndyn) * 32;
+                if (bsmem > S->broad_smem_set) {
+                    CC_CUDA(cudaFuncSetAttribute(ccdev::cc_broad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 48 * 1024)));
+                    S->broad_smem_set = std::max<size_t>(bsmem, 48 * 1024);
+                }
+                ccdev::cc_broad_kernel<<<(m + group - 1) / group, 32 * bw, bsmem, cs>>>(P, group);
+                CC_CUDA(cudaGetLastError());
+                S->stats.launches++;
             }
-            CC_CUDA(cudaGetLastError());
-            S->stats.launches++;
         }
         if (timeline) CC_CUDA(cudaEventRecord(S->tl_events[3 * ci + 1], cs));
         if (fk_only) {

@@ -31,7 +31,8 @@ def main():
     t = sys.argv[1]
     workload = "pr2_pr2test1_1m"
     shutil.copy(os.path.join(G, "%s_launches.csv" % t), os.path.join(P, "%s_launches.csv" % t))
-    for k in ("trav", "fk"):
+    has_broad = os.path.isfile(os.path.join(G, "%s_prof_broad.ncu-rep" % t))
+    for k in ("trav", "fk") + (("broad",) if has_broad else ()):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
                                os.path.join(G, "%s_prof_%s.ncu-rep" % (t, k)), os.path.join(P, "%s_%s" % (t, k))])
     sass = subprocess.run(["ncu", "-i", os.path.join(G, "%s_prof_trav.ncu-rep" % t), "--page", "source", "--csv", "--print-source", "sass"],
@@ -44,12 +45,12 @@ def main():
             if len(r) > 2:
                 f.write("\t".join(r[:6]) + "\n")
     # launch list: configurations per traversal launch = the chunk size of the bench step
-    nlaunch = {"trav": 0, "fk": 0}
-    dur = {"trav": 0.0, "fk": 0.0}
+    nlaunch = {"trav": 0, "fk": 0, "broad": 0}
+    dur = {"trav": 0.0, "fk": 0.0, "broad": 0.0}
     for r in csv.reader(open(os.path.join(P, "%s_launches.csv" % t), errors="ignore")):
         if len(r) > 5 and "cc_" in " ".join(r):
             name = " ".join(r)
-            k = "trav" if "cc_traverse" in name else ("fk" if "cc_fk" in name else None)
+            k = "trav" if "cc_traverse" in name else ("fk" if "cc_fk" in name else ("broad" if "cc_broad" in name else None))
             if k:
                 nlaunch[k] += 1
                 try:
@@ -57,22 +58,25 @@ def main():
                 except ValueError:
                     pass
     mt, mf = raw_metrics(os.path.join(G, "%s_prof_trav.ncu-rep" % t)), raw_metrics(os.path.join(G, "%s_prof_fk.ncu-rep" % t))
+    mb = raw_metrics(os.path.join(G, "%s_prof_broad.ncu-rep" % t)) if has_broad else {}
     cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
     n_step = 1000000
     chunks = (n_step + cfg - 1) // cfg
     wt, wf = float(mt["smsp__inst_executed.sum"]), float(mf["smsp__inst_executed.sum"])
+    wb = float(mb["smsp__inst_executed.sum"]) if has_broad else 0.0
     last = min(cfg, n_step - (chunks - 1) * cfg)
 
     def g(m, k):
         return float(m[k]) if m.get(k) not in (None, "") else None
 
     phys = {"workload": workload,
-            "kernels": "cc_traverse_kernel + cc_fk_kernel: every kernel of the bench step (profiles/%s_launches.csv: %d + %d launches for 5 steps)" % (
-                t, nlaunch["trav"], nlaunch["fk"]),
+            "kernels": "cc_traverse_kernel + cc_fk_kernel + cc_broad_kernel: every kernel of the bench step (profiles/%s_launches.csv: %d + %d + %d launches)" % (
+                t, nlaunch["trav"], nlaunch["fk"], nlaunch["broad"]),
             "source": "profiles/%s_trav_summary.md + profiles/%s_fk_summary.md (ncu --set full --clock-control none --import-source on, at HEAD, "
                       "one %d-configuration chunk each); SASS with execution counts in profiles/%s_trav_sass.txt" % (t, t, cfg, t),
             "configurations_per_captured_launch": cfg,
-            "warp_instructions_per_configuration": (wt + wf) / cfg,
+            "warp_instructions_per_configuration": (wt + wf + wb) / cfg,
+            "warp_instructions_per_configuration_broadphase": wb / cfg,
             "warp_instructions_per_configuration_traversal": wt / cfg,
             "warp_instructions_per_configuration_fk": wf / cfg,
             "threads_per_instruction": g(mt, "smsp__thread_inst_executed_per_inst_executed.ratio"),
@@ -89,12 +93,13 @@ def main():
     json.dump(phys, open(os.path.join(P, "physical_%s.json" % workload), "w"), indent=1)
     a = json.load(open(os.path.join(P, "%s_trav_traffic.json" % t)))["dram_bytes_per_launch"]
     b = json.load(open(os.path.join(P, "%s_fk_traffic.json" % t)))["dram_bytes_per_launch"]
+    cbytes = json.load(open(os.path.join(P, "%s_broad_traffic.json" % t)))["dram_bytes_per_launch"] if has_broad else 0.0
     scale = (chunks - 1) + last / float(cfg)
     traffic = {"workload": workload,
                "source": "profiles/%s_trav_traffic.json + profiles/%s_fk_traffic.json (ncu --set full at HEAD, one %d-configuration chunk each)" % (t, t, cfg),
                "chunks_per_step": chunks, "configurations_per_captured_launch": cfg, "trav_dram_bytes_per_launch": a, "fk_dram_bytes_per_launch": b,
-               "dram_bytes_per_step": scale * (a + b),
-               "note": "physical DRAM bytes of one 1M-configuration bench step = (chunks scaled to 1M configurations) x (cc_fk_kernel + cc_traverse_kernel)"}
+               "broad_dram_bytes_per_launch": cbytes, "dram_bytes_per_step": scale * (a + b + cbytes),
+               "note": "physical DRAM bytes of one 1M-configuration bench step = (chunks scaled to 1M configurations) x (cc_fk_kernel + cc_broad_kernel + cc_traverse_kernel)"}
     json.dump(traffic, open(os.path.join(P, "traffic_%s.json" % workload), "w"), indent=1)
     print(json.dumps(phys, indent=1))
     print(json.dumps(traffic, indent=1))
