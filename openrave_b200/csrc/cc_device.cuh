@@ -641,16 +641,21 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // ================================================================================================ kernel 1b: broadphase
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
 // one bit per pair, one row of cand_words words per configuration.  A thread block takes `group` (<= 32) consecutive
-// configurations: their boxes are one contiguous span of the FK kernel's output (1.3 KB per PR2 configuration), copied to shared
-// memory with coalesced loads — ONE trip to DRAM per block; sweeping configuration after configuration straight from global
-// memory costs a dependent DRAM round trip per step (682 us per 262 144-configuration PR2 chunk, issue-active 18 %, long-scoreboard
-// 23.8: profiles/r02n_broad_summary.md).  Each warp then owns words of 32 pairs (lane = pair): the pair is decoded once, the box
-// of a static slot is loaded once and stays in registers, the boxes of dynamic slots come from shared memory (pairs are in the
-// reference's order, link by link, so the lanes of a word mostly read the same box of slot a: a broadcast).  Lane i keeps
-// configuration i's ballot and the word goes out with one store.  In the traversal kernel the same test decodes the pair for
-// every configuration, compacts candidates step by step and holds a 72-register warp while it waits for the boxes: 1 450 of
-// 7 430 warp instructions per PR2 configuration and 28 % of its stall samples (profiles/r02i_trav_sass.txt).
+// configurations: their boxes are one contiguous span of the FK kernel's output (1.3 KB per PR2 configuration), read once with
+// coalesced 256-bit loads and kept in shared memory as 16-bit fixed-point {min, max} triples, 16 bytes per box (a 32 m cube around
+// the query body's base, 0.49 mm steps, min rounded down and max up, saturating: a monotone map, so an overlap is never lost).
+// Each warp then owns words of 32 pairs (lane = pair): the pair is decoded once, a static slot's box is quantised once and stays
+// in registers, a dynamic slot's box is ONE shared-memory load per configuration — pairs are in the reference's order, link by
+// link, so the lanes of a word mostly read the same box of slot a (a broadcast).  Lane i keeps configuration i's ballot and the
+// word goes out with one store.  History (profiles/): sweeping configurations straight from global memory costs a dependent DRAM
+// round trip per step (682 us per 262 144-configuration PR2 chunk, r02n_broad_summary.md); FP32 boxes in shared memory made the
+// kernel shared-memory-bound (18 wavefronts per word and configuration, l1tex 96 %, 463 us, r02o_broad_summary.md).  In the
+// traversal kernel the same test decodes the pair for every configuration, compacts candidates step by step and holds a
+// 72-register warp while it waits for the boxes: 1 450 of 7 430 warp instructions per PR2 configuration and 28 % of its stall
+// samples (r02i_trav_sass.txt).
 constexpr int kBroadMaxWarps = 16;
+constexpr float kBroadHalf = 16.0f;                            // half-size of the quantisation cube (metres, base-centred)
+constexpr float kBroadScale = 65535.0f / (2.0f * kBroadHalf);
 
 struct Box8 { float4 c, e; };
 // one 32-byte box {cx cy cz . | ex ey ez .} with a single 256-bit load (LDG.E.256, sm_100); p is 32-byte aligned
@@ -662,16 +667,33 @@ __device__ __forceinline__ Box8 ld_box(const float4* p)
     return r;
 }
 
+// {minx | miny << 16, minz | maxx << 16, maxy | maxz << 16, 0}: min rounded down, max rounded up (0.01 of a step of slack for the
+// FP32 rounding of the scaling itself), both saturating
+__device__ __forceinline__ uint4 quantise_box(const Box8& b)
+{
+    auto lo = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(floorf((v + kBroadHalf) * kBroadScale - 0.01f), 0.f), 65535.f); };
+    auto hi = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(ceilf((v + kBroadHalf) * kBroadScale + 0.01f), 0.f), 65535.f); };
+    return make_uint4(lo(b.c.x - b.e.x) | (lo(b.c.y - b.e.y) << 16), lo(b.c.z - b.e.z) | (hi(b.c.x + b.e.x) << 16),
+                      hi(b.c.y + b.e.y) | (hi(b.c.z + b.e.z) << 16), 0u);
+}
+
+__device__ __forceinline__ bool qbox_overlap(const uint4 a, const uint4 b)
+{
+    const uint32_t a_minx = a.x & 0xffffu, a_miny = a.x >> 16, a_minz = a.y & 0xffffu, a_maxx = a.y >> 16, a_maxy = a.z & 0xffffu, a_maxz = a.z >> 16;
+    const uint32_t b_minx = b.x & 0xffffu, b_miny = b.x >> 16, b_minz = b.y & 0xffffu, b_maxx = b.y >> 16, b_maxy = b.z & 0xffffu, b_maxz = b.z >> 16;
+    // & on purpose (not &&): no divergent branches
+    return (a_minx <= b_maxx) & (b_minx <= a_maxx) & (a_miny <= b_maxy) & (b_miny <= a_maxy) & (a_minz <= b_maxz) & (b_minz <= a_maxz);
+}
+
 // grid: one block per `group` configurations; block: blockDim.x / 32 warps, warp i takes the words i, i + warps, ...;
-// dynamic shared memory: group * ndyn * 32 bytes
+// dynamic shared memory: group * ndyn * 16 bytes
 __global__ void __launch_bounds__(kBroadMaxWarps * 32)
 cc_broad_kernel(const __grid_constant__ Params P, const int group)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_rows = (float4*)smem_raw;                                        // [group][ndyn][2]
+    uint4* s_rows = (uint4*)smem_raw;                                          // [group][ndyn]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ndyn = P.ndyn;
-    const int row = ndyn * 2;                                                  // float4 per configuration
     const float4* __restrict__ sab = (const float4*)P.st_aabb;
     const int kbeg = (P.flags & kFlagEnv) ? 0 : P.nenv_dev;
     const int kend = (P.flags & kFlagSelf) ? P.npairs_dev : P.nenv_dev;
@@ -679,8 +701,8 @@ cc_broad_kernel(const __grid_constant__ Params P, const int group)
     const int c0 = blockIdx.x * group;
     const int nc = P.n - c0 < group ? P.n - c0 : group;
     {
-        const float4* __restrict__ src = (const float4*)P.aabb + (size_t)c0 * row;
-        for (int i = threadIdx.x; i < nc * row; i += blockDim.x) s_rows[i] = __ldg(src + i);
+        const float4* __restrict__ src = (const float4*)P.aabb + (size_t)c0 * ndyn * 2;
+        for (int i = threadIdx.x; i < nc * ndyn; i += blockDim.x) s_rows[i] = quantise_box(ld_box(src + 2 * i));
     }
     __syncthreads();
     for (int w = w_beg + wib; w < w_end; w += nwarps) {
@@ -690,35 +712,32 @@ cc_broad_kernel(const __grid_constant__ Params P, const int group)
         const uint32_t pr = __ldg(&P.pairs[kk]);
         const int sa = pr & 0xffff, sb = pr >> 16;
         const bool a_dyn = sa < ndyn, b_dyn = sb < ndyn;
-        const float4* pa = s_rows + 2 * (a_dyn ? sa : 0);
-        const float4* pb = s_rows + 2 * (b_dyn ? sb : 0);
-        Box8 A, B;
-        A.c = make_float4(0.f, 0.f, 0.f, 0.f); A.e = A.c; B = A;
-        if (!a_dyn) A = ld_box(sab + 2 * (sa - ndyn));
-        if (!b_dyn) B = ld_box(sab + 2 * (sb - ndyn));
+        const uint4* pa = s_rows + (a_dyn ? sa : 0);
+        const uint4* pb = s_rows + (b_dyn ? sb : 0);
+        uint4 A = make_uint4(0u, 0u, 0u, 0u), B = A;
+        if (!a_dyn) A = quantise_box(ld_box(sab + 2 * (sa - ndyn)));
+        if (!b_dyn) B = quantise_box(ld_box(sab + 2 * (sb - ndyn)));
         int tb = -1;
         if (P.pair_table && live) tb = __ldg(&P.pair_table[kk]);
-        // warp-uniform flavours of the sweep: a word of (moving link, environment link) pairs — the bulk of most plans — reads only
-        // slot a's box per configuration; a word with a certificate table also looks the configuration's cell up
+        // warp-uniform flavours of the sweep: a word of (moving link, environment link) pairs reads only slot a's box per
+        // configuration; a word with a certificate table also looks the configuration's cell up
         const bool env_word = __all_sync(kFull, a_dyn && !b_dyn);
         const bool tables = __any_sync(kFull, tb >= 0);
         uint32_t mine = 0u;
         if (env_word && !tables) {
 #pragma unroll 4
             for (int i = 0; i < nc; ++i) {
-                A.c = pa[0]; A.e = pa[1]; pa += row;
-                // & on purpose (not &&): no lazily evaluated loads, no divergent branches
-                const bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
-                const unsigned m = __ballot_sync(kFull, ov);
+                A = *pa; pa += ndyn;
+                const unsigned m = __ballot_sync(kFull, live & qbox_overlap(A, B));
                 if (lane == i) mine = m;
             }
         } else {
 #pragma unroll 2
             for (int i = 0; i < nc; ++i) {
-                if (a_dyn) { A.c = pa[0]; A.e = pa[1]; }
-                if (b_dyn) { B.c = pb[0]; B.e = pb[1]; }
-                pa += row; pb += row;
-                bool ov = live & (fabsf(A.c.x - B.c.x) <= A.e.x + B.e.x) & (fabsf(A.c.y - B.c.y) <= A.e.y + B.e.y) & (fabsf(A.c.z - B.c.z) <= A.e.z + B.e.z);
+                if (a_dyn) A = *pa;
+                if (b_dyn) B = *pb;
+                pa += ndyn; pb += ndyn;
+                bool ov = live & qbox_overlap(A, B);
                 if (ov && tb >= 0 && table_cell_free(P, tb, P.q + (size_t)(c0 + i) * P.ncols)) ov = false;
                 const unsigned m = __ballot_sync(kFull, ov);
                 if (lane == i) mine = m;

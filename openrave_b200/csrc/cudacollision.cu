@@ -718,8 +718,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
             if (bwords > 0) {
                 const int rounds = (bwords + ccdev::kBroadMaxWarps - 1) / ccdev::kBroadMaxWarps;
                 const int bw = (bwords + rounds - 1) / rounds;          // warps per block: the words spread evenly over the rounds
-                const int group = std::max(1, std::min(32, (96 * 1024) / std::max(1, P.ndyn * 32)));     // configurations per block
-                const size_t bsmem = (size_t)group * std::max(1, P.ndyn) * 32;
+                const int group = std::max(1, std::min(32, (96 * 1024) / std::max(1, P.ndyn * 16)));     // configurations per block
+                const size_t bsmem = (size_t)group * std::max(1, P.ndyn) * 16;
                 if (bsmem > S->broad_smem_set) {
                     CC_CUDA(cudaFuncSetAttribute(ccdev::cc_broad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 48 * 1024)));
                     S->broad_smem_set = std::max<size_t>(bsmem, 48 * 1024);

@@ -37,16 +37,18 @@ for rep in range(3):
     torch.cuda.synchronize()
     ms, lane = cc.GetTimeline()
     step = e0.elapsed_time(e1)
-    # time during which both lanes had a chunk in flight: intersect the union of lane 0's intervals with lane 1's
+    # time during which at least two lanes had a chunk in flight
     grid = np.linspace(0, step, 20001)
-    busy = [np.zeros_like(grid, dtype=bool), np.zeros_like(grid, dtype=bool)]
+    busy = [np.zeros_like(grid, dtype=bool) for _ in range(max(2, max(lane) + 1))]
     for (a, b, c), l in zip(ms, lane):
         busy[l] |= (grid >= a) & (grid <= c)
+    nbusy = np.sum(busy, axis=0)
     recs.append({"step_ms": step,
                  "chunks": [{"lane": int(l), "lane_free_ms": round(a, 4), "fk_end_ms": round(b, 4), "traversal_end_ms": round(c, 4)}
                             for (a, b, c), l in zip(ms, lane)],
                  "sum_of_chunk_intervals_ms": float(sum(c - a for a, b, c in ms)),
                  "sum_of_fk_intervals_ms": float(sum(b - a for a, b, c in ms)),
-                 "both_lanes_busy_ms": float((busy[0] & busy[1]).mean() * step),
-                 "any_lane_busy_ms": float((busy[0] | busy[1]).mean() * step)})
+                 "lanes": len(busy),
+                 "two_or_more_lanes_busy_ms": float((nbusy >= 2).mean() * step),
+                 "any_lane_busy_ms": float((nbusy >= 1).mean() * step)})
 print(json.dumps({"workload": workload, "n": n, "steps": recs}, indent=1))
