@@ -85,7 +85,7 @@ struct FkStep {                 // 256 bytes
                                 // bit4 constant step: the child's pose is emitted as running * L, the running transform is kept
     int32_t load_parent;        // -2: parent pose is the running transform, -1: link 0's pose, >=0: parked pose index
     int32_t save;               // >=0: park this child's pose (a later step branches off it)
-    int32_t pad;
+    int32_t pose_in;            // two-phase FK kernel: index (0 = link 0, 1 + j = child of the j-th varying step) of the pose this step starts from
     double src_const;           // value when src_col < 0
     double src_lower, src_upper;// limits of the source DOF (KinBody::SetDOFValues clamps DOF values first)
     double a, b;                // mimic: value = a*src + b
@@ -93,7 +93,8 @@ struct FkStep {                 // 256 bytes
     double L[8];                // left transform  {qw qx qy qz tx ty tz 0}
     double R[8];                // right transform
     double axis[4];
-    double pad2;
+    int32_t pose_out;           // two-phase FK kernel: where a varying step stores its child's pose (-1: constant step)
+    int32_t pad2;
 };
 static_assert(sizeof(FkStep) == 256, "FkStep layout");
 
@@ -115,6 +116,7 @@ struct Params {
     const FkStep* steps;        // depth-first order, pruned to the ancestors of the dynamic slots
     const uint32_t* hoisted_mask;
     int32_t nq, ndyn, nstatic, npairs_dev, nenv_dev, nenv_total, nsteps, ncols;
+    int32_t npose;              // poses the two-phase FK kernel keeps per configuration: link 0 + one per varying step
     int32_t hoisted_first_env, hoisted_first_self, mask_words, flags;
     double base[8];             // pose of link 0 (kept, kinbody.cpp:2281)
     // affine active DOFs (RobotBase::SetActiveDOFValues, robot.cpp:1193-1225): the columns [affine_col, ..) of q hold X | Y | Z and one
@@ -584,6 +586,100 @@ cc_fk_kernel(const __grid_constant__ Params P)
     fk_chain(P, s_steps, s_linkbox, s_emit, D, c);
 }
 
+// ------------------------------------------------------------------------------------------------ kernel 1, two-phase form
+// The same arithmetic as cc_fk_kernel, split so that most of it runs with every thread busy and with coalesced stores:
+//   phase 1  one thread per configuration walks only the VARYING steps (8 of PR2's 41) and leaves every varying link's pose in
+//            shared memory ([configuration][pose][7 doubles], rows padded to an odd length: conflict-free both ways);
+//   phase 2  one thread per (configuration, link): a varying link's pose is read back, a rigidly attached link's pose is
+//            T_anchor * L (one product), then the FP32 R|t, the world AABB and the optional FP64 copy-out.  Consecutive threads
+//            write consecutive slots of one configuration's row, where the one-thread-per-configuration kernel scatters every
+//            16-byte store over 32 rows and walks all 41 links behind one serial dependency chain (issue-active 18 %,
+//            long-scoreboard 14.4, profiles/r02i_fk_summary.md).
+__host__ __device__ inline size_t fk2_fixed_bytes(int nq, int nsteps, int ndyn)
+{
+    return ((size_t)nsteps * sizeof(FkStep) + (size_t)ndyn * 32 + (size_t)nq * 4 + 15) / 16 * 16;
+}
+__host__ __device__ inline int fk2_row_doubles(int npose) { return (npose * 7) | 1; }
+
+__device__ __forceinline__ Xf pose_load(const double* row, int idx)
+{
+    const double* p = row + 7 * idx;
+    Xf t; t.q0 = p[0]; t.q1 = p[1]; t.q2 = p[2]; t.q3 = p[3]; t.tx = p[4]; t.ty = p[5]; t.tz = p[6];
+    return t;
+}
+__device__ __forceinline__ void pose_store(double* row, int idx, const Xf& t)
+{
+    double* p = row + 7 * idx;
+    p[0] = t.q0; p[1] = t.q1; p[2] = t.q2; p[3] = t.q3; p[4] = t.tx; p[5] = t.ty; p[6] = t.tz;
+}
+
+// grid: one block per `group` configurations (group <= blockDim.x); dynamic shared memory: fk2_fixed_bytes + group * row * 8
+__global__ void __launch_bounds__(kFkThreads, 4)
+cc_fk2_kernel(const __grid_constant__ Params P, const int group)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FkStep* s_steps = (FkStep*)smem_raw;
+    float* s_linkbox = (float*)(s_steps + P.nsteps);
+    int32_t* s_emit = (int32_t*)(s_linkbox + 8 * P.ndyn);
+    double* s_pose = (double*)(smem_raw + fk2_fixed_bytes(P.nq, P.nsteps, P.ndyn));
+    const int rowlen = fk2_row_doubles(P.npose);
+    {
+        const int4* src = (const int4*)P.steps; int4* dst = (int4*)s_steps;
+        for (int i = threadIdx.x; i < P.nsteps * (int)(sizeof(FkStep) / 16); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 8 * P.ndyn; i += blockDim.x) s_linkbox[i] = P.link_box[i];
+        for (int i = threadIdx.x; i < P.nq; i += blockDim.x) s_emit[i] = P.emit_index[i];
+    }
+    __syncthreads();
+    const int c0 = blockIdx.x * group;
+    const int nc = P.n - c0 < group ? P.n - c0 : group;
+    const bool pose_mode = (P.flags & kFlagPoseMode) != 0;
+    // ---- phase 1: the varying steps, one thread per configuration
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        const int c = c0 + i;
+        if (P.flags & kFlagInitOutputs) {
+            if (P.verdict) P.verdict[c] = 0u;
+            if (P.first_env) P.first_env[c] = -1;
+            if (P.first_self) P.first_self[c] = -1;
+            if (P.work_out) P.work_out[c] = 0u;
+            if (P.pair_mask) {
+                uint32_t* mrow = P.pair_mask + (size_t)c * P.mask_words;
+                for (int k = 0; k < P.mask_words; ++k) mrow[k] = P.hoisted_mask ? P.hoisted_mask[k] : 0u;
+            }
+        }
+        if (pose_mode) continue;
+        const double* qrow = P.q + (size_t)c * P.ncols;
+        double* row = s_pose + (size_t)i * rowlen;
+        Xf base = xf_load(P.base);                                    // link 0 keeps its pose (kinbody.cpp:2281) ...
+        if (P.affine_mask) base = affine_base(P, base, qrow + P.affine_col);      // ... unless affine DOFs are active
+        pose_store(row, 0, base);
+        for (int s = 0; s < P.nsteps; ++s) {
+            const FkStep& st = s_steps[s];
+            if (st.flags & 16) continue;
+            pose_store(row, st.pose_out, xf_mul(pose_load(row, st.pose_in), joint_transform(st, qrow)));
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per (configuration, link)
+    const int per_cfg = pose_mode ? P.nq : P.nsteps + 1;
+    for (int it = threadIdx.x; it < nc * per_cfg; it += blockDim.x) {
+        const int i = it / per_cfg, e = it - i * per_cfg;
+        const int c = c0 + i;
+        FkDst D;
+        D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
+        D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
+        D.save = nullptr; D.save_pose_stride = D.save_comp_stride = 0;
+        if (pose_mode) {
+            if (s_emit[e] >= 0) emit_link(P, s_linkbox, D, c, e, s_emit[e], xf_load(P.q + ((size_t)c * P.nq + e) * 8));
+            continue;
+        }
+        const double* row = s_pose + (size_t)i * rowlen;
+        if (e == 0) { emit_link(P, s_linkbox, D, c, 0, s_emit[0], pose_load(row, 0)); continue; }
+        const FkStep& st = s_steps[e - 1];
+        const Xf T = (st.flags & 16) ? xf_mul(pose_load(row, st.pose_in), xf_load(st.L)) : pose_load(row, st.pose_out);
+        emit_link(P, s_linkbox, D, c, st.child, s_emit[st.child], T);
+    }
+}
+
 // ================================================================================================ kernel 2: traversal
 constexpr size_t kWarpSmemBytes = (size_t)kNumSlots * 96 + (size_t)kNumSlots * 4 + (size_t)kStackCap * 8 + (size_t)kTriQCap * 8 +
                                   (size_t)kTriQ2Cap * 8 + (size_t)kCandCap * 4;
@@ -642,8 +738,9 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // World-AABB test of every (configuration, device pair) of a chunk, plus the certificate lookup where a table covers the pair:
 // one bit per pair, one row of cand_words words per configuration.  A thread block takes `group` (<= 32) consecutive
 // configurations: their boxes are one contiguous span of the FK kernel's output (1.3 KB per PR2 configuration), read once with
-// coalesced 256-bit loads and kept in shared memory as 16-bit fixed-point {min, max} triples, 16 bytes per box (a 32 m cube around
-// the query body's base, 0.49 mm steps, min rounded down and max up, saturating: a monotone map, so an overlap is never lost).
+// coalesced 256-bit loads and kept in shared memory as 15-bit fixed-point {min, max} triples, 16 bytes per box (a 32 m cube around
+// the query body's base, 0.98 mm steps, min rounded down and max up, saturating: a monotone map, so an overlap is never lost; the
+// six comparisons are four packed subtractions).
 // Each warp then owns words of 32 pairs (lane = pair): the pair is decoded once, a static slot's box is quantised once and stays
 // in registers, a dynamic slot's box is ONE shared-memory load per configuration — pairs are in the reference's order, link by
 // link, so the lanes of a word mostly read the same box of slot a (a broadcast).  Lane i keeps configuration i's ballot and the
@@ -655,7 +752,7 @@ __device__ __noinline__ bool table_cell_free(const Params& P, int tb, const doub
 // samples (r02i_trav_sass.txt).
 constexpr int kBroadMaxWarps = 16;
 constexpr float kBroadHalf = 16.0f;                            // half-size of the quantisation cube (metres, base-centred)
-constexpr float kBroadScale = 65535.0f / (2.0f * kBroadHalf);
+constexpr float kBroadScale = 32767.0f / (2.0f * kBroadHalf);          // 15-bit steps of 0.98 mm
 
 struct Box8 { float4 c, e; };
 // one 32-byte box {cx cy cz . | ex ey ez .} with a single 256-bit load (LDG.E.256, sm_100); p is 32-byte aligned
@@ -667,22 +764,22 @@ __device__ __forceinline__ Box8 ld_box(const float4* p)
     return r;
 }
 
-// {minx | miny << 16, minz | maxx << 16, maxy | maxz << 16, 0}: min rounded down, max rounded up (0.01 of a step of slack for the
-// FP32 rounding of the scaling itself), both saturating
+// {minx | miny << 16, minz, maxx | maxy << 16, maxz} in 15-bit steps: min rounded down, max rounded up (0.01 of a step of slack
+// for the FP32 rounding of the scaling itself), both saturating
 __device__ __forceinline__ uint4 quantise_box(const Box8& b)
 {
-    auto lo = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(floorf((v + kBroadHalf) * kBroadScale - 0.01f), 0.f), 65535.f); };
-    auto hi = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(ceilf((v + kBroadHalf) * kBroadScale + 0.01f), 0.f), 65535.f); };
-    return make_uint4(lo(b.c.x - b.e.x) | (lo(b.c.y - b.e.y) << 16), lo(b.c.z - b.e.z) | (hi(b.c.x + b.e.x) << 16),
-                      hi(b.c.y + b.e.y) | (hi(b.c.z + b.e.z) << 16), 0u);
+    auto lo = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(floorf((v + kBroadHalf) * kBroadScale - 0.01f), 0.f), 32767.f); };
+    auto hi = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(ceilf((v + kBroadHalf) * kBroadScale + 0.01f), 0.f), 32767.f); };
+    return make_uint4(lo(b.c.x - b.e.x) | (lo(b.c.y - b.e.y) << 16), lo(b.c.z - b.e.z), hi(b.c.x + b.e.x) | (hi(b.c.y + b.e.y) << 16), hi(b.c.z + b.e.z));
 }
 
+// a.min <= b.max and b.min <= a.max on all three axes, two 15-bit fields per subtraction: (max | guard) - min keeps the guard bit
+// (bit 15 of its half) exactly when max >= min, and never borrows across the halves
 __device__ __forceinline__ bool qbox_overlap(const uint4 a, const uint4 b)
 {
-    const uint32_t a_minx = a.x & 0xffffu, a_miny = a.x >> 16, a_minz = a.y & 0xffffu, a_maxx = a.y >> 16, a_maxy = a.z & 0xffffu, a_maxz = a.z >> 16;
-    const uint32_t b_minx = b.x & 0xffffu, b_miny = b.x >> 16, b_minz = b.y & 0xffffu, b_maxx = b.y >> 16, b_maxy = b.z & 0xffffu, b_maxz = b.z >> 16;
-    // & on purpose (not &&): no divergent branches
-    return (a_minx <= b_maxx) & (b_minx <= a_maxx) & (a_miny <= b_maxy) & (b_miny <= a_maxy) & (a_minz <= b_maxz) & (b_minz <= a_maxz);
+    constexpr uint32_t G = 0x80008000u;
+    const uint32_t r = ((b.z | G) - a.x) & ((b.w | G) - a.y) & ((a.z | G) - b.x) & ((a.w | G) - b.y);
+    return (r & G) == G;
 }
 
 // grid: one block per `group` configurations; block: blockDim.x / 32 warps, warp i takes the words i, i + warps, ...;

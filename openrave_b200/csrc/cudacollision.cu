@@ -116,6 +116,7 @@ struct cc_scene {
     int total_nodes = 0, total_tris = 0;
     DevBuf<uint2> d_spill[kMaxLanes];       // one per pipeline lane (one chunk per lane is in flight at a time)
     int spill_warps = 0;
+    size_t fk2_smem_set = 0;                // dynamic shared memory cc_fk2_kernel has been opted into
     size_t broad_smem_set = 0;              // dynamic shared memory cc_broad_kernel has been opted into
     cudaStream_t lane_stream[kMaxLanes] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
@@ -395,7 +396,7 @@ void pose_to_rt32(const double* x, const double center[3], float* o)
 struct Plan {
     std::vector<uint32_t> pairs;     // slot_a | slot_b << 16
     std::vector<int32_t> orig;
-    int nenv = 0, ndyn = 0, nstatic = 0, nsave = 0;
+    int nenv = 0, ndyn = 0, nstatic = 0, nsave = 0, npose = 1;
     std::vector<std::pair<int, int>> statics;   // (body, link) of every static slot (poses refreshed by cc_query_refresh)
     std::vector<double> st_pose;                // [nstatic][8] the poses those slots were laid out with (what moved since? cc_query_refresh)
     std::vector<int32_t> emit;       // [nq] link -> dynamic slot or -1
@@ -547,7 +548,7 @@ void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev
     P.steps = pl.d_steps.p;
     P.hoisted_mask = use_hoisted ? Q->d_hoisted_mask.p : nullptr;
     P.nq = Q->nq; P.ndyn = pl.ndyn; P.nstatic = pl.nstatic; P.npairs_dev = (int)pl.pairs.size(); P.nenv_dev = pl.nenv;
-    P.nenv_total = Q->nenv_total; P.nsteps = (int)pl.steps.size(); P.ncols = Q->ncols;
+    P.nenv_total = Q->nenv_total; P.nsteps = (int)pl.steps.size(); P.ncols = Q->ncols; P.npose = pl.npose;
     P.hoisted_first_env = use_hoisted ? Q->hoisted_first_env : ccdev::kNone;
     P.hoisted_first_self = use_hoisted ? Q->hoisted_first_self : ccdev::kNone;
     P.mask_words = Q->mask_words;
@@ -561,6 +562,36 @@ void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev
     P.stats = S->d_stats.p;
     P.spill_cap = 2048;
     P.split = 1;
+}
+
+// FK of m configurations on stream cs: the two-phase kernel (cc_fk2_kernel) unless its per-block pose table does not fit in shared
+// memory or CC_TUNE_FK2=0 asks for the one-thread-per-configuration form (A/B: profiles/r02q_ab_fk2.log)
+int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
+{
+    static const bool tune_fk2 = !(getenv("CC_TUNE_FK2") && atoi(getenv("CC_TUNE_FK2")) == 0);
+    const size_t fixed = ccdev::fk2_fixed_bytes(P.nq, P.nsteps, P.ndyn);
+    const size_t row = (size_t)ccdev::fk2_row_doubles(P.npose) * sizeof(double);
+    int group = 0;
+    if (tune_fk2)
+        for (int g = ccdev::kFkThreads; g >= 32; g -= 32)
+            if (fixed + g * row <= (g == 32 ? 200u : 48u) * 1024u) { group = g; break; }       // <= 48 KB per block where possible (4 - 5 resident blocks)
+    if (group > 0) {
+        const size_t smem = fixed + group * row;
+        if (smem > S->fk2_smem_set) {
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            S->fk2_smem_set = std::max<size_t>(smem, 48 * 1024);
+        }
+        ccdev::cc_fk2_kernel<<<(m + group - 1) / group, ccdev::kFkThreads, smem, cs>>>(P, group);
+    } else {
+        const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
+        if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
+        if (fk_smem > 48 * 1024)
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
+    }
+    CC_CUDA(cudaGetLastError());
+    S->stats.launches++;
+    return CC_OK;
 }
 
 int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int n, int flags, uint32_t* d_verdict,
@@ -639,10 +670,6 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         CC_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     }
 
-    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
-    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
-    if (fk_smem > 48 * 1024)
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
     if (Q->trace_work && !fk_only) { CC_CUDA(Q->d_work.reserve((size_t)n)); Q->work_n = n; }
     if (contacts) { P.contact_out = Q->contact_out; P.contact_count = Q->contact_count; P.contact_cap = Q->contact_cap; }
     const bool use_tables = Q->ntables > 0 && &pl == &Q->mainl && !(flags & ccdev::kFlagPoseMode) && !fk_only;
@@ -708,9 +735,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
         if (!fk_only) CC_CUDA(cudaMemsetAsync(Q->d_counters[k].p, 0, sizeof(int32_t), cs));
         if (timeline) { S->tl_lane[ci] = k; CC_CUDA(cudaEventRecord(S->tl_events[3 * ci], cs)); }
         if (!(tune_skip_fk && ci >= 2 && !fk_only)) {
-            ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, cs>>>(P);
-            CC_CUDA(cudaGetLastError());
-            S->stats.launches++;
+            const int rc = launch_fk(S, P, m, cs);
+            if (rc != CC_OK) return rc;
         }
         if (use_cand) {
             const int kb = (P.flags & ccdev::kFlagEnv) ? 0 : P.nenv_dev, ke = (P.flags & ccdev::kFlagSelf) ? P.npairs_dev : P.nenv_dev;
@@ -801,10 +827,6 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     CC_CUDA(Q->d_q.reserve(std::max<size_t>(1, (size_t)chunk * row_doubles)));
     CC_CUDA(Q->d_dist.reserve((size_t)chunk * outs_per_cfg)); CC_CUDA(Q->d_dpair.reserve((size_t)chunk * outs_per_cfg));
     CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
-    const size_t fk_smem = ccdev::fk_smem_bytes(P.nq, P.nsteps, P.ndyn);
-    if (fk_smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "kinematic chain + environment tables exceed one block's shared memory");
-    if (fk_smem > 48 * 1024)
-        CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
     const size_t d_smem = ccdev::kDistWarpSmemBytes * ccdev::kWarpsPerBlock;
     static int dist_blocks_per_sm = 0;
     if (dist_blocks_per_sm == 0) {
@@ -829,14 +851,16 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
         P.q = Q->d_q.p;
         P.xf32 = Q->d_xf32[0].p; P.aabb = Q->d_aabb[0].p; P.fksave = Q->d_fksave[0].p; P.counters = Q->d_counters[0].p;
         CC_CUDA(cudaMemsetAsync(Q->d_counters[0].p, 0, sizeof(int32_t), st));
-        ccdev::cc_fk_kernel<<<(m + ccdev::kFkThreads - 1) / ccdev::kFkThreads, ccdev::kFkThreads, fk_smem, st>>>(P);
-        CC_CUDA(cudaGetLastError());
+        {
+            const int rc2 = launch_fk(S, P, m, st);
+            if (rc2 != CC_OK) return rc2;
+        }
         int grid = dist_blocks_per_sm * S->num_sms;
         const long long need = ((long long)m * outs_per_cfg + ccdev::kWarpsPerBlock - 1) / ccdev::kWarpsPerBlock;
         if (grid > need) grid = (int)need;
         ccdev::cc_distance_kernel<<<grid, ccdev::kWarpsPerBlock * 32, d_smem, st>>>(P, D);
         CC_CUDA(cudaGetLastError());
-        S->stats.launches += 2;
+        S->stats.launches += 1;
         CC_CUDA(cudaMemcpyAsync(h_dist + (size_t)off * outs_per_cfg, Q->d_dist.p, (size_t)m * outs_per_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (h_pair && !per_pair) CC_CUDA(cudaMemcpyAsync(h_pair + off, Q->d_dpair.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         if (h_pts && !per_pair) CC_CUDA(cudaMemcpyAsync(h_pts + (size_t)off * 6, Q->d_dpts.p, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1259,6 +1283,7 @@ static void compile_fk_program(const cc_query* Q, Plan& pl)
     const int nl = Q->nq;
     pl.steps.clear();
     pl.nsave = 0;
+    pl.npose = 1;
     if (!Q->has_fk || Q->steps.empty()) return;
     static const bool fold = !(getenv("CC_TUNE_FK_FOLD") && atoi(getenv("CC_TUNE_FK_FOLD")) == 0);    // 0: walk every joint (A/B)
     std::vector<uint8_t> need(nl, 0);
@@ -1303,6 +1328,17 @@ static void compile_fk_program(const cc_query* Q, Plan& pl)
     for (const ccdev::FkStep& v : varying) {
         pl.steps.push_back(v);
         for (const ccdev::FkStep& e : consts[v.child]) pl.steps.push_back(e);
+    }
+    // two-phase kernel: every varying step's child pose has a slot in the per-configuration pose table (0 = link 0)
+    {
+        std::vector<int> pose_of_link(nl, 0);
+        int nv = 0;
+        for (ccdev::FkStep& st : pl.steps) {
+            st.pose_in = pose_of_link[st.parent];
+            if (st.flags & 16) st.pose_out = -1;
+            else { st.pose_out = ++nv; pose_of_link[st.child] = nv; }
+        }
+        pl.npose = 1 + nv;
     }
     // where each varying step finds its starting pose: the running transform, the base, or a parked pose
     std::vector<int> save_of_link(nl, -1);
