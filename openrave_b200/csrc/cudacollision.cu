@@ -116,8 +116,6 @@ struct cc_scene {
     int total_nodes = 0, total_tris = 0;
     DevBuf<uint2> d_spill[kMaxLanes];       // one per pipeline lane (one chunk per lane is in flight at a time)
     int spill_warps = 0;
-    size_t fk2_smem_set = 0;                // dynamic shared memory cc_fk2_kernel has been opted into
-    size_t broad_smem_set = 0;              // dynamic shared memory cc_broad_kernel has been opted into
     cudaStream_t lane_stream[kMaxLanes] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     int32_t* h_err = nullptr;               // error flag (a traversal overflowed its spill area): page-locked, mapped into the
@@ -564,6 +562,10 @@ void init_params(cc_query* Q, const Plan& pl, bool use_hoisted, int flags, ccdev
     P.split = 1;
 }
 
+// per-device record of the kernels whose dynamic shared-memory limit has been raised
+struct SmemOpted { bool fk2 = false, broad = false; int dist_blocks_per_sm = 0; };
+SmemOpted g_smem_opted[64];
+
 // FK of m configurations on stream cs: the two-phase kernel (cc_fk2_kernel) unless its per-block pose table does not fit in shared
 // memory or CC_TUNE_FK2=0 asks for the one-thread-per-configuration form (A/B: profiles/r02q_ab_fk2.log)
 int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
@@ -577,9 +579,11 @@ int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
             if (fixed + g * row <= (g == 32 ? 200u : 48u) * 1024u) { group = g; break; }       // <= 48 KB per block where possible (4 - 5 resident blocks)
     if (group > 0) {
         const size_t smem = fixed + group * row;
-        if (smem > S->fk2_smem_set) {
-            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-            S->fk2_smem_set = std::max<size_t>(smem, 48 * 1024);
+        if (!g_smem_opted[S->device & 63].fk2) {
+            // the opt-in is a property of the kernel on a device, shared by every scene of the process: raise it once to the most any
+            // launch may ask for (a per-scene record of "what I asked for last" lets one scene lower another's limit)
+            CC_CUDA(cudaFuncSetAttribute(ccdev::cc_fk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            g_smem_opted[S->device & 63].fk2 = true;
         }
         ccdev::cc_fk2_kernel<<<(m + group - 1) / group, ccdev::kFkThreads, smem, cs>>>(P, group);
     } else {
@@ -746,9 +750,9 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
                 const int bw = (bwords + rounds - 1) / rounds;          // warps per block: the words spread evenly over the rounds
                 const int group = std::max(1, std::min(32, (96 * 1024) / std::max(1, P.ndyn * 16)));     // configurations per block
                 const size_t bsmem = (size_t)group * std::max(1, P.ndyn) * 16;
-                if (bsmem > S->broad_smem_set) {
-                    CC_CUDA(cudaFuncSetAttribute(ccdev::cc_broad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bsmem, 48 * 1024)));
-                    S->broad_smem_set = std::max<size_t>(bsmem, 48 * 1024);
+                if (!g_smem_opted[S->device & 63].broad) {
+                    CC_CUDA(cudaFuncSetAttribute(ccdev::cc_broad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    g_smem_opted[S->device & 63].broad = true;
                 }
                 ccdev::cc_broad_kernel<<<(m + group - 1) / group, 32 * bw, bsmem, cs>>>(P, group);
                 CC_CUDA(cudaGetLastError());
@@ -828,7 +832,7 @@ int launch_distance(cc_query* Q, const Plan& pl, bool pose_mode, const double* h
     CC_CUDA(Q->d_dist.reserve((size_t)chunk * outs_per_cfg)); CC_CUDA(Q->d_dpair.reserve((size_t)chunk * outs_per_cfg));
     CC_CUDA(Q->d_dpts.reserve((size_t)chunk * 6));
     const size_t d_smem = ccdev::kDistWarpSmemBytes * ccdev::kWarpsPerBlock;
-    static int dist_blocks_per_sm = 0;
+    int& dist_blocks_per_sm = g_smem_opted[S->device & 63].dist_blocks_per_sm;      // per device: the opt-in below is
     if (dist_blocks_per_sm == 0) {
         CC_CUDA(cudaFuncSetAttribute(ccdev::cc_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem));
         CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dist_blocks_per_sm, ccdev::cc_distance_kernel, ccdev::kWarpsPerBlock * 32, d_smem));
