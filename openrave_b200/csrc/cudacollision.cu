@@ -570,11 +570,16 @@ SmemOpted g_smem_opted[64];
 // memory or CC_TUNE_FK2=0 asks for the one-thread-per-configuration form (A/B: profiles/r02q_ab_fk2.log)
 int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
 {
-    static const bool tune_fk2 = !(getenv("CC_TUNE_FK2") && atoi(getenv("CC_TUNE_FK2")) == 0);
+    // the two-phase form pays when most links are rigidly attached to a few moving ones (PR2, arm + torso active: 8 varying steps,
+    // 33 constant ones: +2.5 %); a chain of varying steps only (HIRO-NX, every DOF active) runs its serial phase with a quarter of
+    // the block and loses 8 % (profiles/r02q_ab.log).  CC_TUNE_FK2 = 0 / 1 forces one form.
+    static const int tune_fk2 = getenv("CC_TUNE_FK2") ? atoi(getenv("CC_TUNE_FK2")) : -1;
+    const int nvary = P.npose - 1, nconst = P.nsteps - nvary;
+    const bool want_fk2 = tune_fk2 >= 0 ? tune_fk2 != 0 : ((P.flags & ccdev::kFlagPoseMode) != 0 || nconst >= 2 * nvary);
     const size_t fixed = ccdev::fk2_fixed_bytes(P.nq, P.nsteps, P.ndyn);
     const size_t row = (size_t)ccdev::fk2_row_doubles(P.npose) * sizeof(double);
     int group = 0;
-    if (tune_fk2)
+    if (want_fk2)
         for (int g = ccdev::kFkThreads; g >= 32; g -= 32)
             if (fixed + g * row <= (g == 32 ? 200u : 48u) * 1024u) { group = g; break; }       // <= 48 KB per block where possible (4 - 5 resident blocks)
     if (group > 0) {
