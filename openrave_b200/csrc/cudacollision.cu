@@ -655,6 +655,8 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     int chunk = (int)std::min<size_t>(262144, std::max<size_t>(1024, ((size_t)1 << 30) / per_cfg));
     static const int tune_chunk = getenv("CC_TUNE_CHUNK") ? atoi(getenv("CC_TUNE_CHUNK")) : 0;      // profiling knob: configurations per chunk
     if (tune_chunk > 0) chunk = (tune_chunk + 127) / 128 * 128;
+    else if (n >= 98304 && n <= chunk) chunk = ((n + 1) / 2 + 127) / 128 * 128;      // a single chunk overlaps nothing: two halves (+2.5 % on
+                                                                                      // the 100k-configuration WAM batch, profiles/r02r_chunk_sweep.log)
     chunk = std::min(chunk, (n + 127) / 128 * 128);
     const int nchunks = (n + chunk - 1) / chunk;
     const bool overlap = nchunks >= 2;
