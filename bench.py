@@ -642,7 +642,10 @@ def main():
         e2e_s = (time.perf_counter() - t0) / args.steps
     else:
         torch.cuda.synchronize()
-        dist.barrier()
+        # the other ranks wait on the HOST (gloo): an NCCL barrier parks a spinning kernel on their GPUs, and rank 0's kernels on those
+        # GPUs would then time-slice against another process's context (69 instead of 180+ M configs/s on two GPUs, profiles/r02t_*)
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
         e2e_s = 0.0
         if rank == 0:
             env_m, robot_m, _, _ = load_world(args.workload)
@@ -664,7 +667,7 @@ def main():
                      "kernel_launches_per_call": int((cc_m.GetStatistics()["launches"]) // (args.steps + 3))}
             bq_m.close()
             cc_m.DestroyEnvironment()
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         if rank != 0:
             v_last = d_verdict.cpu().numpy().astype(np.uint32)
     sampler.stop_flag = True
