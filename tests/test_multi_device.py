@@ -71,7 +71,8 @@ def _check_equal_to_single(devices, scene, manip, n):
     for e, r in ((env1, robot1), (env2, robot2)):
         mug = [x for x in e.GetBodies() if x.name == "mug1"]
         if mug:
-            mug[0].SetTransform(rm.t_mul([l for l in r.links if l.name == "wam4"][0].t, (rm.IDENT_Q, (0.0, 0.0, 0.25))))
+            near = r.GetLink("wam4") or r.GetLink("r_forearm_link") or r.links[-1]
+            mug[0].SetTransform(rm.t_mul(near.t, (rm.IDENT_Q, (0.0, 0.0, 0.25))))
     a2 = one.CheckCollisionBatch(robot1, q, active=active)
     b2 = many.CheckCollisionBatch(robot2, q, active=active)
     assert _same(a2, b2)

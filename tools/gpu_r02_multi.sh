@@ -7,7 +7,7 @@ N=${1:-2}
 TAG=${2:-r02m}
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 900 python -m pytest tests/test_multi_device.py -m gpu -q > gpurun_out/${TAG}_pytest_multi_n$N.log 2>&1; echo "multi-device pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest_multi_n$N.log
-timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench N=1 rc=$?"; cut -c1-160 gpurun_out/${TAG}_bench_n1.json
+[ -n "${SKIP_N1:-}" ] || timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench N=1 rc=$?"; cut -c1-160 gpurun_out/${TAG}_bench_n1.json
 for w in ${WORKLOADS:-pr2_pr2test1_1m}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --workload $w --no-cpu-baseline \
       > gpurun_out/${TAG}_bench_n${N}_$w.json 2> gpurun_out/${TAG}_bench_n${N}_$w.err; echo "bench N=$N $w rc=$?"
