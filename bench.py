@@ -612,10 +612,13 @@ def main():
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     ms = (sum(ms_steps) + (evs[-1][1].elapsed_time(e_tail) if world > 1 else 0.0)) / len(ms_steps)
     kernel_ms = ms
+    ms_per_rank = [ms]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allms = torch.empty(world, device="cuda")
+        dist.all_gather_into_tensor(allms, t)
+        ms_per_rank = [float(x) for x in allms.cpu()]
+        ms = max(ms_per_rank)               # the step of the slowest rank (GPUs of one box differ by a few per cent)
 
     # the report == NULL flavour the planners use (CC_BATCH_FIRST_HIT): same kernels, stops at the first contact
     from openrave_b200.checker import BATCH_FIRST_HIT
@@ -716,6 +719,7 @@ def main():
                            "bvh_nodes": bq.info.total_nodes, "tris": bq.info.total_tris,
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
                            "parallelism": "configs sharded, scene replicated (dp%d)" % world, "multi_device_e2e": multi,
+                           "ms_per_step_per_rank": [round(x, 4) for x in ms_per_rank],
                            "collective": (None if world == 1 else "one ncclAllGather of the results per step (12 B / configuration), overlapped with the "
                                           "next step's kernels; the last gather is waited for inside the timed region"),
                            "colliding_fraction": float((v_last != 0).mean()),
