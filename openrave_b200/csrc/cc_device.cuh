@@ -588,10 +588,8 @@ cc_fk_kernel(const __grid_constant__ Params P)
 
 // ------------------------------------------------------------------------------------------------ kernel 1, two-phase form
 // The same arithmetic as cc_fk_kernel, split so that most of it runs with every thread busy and with coalesced stores:
-//   phase 1  the VARYING steps only (8 of PR2's 41): (a) one thread per (configuration, step) computes L * J(q) * R — the sincos
-//            and two of the step's three products do not depend on the chain; (b) one thread per configuration multiplies down
-//            the chain, one product per step, and leaves every varying link's pose in shared memory ([configuration][pose]
-//            [7 doubles], rows padded to an odd length: conflict-free both ways);
+//   phase 1  one thread per configuration walks only the VARYING steps (8 of PR2's 41) and leaves every varying link's pose in
+//            shared memory ([configuration][pose][7 doubles], rows padded to an odd length: conflict-free both ways);
 //   phase 2  one thread per (configuration, link): a varying link's pose is read back, a rigidly attached link's pose is
 //            T_anchor * L (one product), then the FP32 R|t, the world AABB and the optional FP64 copy-out.  Consecutive threads
 //            write consecutive slots of one configuration's row, where the one-thread-per-configuration kernel scatters every
@@ -635,18 +633,7 @@ cc_fk2_kernel(const __grid_constant__ Params P, const int group)
     const int c0 = blockIdx.x * group;
     const int nc = P.n - c0 < group ? P.n - c0 : group;
     const bool pose_mode = (P.flags & kFlagPoseMode) != 0;
-    // ---- phase 1a: L * J(q) * R of every varying step, one thread per (configuration, step): the sincos and two of the three
-    // products of a step do not depend on the chain, only the last product does
-    if (!pose_mode) {
-        for (int it = threadIdx.x; it < nc * P.nsteps; it += blockDim.x) {
-            const int i = it / P.nsteps, sidx = it - i * P.nsteps;
-            const FkStep& st = s_steps[sidx];
-            if (st.flags & 16) continue;
-            pose_store(s_pose + (size_t)i * rowlen, st.pose_out, joint_transform(st, P.q + (size_t)(c0 + i) * P.ncols));
-        }
-    }
-    __syncthreads();
-    // ---- phase 1b: the chain itself, one thread per configuration: T_child = T_parent * (L J R), in place
+    // ---- phase 1: the varying steps, one thread per configuration
     for (int i = threadIdx.x; i < nc; i += blockDim.x) {
         const int c = c0 + i;
         if (P.flags & kFlagInitOutputs) {
@@ -668,7 +655,7 @@ cc_fk2_kernel(const __grid_constant__ Params P, const int group)
         for (int s = 0; s < P.nsteps; ++s) {
             const FkStep& st = s_steps[s];
             if (st.flags & 16) continue;
-            pose_store(row, st.pose_out, xf_mul(pose_load(row, st.pose_in), pose_load(row, st.pose_out)));
+            pose_store(row, st.pose_out, xf_mul(pose_load(row, st.pose_in), joint_transform(st, qrow)));
         }
     }
     __syncthreads();
