@@ -412,7 +412,8 @@ struct FkDst {
 
 // Emit one link pose: optional FP64 copy-out, FP32 R|t (matrixFromQuat, geometry.h:779-800) and the world AABB
 // of the link's root box, both into the dynamic slot `d` of configuration `c` (d < 0: only the copy-out).
-__device__ __forceinline__ void emit_link(const Params& P, const float* linkbox, const FkDst& D, int c, int l, int d, const Xf& T)
+__device__ __forceinline__ void emit_link_box(const Params& P, const FkDst& D, int c, int l, int d, const Xf& T,
+                                              float cx, float cy, float cz, float ex, float ey, float ez)
 {
     if (P.fk_out) {
         double* dst = P.fk_out + ((size_t)c * P.nq + l) * 8;
@@ -430,15 +431,20 @@ __device__ __forceinline__ void emit_link(const Params& P, const float* linkbox,
     dst[0] = make_float4(R[0], R[1], R[2], R[3]);
     dst[1] = make_float4(R[4], R[5], R[6], R[7]);
     dst[2] = make_float4(R[8], t[0], t[1], t[2]);
-    const float* lb = linkbox + 8 * d;
     const float reps = 1e-6f;
-    const float cx = lb[0], cy = lb[1], cz = lb[2], ex = lb[3], ey = lb[4], ez = lb[5];
     float4* ab = (float4*)(D.ab + (size_t)d * D.ab_stride);
     ab[0] = make_float4(fmaf(R[0], cx, fmaf(R[1], cy, fmaf(R[2], cz, t[0]))), fmaf(R[3], cx, fmaf(R[4], cy, fmaf(R[5], cz, t[1]))),
                         fmaf(R[6], cx, fmaf(R[7], cy, fmaf(R[8], cz, t[2]))), 0.f);
     ab[1] = make_float4((fabsf(R[0]) + reps) * ex + (fabsf(R[1]) + reps) * ey + (fabsf(R[2]) + reps) * ez,
                         (fabsf(R[3]) + reps) * ex + (fabsf(R[4]) + reps) * ey + (fabsf(R[5]) + reps) * ez,
                         (fabsf(R[6]) + reps) * ex + (fabsf(R[7]) + reps) * ey + (fabsf(R[8]) + reps) * ez, 0.f);
+}
+
+// (link boxes as an array of {cx cy cz ex ey ez . .} records)
+__device__ __forceinline__ void emit_link(const Params& P, const float* linkbox, const FkDst& D, int c, int l, int d, const Xf& T)
+{
+    const float* lb = linkbox + 8 * (d < 0 ? 0 : d);
+    emit_link_box(P, D, c, l, d, T, lb[0], lb[1], lb[2], lb[3], lb[4], lb[5]);
 }
 
 // L * J(value) * R of one joint (kinbody.cpp:2404-2478); the value rules follow kinbody.cpp:2149-2224, 2308-2386.
@@ -597,7 +603,9 @@ cc_fk_kernel(const __grid_constant__ Params P)
 //            long-scoreboard 14.4, profiles/r02i_fk_summary.md).
 __host__ __device__ inline size_t fk2_fixed_bytes(int nq, int nsteps, int ndyn)
 {
-    return ((size_t)nsteps * sizeof(FkStep) + (size_t)ndyn * 32 + (size_t)nq * 4 + 15) / 16 * 16;
+    // chain program | link -> slot | per item of phase 2 (link 0 + one per step), structure-of-arrays: 7 doubles of L, then
+    // {flags, pose_in, pose_out, child} | link boxes, structure-of-arrays (6 floats per dynamic slot)
+    return ((size_t)nsteps * sizeof(FkStep) + (size_t)nq * 4 + 15) / 16 * 16 + ((size_t)(nsteps + 1) * (56 + 16) + (size_t)ndyn * 24 + 15) / 16 * 16;
 }
 __host__ __device__ inline int fk2_row_doubles(int npose) { return (npose * 7) | 1; }
 
@@ -619,17 +627,32 @@ cc_fk2_kernel(const __grid_constant__ Params P, const int group)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FkStep* s_steps = (FkStep*)smem_raw;
-    float* s_linkbox = (float*)(s_steps + P.nsteps);
-    int32_t* s_emit = (int32_t*)(s_linkbox + 8 * P.ndyn);
+    int32_t* s_emit = (int32_t*)(s_steps + P.nsteps);
+    const int ni = P.nsteps + 1;                                    // items of phase 2 per configuration: link 0 + one per step
+    double* s_L = (double*)(smem_raw + ((size_t)P.nsteps * sizeof(FkStep) + (size_t)P.nq * 4 + 15) / 16 * 16);      // [7][ni]
+    int32_t* s_meta = (int32_t*)(s_L + 7 * ni);                     // [4][ni]: flags, pose_in, pose_out, child
+    float* s_lb = (float*)(s_meta + 4 * ni);                        // [6][ndyn]
     double* s_pose = (double*)(smem_raw + fk2_fixed_bytes(P.nq, P.nsteps, P.ndyn));
     const int rowlen = fk2_row_doubles(P.npose);
     {
         const int4* src = (const int4*)P.steps; int4* dst = (int4*)s_steps;
         for (int i = threadIdx.x; i < P.nsteps * (int)(sizeof(FkStep) / 16); i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < 8 * P.ndyn; i += blockDim.x) s_linkbox[i] = P.link_box[i];
         for (int i = threadIdx.x; i < P.nq; i += blockDim.x) s_emit[i] = P.emit_index[i];
+        for (int i = threadIdx.x; i < 6 * P.ndyn; i += blockDim.x) { const int k = i / P.ndyn, d = i - k * P.ndyn; s_lb[i] = P.link_box[8 * d + k]; }
     }
     __syncthreads();
+    // phase 2 reads its step constants with consecutive threads on consecutive steps: as 256-byte records every such load is a
+    // 32-way bank conflict (l1tex 87 % of peak, profiles/r02x_fk2_summary.md), as arrays it is conflict-free
+    for (int e = threadIdx.x; e < ni; e += blockDim.x) {
+        if (e == 0) {
+            s_meta[0] = 0; s_meta[ni] = 0; s_meta[2 * ni] = 0; s_meta[3 * ni] = 0;
+            for (int k = 0; k < 7; ++k) s_L[k * ni] = k == 0 ? 1.0 : 0.0;
+        } else {
+            const FkStep& st = s_steps[e - 1];
+            s_meta[e] = st.flags; s_meta[ni + e] = st.pose_in; s_meta[2 * ni + e] = st.pose_out; s_meta[3 * ni + e] = st.child;
+            for (int k = 0; k < 7; ++k) s_L[k * ni + e] = st.L[k];
+        }
+    }
     const int c0 = blockIdx.x * group;
     const int nc = P.n - c0 < group ? P.n - c0 : group;
     const bool pose_mode = (P.flags & kFlagPoseMode) != 0;
@@ -668,15 +691,24 @@ cc_fk2_kernel(const __grid_constant__ Params P, const int group)
         D.xf = P.xf32 + (size_t)c * P.ndyn * 12; D.xf_stride = 12;
         D.ab = P.aabb + (size_t)c * P.ndyn * 8; D.ab_stride = 8;
         D.save = nullptr; D.save_pose_stride = D.save_comp_stride = 0;
+        int l, d;
+        Xf T;
         if (pose_mode) {
-            if (s_emit[e] >= 0) emit_link(P, s_linkbox, D, c, e, s_emit[e], xf_load(P.q + ((size_t)c * P.nq + e) * 8));
-            continue;
+            l = e; d = s_emit[e];
+            if (d < 0) continue;
+            T = xf_load(P.q + ((size_t)c * P.nq + e) * 8);
+        } else {
+            const double* row = s_pose + (size_t)i * rowlen;
+            const int flags = s_meta[e];
+            l = s_meta[3 * ni + e]; d = s_emit[l];
+            if (flags & 16) {
+                Xf L; L.q0 = s_L[e]; L.q1 = s_L[ni + e]; L.q2 = s_L[2 * ni + e]; L.q3 = s_L[3 * ni + e];
+                L.tx = s_L[4 * ni + e]; L.ty = s_L[5 * ni + e]; L.tz = s_L[6 * ni + e];
+                T = xf_mul(pose_load(row, s_meta[ni + e]), L);
+            } else T = pose_load(row, s_meta[2 * ni + e]);          // (item 0: link 0, pose 0)
         }
-        const double* row = s_pose + (size_t)i * rowlen;
-        if (e == 0) { emit_link(P, s_linkbox, D, c, 0, s_emit[0], pose_load(row, 0)); continue; }
-        const FkStep& st = s_steps[e - 1];
-        const Xf T = (st.flags & 16) ? xf_mul(pose_load(row, st.pose_in), xf_load(st.L)) : pose_load(row, st.pose_out);
-        emit_link(P, s_linkbox, D, c, st.child, s_emit[st.child], T);
+        const int dd = d < 0 ? 0 : d;
+        emit_link_box(P, D, c, l, d, T, s_lb[dd], s_lb[P.ndyn + dd], s_lb[2 * P.ndyn + dd], s_lb[3 * P.ndyn + dd], s_lb[4 * P.ndyn + dd], s_lb[5 * P.ndyn + dd]);
     }
 }
 
