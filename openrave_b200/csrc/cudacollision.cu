@@ -658,7 +658,17 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
     else if (n >= 98304 && n <= chunk) chunk = ((n + 1) / 2 + 127) / 128 * 128;      // a single chunk overlaps nothing: two halves (+2.5 % on
                                                                                       // the 100k-configuration WAM batch, profiles/r02r_chunk_sweep.log)
     chunk = std::min(chunk, (n + 127) / 128 * 128);
-    const int nchunks = (n + chunk - 1) / chunk;
+    // host-buffer batches of three chunks or more start with a quarter and a half chunk: the first kernels wait for their
+    // slice's H2D copy (16.8 MB per full PR2 chunk), a short first slice gets the device going sooner (CC_TUNE_RAMP=0: off)
+    static const bool tune_ramp = !(getenv("CC_TUNE_RAMP") && atoi(getenv("CC_TUNE_RAMP")) == 0);
+    std::vector<int> sizes;
+    {
+        const bool ramp = tune_ramp && hio && hio->in && n >= 3 * chunk && !fk_only;
+        int left = n;
+        if (ramp) { sizes.push_back(chunk / 4 / 128 * 128); sizes.push_back(chunk / 2 / 128 * 128); left -= sizes[0] + sizes[1]; }
+        while (left > 0) { sizes.push_back(std::min(chunk, left)); left -= sizes.back(); }
+    }
+    const int nchunks = (int)sizes.size();
     const bool overlap = nchunks >= 2;
     static const int nlanes = std::min(kMaxLanes, std::max(2, getenv("CC_TUNE_LANES") ? atoi(getenv("CC_TUNE_LANES")) : 4));     // pipeline lanes: 4 > 3 > 2 by about 1 % (profiles/r02n_ab.log)
     static const int tune_skip_fk = getenv("CC_TUNE_SKIP_FK") ? atoi(getenv("CC_TUNE_SKIP_FK")) : 0;  // profiling knob: FK only for the first
@@ -724,9 +734,9 @@ int launch(cc_query* Q, const Plan& pl, bool use_hoisted, const double* d_q, int
                                 cudaMemcpyDeviceToHost, cs);
         return e;
     };
-    int ci = 0;
-    for (int off = 0; off < n; off += chunk, ++ci) {
-        const int m = std::min(chunk, n - off);
+    int off = 0;
+    for (int ci = 0; ci < nchunks; off += sizes[ci], ++ci) {
+        const int m = sizes[ci];
         const int k = overlap ? (ci % nlanes) : 0;
         cudaStream_t cs = overlap ? S->lane_stream[k] : st;
         if (hio && hio->in && row_doubles > 0)
