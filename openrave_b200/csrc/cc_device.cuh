@@ -51,8 +51,8 @@ constexpr int kFkThreads = 128;
 #ifndef CC_LD256
 #define CC_LD256 1           // 256-bit loads (LDG.E.256, sm_100) for the 32-byte BVH nodes and boxes (0: pairs of 128-bit loads, A/B)
 #endif
-#ifndef CC_SPLIT_LANES
-#define CC_SPLIT_LANES 1     // 1: a descent iteration with <= 16 items gives every item two lanes, one per child (0: one lane per item, A/B)
+#ifndef CC_OUT_SELECT
+#define CC_OUT_SELECT 0      // 1: the descent builds its outputs with selects instead of divergent branches (A/B)
 #endif
 #ifndef CC_TRIQ_CAP
 #define CC_TRIQ_CAP 96
@@ -1199,21 +1199,12 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         __syncwarp();
                         if (slot_dead) { sp = filter_queue(stack, sp, slot_dead, lane, lt_mask); if (sp == 0) continue; }
                     }
-                    // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other).  With 16 items or fewer
-                    // (the first levels under a candidate pair, the last ones before the stack runs dry: 20 of 32 lanes are busy on
-                    // average) an item takes TWO lanes, one per child: one box test per lane instead of two, the same outputs in the
-                    // same order
-#if CC_SPLIT_LANES
-                    const bool two_lanes = sp <= 16;
-#else
-                    const bool two_lanes = false;
-#endif
-                    const int n = two_lanes ? sp : (sp < 32 ? sp : 32);
+                    // ---- pop up to 32 items; each is (children x, x+1 of one tree) x (node y of the other)
+                    const int n = sp < 32 ? sp : 32;
                     ++iters;
-                    const int my = two_lanes ? (lane >> 1) : lane;
-                    const bool valid = my < n;
+                    const bool valid = lane < n;
                     uint2 it = make_uint2(0u, 0u);
-                    if (valid) it = stack[sp - 1 - my];
+                    if (valid) it = stack[sp - 1 - lane];
                     sp -= n;
                     __syncwarp();
                     uint32_t of = 0u;      // bit 0 / 1: child 0 / 1 goes to the triangle queue, bit 2 / 3: child 0 / 1 is pushed back as an item
@@ -1222,52 +1213,67 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         const uint32_t sbits = it.x & 0xfc000000u;
                         const uint32_t x = it.x & 0x3ffffffu, y = it.y & 0x7fffffffu;
                         const bool side = (it.y >> 31) != 0u;                  // false: x is in tree A, true: x is in tree B
+#if CC_LD256
+                        // a node is 32 bytes: one 256-bit load each (3 instead of 6 loads per item, half the L1 tag lookups)
+                        const Box8 n0 = ld_box(&P.nodes[2 * x]), n1 = ld_box(&P.nodes[2 * x + 2]), no = ld_box(&P.nodes[2 * y]);
+                        const float4 c0a = n0.c, c0b = n0.e, c1a = n1.c, c1b = n1.e, oa = no.c, ob = no.e;
+#else
+                        const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
+                        const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
+                        const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
+#endif
                         const float* rt = slot_rt + 24 * (it.x >> 26) + (side ? 12 : 0);      // maps the other node into the children's frame
                         float R[9], t[3];
 #pragma unroll
                         for (int k = 0; k < 9; ++k) R[k] = rt[k];
                         t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-                        // a surviving child: two leaves -> triangle queue; else split the larger box (|e|^2 of the child against the
-                        // other node's, PQP.cpp:539-544; any rule is verdict-neutral)
-                        auto child_out = [&](int ch, int lc, float sc, int lo, float so) {
-                            uint2 out;
-                            const bool tq = lc < 0 && lo < 0;
-                            if (tq) {
-                                out = side ? make_uint2((uint32_t)(~lo) | sbits, (uint32_t)(~lc))
-                                           : make_uint2((uint32_t)(~lc) | sbits, (uint32_t)(~lo));
-                            } else if (lo < 0 || (lc >= 0 && sc > so)) {
-                                out = make_uint2((uint32_t)lc | sbits, it.y);                                     // split the child
-                            } else {
-                                out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));     // split the other
+                        if (counters) n_bv += 2;
+                        const int lo = __float_as_int(oa.w);
+                        bool ov0, ov1;
+                        box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
+                                         oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
+#if CC_OUT_SELECT
+                        // branch-free form of the loop below (selects instead of divergent paths)
+                        {
+                            const uint32_t flip = side ? 0u : 0x80000000u;
+                            const bool ol = lo < 0;
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) {
+                                const bool ov = ch ? ov1 : ov0;
+                                const int lc = __float_as_int(ch ? c1a.w : c0a.w);
+                                const float sc = ch ? c1b.w : c0b.w;
+                                const bool cl = lc < 0;
+                                const bool tq = ov & cl & ol;
+                                const bool splitc = ol | (!cl & (sc > ob.w));
+                                const uint32_t ta = side ? (uint32_t)(~lo) : (uint32_t)(~lc), tb = side ? (uint32_t)(~lc) : (uint32_t)(~lo);
+                                const uint32_t px = splitc ? (uint32_t)lc : (uint32_t)lo;
+                                const uint32_t py = splitc ? it.y : ((x + ch) | flip);
+                                const uint2 out = make_uint2((tq ? ta : px) | sbits, tq ? tb : py);
+                                if (ch) o1 = out; else o0 = out;
+                                of |= (tq ? 1u : (ov ? 4u : 0u)) << ch;
                             }
-                            if (ch) o1 = out; else o0 = out;
-                            of |= (tq ? 1u : 4u) << ch;
-                        };
-                        if (two_lanes) {
-                            const int ch = lane & 1;
-                            const Box8 nc = ld_box(&P.nodes[2 * (x + ch)]), no = ld_box(&P.nodes[2 * y]);
-                            if (counters) n_bv += 1;
-                            bool ova, ovb;      // (the pair form with the same box twice: identical arithmetic, the duplicate folds away)
-                            box_overlap_pair(R, t, nc.c.x, nc.c.y, nc.c.z, nc.e.x, nc.e.y, nc.e.z, nc.c.x, nc.c.y, nc.c.z, nc.e.x, nc.e.y, nc.e.z,
-                                             no.c.x, no.c.y, no.c.z, no.e.x, no.e.y, no.e.z, ova, ovb);
-                            if (ova) child_out(ch, __float_as_int(nc.c.w), nc.e.w, __float_as_int(no.c.w), no.e.w);
-                        } else {
-#if CC_LD256
-                            // a node is 32 bytes: one 256-bit load each (3 instead of 6 loads per item, half the L1 tag lookups)
-                            const Box8 n0 = ld_box(&P.nodes[2 * x]), n1 = ld_box(&P.nodes[2 * x + 2]), no = ld_box(&P.nodes[2 * y]);
-                            const float4 c0a = n0.c, c0b = n0.e, c1a = n1.c, c1b = n1.e, oa = no.c, ob = no.e;
-#else
-                            const float4 c0a = __ldg(&P.nodes[2 * x]), c0b = __ldg(&P.nodes[2 * x + 1]);
-                            const float4 c1a = __ldg(&P.nodes[2 * x + 2]), c1b = __ldg(&P.nodes[2 * x + 3]);
-                            const float4 oa = __ldg(&P.nodes[2 * y]), ob = __ldg(&P.nodes[2 * y + 1]);
-#endif
-                            if (counters) n_bv += 2;
-                            bool ov0, ov1;
-                            box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
-                                             oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
-                            if (ov0) child_out(0, __float_as_int(c0a.w), c0b.w, __float_as_int(oa.w), ob.w);
-                            if (ov1) child_out(1, __float_as_int(c1a.w), c1b.w, __float_as_int(oa.w), ob.w);
                         }
+#else
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            if (ch ? ov1 : ov0) {
+                                const int lc = __float_as_int(ch ? c1a.w : c0a.w);
+                                const float sc = ch ? c1b.w : c0b.w;            // |e|^2 of the child, of the other node: ob.w
+                                uint2 out;
+                                const bool tq = lc < 0 && lo < 0;
+                                if (tq) {
+                                    out = side ? make_uint2((uint32_t)(~lo) | sbits, (uint32_t)(~lc))
+                                               : make_uint2((uint32_t)(~lc) | sbits, (uint32_t)(~lo));
+                                } else if (lo < 0 || (lc >= 0 && sc > ob.w)) {
+                                    out = make_uint2((uint32_t)lc | sbits, it.y);                                     // split the child
+                                } else {
+                                    out = make_uint2((uint32_t)lo | sbits, (x + ch) | (side ? 0u : 0x80000000u));     // split the other
+                                }
+                                if (ch) o1 = out; else o0 = out;
+                                of |= (tq ? 1u : 4u) << ch;
+                            }
+                        }
+#endif
                     }
                     const bool tq0 = (of & 1u) != 0u, tq1 = (of & 2u) != 0u, ps0 = (of & 4u) != 0u, ps1 = (of & 8u) != 0u;
                     const unsigned t0m = __ballot_sync(kFull, tq0), t1m = __ballot_sync(kFull, tq1);
