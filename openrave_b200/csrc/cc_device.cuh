@@ -51,9 +51,6 @@ constexpr int kFkThreads = 128;
 #ifndef CC_LD256
 #define CC_LD256 1           // 256-bit loads (LDG.E.256, sm_100) for the 32-byte BVH nodes and boxes (0: pairs of 128-bit loads, A/B)
 #endif
-#ifndef CC_OUT_SELECT
-#define CC_OUT_SELECT 0      // 1: the descent builds its outputs with selects instead of divergent branches (A/B)
-#endif
 #ifndef CC_TRIQ_CAP
 #define CC_TRIQ_CAP 96
 #endif
@@ -1232,28 +1229,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                         bool ov0, ov1;
                         box_overlap_pair(R, t, c0a.x, c0a.y, c0a.z, c0b.x, c0b.y, c0b.z, c1a.x, c1a.y, c1a.z, c1b.x, c1b.y, c1b.z,
                                          oa.x, oa.y, oa.z, ob.x, ob.y, ob.z, ov0, ov1);
-#if CC_OUT_SELECT
-                        // branch-free form of the loop below (selects instead of divergent paths)
-                        {
-                            const uint32_t flip = side ? 0u : 0x80000000u;
-                            const bool ol = lo < 0;
-#pragma unroll
-                            for (int ch = 0; ch < 2; ++ch) {
-                                const bool ov = ch ? ov1 : ov0;
-                                const int lc = __float_as_int(ch ? c1a.w : c0a.w);
-                                const float sc = ch ? c1b.w : c0b.w;
-                                const bool cl = lc < 0;
-                                const bool tq = ov & cl & ol;
-                                const bool splitc = ol | (!cl & (sc > ob.w));
-                                const uint32_t ta = side ? (uint32_t)(~lo) : (uint32_t)(~lc), tb = side ? (uint32_t)(~lc) : (uint32_t)(~lo);
-                                const uint32_t px = splitc ? (uint32_t)lc : (uint32_t)lo;
-                                const uint32_t py = splitc ? it.y : ((x + ch) | flip);
-                                const uint2 out = make_uint2((tq ? ta : px) | sbits, tq ? tb : py);
-                                if (ch) o1 = out; else o0 = out;
-                                of |= (tq ? 1u : (ov ? 4u : 0u)) << ch;
-                            }
-                        }
-#else
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
                             if (ch ? ov1 : ov0) {
@@ -1273,7 +1248,6 @@ cc_traverse_kernel(const __grid_constant__ Params P)
                                 of |= (tq ? 1u : 4u) << ch;
                             }
                         }
-#endif
                     }
                     const bool tq0 = (of & 1u) != 0u, tq1 = (of & 2u) != 0u, ps0 = (of & 4u) != 0u, ps1 = (of & 8u) != 0u;
                     const unsigned t0m = __ballot_sync(kFull, tq0), t1m = __ballot_sync(kFull, tq1);
