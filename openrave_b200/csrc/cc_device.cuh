@@ -36,7 +36,10 @@
 
 namespace ccdev {
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef CC_WARPS_PER_BLOCK
+#define CC_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = CC_WARPS_PER_BLOCK;
 #ifndef CC_MIN_BLOCKS
 #define CC_MIN_BLOCKS 7
 #endif
