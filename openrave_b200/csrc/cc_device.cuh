@@ -37,13 +37,13 @@
 namespace ccdev {
 
 #ifndef CC_WARPS_PER_BLOCK
-#define CC_WARPS_PER_BLOCK 4
+#define CC_WARPS_PER_BLOCK 2     // 2 warps per block, 14 blocks per SM: a block's slot frees as soon as its two warps run dry (+0.1 .. 0.4 % over 4 x 7, profiles/r02B_ab.log)
 #endif
 constexpr int kWarpsPerBlock = CC_WARPS_PER_BLOCK;
 #ifndef CC_MIN_BLOCKS
-#define CC_MIN_BLOCKS 7
+#define CC_MIN_BLOCKS 14
 #endif
-constexpr int kMinBlocksPerSM = CC_MIN_BLOCKS;   // shared memory allows 7 blocks (28 warps) per SM: the register cap follows that (73), not 8 blocks (64)
+constexpr int kMinBlocksPerSM = CC_MIN_BLOCKS;   // shared memory allows 28 warps per SM (14 blocks of 2): the register cap follows that (73), not 32 warps (64)
 constexpr int kFkThreads = 128;
 #ifndef CC_STACK_CAP
 #define CC_STACK_CAP 320
