@@ -28,8 +28,10 @@ def raw_metrics(rep):
 
 
 def main():
+    # harvest_r02.py TAG [configs_per_launch] [workload] [configs_per_step]; the captures of a workload other than the default are
+    # named TAG_<workload>_prof_*.ncu-rep and TAG_<workload>_launches.csv (the TAG passed here is then "TAG_<workload>")
     t = sys.argv[1]
-    workload = "pr2_pr2test1_1m"
+    workload = sys.argv[3] if len(sys.argv) > 3 else "pr2_pr2test1_1m"
     shutil.copy(os.path.join(G, "%s_launches.csv" % t), os.path.join(P, "%s_launches.csv" % t))
     has_broad = os.path.isfile(os.path.join(G, "%s_prof_broad.ncu-rep" % t))
     for k in ("trav", "fk") + (("broad",) if has_broad else ()):
@@ -60,7 +62,7 @@ def main():
     mt, mf = raw_metrics(os.path.join(G, "%s_prof_trav.ncu-rep" % t)), raw_metrics(os.path.join(G, "%s_prof_fk.ncu-rep" % t))
     mb = raw_metrics(os.path.join(G, "%s_prof_broad.ncu-rep" % t)) if has_broad else {}
     cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
-    n_step = 1000000
+    n_step = int(sys.argv[4]) if len(sys.argv) > 4 else 1000000
     chunks = (n_step + cfg - 1) // cfg
     wt, wf = float(mt["smsp__inst_executed.sum"]), float(mf["smsp__inst_executed.sum"])
     wb = float(mb["smsp__inst_executed.sum"]) if has_broad else 0.0
@@ -70,7 +72,7 @@ def main():
         return float(m[k]) if m.get(k) not in (None, "") else None
 
     phys = {"workload": workload,
-            "kernels": "cc_traverse_kernel + cc_fk_kernel + cc_broad_kernel: every kernel of the bench step (profiles/%s_launches.csv: %d + %d + %d launches)" % (
+            "kernels": "cc_traverse_kernel + cc_fk_kernel / cc_fk2_kernel + cc_broad_kernel: every kernel of the bench step (profiles/%s_launches.csv: %d + %d + %d launches)" % (
                 t, nlaunch["trav"], nlaunch["fk"], nlaunch["broad"]),
             "source": "profiles/%s_trav_summary.md + profiles/%s_fk_summary.md (ncu --set full --clock-control none --import-source on, at HEAD, "
                       "one %d-configuration chunk each); SASS with execution counts in profiles/%s_trav_sass.txt" % (t, t, cfg, t),
@@ -99,7 +101,7 @@ def main():
                "source": "profiles/%s_trav_traffic.json + profiles/%s_fk_traffic.json (ncu --set full at HEAD, one %d-configuration chunk each)" % (t, t, cfg),
                "chunks_per_step": chunks, "configurations_per_captured_launch": cfg, "trav_dram_bytes_per_launch": a, "fk_dram_bytes_per_launch": b,
                "broad_dram_bytes_per_launch": cbytes, "dram_bytes_per_step": scale * (a + b + cbytes),
-               "note": "physical DRAM bytes of one 1M-configuration bench step = (chunks scaled to 1M configurations) x (cc_fk_kernel + cc_broad_kernel + cc_traverse_kernel)"}
+               "note": "physical DRAM bytes of one bench step = (chunks scaled to the step's configurations) x (cc_fk_kernel + cc_broad_kernel + cc_traverse_kernel)"}
     json.dump(traffic, open(os.path.join(P, "traffic_%s.json" % workload), "w"), indent=1)
     print(json.dumps(phys, indent=1))
     print(json.dumps(traffic, indent=1))
