@@ -347,7 +347,7 @@ int cc_query_get_work_trace(cc_query* q, uint32_t* out_iterations, int n);
  * with tracing on, three timed events per chunk are recorded on the chunk's lane.  cc_scene_get_timeline (synchronises)
  * returns, for every chunk of the last traced call, milliseconds since the call's start event: {the lane became free for this
  * chunk, its FK kernel ended, its traversal kernel ended} and the chunk's lane.  Overlapping [FK end, traversal end] intervals
- * of consecutive chunks are the two-stream overlap bench.py's roofline accounting relies on (profiles/ holds the records). */
+ * of consecutive chunks are the multi-stream overlap bench.py's roofline accounting relies on (profiles/ holds the records). */
 int cc_scene_trace_timeline(cc_scene* s, int enabled);
 int cc_scene_get_timeline(cc_scene* s, double* out_ms /* [chunks][3] */, int32_t* out_lane /* [chunks], may be NULL */,
                           int max_chunks, int* out_chunks);

@@ -1,20 +1,26 @@
 // cc_device.cuh — device side of the batched collision checker (sm_100a only).
 //
-// Two kernels per chunk of configurations, both hand-written for B200:
+// Three kernels per chunk of configurations, all hand-written for B200:
 //
 //   cc_fk_kernel        ONE THREAD per configuration.  The FK chain program is uniform across the warp, so
 //                       KinBody::SetDOFValues' joint loop (kinbody.cpp:2286-2481) runs divergence-free in FP64 with
 //                       the running transform in registers (the chain is walked depth-first and pruned to the links
 //                       the bound pairs need; only branch-point links are parked in a coalesced SoA scratch).  Every
 //                       needed link pose is emitted as FP32 R|t (base-centred) plus its world AABB.
-//   cc_traverse_kernel  persistent, ONE WARP per configuration: link-AABB x {static-AABB, link-AABB} broadphase over
-//                       the bound pair table in reference order, 32 pairs per step -> dense batches of 32 candidate
-//                       root pairs (relative pose + 15-axis SAT of the root boxes) -> warp-cooperative dual-BVH descent.
-//                       A stack item names the two CHILDREN of the node being split plus the other node, so one pop
-//                       is one 64-byte + one 32-byte fetch and two independent box tests per lane; leaf x leaf hits
-//                       are parked in a triangle queue and tested 32 at a time with PQP's 17-axis triangle SAT
-//                       (pqp/PQP.cpp:350-459) in FP32.  All warp state lives in registers; the stack, the triangle
-//                       queue and the per-pair relative poses live in 5.7 KB of shared memory per warp.
+//   cc_fk2_kernel       the same arithmetic in two phases (varying steps per configuration, then one thread per
+//                       (configuration, link) with coalesced stores): chosen per plan when rigidly attached links
+//                       dominate, and for pose mode.
+//   cc_broad_kernel     world-AABB test of every (configuration, pair) + certificate-cell lookup -> one candidate bit per
+//                       pair: a block per 32 configurations, their boxes staged in shared memory as 15-bit fixed point,
+//                       a warp per word of 32 pairs.
+//   cc_traverse_kernel  persistent, ONE WARP per configuration: candidate bits (or, for small split batches, an in-warp
+//                       link-AABB x {static-AABB, link-AABB} broadphase over the bound pair table in reference order)
+//                       -> dense batches of 32 candidate root pairs (relative pose + SAT of the root boxes) ->
+//                       warp-cooperative dual-BVH descent.  A stack item names the two CHILDREN of the node being split
+//                       plus the other node, so one pop is three 256-bit node loads and two independent box tests per
+//                       lane; leaf x leaf hits are parked in a triangle queue and tested 32 at a time with PQP's 17-axis
+//                       triangle SAT (pqp/PQP.cpp:350-459) in FP32.  All warp state lives in registers; the stack, the
+//                       triangle queues and the per-pair relative poses live in 7.5 KB of shared memory per warp.
 //
 // Conservative pruning: node boxes are inflated at build time and |R| entries get +1e-6 like
 // OBB_Disjoint.h:67-78, so FP32 rounding can never prune a true contact; the verdict is the OR of the
