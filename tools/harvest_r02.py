@@ -21,10 +21,15 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 
-def raw_metrics(rep):
+def raw_metrics(rep, want_grid=None):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    return dict(zip(rows[0], rows[2]))
+    gi = rows[0].index("launch__grid_size")
+    # several launches captured (bind-time probes, certificate grids, the bench chunks): the one whose grid is the bench chunk's,
+    # else the largest
+    match = [r for r in rows[2:] if want_grid and int(float(r[gi] or 0)) == want_grid]
+    best = match[0] if match else max(rows[2:], key=lambda r: float(r[gi] or 0))
+    return dict(zip(rows[0], best))
 
 
 def main():
@@ -34,9 +39,11 @@ def main():
     workload = sys.argv[3] if len(sys.argv) > 3 else "pr2_pr2test1_1m"
     shutil.copy(os.path.join(G, "%s_launches.csv" % t), os.path.join(P, "%s_launches.csv" % t))
     has_broad = os.path.isfile(os.path.join(G, "%s_prof_broad.ncu-rep" % t))
+    cfg0 = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
     for k in ("trav", "fk") + (("broad",) if has_broad else ()):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
-                               os.path.join(G, "%s_prof_%s.ncu-rep" % (t, k)), os.path.join(P, "%s_%s" % (t, k))])
+                               os.path.join(G, "%s_prof_%s.ncu-rep" % (t, k)), os.path.join(P, "%s_%s" % (t, k))] +
+                              ([str((cfg0 + 127) // 128)] if k == "fk" else []))
     sass = subprocess.run(["ncu", "-i", os.path.join(G, "%s_prof_trav.ncu-rep" % t), "--page", "source", "--csv", "--print-source", "sass"],
                           capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(sass)))
@@ -59,12 +66,19 @@ def main():
                     dur[k] += float(r[-1])
                 except ValueError:
                     pass
-    mt, mf = raw_metrics(os.path.join(G, "%s_prof_trav.ncu-rep" % t)), raw_metrics(os.path.join(G, "%s_prof_fk.ncu-rep" % t))
-    mb = raw_metrics(os.path.join(G, "%s_prof_broad.ncu-rep" % t)) if has_broad else {}
     cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
+    mt = raw_metrics(os.path.join(G, "%s_prof_trav.ncu-rep" % t))
+    mf = raw_metrics(os.path.join(G, "%s_prof_fk.ncu-rep" % t), want_grid=(cfg + 127) // 128)      # cc_fk_kernel: 128 configurations per block
+    mb = raw_metrics(os.path.join(G, "%s_prof_broad.ncu-rep" % t)) if has_broad else {}
     n_step = int(sys.argv[4]) if len(sys.argv) > 4 else 1000000
     chunks = (n_step + cfg - 1) // cfg
     wt, wf = float(mt["smsp__inst_executed.sum"]), float(mf["smsp__inst_executed.sum"])
+    # the captured FK launch may be one of the certificate builder's (another batch size): cc_fk_kernel runs one configuration per
+    # thread, 128 per block, so its own size is known; scale its counters to the bench chunk
+    fk_scale = 1.0
+    if "cc_fk_kernel" in mf.get("Kernel Name", "") and float(mf["launch__grid_size"]) * 128 != cfg:
+        fk_scale = cfg / (float(mf["launch__grid_size"]) * 128.0)
+        wf *= fk_scale
     wb = float(mb["smsp__inst_executed.sum"]) if has_broad else 0.0
     last = min(cfg, n_step - (chunks - 1) * cfg)
 
@@ -77,6 +91,8 @@ def main():
             "source": "profiles/%s_trav_summary.md + profiles/%s_fk_summary.md (ncu --set full --clock-control none --import-source on, at HEAD, "
                       "one %d-configuration chunk each); SASS with execution counts in profiles/%s_trav_sass.txt" % (t, t, cfg, t),
             "configurations_per_captured_launch": cfg,
+            "fk_capture_note": (None if fk_scale == 1.0 else "the captured cc_fk_kernel launch is one of the certificate builder's (%d configurations, every link "
+                                "emitted); its counters are scaled to the bench chunk" % int(round(cfg / fk_scale))),
             "warp_instructions_per_configuration": (wt + wf + wb) / cfg,
             "warp_instructions_per_configuration_broadphase": wb / cfg,
             "warp_instructions_per_configuration_traversal": wt / cfg,
@@ -94,7 +110,7 @@ def main():
                         "per-chunk link poses the FK kernel hands to the traversal kernel"}
     json.dump(phys, open(os.path.join(P, "physical_%s.json" % workload), "w"), indent=1)
     a = json.load(open(os.path.join(P, "%s_trav_traffic.json" % t)))["dram_bytes_per_launch"]
-    b = json.load(open(os.path.join(P, "%s_fk_traffic.json" % t)))["dram_bytes_per_launch"]
+    b = json.load(open(os.path.join(P, "%s_fk_traffic.json" % t)))["dram_bytes_per_launch"] * fk_scale
     cbytes = json.load(open(os.path.join(P, "%s_broad_traffic.json" % t)))["dram_bytes_per_launch"] if has_broad else 0.0
     scale = (chunks - 1) + last / float(cfg)
     traffic = {"workload": workload,

@@ -60,12 +60,16 @@ def main():
             v, u = float(vals[key]), un[key].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
         rd, wr = tobytes("dram__bytes_read.sum"), tobytes("dram__bytes_write.sum")
-        traffic = {"kernel": kname, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+        grid = int(float(vals.get("launch__grid_size", "0") or 0))
+        want = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+        if traffic and (traffic.get("grid_size") == want or (grid != want and grid <= traffic.get("grid_size", -1))):
+            continue                      # several launches captured: the one with the wanted grid (argv[3]), else the largest
+        traffic = {"grid_size": grid, "launch_index": li, "kernel": kname, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                    "gpu_time_ms_under_ncu": float(vals["gpu__time_duration.sum"]) * (1e-3 if un["gpu__time_duration.sum"] == "us" else 1.0)
                    if un["gpu__time_duration.sum"] in ("ms", "us") else vals["gpu__time_duration.sum"],
                    "l2_hit_rate_pct": float(vals.get("lts__t_sector_hit_rate.pct", "nan")), "source": rep.split("/")[-1]}
     src = ncu_csv(rep, "source")
-    if len(src) > 2:
+    if len(src) > 2 and "# Samples" in src[1]:
         h = src[1]
         d = src[2:]
         isamp, iex, ith, isrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Avg. Threads Executed"), h.index("Source")
