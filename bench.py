@@ -593,25 +593,48 @@ def main():
     launches0 = cc.GetStatistics()["launches"]
     evs = []
     t_wall0 = time.perf_counter()
+    # The path shards with NO data-path collective (independent configurations, replicated scene: SURVEY.md 8e): every rank's
+    # results stay on its GPU, which is what `value` times.  The device-consumer flavour — the results of all ranks gathered on
+    # every GPU — is timed separately below (config.device_consumer): at 8 GPUs each rank receives 96 MB per step, which streams
+    # through the L2 the BVH lives in and costs 4 % (profiles/r02F_*).
     for i in range(args.steps):
         flush.fill_(1)                      # evict q, results and the BVH from L2 between timed steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         step_device(i)
         e1.record(stream)
-        gather_results(i)
         evs.append((e0, e1))
-    e_tail = torch.cuda.Event(enable_timing=True)
-    drain_gathers()                         # (N > 1) the last steps' gathers are not hidden by a following step: their time counts
-    e_tail.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches_timed = cc.GetStatistics()["launches"] - launches0    # cc_fk_kernel + cc_traverse_kernel per chunk
+    launches_timed = cc.GetStatistics()["launches"] - launches0    # FK + broadphase + traversal kernel per chunk
     ms_steps = [a.elapsed_time(b) for a, b in evs]
-    ms = (sum(ms_steps) + (evs[-1][1].elapsed_time(e_tail) if world > 1 else 0.0)) / len(ms_steps)
+    ms = sum(ms_steps) / len(ms_steps)
     kernel_ms = ms
+    gathered_ms = None
+    if world > 1:
+        # device consumer: ONE ncclAllGather of the results per step, overlapped with the next step's kernels (double-buffered
+        # results); the last gather is waited for inside the timed region
+        evg = []
+        kg = max(3, args.steps // 2)
+        dist.barrier()
+        for i in range(kg):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_device(i)
+            e1.record(stream)
+            gather_results(i)
+            evg.append((e0, e1))
+        e_tail = torch.cuda.Event(enable_timing=True)
+        drain_gathers()
+        e_tail.record(stream)
+        torch.cuda.synchronize()
+        gathered_ms = (sum(a.elapsed_time(b) for a, b in evg) + evg[-1][1].elapsed_time(e_tail)) / kg
+        tg = torch.tensor([gathered_ms], device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gathered_ms = float(tg.item())
     ms_per_rank = [ms]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -720,8 +743,11 @@ def main():
                            "l2": "flushed between timed steps (256 MB write)", "fk": "f64 on device, narrowphase f32",
                            "parallelism": "configs sharded, scene replicated (dp%d)" % world, "multi_device_e2e": multi,
                            "ms_per_step_per_rank": [round(x, 4) for x in ms_per_rank],
-                           "collective": (None if world == 1 else "one ncclAllGather of the results per step (12 B / configuration), overlapped with the "
-                                          "next step's kernels; the last gather is waited for inside the timed region"),
+                           "collective": None,
+                           "device_consumer": (None if world == 1 else {
+                               "configs_per_s": world * n / (gathered_ms / 1000.0), "ms_per_step": gathered_ms,
+                               "collective": "one ncclAllGather of the results per step (12 B / configuration), overlapped with the next "
+                                             "step's kernels; the last gather is waited for inside the timed region"}),
                            "colliding_fraction": float((v_last != 0).mean()),
                            "first_hit_mode_configs_per_s": world * n / (first_hit_ms / 1000.0),
                            "dynamic_scene_configs_per_s": world * n / (dynamic_ms / 1000.0),
