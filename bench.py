@@ -17,7 +17,15 @@ A "step" is one pass of the hot path over one batch of synthetic uniform-random 
              measured HBM copy bandwidth.  The reference has no broadphase and enumerates all contacts, the
              kernel culls and stops at the first contact per pair, so `frac` can exceed 1: it measures how much
              of the reference's work the kernel avoids, not DRAM utilisation (`traffic` is the physical bytes).
-  cpu_baseline  the oracle (reference-PQP-linked when oracle/_ref exists) timed single-threaded on this host
+             `roofline.physical` holds the physical fractions, each traceable to a file under profiles/ taken at HEAD
+             (tools/harvest_r02.py): issue_frac (warp instructions per configuration x configs/s / issue slots),
+             lane_efficiency (threads per executed instruction / 32), dram_frac (DRAM bytes per step / step time / HBM peak)
+  cpu_baseline  the oracle (reference-PQP-linked when oracle/_ref exists) timed single-threaded on this host, plus `parity`:
+             the CUDA results of the timed batch against that oracle on all host cores (a bounded sample) and the committed
+             full-size sweep (profiles/r02_parity_<workload>.json)
+  N > 1      `value`: every rank checks its own shard, results stay on its GPU (no data-path collective), max over ranks;
+             `config.device_consumer`: the same with one overlapped ncclAllGather of the results per step;
+             `e2e`: ONE process (rank 0) drives all N GPUs through a multi-device scene and one cc_check_batch call
 """
 import argparse
 import json
