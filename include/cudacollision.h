@@ -369,6 +369,13 @@ int cc_scene_get_stats(const cc_scene* s, cc_stats* out);
 int cc_debug_build_bvh(const double* vertices, int nvertices, const int32_t* triangles, int ntriangles, float* out_nodes,
                        int max_nodes, int* out_count);
 
+/* Diagnostic (no device needed): the box test of the broadphase kernel on the host, compiled from the same source as the kernel.
+ * boxes_a / boxes_b: [n][8] floats {cx cy cz . ex ey ez .} (the FK kernel's world AABBs, base-centred).  out[i]: bit 0 = the
+ * boxes overlap (|ca - cb| <= ea + eb on all axes, evaluated in double), bit 1 = the kernel's 15-bit fixed-point test says
+ * so.  The kernel is conservative when bit 0 implies bit 1 (the reference has no broadphase: collisionPQP.h:432-498 visits
+ * every link pair, so a pair may only ever be dropped when its boxes are disjoint). */
+int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, uint8_t* out);
+
 /* ==== planners on the batched entry (BASELINE.json configs[2]) =========================================
  * The reference's RRT family spends its time in PlannerParameters::CheckPathAllConstraints (planner.h:373-379) ->
  * DynamicsCollisionConstraint::Check (planningutils.cpp:2586-3629), one sample at a time.  These entry points run the same

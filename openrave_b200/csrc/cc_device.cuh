@@ -804,7 +804,7 @@ __device__ __forceinline__ Box8 ld_box(const float4* p)
 
 // {minx | miny << 16, minz, maxx | maxy << 16, maxz} in 15-bit steps: min rounded down, max rounded up (0.01 of a step of slack
 // for the FP32 rounding of the scaling itself), both saturating
-__device__ __forceinline__ uint4 quantise_box(const Box8& b)
+__host__ __device__ __forceinline__ uint4 quantise_box(const Box8& b)
 {
     auto lo = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(floorf((v + kBroadHalf) * kBroadScale - 0.01f), 0.f), 32767.f); };
     auto hi = [](float v) -> uint32_t { return (uint32_t)fminf(fmaxf(ceilf((v + kBroadHalf) * kBroadScale + 0.01f), 0.f), 32767.f); };
@@ -813,7 +813,7 @@ __device__ __forceinline__ uint4 quantise_box(const Box8& b)
 
 // a.min <= b.max and b.min <= a.max on all three axes, two 15-bit fields per subtraction: (max | guard) - min keeps the guard bit
 // (bit 15 of its half) exactly when max >= min, and never borrows across the halves
-__device__ __forceinline__ bool qbox_overlap(const uint4 a, const uint4 b)
+__host__ __device__ __forceinline__ bool qbox_overlap(const uint4 a, const uint4 b)
 {
     constexpr uint32_t G = 0x80008000u;
     const uint32_t r = ((b.z | G) - a.x) & ((b.w | G) - a.y) & ((a.z | G) - b.x) & ((a.w | G) - b.y);

@@ -2495,6 +2495,25 @@ int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
 
 }  // extern "C"
 
+// Diagnostic, no device needed: the broadphase kernel's box test on the host — the very functions cc_broad_kernel compiles
+// (quantise_box, qbox_overlap), so that a CPU test can check that an overlap of the FP32 boxes is never lost.
+extern "C" int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, uint8_t* out)
+{
+    if (!boxes_a || !boxes_b || !out || n < 0) return fail(CC_ERR_INVALID, "cc_debug_broad_overlap: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        const float* a = boxes_a + 8 * (size_t)i;
+        const float* b = boxes_b + 8 * (size_t)i;
+        ccdev::Box8 A, B;
+        A.c = make_float4(a[0], a[1], a[2], a[3]); A.e = make_float4(a[4], a[5], a[6], a[7]);
+        B.c = make_float4(b[0], b[1], b[2], b[3]); B.e = make_float4(b[4], b[5], b[6], b[7]);
+        bool exact = true;
+        for (int k = 0; k < 3; ++k) exact = exact && fabs((double)a[k] - (double)b[k]) <= (double)a[4 + k] + (double)b[4 + k];
+        const bool quantised = ccdev::qbox_overlap(ccdev::quantise_box(A), ccdev::quantise_box(B));
+        out[i] = (uint8_t)((exact ? 1 : 0) | (quantised ? 2 : 0));
+    }
+    return CC_OK;
+}
+
 // Diagnostic, no device needed: the BVH of one triangle mesh exactly as cc_scene_commit builds it (binned surface-area
 // splits, one triangle per leaf, children adjacent).  The CPU tests check its invariants; the GPU never sees this call.
 extern "C" int cc_debug_build_bvh(const double* vertices, int nvertices, const int32_t* triangles, int ntriangles, float* out_nodes,
