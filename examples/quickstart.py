@@ -40,6 +40,15 @@ def main():
     v = res["verdict"]
     print("%d configurations: %.1f %% env collisions, %.1f %% self collisions" % (len(q), 100 * (v & 1).mean(), 100 * ((v >> 1) & 1).mean()))
 
+    # CO_Distance for a batch: exact minimum separation, the link pair that attains it, the closest points
+    d = cc.DistanceBatch(robot, q[:20000])
+    k = int(np.argmax(d["distance"]))
+    print("clearance: median %.4f m, largest %.4f m (link %d against body %d link %d)" % (
+        float(np.median(d["distance"])), float(d["distance"][k]), *[int(x) for x in d["pair"][k]]))
+
+    # several GPUs of one box behind the same object: RaveCreateCollisionChecker(env, "cudacollision 0,1,2,3") — every call
+    # above stays the same, batches are range-sharded inside the library
+
     # an edge check (CheckPathAllConstraints) and a plan, both on the batched entry
     free = q[v == 0]
     planner = pl.BirrtPlanner(robot, cc)
