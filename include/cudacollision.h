@@ -415,6 +415,9 @@ typedef struct cc_birrt_params {
     int32_t speculate_steps;         /* steps of a ray sent per round: 0 the whole ray, n > 0 fixed chunks, n < 0 adaptive (|n| first,
                                       * doubling while the chunks pass); the plans are the same for every value */
     int32_t post_processor;          /* cc_post_processor: PlannerParameters::_sPostProcessingPlanner */
+    int32_t minimum_goal_paths;      /* RRTParameters::_minimumgoalpaths (plannerparameters.h:740): goals to connect to before the
+                                      * shortest path is returned; <= 1 -> 1 (the default).  BiRRT only (rrt.h:495-531). */
+    int32_t reserved;
 } cc_birrt_params;
 
 /* The path optimiser that runs on the raw plan (`_sPostProcessingPlanner`): the default "linearsmoother"
@@ -439,6 +442,8 @@ typedef struct cc_plan_result {
     uint64_t configs_serial;         /* configurations the serial per-sample loop would have checked (up to each first failure) */
     int32_t start_index, goal_index; /* GOALPATH::startindex / goalindex (rrt.h:296-302): which initial configuration (rank among the
                                       * valid ones) and which goal (index as given) the plan connects; -1 when there is no plan */
+    int32_t goal_paths;              /* goals a path was found to (_vgoalpaths.size()); the plan is the shortest of them */
+    int32_t reserved;
 } cc_plan_result;
 
 /* A checker for groups of ordered segments.  Configurations q[nconfigs][ndof]; segment s owns configurations
@@ -456,6 +461,14 @@ int cc_planner_destroy(cc_planner* p);
 int cc_planner_set_query(cc_planner* p, cc_query* q);
 /* Edge checks through a caller-supplied checker (the test harness plugs the CPU oracle in here). */
 int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user);
+
+/* PlannerParameters::_samplegoalfn / _sampleinitialfn (planner.h:298-311; BirrtPlanner::PlanPath, rrt.h:422-437): called once per
+ * main-loop iteration of every BiRRT problem; a callback that returns 1 has written a new goal (initial) configuration to
+ * q_out[ndof], which becomes a new root of the backward (forward) tree as it is — the reference does not check it either; its
+ * goal index is the next free one.  With a goal sampler a problem may start without any valid goal.  NULL switches a sampler
+ * off.  `problem` is the problem's position in the batch. */
+typedef int (*cc_config_sampler_fn)(void* user, int problem, int ndof, double* q_out);
+int cc_planner_set_samplers(cc_planner* planner, cc_config_sampler_fn goal_fn, cc_config_sampler_fn initial_fn, void* user);
 /* The sample sequence DynamicsCollisionConstraint::Check visits for the edge q0 -> q1 (planningutils.cpp:2692-2835,
  * 3405-3454), in checking order.  interval: 0 IT_Open, 1 IT_OpenStart, 2 IT_OpenEnd, 3 IT_Closed (planner.h).  Writes at
  * most max_configs rows to out_configs (may be NULL) and returns the count in *out_count; -1 there = the edge leaves the

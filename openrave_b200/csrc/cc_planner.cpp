@@ -402,6 +402,7 @@ struct Tree {
     std::vector<double> q;          // [nodes][dof]
     std::vector<int32_t> parent;
     std::vector<uint32_t> userdata;
+    std::vector<uint8_t> usenn;      // 0: left out of nearest-neighbour queries (InvalidateNodesWithParent, rplanners.h:242-266)
     int size() const { return (int)parent.size(); }
     const double* cfg(int i) const { return &q[(size_t)i * dof]; }
     int nearest(const CSpace& cs, const double* target, double* dist_out = nullptr) const
@@ -409,11 +410,20 @@ struct Tree {
         int best = -1;
         double bd = INFINITY;
         for (int i = 0; i < size(); ++i) {
+            if (!usenn[i]) continue;
             const double d = cs.dist(cfg(i), target);
             if (d < bd) { bd = d; best = i; }
         }
         if (dist_out) *dist_out = bd;
         return best;
+    }
+    // a goal that has been reached and everything grown from it leave the nearest-neighbour queries (the nodes stay: paths
+    // already extracted refer to them, and _InsertNode's minimum-distance rule still sees them)
+    void invalidate_with_parent(int root)
+    {
+        usenn[root] = 0;
+        for (int i = root + 1; i < size(); ++i)        // parents precede their children
+            if (parent[i] >= 0 && !usenn[parent[i]]) usenn[i] = 0;
     }
     // is some node within `r` of c?  (weighted distance; a node is rejected as soon as its partial sum exceeds r^2, which for
     // r = 0.001 * step happens at the first coordinate for all but coincident nodes)
@@ -444,6 +454,7 @@ struct Tree {
         q.insert(q.end(), c, c + dof);
         parent.push_back(par);
         userdata.push_back(ud);
+        usenn.push_back(1);
         return size() - 1;
     }
 };
@@ -462,6 +473,8 @@ struct cc_planner {
     cc_query* query = nullptr;
     cc_group_check_fn fn = nullptr;
     void* user = nullptr;
+    cc_config_sampler_fn sample_goal_fn = nullptr, sample_initial_fn = nullptr;     // PlannerParameters::_samplegoalfn / _sampleinitialfn
+    void* sampler_user = nullptr;
     std::vector<std::unique_ptr<Problem>> problems;
     uint64_t totals[4] = {0, 0, 0, 0};
     // page-locked staging for the GPU checker (cc_host_alloc): configurations in, verdicts out
@@ -478,6 +491,9 @@ struct Problem {
     std::vector<double> start, goal;          // first initial / goal configuration (BasicRRT plans with these)
     std::vector<double> starts_all, goals_all; // every initial / goal configuration of the problem, flat (BiRRT)
     uint32_t seed = 0;
+    int index = 0;                            // position in the batch (what the sampler callbacks are told)
+    cc_config_sampler_fn sample_goal_fn = nullptr, sample_initial_fn = nullptr;
+    void* sampler_user = nullptr;
     cc_plan_result res{};
     std::vector<double> path_raw, path;       // flat [waypoints][dof]
 
@@ -1108,25 +1124,49 @@ struct Problem {
             goal_nodes[k] = bwd.insert(*cs, -1, v, (uint32_t)k);
             if (goal_nodes[k] >= 0) ++nvalidgoals;
         }
-        if (bwd.size() == 0) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }
+        if (bwd.size() == 0 && !sample_goal_fn) { res.status = CC_PLAN_BAD_GOAL; co_return 0; }     // "no goals specified" (rrt.h:349-355)
 
         const int maxiter = prm.max_iterations > 0 ? prm.max_iterations : 10000;
         Tree* A = &fwd;
         Tree* B = &bwd;
         int ia = -1, ib = -1, iter = 0;
-        bool sample_goal = true, solved = false;
+        // RRTParameters::_minimumgoalpaths (plannerparameters.h:740): keep going until that many goals — or every valid one — have a
+        // path; the shortest is returned (rrt.h:495-531, 540-546)
+        const int want_paths = std::max(1, (int)prm.minimum_goal_paths);
+        struct GoalPath { std::vector<double> q; double length; int32_t start_index, goal_index; };
+        std::vector<GoalPath> goal_paths;
+        bool sample_goal = true;
+        int ninitial = fwd.size();                          // _vecInitialNodes.size(): the userdata of the next sampled initial
         std::vector<double> target;
-        while (!solved && iter < 3 * maxiter) {
+        while (iter < 3 * maxiter) {
             ++iter;
             res.iterations++;
+            // goals and initial configurations that arrive while planning (an IK sampler that keeps producing solutions): added
+            // as new roots as they are, like the reference does (rrt.h:422-437); a configuration too close to an existing node
+            // keeps its slot as a dummy
+            if (sample_goal_fn) {
+                std::vector<double> v(n);
+                if (sample_goal_fn(sampler_user, index, n, v.data())) {
+                    goal_nodes.push_back(bwd.insert(*cs, -1, v.data(), (uint32_t)goal_nodes.size()));
+                    ++nvalidgoals;
+                }
+            }
+            if (sample_initial_fn) {
+                std::vector<double> v(n);
+                if (sample_initial_fn(sampler_user, index, n, v.data())) fwd.insert(*cs, -1, v.data(), (uint32_t)ninitial++);
+            }
+            if (bwd.size() == 0) continue;                  // nothing to grow towards yet
+            const int ngoals_now = (int)goal_nodes.size();
             target.clear();
             if ((sample_goal || uniform.real(IT_Closed) < prm.goal_bias) && nvalidgoals > 0) {
                 sample_goal = false;
-                // up to 3 x #goals draws until one names a goal that stands (rrt.h:443-466; with _minimumgoalpaths = 1 no goal
-                // has been reached yet while the loop runs)
-                for (int testiter = 0; testiter < ngoals * 3; ++testiter) {
-                    const uint32_t gi = uniform.u32() % (uint32_t)ngoals;
+                // up to 3 x #goals draws until one names a goal that stands and has no path yet (rrt.h:443-466)
+                for (int testiter = 0; testiter < ngoals_now * 3; ++testiter) {
+                    const uint32_t gi = uniform.u32() % (uint32_t)ngoals_now;
                     if (goal_nodes[gi] < 0) continue;
+                    bool found = false;
+                    for (const GoalPath& gp : goal_paths) if (gp.goal_index == (int32_t)gi) { found = true; break; }
+                    if (found) continue;
                     target.assign(bwd.cfg(goal_nodes[gi]), bwd.cfg(goal_nodes[gi]) + n);
                     break;
                 }
@@ -1139,28 +1179,43 @@ struct Problem {
             }
             std::vector<double> toward(A->cfg(ia), A->cfg(ia) + n);
             et = co_await extend(*B, toward, ib);
-            if (et == ET_Connected) { solved = true; break; }
+            if (et == ET_Connected) {
+                // _ExtractPath: forward chain root -> connection, then backward chain connection -> root, _SimpleOptimizePath(10)
+                const int cf = (A == &fwd) ? ia : ib, cb = (A == &bwd) ? ia : ib;
+                GoalPath gp;
+                gp.goal_index = -1;
+                std::vector<int> chain;
+                for (int i = cf; i >= 0; i = fwd.parent[i]) chain.push_back(i);
+                for (auto it = chain.rbegin(); it != chain.rend(); ++it) gp.q.insert(gp.q.end(), fwd.cfg(*it), fwd.cfg(*it) + n);
+                int goal_root = -1;
+                for (int i = cb; i >= 0; i = bwd.parent[i]) {
+                    gp.q.insert(gp.q.end(), bwd.cfg(i), bwd.cfg(i) + n);
+                    if (bwd.parent[i] < 0) { gp.goal_index = (int32_t)bwd.userdata[i]; goal_root = i; }    // GOALPATH::goalindex (rrt.h:633-644)
+                }
+                gp.start_index = (int32_t)fwd.userdata[chain.back()];                                      // GOALPATH::startindex (:622-631)
+                co_await simple_optimize(gp.q, prm.path_optimize_iterations);
+                gp.length = path_length(gp.q);
+                goal_paths.push_back(std::move(gp));
+                if ((int)goal_paths.size() >= want_paths || (int)goal_paths.size() >= nvalidgoals) break;
+                sample_goal = true;
+                // more goals wanted: nothing may connect to the tree grown from this goal again
+                bwd.invalidate_with_parent(goal_root);
+            }
             std::swap(A, B);
             iter += 3;
             if (iter > 3 * maxiter) break;
         }
         res.nodes_forward = fwd.size();
         res.nodes_backward = bwd.size();
-        if (!solved) { res.status = CC_PLAN_FAILED; co_return 0; }
-        // _ExtractPath: forward chain root -> connection, then backward chain connection -> root
-        const int cf = (A == &fwd) ? ia : ib, cb = (A == &bwd) ? ia : ib;
-        std::vector<int> chain;
-        for (int i = cf; i >= 0; i = fwd.parent[i]) chain.push_back(i);
-        path_raw.clear();
-        for (auto it = chain.rbegin(); it != chain.rend(); ++it) path_raw.insert(path_raw.end(), fwd.cfg(*it), fwd.cfg(*it) + n);
-        for (int i = cb; i >= 0; i = bwd.parent[i]) {
-            path_raw.insert(path_raw.end(), bwd.cfg(i), bwd.cfg(i) + n);
-            if (bwd.parent[i] < 0) res.goal_index = (int32_t)bwd.userdata[i];         // GOALPATH::goalindex (rrt.h:633-644)
-        }
-        res.start_index = (int32_t)fwd.userdata[chain.back()];                          // GOALPATH::startindex (:622-631)
-        co_await simple_optimize(path_raw, prm.path_optimize_iterations);
+        res.goal_paths = (int32_t)goal_paths.size();
+        if (goal_paths.empty()) { res.status = CC_PLAN_FAILED; co_return 0; }
+        size_t ibest = 0;
+        for (size_t k = 1; k < goal_paths.size(); ++k) if (goal_paths[k].length < goal_paths[ibest].length) ibest = k;
+        path_raw = goal_paths[ibest].q;
+        res.goal_index = goal_paths[ibest].goal_index;
+        res.start_index = goal_paths[ibest].start_index;
         res.waypoints_raw = (int)path_raw.size() / n;
-        res.length_raw = path_length(path_raw);
+        res.length_raw = goal_paths[ibest].length;
         if (prm.smoother_iterations > 0 && prm.post_processor == CC_POST_SHORTCUT_LINEAR) co_await shortcut_linear(path_raw, path);
         else if (prm.smoother_iterations > 0) co_await smooth(path_raw, path);
         else path = path_raw;
@@ -1259,6 +1314,15 @@ int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user)
     p->fn = fn;
     p->user = user;
     p->query = nullptr;
+    return CC_OK;
+}
+
+int cc_planner_set_samplers(cc_planner* p, cc_config_sampler_fn goal_fn, cc_config_sampler_fn initial_fn, void* user)
+{
+    if (!p) return fail(CC_ERR_INVALID, "cc_planner_set_samplers: planner is NULL");
+    p->sample_goal_fn = goal_fn;
+    p->sample_initial_fn = initial_fn;
+    p->sampler_user = user;
     return CC_OK;
 }
 
@@ -1397,12 +1461,18 @@ static int plan_batch(cc_planner* p, const cc_birrt_params* params, int kind, in
         pr->prm = *params;
         const int s0 = start_begin ? start_begin[k] : k, s1 = start_begin ? start_begin[k + 1] : k + 1;
         const int g0 = goal_begin ? goal_begin[k] : k, g1 = goal_begin ? goal_begin[k + 1] : k + 1;
-        if (s1 <= s0 || g1 <= g0) { p->problems.clear(); return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: a problem needs at least one initial and one goal configuration"); }
+        const bool goals_may_come = kind == 0 && p->sample_goal_fn != nullptr;       // BiRRT with a goal sampler may start without goals (rrt.h:349)
+        if (s1 <= s0 || g1 < g0 || (g1 == g0 && !goals_may_come)) {
+            p->problems.clear();
+            return fail(CC_ERR_INVALID, "cc_birrt_plan_batch: a problem needs at least one initial and one goal configuration");
+        }
         pr->starts_all.assign(starts + (size_t)s0 * n, starts + (size_t)s1 * n);
         pr->goals_all.assign(goals + (size_t)g0 * n, goals + (size_t)g1 * n);
         pr->start.assign(pr->starts_all.begin(), pr->starts_all.begin() + n);
-        pr->goal.assign(pr->goals_all.begin(), pr->goals_all.begin() + n);
+        if (g1 > g0) pr->goal.assign(pr->goals_all.begin(), pr->goals_all.begin() + n);
         pr->seed = seeds ? seeds[k] : 0;
+        pr->index = k;
+        pr->sample_goal_fn = p->sample_goal_fn; pr->sample_initial_fn = p->sample_initial_fn; pr->sampler_user = p->sampler_user;
         std::memset(&pr->res, 0, sizeof(pr->res));
         pr->res.start_index = pr->res.goal_index = -1;
         p->problems.push_back(std::move(pr));

@@ -677,7 +677,7 @@ class cc_birrt_params(ctypes.Structure):
     _fields_ = [("step_length", ctypes.c_double), ("goal_bias", ctypes.c_double), ("point_tolerance", ctypes.c_double),
                 ("max_iterations", ctypes.c_int32), ("path_optimize_iterations", ctypes.c_int32),
                 ("smoother_iterations", ctypes.c_int32), ("max_extend_steps", ctypes.c_int32), ("speculate_steps", ctypes.c_int32),
-                ("post_processor", ctypes.c_int32)]
+                ("post_processor", ctypes.c_int32), ("minimum_goal_paths", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class cc_plan_result(ctypes.Structure):
@@ -685,7 +685,7 @@ class cc_plan_result(ctypes.Structure):
                 ("nodes_backward", ctypes.c_int32), ("waypoints_raw", ctypes.c_int32), ("waypoints", ctypes.c_int32),
                 ("rounds", ctypes.c_int32), ("shortcuts", ctypes.c_int32), ("length_raw", ctypes.c_double),
                 ("length", ctypes.c_double), ("configs_submitted", ctypes.c_uint64), ("configs_serial", ctypes.c_uint64),
-                ("start_index", ctypes.c_int32), ("goal_index", ctypes.c_int32)]
+                ("start_index", ctypes.c_int32), ("goal_index", ctypes.c_int32), ("goal_paths", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class cc_edge_result(ctypes.Structure):
@@ -695,7 +695,7 @@ class cc_edge_result(ctypes.Structure):
 
 PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1, "linearsmoother 0": 2}          # PlannerParameters::_sPostProcessingPlanner
-PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker",
+PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker", "cc_planner_set_samplers",
                    "cc_planner_edge_samples", "cc_planner_edge_sample_times", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_birrt_plan_batch_multi", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
@@ -718,6 +718,7 @@ def _planner_lib():
     lib.cc_birrt_plan_batch_multi.argtypes = [vp, ctypes.POINTER(cc_birrt_params), ci, vp, vp, vp, vp, vp, vp]
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
+    lib.cc_planner_set_samplers.argtypes = [vp, vp, vp, vp]
     lib._planner_ready = True
     return lib
 
@@ -730,7 +731,8 @@ class BirrtPlanner(object):
     (start, goal) problems in lockstep; `PlanPath` is the single-problem call of the reference API."""
 
     def __init__(self, robot, checker, step_length=0.04, max_iterations=10000, goal_bias=0.01, smoother_iterations=100,
-                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8, post_processor="linearsmoother"):
+                 path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8, post_processor="linearsmoother",
+                 minimum_goal_paths=1):
         self.lib = _planner_lib()
         self.robot = robot
         self.active = list(robot.GetActiveDOFIndices())
@@ -747,7 +749,8 @@ class BirrtPlanner(object):
         self._ck(self.lib.cc_planner_create(ctypes.byref(sp), ctypes.byref(h)))
         self.handle = h
         self.params = cc_birrt_params(step_length, goal_bias, point_tolerance, max_iterations, path_optimize_iterations,
-                                      smoother_iterations, 100, speculate_steps, POST_PROCESSORS[post_processor])
+                                      smoother_iterations, 100, speculate_steps, POST_PROCESSORS[post_processor],
+                                      int(minimum_goal_paths), 0)     # RRTParameters::_minimumgoalpaths (PlanBatchMulti problems)
         self._keep = None
         if isinstance(checker, tuple):
             fn, blk = checker
@@ -866,6 +869,28 @@ class BirrtPlanner(object):
 
     def PlanPath(self, start, goal, seed=0):
         return self.PlanBatch([start], [goal], [seed])[0]
+
+    def SetSamplers(self, samplegoalfn=None, sampleinitialfn=None):
+        """PlannerParameters::_samplegoalfn / _sampleinitialfn: callables (problem index) -> configuration or None, asked once per
+        main-loop iteration of every BiRRT problem (cc_planner_set_samplers)."""
+        proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double))
+
+        def wrap(fn):
+            if fn is None:
+                return None
+
+            def cb(user, problem, ndof, out):
+                v = fn(problem)
+                if v is None:
+                    return 0
+                for k in range(ndof):
+                    out[k] = float(v[k])
+                return 1
+            return proto(cb)
+        self._samplers = (wrap(samplegoalfn), wrap(sampleinitialfn))          # keep the thunks alive
+        g, i = self._samplers
+        self._ck(self.lib.cc_planner_set_samplers(self.handle, ctypes.cast(g, ctypes.c_void_p) if g else None,
+                                                  ctypes.cast(i, ctypes.c_void_p) if i else None, None))
 
     def PlanBatchMulti(self, starts_per_problem, goals_per_problem, seeds=None):
         """BiRRT with several initial / goal configurations per problem (lists of [k_i, ndof] arrays): cc_birrt_plan_batch_multi.

@@ -951,8 +951,8 @@ private:
 // RaveCreatePlanner(env, "cudabirrt"): BirrtPlanner's interface (plugins/rplanners/rrt.h:279-659) on cc_birrt_plan_batch.  InitPlan reads
 // the same RRTParameters (goal bias is BirrtPlanner's constant 0.01, rrt.h:315), PlanPath plans vinitialconfig -> vgoalconfig and
 // appends the smoothed waypoints to the trajectory; PlanPathBatch is the new entry for callers that hold many queries.  Needs the
-// environment's collision checker to be "cudacollision".  Multiple initial / goal configurations, goal / initial samplers and
-// planner callbacks are not carried over (single start, single goal per problem).
+// environment's collision checker to be "cudacollision".  Several initial / goal configurations, _minimumgoalpaths and the goal /
+// initial samplers (_samplegoalfn, _sampleinitialfn) are carried over; planner progress callbacks (_RegisterCallback) are not.
 class CudaBirrtPlanner : public PlannerBase
 {
 public:
@@ -1000,6 +1000,7 @@ public:
         _birrt.post_processor = _parameters->_sPostProcessingPlanner == "shortcut_linear" ? CC_POST_SHORTCUT_LINEAR
                                 : _parameters->_sPostProcessingPlanner == "linearsmoother 0" ? CC_POST_LINEARSMOOTHER_SHORTCUTS   // creation args (linearsmoother.cpp:25-26)
                                 : CC_POST_LINEARSMOOTHER;
+        _birrt.minimum_goal_paths = (int32_t)_parameters->_minimumgoalpaths;     // plannerparameters.h:740 (1 unless the caller's XML set it)
         return PlannerStatus(PS_HasSolution);
     }
 
@@ -1008,8 +1009,12 @@ public:
         if (!_planner || !_parameters) return PlannerStatus("cudabirrt: not initialized", PS_Failed);
         const int ndof = _parameters->GetDOF();
         const int ninitial = (int)_parameters->vinitialconfig.size() / ndof, ngoals = (int)_parameters->vgoalconfig.size() / ndof;
-        if (ninitial < 1 || ngoals < 1 || (int)_parameters->vinitialconfig.size() % ndof || (int)_parameters->vgoalconfig.size() % ndof)
-            return PlannerStatus("cudabirrt: initial / goal configurations are improperly specified", PS_Failed);      // rrt.h:65-69, 322-328
+        if (ninitial < 1 || (ngoals < 1 && !_parameters->_samplegoalfn) || (int)_parameters->vinitialconfig.size() % ndof ||
+            (int)_parameters->vgoalconfig.size() % ndof)
+            return PlannerStatus("cudabirrt: initial / goal configurations are improperly specified", PS_Failed);      // rrt.h:65-69, 322-328, 349-355
+        // _samplegoalfn / _sampleinitialfn (planner.h:298-311): asked once per iteration, like BirrtPlanner::PlanPath does (rrt.h:422-437)
+        cc_planner_set_samplers(_planner, !!_parameters->_samplegoalfn ? &CudaBirrtPlanner::_SampleGoalThunk : NULL,
+                                !!_parameters->_sampleinitialfn ? &CudaBirrtPlanner::_SampleInitialThunk : NULL, this);
         // several initial configurations and several goals (one per IK solution, say) are one problem (rrt.h:72-88, 327-343)
         EnvironmentLock lock(GetEnv()->GetMutex());
         const int32_t start_begin[2] = {0, ninitial}, goal_begin[2] = {0, ngoals};
@@ -1058,6 +1063,16 @@ public:
     virtual PlannerParametersConstPtr GetParameters() const { return _parameters; }
 
 private:
+    static int _SampleThunk(const boost::function<bool(std::vector<dReal>&)>& fn, int ndof, double* q_out)
+    {
+        std::vector<dReal> v;
+        if (!fn(v) || (int)v.size() < ndof) return 0;
+        std::copy(v.begin(), v.begin() + ndof, q_out);
+        return 1;
+    }
+    static int _SampleGoalThunk(void* user, int, int ndof, double* q_out) { return _SampleThunk(static_cast<CudaBirrtPlanner*>(user)->_parameters->_samplegoalfn, ndof, q_out); }
+    static int _SampleInitialThunk(void* user, int, int ndof, double* q_out) { return _SampleThunk(static_cast<CudaBirrtPlanner*>(user)->_parameters->_sampleinitialfn, ndof, q_out); }
+
     RobotBasePtr _robot;
     RRTParametersPtr _parameters;
     cc_planner* _planner;

@@ -292,3 +292,104 @@ def test_birrt_with_several_initial_and_goal_configurations(wamtest1):
     assert not orc.check_batch(robot, r["path"])["verdict"].any()
     assert res[1]["status"] == pl.PLAN_BAD_GOAL and res[1]["goal_index"] == -1
     assert P.PlanBatchMulti([np.array([bad[0]])], [np.array([good[0]])], [1])[0]["status"] == pl.PLAN_BAD_INITIAL
+
+
+def test_birrt_minimum_goal_paths_returns_the_shortest_of_several(wamtest1):
+    """RRTParameters::_minimumgoalpaths (plannerparameters.h:740; rrt.h:495-531, 540-546): with k goals wanted the planner keeps
+    going after its first connection — the reached goal and everything grown from it leave the nearest-neighbour queries
+    (InvalidateNodesWithParent, rplanners.h:242-266), the next goal is sampled at once — until k goals (or every valid one) have a
+    path, and returns the shortest.  With 1 (the default) nothing changes.  The reference's own nearest-neighbour query treats
+    invalidated nodes in a traversal-order-dependent way (rplanners.h:677-690), so which later goals connect first is "parity
+    unpinned"; the properties below are what the feature promises."""
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 400, seed=21, active=act)
+    good = q[orc.check_batch(robot, q, active=act)["verdict"] == 0]
+    S = [good[0][None], good[5][None]]
+    G = [good[1:4], good[6:9]]
+    cons = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    base = pl.BirrtPlanner(robot, orc.group_checker(robot)).PlanBatchMulti(S, G, [5, 6])
+    one = pl.BirrtPlanner(robot, orc.group_checker(robot), minimum_goal_paths=1).PlanBatchMulti(S, G, [5, 6])
+    for a, b in zip(base, one):
+        assert a["goal_paths"] == 1 and np.array_equal(a["path"], b["path"]) and a["iterations"] == b["iterations"]
+    for want in (2, 3, 7):
+        P = pl.BirrtPlanner(robot, orc.group_checker(robot), minimum_goal_paths=want)
+        res = P.PlanBatchMulti(S, G, [5, 6])
+        again = P.PlanBatchMulti(S, G, [5, 6])
+        for k, (r, r2, b) in enumerate(zip(res, again, base)):
+            assert r["status"] == pl.PLAN_SOLVED and r["goal_paths"] == min(want, 3)       # never more than there are valid goals
+            assert r["iterations"] >= b["iterations"]                                          # the first connection is the default run's
+            assert r["length_raw"] <= b["length_raw"] + 1e-9                                  # ... and stays a candidate
+            p = r["path"]
+            assert np.array_equal(p[0], S[k][0]) and np.array_equal(p[-1], G[k][r["goal_index"]])
+            assert not orc.check_batch(robot, p)["verdict"].any()
+            edges = [(p[i], p[i + 1]) for i in range(len(p) - 1)]
+            assert not any(cons.CheckMany(edges, pl.IT_Open, options=0xffff))
+            assert np.array_equal(r["path"], r2["path"]) and r["goal_index"] == r2["goal_index"]
+
+
+def test_birrt_goal_and_initial_samplers(wamtest1):
+    """PlannerParameters::_samplegoalfn / _sampleinitialfn (rrt.h:422-437): configurations that arrive while the planner runs become
+    new roots of the backward / forward tree.  A problem whose only listed goal collides is refused without a goal sampler
+    ("no goals specified", rrt.h:349-355) and solved with one; the plan says which sampled goal (index after the listed ones)
+    and which initial configuration it joins."""
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 400, seed=33, active=act)
+    v = orc.check_batch(robot, q, active=act)["verdict"]
+    bad, good = q[v != 0], q[v == 0]
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    S, G = [good[0][None]], [bad[0][None]]
+    assert P.PlanBatchMulti(S, G, [4])[0]["status"] == pl.PLAN_BAD_GOAL
+    calls = {"goal": 0, "initial": 0}
+
+    def goal_sampler(problem):
+        calls["goal"] += 1
+        return good[1] if calls["goal"] == 3 else (good[2] if calls["goal"] == 5 else None)     # two goals arrive, at iterations 3 and 5
+
+    def initial_sampler(problem):
+        calls["initial"] += 1
+        return good[3] if calls["initial"] == 2 else None
+
+    P.SetSamplers(goal_sampler, initial_sampler)
+    r = P.PlanBatchMulti(S, G, [4])[0]
+    assert r["status"] == pl.PLAN_SOLVED and calls["goal"] >= 3 and calls["initial"] >= 2
+    assert r["goal_index"] in (1, 2) and r["start_index"] in (0, 1)           # the listed goal keeps index 0 (a dummy), sampled ones follow
+    goal = {1: good[1], 2: good[2]}[r["goal_index"]]
+    start = {0: good[0], 1: good[3]}[r["start_index"]]
+    p = r["path"]
+    assert np.array_equal(p[0], start) and np.array_equal(p[-1], goal)
+    cons = pl.DynamicsCollisionConstraint(robot, OracleBatchAdapter(orc))
+    assert not orc.check_batch(robot, p)["verdict"].any()
+    assert not any(cons.CheckMany([(p[i], p[i + 1]) for i in range(len(p) - 1)], pl.IT_Open, options=0xffff))
+    # switched off again: the same refusal as before; and samplers that never produce anything change nothing
+    P.SetSamplers(None, None)
+    assert P.PlanBatchMulti(S, G, [4])[0]["status"] == pl.PLAN_BAD_GOAL
+    S2, G2 = [good[0][None]], [good[1][None]]
+    a = P.PlanBatchMulti(S2, G2, [9])[0]
+    P.SetSamplers(lambda k: None, lambda k: None)
+    b = P.PlanBatchMulti(S2, G2, [9])[0]
+    assert np.array_equal(a["path"], b["path"]) and a["iterations"] == b["iterations"]
+
+
+def test_birrt_may_start_without_goals_when_a_goal_sampler_is_set(wamtest1):
+    """rrt.h:349-355: "no goals specified" only without _samplegoalfn."""
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 200, seed=35, active=act)
+    good = q[orc.check_batch(robot, q, active=act)["verdict"] == 0]
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    empty = np.zeros((0, len(act)))
+    with pytest.raises(RuntimeError):
+        P.PlanBatchMulti([good[0][None]], [empty], [2])
+    n = {"k": 0}
+
+    def goal_sampler(problem):
+        n["k"] += 1
+        return good[1] if n["k"] == 4 else None
+
+    P.SetSamplers(goal_sampler, None)
+    r = P.PlanBatchMulti([good[0][None]], [empty], [2])[0]
+    assert r["status"] == pl.PLAN_SOLVED and r["goal_index"] == 0 and r["iterations"] >= 4
+    assert np.array_equal(r["path"][0], good[0]) and np.array_equal(r["path"][-1], good[1])
+    assert not orc.check_batch(robot, r["path"])["verdict"].any()
