@@ -417,7 +417,8 @@ typedef struct cc_birrt_params {
     int32_t post_processor;          /* cc_post_processor: PlannerParameters::_sPostProcessingPlanner */
     int32_t minimum_goal_paths;      /* RRTParameters::_minimumgoalpaths (plannerparameters.h:740): goals to connect to before the
                                       * shortest path is returned; <= 1 -> 1 (the default).  BiRRT only (rrt.h:495-531). */
-    int32_t reserved;
+    int32_t max_planning_time_ms;    /* PlannerParameters::_nMaxPlanningTime (planner.h; rrt.h:414-420): stop the search this long after
+                                      * the call started; <= 0: no limit.  BiRRT only. */
 } cc_birrt_params;
 
 /* The path optimiser that runs on the raw plan (`_sPostProcessingPlanner`): the default "linearsmoother"
@@ -427,7 +428,8 @@ typedef struct cc_birrt_params {
 enum cc_post_processor { CC_POST_LINEARSMOOTHER = 0, CC_POST_SHORTCUT_LINEAR = 1,
                          CC_POST_LINEARSMOOTHER_SHORTCUTS = 2 /* "linearsmoother 0": _nUseSingleDOFSmoothing = 0, shortcuts only (linearsmoother.cpp:25-26, 241-244) */ };
 
-enum cc_plan_status { CC_PLAN_FAILED = 0, CC_PLAN_SOLVED = 1, CC_PLAN_BAD_INITIAL = 2, CC_PLAN_BAD_GOAL = 3 };
+enum cc_plan_status { CC_PLAN_FAILED = 0, CC_PLAN_SOLVED = 1, CC_PLAN_BAD_INITIAL = 2, CC_PLAN_BAD_GOAL = 3,
+                      CC_PLAN_INTERRUPTED = 4 /* PS_Interrupted: a progress callback answered CC_PA_INTERRUPT */ };
 
 typedef struct cc_plan_result {
     int32_t status;                  /* cc_plan_status */
@@ -468,6 +470,12 @@ int cc_planner_set_checker(cc_planner* p, cc_group_check_fn fn, void* user);
  * goal index is the next free one.  With a goal sampler a problem may start without any valid goal.  NULL switches a sampler
  * off.  `problem` is the problem's position in the batch. */
 typedef int (*cc_config_sampler_fn)(void* user, int problem, int ndof, double* q_out);
+
+/* PlannerBase::RegisterPlanCallback / _CallCallbacks (planner.h:76-79, 700-716; BirrtPlanner::PlanPath, rrt.h:401-412): called at the
+ * top of every main-loop iteration of every BiRRT problem with PlannerProgress::_iteration; the answer is a PlannerAction. */
+enum cc_planner_action { CC_PA_NONE = 0, CC_PA_INTERRUPT = 1, CC_PA_RETURN_WITH_ANY_SOLUTION = 2 };
+typedef int (*cc_progress_fn)(void* user, int problem, int iteration);
+int cc_planner_set_progress_callback(cc_planner* planner, cc_progress_fn fn, void* user);
 int cc_planner_set_samplers(cc_planner* planner, cc_config_sampler_fn goal_fn, cc_config_sampler_fn initial_fn, void* user);
 /* The sample sequence DynamicsCollisionConstraint::Check visits for the edge q0 -> q1 (planningutils.cpp:2692-2835,
  * 3405-3454), in checking order.  interval: 0 IT_Open, 1 IT_OpenStart, 2 IT_OpenEnd, 3 IT_Closed (planner.h).  Writes at

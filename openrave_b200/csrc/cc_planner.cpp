@@ -475,6 +475,8 @@ struct cc_planner {
     void* user = nullptr;
     cc_config_sampler_fn sample_goal_fn = nullptr, sample_initial_fn = nullptr;     // PlannerParameters::_samplegoalfn / _sampleinitialfn
     void* sampler_user = nullptr;
+    cc_progress_fn progress_fn = nullptr;                                           // PlannerBase::_CallCallbacks
+    void* progress_user = nullptr;
     std::vector<std::unique_ptr<Problem>> problems;
     uint64_t totals[4] = {0, 0, 0, 0};
     // page-locked staging for the GPU checker (cc_host_alloc): configurations in, verdicts out
@@ -494,6 +496,9 @@ struct Problem {
     int index = 0;                            // position in the batch (what the sampler callbacks are told)
     cc_config_sampler_fn sample_goal_fn = nullptr, sample_initial_fn = nullptr;
     void* sampler_user = nullptr;
+    cc_progress_fn progress_fn = nullptr;
+    void* progress_user = nullptr;
+    std::chrono::steady_clock::time_point t_start;
     cc_plan_result res{};
     std::vector<double> path_raw, path;       // flat [waypoints][dof]
 
@@ -1135,12 +1140,21 @@ struct Problem {
         const int want_paths = std::max(1, (int)prm.minimum_goal_paths);
         struct GoalPath { std::vector<double> q; double length; int32_t start_index, goal_index; };
         std::vector<GoalPath> goal_paths;
-        bool sample_goal = true;
+        bool sample_goal = true, interrupted = false;
         int ninitial = fwd.size();                          // _vecInitialNodes.size(): the userdata of the next sampled initial
         std::vector<double> target;
         while (iter < 3 * maxiter) {
             ++iter;
             res.iterations++;
+            // callbacks first, "since code can continue" (rrt.h:401-412): PA_Interrupt ends the problem, PA_ReturnWithAnySolution
+            // ends the search as soon as some goal has a path; then the time budget (_nMaxPlanningTime, rrt.h:414-420)
+            if (progress_fn) {
+                const int action = progress_fn(progress_user, index, iter / 3);
+                if (action == CC_PA_INTERRUPT) { interrupted = true; break; }
+                if (action == CC_PA_RETURN_WITH_ANY_SOLUTION && !goal_paths.empty()) break;
+            }
+            if (prm.max_planning_time_ms > 0 &&
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count() >= (double)prm.max_planning_time_ms) break;
             // goals and initial configurations that arrive while planning (an IK sampler that keeps producing solutions): added
             // as new roots as they are, like the reference does (rrt.h:422-437); a configuration too close to an existing node
             // keeps its slot as a dummy
@@ -1208,6 +1222,7 @@ struct Problem {
         res.nodes_forward = fwd.size();
         res.nodes_backward = bwd.size();
         res.goal_paths = (int32_t)goal_paths.size();
+        if (interrupted) { res.status = CC_PLAN_INTERRUPTED; co_return 0; }        // PS_Interrupted: no trajectory, whatever was found
         if (goal_paths.empty()) { res.status = CC_PLAN_FAILED; co_return 0; }
         size_t ibest = 0;
         for (size_t k = 1; k < goal_paths.size(); ++k) if (goal_paths[k].length < goal_paths[ibest].length) ibest = k;
@@ -1323,6 +1338,14 @@ int cc_planner_set_samplers(cc_planner* p, cc_config_sampler_fn goal_fn, cc_conf
     p->sample_goal_fn = goal_fn;
     p->sample_initial_fn = initial_fn;
     p->sampler_user = user;
+    return CC_OK;
+}
+
+int cc_planner_set_progress_callback(cc_planner* p, cc_progress_fn fn, void* user)
+{
+    if (!p) return fail(CC_ERR_INVALID, "cc_planner_set_progress_callback: planner is NULL");
+    p->progress_fn = fn;
+    p->progress_user = user;
     return CC_OK;
 }
 
@@ -1473,6 +1496,8 @@ static int plan_batch(cc_planner* p, const cc_birrt_params* params, int kind, in
         pr->seed = seeds ? seeds[k] : 0;
         pr->index = k;
         pr->sample_goal_fn = p->sample_goal_fn; pr->sample_initial_fn = p->sample_initial_fn; pr->sampler_user = p->sampler_user;
+        pr->progress_fn = p->progress_fn; pr->progress_user = p->progress_user;
+        pr->t_start = std::chrono::steady_clock::now();
         std::memset(&pr->res, 0, sizeof(pr->res));
         pr->res.start_index = pr->res.goal_index = -1;
         p->problems.push_back(std::move(pr));

@@ -677,7 +677,7 @@ class cc_birrt_params(ctypes.Structure):
     _fields_ = [("step_length", ctypes.c_double), ("goal_bias", ctypes.c_double), ("point_tolerance", ctypes.c_double),
                 ("max_iterations", ctypes.c_int32), ("path_optimize_iterations", ctypes.c_int32),
                 ("smoother_iterations", ctypes.c_int32), ("max_extend_steps", ctypes.c_int32), ("speculate_steps", ctypes.c_int32),
-                ("post_processor", ctypes.c_int32), ("minimum_goal_paths", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("post_processor", ctypes.c_int32), ("minimum_goal_paths", ctypes.c_int32), ("max_planning_time_ms", ctypes.c_int32)]
 
 
 class cc_plan_result(ctypes.Structure):
@@ -693,9 +693,10 @@ class cc_edge_result(ctypes.Structure):
                 ("perturbed", ctypes.c_int32), ("time_when_invalid", ctypes.c_double)]
 
 
-PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL = 0, 1, 2, 3
+PLAN_FAILED, PLAN_SOLVED, PLAN_BAD_INITIAL, PLAN_BAD_GOAL, PLAN_INTERRUPTED = 0, 1, 2, 3, 4
+PA_None, PA_Interrupt, PA_ReturnWithAnySolution = 0, 1, 2                # PlannerAction (planner.h:76-79)
 POST_PROCESSORS = {"linearsmoother": 0, "shortcut_linear": 1, "linearsmoother 0": 2}          # PlannerParameters::_sPostProcessingPlanner
-PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker", "cc_planner_set_samplers",
+PLANNER_EXPORTS = ["cc_planner_create", "cc_planner_destroy", "cc_planner_set_query", "cc_planner_set_checker", "cc_planner_set_samplers", "cc_planner_set_progress_callback",
                    "cc_planner_edge_samples", "cc_planner_edge_sample_times", "cc_planner_ramp_samples", "cc_planner_check_edges", "cc_birrt_plan_batch", "cc_birrt_plan_batch_multi", "cc_basicrrt_plan_batch", "cc_planner_get_path", "cc_planner_get_totals"]
 
 
@@ -719,6 +720,7 @@ def _planner_lib():
     lib.cc_planner_get_path.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci)]
     lib.cc_planner_get_totals.argtypes = [vp, vp]
     lib.cc_planner_set_samplers.argtypes = [vp, vp, vp, vp]
+    lib.cc_planner_set_progress_callback.argtypes = [vp, vp, vp]
     lib._planner_ready = True
     return lib
 
@@ -732,7 +734,7 @@ class BirrtPlanner(object):
 
     def __init__(self, robot, checker, step_length=0.04, max_iterations=10000, goal_bias=0.01, smoother_iterations=100,
                  path_optimize_iterations=10, point_tolerance=0.2, speculate_steps=-8, post_processor="linearsmoother",
-                 minimum_goal_paths=1):
+                 minimum_goal_paths=1, max_planning_time_ms=0):
         self.lib = _planner_lib()
         self.robot = robot
         self.active = list(robot.GetActiveDOFIndices())
@@ -750,7 +752,7 @@ class BirrtPlanner(object):
         self.handle = h
         self.params = cc_birrt_params(step_length, goal_bias, point_tolerance, max_iterations, path_optimize_iterations,
                                       smoother_iterations, 100, speculate_steps, POST_PROCESSORS[post_processor],
-                                      int(minimum_goal_paths), 0)     # RRTParameters::_minimumgoalpaths (PlanBatchMulti problems)
+                                      int(minimum_goal_paths), int(max_planning_time_ms))     # RRTParameters::_minimumgoalpaths, _nMaxPlanningTime
         self._keep = None
         if isinstance(checker, tuple):
             fn, blk = checker
@@ -869,6 +871,13 @@ class BirrtPlanner(object):
 
     def PlanPath(self, start, goal, seed=0):
         return self.PlanBatch([start], [goal], [seed])[0]
+
+    def SetProgressCallback(self, fn=None):
+        """PlannerBase::RegisterPlanCallback: fn(problem, iteration) -> PA_None / PA_Interrupt / PA_ReturnWithAnySolution, asked at
+        the top of every BiRRT iteration (cc_planner_set_progress_callback)."""
+        proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int)
+        self._progress = proto(lambda user, problem, iteration: int(fn(problem, iteration) or 0)) if fn is not None else None
+        self._ck(self.lib.cc_planner_set_progress_callback(self.handle, ctypes.cast(self._progress, ctypes.c_void_p) if self._progress else None, None))
 
     def SetSamplers(self, samplegoalfn=None, sampleinitialfn=None):
         """PlannerParameters::_samplegoalfn / _sampleinitialfn: callables (problem index) -> configuration or None, asked once per

@@ -952,7 +952,7 @@ private:
 // the same RRTParameters (goal bias is BirrtPlanner's constant 0.01, rrt.h:315), PlanPath plans vinitialconfig -> vgoalconfig and
 // appends the smoothed waypoints to the trajectory; PlanPathBatch is the new entry for callers that hold many queries.  Needs the
 // environment's collision checker to be "cudacollision".  Several initial / goal configurations, _minimumgoalpaths and the goal /
-// initial samplers (_samplegoalfn, _sampleinitialfn) are carried over; planner progress callbacks (_RegisterCallback) are not.
+// initial samplers (_samplegoalfn, _sampleinitialfn), the registered progress callbacks and _nMaxPlanningTime are carried over.
 class CudaBirrtPlanner : public PlannerBase
 {
 public:
@@ -1001,6 +1001,7 @@ public:
                                 : _parameters->_sPostProcessingPlanner == "linearsmoother 0" ? CC_POST_LINEARSMOOTHER_SHORTCUTS   // creation args (linearsmoother.cpp:25-26)
                                 : CC_POST_LINEARSMOOTHER;
         _birrt.minimum_goal_paths = (int32_t)_parameters->_minimumgoalpaths;     // plannerparameters.h:740 (1 unless the caller's XML set it)
+        _birrt.max_planning_time_ms = (int32_t)_parameters->_nMaxPlanningTime;    // milliseconds (planner.h; rrt.h:414-420)
         return PlannerStatus(PS_HasSolution);
     }
 
@@ -1015,6 +1016,7 @@ public:
         // _samplegoalfn / _sampleinitialfn (planner.h:298-311): asked once per iteration, like BirrtPlanner::PlanPath does (rrt.h:422-437)
         cc_planner_set_samplers(_planner, !!_parameters->_samplegoalfn ? &CudaBirrtPlanner::_SampleGoalThunk : NULL,
                                 !!_parameters->_sampleinitialfn ? &CudaBirrtPlanner::_SampleInitialThunk : NULL, this);
+        cc_planner_set_progress_callback(_planner, &CudaBirrtPlanner::_ProgressThunk, this);       // RegisterPlanCallback (planner.h:700-716)
         // several initial configurations and several goals (one per IK solution, say) are one problem (rrt.h:72-88, 327-343)
         EnvironmentLock lock(GetEnv()->GetMutex());
         const int32_t start_begin[2] = {0, ninitial}, goal_begin[2] = {0, ngoals};
@@ -1023,6 +1025,7 @@ public:
         if (cc_birrt_plan_batch_multi(_planner, &_birrt, 1, start_begin, _parameters->vinitialconfig.data(), goal_begin,
                                       _parameters->vgoalconfig.data(), &seed, &result) != CC_OK)
             throw OPENRAVE_EXCEPTION_FORMAT("cudabirrt: %s", cc_last_error(), ORE_Failed);
+        if (result.status == CC_PLAN_INTERRUPTED) return PlannerStatus("cudabirrt: planning was interrupted", PS_Interrupted);     // rrt.h:405-407
         if (result.status != CC_PLAN_SOLVED)
             return PlannerStatus("cudabirrt: no path", result.status == CC_PLAN_BAD_INITIAL ? (PS_Failed | PS_FailedDueToInitial)
                                                        : result.status == CC_PLAN_BAD_GOAL ? (PS_Failed | PS_FailedDueToGoal) : PS_Failed);
@@ -1069,6 +1072,12 @@ private:
         if (!fn(v) || (int)v.size() < ndof) return 0;
         std::copy(v.begin(), v.begin() + ndof, q_out);
         return 1;
+    }
+    static int _ProgressThunk(void* user, int, int iteration)
+    {
+        PlannerProgress progress;
+        progress._iteration = iteration;
+        return (int)static_cast<CudaBirrtPlanner*>(user)->_CallCallbacks(progress);     // PA_None / PA_Interrupt / PA_ReturnWithAnySolution
     }
     static int _SampleGoalThunk(void* user, int, int ndof, double* q_out) { return _SampleThunk(static_cast<CudaBirrtPlanner*>(user)->_parameters->_samplegoalfn, ndof, q_out); }
     static int _SampleInitialThunk(void* user, int, int ndof, double* q_out) { return _SampleThunk(static_cast<CudaBirrtPlanner*>(user)->_parameters->_sampleinitialfn, ndof, q_out); }

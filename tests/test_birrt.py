@@ -393,3 +393,37 @@ def test_birrt_may_start_without_goals_when_a_goal_sampler_is_set(wamtest1):
     assert r["status"] == pl.PLAN_SOLVED and r["goal_index"] == 0 and r["iterations"] >= 4
     assert np.array_equal(r["path"][0], good[0]) and np.array_equal(r["path"][-1], good[1])
     assert not orc.check_batch(robot, r["path"])["verdict"].any()
+
+
+def test_birrt_progress_callbacks_and_time_budget(wamtest1):
+    """PlannerBase::_CallCallbacks at the top of every iteration (rrt.h:401-412): PA_Interrupt ends the problem with PS_Interrupted,
+    PA_ReturnWithAnySolution ends a several-goals search at the first path; _nMaxPlanningTime (rrt.h:414-420) bounds the search."""
+    env, robot, orc = wamtest1
+    act = robot.GetActiveDOFIndices()
+    q = sample_configs(robot, 400, seed=21, active=act)
+    good = q[orc.check_batch(robot, q, active=act)["verdict"] == 0]
+    S, G = [good[0][None]], [good[1:4]]
+    base = pl.BirrtPlanner(robot, orc.group_checker(robot)).PlanBatchMulti(S, G, [5])[0]
+    assert base["status"] == pl.PLAN_SOLVED
+    seen = []
+    P = pl.BirrtPlanner(robot, orc.group_checker(robot))
+    P.SetProgressCallback(lambda problem, iteration: seen.append((problem, iteration)) or pl.PA_None)
+    r = P.PlanBatchMulti(S, G, [5])[0]
+    assert np.array_equal(r["path"], base["path"]) and len(seen) == r["iterations"] and seen[0] == (0, 0)
+    # interrupt at the first call
+    P.SetProgressCallback(lambda problem, iteration: pl.PA_Interrupt)
+    ri = P.PlanBatchMulti(S, G, [5])[0]
+    assert ri["status"] == pl.PLAN_INTERRUPTED and ri["iterations"] == 1 and len(ri["path"]) == 0
+    # three goals wanted, "return with any solution" from the start: the search ends at the first connection, which is the default run's
+    P3 = pl.BirrtPlanner(robot, orc.group_checker(robot), minimum_goal_paths=3)
+    full = P3.PlanBatchMulti(S, G, [5])[0]
+    P3.SetProgressCallback(lambda problem, iteration: pl.PA_ReturnWithAnySolution)
+    anyr = P3.PlanBatchMulti(S, G, [5])[0]
+    assert full["goal_paths"] == 3 and anyr["goal_paths"] == 1 and anyr["status"] == pl.PLAN_SOLVED
+    assert np.array_equal(anyr["path_raw"], base["path_raw"]) and anyr["iterations"] <= full["iterations"]
+    # a time budget that has already run out when the first iteration starts: no plan, no error
+    Pt = pl.BirrtPlanner(robot, orc.group_checker(robot), max_planning_time_ms=1)
+    import time
+    Pt.SetProgressCallback(lambda problem, iteration: time.sleep(0.01) or pl.PA_None)
+    rt = Pt.PlanBatchMulti(S, G, [5])[0]
+    assert rt["status"] == pl.PLAN_FAILED and rt["iterations"] == 1
