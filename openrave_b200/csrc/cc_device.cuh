@@ -648,7 +648,7 @@ cc_fk2_kernel(const __grid_constant__ Params P, const int group)
     }
     __syncthreads();
     // phase 2 reads its step constants with consecutive threads on consecutive steps: as 256-byte records every such load is a
-    // 32-way bank conflict (l1tex 87 % of peak, profiles/r02x_fk2_summary.md), as arrays it is conflict-free
+    // 32-way bank conflict (l1tex 87 % of peak in profiles/r02x_fk2_summary.md, 49 % after in r02y_fk2_summary.md), as arrays it is conflict-free
     for (int e = threadIdx.x; e < ni; e += blockDim.x) {
         if (e == 0) {
             s_meta[0] = 0; s_meta[ni] = 0; s_meta[2 * ni] = 0; s_meta[3 * ni] = 0;

@@ -567,7 +567,7 @@ struct SmemOpted { bool fk2 = false, broad = false; int dist_blocks_per_sm = 0; 
 SmemOpted g_smem_opted[64];
 
 // FK of m configurations on stream cs: the two-phase kernel (cc_fk2_kernel) unless its per-block pose table does not fit in shared
-// memory or CC_TUNE_FK2=0 asks for the one-thread-per-configuration form (A/B: profiles/r02q_ab_fk2.log)
+// memory or CC_TUNE_FK2=0 asks for the one-thread-per-configuration form (A/B: profiles/r02y_ab_fk2.log)
 int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
 {
     // the two-phase form pays when most links are rigidly attached to a few moving ones (PR2, arm + torso active: 8 varying steps,
