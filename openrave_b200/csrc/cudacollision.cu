@@ -571,8 +571,8 @@ SmemOpted g_smem_opted[64];
 int launch_fk(cc_scene* S, const ccdev::Params& P, int m, cudaStream_t cs)
 {
     // the two-phase form pays when most links are rigidly attached to a few moving ones (PR2, arm + torso active: 8 varying steps,
-    // 33 constant ones: +2.5 %); a chain of varying steps only (HIRO-NX, every DOF active) runs its serial phase with a quarter of
-    // the block and loses 8 % (profiles/r02q_ab.log).  CC_TUNE_FK2 = 0 / 1 forces one form.
+    // 33 constant ones: 95.8 -> 103.0 M configs/s); a chain of varying steps only (HIRO-NX, every DOF active) runs its serial phase
+    // with a quarter of the block and loses 7 % (profiles/r02y_ab_fk2.log).  CC_TUNE_FK2 = 0 / 1 forces one form.
     static const int tune_fk2 = getenv("CC_TUNE_FK2") ? atoi(getenv("CC_TUNE_FK2")) : -1;
     const int nvary = P.npose - 1, nconst = P.nsteps - nvary;
     const bool want_fk2 = tune_fk2 >= 0 ? tune_fk2 != 0 : ((P.flags & ccdev::kFlagPoseMode) != 0 || nconst >= 2 * nvary);
