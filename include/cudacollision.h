@@ -69,16 +69,23 @@ typedef struct cc_joint {
     int32_t parent_link;   /* Joint::GetHierarchyParentLink()->GetIndex() */
     int32_t child_link;    /* Joint::GetHierarchyChildLink()->GetIndex() */
     int32_t dof_index;     /* >= 0 for an active joint, -1 for passive/mimic */
-    int32_t mimic_dof;     /* DOF the mimic equation reads, -1 if not mimic */
+    int32_t mimic_dof;     /* DOF the mimic equation reads, -1 if not mimic, CC_MIMIC_EXTERNAL: evaluated by the caller (below) */
     int32_t is_static;     /* Joint::IsStatic() */
     int32_t is_circular;   /* Joint::IsCircular(0) */
-    int32_t reserved;
+    int32_t reserved;      /* CC_MIMIC_EXTERNAL: ordinal (0, 1, ...) of this joint among the body's externally evaluated ones */
     double mimic_a, mimic_b;
     double lower, upper;   /* Joint::GetLimits */
     double left[8];
     double right[8];
     double axis[4];        /* xyz + pad */
 } cc_joint;
+
+/* A mimic joint whose equation is not a*q[dof]+b (an fparser expression, several source joints): the reference evaluates it on
+ * the host per SetDOFValues call (kinbody.cpp:2308-2320, Joint::_Eval) and so does the caller here — for every configuration of a
+ * batch its raw value goes into column (number of active joint DOFs + ordinal) of q, before the affine columns; the library
+ * applies the mimic limit rules (kinbody.cpp:2326-2386) and the joint transform.  Pairs whose relative pose such a joint can
+ * change are never hoisted or certified. */
+enum { CC_MIMIC_EXTERNAL = -2 };
 
 /* Flags of the batched entry. */
 enum cc_batch_flags {

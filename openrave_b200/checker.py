@@ -195,6 +195,27 @@ class BoundQuery(object):
         self.links = self.links[:info.nlinks]
         self.nlinks_body = len(body.links)
         self.stale_own = False      # the query body itself moved since the last refresh (matters to the FK-mode entries only)
+        self.active = []            # DOF index of every joint column (set by bind)
+        self.externals = []         # mimic joints whose equation this side evaluates per configuration (CC_MIMIC_EXTERNAL)
+
+    def rows(self, q):
+        """The rows the C entry takes: [active joint values | values of the externally evaluated mimic joints | affine values].
+        The caller passes [active joint values | affine values]; the middle block is computed here the way SetDOFValues would
+        (clamped DOF values in, raw equation values out: the library applies the mimic limit rules)."""
+        ncols = max(self.info.ndof_active, 1)
+        if not self.externals:
+            return np.ascontiguousarray(q, dtype=np.float64).reshape(-1, ncols)
+        from .kinbody import external_mimic_values
+        ne, na = len(self.externals), len(self.active)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, ncols - ne)
+        body = self.body
+        full = np.tile(np.array(body.GetDOFValues(), dtype=np.float64), (q.shape[0], 1))
+        full[:, self.active] = q[:, :na]
+        for j in body.joints:                                    # SetDOFValues clamps non-circular DOF values first
+            if j.dofindex >= 0 and not j.circular:
+                full[:, j.dofindex] = np.clip(full[:, j.dofindex], j.lower, j.upper)
+        ext = external_mimic_values(body, full, self.externals)
+        return np.ascontiguousarray(np.hstack([q[:, :na], ext, q[:, na:]]))
 
     def refresh(self):
         """cc_query_refresh: re-read captured poses / inactive DOF values after bodies moved."""
@@ -254,7 +275,7 @@ class BoundQuery(object):
     def check(self, q, flags=BATCH_ENV | BATCH_SELF, want_mask=False, out=None):
         """`out` = (verdict u32[n], first_env i32[n], first_self i32[n]) lets a caller reuse (pinned) result buffers."""
         self._fresh_for_fk()
-        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+        q = self.rows(q)
         n = q.shape[0]
         if out is not None:
             verdict, fe, fs = out
@@ -286,7 +307,7 @@ class BoundQuery(object):
             fn = self.lib.cc_distance_poses
         else:
             self._fresh_for_fk()
-            a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+            a = self.rows(q)
             fn = self.lib.cc_distance_batch
         n = a.shape[0]
         dist = np.zeros(n, dtype=np.float64)
@@ -303,7 +324,7 @@ class BoundQuery(object):
             fn = self.lib.cc_tolerance_poses
         else:
             self._fresh_for_fk()
-            a = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+            a = self.rows(q)
             fn = self.lib.cc_tolerance_batch
         n = a.shape[0]
         mask = np.zeros((n, self.info.mask_words), dtype=np.uint32)
@@ -334,7 +355,7 @@ class BoundQuery(object):
 
     def fk(self, q):
         self._fresh_for_fk()
-        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, max(self.info.ndof_active, 1))
+        q = self.rows(q)
         n = q.shape[0]
         out = np.zeros((n, self.info.nlinks, 8), dtype=np.float64)
         self.checker._ck(self.lib.cc_fk_batch(self.handle, _ptr(q), n, _ptr(out)))
@@ -369,6 +390,7 @@ class CudaCollisionChecker(object):
         self._bodies = {}
         self._dirty = set()
         self._kin_dirty = set()
+        self._externals = {}
         self._options = 0
         self._queries = {}
         self._epoch = 0
@@ -524,7 +546,9 @@ class CudaCollisionChecker(object):
         bid = self._ids[id(body)]
         if id(body) in self._kin_dirty:
             if body.sorted_joints_all:
-                arr, n = flatten.joint_table(body)
+                ext = []
+                arr, n = flatten.joint_table(body, externals=ext)      # mimic equations the device cannot evaluate come back in `ext`
+                self._externals[bid] = ext
                 aff = flatten.affects_table(body)
                 self._ck(self.lib.cc_body_set_kinematics(self.scene, bid, body.GetDOF(), n, ctypes.addressof(arr), _ptr(aff)))
                 cur = np.array(body.GetDOFValues(), dtype=np.float64)
@@ -565,6 +589,8 @@ class CudaCollisionChecker(object):
                 act = np.array(active, dtype=np.int32)
                 self._ck(self.lib.cc_query_create(self.scene, bid, _ptr(act), len(active), opts, ctypes.byref(h)))
             q = BoundQuery(self, h, body)
+            q.active = list(active) if active is not None else list(range(body.GetDOF()))
+            q.externals = list(self._externals.get(bid, []))
             self._queries[key] = q
         return q
 

@@ -59,6 +59,7 @@ bool pair_rates(const HBody& B, const ChainInfo& ci, const std::vector<int>& col
     for (int side = 0; side < 2; ++side)
         for (int j : (side == 0 ? pa : pb)) {
             const cc_joint& J = B.joints[j];
+            if (J.mimic_dof == CC_MIMIC_EXTERNAL) return false;          // value supplied per configuration: not a function of one DOF we know
             if (J.mimic_dof >= 0) { if (col_of_dof[J.mimic_dof] >= 0) return false; continue; }
             if (J.is_static || J.dof_index < 0) continue;
             if (col_of_dof[J.dof_index] >= 0) varying.push_back(std::make_pair(j, side == 0));
@@ -194,6 +195,7 @@ static int build_pair_tables(cc_query* Q)
             bool ok = true;
             for (int idx = (int)path.size() - 1; idx >= 0 && ok; --idx) {
                 const cc_joint& J = B->joints[path[idx]];
+                if (J.mimic_dof == CC_MIMIC_EXTERNAL) { ok = false; continue; }
                 if (J.mimic_dof >= 0) { if (col_of_dof[J.mimic_dof] >= 0) { if (first < 0) ok = false; } continue; }
                 if (!J.is_static && J.dof_index >= 0 && col_of_dof[J.dof_index] >= 0 && first < 0) first = idx;
             }

@@ -492,7 +492,8 @@ struct cc_query {
     bool trace_work = false;
     int work_n = 0;
     std::vector<cc_query*> peers;            // the same query bound on every peer replica of a multi-device scene
-    int affine_mask = 0, naffine = 0;        // affine active DOFs: their columns follow the joint columns of q
+    int affine_mask = 0, naffine = 0;        // affine active DOFs: their columns are the last ones of q
+    int nexternal = 0;                       // externally evaluated mimic joints: their columns follow the active joint DOFs
     double affine_axis[4] = {0, 0, 1, 0}, affine_qstart[4] = {1, 0, 0, 0};
     // staging for the host-buffer API
     DevBuf<double> d_q, d_fk;
@@ -1134,6 +1135,8 @@ int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const c
         const cc_joint& j = joints[k];
         if (j.parent_link < 0 || j.parent_link >= nl || j.child_link < 0 || j.child_link >= nl) return fail(CC_ERR_INVALID, "joint link out of range");
         if (j.dof_index >= ndof || j.mimic_dof >= ndof) return fail(CC_ERR_INVALID, "joint dof out of range");
+        if (j.mimic_dof < -1 && (j.mimic_dof != CC_MIMIC_EXTERNAL || j.reserved < 0 || j.reserved >= 4096 || j.dof_index >= 0))
+            return fail(CC_ERR_INVALID, "externally evaluated mimic joint: mimic_dof = CC_MIMIC_EXTERNAL, reserved = its column ordinal, dof_index = -1");
         if (j.type != CC_JOINT_REVOLUTE && j.type != CC_JOINT_PRISMATIC) return fail(CC_ERR_UNSUPPORTED, "only 1-DOF revolute/prismatic joints");
     }
     b->ndof = ndof;
@@ -1575,14 +1578,17 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         if (act[c] < 0 || act[c] >= B->ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
         col_of_dof[act[c]] = (int)c;
     }
-    Q->ncols = (int)act.size() + Q->naffine;
+    // columns of q: active joint DOFs | values of externally evaluated mimic joints (CC_MIMIC_EXTERNAL, by ordinal) | affine DOFs
+    Q->nexternal = 0;
+    for (const cc_joint& j : B->joints) if (j.mimic_dof == CC_MIMIC_EXTERNAL) Q->nexternal = std::max(Q->nexternal, j.reserved + 1);
+    Q->ncols = (int)act.size() + Q->nexternal + Q->naffine;
     Q->col_of_dof = col_of_dof;
     Q->cur_active.assign((size_t)Q->ncols, 0.0);
     for (size_t c = 0; c < act.size(); ++c) Q->cur_active[c] = B->dofvals[act[c]];
     if (Q->naffine) {
         // the bound pose in affine coordinates — only the translation matters: the pairs evaluated at the bound values are the
         // pose-invariant (self) ones, and a base rotation does not change them
-        size_t c = act.size();
+        size_t c = act.size() + (size_t)Q->nexternal;
         for (int k = 0; k < 3; ++k) if (Q->affine_mask & (1 << k)) Q->cur_active[c++] = B->links.empty() ? 0.0 : B->links[0].xf[4 + k];
         if (Q->affine_mask & CC_DOF_RotationQuat) Q->cur_active[c] = 1.0;
     }
@@ -1591,6 +1597,12 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     for (int l = 0; l < nl; ++l)
         for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
     if (Q->naffine) std::fill(moves.begin(), moves.end(), (uint8_t)1);        // the base moves: so does every link
+    // an externally evaluated mimic joint takes a new value with every row whatever the active set is: everything below it moves
+    // (joints are listed parent before child; the chain compiler below rejects any other order)
+    for (const cc_joint& j : joints)
+        if (j.child_link >= 0 && j.child_link < nl && j.parent_link >= 0 && j.parent_link < nl &&
+            (j.mimic_dof == CC_MIMIC_EXTERNAL || moves[j.parent_link]))
+            moves[j.child_link] = 1;
 
     // ---- FK chain program
     Q->has_fk = true;
@@ -1646,6 +1658,14 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
             }
             if (src_circ) st.flags |= 8;
             st.a = j.mimic_a; st.b = j.mimic_b; st.lower = j.lower; st.upper = j.upper;
+            if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
+                // the equation is evaluated by the caller (fparser expressions the reference evaluates on the host too,
+                // kinbody.cpp:2308-2320): its value arrives as a column of q and goes through the mimic limit rules (:2326-2386)
+                st.src_col = (int)act.size() + j.reserved;
+                st.src_const = 0.0;
+                st.flags |= 2 | 8;                       // mimic; the "source" is the value itself: no source clamp
+                st.a = 1.0; st.b = 0.0;
+            }
             memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
             Q->steps.push_back(st);
         }
@@ -1657,6 +1677,28 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     }
     memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
     Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
+
+    // a self pair keeps its relative pose for the whole batch when no joint on the tree path between its two links is driven by
+    // an active DOF — directly, through a mimic equation, or by the caller (CC_MIMIC_EXTERNAL).  (Comparing the DOFs that affect
+    // the two links is not enough: a mimic joint between them may follow a DOF that moves both.)
+    std::vector<int> parent_joint(nl, -1);
+    std::vector<uint8_t> jdriven(joints.size(), 0);
+    for (size_t k = 0; k < joints.size(); ++k) {
+        const cc_joint& j = joints[k];
+        if (j.child_link >= 0 && j.child_link < nl) parent_joint[j.child_link] = (int)k;
+        if (j.is_static) continue;
+        const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+        jdriven[k] = j.mimic_dof == CC_MIMIC_EXTERNAL || (srcdof >= 0 && col_of_dof[srcdof] >= 0);
+    }
+    auto pose_invariant = [&](int a, int b) {
+        std::vector<int> pa, pb;
+        for (int l = a, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pa.push_back(parent_joint[l]); l = joints[parent_joint[l]].parent_link; }
+        for (int l = b, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pb.push_back(parent_joint[l]); l = joints[parent_joint[l]].parent_link; }
+        while (!pa.empty() && !pb.empty() && pa.back() == pb.back()) { pa.pop_back(); pb.pop_back(); }
+        for (int k : pa) if (jdriven[k]) return false;
+        for (int k : pb) if (jdriven[k]) return false;
+        return true;
+    };
 
     // ---- split the pair list and lay the three plans out
     const int np = (int)Q->quads.size() / 4;
@@ -1679,9 +1721,7 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         if (allow_hoist && Q->has_fk) {
             if (cls == 0) hoist = !moves[a];
             else {
-                const int b = Q->quads[4 * p + 2];
-                hoist = true;
-                for (int d : act) if (affects(d, a) != affects(d, b)) { hoist = false; break; }
+                hoist = pose_invariant(a, Q->quads[4 * p + 2]);
             }
         }
         (hoist ? p_hoist : p_main).push_back(p);

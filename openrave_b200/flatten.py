@@ -44,8 +44,13 @@ def link_mesh_arrays(link):
     return v, i
 
 
-def joint_table(body):
-    """The FK chain program: one cc_joint per entry of the dependency-ordered joint list."""
+CC_MIMIC_EXTERNAL = -2
+
+
+def joint_table(body, externals=None):
+    """The FK chain program: one cc_joint per entry of the dependency-ordered joint list.  A mimic equation that is not
+    a * q[dof] + b can only go to a caller that evaluates it per configuration (CC_MIMIC_EXTERNAL): pass a list as `externals`
+    and it receives those joints in column order; without it such a body raises NotImplementedError."""
     js = body.sorted_joints_all
     arr = (cc_joint * max(1, len(js)))()
     for k, j in enumerate(js):
@@ -58,14 +63,19 @@ def joint_table(body):
         c.mimic_a, c.mimic_b = 0.0, 0.0
         if j.mimic is not None:
             aff = j.mimic.affine()
-            if aff is None:
-                raise NotImplementedError("mimic joint %s: only affine single-DOF equations run on the device (%r)"
-                                          % (j.name, j.mimic.text))
-            src = body.GetJoint(aff[0])
-            if src is None or src.dofindex < 0:
-                raise NotImplementedError("mimic joint %s must read an active DOF" % j.name)
-            c.mimic_dof = src.dofindex
-            c.mimic_a, c.mimic_b = aff[1], aff[2]
+            src = body.GetJoint(aff[0]) if aff is not None else None
+            if aff is None or src is None or src.dofindex < 0:
+                if externals is None or j.IsStatic():
+                    if aff is None:
+                        raise NotImplementedError("mimic joint %s: only affine single-DOF equations run on the device (%r)"
+                                                  % (j.name, j.mimic.text))
+                    raise NotImplementedError("mimic joint %s must read an active DOF" % j.name)
+                c.mimic_dof = CC_MIMIC_EXTERNAL
+                c.reserved = len(externals)
+                externals.append(j)
+            else:
+                c.mimic_dof = src.dofindex
+                c.mimic_a, c.mimic_b = aff[1], aff[2]
             c.dof_index = -1
         c.is_static = 1 if j.IsStatic() else 0
         c.is_circular = 1 if j.circular else 0

@@ -223,6 +223,11 @@ class MimicExpr(object):
     def eval(self, values):
         return float(eval(self._code, {"__builtins__": {}}, dict(values)))
 
+    def eval_many(self, values, n):
+        """The same for n configurations at once: `values` maps joint names to arrays [n] (or scalars)."""
+        import numpy as np
+        return np.broadcast_to(np.asarray(eval(self._code, {"__builtins__": {}}, dict(values)), dtype=np.float64), (n,)).copy()
+
     def affine(self):
         """Return (varname, a, b) if the expression is affine in exactly one joint, else None."""
         if len(self.varnames) != 1:
@@ -947,6 +952,36 @@ def fk_transforms(body, vals, tbase, checklimits=True):
         ts[child.index] = rm.t_mul(tparent, tlocal)
         computed[child.index] = True
     return ts
+
+
+def external_mimic_values(body, vals, externals, checklimits=True):
+    """What a caller of the batched entry supplies for mimic joints whose equation the device cannot evaluate (CC_MIMIC_EXTERNAL):
+    their RAW equation values for n full DOF vectors `vals` [n, ndof] (already clamped like SetDOFValues clamps them,
+    kinbody.cpp:2149-2224), evaluated the way SetDOFValues' joint loop does (kinbody.cpp:2308-2386): a source that is itself a
+    passive mimic joint contributes its clamped value.  Returns [n, len(externals)]."""
+    import numpy as np
+    n = vals.shape[0]
+    out = np.zeros((n, len(externals)), dtype=np.float64)
+    passive_vals = {}
+    for j in body.sorted_joints_all:
+        if j.IsStatic() or j.mimic is None:
+            continue
+        env = {}
+        for src in j.mimic_src:
+            env[src.name] = vals[:, src.dofindex] if src.dofindex >= 0 else passive_vals.get(src.name, np.zeros(n))
+        ev = j.mimic.eval_many(env, n)
+        for k, e in enumerate(externals):
+            if e is j:
+                out[:, k] = ev
+        v = ev.copy()
+        if not j.circular:
+            lo = (ev < j.lower) & ((ev >= j.lower - G_EPSILON_JOINT_LIMIT) | (checklimits & (ev < j.lower - G_EPSILON_EVAL_JOINT_LIMIT)))
+            hi = (ev > j.upper) & ((ev <= j.upper + G_EPSILON_JOINT_LIMIT) | (checklimits & (ev > j.upper + G_EPSILON_EVAL_JOINT_LIMIT)))
+            v[lo] = j.lower
+            v[hi] = j.upper
+        if j.dofindex < 0:
+            passive_vals[j.name] = v
+    return out
 
 
 class Robot(KinBody):

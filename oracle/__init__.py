@@ -107,6 +107,7 @@ class OracleChecker(object):
         self.scene = None
         self._ids = {}
         self._dirty = set()
+        self._pose_only = set()      # bodies whose FK the C restatement cannot run (non-affine mimic): pose mode only
         self._options = 0
 
     # ---- CollisionCheckerBase surface
@@ -189,10 +190,18 @@ class OracleChecker(object):
     def _sync_kinematics(self, body):
         bid = self._ids[id(body)]
         if body.GetDOF() > 0:
-            arr, n = flatten.joint_table(body)
-            aff = flatten.affects_table(body)
-            cur = np.array(body.GetDOFValues(), dtype=np.float64)
-            self.lib.orc_body_set_kinematics(self.scene, bid, body.GetDOF(), n, ctypes.addressof(arr), _ptr(aff), _ptr(cur))
+            try:
+                arr, n = flatten.joint_table(body)
+                self._pose_only.discard(bid)
+            except NotImplementedError:
+                # a mimic equation the C restatement's FK does not evaluate: such a body is checked in pose mode only (the
+                # link poses then come from the harness' SetDOFValues, kinbody.fk_transforms)
+                self._pose_only.add(bid)
+                arr = None
+            if arr is not None:
+                aff = flatten.affects_table(body)
+                cur = np.array(body.GetDOFValues(), dtype=np.float64)
+                self.lib.orc_body_set_kinematics(self.scene, bid, body.GetDOF(), n, ctypes.addressof(arr), _ptr(aff), _ptr(cur))
         if len(body.links) > 1:
             na = np.array(body.GetNonAdjacentLinks(0, checker=self), dtype=np.int32)
         else:
@@ -231,6 +240,8 @@ class OracleChecker(object):
             n = q.shape[0]
             opt.pose_mode = 1
         else:
+            if bid in self._pose_only:
+                raise NotImplementedError("%s has a mimic equation the oracle's FK does not evaluate: pass poses" % body.name)
             q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active) + flatten.affine_count(getattr(body, "affine_dofs", 0)))
             n = q.shape[0]
         nl = len(body.links) + sum(len(g.body.links) for g in getattr(body, "grabbed", []))   # grabbed links follow the body's own
