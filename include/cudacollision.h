@@ -383,6 +383,17 @@ int cc_debug_build_bvh(const double* vertices, int nvertices, const int32_t* tri
  * every link pair, so a pair may only ever be dropped when its boxes are disjoint). */
 int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, uint8_t* out);
 
+/* Diagnostic (no device needed): what a bound query treats as fixed for the length of a batch — the host rule behind
+ * cc_query_info.npairs_hoisted.  joints / affects as for cc_body_set_kinematics (affects: [ndof][nlinks]); active: the active DOF
+ * indices; base_moves: affine DOFs are active.  out_moves[l] = 1 when link l's world pose depends on the rows of q (an active DOF
+ * affects it, KinBody::DoesAffect kinbody.cpp:4787-4818; the base moves; a CC_MIMIC_EXTERNAL joint sits above it);
+ * out_invariant[p] = 1 when the pose of link pairs[2p+1] in the frame of link pairs[2p] cannot change: no joint on the tree path
+ * between the two is driven by an active DOF, directly, through a mimic equation, or by the caller.  An environment pair is
+ * evaluated once at bind time when its link does not move, a self pair when it is invariant; the reference evaluates every pair
+ * at every configuration (collisionPQP.h:364-417), so either flag may only be set when the verdict cannot change. */
+int cc_debug_motion_classes(const cc_joint* joints, int njoints, int nlinks, int ndof, const uint8_t* affects, const int32_t* active,
+                            int nactive, int base_moves, const int32_t* pairs, int npairs, uint8_t* out_moves, uint8_t* out_invariant);
+
 /* ==== planners on the batched entry (BASELINE.json configs[2]) =========================================
  * The reference's RRT family spends its time in PlannerParameters::CheckPathAllConstraints (planner.h:373-379) ->
  * DynamicsCollisionConstraint::Check (planningutils.cpp:2586-3629), one sample at a time.  These entry points run the same

@@ -19,6 +19,7 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/cudacollision.h"
@@ -1551,6 +1552,52 @@ static int evaluate_hoisted(cc_query* Q)
     return CC_OK;
 }
 
+// What a batch can change.  `moves[l]`: link l's WORLD pose depends on the rows of q — an active DOF affects it
+// (KinBody::DoesAffect, which follows mimic equations to their source DOFs), the base itself moves (affine DOFs), or an
+// externally evaluated mimic joint (CC_MIMIC_EXTERNAL: a new value with every row whatever the active set is) sits above it.
+// `pose_invariant(a, b)`: the pose of link b in link a's frame cannot change — no joint on the tree path between them is driven
+// by an active DOF, directly, through a mimic equation, or by the caller.  (Comparing the DOFs that affect the two links is not
+// enough: a mimic joint between them may follow a DOF that moves both.)
+struct MotionClasses {
+    std::vector<uint8_t> moves;          // per link
+    std::vector<int> parent_joint;       // per link: the joint whose child it is, -1 for the root
+    std::vector<uint8_t> jdriven;        // per joint
+    const std::vector<cc_joint>* joints = nullptr;
+
+    void build(const std::vector<cc_joint>& J, int nl, const std::vector<int>& act, const std::vector<int>& col_of_dof, bool base_moves,
+               const std::function<bool(int, int)>& affects)
+    {
+        joints = &J;
+        moves.assign((size_t)nl, 0);
+        for (int l = 0; l < nl; ++l)
+            for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
+        if (base_moves) std::fill(moves.begin(), moves.end(), (uint8_t)1);
+        parent_joint.assign((size_t)nl, -1);
+        jdriven.assign(J.size(), 0);
+        // (joints are listed parent before child; the chain compiler rejects any other order)
+        for (size_t k = 0; k < J.size(); ++k) {
+            const cc_joint& j = J[k];
+            if (j.child_link < 0 || j.child_link >= nl || j.parent_link < 0 || j.parent_link >= nl) continue;
+            parent_joint[j.child_link] = (int)k;
+            if (j.mimic_dof == CC_MIMIC_EXTERNAL || moves[j.parent_link]) moves[j.child_link] = 1;
+            if (j.is_static) continue;
+            const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+            jdriven[k] = j.mimic_dof == CC_MIMIC_EXTERNAL || (srcdof >= 0 && srcdof < (int)col_of_dof.size() && col_of_dof[srcdof] >= 0);
+        }
+    }
+    bool pose_invariant(int a, int b) const
+    {
+        const std::vector<cc_joint>& J = *joints;
+        std::vector<int> pa, pb;
+        for (int l = a, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pa.push_back(parent_joint[l]); l = J[parent_joint[l]].parent_link; }
+        for (int l = b, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pb.push_back(parent_joint[l]); l = J[parent_joint[l]].parent_link; }
+        while (!pa.empty() && !pb.empty() && pa.back() == pb.back()) { pa.pop_back(); pb.pop_back(); }
+        for (int k : pa) if (jdriven[k]) return false;
+        for (int k : pb) if (jdriven[k]) return false;
+        return true;
+    }
+};
+
 static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool all_dofs_active, bool allow_hoist)
 {
     cc_scene* S = Q->scene;
@@ -1593,16 +1640,9 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         if (Q->affine_mask & CC_DOF_RotationQuat) Q->cur_active[c] = 1.0;
     }
     auto affects = [&](int d, int l) { return B->affects[(size_t)d * nlb + Q->ql_host[l]] != 0; };
-    std::vector<uint8_t> moves(nl, 0);
-    for (int l = 0; l < nl; ++l)
-        for (int d : act) if (affects(d, l)) { moves[l] = 1; break; }
-    if (Q->naffine) std::fill(moves.begin(), moves.end(), (uint8_t)1);        // the base moves: so does every link
-    // an externally evaluated mimic joint takes a new value with every row whatever the active set is: everything below it moves
-    // (joints are listed parent before child; the chain compiler below rejects any other order)
-    for (const cc_joint& j : joints)
-        if (j.child_link >= 0 && j.child_link < nl && j.parent_link >= 0 && j.parent_link < nl &&
-            (j.mimic_dof == CC_MIMIC_EXTERNAL || moves[j.parent_link]))
-            moves[j.child_link] = 1;
+    MotionClasses motion;
+    motion.build(joints, nl, act, col_of_dof, Q->naffine != 0, affects);
+    const std::vector<uint8_t>& moves = motion.moves;
 
     // ---- FK chain program
     Q->has_fk = true;
@@ -1678,28 +1718,6 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     memcpy(Q->base, B->links.empty() ? std::vector<double>(8, 0).data() : B->links[0].xf, sizeof(Q->base));
     Q->center[0] = Q->base[4]; Q->center[1] = Q->base[5]; Q->center[2] = Q->base[6];
 
-    // a self pair keeps its relative pose for the whole batch when no joint on the tree path between its two links is driven by
-    // an active DOF — directly, through a mimic equation, or by the caller (CC_MIMIC_EXTERNAL).  (Comparing the DOFs that affect
-    // the two links is not enough: a mimic joint between them may follow a DOF that moves both.)
-    std::vector<int> parent_joint(nl, -1);
-    std::vector<uint8_t> jdriven(joints.size(), 0);
-    for (size_t k = 0; k < joints.size(); ++k) {
-        const cc_joint& j = joints[k];
-        if (j.child_link >= 0 && j.child_link < nl) parent_joint[j.child_link] = (int)k;
-        if (j.is_static) continue;
-        const int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
-        jdriven[k] = j.mimic_dof == CC_MIMIC_EXTERNAL || (srcdof >= 0 && col_of_dof[srcdof] >= 0);
-    }
-    auto pose_invariant = [&](int a, int b) {
-        std::vector<int> pa, pb;
-        for (int l = a, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pa.push_back(parent_joint[l]); l = joints[parent_joint[l]].parent_link; }
-        for (int l = b, g = 0; l >= 0 && parent_joint[l] >= 0 && g < 1 << 16; ++g) { pb.push_back(parent_joint[l]); l = joints[parent_joint[l]].parent_link; }
-        while (!pa.empty() && !pb.empty() && pa.back() == pb.back()) { pa.pop_back(); pb.pop_back(); }
-        for (int k : pa) if (jdriven[k]) return false;
-        for (int k : pb) if (jdriven[k]) return false;
-        return true;
-    };
-
     // ---- split the pair list and lay the three plans out
     const int np = (int)Q->quads.size() / 4;
     Q->mask_words = std::max(1, (np + 31) / 32);
@@ -1721,7 +1739,7 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
         if (allow_hoist && Q->has_fk) {
             if (cls == 0) hoist = !moves[a];
             else {
-                hoist = pose_invariant(a, Q->quads[4 * p + 2]);
+                hoist = motion.pose_invariant(a, Q->quads[4 * p + 2]);
             }
         }
         (hoist ? p_hoist : p_main).push_back(p);
@@ -2537,6 +2555,29 @@ int cc_scene_get_stats(const cc_scene* sc, cc_stats* out)
 
 // Diagnostic, no device needed: the broadphase kernel's box test on the host — the very functions cc_broad_kernel compiles
 // (quantise_box, qbox_overlap), so that a CPU test can check that an overlap of the FP32 boxes is never lost.
+extern "C" int cc_debug_motion_classes(const cc_joint* joints, int njoints, int nlinks, int ndof, const uint8_t* affects, const int32_t* active,
+                                       int nactive, int base_moves, const int32_t* pairs, int npairs, uint8_t* out_moves, uint8_t* out_invariant)
+{
+    if (!joints || njoints < 0 || nlinks <= 0 || ndof < 0 || (ndof && !affects) || nactive < 0 || (nactive && !active) || npairs < 0 ||
+        (npairs && (!pairs || !out_invariant)) || !out_moves)
+        return fail(CC_ERR_INVALID, "cc_debug_motion_classes: bad arguments");
+    std::vector<cc_joint> J(joints, joints + njoints);
+    std::vector<int> act(active, active + nactive), col_of_dof((size_t)ndof, -1);
+    for (int c = 0; c < nactive; ++c) {
+        if (act[c] < 0 || act[c] >= ndof) return fail(CC_ERR_INVALID, "cc_debug_motion_classes: active DOF index out of range");
+        col_of_dof[act[c]] = c;
+    }
+    MotionClasses m;
+    m.build(J, nlinks, act, col_of_dof, base_moves != 0, [&](int d, int l) { return affects[(size_t)d * nlinks + l] != 0; });
+    memcpy(out_moves, m.moves.data(), (size_t)nlinks);
+    for (int p = 0; p < npairs; ++p) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        if (a < 0 || a >= nlinks || b < 0 || b >= nlinks) return fail(CC_ERR_INVALID, "cc_debug_motion_classes: link out of range");
+        out_invariant[p] = m.pose_invariant(a, b) ? 1 : 0;
+    }
+    return CC_OK;
+}
+
 extern "C" int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, uint8_t* out)
 {
     if (!boxes_a || !boxes_b || !out || n < 0) return fail(CC_ERR_INVALID, "cc_debug_broad_overlap: bad arguments");
