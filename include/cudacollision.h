@@ -111,6 +111,8 @@ typedef struct cc_query_info {
     int32_t mask_words;        /* uint32 words per configuration in the pair bitmask */
     int32_t total_nodes;       /* BVH nodes resident on the device */
     int32_t total_tris;        /* triangles resident on the device */
+    int32_t nexternal;         /* of ndof_active: columns holding CC_MIMIC_EXTERNAL joint values (after the active joint DOFs) */
+    int32_t reserved;
 } cc_query_info;
 
 typedef struct cc_stats {
@@ -189,6 +191,15 @@ int cc_body_release_grabbed(cc_scene* s, int body, int grabbed_body);
 /* ---- kinematics of a body, read off a computed KinBody (used by the batched entry only) */
 int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const cc_joint* joints_in_fk_order,
                            const uint8_t* dof_affects_link /* [ndof][nlinks], KinBody::DoesAffect != 0 */);
+
+/* Optional evaluator for CC_MIMIC_EXTERNAL joints, for callers that have the equation text but no evaluator of their own (from
+ * outside KinBody the reference offers none: OpenRAVEFunctionParserReal is opaque, kinbody.h:27-28).  `equation` is the joint's
+ * mimic_pos string (Joint::GetMimicEquation(0, 0)) in fparser syntax over joint names; joint_names[njoints] names the joints of
+ * cc_body_set_kinematics in the same order.  The library compiles it (operators () ^ unary- ! * / % + - = != < <= > >= & |,
+ * fparser's elementary functions and if(); inline variables and OpenRAVE's polyroots* / SSSA / SASA / SASS helpers are refused with
+ * CC_ERR_UNSUPPORTED and the position of the error in cc_last_error()).  Call after cc_body_set_kinematics, which forgets all
+ * equations. */
+int cc_body_set_mimic_equation(cc_scene* s, int body, int joint, const char* equation, const char* const* joint_names, int njoints);
 /* KinBody::GetDOFValues(): the values the DOFs that are NOT active in a query keep (robot.cpp:1193-1225) */
 int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof);
 /* KinBody::GetNonAdjacentLinks(0): packed pairs in CompareNonAdjacentFarthest order */
@@ -226,6 +237,15 @@ int cc_query_create_affine(cc_scene* s, int body, const int32_t* active_dofs, in
 int cc_query_refresh(cc_query* q);
 int cc_query_destroy(cc_query* q);
 int cc_query_get_info(const cc_query* q, cc_query_info* info);
+
+/* Host-side: rows [active joint DOFs | affine DOFs] -> the rows the batched entries take, [active joint DOFs | values of the
+ * CC_MIMIC_EXTERNAL joints | affine DOFs] (cc_query_info.ndof_active columns), using the equations registered with
+ * cc_body_set_mimic_equation: per row the value part of SetDOFValues' joint loop (kinbody.cpp:2149-2224, 2286-2400) — DOF values
+ * clamped, inactive DOFs at the body's current values, joints in the listed order, an equation reading a passive joint gets the
+ * value the limit rules gave it.  An equation that fails to evaluate (fparser's EvalError: division by zero, sqrt / log / trig
+ * domain) fails the call with CC_ERR_INVALID naming the joint and the row; the reference logs a warning and keeps the previous
+ * passive value (kinbody.cpp:2318-2320).  CC_ERR_STATE when an external joint has no equation. */
+int cc_query_expand_rows(cc_query* q, const double* q_in, int64_t n, double* q_out);
 /* pair index -> {query link, other body, other link, 0=env|1=self}, [npairs][4] */
 int cc_query_get_pairs(const cc_query* q, int32_t* out_quads);
 /* query link index -> {body, link}, [nlinks][2]: the body's own links first, then the links of its grabbed bodies */
@@ -393,6 +413,16 @@ int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, ui
  * at every configuration (collisionPQP.h:364-417), so either flag may only be set when the verdict cannot change. */
 int cc_debug_motion_classes(const cc_joint* joints, int njoints, int nlinks, int ndof, const uint8_t* affects, const int32_t* active,
                             int nactive, int base_moves, const int32_t* pairs, int npairs, uint8_t* out_moves, uint8_t* out_invariant);
+
+/* Diagnostics (no device needed) of the mimic-equation evaluator.  cc_debug_mimic_eval: out[i] = equation(values[i][0..nnames)),
+ * err[i] = fparser's EvalError code (0 fine, 1 division by zero, 2 sqrt, 3 log, 4 trig domain) or 5 for a power / a result that
+ * is NaN or infinite, which fparser reports as one of its codes or not at all depending on how it rewrote the power; out[i] is then 0.
+ * cc_debug_expand_rows: cc_query_expand_rows on explicit arguments — equations[njoints] holds the text for CC_MIMIC_EXTERNAL joints
+ * and NULL elsewhere, dofvals the body's current DOF values, active the active DOF indices. */
+int cc_debug_mimic_eval(const char* equation, const char* const* names, int nnames, const double* values, int64_t n, double* out, int32_t* err);
+int cc_debug_expand_rows(const cc_joint* joints, int njoints, int ndof, const double* dofvals, const char* const* equations,
+                         const char* const* joint_names, const int32_t* active, int nactive, int naffine, const double* q_in, int64_t n,
+                         double* q_out);
 
 /* ==== planners on the batched entry (BASELINE.json configs[2]) =========================================
  * The reference's RRT family spends its time in PlannerParameters::CheckPathAllConstraints (planner.h:373-379) ->

@@ -34,7 +34,7 @@ class CudaCollisionError(RuntimeError):
 
 class cc_query_info(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("ndof_active", "nlinks", "npairs_env", "npairs_self", "npairs_hoisted",
-                                              "mask_words", "total_nodes", "total_tris")]
+                                              "mask_words", "total_nodes", "total_tris", "nexternal", "reserved")]
 
 
 class cc_certificate(ctypes.Structure):
@@ -65,7 +65,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
-           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_debug_broad_overlap", "cc_debug_motion_classes", "cc_query_get_certificates", "cc_debug_pair_rates",
+           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_debug_broad_overlap", "cc_debug_motion_classes", "cc_body_set_mimic_equation", "cc_query_expand_rows", "cc_debug_mimic_eval", "cc_debug_expand_rows", "cc_query_get_certificates", "cc_debug_pair_rates",
            "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices", "cc_query_create_affine",
            "cc_body_set_link_primitives", "cc_scene_set_analytic_primitives"]
 
@@ -124,6 +124,11 @@ def load_library():
     lib.cc_query_get_certificates.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     lib.cc_debug_pair_rates.argtypes = [vp, ci, ci, vp, ci, ci, ci, cd, cd, vp, vp, ctypes.POINTER(ci)]
     lib.cc_debug_motion_classes.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, vp, ci, vp, vp]
+    cpp = ctypes.POINTER(ctypes.c_char_p)
+    lib.cc_body_set_mimic_equation.argtypes = [vp, ci, ci, ctypes.c_char_p, cpp, ci]
+    lib.cc_query_expand_rows.argtypes = [vp, vp, ctypes.c_int64, vp]
+    lib.cc_debug_mimic_eval.argtypes = [ctypes.c_char_p, cpp, ci, vp, ctypes.c_int64, vp, vp]
+    lib.cc_debug_expand_rows.argtypes = [vp, ci, ci, vp, cpp, cpp, vp, ci, ci, vp, ctypes.c_int64, vp]
     lib.cc_debug_broad_overlap.argtypes = [vp, vp, ci, vp]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
@@ -651,6 +656,19 @@ class CudaCollisionChecker(object):
             depth = float(np.linalg.norm(p2 - p1))
             norm = (p2 - p1) / depth if depth > 0 else np.zeros(3)
             report.contacts = [(p1.copy(), norm, -depth)]
+
+    def RegisterMimicEquations(self, body, active=None):
+        """Hand the text of the body's non-affine mimic equations to the library (cc_body_set_mimic_equation), so that callers
+        without an evaluator of their own — the planner host (cc_planner_set_query) and cc_query_expand_rows — can fill the
+        CC_MIMIC_EXTERNAL columns.  This twin keeps evaluating them itself (BoundQuery.rows).  Returns the number registered."""
+        bq = self.bind(body, active)                       # makes sure the kinematics went over
+        bid = self._ids[id(body)]
+        js = body.sorted_joints_all
+        names = (ctypes.c_char_p * max(len(js), 1))(*[j.name.encode() for j in js])
+        for e in bq.externals:
+            k = [i for i, j in enumerate(js) if j is e][0]
+            self._ck(self.lib.cc_body_set_mimic_equation(self.scene, bid, k, e.mimic.text.replace("**", "^").encode(), names, len(js)))
+        return len(bq.externals)
 
     def ForwardKinematicsBatch(self, robot, q, active=None):
         return self.bind(robot, active).fk(q)

@@ -481,6 +481,7 @@ struct cc_planner {
     uint64_t totals[4] = {0, 0, 0, 0};
     // page-locked staging for the GPU checker (cc_host_alloc): configurations in, verdicts out
     double* pin_q = nullptr; size_t pin_q_cap = 0;
+    int query_cols = 0;              // columns of the rows the bound query takes: cs.n + its host-evaluated mimic columns
     uint32_t* pin_v = nullptr; size_t pin_v_cap = 0;
     ~cc_planner() { if (pin_q) cc_host_free(pin_q); if (pin_v) cc_host_free(pin_v); }
 };
@@ -1248,7 +1249,8 @@ int gpu_group_check(cc_planner* p, const double* cfg, int nconfigs, int ndof, co
                     const int32_t* segment_begin, int32_t* first_fail_segment, int32_t* fail_verdict, int32_t* first_fail_config)
 {
     // stage through page-locked buffers: the copies of small batches then cost a few microseconds instead of tens
-    const size_t need_q = (size_t)std::max(nconfigs, 1) * ndof, need_v = (size_t)std::max(nconfigs, 1);
+    const int cols = std::max(ndof, p->query_cols);
+    const size_t need_q = (size_t)std::max(nconfigs, 1) * cols, need_v = (size_t)std::max(nconfigs, 1);
     if (need_q > p->pin_q_cap) {
         if (p->pin_q) cc_host_free(p->pin_q);
         p->pin_q = nullptr; p->pin_q_cap = 0;
@@ -1267,7 +1269,12 @@ int gpu_group_check(cc_planner* p, const double* cfg, int nconfigs, int ndof, co
     }
     uint32_t* verdict = p->pin_v;
     if (nconfigs > 0) {
-        std::memcpy(p->pin_q, cfg, (size_t)nconfigs * ndof * sizeof(double));
+        if (cols == ndof) std::memcpy(p->pin_q, cfg, (size_t)nconfigs * ndof * sizeof(double));
+        else {
+            // the body has mimic equations the device cannot hold: the library evaluates them per configuration on the host
+            const int rce = cc_query_expand_rows(p->query, cfg, nconfigs, p->pin_q);
+            if (rce != CC_OK) return rce;
+        }
         const int rc = cc_check_batch(p->query, p->pin_q, nconfigs, CC_BATCH_ENV | CC_BATCH_SELF | CC_BATCH_FIRST_HIT, verdict, nullptr, nullptr, nullptr);
         if (rc != CC_OK) return rc;
     }
@@ -1317,8 +1324,9 @@ int cc_planner_set_query(cc_planner* p, cc_query* q)
     cc_query_info info;
     const int rc = cc_query_get_info(q, &info);
     if (rc != CC_OK) return rc;
-    if (info.ndof_active != p->cs.n) return fail(CC_ERR_INVALID, "cc_planner_set_query: the query's active DOFs differ from the planner's");
+    if (info.ndof_active - info.nexternal != p->cs.n) return fail(CC_ERR_INVALID, "cc_planner_set_query: the query's active DOFs differ from the planner's");
     p->query = q;
+    p->query_cols = info.ndof_active;
     p->fn = nullptr;
     return CC_OK;
 }

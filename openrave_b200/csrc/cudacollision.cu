@@ -26,6 +26,7 @@
 #include "cc_device.cuh"
 #include "cc_distance.cuh"
 #include "cc_analytic.cuh"
+#include "cc_mimic_expr.h"
 
 namespace {
 
@@ -78,6 +79,8 @@ struct HBody {
         std::vector<int32_t> noncolliding;  // (body, link) pairs: Grabbed::_listNonCollidingLinksWhenGrabbed
     };
     std::vector<Grab> grabs;
+    // equations of CC_MIMIC_EXTERNAL joints handed over with cc_body_set_mimic_equation: [njoints], empty where there is none
+    std::vector<ccexpr::Program> mimic_prog;
 };
 
 const float kBoxInflate = 1e-5f;   // metres added to every half extent (conservative pruning, see cc_device.cuh)
@@ -1144,7 +1147,151 @@ int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const c
     b->joints.assign(joints, joints + njoints);
     b->affects.assign(affects, affects + (size_t)ndof * nl);
     if ((int)b->dofvals.size() != ndof) b->dofvals.assign(ndof, 0.0);
+    b->mimic_prog.assign((size_t)njoints, ccexpr::Program());
     return forward_peers(s, [&](cc_scene* p) { return cc_body_set_kinematics(p, body, ndof, njoints, joints, affects); });
+}
+
+// ---- mimic equations the chain program cannot hold: evaluated on the host, handed to the device as columns of q
+namespace {
+// The value a mimic joint takes for the evaluated `ev` (kinbody.cpp:2326-2375; same rule as ccdev::joint_transform).
+inline double mimic_limit_rule(double ev, const cc_joint& j)
+{
+    if (j.is_circular) return ev;
+    if (ev < j.lower) { if (ev >= j.lower - CC_EPSILON_JOINT_LIMIT || ev < j.lower - CC_EPSILON_EVAL_JOINT_LIMIT) return j.lower; }
+    else if (ev > j.upper) { if (ev <= j.upper + CC_EPSILON_JOINT_LIMIT || ev > j.upper + CC_EPSILON_EVAL_JOINT_LIMIT) return j.upper; }
+    return ev;
+}
+
+// rows [active joint values | affine values] -> rows [active joint values | raw values of the CC_MIMIC_EXTERNAL joints by ordinal |
+// affine values], the layout the batched entries take.  Per row this is the part of SetDOFValues' joint loop that produces joint
+// VALUES (kinbody.cpp:2149-2224 clamp, 2286-2400 loop): DOF values clamped to their limits, joints in the listed (dependency)
+// order, an equation reads DOF values directly and passive joints through the value the loop gave them.
+int expand_rows_host(const std::vector<cc_joint>& J, int ndof, const double* dofvals, const std::vector<ccexpr::Program>& prog,
+                     const int32_t* active, int nactive, int naffine, int nexternal, const double* q_in, int64_t n, double* q_out)
+{
+    const int nj = (int)J.size();
+    std::vector<double> lo((size_t)ndof, 0.0), hi((size_t)ndof, 0.0);
+    std::vector<uint8_t> circ((size_t)ndof, 1);
+    for (const cc_joint& j : J)
+        if (j.dof_index >= 0 && j.dof_index < ndof) { lo[j.dof_index] = j.lower; hi[j.dof_index] = j.upper; circ[j.dof_index] = j.is_circular != 0; }
+    for (int k = 0; k < nj; ++k)
+        if (J[k].mimic_dof == CC_MIMIC_EXTERNAL && !J[k].is_static && (k >= (int)prog.size() || prog[k].ops.empty())) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "joint %d is CC_MIMIC_EXTERNAL and has no equation (cc_body_set_mimic_equation)", k);
+            return fail(CC_ERR_STATE, msg);
+        }
+    std::vector<double> full((size_t)ndof), jv((size_t)nj);
+    const int nin = nactive + naffine, nout = nactive + nexternal + naffine;
+    for (int64_t i = 0; i < n; ++i) {
+        const double* in = q_in + (size_t)i * nin;
+        double* out = q_out + (size_t)i * nout;
+        for (int d = 0; d < ndof; ++d) full[d] = dofvals[d];
+        for (int c = 0; c < nactive; ++c) full[active[c]] = in[c];
+        for (int d = 0; d < ndof; ++d)
+            if (!circ[d]) full[d] = full[d] < lo[d] ? lo[d] : full[d] > hi[d] ? hi[d] : full[d];
+        for (int k = 0; k < nj; ++k) jv[k] = J[k].dof_index >= 0 ? full[J[k].dof_index] : 0.0;
+        for (int e = 0; e < nexternal; ++e) out[nactive + e] = 0.0;
+        for (int k = 0; k < nj; ++k) {
+            const cc_joint& j = J[k];
+            if (j.is_static || j.dof_index >= 0) continue;
+            if (j.mimic_dof >= 0) jv[k] = mimic_limit_rule(j.mimic_a * full[j.mimic_dof] + j.mimic_b, j);
+            else if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
+                int err = 0;
+                const double ev = prog[k].eval(jv.data(), &err);
+                if (err) {
+                    char msg[200];
+                    snprintf(msg, sizeof(msg), "the mimic equation of joint %d failed to evaluate at row %lld (error %d: %s)", k, (long long)i, err,
+                             err == 1 ? "division by zero" : err == 2 ? "sqrt of a negative value" : err == 3 ? "log of a non-positive value" : err == 4 ? "trigonometric domain" : "value not finite");
+                    return fail(CC_ERR_INVALID, msg);
+                }
+                out[nactive + j.reserved] = ev;
+                jv[k] = mimic_limit_rule(ev, j);
+            } else jv[k] = j.is_circular ? 0.0 : (0.0 < j.lower ? j.lower : 0.0 > j.upper ? j.upper : 0.0);   // passive: 0 clamped (kinbody.cpp:2262-2275)
+        }
+        for (int c = 0; c < nactive; ++c) out[c] = in[c];
+        for (int c = 0; c < naffine; ++c) out[nactive + nexternal + c] = in[nactive + c];
+    }
+    return CC_OK;
+}
+
+int compile_equation(const char* equation, const char* const* joint_names, int njoints, ccexpr::Program& prog)
+{
+    int pos = 0;
+    std::string why;
+    if (!ccexpr::compile(equation, joint_names, njoints, prog, &pos, &why)) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "mimic equation '%.200s': %s at position %d", equation ? equation : "", why.c_str(), pos);
+        return fail(CC_ERR_UNSUPPORTED, msg);
+    }
+    return CC_OK;
+}
+}   // namespace
+
+int cc_body_set_mimic_equation(cc_scene* s, int body, int joint, const char* equation, const char* const* joint_names, int njoints)
+{
+    HBody* b = get_body(s, body);
+    if (!b || !equation || !joint_names) return fail(CC_ERR_INVALID, "bad arguments");
+    if (njoints != (int)b->joints.size()) return fail(CC_ERR_INVALID, "cc_body_set_mimic_equation: one name per joint of cc_body_set_kinematics, in the same order");
+    if (joint < 0 || joint >= njoints || b->joints[joint].mimic_dof != CC_MIMIC_EXTERNAL)
+        return fail(CC_ERR_INVALID, "cc_body_set_mimic_equation: the joint is not declared CC_MIMIC_EXTERNAL");
+    ccexpr::Program prog;
+    const int rc = compile_equation(equation, joint_names, njoints, prog);
+    if (rc != CC_OK) return rc;
+    // a variable must have its value when this joint's turn comes: a DOF, or a passive joint listed earlier
+    for (int v : prog.vars)
+        if (b->joints[v].dof_index < 0 && v >= joint) return fail(CC_ERR_INVALID, "cc_body_set_mimic_equation: the equation reads a passive joint listed after this one");
+    b->mimic_prog.resize((size_t)njoints);
+    b->mimic_prog[joint] = prog;
+    return CC_OK;                      // host-side only: peer replicas take the expanded rows
+}
+
+int cc_query_expand_rows(cc_query* q, const double* q_in, int64_t n, double* q_out)
+{
+    if (!q || n < 0 || (n > 0 && (!q_in || !q_out))) return fail(CC_ERR_INVALID, "bad arguments");
+    const HBody* B = q->scene->bodies[q->body];
+    const int nactive = q->ncols - q->nexternal - q->naffine;
+    std::vector<int32_t> active((size_t)nactive, -1);
+    for (int d = 0; d < (int)q->col_of_dof.size(); ++d) if (q->col_of_dof[d] >= 0 && q->col_of_dof[d] < nactive) active[q->col_of_dof[d]] = d;
+    return expand_rows_host(B->joints, B->ndof, B->dofvals.data(), B->mimic_prog, active.data(), nactive, q->naffine, q->nexternal, q_in, n, q_out);
+}
+
+int cc_debug_mimic_eval(const char* equation, const char* const* names, int nnames, const double* values, int64_t n, double* out, int32_t* err)
+{
+    if (!equation || nnames < 0 || (nnames && !names) || n < 0 || (n && (!out || (nnames && !values)))) return fail(CC_ERR_INVALID, "bad arguments");
+    ccexpr::Program prog;
+    const int rc = compile_equation(equation, names, nnames, prog);
+    if (rc != CC_OK) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        int e = 0;
+        out[i] = prog.eval(values + (size_t)i * nnames, &e);
+        if (err) err[i] = e;
+    }
+    return CC_OK;
+}
+
+int cc_debug_expand_rows(const cc_joint* joints, int njoints, int ndof, const double* dofvals, const char* const* equations,
+                         const char* const* joint_names, const int32_t* active, int nactive, int naffine, const double* q_in, int64_t n,
+                         double* q_out)
+{
+    if (!joints || njoints <= 0 || ndof < 0 || (ndof && !dofvals) || !equations || !joint_names || nactive < 0 || (nactive && !active) ||
+        naffine < 0 || n < 0 || (n && (!q_in || !q_out)))
+        return fail(CC_ERR_INVALID, "bad arguments");
+    std::vector<cc_joint> J(joints, joints + njoints);
+    std::vector<ccexpr::Program> prog((size_t)njoints);
+    int nexternal = 0;
+    for (int k = 0; k < njoints; ++k) {
+        if (J[k].dof_index >= ndof || J[k].mimic_dof >= ndof) return fail(CC_ERR_INVALID, "joint dof out of range");
+        if (J[k].mimic_dof != CC_MIMIC_EXTERNAL) continue;
+        if (J[k].reserved < 0 || J[k].reserved >= 4096) return fail(CC_ERR_INVALID, "external ordinal out of range");
+        nexternal = std::max(nexternal, J[k].reserved + 1);
+        if (!equations[k]) continue;
+        const int rc = compile_equation(equations[k], joint_names, njoints, prog[k]);
+        if (rc != CC_OK) return rc;
+        for (int v : prog[k].vars)
+            if (J[v].dof_index < 0 && v >= k) return fail(CC_ERR_INVALID, "the equation reads a passive joint listed after its own");
+    }
+    for (int c = 0; c < nactive; ++c) if (active[c] < 0 || active[c] >= ndof) return fail(CC_ERR_INVALID, "active DOF index out of range");
+    return expand_rows_host(J, ndof, dofvals, prog, active, nactive, naffine, nexternal, q_in, n, q_out);
 }
 
 int cc_body_set_dof_values(cc_scene* s, int body, const double* values, int ndof)
@@ -2156,6 +2303,8 @@ int cc_query_get_info(const cc_query* q, cc_query_info* info)
 {
     if (!q || !info) return fail(CC_ERR_INVALID, "bad arguments");
     info->ndof_active = q->ncols;
+    info->nexternal = q->nexternal;
+    info->reserved = 0;
     info->nlinks = q->nq;
     info->npairs_env = q->nenv_total;
     info->npairs_self = q->nself_total;

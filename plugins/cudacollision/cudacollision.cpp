@@ -227,10 +227,17 @@ public:
         cc_query* query = _Bind(probot, &probot->GetActiveDOFIndices(), probot);
         if (_stale.erase(query)) _Check(cc_query_refresh(query));      // base pose / inactive DOF values of the robot moved
         std::vector<int32_t> fe(firstpairs ? n : 0), fs(firstpairs ? n : 0);
+        cc_query_info info;
+        cc_query_get_info(query, &info);
+        if (info.ndof_active != ndof) {
+            // the robot has mimic equations the device cannot hold (CC_MIMIC_EXTERNAL, _SyncKinematics): the library evaluates
+            // them on the host and the rows grow by one column per such joint
+            _vexpanded.resize((size_t)n * info.ndof_active);
+            _Check(cc_query_expand_rows(query, q, n, _vexpanded.data()));
+            q = _vexpanded.data();
+        }
         _Check(cc_check_batch(query, q, n, flags, verdict, firstpairs ? fe.data() : NULL, firstpairs ? fs.data() : NULL, NULL));
         if (firstpairs) {
-            cc_query_info info;
-            cc_query_get_info(query, &info);
             std::vector<int32_t> quads(4 * (size_t)std::max(1, info.npairs_env + info.npairs_self));
             cc_query_get_pairs(query, quads.data());
             for (int i = 0; i < n; ++i) {
@@ -703,6 +710,7 @@ private:
         if (pinfo->kinematicsDirty) {
             const std::vector<KinBody::JointPtr>& vjoints = pbody->GetDependencyOrderedJointsAll();
             std::vector<cc_joint> joints(vjoints.size());
+            std::vector<int> vexternal;
             for (size_t k = 0; k < vjoints.size(); ++k) {
                 const KinBody::Joint& j = *vjoints[k];
                 cc_joint& o = joints[k];
@@ -725,12 +733,16 @@ private:
                 if (j.IsMimic(0) && !j.IsStatic()) {
                     std::vector<int> vmimicdofs;
                     j.GetMimicDOFIndices(vmimicdofs, 0);
-                    if (vmimicdofs.size() != 1) throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: mimic joint %s reads %d DOFs", j.GetName() % vmimicdofs.size(), ORE_NotImplemented);
-                    const std::string var = pbody->GetJointFromDOFIndex(vmimicdofs[0])->GetName();
-                    if (!ParseAffineMimic(j.GetMimicEquation(0, 0), var, o.mimic_a, o.mimic_b))
-                        throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: mimic equation '%s' of joint %s is not affine", j.GetMimicEquation(0, 0) % j.GetName(), ORE_NotImplemented);
-                    o.mimic_dof = vmimicdofs[0];
                     o.dof_index = -1;
+                    if (vmimicdofs.size() == 1 && ParseAffineMimic(j.GetMimicEquation(0, 0), pbody->GetJointFromDOFIndex(vmimicdofs[0])->GetName(), o.mimic_a, o.mimic_b))
+                        o.mimic_dof = vmimicdofs[0];
+                    else {
+                        // any other fparser expression (kinbody.cpp:2308-2320): the library compiles the text and evaluates it on
+                        // the host per configuration (cc_body_set_mimic_equation / cc_query_expand_rows)
+                        o.mimic_dof = CC_MIMIC_EXTERNAL;
+                        o.reserved = (int)vexternal.size();
+                        vexternal.push_back((int)k);
+                    }
                 }
             }
             const int ndof = pbody->GetDOF(), nl = (int)pbody->GetLinks().size();
@@ -740,6 +752,15 @@ private:
                 for (int l = 0; l < nl; ++l) affects[(size_t)d * nl + l] = pbody->DoesAffect(jointindex, l) ? 1 : 0;
             }
             _Check(cc_body_set_kinematics(_scene, pinfo->id, ndof, (int)joints.size(), joints.data(), affects.data()));
+            if (!vexternal.empty()) {
+                std::vector<const char*> vnames(vjoints.size());
+                for (size_t k = 0; k < vjoints.size(); ++k) vnames[k] = vjoints[k]->GetName().c_str();
+                for (size_t e = 0; e < vexternal.size(); ++e) {
+                    const std::string eq = vjoints[vexternal[e]]->GetMimicEquation(0, 0);
+                    if (cc_body_set_mimic_equation(_scene, pinfo->id, vexternal[e], eq.c_str(), vnames.data(), (int)vnames.size()) != CC_OK)
+                        throw OPENRAVE_EXCEPTION_FORMAT("cudacollision: joint %s: %s", vjoints[vexternal[e]]->GetName() % cc_last_error(), ORE_NotImplemented);
+                }
+            }
             std::vector<dReal> values;
             pbody->GetDOFValues(values);
             if (ndof > 0) _Check(cc_body_set_dof_values(_scene, pinfo->id, values.data(), ndof));
@@ -943,6 +964,7 @@ private:
     std::map<int, KinBodyWeakPtr> _byid;
     std::map<QueryKey, cc_query*> _queries;
     std::set<cc_query*> _stale;            // queries whose own body moved since their last refresh (matters to the FK-mode entry only)
+    std::vector<double> _vexpanded;        // rows of CheckCollisionBatch with the host-evaluated mimic columns filled in
 };
 
 #include "cudabatched.h"
