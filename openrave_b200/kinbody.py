@@ -204,39 +204,77 @@ def _transform_distance_fast(t1, t2, frotweight=1.0, ftransweight=1.0):
 # ----------------------------------------------------------------------------- mimic expressions
 class MimicExpr(object):
     """A mimic_pos equation (an fparser expression over joint names in the reference,
-    kinbodyjoint.cpp SetMimicEquations).  Parsed with Python's ast into a tiny arithmetic
-    evaluator; `affine()` extracts value = a*q[src] + b, the form the device chain program stores."""
+    kinbodyjoint.cpp SetMimicEquations).  Plain arithmetic is parsed with Python's ast into a tiny
+    evaluator; anything else of fparser's language is handed to the library's compiler for it;
+    `affine()` extracts value = a*q[src] + b, the form the device chain program stores."""
 
     _ALLOWED = (ast.Expression, ast.BinOp, ast.UnaryOp, ast.Add, ast.Sub, ast.Mult, ast.Div, ast.Pow,
                 ast.USub, ast.UAdd, ast.Name, ast.Load, ast.Constant)
 
+    # names of fparser's functions (3rdparty/fparser-4.5.2/extrasrc/fptypes.hh:118-160) that the library's compiler knows
+    _FUNCTIONS = frozenset("abs acos acosh asin asinh atan atan2 atanh cbrt ceil cos cosh cot csc exp exp2 floor hypot if int log "
+                           "log10 log2 max min pow sec sin sinh sqrt tan tanh trunc".split())
+
     def __init__(self, text):
         self.text = text.strip()
-        expr = self.text.replace("^", "**")
-        self.tree = ast.parse(expr, mode="eval")
-        for node in ast.walk(self.tree):
-            if not isinstance(node, self._ALLOWED):
-                raise ValueError("unsupported mimic expression %r" % text)
-        self.varnames = sorted({n.id for n in ast.walk(self.tree) if isinstance(n, ast.Name)})
-        self._code = compile(self.tree, "<mimic>", "eval")
+        self._code = None
+        try:
+            self.tree = ast.parse(self.text.replace("^", "**"), mode="eval")
+            for node in ast.walk(self.tree):
+                if not isinstance(node, self._ALLOWED):
+                    raise ValueError("not plain arithmetic")
+            self.varnames = sorted({n.id for n in ast.walk(self.tree) if isinstance(n, ast.Name)})
+            self._code = compile(self.tree, "<mimic>", "eval")
+        except (ValueError, SyntaxError):
+            # functions, comparisons, if(): the rest of fparser's language goes through the library's own compiler for it
+            # (csrc/cc_mimic_expr.h, a host-side entry that needs no device)
+            import re
+            self.tree = None
+            self.varnames = sorted(set(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", re.sub(r"\b0[xX][0-9a-fA-F]+|\b\d+\.?\d*([eE][-+]?\d+)?", " ", self.text)))
+                                   - self._FUNCTIONS)
+            try:
+                self._library_eval([[0.0] * len(self.varnames)])
+            except RuntimeError as e:
+                raise ValueError("unsupported mimic expression %r: %s" % (text, e))
+
+    def _library_eval(self, rows):
+        import ctypes
+        import numpy as np
+        from .checker import load_library
+        lib = load_library()
+        names = (ctypes.c_char_p * max(len(self.varnames), 1))(*[v.encode() for v in self.varnames])
+        v = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, max(len(self.varnames), 1))
+        out = np.zeros(len(v))
+        err = np.zeros(len(v), dtype=np.int32)
+        if lib.cc_debug_mimic_eval(self.text.encode(), names, len(self.varnames), v.ctypes.data_as(ctypes.c_void_p), len(v),
+                                   out.ctypes.data_as(ctypes.c_void_p), err.ctypes.data_as(ctypes.c_void_p)) != 0:
+            raise RuntimeError(lib.cc_last_error().decode())
+        return out                      # a row that failed to evaluate reads 0, as fparser's Eval returns
 
     def eval(self, values):
+        if self._code is None:
+            return float(self._library_eval([[float(values[v]) for v in self.varnames]])[0])
         return float(eval(self._code, {"__builtins__": {}}, dict(values)))
 
     def eval_many(self, values, n):
         """The same for n configurations at once: `values` maps joint names to arrays [n] (or scalars)."""
         import numpy as np
+        if self._code is None:
+            cols = [np.broadcast_to(np.asarray(values[v], dtype=np.float64), (n,)) for v in self.varnames]
+            return self._library_eval(np.stack(cols, axis=1) if cols else np.zeros((n, 1)))
         return np.broadcast_to(np.asarray(eval(self._code, {"__builtins__": {}}, dict(values)), dtype=np.float64), (n,)).copy()
 
     def affine(self):
         """Return (varname, a, b) if the expression is affine in exactly one joint, else None."""
-        if len(self.varnames) != 1:
+        if len(self.varnames) != 1 or self._code is None:      # sampling proves nothing about min(), if(), floor() ...
             return None
         v = self.varnames[0]
-        f0, f1, f2 = self.eval({v: 0.0}), self.eval({v: 1.0}), self.eval({v: -2.5})
+        f0, f1 = self.eval({v: 0.0}), self.eval({v: 1.0})
         a, b = f1 - f0, f0
-        if abs((a * -2.5 + b) - f2) > 1e-12 * max(1.0, abs(f2)):
-            return None
+        for x in (-2.5, 0.37, 1.9, -0.71):
+            fx = self.eval({v: x})
+            if abs((a * x + b) - fx) > 1e-12 * max(1.0, abs(fx)):
+                return None
         return v, a, b
 
 

@@ -234,3 +234,32 @@ def test_expand_rows_refuses_what_it_cannot_evaluate():
                                   act.ctypes.data_as(ctypes.c_void_p), len(act), 0, q.ctypes.data_as(ctypes.c_void_p), 1,
                                   out.ctypes.data_as(ctypes.c_void_p))
     assert rc != 0 and "no equation" in lib.cc_last_error().decode()
+
+
+def test_a_robot_with_fparser_functions_in_its_equations_loads_and_moves():
+    """The harness evaluates what Python's arithmetic cannot through the library's compiler: the loaders accept such robots, the
+    FK restatement moves them, and the rows for the device come out the same either way."""
+    env = load_scene("lab1")
+    robot = env.GetRobots()[0]
+    byname = {j.name: j for j in robot.all_joints()}
+    byname["JF1mimic"].mimic = MimicExpr("0.3 + 0.5*sin(JF1)^2 + if(JF2 > 1, 0.2, 0.1*JF2)")
+    byname["JF2mimic"].mimic = MimicExpr("max(JF1mimic/2, 0.25) + atan2(JF3, 1)/5")
+    assert byname["JF1mimic"].mimic.affine() is None and byname["JF1mimic"].mimic.varnames == ["JF1", "JF2"]
+    robot.compute_internal_information()
+    ext = []
+    arr, nj = flatten.joint_table(robot, externals=ext)
+    assert [j.name for j in ext] == ["JF1mimic", "JF2mimic"]
+    d = {n: robot.GetJoint(n).dofindex for n in ("JF1", "JF2", "JF3")}
+    q = np.array(robot.GetDOFValues())
+    q[d["JF1"]], q[d["JF2"]], q[d["JF3"]] = 0.9, 1.3, 0.4
+    robot.SetDOFValues(q.tolist())
+    e1 = 0.3 + 0.5 * np.sin(0.9) ** 2 + 0.2
+    e2 = max(min(max(e1, byname["JF1mimic"].lower), byname["JF1mimic"].upper) / 2, 0.25) + np.arctan2(0.4, 1) / 5
+    active = list(range(robot.GetDOF()))
+    rc, out = _expand(robot, arr, nj, ext, active, q[None])
+    assert rc == 0
+    assert abs(out[0, len(active)] - e1) < 1e-15 and abs(out[0, len(active) + 1] - e2) < 1e-15
+    want = external_mimic_values(robot, q[None], ext)
+    assert np.abs(want - out[:, len(active):]).max() < 1e-15
+    with pytest.raises(ValueError):
+        MimicExpr("polyroots2(JF1, 1, 2)")
