@@ -414,6 +414,18 @@ int cc_debug_broad_overlap(const float* boxes_a, const float* boxes_b, int n, ui
 int cc_debug_motion_classes(const cc_joint* joints, int njoints, int nlinks, int ndof, const uint8_t* affects, const int32_t* active,
                             int nactive, int base_moves, const int32_t* pairs, int npairs, uint8_t* out_moves, uint8_t* out_invariant);
 
+/* Diagnostic (no device needed): the FK chain program a query compiles for the device — joints in depth-first order, everything
+ * rigidly attached to a varying joint's child folded into one constant per link, pose-table slots and parked poses assigned — run
+ * on the host in double precision with the device's operation order.  Arguments as for cc_body_set_kinematics /
+ * cc_body_set_dof_values / cc_query_create; base_pose = link 0's pose {quat wxyz, xyz, 0}; wanted_links[nlinks] (NULL: all) marks
+ * the links whose poses are needed (the compiler drops chains nobody needs); walk 0 = the order of cc_fk_kernel (running
+ * transform + parked poses), 1 = cc_fk2_kernel (pose table).  q: [n][nactive + external columns]; out_poses: [n][nlinks][8],
+ * zeros for links that are not wanted; out_counts (may be NULL): {steps, varying steps, pose-table slots, parked poses}.
+ * Restates KinBody::SetDOFValues' joint loop (kinbody.cpp:2286-2481): tests/test_fk_program.py against the harness. */
+int cc_debug_fk_program(const cc_joint* joints, int njoints, int nlinks, int ndof, const double* dofvals, const double* base_pose,
+                        const int32_t* active, int nactive, const uint8_t* wanted_links, int walk, const double* q, int64_t n,
+                        double* out_poses, int32_t* out_counts);
+
 /* Diagnostics (no device needed) of the mimic-equation evaluator.  cc_debug_mimic_eval: out[i] = equation(values[i][0..nnames)),
  * err[i] = fparser's EvalError code (0 fine, 1 division by zero, 2 sqrt, 3 log, 4 trig domain) or 5 for a power / a result that
  * is NaN or infinite, which fparser reports as one of its codes or not at all depending on how it rewrote the power; out[i] is then 0.

@@ -65,7 +65,7 @@ EXPORTS = ["cc_last_error", "cc_version", "cc_scene_create", "cc_scene_destroy",
            "cc_host_alloc", "cc_host_free", "cc_body_set_grabbed", "cc_body_release_grabbed", "cc_query_get_links",
            "cc_distance_batch", "cc_distance_poses", "cc_scene_set_pair_tables", "cc_query_get_table_count",
            "cc_tolerance_batch", "cc_tolerance_poses", "cc_device_fp32_peak", "cc_query_refresh",
-           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_debug_broad_overlap", "cc_debug_motion_classes", "cc_body_set_mimic_equation", "cc_query_expand_rows", "cc_debug_mimic_eval", "cc_debug_expand_rows", "cc_query_get_certificates", "cc_debug_pair_rates",
+           "cc_contacts_poses", "cc_tri_tri_contact", "cc_debug_build_bvh", "cc_debug_broad_overlap", "cc_debug_motion_classes", "cc_body_set_mimic_equation", "cc_query_expand_rows", "cc_debug_mimic_eval", "cc_debug_expand_rows", "cc_debug_fk_program", "cc_query_get_certificates", "cc_debug_pair_rates",
            "cc_scene_trace_timeline", "cc_scene_get_timeline", "cc_scene_create_multi", "cc_scene_get_devices", "cc_query_create_affine",
            "cc_body_set_link_primitives", "cc_scene_set_analytic_primitives"]
 
@@ -129,6 +129,7 @@ def load_library():
     lib.cc_query_expand_rows.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.cc_debug_mimic_eval.argtypes = [ctypes.c_char_p, cpp, ci, vp, ctypes.c_int64, vp, vp]
     lib.cc_debug_expand_rows.argtypes = [vp, ci, ci, vp, cpp, cpp, vp, ci, ci, vp, ctypes.c_int64, vp]
+    lib.cc_debug_fk_program.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, vp, ctypes.c_int64, vp, vp]
     lib.cc_debug_broad_overlap.argtypes = [vp, vp, ci, vp]
     lib.cc_distance_batch.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]
     lib.cc_distance_poses.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp, vp, vp]

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <limits>
+#include <memory>
 #include <random>
 #include <string>
 #include <thread>
@@ -1423,12 +1424,15 @@ static HXf hxf_mul(const HXf& a, const HXf& b)
 static HXf hxf_load(const double* p) { HXf r; for (int i = 0; i < 4; ++i) r.q[i] = p[i]; for (int i = 0; i < 3; ++i) r.t[i] = p[4 + i]; return r; }
 static void hxf_store(const HXf& x, double* p) { for (int i = 0; i < 4; ++i) p[i] = x.q[i]; for (int i = 0; i < 3; ++i) p[4 + i] = x.t[i]; p[7] = 0.0; }
 
-// L * J(value) * R of a joint whose value does not depend on an active DOF (ccdev::joint_transform with src_col < 0)
-static HXf host_constant_joint(const ccdev::FkStep& st)
+// L * J(value) * R of a joint: ccdev::joint_transform on the host.  qrow == NULL: a joint whose value does not depend on the rows
+// of q (src_col < 0), the only use the product has for it; with a row it is the device-free restatement behind cc_debug_fk_program.
+static HXf host_joint(const ccdev::FkStep& st, const double* qrow);
+static HXf host_constant_joint(const ccdev::FkStep& st) { return host_joint(st, nullptr); }
+static HXf host_joint(const ccdev::FkStep& st, const double* qrow)
 {
     const HXf L = hxf_load(st.L);
     if (st.flags & 1) return L;
-    double v = st.src_const;
+    double v = qrow && st.src_col >= 0 ? qrow[st.src_col] : st.src_const;
     if (!(st.flags & 8)) { if (v < st.src_lower) v = st.src_lower; else if (v > st.src_upper) v = st.src_upper; }
     if (st.flags & 2) {
         const double ev = st.a * v + st.b;
@@ -1530,6 +1534,82 @@ static void compile_fk_program(const cc_query* Q, Plan& pl)
         }
         last_varying = (int)i;
     }
+}
+
+static int build_chain_steps(const std::vector<cc_joint>& joints, int nl, const std::vector<int>& col_of_dof, int nactive, const double* dofvals,
+                             std::vector<ccdev::FkStep>& steps, std::vector<int>& depth);
+
+// One configuration through a compiled chain program on the host, in the order the device walks it.  walk 0: cc_fk_kernel
+// (ccdev::fk_chain: running transform, poses later branches start from parked in `save` slots); walk 1: cc_fk2_kernel (every varying
+// step reads and writes a slot of the per-configuration pose table, the constant steps hang off those slots).
+static void host_run_program(const Plan& pl, const double* base8, const double* qrow, int nl, int walk, double* out)
+{
+    for (size_t i = 0; i < (size_t)nl * 8; ++i) out[i] = 0.0;
+    const HXf base = hxf_load(base8);
+    hxf_store(base, out);
+    if (walk == 0) {
+        std::vector<HXf> saved((size_t)std::max(1, pl.nsave));
+        HXf cur = base;
+        for (const ccdev::FkStep& st : pl.steps) {
+            if (st.load_parent == -1) cur = base;
+            else if (st.load_parent >= 0) cur = saved[st.load_parent];
+            if (st.flags & 16) { if (pl.emit[st.child] >= 0) hxf_store(hxf_mul(cur, hxf_load(st.L)), out + 8 * (size_t)st.child); continue; }
+            cur = hxf_mul(cur, host_joint(st, qrow));
+            if (st.save >= 0) saved[st.save] = cur;
+            if (pl.emit[st.child] >= 0) hxf_store(cur, out + 8 * (size_t)st.child);
+        }
+    } else {
+        std::vector<HXf> pose((size_t)std::max(1, pl.npose));
+        pose[0] = base;
+        for (const ccdev::FkStep& st : pl.steps) {
+            if (st.flags & 16) continue;
+            pose[st.pose_out] = hxf_mul(pose[st.pose_in], host_joint(st, qrow));
+            if (pl.emit[st.child] >= 0) hxf_store(pose[st.pose_out], out + 8 * (size_t)st.child);
+        }
+        for (const ccdev::FkStep& st : pl.steps)
+            if ((st.flags & 16) && pl.emit[st.child] >= 0) hxf_store(hxf_mul(pose[st.pose_in], hxf_load(st.L)), out + 8 * (size_t)st.child);
+    }
+}
+
+int cc_debug_fk_program(const cc_joint* joints, int njoints, int nlinks, int ndof, const double* dofvals, const double* base_pose,
+                        const int32_t* active, int nactive, const uint8_t* wanted_links, int walk, const double* q, int64_t n,
+                        double* out_poses, int32_t* out_counts)
+{
+    if (!joints || njoints <= 0 || nlinks <= 0 || ndof < 0 || (ndof && !dofvals) || !base_pose || nactive < 0 || (nactive && !active) ||
+        (walk != 0 && walk != 1) || n < 0 || (n && (!q || !out_poses)))
+        return fail(CC_ERR_INVALID, "cc_debug_fk_program: bad arguments");
+    std::vector<cc_joint> J(joints, joints + njoints);
+    std::vector<int> col_of_dof((size_t)ndof, -1);
+    for (int c = 0; c < nactive; ++c) {
+        if (active[c] < 0 || active[c] >= ndof) return fail(CC_ERR_INVALID, "cc_debug_fk_program: active DOF index out of range");
+        col_of_dof[active[c]] = c;
+    }
+    int nexternal = 0;
+    for (const cc_joint& j : J) {
+        if (j.parent_link < 0 || j.parent_link >= nlinks || j.child_link < 0 || j.child_link >= nlinks) return fail(CC_ERR_INVALID, "joint link out of range");
+        if (j.dof_index >= ndof || j.mimic_dof >= ndof) return fail(CC_ERR_INVALID, "joint dof out of range");
+        if (j.mimic_dof == CC_MIMIC_EXTERNAL) nexternal = std::max(nexternal, j.reserved + 1);
+    }
+    std::unique_ptr<cc_query> Q(new cc_query());
+    Q->nq = nlinks;
+    Q->has_fk = true;
+    std::vector<int> depth;
+    const int rc = build_chain_steps(J, nlinks, col_of_dof, nactive, dofvals, Q->steps, depth);
+    if (rc != CC_OK) return rc;
+    Plan pl;
+    pl.emit.assign((size_t)nlinks, -1);
+    int ne = 0;
+    for (int l = 0; l < nlinks; ++l) if (!wanted_links || wanted_links[l]) pl.emit[l] = ne++;
+    compile_fk_program(Q.get(), pl);
+    if (out_counts) {
+        int nv = 0;
+        for (const ccdev::FkStep& st : pl.steps) nv += (st.flags & 16) ? 0 : 1;
+        out_counts[0] = (int32_t)pl.steps.size(); out_counts[1] = nv; out_counts[2] = pl.npose; out_counts[3] = pl.nsave;
+    }
+    const int ncols = nactive + nexternal;
+    for (int64_t i = 0; i < n; ++i)
+        host_run_program(pl, base_pose, q + (size_t)i * ncols, nlinks, walk, out_poses + (size_t)i * nlinks * 8);
+    return CC_OK;
 }
 
 // Lay one pair list out for the device.  `dynamic[l]`: query link l gets a per-configuration pose (scratch slot); every
@@ -1699,6 +1779,77 @@ static int evaluate_hoisted(cc_query* Q)
     return CC_OK;
 }
 
+// The chain program of a body over one active set: one ccdev::FkStep per joint, depth-first (children in listed order) so that a
+// child usually follows its parent.  `depth[l]` comes back -1 for a link no joint reaches.  (Shared by the query builder and the
+// device-free cc_debug_fk_program.)
+static int build_chain_steps(const std::vector<cc_joint>& joints, int nl, const std::vector<int>& col_of_dof, int nactive, const double* dofvals,
+                             std::vector<ccdev::FkStep>& steps, std::vector<int>& depth)
+{
+    steps.clear();
+    depth.assign((size_t)nl, -1);
+    depth[0] = 0;
+    std::vector<int> sdepth(joints.size(), 0);
+    for (size_t k = 0; k < joints.size(); ++k) {
+        const cc_joint& j = joints[k];
+        if (depth[j.parent_link] < 0) return fail(CC_ERR_INVALID, "joints are not listed parent-before-child from link 0");
+        if (depth[j.child_link] >= 0) return fail(CC_ERR_UNSUPPORTED, "closed kinematic loops are not supported");
+        depth[j.child_link] = depth[j.parent_link] + 1;
+        sdepth[k] = depth[j.child_link];
+    }
+    // depth-first order (children in listed order): a child usually follows its parent, so the device keeps the
+    // running transform in registers and parks only the poses later branches start from
+    std::vector<std::vector<int>> kids(nl);
+    for (size_t k = 0; k < joints.size(); ++k) kids[joints[k].parent_link].push_back((int)k);
+    std::vector<int> ord;
+    {
+        std::vector<std::pair<int, size_t>> stk;     // (link, next child position)
+        stk.push_back(std::make_pair(0, (size_t)0));
+        while (!stk.empty()) {
+            std::pair<int, size_t>& top = stk.back();
+            if (top.second >= kids[top.first].size()) { stk.pop_back(); continue; }
+            const int k = kids[top.first][top.second++];
+            ord.push_back(k);
+            stk.push_back(std::make_pair(joints[k].child_link, (size_t)0));
+        }
+    }
+    if (ord.size() != joints.size()) return fail(CC_ERR_INVALID, "joint tree is not connected to link 0");
+    for (int k : ord) {
+        const cc_joint& j = joints[k];
+        ccdev::FkStep st;
+        memset(&st, 0, sizeof(st));
+        st.type = j.type; st.parent = j.parent_link; st.child = j.child_link;
+        int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
+        st.src_col = srcdof >= 0 ? col_of_dof[srcdof] : -1;
+        st.src_const = srcdof >= 0 ? dofvals[srcdof] : 0.0;
+        st.flags = (j.is_static ? 1 : 0) | (j.mimic_dof >= 0 ? 2 : 0) | (j.is_circular ? 4 : 0);
+        st.src_lower = j.lower; st.src_upper = j.upper;
+        bool src_circ = j.is_circular != 0;
+        if (j.mimic_dof >= 0) {
+            // limits of the DOF the equation reads
+            bool found = false;
+            for (const cc_joint& o : joints)
+                if (o.dof_index == j.mimic_dof) { st.src_lower = o.lower; st.src_upper = o.upper; src_circ = o.is_circular != 0; found = true; break; }
+            if (!found) return fail(CC_ERR_INVALID, "mimic source DOF has no joint");
+        } else if (srcdof < 0) {
+            // passive, non-mimic joint: value 0 clamped to its own limits (kinbody.cpp:2262-2275)
+            st.src_const = 0.0;
+        }
+        if (src_circ) st.flags |= 8;
+        st.a = j.mimic_a; st.b = j.mimic_b; st.lower = j.lower; st.upper = j.upper;
+        if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
+            // the equation is evaluated by the caller (fparser expressions the reference evaluates on the host too,
+            // kinbody.cpp:2308-2320): its value arrives as a column of q and goes through the mimic limit rules (:2326-2386)
+            st.src_col = nactive + j.reserved;
+            st.src_const = 0.0;
+            st.flags |= 2 | 8;                       // mimic; the "source" is the value itself: no source clamp
+            st.a = 1.0; st.b = 0.0;
+        }
+        memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
+        steps.push_back(st);
+    }
+    return CC_OK;
+}
+
 // What a batch can change.  `moves[l]`: link l's WORLD pose depends on the rows of q — an active DOF affects it
 // (KinBody::DoesAffect, which follows mimic equations to their source DOFs), the base itself moves (affine DOFs), or an
 // externally evaluated mimic joint (CC_MIMIC_EXTERNAL: a new value with every row whatever the active set is) sits above it.
@@ -1795,67 +1946,9 @@ static int finish_query(cc_query* Q, const int32_t* active, int nactive, bool al
     Q->has_fk = true;
     Q->steps.clear();
     if (!joints.empty()) {
-        std::vector<int> depth(nl, -1);
-        depth[0] = 0;
-        std::vector<int> sdepth(joints.size(), 0);
-        for (size_t k = 0; k < joints.size(); ++k) {
-            const cc_joint& j = joints[k];
-            if (depth[j.parent_link] < 0) return fail(CC_ERR_INVALID, "joints are not listed parent-before-child from link 0");
-            if (depth[j.child_link] >= 0) return fail(CC_ERR_UNSUPPORTED, "closed kinematic loops are not supported");
-            depth[j.child_link] = depth[j.parent_link] + 1;
-            sdepth[k] = depth[j.child_link];
-        }
-        // depth-first order (children in listed order): a child usually follows its parent, so the device keeps the
-        // running transform in registers and parks only the poses later branches start from
-        std::vector<std::vector<int>> kids(nl);
-        for (size_t k = 0; k < joints.size(); ++k) kids[joints[k].parent_link].push_back((int)k);
-        std::vector<int> ord;
-        {
-            std::vector<std::pair<int, size_t>> stk;     // (link, next child position)
-            stk.push_back(std::make_pair(0, (size_t)0));
-            while (!stk.empty()) {
-                std::pair<int, size_t>& top = stk.back();
-                if (top.second >= kids[top.first].size()) { stk.pop_back(); continue; }
-                const int k = kids[top.first][top.second++];
-                ord.push_back(k);
-                stk.push_back(std::make_pair(joints[k].child_link, (size_t)0));
-            }
-        }
-        if (ord.size() != joints.size()) return fail(CC_ERR_INVALID, "joint tree is not connected to link 0");
-        for (int k : ord) {
-            const cc_joint& j = joints[k];
-            ccdev::FkStep st;
-            memset(&st, 0, sizeof(st));
-            st.type = j.type; st.parent = j.parent_link; st.child = j.child_link;
-            int srcdof = j.mimic_dof >= 0 ? j.mimic_dof : j.dof_index;
-            st.src_col = srcdof >= 0 ? col_of_dof[srcdof] : -1;
-            st.src_const = srcdof >= 0 ? B->dofvals[srcdof] : 0.0;
-            st.flags = (j.is_static ? 1 : 0) | (j.mimic_dof >= 0 ? 2 : 0) | (j.is_circular ? 4 : 0);
-            st.src_lower = j.lower; st.src_upper = j.upper;
-            bool src_circ = j.is_circular != 0;
-            if (j.mimic_dof >= 0) {
-                // limits of the DOF the equation reads
-                bool found = false;
-                for (const cc_joint& o : joints)
-                    if (o.dof_index == j.mimic_dof) { st.src_lower = o.lower; st.src_upper = o.upper; src_circ = o.is_circular != 0; found = true; break; }
-                if (!found) return fail(CC_ERR_INVALID, "mimic source DOF has no joint");
-            } else if (srcdof < 0) {
-                // passive, non-mimic joint: value 0 clamped to its own limits (kinbody.cpp:2262-2275)
-                st.src_const = 0.0;
-            }
-            if (src_circ) st.flags |= 8;
-            st.a = j.mimic_a; st.b = j.mimic_b; st.lower = j.lower; st.upper = j.upper;
-            if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
-                // the equation is evaluated by the caller (fparser expressions the reference evaluates on the host too,
-                // kinbody.cpp:2308-2320): its value arrives as a column of q and goes through the mimic limit rules (:2326-2386)
-                st.src_col = (int)act.size() + j.reserved;
-                st.src_const = 0.0;
-                st.flags |= 2 | 8;                       // mimic; the "source" is the value itself: no source clamp
-                st.a = 1.0; st.b = 0.0;
-            }
-            memcpy(st.L, j.left, sizeof(st.L)); memcpy(st.R, j.right, sizeof(st.R)); memcpy(st.axis, j.axis, sizeof(st.axis));
-            Q->steps.push_back(st);
-        }
+        std::vector<int> depth;
+        const int rcs = build_chain_steps(joints, nl, col_of_dof, (int)act.size(), B->dofvals.data(), Q->steps, depth);
+        if (rcs != CC_OK) return rcs;
         for (int l = 1; l < nl; ++l)
             if (depth[l] < 0 && Q->qlink(l).ntris() > 0) Q->has_fk = false;   // a link no joint reaches: pose mode only
     } else {
