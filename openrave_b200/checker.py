@@ -399,6 +399,7 @@ class CudaCollisionChecker(object):
         self._dirty = set()
         self._kin_dirty = set()
         self._externals = {}
+        self._equations_registered = set()
         self._options = 0
         self._queries = {}
         self._epoch = 0
@@ -451,6 +452,7 @@ class CudaCollisionChecker(object):
             self._ck(self.lib.cc_scene_set_analytic_primitives(self.scene, 1))
         self._ids, self._bodies, self._dirty, self._kin_dirty = {}, {}, set(), set()
         self._grab_epochs = {}
+        self._externals, self._equations_registered = {}, set()
         for b in self.env.GetBodies():
             self.InitKinBody(b)
         return True
@@ -562,6 +564,8 @@ class CudaCollisionChecker(object):
                 cur = np.array(body.GetDOFValues(), dtype=np.float64)
                 if body.GetDOF() > 0:
                     self._ck(self.lib.cc_body_set_dof_values(self.scene, bid, _ptr(cur), body.GetDOF()))
+                if bid in self._equations_registered:        # cc_body_set_kinematics forgets the equations
+                    self._send_equations(body, bid, ext)
             self._kin_dirty.discard(id(body))
         if need_pairs and len(body.links) > 1:
             na = np.array(body.GetNonAdjacentLinks(0, checker=self), dtype=np.int32)
@@ -664,12 +668,16 @@ class CudaCollisionChecker(object):
         CC_MIMIC_EXTERNAL columns.  This twin keeps evaluating them itself (BoundQuery.rows).  Returns the number registered."""
         bq = self.bind(body, active)                       # makes sure the kinematics went over
         bid = self._ids[id(body)]
+        self._send_equations(body, bid, bq.externals)
+        self._equations_registered.add(bid)                # sent again whenever the kinematics are
+        return len(bq.externals)
+
+    def _send_equations(self, body, bid, externals):
         js = body.sorted_joints_all
         names = (ctypes.c_char_p * max(len(js), 1))(*[j.name.encode() for j in js])
-        for e in bq.externals:
+        for e in externals:
             k = [i for i, j in enumerate(js) if j is e][0]
             self._ck(self.lib.cc_body_set_mimic_equation(self.scene, bid, k, e.mimic.text.replace("**", "^").encode(), names, len(js)))
-        return len(bq.externals)
 
     def ForwardKinematicsBatch(self, robot, q, active=None):
         return self.bind(robot, active).fk(q)
