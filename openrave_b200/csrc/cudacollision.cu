@@ -1181,9 +1181,13 @@ int expand_rows_host(const std::vector<cc_joint>& J, int ndof, const double* dof
             snprintf(msg, sizeof(msg), "joint %d is CC_MIMIC_EXTERNAL and has no equation (cc_body_set_mimic_equation)", k);
             return fail(CC_ERR_STATE, msg);
         }
-    std::vector<double> full((size_t)ndof), jv((size_t)nj);
     const int nin = nactive + naffine, nout = nactive + nexternal + naffine;
-    for (int64_t i = 0; i < n; ++i) {
+    // rows are independent: large batches are split over the host cores (a row costs a few hundred ns on one core, the device
+    // checks one in 10); the first failing row, in row order, is the one reported
+    struct Failure { int64_t row = -1; int joint = -1, err = 0; };
+    auto run = [&](int64_t begin, int64_t end, Failure& f) {
+    std::vector<double> full((size_t)ndof), jv((size_t)nj);
+    for (int64_t i = begin; i < end; ++i) {
         const double* in = q_in + (size_t)i * nin;
         double* out = q_out + (size_t)i * nout;
         for (int d = 0; d < ndof; ++d) full[d] = dofvals[d];
@@ -1199,12 +1203,7 @@ int expand_rows_host(const std::vector<cc_joint>& J, int ndof, const double* dof
             else if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
                 int err = 0;
                 const double ev = prog[k].eval(jv.data(), &err);
-                if (err) {
-                    char msg[200];
-                    snprintf(msg, sizeof(msg), "the mimic equation of joint %d failed to evaluate at row %lld (error %d: %s)", k, (long long)i, err,
-                             err == 1 ? "division by zero" : err == 2 ? "sqrt of a negative value" : err == 3 ? "log of a non-positive value" : err == 4 ? "trigonometric domain" : "value not finite");
-                    return fail(CC_ERR_INVALID, msg);
-                }
+                if (err) { f.row = i; f.joint = k; f.err = err; return; }
                 out[nactive + j.reserved] = ev;
                 jv[k] = mimic_limit_rule(ev, j);
             } else jv[k] = j.is_circular ? 0.0 : (0.0 < j.lower ? j.lower : 0.0 > j.upper ? j.upper : 0.0);   // passive: 0 clamped (kinbody.cpp:2262-2275)
@@ -1212,6 +1211,23 @@ int expand_rows_host(const std::vector<cc_joint>& J, int ndof, const double* dof
         for (int c = 0; c < nactive; ++c) out[c] = in[c];
         for (int c = 0; c < naffine; ++c) out[nactive + nexternal + c] = in[nactive + c];
     }
+    };
+    const int64_t kRowsPerThread = 8192;
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n / kRowsPerThread, 64), (int64_t)std::max(1u, std::thread::hardware_concurrency())));
+    std::vector<Failure> failures((size_t)nthreads);
+    if (nthreads == 1) run(0, n, failures[0]);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(run, n * t / nthreads, n * (t + 1) / nthreads, std::ref(failures[t]));
+        for (std::thread& th : pool) th.join();
+    }
+    for (const Failure& f : failures)             // thread t holds rows before those of thread t + 1
+        if (f.row >= 0) {
+            char msg[200];
+            snprintf(msg, sizeof(msg), "the mimic equation of joint %d failed to evaluate at row %lld (error %d: %s)", f.joint, (long long)f.row, f.err,
+                     f.err == 1 ? "division by zero" : f.err == 2 ? "sqrt of a negative value" : f.err == 3 ? "log of a non-positive value" : f.err == 4 ? "trigonometric domain" : "value not finite");
+            return fail(CC_ERR_INVALID, msg);
+        }
     return CC_OK;
 }
 
