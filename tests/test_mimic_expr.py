@@ -219,6 +219,13 @@ def test_expand_rows_refuses_what_it_cannot_evaluate():
     q[0, robot.GetJoint("JF1").dofindex] = 0.0
     rc, _ = _expand(robot, arr, nj, ext, active, q)
     assert rc != 0 and "division by zero" in lib.cc_last_error().decode()
+    # a large batch is split over threads: the first failing row in ROW order is the one named, and rows before it are filled
+    big = np.tile(np.array(robot.GetDOFValues()), (40000, 1))
+    big[:, robot.GetJoint("JF1").dofindex] = 0.5
+    big[[31000, 9000, 25000], robot.GetJoint("JF1").dofindex] = 0.0
+    rc, out = _expand(robot, arr, nj, ext, active, big)
+    assert rc != 0 and "row 9000 " in lib.cc_last_error().decode()
+    assert (out[:9000, len(active)] == 2.0).all()
     # an unknown function
     byname["JF1mimic"].mimic.text = "polyroots2(JF1, 1, 2)"
     rc, _ = _expand(robot, arr, nj, ext, active, q)
