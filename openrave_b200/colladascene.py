@@ -132,6 +132,15 @@ class ColladaRobotReader(object):
         if not url or not url.startswith("#"):
             raise NotImplementedError("external COLLADA reference %r" % url)
         e = self.by_id.get(url[1:])
+        if e is None and "/" in url:
+            # "#<id>/<id or sid of a descendant>/...": some exporters give every mesh's <vertices> the same id and address it through
+            # its geometry (man1.zae, neuronics-katana.zae)
+            parts = url[1:].split("/")
+            e = self.by_id.get(parts[0])
+            for name in parts[1:]:
+                if e is None:
+                    break
+                e = next((d for d in e.iter() if d is not e and (d.attrib.get("id") == name or d.attrib.get("sid") == name)), None)
         if e is None:
             raise ValueError("%s: unresolved reference %s" % (self.path, url))
         return e

@@ -99,8 +99,24 @@ class Environment(object):
                     for l in b.links:
                         l.prims = prims.get(b.name, {}).get("%d:%s" % (l.index, l.name), [])
             return True
+        # EnvironmentBase::Load takes a scene, a robot or a kinbody file (environment-core.h: the root tag decides for XML; a COLLADA
+        # file brings the bodies it holds)
         from .xmlscene import SceneLoader
-        SceneLoader(self.data_dirs).load_environment(self, filename)
+        loader = SceneLoader(self.data_dirs)
+        path = loader.find_file(filename, None)
+        if path is None:
+            raise IOError("cannot find %s" % filename)
+        import os
+        if os.path.splitext(path)[1].lower() in (".zae", ".dae"):
+            self.Add(loader.load_body_file(self, path, robot=True))
+            return True
+        tag = loader._parse(path).tag
+        if tag == "environment":
+            loader.load_environment(self, path)
+        elif tag in ("robot", "kinbody"):
+            self.Add(loader.load_body_file(self, path, robot=(tag == "robot")))      # IAM_StrictNameChecking, xmlreaders-core.cpp:3624-3638
+        else:
+            raise ValueError("%s: root element is <%s>, expected <environment>, <robot> or <kinbody>" % (path, tag))
         return True
 
     def ReadKinBodyURI(self, filename):

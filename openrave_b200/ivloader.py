@@ -170,7 +170,7 @@ def load_iv(path):
             return _load_iv_binary(path, head + f.read())
     with open(path, "r", errors="replace") as f:
         text = f.read()
-    if not text.startswith("#Inventor"):
+    if not (text.startswith("#Inventor") or text.startswith("#VRML V1.0 ascii")):     # VRML 1.0 is Inventor's ASCII grammar
         raise ValueError("%s: not an ASCII Inventor file" % path)
     chunks = [_parse_floats32(m.group(1)) for m in _POINT_RE.finditer(text)]
     if not chunks and re.search(r"\bFile\s*\{", text):

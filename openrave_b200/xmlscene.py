@@ -79,8 +79,8 @@ class SceneLoader(object):
     def load_mesh(self, path):
         if path not in self._mesh_cache:
             ext = os.path.splitext(path)[1].lower()
-            if ext != ".iv":
-                raise NotImplementedError("mesh format %s (only ASCII .iv through the ivcon path)" % ext)
+            if ext not in (".iv", ".wrl", ".vrml"):      # (.wrl: the VRML 1.0 subset, i.e. Inventor's grammar; VRML 2.0 needs Coin3D in the reference too)
+                raise NotImplementedError("mesh format %s (only Inventor .iv / VRML 1.0 through the ivcon path)" % ext)
             self._mesh_cache[path] = load_iv(path)
         return self._mesh_cache[path]
 
@@ -164,10 +164,18 @@ class SceneLoader(object):
     def read_robot(self, elem, robot, pdir):
         roottransoffset = len(robot.links)
         atts = elem.attrib
-        if "file" in atts:
-            self._load_into(robot, atts["file"], pdir, True)
-        rootoffset, rootj, rootjp = len(robot.links), len(robot.joints), len(robot.passive_joints)
         prefix = atts.get("prefix", "")
+        if "file" in atts:
+            # the file is read with this element's other attributes (xmlreaders-core.cpp:1770-1812): its own reader applies the
+            # prefix to what it loads, so the children of THIS element already see the prefixed names
+            fileoffset = len(robot.links), len(robot.joints), len(robot.passive_joints)
+            had = {id(m) for m in robot.manipulators}
+            self._load_into(robot, atts["file"], pdir, True)
+            if prefix:
+                self._apply_prefix(robot, prefix, *fileoffset)
+                self._prefix_manipulators(robot, prefix, had)
+        rootoffset, rootj, rootjp = len(robot.links), len(robot.joints), len(robot.passive_joints)
+        had_manips = {id(m) for m in robot.manipulators}
         trans = rm.IDENT_T
         for child in elem:
             tag = child.tag
@@ -183,8 +191,18 @@ class SceneLoader(object):
             robot.name = atts["name"]
         if prefix:
             self._apply_prefix(robot, prefix, rootoffset, rootj, rootjp)
+            self._prefix_manipulators(robot, prefix, had_manips)
         for l in robot.links[roottransoffset:]:
             l.t = rm.t_mul(trans, l.t)
+
+    @staticmethod
+    def _prefix_manipulators(robot, prefix, initial):
+        """xmlreaders-core.cpp:3106-3116: manipulators that did not exist before this reader get the prefix on their name and on
+        their gripper joint names (their base / effector are link objects here, renamed with the links)."""
+        for m in robot.manipulators:
+            if id(m) not in initial:
+                m.name = prefix + m.name
+                m.gripper_joint_names = [prefix + n for n in getattr(m, "gripper_joint_names", [])]
 
     def _read_manipulator(self, elem, robot):
         name = elem.attrib.get("name", "")
@@ -214,22 +232,25 @@ class SceneLoader(object):
             renamed[j.name] = prefix + j.name
             j.name = prefix + j.name
         for j in body.joints[rootj:] + body.passive_joints[rootjp:]:
-            if j.mimic is not None:
-                text = j.mimic.text
-                for old, new in renamed.items():
-                    text = text.replace(old, new)
-                j.mimic = MimicExpr(text)
+            if j.mimic is not None and renamed:
+                # one pass, longest names first (utils::SearchAndReplace): "JF1mimic" must not be rewritten through "JF1"
+                import re
+                pat = re.compile("|".join(re.escape(k) for k in sorted(renamed, key=len, reverse=True)))
+                j.mimic = MimicExpr(pat.sub(lambda m: renamed[m.group(0)], j.mimic.text))
 
     # ------------------------------------------------------------------ kinbody
     def read_kinbody(self, elem, body, pdir, scale=(1.0, 1.0, 1.0)):
         roottransoffset = len(body.links)
         atts = elem.attrib
+        prefix = atts.get("prefix", "")
         if "file" in atts:
+            fileoffset = len(body.links), len(body.joints), len(body.passive_joints)      # (see read_robot)
             self._load_into(body, atts["file"], pdir, False)
+            if prefix:
+                self._apply_prefix(body, prefix, *fileoffset)
         rootoffset, rootj, rootjp = len(body.links), len(body.joints), len(body.passive_joints)
         if "makejoinedlinksadjacent" in atts:
             body.make_joined_links_adjacent = int(atts["makejoinedlinksadjacent"]) != 0
-        prefix = atts.get("prefix", "")
         vtransforms = [l.t for l in body.links]    # `_vTransforms`: original poses for <offsetfrom>
         trans = rm.IDENT_T
         modelsdir = ""
