@@ -242,7 +242,9 @@ class OracleChecker(object):
         else:
             if bid in self._pose_only:
                 raise NotImplementedError("%s has a mimic equation the oracle's FK does not evaluate: pass poses" % body.name)
-            q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, len(active) + flatten.affine_count(getattr(body, "affine_dofs", 0)))
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            ncols = len(active) + flatten.affine_count(getattr(body, "affine_dofs", 0))
+            q = q.reshape(-1, ncols) if ncols else q.reshape(q.shape[0] if q.ndim == 2 else 1, 0)     # (a body without DOFs: n rows of nothing)
             n = q.shape[0]
         nl = len(body.links) + sum(len(g.body.links) for g in getattr(body, "grabbed", []))   # grabbed links follow the body's own
         verdict = np.zeros(n, dtype=np.uint32)

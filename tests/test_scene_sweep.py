@@ -107,3 +107,31 @@ def test_load_takes_scenes_robots_and_kinbodies():
     assert [(b.name, b.is_robot) for b in env.GetBodies()] == [("BarrettWAM", True), ("mug", False)]
     with pytest.raises(ValueError):
         env.Load("data/lab1.env.xml")            # strict name checking: the scene brings a second BarrettWAM
+
+
+def test_every_loaded_scene_flattens_and_goes_through_the_oracle():
+    """What the checkers take from a scene — FK chain, affects table, non-adjacent pairs, meshes — exists for every file: the joint
+    table has no equation the device could not hold (every shipped mimic equation is affine), and the oracle builds its models and
+    answers one batched query per robot at the load pose."""
+    import oracle
+    from openrave_b200 import flatten
+    robots = 0
+    for f in _files():
+        if os.path.basename(f) in SPHERICAL:
+            continue
+        env = Environment()
+        env.Load(f)
+        orc = oracle.OracleChecker(env, "port")
+        env.SetCollisionChecker(orc)
+        for b in env.GetBodies():
+            if b.GetDOF() > 0:
+                ext = []
+                arr, n = flatten.joint_table(b, externals=ext)
+                assert n == len(b.sorted_joints_all) and not ext, (f, b.name)
+                assert flatten.affects_table(b).shape == (b.GetDOF(), len(b.links))
+        for r in env.GetRobots():
+            out = orc.check_batch(r, np.array([r.GetDOFValues()]), active=list(range(r.GetDOF())))
+            assert out["verdict"].shape == (1,)
+            robots += 1
+        orc.DestroyEnvironment()
+    assert robots >= 50
