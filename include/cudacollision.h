@@ -196,7 +196,7 @@ int cc_body_set_kinematics(cc_scene* s, int body, int ndof, int njoints, const c
  * outside KinBody the reference offers none: OpenRAVEFunctionParserReal is opaque, kinbody.h:27-28).  `equation` is the joint's
  * mimic_pos string (Joint::GetMimicEquation(0, 0)) in fparser syntax over joint names; joint_names[njoints] names the joints of
  * cc_body_set_kinematics in the same order.  The library compiles it (operators () ^ unary- ! * / % + - = != < <= > >= & |,
- * fparser's elementary functions and if(); inline variables and OpenRAVE's polyroots* / SSSA / SASA / SASS helpers are refused with
+ * fparser's elementary functions, if(), OpenRAVE's SSSA / SASA / SASS; inline variables and the polyroots* helpers are refused with
  * CC_ERR_UNSUPPORTED and the position of the error in cc_last_error()).  Call after cc_body_set_kinematics, which forgets all
  * equations. */
 int cc_body_set_mimic_equation(cc_scene* s, int body, int joint, const char* equation, const char* const* joint_names, int njoints);

@@ -14,7 +14,7 @@ Restates what the reference's reader does for documents written by the OpenRAVE 
   DOF order: bound actuators first, in attach_actuator order                                    :3720-3792
 
 Transform elements compose left to right (`_ExtractFullTransform`, :4543-4550); rotations are axis + degrees (:4463).
-Documents that use other features (instance_joint across files, polylists, primitives in geometry_info, physics) raise
+Documents that use other features (instance_joint across files, <polygons>, container / cage geometries, physics) raise
 NotImplementedError instead of guessing.
 """
 import math
@@ -68,27 +68,28 @@ def read_document(path):
     return root
 
 
-def element_transform(elem):
-    """_ExtractFullTransform: product of the element's translate / rotate / matrix children, in order."""
+def element_transform(elem, unit=1.0):
+    """_ExtractFullTransform: product of the element's translate / rotate / matrix children, in order; lengths times the
+    document's unit (_GetUnitScale, :4473-4486, 5805-5820)."""
     t = rm.IDENT_T
     for c in elem:
         if c.tag == "translate":
             v = _floats(c.text)
-            t = rm.t_mul(t, (rm.IDENT_Q, (v[0], v[1], v[2])))
+            t = rm.t_mul(t, (rm.IDENT_Q, (v[0] * unit, v[1] * unit, v[2] * unit)))
         elif c.tag == "rotate":
             v = _floats(c.text)
             t = rm.t_mul(t, (rm.quat_from_axis_angle((v[0], v[1], v[2]), v[3] * (rm.PI / 180.0)), (0.0, 0.0, 0.0)))
         elif c.tag == "matrix":
             v = _floats(c.text)
             q = rm.quat_from_matrix(((v[0], v[1], v[2]), (v[4], v[5], v[6]), (v[8], v[9], v[10])))
-            t = rm.t_mul(t, (q, (v[3], v[7], v[11])))
+            t = rm.t_mul(t, (q, (v[3] * unit, v[7] * unit, v[11] * unit)))
         elif c.tag in ("scale", "skew", "lookat"):
             raise NotImplementedError("COLLADA <%s> transforms" % c.tag)
     return t
 
 
 def _mathml_to_text(elem, jointname_of):
-    """_ExtractMathML for the operators the writer emits: apply(plus|minus|times|divide|power), cn, csymbol/ci."""
+    """_ExtractMathML (colladareader.cpp:5275-5650): MathML content markup -> the fparser text OpenRAVE keeps as the equation."""
     tag = elem.tag
     if tag == "math":
         kids = list(elem)
@@ -97,21 +98,62 @@ def _mathml_to_text(elem, jointname_of):
         return _mathml_to_text(kids[0], jointname_of)
     if tag == "cn":
         return repr(float((elem.text or "0").strip()))
-    if tag in ("csymbol", "ci"):
+    if tag == "pi":
+        return "3.14159265358979323846"
+    if tag == "csymbol":
         return jointname_of((elem.text or "").strip())
-    if tag == "apply":
-        kids = list(elem)
-        op = kids[0].tag
-        args = [_mathml_to_text(k, jointname_of) for k in kids[1:]]
-        sym = {"plus": "+", "minus": "-", "times": "*", "divide": "/"}.get(op)
-        if sym is not None:
-            if op == "minus" and len(args) == 1:
-                return "(-%s)" % args[0]
-            return "(" + sym.join(args) + ")"
-        if op == "power":
-            return "pow(%s,%s)" % (args[0], args[1])
-        raise NotImplementedError("MathML operator <%s>" % op)
-    raise NotImplementedError("MathML element <%s>" % tag)
+    if tag == "ci":
+        return (elem.text or "").strip()
+    if tag != "apply":
+        raise NotImplementedError("MathML element <%s>" % tag)
+    kids = list(elem)
+    head = kids[0]
+    op = head.tag
+    arg = lambda k: _mathml_to_text(kids[k], jointname_of)
+    args = lambda: [_mathml_to_text(k, jointname_of) for k in kids[1:]]
+    nary = {"plus": "+", "times": "*", "and": "&", "or": "|"}
+    binary = {"divide": "(%s/%s)", "quotient": "floor(%s/%s)", "rem": "(%s%%%s)", "power": "pow(%s,%s)", "eq": "(%s=%s)", "neq": "(%s!=%s)",
+              "gt": "(%s>%s)", "lt": "(%s<%s)", "geq": "(%s>=%s)", "leq": "(%s<=%s)"}
+    unary = {"not": "(!%s)", "floor": "floor(%s)", "ceiling": "ceil(%s)", "ln": "log(%s)", "arcsin": "asin(%s)", "arccos": "acos(%s)",
+             "arctan": "atan(%s)", "arccosh": "acosh(%s)", "arcsinh": "asinh(%s)", "arctanh": "atanh(%s)"}
+    if op in nary:
+        return "(" + nary[op].join(args()) + ")"
+    if op == "minus":
+        return "(-%s)" % arg(1) if len(kids) == 2 else "(%s-%s)" % (arg(1), arg(2))
+    if op in binary:
+        return binary[op] % (arg(1), arg(2))
+    if op in unary:
+        return unary[op] % arg(1)
+    if op in ("root", "log"):
+        # <degree> / <logbase> qualifier first, if any
+        qual = kids[1] if len(kids) > 2 and kids[1].tag in ("degree", "logbase") else None
+        num = _mathml_to_text(kids[-1], jointname_of)
+        q = _mathml_to_text(list(qual)[0], jointname_of) if qual is not None and len(qual) else None
+        if op == "root":
+            if q is None or float(q) == 2.0:
+                return "sqrt(%s)" % num
+            if float(q) == 1.0:
+                return "(%s)" % num
+            return "cbrt(%s)" % num if float(q) == 3.0 else "pow(%s,1.0/%s)" % (num, q)
+        if q is None or float(q) == 10.0:
+            return "log10(%s)" % num
+        return "log2(%s)" % num if float(q) == 2.0 else "(log(%s)/log(%s))" % (num, q)
+    if op == "csymbol":
+        if head.attrib.get("encoding") == "text/xml":
+            fn = (head.text or "").strip()
+            if fn == "INRANGE":
+                a, b, c = arg(1), arg(2), arg(3)
+                return "((%s>=%s)&(%s<=%s))" % (a, b, a, c)
+            if fn in ("SSSA", "SASA", "SASS"):
+                return "%s(%s,%s,%s)" % (fn, arg(1), arg(2), arg(3))
+            if fn == "atan2":
+                return "atan2(%s,%s)" % (arg(1), arg(2))
+            raise NotImplementedError("MathML csymbol function %r" % fn)
+        return _mathml_to_text(head, jointname_of)
+    if op in ("implies", "forall", "exists", "conjugate", "arg", "real", "imaginary", "lcm", "factorial", "xor", "arccot", "arccoth",
+              "arccsc", "arccsch", "arcsec", "arcsech"):
+        raise NotImplementedError("MathML operator <%s>" % op)       # (the reference emits acot() ...: names fparser does not know)
+    return "%s(%s)" % (op, ",".join(args()))        # sin, cos, tan, abs, exp, min, max, ...: the tag is fparser's name
 
 
 class ColladaRobotReader(object):
@@ -120,6 +162,17 @@ class ColladaRobotReader(object):
         self.root = read_document(path)
         self.by_id = {}
         self.parent = {}
+        # <asset><unit meter=...>: one unit per document (what the shipped files have); _GetUnitScale looks it up per element
+        self.unit = 1.0
+        units = set()
+        for a in self.root.iter("asset"):
+            u = a.find("unit")
+            if u is not None and u.attrib.get("meter"):
+                units.add(float(u.attrib["meter"]))
+        if len(units) > 1:
+            raise NotImplementedError("COLLADA document with several length units %s" % sorted(units))
+        if units:
+            self.unit = units.pop()
         for e in self.root.iter():
             i = e.attrib.get("id")
             if i:
@@ -312,11 +365,11 @@ class ColladaRobotReader(object):
             chain.append(p)
             p = self.parent.get(p)
         for n in reversed(chain):
-            t = rm.t_mul(t, element_transform(n))
+            t = rm.t_mul(t, element_transform(n, self.unit))
         return t
 
     def _node_world(self, node):
-        return rm.t_mul(self._node_parent_transform(node), element_transform(node))
+        return rm.t_mul(self._node_parent_transform(node), element_transform(node, self.unit))
 
     # ---------------------------------------------------------------- links and joints
     def _link_name(self, le):
@@ -331,7 +384,7 @@ class ColladaRobotReader(object):
             link.index = len(body.links)
             body.links.append(link)
         self.link_by_sid[le.attrib.get("sid", name)] = link
-        link.t = rm.t_mul(tparent, element_transform(le))
+        link.t = rm.t_mul(tparent, element_transform(le, self.unit))
         if node is not None:
             self._extract_geometries(node, link)
         for att in le.findall("attachment_full"):
@@ -343,7 +396,7 @@ class ColladaRobotReader(object):
                 raise ValueError("%s: attachment joint %s not found" % (self.path, jref))
             if je.tag == "instance_joint":
                 je = self._url(je.attrib.get("url"))
-            tatt = element_transform(att)
+            tatt = element_transform(att, self.unit)
             axes = [c for c in je if c.tag in ("revolute", "prismatic")]
             if len(axes) != 1:
                 raise NotImplementedError("joint %s has %d axes (only 1-DOF joints)" % (jref, len(axes)))
@@ -371,7 +424,8 @@ class ColladaRobotReader(object):
             v = _floats(ax.find("axis").text)
             n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2]
             axis = rm.normalize3((v[0], v[1], v[2])) if n2 > 0 else (0.0, 0.0, 1.0)
-            mult = rm.PI / 180.0 if j.type == "hinge" else 1.0
+            mult = rm.PI / 180.0 if j.type == "hinge" else self.unit          # (:2341)
+            self.joint_units[j.name] = 1.0 if j.type == "hinge" else self.unit        # _mapJointUnits (:2091-2121)
             locked = self._resolve_bool(info, "locked") if info is not None else None
             has_soft = has_hard = False
             circular = None
@@ -478,51 +532,131 @@ class ColladaRobotReader(object):
         for ig in igs:
             ge = self._url(ig.attrib.get("url"))
             tlocal = rm.IDENT_T
+            primitive = None
             for ex in ge.findall("extra"):
                 if ex.attrib.get("type") == "geometry_info":
                     tec = self._openrave_technique(ex)
                     if tec is not None:
-                        for prim in ("box", "sphere", "cylinder", "capsule", "container", "cage"):
+                        for prim in ("container", "cage", "calibration_board"):
                             if tec.find(prim) is not None:
                                 raise NotImplementedError("geometry_info primitive <%s>" % prim)
-                        tlocal = element_transform(tec)
+                        tlocal = element_transform(tec, self.unit)
+                        primitive = self._geometry_info_primitive(tec, tlocal) or primitive
+            if primitive is not None:
+                # ExtractGeometry (:2956-3270): an analytic primitive in geometry_info replaces the mesh
+                primitive.name = ge.attrib.get("name", "")
+                primitive.t = rm.t_mul(tnodegeom, primitive.t)
+                primitive.init_collision_mesh()
+                link.geometries.append(primitive)
+                continue
             mesh = ge.find("mesh")
             if mesh is None:
                 continue
-            for kind in ("trifans", "tristrips", "polylist", "polygons"):
-                if mesh.find(kind) is not None:
-                    raise NotImplementedError("COLLADA <%s> primitives" % kind)
+            if mesh.find("polygons") is not None and not any(mesh.find(k) is not None for k in ("triangles", "trifans", "tristrips", "polylist")):
+                raise NotImplementedError("COLLADA <polygons> primitives")      # (the reference skips them too: :3291-3318)
             tlocalinv = rm.t_inv(tlocal)
-            for tri in mesh.findall("triangles"):
-                g = Geometry("trimesh")
-                g.name = ge.attrib.get("name", "")
-                stride, voff = 0, -1
-                vsrc = None
-                for inp in tri.findall("input"):
-                    off = int(inp.attrib.get("offset", "0"))
-                    if inp.attrib.get("semantic") == "VERTEX":
-                        voff = off
-                        vsrc = self._url(inp.attrib.get("source"))
-                    stride = max(stride, off)
-                stride += 1
-                if vsrc is None:
-                    continue
-                pos = None
-                for inp in vsrc.findall("input"):
-                    if inp.attrib.get("semantic") == "POSITION":
-                        pos = self._url(inp.attrib.get("source"))
-                if pos is None:
-                    continue
-                fl = np.array(_floats(pos.find("float_array").text), dtype=np.float64).reshape(-1, 3)
-                idx = np.array([int(x) for x in (tri.find("p").text or "").split()], dtype=np.int64)
-                ntri = int(tri.attrib.get("count", "0"))
-                vidx = idx[voff::stride][:3 * ntri]
-                # the reader emits a triangle soup: one vertex per index (:2617-2629), in the geometry's local frame
-                verts = fl[vidx]
-                g.verts = rm_transform_points(tlocalinv, verts)
-                g.idx = np.arange(verts.shape[0], dtype=np.int32).reshape(-1, 3)
-                g.t = rm.t_mul(tnodegeom, tlocal)
-                link.geometries.append(g)
+            # one geometry per primitive element, in the reference's order of kinds (:3291-3318)
+            for kind in ("triangles", "trifans", "tristrips", "polylist"):
+                for tri in mesh.findall(kind):
+                    soup = self._primitive_soup(tri, kind)
+                    if soup is None:
+                        continue
+                    verts, idx = soup
+                    g = Geometry("trimesh")
+                    g.name = ge.attrib.get("name", "")
+                    g.verts = rm_transform_points(tlocalinv, verts)
+                    g.idx = idx
+                    g.t = rm.t_mul(tnodegeom, tlocal)
+                    link.geometries.append(g)
+
+    @staticmethod
+    def _geometry_info_primitive(tec, tlocal):
+        """box / sphere / cylinder / cylinderz of a geometry_info technique (:2982-3050); None when it holds none."""
+        def first_floats(elem, name, n):
+            c = elem.find(name)
+            v = _floats(c.text) if c is not None else []
+            return v[:n] if len(v) >= n else None
+        for child in tec:
+            if child.tag == "box":
+                v = first_floats(child, "half_extents", 3)
+                if v:
+                    g = Geometry("box"); g.data = (v[0], v[1], v[2]); g.t = tlocal
+                    return g
+            elif child.tag == "sphere":
+                v = first_floats(child, "radius", 1)
+                if v:
+                    g = Geometry("sphere"); g.data = (v[0], 0.0, 0.0); g.t = tlocal
+                    return g
+            elif child.tag in ("cylinder", "cylinderz"):
+                r, h = first_floats(child, "radius", 1), first_floats(child, "height", 1)
+                if r and h:
+                    g = Geometry("cylinder"); g.data = (r[0], h[0], 0.0)
+                    # COLLADA cylinders run along y, OpenRAVE's along z (:3025-3027)
+                    g.t = rm.t_mul(tlocal, (rm.quat_rotate_direction((0.0, 0.0, 1.0), (0.0, 1.0, 0.0)), (0.0, 0.0, 0.0))) if child.tag == "cylinder" else tlocal
+                    return g
+        return None
+
+    def _primitive_soup(self, tri, kind):
+        """Vertices and triangle indices of one <triangles> / <trifans> / <tristrips> / <polylist> element the way the reader
+        emits them (:2566-2900): one vertex per index; fans and polygons as (first, i-1, i), strips with alternating winding."""
+        stride, voff = 0, -1
+        vsrc = None
+        for inp in tri.findall("input"):
+            off = int(inp.attrib.get("offset", "0"))
+            if inp.attrib.get("semantic") == "VERTEX":
+                voff = off
+                vsrc = self._url(inp.attrib.get("source"))
+            stride = max(stride, off)
+        stride += 1
+        if vsrc is None:
+            return None
+        pos = None
+        for inp in vsrc.findall("input"):
+            if inp.attrib.get("semantic") == "POSITION":
+                pos = self._url(inp.attrib.get("source"))
+        if pos is None:
+            return None
+        cache = self.__dict__.setdefault("_position_cache", {})         # thousands of primitives may share one <source>
+        fl = cache.get(id(pos))
+        if fl is None:
+            fl = cache[id(pos)] = np.array((pos.find("float_array").text or "").split(), dtype=np.float64).reshape(-1, 3) * self.unit
+        count = int(tri.attrib.get("count", "0"))
+        plists = [np.array([int(x) for x in (p.text or "").split()], dtype=np.int64) for p in tri.findall("p")]
+        if kind == "triangles":
+            if not plists:
+                return None
+            vidx = plists[0][voff::stride][:3 * count]
+            verts = fl[vidx]
+            return verts, np.arange(verts.shape[0], dtype=np.int32).reshape(-1, 3)
+        verts, tris = [], []
+        if kind in ("trifans", "tristrips"):
+            for p in plists[:count]:
+                vidx = p[voff::stride]
+                start = len(verts)
+                verts.extend(fl[vidx])
+                flip = False
+                for iv in range(start + 2, len(verts)):
+                    if kind == "trifans":
+                        tris.append((start, iv - 1, iv))
+                    else:
+                        tris.append((iv - 2, iv, iv - 1) if flip else (iv - 2, iv - 1, iv))
+                        flip = not flip
+        else:   # polylist
+            vc = tri.find("vcount")
+            counts = [int(x) for x in (vc.text or "").split()] if vc is not None else []
+            p = plists[0] if plists else np.zeros(0, dtype=np.int64)
+            k = voff
+            for nv in counts:
+                if nv > 0 and k + (nv - 1) * stride < len(p):
+                    start = len(verts)
+                    for _ in range(nv):
+                        verts.append(fl[p[k]])
+                        k += stride
+                    for iv in range(start + 2, len(verts)):
+                        tris.append((start, iv - 1, iv))
+        if not tris:
+            return None
+        return np.array(verts, dtype=np.float64).reshape(-1, 3), np.array(tris, dtype=np.int32).reshape(-1, 3)
 
     # ---------------------------------------------------------------- formulas, extras, manipulators
     def _extract_formulas(self, ktec):
@@ -538,7 +672,8 @@ class ColladaRobotReader(object):
                 jj = self._joint_from_ref(ref)
                 if jj is None:
                     raise ValueError("formula references unknown joint %s" % ref)
-                return jj.name
+                u = self.joint_units.get(jj.name, 1.0)
+                return jj.name if u == 1.0 else "(%r*%s)" % (1.0 / u, jj.name)        # (:5623-5628)
             tec = None
             for t in f.findall("technique"):
                 if t.attrib.get("profile") == "OpenRAVE":
@@ -553,7 +688,10 @@ class ColladaRobotReader(object):
                 if kids:
                     eq = _mathml_to_text(kids[0], jointname_of)
             if eq:
-                j.mimic = MimicExpr(eq)
+                tu = self.joint_units.get(j.name, 1.0)
+                if tu != 1.0:
+                    eq = "%r*(%s)" % (tu, eq)                                        # (:1618-1620)
+                j.mimic = MimicExpr(eq, names=[jj.name for jj in self.body.all_joints() + self.new_active + self.new_passive])
 
     def _link_from_ref(self, ref):
         e = self._resolve_sidref(ref)
@@ -596,7 +734,7 @@ class ColladaRobotReader(object):
                 m.base = self._link_from_ref(fo.attrib.get("link", ""))
             if ft is not None:
                 m.effector = self._link_from_ref(ft.attrib.get("link", ""))
-                m.t_local = element_transform(ft)
+                m.t_local = element_transform(ft, self.unit)
             for gj in tec.findall("gripper_joint"):
                 j = self._joint_from_ref(gj.attrib.get("joint", ""))
                 if j is not None:

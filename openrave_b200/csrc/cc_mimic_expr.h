@@ -6,8 +6,8 @@
 // language into a small stack program: fparser's operator table and precedences ("The function string syntax" of its
 // documentation: () ^ unary- ! * / % + - comparisons & |, '^' right-associative and binding tighter than a unary minus on its
 // left), its elementary functions, its comparison epsilon as OpenRAVE sets it (g_fEpsilonLinear, kinbodyjoint.cpp:751-753) and its
-// truth rule (|x| >= 0.5).  Not supported, and refused at parse time: inline variables (y := ...), units, user constants, and
-// OpenRAVE's multi-valued helper functions (polyroots*, SSSA, SASA, SASS).
+// truth rule (|x| >= 0.5), plus OpenRAVE's single-valued triangle helpers SSSA / SASA / SASS.  Not supported, and refused at parse
+// time: inline variables (y := ...), units, user constants, and OpenRAVE's multi-valued polyroots* helpers.
 //
 // Pinned in tests/test_mimic_expr.py against the vendored fparser itself (oracle/_ref/libfparser_ref.so).
 #pragma once
@@ -25,12 +25,13 @@ namespace ccexpr {
 
 enum Code : int {
     kConst, kVar, kNeg, kNot, kAdd, kSub, kMul, kDiv, kMod, kPow, kEq, kNe, kLt, kLe, kGt, kGe, kAnd, kOr, kJumpIfFalse, kJump,
-    kFn1, kFn2
+    kFn1, kFn2, kFn3
 };
 enum Fn : int {
     fAbs, fAcos, fAcosh, fAsin, fAsinh, fAtan, fAtanh, fCbrt, fCeil, fCos, fCosh, fCot, fCsc, fExp, fExp2, fFloor, fInt, fLog, fLog10,
     fLog2, fSec, fSin, fSinh, fSqrt, fTan, fTanh, fTrunc,                     // one argument
-    fAtan2, fHypot, fMax, fMin, fPowFn                                          // two arguments
+    fAtan2, fHypot, fMax, fMin, fPowFn,                                         // two arguments
+    fSSSA, fSASA, fSASS                                                         // three: OpenRAVE's triangle helpers (kinbodyjoint.cpp:722-746)
 };
 struct FnName { const char* name; int fn; int nargs; };
 static const FnName kFunctions[] = {
@@ -40,6 +41,9 @@ static const FnName kFunctions[] = {
     {"int", fInt, 1}, {"log", fLog, 1}, {"log10", fLog10, 1}, {"log2", fLog2, 1}, {"max", fMax, 2}, {"min", fMin, 2},
     {"pow", fPowFn, 2}, {"sec", fSec, 1}, {"sin", fSin, 1}, {"sinh", fSinh, 1}, {"sqrt", fSqrt, 1}, {"tan", fTan, 1},
     {"tanh", fTanh, 1}, {"trunc", fTrunc, 1},
+    // registered on top of fparser by CreateJointFunctionParser (kinbodyjoint.cpp:748-765); COLLADA formulas of closed linkages
+    // use them (colladareader.cpp:5571-5574)
+    {"SSSA", fSSSA, 3}, {"SASA", fSASA, 3}, {"SASS", fSASS, 3},
 };
 
 // fparser's EvalError() codes, plus kNotFinite: a power or the final value that is NaN or infinite.  (fparser rewrites powers at
@@ -134,6 +138,22 @@ struct Program {
                 case fTanh: r = tanh(x); break;
                 case fTrunc: r = trunc(x); break;
                 }
+                st[sp - 1] = r;
+                break;
+            }
+            case kFn3: {
+                const double c = st[--sp], b = st[--sp], a = st[sp - 1];
+                double r = 0;
+                switch (o.arg) {
+                case fSSSA: {                 // three sides -> the angle opposite the first
+                    const double f = (a * a + b * b - c * c) / (2 * b);
+                    r = atan2(sqrt(a * a - f * f), b - f);
+                    break;
+                }
+                case fSASA: r = atan2(a * sin(b), c - a * cos(b)); break;            // side, angle, side -> the missing angle
+                case fSASS: r = sqrt(a * a + c * c - 2 * a * c * cos(b)); break;      // side, angle, side -> the missing side
+                }
+                if (!isfinite(r)) { e = kNotFinite; r = 0; }
                 st[sp - 1] = r;
                 break;
             }
@@ -343,12 +363,12 @@ private:
                 pos_ = end;
                 if (!eat('(')) { fail("expected '(' after a function name"); return; }
                 parse_or();
-                if (f.nargs == 2) {
+                for (int a = 1; a < f.nargs; ++a) {
                     if (!failed_ && !eat(',')) { fail("expected ','"); return; }
                     parse_or();
                 }
                 if (!failed_ && !eat(')')) { fail("expected ')'"); return; }
-                if (f.nargs == 1) emit(kFn1, f.fn, 0, 1, 1); else emit(kFn2, f.fn, 0, 2, 1);
+                if (f.nargs == 1) emit(kFn1, f.fn, 0, 1, 1); else if (f.nargs == 2) emit(kFn2, f.fn, 0, 2, 1); else emit(kFn3, f.fn, 0, 3, 1);
                 return;
             }
         fail("unknown name (not a joint of this body and not a supported function)");

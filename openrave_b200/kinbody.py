@@ -213,25 +213,44 @@ class MimicExpr(object):
 
     # names of fparser's functions (3rdparty/fparser-4.5.2/extrasrc/fptypes.hh:118-160) that the library's compiler knows
     _FUNCTIONS = frozenset("abs acos acosh asin asinh atan atan2 atanh cbrt ceil cos cosh cot csc exp exp2 floor hypot if int log "
-                           "log10 log2 max min pow sec sin sinh sqrt tan tanh trunc".split())
+                           "log10 log2 max min pow sec sin sinh sqrt tan tanh trunc SSSA SASA SASS".split())
 
-    def __init__(self, text):
+    def __init__(self, text, names=None):
+        """`names`: the joint names the equation may use.  Needed when a name is not an identifier ("dummy-1",
+        "DarmSim/lowerTiltTopJoint" in COLLADA robots): names are then matched as the reference's substitution matches them,
+        longest first (kinbodyjoint.cpp:2236-2244), before anything is parsed."""
+        import re
         self.text = text.strip()
         self._code = None
+        self._alias = None
+        parse_text = self.text
+        if names:
+            pat = re.compile("|".join(re.escape(k) for k in sorted(set(names), key=len, reverse=True)))
+            used = sorted(set(pat.findall(self.text)))
+            self._alias = {k: "_v%d_" % i for i, k in enumerate(used)}
+            parse_text = pat.sub(lambda m: self._alias[m.group(0)], self.text)
         try:
-            self.tree = ast.parse(self.text.replace("^", "**"), mode="eval")
+            self.tree = ast.parse(parse_text.replace("^", "**"), mode="eval")
             for node in ast.walk(self.tree):
                 if not isinstance(node, self._ALLOWED):
                     raise ValueError("not plain arithmetic")
-            self.varnames = sorted({n.id for n in ast.walk(self.tree) if isinstance(n, ast.Name)})
+            found = sorted({n.id for n in ast.walk(self.tree) if isinstance(n, ast.Name)})
+            if self._alias is not None:
+                back = {v: k for k, v in self._alias.items()}
+                if any(f not in back for f in found):
+                    raise ValueError("unknown name")
+                found = sorted(back[f] for f in found)
+            self.varnames = found
             self._code = compile(self.tree, "<mimic>", "eval")
         except (ValueError, SyntaxError):
             # functions, comparisons, if(): the rest of fparser's language goes through the library's own compiler for it
             # (csrc/cc_mimic_expr.h, a host-side entry that needs no device)
-            import re
             self.tree = None
-            self.varnames = sorted(set(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", re.sub(r"\b0[xX][0-9a-fA-F]+|\b\d+\.?\d*([eE][-+]?\d+)?", " ", self.text)))
-                                   - self._FUNCTIONS)
+            if self._alias is not None:
+                self.varnames = sorted(self._alias)
+            else:
+                self.varnames = sorted(set(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", re.sub(r"\b0[xX][0-9a-fA-F]+|\b\d+\.?\d*([eE][-+]?\d+)?", " ", self.text)))
+                                       - self._FUNCTIONS)
             try:
                 self._library_eval([[0.0] * len(self.varnames)])
             except RuntimeError as e:
@@ -254,7 +273,12 @@ class MimicExpr(object):
     def eval(self, values):
         if self._code is None:
             return float(self._library_eval([[float(values[v]) for v in self.varnames]])[0])
-        return float(eval(self._code, {"__builtins__": {}}, dict(values)))
+        return float(eval(self._code, {"__builtins__": {}}, self._env(values)))
+
+    def _env(self, values):
+        if self._alias is None:
+            return dict(values)
+        return {self._alias[k]: values[k] for k in self.varnames}
 
     def eval_many(self, values, n):
         """The same for n configurations at once: `values` maps joint names to arrays [n] (or scalars)."""
@@ -262,7 +286,7 @@ class MimicExpr(object):
         if self._code is None:
             cols = [np.broadcast_to(np.asarray(values[v], dtype=np.float64), (n,)) for v in self.varnames]
             return self._library_eval(np.stack(cols, axis=1) if cols else np.zeros((n, 1)))
-        return np.broadcast_to(np.asarray(eval(self._code, {"__builtins__": {}}, dict(values)), dtype=np.float64), (n,)).copy()
+        return np.broadcast_to(np.asarray(eval(self._code, {"__builtins__": {}}, self._env(values)), dtype=np.float64), (n,)).copy()
 
     def affine(self):
         """Return (varname, a, b) if the expression is affine in exactly one joint, else None."""

@@ -65,7 +65,7 @@ def body_from_dict(d, meshes, env=None):
         j.links = [body.links[jd["links"][0]], body.links[jd["links"][1]]]
         j.lower, j.upper, j.offset = jd["lower"], jd["upper"], jd["offset"]
         j.circular, j.resolution, j.weight = jd["circular"], jd["resolution"], jd["weight"]
-        j.mimic = MimicExpr(jd["mimic"]) if jd["mimic"] else None
+        j.mimic = MimicExpr(jd["mimic"], names=[x["name"] for x in d["joints"]]) if jd["mimic"] else None
         j.axis = tuple(jd["axis"])
         j.anchor = tuple(jd["anchor"])
         j.t_left_nooffset, j.t_right_nooffset = _t_tuple(jd["tl"]), _t_tuple(jd["tr"])

@@ -135,3 +135,72 @@ def test_every_loaded_scene_flattens_and_goes_through_the_oracle():
             robots += 1
         orc.DestroyEnvironment()
     assert robots >= 50
+
+
+EXTRA_REFUSED = {
+    "kuka-kr360.zae": NotImplementedError,                 # a joint with two axes
+    "calibration_board.dae": NotImplementedError,          # the calibration-board geometry type
+    "bobcat.robot.xml": IOError,                           # its meshes are not in the tree (and are VRML 2.0: Coin3D in the reference)
+    "arm_bucket_assy_Amimic.robot.xml": IOError,
+}
+
+
+def test_the_collada_robot_collection_and_the_reference_test_data():
+    """src/collada_robots (31 more robots, several in millimetres, with <trifans>, SASA / SASS formulas of closed linkages, joint
+    names that are not identifiers) and test/testdata."""
+    files = sorted(glob.glob("/root/reference/src/collada_robots/*.zae") + glob.glob("/root/reference/test/testdata/*.xml") +
+                   glob.glob("/root/reference/test/testdata/*.dae"))
+    assert len(files) >= 36
+    refused = {}
+    for f in files:
+        env = Environment()
+        try:
+            env.Load(f)
+        except (NotImplementedError, IOError) as e:
+            refused[os.path.basename(f)] = type(e)
+            continue
+        b = env.GetBodies()[0]
+        for l in b.links:
+            if len(l.idx):
+                assert l.idx.min() >= 0 and l.idx.max() < len(l.verts), (f, l.name)
+                assert np.isfinite(np.asarray(l.verts)).all()
+        lo, hi = (np.array(x) for x in b.GetDOFLimits()) if b.GetDOF() else (np.zeros(0), np.zeros(0))
+        if b.GetDOF():
+            b.SetDOFValues((lo + 0.3 * (hi - lo)).tolist())          # every equation evaluates
+            for l in b.links:
+                assert np.isfinite(np.array(l.t[0])).all() and np.isfinite(np.array(l.t[1])).all(), (f, l.name)
+    assert {k: (IOError if issubclass(v, IOError) else v) for k, v in refused.items()} == EXTRA_REFUSED
+
+
+def test_units_formula_functions_and_names_that_are_not_identifiers():
+    env = Environment()
+    env.Load("/root/reference/src/collada_robots/kuka-kr150.zae")          # <unit meter="0.001">, <trifans>
+    r = env.GetBodies()[0]
+    v = np.vstack([np.asarray(rm_pts(l)) for l in r.links if len(l.verts)])
+    size = v.max(axis=0) - v.min(axis=0)
+    assert 1.0 < size.max() < 5.0                                           # metres, not millimetres
+    env = Environment()
+    env.Load("/root/reference/src/collada_robots/kuka-kr210l180.zae")      # the gas spring: SASA / SASS of the arm angle
+    r = env.GetBodies()[0]
+    eqs = {j.name: j.mimic for j in r.passive_joints if j.mimic is not None}
+    assert any("SASA(" in m.text for m in eqs.values())
+    m = [m for m in eqs.values() if m.text.startswith("SASA(")][0]
+    a, b = 185.0, 697.271
+    g = 90.0 * 0.0174533 + 0.25
+    assert abs(m.eval({m.varnames[0]: 0.25}) - np.arctan2(a * np.sin(g), b - a * np.cos(g))) < 1e-12
+    env = Environment()
+    env.Load("/root/reference/src/collada_robots/darpa-arm.zae")
+    r = env.GetBodies()[0]
+    j = [j for j in r.passive_joints if j.name == "DarmSim/lowerTiltTopJoint"][0]
+    assert j.mimic.varnames == ["DarmSim/LowerPanTilt/Tilt"] and j.mimic.affine() == ("DarmSim/LowerPanTilt/Tilt", -1.0, -0.0)
+    env = Environment()
+    env.Load("/root/reference/test/testdata/box0.dae")                      # geometry_info <box>
+    b = env.GetBodies()[0]
+    v = np.asarray(b.links[0].verts)
+    assert len(v) == 8 and np.allclose((v.max(axis=0) - v.min(axis=0)) / 2, [0.1, 0.05, 0.1])
+
+
+def rm_pts(link):
+    """world-frame vertices of a link"""
+    R = np.array(rm.matrix_from_quat(link.t[0]))
+    return np.asarray(link.verts) @ R.T + np.array(link.t[1])
