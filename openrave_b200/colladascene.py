@@ -446,7 +446,7 @@ class ColladaRobotReader(object):
                         b = np_.find("bool")
                         i = np_.find("int")
                         if b is not None:
-                            circular = (b.text or "").strip().lower() == "true"
+                            circular = (b.text or "").strip().lower() in ("true", "1")
                         elif i is not None:
                             circular = int((i.text or "0").strip()) != 0
                     elif sid == "planning_weight":
@@ -485,14 +485,14 @@ class ColladaRobotReader(object):
             return None
         b = e.find("bool")
         if b is not None:
-            return (b.text or "").strip().lower() == "true"
+            return (b.text or "").strip().lower() in ("true", "1")          # xsBoolean
         p = e.find("param")
         if p is not None:
             for np_ in info.findall("newparam"):
                 if np_.attrib.get("sid") == (p.text or "").strip():
                     bb = np_.find("bool")
                     if bb is not None:
-                        return (bb.text or "").strip().lower() == "true"
+                        return (bb.text or "").strip().lower() in ("true", "1")
         return None
 
     @staticmethod
@@ -717,7 +717,7 @@ class ColladaRobotReader(object):
                     l = self._link_from_ref(e.attrib.get("link", ""))
                     b = e.find("bool")
                     if l is not None and b is not None:
-                        l.enabled = (b.text or "").strip().lower() == "true"
+                        l.enabled = (b.text or "").strip().lower() in ("true", "1")
                 elif e.tag == "bind_instance_geometry":
                     pass    # geometry groups are not on the collision path
 
