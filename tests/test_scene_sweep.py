@@ -204,3 +204,38 @@ def rm_pts(link):
     """world-frame vertices of a link"""
     R = np.array(rm.matrix_from_quat(link.t[0]))
     return np.asarray(link.verts) @ R.T + np.array(link.t[1])
+
+
+def test_a_shipped_robot_with_non_affine_mimic_equations_through_the_device_path_on_the_host():
+    """kuka-kr210l180: the gas spring between base and arm is two passive joints whose angles are SASA(...) of the shoulder angle —
+    mimic equations the device chain program cannot hold.  They become caller-evaluated columns (CC_MIMIC_EXTERNAL); the library's
+    own compiler fills them from the equation text, and the FK chain program walked on the host with those columns reproduces the
+    harness' SetDOFValues for the whole robot."""
+    import ctypes
+    from openrave_b200 import flatten
+    from openrave_b200.checker import load_library
+    from openrave_b200.kinbody import external_mimic_values
+    from test_fk_program import _harness, _pose_err, _program
+    from test_mimic_expr import _expand
+    env = Environment()
+    env.Load("/root/reference/src/collada_robots/kuka-kr210l180.zae")
+    robot = env.GetBodies()[0]
+    ext = []
+    arr, nj = flatten.joint_table(robot, externals=ext)
+    assert len(ext) == 2 and all("SASA(" in e.mimic.text for e in ext)
+    lo, hi = (np.array(x) for x in robot.GetDOFLimits())
+    rng = np.random.default_rng(3)
+    active = list(range(robot.GetDOF()))
+    q = lo + (hi - lo) * rng.random((64, robot.GetDOF()))
+    rc, rows = _expand(robot, arr, nj, ext, active, q)                     # the library's compiler + expansion
+    assert rc == 0, load_library().cc_last_error()
+    want_cols = external_mimic_values(robot, q, ext)                       # the twin's
+    assert np.abs(rows[:, len(active):] - want_cols).max() < 1e-12
+    want = _harness(robot, q)
+    for walk in (0, 1):
+        got, counts = _program(robot, arr, nj, active, rows, walk)
+        assert _pose_err(got, want) < 1e-11, walk
+    # the spring really moves with the shoulder
+    j2 = robot.GetJoint("Joint_2").dofindex
+    assert np.ptp(rows[:, len(active)]) > 0.05 and abs(np.corrcoef(q[:, j2], rows[:, len(active)])[0, 1]) > 0.5
+    del ctypes
