@@ -14,7 +14,7 @@ g++ -O1 -g -std=c++20 -fPIC -Wall $SAN -c "$ROOT/openrave_b200/csrc/cc_planner.c
 cd "$ROOT"
 TESTS="tests/test_birrt.py tests/test_bvh_build.py tests/test_edge_check.py tests/test_pair_tables.py tests/test_ramp_check.py
        tests/test_cachechecker.py tests/test_affine_dofs.py tests/test_motion_classes.py tests/test_fk_program.py tests/test_mimic_expr.py
-       tests/test_broadphase_boxes.py tests/test_capi_symbols.py"
+       tests/test_broadphase_boxes.py tests/test_capi_symbols.py tests/test_scene_sweep.py"
 LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1 \
     CUDACOLLISION_LIB=$ROOT/build/libcc_asan.so python -m pytest $TESTS -q -s -m "not gpu" > "$LOG" 2>&1 || true
 tail -2 "$LOG"
