@@ -108,7 +108,10 @@ class Environment(object):
             raise IOError("cannot find %s" % filename)
         import os
         if os.path.splitext(path)[1].lower() in (".zae", ".dae"):
-            self.Add(loader.load_body_file(self, path, robot=True))
+            # a document with an articulated system brings a robot, anything else a kinbody (colladareader.cpp Extract)
+            from .colladascene import read_document
+            is_robot = any(True for _ in read_document(path).iter("instance_articulated_system"))
+            self.Add(loader.load_body_file(self, path, robot=is_robot))
             return True
         tag = loader._parse(path).tag
         if tag == "environment":
