@@ -162,6 +162,7 @@ class ColladaRobotReader(object):
         self.root = read_document(path)
         self.by_id = {}
         self.parent = {}
+        self._position_cache = {}
         # <asset><unit meter=...>: one unit per document (what the shipped files have); _GetUnitScale looks it up per element
         self.unit = 1.0
         units = set()
@@ -616,10 +617,9 @@ class ColladaRobotReader(object):
                 pos = self._url(inp.attrib.get("source"))
         if pos is None:
             return None
-        cache = self.__dict__.setdefault("_position_cache", {})         # thousands of primitives may share one <source>
-        fl = cache.get(id(pos))
+        fl = self._position_cache.get(id(pos))                          # thousands of primitives may share one <source>
         if fl is None:
-            fl = cache[id(pos)] = np.array((pos.find("float_array").text or "").split(), dtype=np.float64).reshape(-1, 3) * self.unit
+            fl = self._position_cache[id(pos)] = np.array((pos.find("float_array").text or "").split(), dtype=np.float64).reshape(-1, 3) * self.unit
         count = int(tri.attrib.get("count", "0"))
         plists = [np.array([int(x) for x in (p.text or "").split()], dtype=np.int64) for p in tri.findall("p")]
         if kind == "triangles":
