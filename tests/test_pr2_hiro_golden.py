@@ -94,4 +94,18 @@ def test_hironx_structure_and_home():
     assert manips["leftarm_torso"].GetArmIndices() == [0, 13, 14, 15, 16, 17, 18]
     assert not env.CheckCollision(robot)          # test_collision.py:26-35 loads this scene and expects a free start
     assert not robot.CheckSelfCollision()
-    assert len(robot.GetNonAdjacentLinks(0)) > 150
+    # regression pin (no external golden exists: the reference cannot run here): 24 links -> 276 pairs, 252 of them non-adjacent and
+    # apart at the load pose.  The same list comes back through the CUDA checker's probe (tests/test_gpu_parity_robots.py).
+    assert len(robot.GetNonAdjacentLinks(0)) == 252
+
+
+def test_pr2_nonadjacent_pair_count():
+    """901 self pairs: 88 links -> 3828 pairs, minus adjacency (joined links, the 31 ignore_link_pair extras, links one non-static
+    joint apart, geometry-less links) and minus the pairs in contact at the load pose (kinbody.cpp:4940-5010, 5532-5612).  Regression
+    pin; the round-1 review counted the same number independently."""
+    env = load_scene("pr2test1")
+    env.SetCollisionChecker(oracle.OracleChecker(env, "port"))
+    robot = env.GetRobots()[0]
+    na = robot.GetNonAdjacentLinks(0)
+    assert len(na) == 901 and len(set(na)) == 901
+    assert all((v & 0xffff) < (v >> 16) < 88 for v in na)
