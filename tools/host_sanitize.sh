@@ -19,3 +19,4 @@ LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so
     CUDACOLLISION_LIB=$ROOT/build/libcc_asan.so python -m pytest $TESTS -q -s -m "not gpu" > "$LOG" 2>&1 || true
 tail -2 "$LOG"
 echo "sanitizer reports: $(grep -c 'runtime error\|AddressSanitizer' "$LOG" || true)"
+rm -f "$ROOT/build/libcc_asan.so" "$ROOT/build/cc_planner_asan.o"      # 30 MB that would otherwise travel to the GPU box
