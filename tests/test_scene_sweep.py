@@ -239,3 +239,53 @@ def test_a_shipped_robot_with_non_affine_mimic_equations_through_the_device_path
     j2 = robot.GetJoint("Joint_2").dofindex
     assert np.ptp(rows[:, len(active)]) > 0.05 and abs(np.corrcoef(q[:, j2], rows[:, len(active)])[0, 1]) > 0.5
     del ctypes
+
+
+def test_fk_chain_program_of_every_shipped_robot():
+    """`cc_debug_fk_program` (the program a query compiles for the device, walked on the host in both kernel orders) against the
+    harness' SetDOFValues for every articulated body of every file that loads: one refusal — pumabarrett.robot.xml includes the
+    hand without a joint to the arm, a forest the chain compiler rejects by name instead of guessing which tree moves."""
+    from openrave_b200 import flatten
+    from openrave_b200.checker import load_library
+    from openrave_b200.kinbody import external_mimic_values
+    from test_fk_program import _harness, _pose_err
+    import ctypes
+    lib = load_library()
+    files = sorted(glob.glob(REF + "/robots/*") + glob.glob(REF + "/collada_robots/*.zae") + glob.glob(REF + "/data/*.env.xml"))
+    rng = np.random.default_rng(1)
+    bodies, refused, worst = 0, [], 0.0
+    for f in files:
+        if not f.endswith((".xml", ".zae")):
+            continue
+        env = Environment()
+        try:
+            env.Load(f)
+        except (NotImplementedError, IOError):
+            continue
+        for b in env.GetBodies():
+            if b.GetDOF() == 0 or len(b.links) < 2:
+                continue
+            ext = []
+            arr, nj = flatten.joint_table(b, externals=ext)
+            lo, hi = (np.array(x) for x in b.GetDOFLimits())
+            q = lo + (hi - lo) * rng.random((4, b.GetDOF()))
+            rows = np.hstack([q, external_mimic_values(b, q, ext)]) if ext else q
+            want = _harness(b, q)
+            nl = len(b.links)
+            dof = np.array(b.GetDOFValues(), dtype=np.float64)
+            base = flatten.transforms8([b.links[0].t])[0].copy()
+            act = np.arange(b.GetDOF(), dtype=np.int32)
+            rows = np.ascontiguousarray(rows, dtype=np.float64)
+            for walk in (0, 1):
+                out = np.zeros((len(q), nl, 8))
+                rc = lib.cc_debug_fk_program(ctypes.addressof(arr), nj, nl, b.GetDOF(), dof.ctypes.data_as(ctypes.c_void_p),
+                                             base.ctypes.data_as(ctypes.c_void_p), act.ctypes.data_as(ctypes.c_void_p), len(act), None, walk,
+                                             rows.ctypes.data_as(ctypes.c_void_p), len(q), out.ctypes.data_as(ctypes.c_void_p), None)
+                if rc != 0:
+                    refused.append((os.path.basename(f), lib.cc_last_error().decode()))
+                    break
+                worst = max(worst, _pose_err(out, want))
+            else:
+                bodies += 1
+    assert bodies >= 85 and worst < 1e-11, (bodies, worst)
+    assert [r[0] for r in refused] == ["pumabarrett.robot.xml"] and "parent-before-child" in refused[0][1]
