@@ -7,6 +7,7 @@ against brute force — the harness' SetDOFValues restatement at random values o
 configurations, and on hand-built chains that contain the case the first form of the rule got wrong.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -154,3 +155,51 @@ def test_bad_arguments_are_refused():
     assert lib.cc_debug_motion_classes(ctypes.addressof(arr), nj, 2, 1, aff.ctypes.data_as(ctypes.c_void_p), act.ctypes.data_as(ctypes.c_void_p),
                                        1, 0, bad_pair.ctypes.data_as(ctypes.c_void_p), 1, out.ctypes.data_as(ctypes.c_void_p),
                                        out.ctypes.data_as(ctypes.c_void_p)) != 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/robots"), reason="needs /root/reference")
+def test_soundness_on_every_shipped_robot():
+    """The two flags may only be set when nothing can change (the reference evaluates every pair at every configuration): for
+    every robot file under src/robots and src/collada_robots that loads, with all DOFs active and with a random half of them, no
+    link flagged still moves and no pair flagged invariant changes its relative pose.  (pumabarrett.robot.xml — a hand that no joint
+    ties to its arm — is left out: the query builder refuses that forest before these flags are used.)"""
+    import glob
+    from openrave_b200.environment import Environment
+    files = sorted(glob.glob("/root/reference/src/robots/*") + glob.glob("/root/reference/src/collada_robots/*.zae"))
+    rng = np.random.default_rng(2)
+    bodies = 0
+    for f in files:
+        if not f.endswith((".xml", ".zae")) or f.endswith("pumabarrett.robot.xml"):
+            continue
+        env = Environment()
+        try:
+            env.Load(f)
+        except (NotImplementedError, IOError):
+            continue
+        for b in env.GetBodies():
+            if b.GetDOF() == 0 or len(b.links) < 2 or len(b.links) > 50:
+                continue
+            arr, nj = flatten.joint_table(b, externals=[])
+            aff = flatten.affects_table(b)
+            nl, ndof = len(b.links), b.GetDOF()
+            lo, hi = (np.array(x) for x in b.GetDOFLimits())
+            q0 = np.array(b.GetDOFValues())
+            pairs = [(a, c) for a in range(nl) for c in range(a + 1, nl)]
+            for active in (list(range(ndof)), sorted(rng.choice(ndof, max(1, ndof // 2), replace=False).tolist())):
+                moves, inv = _classes(arr, nj, nl, ndof, aff, active, pairs)
+                poses = []
+                for _ in range(4):
+                    q = q0.copy()
+                    q[active] = lo[active] + rng.random(len(active)) * (hi[active] - lo[active])
+                    b.SetDOFValues(q.tolist())
+                    poses.append(b.GetLinkTransformations())
+                b.SetDOFValues(q0.tolist())
+                for l in range(nl):
+                    if not moves[l]:
+                        assert all(_same(poses[0][l], p[l]) for p in poses[1:]), (f, b.name, l, active)
+                rel = [[rm.t_inv(p[l]) for l in range(nl)] for p in poses]
+                for k, (a, c) in enumerate(pairs):
+                    if inv[k]:
+                        assert all(_same(rm.t_mul(rel[0][a], poses[0][c]), rm.t_mul(rel[i][a], poses[i][c])) for i in range(1, 4)), (f, b.name, a, c, active)
+            bodies += 1
+    assert bodies >= 50
