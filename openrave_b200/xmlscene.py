@@ -93,16 +93,33 @@ class SceneLoader(object):
         if root.tag != "environment":
             raise ValueError("%s: root element is <%s>, expected <environment>" % (path, root.tag))
         pdir = os.path.dirname(path)
+        if "file" in root.attrib:
+            # <Environment file="...">: that scene first, then this element's own bodies (InterfaceXMLReader's file attribute,
+            # xmlreaders-core.cpp:1770-1812; hanoi_complex2.env.xml, pa10grasp2.env.xml)
+            inner = self.find_file(root.attrib["file"], pdir)
+            if inner is None:
+                raise IOError("cannot find %s (from %s)" % (root.attrib["file"], pdir))
+            self.load_environment(env, inner)
         for child in root:
             if child.tag == "robot":
                 body = Robot(env)
                 self.read_robot(child, body, pdir)
                 env.Add(body)
+                self._apply_jointvalues(body)
             elif child.tag == "kinbody":
                 body = KinBody(env)
                 self.read_kinbody(child, body, pdir)
                 env.Add(body)
+                self._apply_jointvalues(body)
         return env
+
+    @staticmethod
+    def _apply_jointvalues(body):
+        """<jointvalues>: SetDOFValues once the body is in the environment, ignored when the count is not the DOF count
+        (xmlreaders-core.cpp:3404-3411, 3418-3425)."""
+        vals = getattr(body, "_xml_jointvalues", None)
+        if vals is not None and len(vals) == body.GetDOF() and vals:
+            body.SetDOFValues(list(vals))
 
     def load_body_file(self, env, filename, robot=False):
         path = self.find_file(filename, None)
@@ -187,6 +204,8 @@ class SceneLoader(object):
                 self._read_manipulator(child, robot)
             elif tag in ("translation", "rotationaxis", "rotationmat", "quat"):
                 trans = self._apply_pose_tag(tag, child.text, trans)
+            elif tag == "jointvalues":
+                robot._xml_jointvalues = _floats(child.text)         # the robot's own tag wins over a nested kinbody's (:2985, 3019)
         if atts.get("name"):
             robot.name = atts["name"]
         if prefix:
@@ -251,6 +270,9 @@ class SceneLoader(object):
         rootoffset, rootj, rootjp = len(body.links), len(body.joints), len(body.passive_joints)
         if "makejoinedlinksadjacent" in atts:
             body.make_joined_links_adjacent = int(atts["makejoinedlinksadjacent"]) != 0
+        skip_before = getattr(self, "_skipgeometry", False)
+        if "skipgeometry" in atts:                       # links without their <geom> children (:2037-2039; jack.kinbody.xml)
+            self._skipgeometry = atts["skipgeometry"].strip().lower() in ("true", "1")
         vtransforms = [l.t for l in body.links]    # `_vTransforms`: original poses for <offsetfrom>
         trans = rm.IDENT_T
         modelsdir = ""
@@ -277,12 +299,15 @@ class SceneLoader(object):
                     body.forced_adjacent.add(_pair(l0.index, l1.index))
             elif tag == "modelsdir":
                 modelsdir = (child.text or "").strip() + "/"
+            elif tag == "jointvalues":
+                body._xml_jointvalues = _floats(child.text)          # applied once the body is in the environment (:2332, 3404-3411)
         if atts.get("name"):
             body.name = atts["name"]
         if prefix:
             self._apply_prefix(body, prefix, rootoffset, rootj, rootjp)
         for l in body.links[roottransoffset:]:
             l.t = rm.t_mul(trans, l.t)
+        self._skipgeometry = skip_before
 
     # ------------------------------------------------------------------ link
     def _read_link(self, elem, body, vtransforms, pdir, modelsdir, scale):
@@ -309,6 +334,8 @@ class SceneLoader(object):
                 if offsetfrom is None:
                     raise ValueError("offsetfrom link %r not found in %s" % (child.text, body.name))
             elif tag in ("geom", "geometry"):
+                if getattr(self, "_skipgeometry", False):
+                    continue
                 g = self._read_geometry(child, pdir, modelsdir, scale)
                 if g is not None:
                     link.geometries.append(g)

@@ -289,3 +289,22 @@ def test_fk_chain_program_of_every_shipped_robot():
                 bodies += 1
     assert bodies >= 85 and worst < 1e-11, (bodies, worst)
     assert [r[0] for r in refused] == ["pumabarrett.robot.xml"] and "parent-before-child" in refused[0][1]
+
+
+def test_environment_file_attribute_jointvalues_and_skipgeometry():
+    """Three reader rules the BASELINE scenes never use: <Environment file=...> loads that scene first (hanoi_complex2, pa10grasp2);
+    <jointvalues> inside a body of a scene is a SetDOFValues after the body was added (xmlreaders-core.cpp:3404-3411);
+    skipgeometry="true" drops the <geom> children (jack.kinbody.xml)."""
+    env = Environment()
+    env.Load(REF + "/data/hanoi_complex2.env.xml")
+    names = [b.name for b in env.GetBodies()]
+    assert "Puma" in names and names[-2:] == ["pole", "pole2"] and len(names) == 11
+    env = Environment()
+    env.Load(REF + "/data/testwamcamera.env.xml")
+    r = env.GetRobots()[0]
+    q = r.GetDOFValues()
+    assert abs(q[3] - 0.8) < 1e-12 and abs(q[10] - min(3.0, r.GetDOFLimits()[1][10])) < 1e-12 and q[0] == 0.0
+    env = Environment()
+    env.Load(REF + "/data/jack.kinbody.xml")
+    b = env.GetBodies()[0]
+    assert len(b.links) == 3 and sum(len(l.idx) for l in b.links) == 0
