@@ -1185,20 +1185,32 @@ int expand_rows_host(const std::vector<cc_joint>& J, int ndof, const double* dof
     // rows are independent: large batches are split over the host cores (a row costs a few hundred ns on one core, the device
     // checks one in 10); the first failing row, in row order, is the one reported
     struct Failure { int64_t row = -1; int joint = -1, err = 0; };
+    // everything that does not depend on the row: the clamped values of the inactive DOFs, which joints read which column, and the
+    // passive joints in the order the loop visits them
+    std::vector<double> full0((size_t)ndof);
+    for (int d = 0; d < ndof; ++d) full0[d] = circ[d] ? dofvals[d] : (dofvals[d] < lo[d] ? lo[d] : dofvals[d] > hi[d] ? hi[d] : dofvals[d]);
+    std::vector<double> jv0((size_t)nj, 0.0);
+    for (int k = 0; k < nj; ++k) if (J[k].dof_index >= 0) jv0[k] = full0[J[k].dof_index];
+    std::vector<std::pair<int, int>> joint_of_col;                 // (joint, column) for joints that carry an active DOF
+    for (int c = 0; c < nactive; ++c)
+        for (int k = 0; k < nj; ++k) if (J[k].dof_index == active[c]) joint_of_col.push_back(std::make_pair(k, c));
+    std::vector<int> passive;
+    for (int k = 0; k < nj; ++k) if (!J[k].is_static && J[k].dof_index < 0) passive.push_back(k);
     auto run = [&](int64_t begin, int64_t end, Failure& f) {
-    std::vector<double> full((size_t)ndof), jv((size_t)nj);
+    std::vector<double> full(full0), jv((size_t)nj);
     for (int64_t i = begin; i < end; ++i) {
         const double* in = q_in + (size_t)i * nin;
         double* out = q_out + (size_t)i * nout;
-        for (int d = 0; d < ndof; ++d) full[d] = dofvals[d];
-        for (int c = 0; c < nactive; ++c) full[active[c]] = in[c];
-        for (int d = 0; d < ndof; ++d)
-            if (!circ[d]) full[d] = full[d] < lo[d] ? lo[d] : full[d] > hi[d] ? hi[d] : full[d];
-        for (int k = 0; k < nj; ++k) jv[k] = J[k].dof_index >= 0 ? full[J[k].dof_index] : 0.0;
+        for (int c = 0; c < nactive; ++c) {
+            const int d = active[c];
+            const double v = in[c];
+            full[d] = circ[d] ? v : (v < lo[d] ? lo[d] : v > hi[d] ? hi[d] : v);
+        }
+        jv = jv0;
+        for (const std::pair<int, int>& kc : joint_of_col) jv[kc.first] = full[active[kc.second]];
         for (int e = 0; e < nexternal; ++e) out[nactive + e] = 0.0;
-        for (int k = 0; k < nj; ++k) {
+        for (int k : passive) {
             const cc_joint& j = J[k];
-            if (j.is_static || j.dof_index >= 0) continue;
             if (j.mimic_dof >= 0) jv[k] = mimic_limit_rule(j.mimic_a * full[j.mimic_dof] + j.mimic_b, j);
             else if (j.mimic_dof == CC_MIMIC_EXTERNAL) {
                 int err = 0;
